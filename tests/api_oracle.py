@@ -1,0 +1,56 @@
+"""`api` namespace over the CPU oracle (see tests/scenarios.py)."""
+
+import os
+
+import oracle
+from oracle import ensembles, host, model_protocol, model_servers, topology, transforms
+
+new_function = oracle.new_function
+V2ModelServer = model_protocol.V2ModelServer
+VotingEnsemble = ensembles.VotingEnsemble
+ParallelRun = ensembles.ParallelRun
+ModelRouter = ensembles.ModelRouter
+MockEvent = host.MockEvent
+MockTrigger = host.MockTrigger
+GraphContext = host.GraphContext
+create_graph_server = host.create_graph_server
+RouterStep = topology.RouterStep
+TaskStep = topology.TaskStep
+MapClass = topology.MapClass
+Imputer = transforms.Imputer
+OneHotEncoder = transforms.OneHotEncoder
+MapValues = transforms.MapValues
+DropFeatures = transforms.DropFeatures
+DateExtractor = transforms.DateExtractor
+SetEventMetadata = transforms.SetEventMetadata
+SKLearnModelServer = model_servers.SKLearnModelServer
+NAME = "oracle"
+
+
+class FeatureRowVotingEnsemble(VotingEnsemble):
+    """router-level preprocess turning a feature dict into a V2 `inputs` row (the idiom of
+    EnrichmentVotingEnsemble.preprocess, serving/routers.py:1335-1342)"""
+
+    def preprocess(self, event):
+        body = event.body
+        if isinstance(body, dict) and "inputs" not in body:
+            event.body = {"inputs": [list(body.values())]}
+        return event
+
+
+class FeatureRowModelServer(SKLearnModelServer):
+    def preprocess(self, request, operation):
+        if isinstance(request, dict) and "inputs" not in request:
+            request = {"inputs": [list(request.values())]}
+        return request
+
+
+def init_from_spec(spec, namespace):
+    """tests/serving/test_serving.py:218-228 (init_ctx): spec via env + nuclio init hook"""
+    import json
+
+    os.environ[host.SERVING_SPEC_ENV] = json.dumps(spec)
+    context = GraphContext()
+    context.is_mock = True
+    host.nuclio_init_hook(context, namespace, "serving_v2")
+    return context
