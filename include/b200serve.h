@@ -1,0 +1,172 @@
+/*
+ * b200serve.h -- C-ABI of the B200 serving-graph engine (libb200serve.so).
+ *
+ * The reference (mlrun/mlrun) has no FFI on this path: its hot path is pure Python.  This header is
+ * the boundary a maintainer binds (ctypes/cffi) to replace the per-event Python step loop with a batched
+ * device plan.  Every entry point names the reference code it replaces (paths relative to the
+ * reference root).  Plain pointers and sizes only; no Python / torch types cross it.
+ *
+ * Conventions
+ *   - every call returns 0 on success or a negative b2s_status; the message is thread-local in
+ *     b2s_last_error();
+ *   - the caller owns host buffers (the library copies on submit); the library owns device memory;
+ *   - a "row" is one event's feature vector: n_in_cols 4-byte words (float32, or int32 where the
+ *     plan says so), rows `row_stride_bytes` apart;
+ *   - outputs are `out_cols` 4-byte words per row (float32 for regression / transform outputs, int32
+ *     for class labels), plus an int32 status word per row (0 = ok) so that the Python layer can turn
+ *     a bad row into that event's 400 response (mlrun/serving/server.py:278-288) without failing the
+ *     whole batch.
+ */
+#ifndef B200SERVE_H
+#define B200SERVE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_VERSION 100 /* 0.1.0 */
+
+typedef enum b2s_status {
+  B2S_OK = 0,
+  B2S_ERR_INVALID = -1,   /* bad argument / plan not finalised / schema mismatch */
+  B2S_ERR_CUDA = -2,      /* a CUDA runtime call failed (message has the CUDA error string) */
+  B2S_ERR_NO_DEVICE = -3, /* no usable GPU: there is NO CPU fallback */
+  B2S_ERR_STATE = -4,     /* call sequence error (not initialised, already finalised ...) */
+  B2S_ERR_TIMEOUT = -5,
+  B2S_ERR_UNSUPPORTED = -6
+} b2s_status;
+
+/* per-row status bits written next to each output row */
+#define B2S_ROW_OK 0
+#define B2S_ROW_NONFINITE_INPUT 1 /* NaN/Inf reached a model input: scikit-learn's predict raises
+                                     ValueError there (called from pkl_model_server.py:58) */
+#define B2S_ROW_BAD_LABEL 2       /* majority vote saw a negative label (serving/routers.py:717-725
+                                     assumes labels 0..max) */
+
+typedef struct b2s_plan_s* b2s_plan_t;
+
+/* output-schema column kinds (b2s_plan_set_output_schema) */
+#define B2S_OUT_COPY 0   /* out = value of source column */
+#define B2S_OUT_ONEHOT 1 /* out = (value == arg) ? 1 : 0 -- OneHotEncoder._encode, feature_store/steps.py:453-471 */
+
+/* model link functions (what the estimator's predict() does after the raw score) */
+#define B2S_LINK_IDENTITY 0   /* regression: out = score[0]                                   */
+#define B2S_LINK_BINARY_GT 1  /* classes[score[0] >  0]  (sklearn LogisticRegression.predict) */
+#define B2S_LINK_BINARY_GE 2  /* classes[score[0] >= 0]  (sklearn GradientBoostingClassifier) */
+#define B2S_LINK_ARGMAX 3     /* classes[argmax_k score[k]], first max wins (np.argmax)       */
+
+/* ensemble vote (VotingEnsemble._apply_logic, serving/routers.py:789-810) */
+#define B2S_VOTE_NONE 0     /* emit every model's prediction: out_cols = n_models                 */
+#define B2S_VOTE_MEAN 1     /* _mean_vote :732-741   -- sum_m w[m] * pred[m]  (fp64)             */
+#define B2S_VOTE_MAJORITY 2 /* _majority_vote :708-730 -- argmax_c sum_m w[m]*[pred[m]==c], first max */
+
+typedef struct b2s_stats {
+  int64_t rows;          /* rows in the batch this call rode in                                  */
+  float h2d_ms;          /* CUDA-event time of the host->device copy                             */
+  float kernel_ms;       /* CUDA-event time of the plan's kernels                                */
+  float d2h_ms;          /* CUDA-event time of the device->host copy                             */
+  float queue_us;        /* submit -> batch sealed (coalescing wait)                             */
+  int32_t kernels;       /* kernel launches in the batch                                         */
+  int32_t nonfinite_rows;/* rows flagged B2S_ROW_NONFINITE_INPUT                                 */
+} b2s_stats;
+
+typedef struct b2s_devinfo {
+  int32_t ordinal, sm_count, cc_major, cc_minor;
+  int64_t total_mem, l2_bytes, smem_per_block_optin;
+  char name[128];
+} b2s_devinfo;
+
+/* ---- library / device ---------------------------------------------------------------------- */
+int b2s_version(void);
+const char* b2s_last_error(void);
+/* Replaces: nothing in the reference (device bring-up).  cfg is "key=value;..." or NULL:
+ *   ring_slots (4), max_batch (65536 rows), max_wait_us (200).  Idempotent per process. */
+int b2s_init(int device_ordinal, const char* cfg);
+int b2s_shutdown(void);
+int b2s_device_info(b2s_devinfo* out);
+/* number of kernels this library has launched since b2s_init (for bench.py's gpu_launches) */
+int64_t b2s_launch_count(void);
+
+/* ---- plan construction ---------------------------------------------------------------------
+ * A plan is the lowered form of a run of recognised graph steps.  It replaces, for those steps, the
+ * reference's per-event loop  FlowStep.run (serving/states.py:1292-1323)  ->  TaskStep.run (:564-599)
+ * -> step handler, and the storey Map chain built by _init_async_objects (:1622-1710). */
+int b2s_plan_create(int32_t n_in_cols, b2s_plan_t* out);
+int b2s_plan_destroy(b2s_plan_t plan);
+
+/* Imputer._impute (feature_store/steps.py:397-406): NaN in column cols[i] -> fills[i]. */
+int b2s_plan_set_impute(b2s_plan_t plan, const int32_t* cols, const float* fills, int32_t n);
+/* MapValues._map_value exact-match branch (steps.py:200-201): v == keys[i] -> vals[i], else unchanged.
+ * Maps are applied after the imputer, in the order they are added. */
+int b2s_plan_add_value_map(b2s_plan_t plan, int32_t col, const float* keys, const float* vals, int32_t n);
+/* MapValues._map_value range branch (steps.py:193-198): first i with lo[i] <= v < hi[i] -> vals[i]. */
+int b2s_plan_add_range_map(b2s_plan_t plan, int32_t col, const float* lo, const float* hi, const float* vals, int32_t n);
+/* Output schema after OneHotEncoder._do_storey (steps.py:473-478) / DropFeatures (:721-729):
+ * out column j reads source column src_col[j] with kind[j] (B2S_OUT_*) and arg[j]. Default: identity. */
+int b2s_plan_set_output_schema(b2s_plan_t plan, const int32_t* src_col, const int32_t* kind, const float* arg, int32_t n_out);
+
+/* Linear scorer = what sklearn's linear estimators compute inside PickleModelServer.predict
+ * (frameworks/_ml_common/pkl_model_server.py:52-60): score[k] = b[k] + sum_j W[k][j] * x_out[j] in fp64.
+ * W is row-major (n_scores x n_out_cols).  classes: label per class index for the classifier links (may be NULL). */
+int b2s_plan_add_linear_model(b2s_plan_t plan, const double* W, const double* b, int32_t n_scores, int32_t link,
+                              const int32_t* classes, int32_t n_classes);
+/* Tree-ensemble scorer (sklearn GradientBoosting* / RandomForest* / DecisionTree* behind the same
+ * predict call).  Trees are concatenated SoA: node i of tree t lives at tree_offset[t] + i.
+ *   feature[i] < 0 marks a leaf whose value is leaf_value[i]; otherwise go left when
+ *   x[feature[i]] <= threshold[i] (sklearn: float32 x vs float64 threshold; thresholds are passed
+ *   already rounded toward -inf to float32, which gives the identical decision).
+ *   score[tree_slot[t]] += tree_scale[t] * leaf_value;  score[k] starts at init[k]. */
+int b2s_plan_add_tree_model(b2s_plan_t plan, int32_t n_trees, const int32_t* tree_offset /* n_trees+1 */,
+                            const int32_t* feature, const float* threshold, const int32_t* left,
+                            const int32_t* right, const double* leaf_value, const int32_t* tree_slot,
+                            const double* tree_scale, const double* init, int32_t n_scores, int32_t link,
+                            const int32_t* classes, int32_t n_classes);
+/* VotingEnsemble reduce over the plan's models (weights in model order; fp64). */
+int b2s_plan_set_vote(b2s_plan_t plan, int32_t vote_kind, const double* weights, int32_t n_weights);
+/* Upload tables to HBM, pick kernels, size staging buffers.  After this the plan is immutable. */
+int b2s_plan_finalize(b2s_plan_t plan);
+/* out_cols 4-byte words per output row; out_is_int != 0 when they are int32 labels */
+int b2s_plan_out_info(b2s_plan_t plan, int32_t* out_cols, int32_t* out_is_int);
+
+/* ---- execution -------------------------------------------------------------------------------
+ * Replaces GraphServer.run -> graph.run (serving/server.py:252-293) for a batch of events. */
+
+/* Device-resident path: rows and outputs already in HBM (roofline runs, CUDA-graph capture, callers that
+ * keep tensors on the GPU).  Asynchronous on `stream` (a cudaStream_t, NULL = the library's stream).
+ * d_status may be NULL. */
+int b2s_run_device(b2s_plan_t plan, const void* d_rows, int64_t n_rows, int64_t row_stride_bytes, void* d_out,
+                   int32_t* d_status, void* stream);
+/* Synchronous host call: pinned staging -> H2D -> kernels -> D2H -> out.  row_status / stats may be NULL. */
+int b2s_run_host(b2s_plan_t plan, const void* rows, int64_t n_rows, int64_t row_stride_bytes, void* out,
+                 int64_t out_bytes, int32_t* row_status, b2s_stats* stats);
+/* Coalescing path (thread-safe, many producers): rows are copied into a pinned ring slot; a dispatcher
+ * thread seals a batch when it holds max_batch rows or the oldest row waited max_wait_us, and runs
+ * H2D -> kernels -> D2H on its own streams.  b2s_wait blocks until the ticket's batch completed and copies
+ * that ticket's rows out.  This is the replacement of storey's SyncEmitSource.emit / await_result hand-off
+ * (serving/states.py:1283-1287). */
+int b2s_submit(b2s_plan_t plan, const void* rows, int64_t n_rows, int64_t row_stride_bytes, uint64_t* ticket);
+int b2s_wait(b2s_plan_t plan, uint64_t ticket, void* out, int64_t out_bytes, int32_t* row_status, b2s_stats* stats);
+/* force the open batch out now (drain callback, serving/server.py:353-384) */
+int b2s_flush(b2s_plan_t plan);
+
+/* pinned host memory for zero-extra-copy submits and for bench.py's e2e leg */
+void* b2s_alloc_pinned(size_t bytes);
+int b2s_free_pinned(void* p);
+/* plain device memory helpers so that ctypes callers need no other CUDA binding */
+void* b2s_device_alloc(size_t bytes);
+int b2s_device_free(void* p);
+int b2s_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes);
+int b2s_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes);
+int b2s_device_sync(void);
+/* time n_iters back-to-back b2s_run_device launches with CUDA events on the library stream (ms total);
+ * used by bench.py so that the timed region contains only the plan's kernels.  d_rows[i % n_bufs]. */
+int b2s_time_device(b2s_plan_t plan, const void* const* d_rows, int32_t n_bufs, int64_t n_rows,
+                    int64_t row_stride_bytes, void* d_out, int32_t n_iters, float* total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SERVE_H */

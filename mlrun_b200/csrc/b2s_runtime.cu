@@ -1,0 +1,1009 @@
+// b2s_runtime.cu -- host runtime behind include/b200serve.h: plan lowering, device tables, launch
+// configuration, pinned ring + dispatcher thread (event coalescing), CUDA-event timing.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <limits>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/b200serve.h"
+#include "b2s_device.cuh"
+
+using namespace b2s;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return fail(B2S_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ globals
+struct Global {
+  bool inited = false;
+  int device = 0;
+  cudaDeviceProp prop{};
+  cudaStream_t stream = nullptr;  // library stream for run_device/run_host/time_device
+  int ring_slots = 4;
+  int64_t max_batch = 65536;
+  int64_t max_wait_us = 200;
+  std::atomic<int64_t> launches{0};
+  std::mutex mu;
+};
+static Global G;
+
+static int64_t cfg_get(const std::string& cfg, const char* key, int64_t dflt) {
+  size_t pos = cfg.find(std::string(key) + "=");
+  if (pos == std::string::npos) return dflt;
+  return atoll(cfg.c_str() + pos + strlen(key) + 1);
+}
+
+// ------------------------------------------------------------------------------------------ plan
+struct HostModel {
+  int kind = MK_LINEAR;
+  int n_scores = 1, link = 0;
+  std::vector<int32_t> classes;
+  // linear
+  std::vector<double> W, b;
+  // trees
+  std::vector<int32_t> tree_offset, feature, left, right, tree_slot;
+  std::vector<float> threshold;
+  std::vector<double> leaf_value, tree_scale, init;
+};
+
+struct Slot {  // one in-flight batch of the coalescing ring
+  char* h_in = nullptr;
+  char* h_out = nullptr;     // out words then status words
+  char* d_in = nullptr;
+  char* d_out = nullptr;
+  int32_t* d_status = nullptr;
+  int64_t rows = 0;
+  uint64_t batch_id = 0;
+  int state = 0;  // 0 free/open, 1 sealed (queued for the dispatcher), 2 in flight, 3 done
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+  std::chrono::steady_clock::time_point first_submit;
+  b2s_stats stats{};
+  int waiters = 0;      // tickets issued on this batch not yet collected
+};
+
+struct b2s_plan_s {
+  int32_t n_in = 0;
+  bool finalized = false;
+  // builder state
+  std::vector<float> fill;
+  std::vector<std::vector<MapEntry>> maps;  // per column
+  std::vector<int32_t> out_src, out_kind;
+  std::vector<float> out_arg;
+  std::vector<HostModel> models;
+  int vote_kind = B2S_VOTE_NONE;
+  std::vector<double> vote_w;
+  // lowered
+  int mode = MODE_STORE;
+  int NS = 1;
+  int out_cols = 0;
+  int out_is_int = 0;
+  KParams kp{};
+  char* d_blob = nullptr;
+  size_t blob_bytes = 0;
+  int grid = 0, block = 0;
+  int kernels_per_batch = 1;
+  // host staging for run_host
+  char* h_stage_in = nullptr;
+  char* h_stage_out = nullptr;
+  char* d_stage_in = nullptr;
+  char* d_stage_out = nullptr;
+  int32_t* d_stage_status = nullptr;
+  int64_t stage_rows = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::mutex host_mu;
+  // coalescing ring
+  std::vector<Slot> slots;
+  int open_slot = -1;
+  uint64_t next_batch = 1;
+  std::map<uint64_t, int> batch_slot;  // live batches -> slot index
+  std::deque<int> sealed;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done, cv_free;
+  std::thread dispatcher;
+  bool stop = false;
+  cudaStream_t ring_stream = nullptr;
+  int64_t ring_cap = 0;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct BlobBuilder {
+  std::vector<char> data;
+  template <typename T>
+  size_t add(const std::vector<T>& v) {
+    size_t off = align_up(data.size(), 16);
+    data.resize(off + std::max<size_t>(v.size() * sizeof(T), 16));
+    if (!v.empty()) memcpy(data.data() + off, v.data(), v.size() * sizeof(T));
+    return off;
+  }
+};
+
+template <int MODE, int NS>
+static cudaError_t launch_rows(const KParams& kp, int grid, int block, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(rows_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)G.prop.sharedMemPerBlockOptin);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  rows_kernel<MODE, NS><<<grid, block, kp.sm_total, st>>>(kp);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_plan(b2s_plan_s* p, const KParams& kp, int grid, cudaStream_t st) {
+  G.launches.fetch_add(1, std::memory_order_relaxed);
+#define B2S_CASE(M, N) \
+  if (p->mode == M && p->NS == N) return launch_rows<M, N>(kp, grid, p->block, st);
+  B2S_CASE(MODE_LINEAR, 1) B2S_CASE(MODE_LINEAR, 2) B2S_CASE(MODE_LINEAR, 4) B2S_CASE(MODE_LINEAR, 8)
+  B2S_CASE(MODE_LINEAR, 16) B2S_CASE(MODE_LINEAR, 32)
+  B2S_CASE(MODE_TREES, 1) B2S_CASE(MODE_TREES, 4) B2S_CASE(MODE_TREES, 8) B2S_CASE(MODE_TREES, 16)
+  B2S_CASE(MODE_STORE, 1)
+#undef B2S_CASE
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------ C-ABI: library
+extern "C" int b2s_version(void) { return B2S_VERSION; }
+extern "C" const char* b2s_last_error(void) { return g_err.c_str(); }
+
+extern "C" int b2s_init(int device_ordinal, const char* cfg) {
+  std::lock_guard<std::mutex> lk(G.mu);
+  if (G.inited) return B2S_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(B2S_ERR_NO_DEVICE, "no CUDA device (%s); this engine has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device_ordinal < 0 || device_ordinal >= n) return fail(B2S_ERR_INVALID, "device ordinal %d out of range", device_ordinal);
+  CUDA_TRY(cudaSetDevice(device_ordinal));
+  CUDA_TRY(cudaGetDeviceProperties(&G.prop, device_ordinal));
+  CUDA_TRY(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  G.device = device_ordinal;
+  std::string c = cfg ? cfg : "";
+  G.ring_slots = (int)cfg_get(c, "ring_slots", 4);
+  G.max_batch = cfg_get(c, "max_batch", 65536);
+  G.max_wait_us = cfg_get(c, "max_wait_us", 200);
+  if (G.ring_slots < 2) G.ring_slots = 2;
+  G.inited = true;
+  return B2S_OK;
+}
+
+extern "C" int b2s_shutdown(void) {
+  std::lock_guard<std::mutex> lk(G.mu);
+  if (!G.inited) return B2S_OK;
+  cudaStreamDestroy(G.stream);
+  G.stream = nullptr;
+  G.inited = false;
+  return B2S_OK;
+}
+
+extern "C" int b2s_device_info(b2s_devinfo* out) {
+  if (!G.inited) return fail(B2S_ERR_STATE, "b2s_init was not called");
+  if (!out) return fail(B2S_ERR_INVALID, "null out");
+  memset(out, 0, sizeof(*out));
+  out->ordinal = G.device;
+  out->sm_count = G.prop.multiProcessorCount;
+  out->cc_major = G.prop.major;
+  out->cc_minor = G.prop.minor;
+  out->total_mem = (int64_t)G.prop.totalGlobalMem;
+  out->l2_bytes = G.prop.l2CacheSize;
+  out->smem_per_block_optin = (int64_t)G.prop.sharedMemPerBlockOptin;
+  strncpy(out->name, G.prop.name, sizeof(out->name) - 1);
+  return B2S_OK;
+}
+
+extern "C" int64_t b2s_launch_count(void) { return G.launches.load(); }
+
+// ------------------------------------------------------------------------------------------ C-ABI: plan building
+extern "C" int b2s_plan_create(int32_t n_in_cols, b2s_plan_t* out) {
+  if (!out || n_in_cols <= 0 || n_in_cols > 65536) return fail(B2S_ERR_INVALID, "bad n_in_cols %d", n_in_cols);
+  auto* p = new b2s_plan_s();
+  p->n_in = n_in_cols;
+  p->fill.assign(n_in_cols, std::numeric_limits<float>::quiet_NaN());
+  p->maps.resize(n_in_cols);
+  *out = p;
+  return B2S_OK;
+}
+
+static int check_build(b2s_plan_t p) {
+  if (!p) return fail(B2S_ERR_INVALID, "null plan");
+  if (p->finalized) return fail(B2S_ERR_STATE, "plan already finalized");
+  return B2S_OK;
+}
+
+extern "C" int b2s_plan_set_impute(b2s_plan_t p, const int32_t* cols, const float* fills, int32_t n) {
+  if (int rc = check_build(p)) return rc;
+  for (int i = 0; i < n; ++i) {
+    if (cols[i] < 0 || cols[i] >= p->n_in) return fail(B2S_ERR_INVALID, "impute column %d out of range", cols[i]);
+    p->fill[cols[i]] = fills[i];
+  }
+  return B2S_OK;
+}
+
+extern "C" int b2s_plan_add_value_map(b2s_plan_t p, int32_t col, const float* keys, const float* vals, int32_t n) {
+  if (int rc = check_build(p)) return rc;
+  if (col < 0 || col >= p->n_in) return fail(B2S_ERR_INVALID, "map column %d out of range", col);
+  for (int i = 0; i < n; ++i) p->maps[col].push_back(MapEntry{keys[i], 0.f, vals[i], (i == 0 ? 256 : 0) | 0});
+  return B2S_OK;
+}
+
+extern "C" int b2s_plan_add_range_map(b2s_plan_t p, int32_t col, const float* lo, const float* hi, const float* vals, int32_t n) {
+  if (int rc = check_build(p)) return rc;
+  if (col < 0 || col >= p->n_in) return fail(B2S_ERR_INVALID, "map column %d out of range", col);
+  for (int i = 0; i < n; ++i) p->maps[col].push_back(MapEntry{lo[i], hi[i], vals[i], (i == 0 ? 256 : 0) | 1});
+  return B2S_OK;
+}
+
+extern "C" int b2s_plan_set_output_schema(b2s_plan_t p, const int32_t* src_col, const int32_t* kind, const float* arg, int32_t n_out) {
+  if (int rc = check_build(p)) return rc;
+  if (n_out <= 0) return fail(B2S_ERR_INVALID, "empty output schema");
+  if (!p->models.empty()) return fail(B2S_ERR_STATE, "set the output schema before adding models");
+  p->out_src.assign(src_col, src_col + n_out);
+  p->out_kind.assign(kind, kind + n_out);
+  p->out_arg.assign(arg, arg + n_out);
+  for (int j = 0; j < n_out; ++j) {
+    if (src_col[j] < 0 || src_col[j] >= p->n_in) return fail(B2S_ERR_INVALID, "schema source column %d out of range", src_col[j]);
+    if (kind[j] != B2S_OUT_COPY && kind[j] != B2S_OUT_ONEHOT) return fail(B2S_ERR_INVALID, "schema kind %d unknown", kind[j]);
+  }
+  return B2S_OK;
+}
+
+static int n_out_of(b2s_plan_t p) { return p->out_src.empty() ? p->n_in : (int)p->out_src.size(); }
+
+static int check_link(int link, int n_scores, int n_classes) {
+  if (link < 0 || link > 3) return fail(B2S_ERR_INVALID, "unknown link %d", link);
+  if (n_scores < 1 || n_scores > kMaxScores) return fail(B2S_ERR_UNSUPPORTED, "n_scores %d not in [1,%d]", n_scores, kMaxScores);
+  if ((link == B2S_LINK_BINARY_GT || link == B2S_LINK_BINARY_GE) && n_classes != 0 && n_classes != 2)
+    return fail(B2S_ERR_INVALID, "binary link needs 2 classes");
+  if (link == B2S_LINK_ARGMAX && n_classes != 0 && n_classes != n_scores) return fail(B2S_ERR_INVALID, "argmax link needs n_scores classes");
+  return B2S_OK;
+}
+
+extern "C" int b2s_plan_add_linear_model(b2s_plan_t p, const double* W, const double* b, int32_t n_scores, int32_t link,
+                                         const int32_t* classes, int32_t n_classes) {
+  if (int rc = check_build(p)) return rc;
+  if (int rc = check_link(link, n_scores, classes ? n_classes : 0)) return rc;
+  if ((int)p->models.size() >= kMaxModels) return fail(B2S_ERR_UNSUPPORTED, "more than %d models in one plan", kMaxModels);
+  HostModel m;
+  m.kind = MK_LINEAR;
+  m.n_scores = n_scores;
+  m.link = link;
+  const int no = n_out_of(p);
+  m.W.assign(W, W + (size_t)n_scores * no);
+  m.b.assign(b, b + n_scores);
+  if (classes) m.classes.assign(classes, classes + n_classes);
+  p->models.push_back(std::move(m));
+  return B2S_OK;
+}
+
+extern "C" int b2s_plan_add_tree_model(b2s_plan_t p, int32_t n_trees, const int32_t* tree_offset, const int32_t* feature,
+                                       const float* threshold, const int32_t* left, const int32_t* right,
+                                       const double* leaf_value, const int32_t* tree_slot, const double* tree_scale,
+                                       const double* init, int32_t n_scores, int32_t link, const int32_t* classes,
+                                       int32_t n_classes) {
+  if (int rc = check_build(p)) return rc;
+  if (int rc = check_link(link, n_scores, classes ? n_classes : 0)) return rc;
+  if (n_scores > 16) return fail(B2S_ERR_UNSUPPORTED, "tree models support at most 16 scores");
+  if ((int)p->models.size() >= kMaxModels) return fail(B2S_ERR_UNSUPPORTED, "more than %d models in one plan", kMaxModels);
+  if (n_trees < 1) return fail(B2S_ERR_INVALID, "n_trees < 1");
+  HostModel m;
+  m.kind = MK_TREES;
+  m.n_scores = n_scores;
+  m.link = link;
+  const int nn = tree_offset[n_trees];
+  const int no = n_out_of(p);
+  m.tree_offset.assign(tree_offset, tree_offset + n_trees + 1);
+  m.feature.assign(feature, feature + nn);
+  m.threshold.assign(threshold, threshold + nn);
+  m.left.assign(left, left + nn);
+  m.right.assign(right, right + nn);
+  m.leaf_value.assign(leaf_value, leaf_value + nn);
+  m.tree_slot.assign(tree_slot, tree_slot + n_trees);
+  m.tree_scale.assign(tree_scale, tree_scale + n_trees);
+  m.init.assign(init, init + n_scores);
+  if (classes) m.classes.assign(classes, classes + n_classes);
+  for (int t = 0; t < n_trees; ++t) {
+    if (tree_slot[t] < 0 || tree_slot[t] >= n_scores) return fail(B2S_ERR_INVALID, "tree %d slot out of range", t);
+    const int lo = tree_offset[t], hi = tree_offset[t + 1];
+    if (hi <= lo) return fail(B2S_ERR_INVALID, "tree %d is empty", t);
+    for (int i = lo; i < hi; ++i) {
+      if (feature[i] >= no) return fail(B2S_ERR_INVALID, "tree %d node %d feature %d >= n_out %d", t, i - lo, feature[i], no);
+      if (feature[i] >= 0) {
+        // children are tree-relative and must point forward (no cycles => the walk terminates)
+        if (left[i] <= i - lo || right[i] <= i - lo || left[i] >= hi - lo || right[i] >= hi - lo)
+          return fail(B2S_ERR_INVALID, "tree %d node %d has bad children", t, i - lo);
+      }
+    }
+  }
+  p->models.push_back(std::move(m));
+  return B2S_OK;
+}
+
+extern "C" int b2s_plan_set_vote(b2s_plan_t p, int32_t vote_kind, const double* weights, int32_t n_weights) {
+  if (int rc = check_build(p)) return rc;
+  if (vote_kind < 0 || vote_kind > 2) return fail(B2S_ERR_INVALID, "unknown vote kind %d", vote_kind);
+  p->vote_kind = vote_kind;
+  p->vote_w.assign(weights, weights + (weights ? n_weights : 0));
+  return B2S_OK;
+}
+
+// ------------------------------------------------------------------------------------------ finalize
+static int pow2_at_least(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+extern "C" int b2s_plan_finalize(b2s_plan_t p) {
+  if (int rc = check_build(p)) return rc;
+  if (!G.inited) return fail(B2S_ERR_STATE, "b2s_init was not called");
+  const int n_in = p->n_in;
+  const bool identity_schema = p->out_src.empty();
+  if (identity_schema) {
+    p->out_src.resize(n_in);
+    p->out_kind.assign(n_in, B2S_OUT_COPY);
+    p->out_arg.assign(n_in, 0.f);
+    for (int j = 0; j < n_in; ++j) p->out_src[j] = j;
+  }
+  const int n_out = (int)p->out_src.size();
+  const int M = (int)p->models.size();
+  if (p->vote_kind != B2S_VOTE_NONE) {
+    if (M == 0) return fail(B2S_ERR_INVALID, "vote without models");
+    if ((int)p->vote_w.size() != M) return fail(B2S_ERR_INVALID, "vote weights (%d) != models (%d)", (int)p->vote_w.size(), M);
+  }
+  bool any_tree = false, any_class = false, any_reg = false;
+  int total_scores = 0, max_scores = 1;
+  for (auto& m : p->models) {
+    any_tree |= (m.kind == MK_TREES);
+    (m.link == B2S_LINK_IDENTITY ? any_reg : any_class) = true;
+    total_scores += m.n_scores;
+    max_scores = std::max(max_scores, m.n_scores);
+  }
+  if (any_class && any_reg) return fail(B2S_ERR_UNSUPPORTED, "classifiers and regressors cannot share one plan output");
+  if (p->vote_kind == B2S_VOTE_MAJORITY && !any_class && M) {
+    // regression outputs voted as labels: allowed (VotingEnsemble casts to int, routers.py:778-780)
+  }
+  p->mode = M == 0 ? MODE_STORE : (any_tree ? MODE_TREES : MODE_LINEAR);
+  p->out_is_int = (M > 0 && (any_class || p->vote_kind == B2S_VOTE_MAJORITY)) ? 1 : 0;
+  if (p->vote_kind == B2S_VOTE_MEAN) p->out_is_int = 0;
+  p->out_cols = M == 0 ? n_out : (p->vote_kind == B2S_VOTE_NONE ? M : 1);
+
+  bool any_fill = false, any_map = false;
+  for (int c = 0; c < n_in; ++c) {
+    any_fill |= !std::isnan(p->fill[c]);
+    any_map |= !p->maps[c].empty();
+  }
+  const bool need_expand = !identity_schema || any_fill || any_map;
+
+  // ---- tables
+  std::vector<uint32_t> flags(n_in, 0);
+  std::vector<int32_t> map_off(n_in + 1, 0);
+  std::vector<MapEntry> maps;
+  for (int c = 0; c < n_in; ++c) {
+    map_off[c] = (int)maps.size();
+    for (auto& e : p->maps[c]) maps.push_back(e);
+    if (!p->maps[c].empty()) flags[c] |= COL_HAS_MAP;
+  }
+  map_off[n_in] = (int)maps.size();
+  for (int j = 0; j < n_out; ++j)
+    if (p->out_kind[j] == B2S_OUT_COPY) flags[p->out_src[j]] |= COL_COPIED;
+
+  int NS = 1;
+  std::vector<int32_t> cat_off(n_in + 1, 0);
+  std::vector<float> cat_val;
+  std::vector<double> wnum, wcat, bias, wgen, leaf, tree_scale;
+  std::vector<ModelDesc> descs(std::max(M, 1));
+  std::vector<int32_t> classes, tree_root, tree_slot;
+  std::vector<TreeNode> nodes;
+
+  if (p->mode == MODE_LINEAR) {
+    NS = pow2_at_least(total_scores);
+    if (NS > kMaxScores) return fail(B2S_ERR_UNSUPPORTED, "total scores %d > %d", total_scores, kMaxScores);
+    // categories per input column, in schema order
+    std::vector<std::vector<int>> col_cats(n_in);
+    for (int j = 0; j < n_out; ++j)
+      if (p->out_kind[j] == B2S_OUT_ONEHOT) col_cats[p->out_src[j]].push_back(j);
+    for (int c = 0; c < n_in; ++c) {
+      cat_off[c] = (int)cat_val.size();
+      for (int j : col_cats[c]) cat_val.push_back(p->out_arg[j]);
+      if (!col_cats[c].empty()) flags[c] |= COL_HAS_CAT;
+    }
+    cat_off[n_in] = (int)cat_val.size();
+    wnum.assign((size_t)n_in * NS, 0.0);
+    wcat.assign(std::max<size_t>(cat_val.size(), 1) * NS, 0.0);
+    bias.assign(NS, 0.0);
+    int so = 0;
+    for (int mi = 0; mi < M; ++mi) {
+      auto& m = p->models[mi];
+      for (int k = 0; k < m.n_scores; ++k) {
+        bias[so + k] = m.b[k];
+        std::vector<int> seen(n_in, 0);
+        for (int j = 0; j < n_out; ++j) {
+          const int c = p->out_src[j];
+          const double w = m.W[(size_t)k * n_out + j];
+          if (p->out_kind[j] == B2S_OUT_COPY) {
+            wnum[(size_t)c * NS + so + k] += w;
+          } else {
+            const int idx = cat_off[c] + seen[c]++;
+            wcat[(size_t)idx * NS + so + k] = w;
+          }
+        }
+      }
+      so += m.n_scores;
+    }
+  } else if (p->mode == MODE_TREES) {
+    NS = max_scores <= 1 ? 1 : (max_scores <= 4 ? 4 : (max_scores <= 8 ? 8 : 16));
+    bias.assign(std::max(total_scores, 1), 0.0);
+  }
+  {
+    int so = 0, co = 0;
+    for (int mi = 0; mi < M; ++mi) {
+      auto& m = p->models[mi];
+      ModelDesc d{};
+      d.kind = m.kind;
+      d.score_off = so;
+      d.n_scores = m.n_scores;
+      d.link = m.link;
+      d.class_off = co;
+      d.n_classes = (int)m.classes.size();
+      for (int32_t c : m.classes) classes.push_back(c);
+      co += (int)m.classes.size();
+      if (p->mode == MODE_TREES) {
+        if (m.kind == MK_TREES) {
+          d.tree_begin = (int)tree_root.size();
+          const int nt = (int)m.tree_slot.size();
+          for (int t = 0; t < nt; ++t) {
+            const int base = (int)nodes.size();
+            tree_root.push_back(base);
+            tree_slot.push_back(m.tree_slot[t]);
+            tree_scale.push_back(m.tree_scale[t]);
+            for (int i = m.tree_offset[t]; i < m.tree_offset[t + 1]; ++i) {
+              TreeNode nd;
+              nd.feature = m.feature[i];
+              nd.threshold = m.threshold[i];
+              nd.left = nd.feature >= 0 ? base + m.left[i] : 0;
+              nd.right = nd.feature >= 0 ? base + m.right[i] : 0;
+              nodes.push_back(nd);
+              leaf.push_back(m.leaf_value[i]);
+            }
+          }
+          d.tree_end = (int)tree_root.size();
+          for (int k = 0; k < m.n_scores; ++k) bias[so + k] = m.init[k];
+        } else {
+          d.w_off = (int)wgen.size();
+          for (double w : m.W) wgen.push_back(w);
+          for (int k = 0; k < m.n_scores; ++k) bias[so + k] = m.b[k];
+        }
+      }
+      descs[mi] = d;
+      so += m.n_scores;
+    }
+  }
+  if (bias.empty()) bias.assign(1, 0.0);
+
+  // ---- upload one blob
+  BlobBuilder bb;
+  const size_t o_fill = bb.add(p->fill), o_flags = bb.add(flags), o_mapoff = bb.add(map_off), o_maps = bb.add(maps),
+               o_osrc = bb.add(p->out_src), o_okind = bb.add(p->out_kind), o_oarg = bb.add(p->out_arg),
+               o_catoff = bb.add(cat_off), o_catval = bb.add(cat_val), o_wnum = bb.add(wnum), o_wcat = bb.add(wcat),
+               o_bias = bb.add(bias), o_models = bb.add(descs), o_classes = bb.add(classes),
+               o_votew = bb.add(p->vote_w), o_wgen = bb.add(wgen), o_nodes = bb.add(nodes), o_leaf = bb.add(leaf),
+               o_troot = bb.add(tree_root), o_tslot = bb.add(tree_slot), o_tscale = bb.add(tree_scale);
+  CUDA_TRY(cudaSetDevice(G.device));
+  CUDA_TRY(cudaMalloc(&p->d_blob, bb.data.size()));
+  CUDA_TRY(cudaMemcpy(p->d_blob, bb.data.data(), bb.data.size(), cudaMemcpyHostToDevice));
+  p->blob_bytes = bb.data.size();
+  char* B = p->d_blob;
+
+  KParams& k = p->kp;
+  memset(&k, 0, sizeof(k));
+  k.n_in = n_in;
+  k.n_out = n_out;
+  k.out_cols = p->out_cols;
+  k.n_models = M;
+  k.n_scores = total_scores;
+  k.vote_kind = p->vote_kind;
+  k.out_is_int = p->out_is_int;
+  k.need_expand = need_expand ? 1 : 0;
+  k.models_pow2 = pow2_at_least(std::max(M, 1));
+  k.n_cat = (int)cat_val.size();
+  k.n_maps = (int)maps.size();
+  k.fill = (const float*)(B + o_fill);
+  k.col_flags = (const uint32_t*)(B + o_flags);
+  k.map_off = (const int32_t*)(B + o_mapoff);
+  k.maps = (const MapEntry*)(B + o_maps);
+  k.out_src = (const int32_t*)(B + o_osrc);
+  k.out_kind = (const int32_t*)(B + o_okind);
+  k.out_arg = (const float*)(B + o_oarg);
+  k.cat_off = (const int32_t*)(B + o_catoff);
+  k.cat_val = (const float*)(B + o_catval);
+  k.wnum = (const double*)(B + o_wnum);
+  k.wcat = (const double*)(B + o_wcat);
+  k.bias = (const double*)(B + o_bias);
+  k.models = (const ModelDesc*)(B + o_models);
+  k.classes = (const int32_t*)(B + o_classes);
+  k.vote_w = (const double*)(B + o_votew);
+  k.wgen = (const double*)(B + o_wgen);
+  k.nodes = (const TreeNode*)(B + o_nodes);
+  k.leaf = (const double*)(B + o_leaf);
+  k.tree_root = (const int32_t*)(B + o_troot);
+  k.tree_slot = (const int32_t*)(B + o_tslot);
+  k.tree_scale = (const double*)(B + o_tscale);
+
+  // ---- launch geometry + shared-memory carve-up
+  // pitch (words): rows 16B aligned and (pitch/4) odd -> conflict-free LDS.128 for one-thread-per-row
+  const int n_in4 = (int)align_up(n_in, 4);
+  int pitch = n_in4 + 4;
+  if (((pitch / 4) & 1) == 0) pitch += 4;
+  int exp_pitch = n_out | 1;
+  const int smem_cap = (int)G.prop.sharedMemPerBlockOptin;
+  const int sms = G.prop.multiProcessorCount;
+  int block, tile_rows, stages, blocks_per_sm;
+  if (p->mode == MODE_LINEAR) {
+    block = 128;
+    tile_rows = block;
+    stages = 3;
+    blocks_per_sm = 2;
+  } else if (p->mode == MODE_TREES) {
+    block = 256;
+    tile_rows = block / k.models_pow2;
+    stages = 2;
+    blocks_per_sm = 2;
+  } else {
+    block = 256;
+    tile_rows = 128;
+    stages = 2;
+    blocks_per_sm = 2;
+  }
+  auto carve = [&](int tr, int st) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+      size_t o = align_up(off, 16);
+      off = o + bytes;
+      return (int32_t)o;
+    };
+    k.sm_fill = take((size_t)n_in * 4);
+    k.sm_flags = take((size_t)n_in * 4);
+    k.sm_mapoff = take((size_t)(n_in + 1) * 4);
+    k.sm_catoff = take((size_t)(n_in + 1) * 4);
+    k.sm_catval = take(std::max<size_t>(cat_val.size(), 1) * 4);
+    k.sm_wnum = take(p->mode == MODE_LINEAR ? (size_t)n_in * NS * 8 : 16);
+    k.sm_wcat = take(p->mode == MODE_LINEAR ? std::max<size_t>(cat_val.size(), 1) * NS * 8 : 16);
+    k.sm_outsrc = take((size_t)n_out * 4);
+    k.sm_outkind = take((size_t)n_out * 4);
+    k.sm_outarg = take((size_t)n_out * 4);
+    k.sm_pred = take(p->mode == MODE_TREES ? (size_t)tr * k.models_pow2 * 8 : 16);
+    k.sm_exp = take((p->mode != MODE_LINEAR && need_expand) ? (size_t)tr * exp_pitch * 4 : 16);
+    k.sm_tiles = take((size_t)st * tr * pitch * 4);
+    return (int)align_up(off, 16);
+  };
+  int total = carve(tile_rows, stages);
+  // shrink until `blocks_per_sm` blocks fit (then until one fits)
+  while (total * blocks_per_sm > smem_cap * 1 && (stages > 2 || blocks_per_sm > 1)) {
+    if (stages > 2) --stages; else --blocks_per_sm;
+    total = carve(tile_rows, stages);
+  }
+  while (total > smem_cap && stages > 1) total = carve(tile_rows, --stages);
+  while (total > smem_cap && tile_rows > 8 && p->mode != MODE_LINEAR) {
+    tile_rows /= 2;
+    total = carve(tile_rows, stages);
+  }
+  if (total > smem_cap) {
+    if (p->mode == MODE_LINEAR) {
+      // wide rows: fewer rows per tile (threads beyond tile_rows idle in the compute phase)
+      while (total > smem_cap && tile_rows > 8) {
+        tile_rows /= 2;
+        total = carve(tile_rows, stages);
+      }
+    }
+    if (total > smem_cap) return fail(B2S_ERR_UNSUPPORTED, "plan needs %d B shared memory > %d B", total, smem_cap);
+  }
+  if (p->mode == MODE_TREES) block = std::max(32, tile_rows * k.models_pow2);
+  k.sm_total = total;
+  k.tile_rows = tile_rows;
+  k.pitch = pitch;
+  k.exp_pitch = exp_pitch;
+  k.stages = stages;
+  p->NS = NS;
+  p->block = block;
+  int occ = std::max(1, std::min(blocks_per_sm, smem_cap / std::max(total, 1)));
+  p->grid = sms * occ;
+
+  for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&p->ev[i]));
+  p->finalized = true;
+  return B2S_OK;
+}
+
+extern "C" int b2s_plan_out_info(b2s_plan_t p, int32_t* out_cols, int32_t* out_is_int) {
+  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+  if (out_cols) *out_cols = p->out_cols;
+  if (out_is_int) *out_is_int = p->out_is_int;
+  return B2S_OK;
+}
+
+// ------------------------------------------------------------------------------------------ execution
+static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t stride, void* d_out, int32_t* d_status,
+                     cudaStream_t st) {
+  if (n_rows == 0) return B2S_OK;
+  KParams k = p->kp;
+  k.rows = (const char*)d_rows;
+  k.row_stride = stride;
+  k.n_rows = n_rows;
+  k.out = (float*)d_out;
+  k.status = d_status;
+  k.vec_ok = ((p->n_in % 4) == 0 && (stride % 16) == 0 && ((uintptr_t)d_rows % 16) == 0) ? 1 : 0;
+  const int64_t tiles = (n_rows + k.tile_rows - 1) / k.tile_rows;
+  const int grid = (int)std::min<int64_t>(p->grid, tiles);
+  cudaError_t e = launch_plan(p, k, grid, st);
+  if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return B2S_OK;
+}
+
+extern "C" int b2s_run_device(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t row_stride_bytes, void* d_out,
+                              int32_t* d_status, void* stream) {
+  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+  if (n_rows < 0 || row_stride_bytes < (int64_t)p->n_in * 4) return fail(B2S_ERR_INVALID, "bad n_rows/stride");
+  return launch_on(p, d_rows, n_rows, row_stride_bytes, d_out, d_status, stream ? (cudaStream_t)stream : G.stream);
+}
+
+static int ensure_stage(b2s_plan_t p, int64_t n_rows) {
+  if (n_rows <= p->stage_rows) return B2S_OK;
+  if (p->h_stage_in) {
+    cudaFreeHost(p->h_stage_in);
+    cudaFreeHost(p->h_stage_out);
+    cudaFree(p->d_stage_in);
+    cudaFree(p->d_stage_out);
+    cudaFree(p->d_stage_status);
+  }
+  const int64_t cap = std::max<int64_t>(n_rows, 4096);
+  CUDA_TRY(cudaMallocHost(&p->h_stage_in, (size_t)cap * p->n_in * 4));
+  CUDA_TRY(cudaMallocHost(&p->h_stage_out, (size_t)cap * (p->out_cols + 1) * 4));
+  CUDA_TRY(cudaMalloc(&p->d_stage_in, (size_t)cap * p->n_in * 4));
+  CUDA_TRY(cudaMalloc(&p->d_stage_out, (size_t)cap * p->out_cols * 4));
+  CUDA_TRY(cudaMalloc(&p->d_stage_status, (size_t)cap * 4));
+  p->stage_rows = cap;
+  return B2S_OK;
+}
+
+static void pack_rows(char* dst, const void* rows, int64_t n_rows, int64_t stride, int64_t row_bytes) {
+  if (stride == row_bytes) {
+    memcpy(dst, rows, (size_t)n_rows * row_bytes);
+  } else {
+    const char* s = (const char*)rows;
+    for (int64_t r = 0; r < n_rows; ++r) memcpy(dst + r * row_bytes, s + r * stride, (size_t)row_bytes);
+  }
+}
+
+extern "C" int b2s_run_host(b2s_plan_t p, const void* rows, int64_t n_rows, int64_t row_stride_bytes, void* out,
+                            int64_t out_bytes, int32_t* row_status, b2s_stats* stats) {
+  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+  const int64_t row_bytes = (int64_t)p->n_in * 4;
+  if (n_rows < 0 || row_stride_bytes < row_bytes) return fail(B2S_ERR_INVALID, "bad n_rows/stride");
+  if (out_bytes < n_rows * p->out_cols * 4) return fail(B2S_ERR_INVALID, "out buffer too small");
+  if (n_rows == 0) return B2S_OK;
+  std::lock_guard<std::mutex> lk(p->host_mu);
+  CUDA_TRY(cudaSetDevice(G.device));
+  if (int rc = ensure_stage(p, n_rows)) return rc;
+  cudaStream_t st = G.stream;
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, rows) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+                      row_stride_bytes == row_bytes;
+  cudaGetLastError();
+  const void* src = rows;
+  if (!pinned) {
+    pack_rows(p->h_stage_in, rows, n_rows, row_stride_bytes, row_bytes);
+    src = p->h_stage_in;
+  }
+  const size_t out_sz = (size_t)n_rows * p->out_cols * 4;
+  CUDA_TRY(cudaEventRecord(p->ev[0], st));
+  CUDA_TRY(cudaMemcpyAsync(p->d_stage_in, src, (size_t)n_rows * row_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(p->ev[1], st));
+  if (int rc = launch_on(p, p->d_stage_in, n_rows, row_bytes, p->d_stage_out, p->d_stage_status, st)) return rc;
+  CUDA_TRY(cudaEventRecord(p->ev[2], st));
+  CUDA_TRY(cudaMemcpyAsync(p->h_stage_out, p->d_stage_out, out_sz, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(p->h_stage_out + out_sz, p->d_stage_status, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(p->ev[3], st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(out, p->h_stage_out, out_sz);
+  const int32_t* hs = (const int32_t*)(p->h_stage_out + out_sz);
+  int bad = 0;
+  for (int64_t r = 0; r < n_rows; ++r) bad += (hs[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
+  if (row_status) memcpy(row_status, hs, (size_t)n_rows * 4);
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->rows = n_rows;
+    cudaEventElapsedTime(&stats->h2d_ms, p->ev[0], p->ev[1]);
+    cudaEventElapsedTime(&stats->kernel_ms, p->ev[1], p->ev[2]);
+    cudaEventElapsedTime(&stats->d2h_ms, p->ev[2], p->ev[3]);
+    stats->kernels = p->kernels_per_batch;
+    stats->nonfinite_rows = bad;
+  }
+  return B2S_OK;
+}
+
+extern "C" int b2s_time_device(b2s_plan_t p, const void* const* d_rows, int32_t n_bufs, int64_t n_rows,
+                               int64_t row_stride_bytes, void* d_out, int32_t n_iters, float* total_ms) {
+  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+  if (n_bufs < 1 || n_iters < 1 || !total_ms) return fail(B2S_ERR_INVALID, "bad arguments");
+  cudaStream_t st = G.stream;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaEventRecord(p->ev[0], st));
+  for (int i = 0; i < n_iters; ++i)
+    if (int rc = launch_on(p, d_rows[i % n_bufs], n_rows, row_stride_bytes, d_out, nullptr, st)) return rc;
+  CUDA_TRY(cudaEventRecord(p->ev[1], st));
+  CUDA_TRY(cudaEventSynchronize(p->ev[1]));
+  CUDA_TRY(cudaEventElapsedTime(total_ms, p->ev[0], p->ev[1]));
+  return B2S_OK;
+}
+
+// ------------------------------------------------------------------------------------------ coalescing ring
+static void dispatcher_main(b2s_plan_s* p) {
+  cudaSetDevice(G.device);
+  std::unique_lock<std::mutex> lk(p->mu);
+  for (;;) {
+    // wake up when a batch is sealed, when the open batch times out, or on stop
+    if (p->sealed.empty()) {
+      if (p->stop) return;
+      if (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0) {
+        auto deadline = p->slots[p->open_slot].first_submit + std::chrono::microseconds(G.max_wait_us);
+        if (p->cv_work.wait_until(lk, deadline) == std::cv_status::timeout) {
+          if (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0 &&
+              std::chrono::steady_clock::now() >= p->slots[p->open_slot].first_submit + std::chrono::microseconds(G.max_wait_us)) {
+            p->slots[p->open_slot].state = 1;
+            p->sealed.push_back(p->open_slot);
+            p->open_slot = -1;
+          }
+        }
+      } else {
+        p->cv_work.wait(lk);
+      }
+      continue;
+    }
+    const int si = p->sealed.front();
+    p->sealed.pop_front();
+    Slot& s = p->slots[si];
+    s.state = 2;
+    const int64_t rows = s.rows;
+    const float queue_us =
+        std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - s.first_submit).count();
+    lk.unlock();
+    cudaStream_t st = p->ring_stream;
+    const int64_t row_bytes = (int64_t)p->n_in * 4;
+    const size_t out_sz = (size_t)rows * p->out_cols * 4;
+    cudaEventRecord(s.e0, st);
+    cudaMemcpyAsync(s.d_in, s.h_in, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st);
+    cudaEventRecord(s.e1, st);
+    launch_on(p, s.d_in, rows, row_bytes, s.d_out, s.d_status, st);
+    cudaEventRecord(s.e2, st);
+    cudaMemcpyAsync(s.h_out, s.d_out, out_sz, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(s.h_out + (size_t)p->ring_cap * p->out_cols * 4, s.d_status, (size_t)rows * 4, cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(s.e3, st);
+    cudaEventSynchronize(s.e3);
+    b2s_stats stt{};
+    stt.rows = rows;
+    cudaEventElapsedTime(&stt.h2d_ms, s.e0, s.e1);
+    cudaEventElapsedTime(&stt.kernel_ms, s.e1, s.e2);
+    cudaEventElapsedTime(&stt.d2h_ms, s.e2, s.e3);
+    stt.queue_us = queue_us;
+    stt.kernels = p->kernels_per_batch;
+    lk.lock();
+    s.stats = stt;
+    s.state = 3;
+    p->cv_done.notify_all();
+  }
+}
+
+static int ring_start(b2s_plan_s* p) {
+  if (!p->slots.empty()) return B2S_OK;
+  CUDA_TRY(cudaSetDevice(G.device));
+  p->ring_cap = G.max_batch;
+  p->slots.resize(G.ring_slots);
+  const int64_t row_bytes = (int64_t)p->n_in * 4;
+  for (auto& s : p->slots) {
+    CUDA_TRY(cudaMallocHost(&s.h_in, (size_t)p->ring_cap * row_bytes));
+    CUDA_TRY(cudaMallocHost(&s.h_out, (size_t)p->ring_cap * (p->out_cols + 1) * 4));
+    CUDA_TRY(cudaMalloc(&s.d_in, (size_t)p->ring_cap * row_bytes));
+    CUDA_TRY(cudaMalloc(&s.d_out, (size_t)p->ring_cap * p->out_cols * 4));
+    CUDA_TRY(cudaMalloc(&s.d_status, (size_t)p->ring_cap * 4));
+    CUDA_TRY(cudaEventCreate(&s.e0));
+    CUDA_TRY(cudaEventCreate(&s.e1));
+    CUDA_TRY(cudaEventCreate(&s.e2));
+    CUDA_TRY(cudaEventCreate(&s.e3));
+  }
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->ring_stream, cudaStreamNonBlocking));
+  p->stop = false;
+  p->dispatcher = std::thread(dispatcher_main, p);
+  return B2S_OK;
+}
+
+// ticket = batch_id << 24 | row offset inside the batch (max_batch <= 2^24 rows)
+extern "C" int b2s_submit(b2s_plan_t p, const void* rows, int64_t n_rows, int64_t row_stride_bytes, uint64_t* ticket) {
+  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+  const int64_t row_bytes = (int64_t)p->n_in * 4;
+  if (n_rows <= 0 || row_stride_bytes < row_bytes || !ticket) return fail(B2S_ERR_INVALID, "bad submit arguments");
+  std::unique_lock<std::mutex> lk(p->mu);
+  if (int rc = ring_start(p)) return rc;
+  if (n_rows > p->ring_cap || p->ring_cap > (1 << 24)) return fail(B2S_ERR_INVALID, "submit of %lld rows exceeds max_batch %lld", (long long)n_rows, (long long)p->ring_cap);
+  for (;;) {
+    if (p->open_slot >= 0 && p->slots[p->open_slot].rows + n_rows > p->ring_cap) {
+      p->slots[p->open_slot].state = 1;
+      p->sealed.push_back(p->open_slot);
+      p->open_slot = -1;
+      p->cv_work.notify_one();
+    }
+    if (p->open_slot < 0) {
+      for (int i = 0; i < (int)p->slots.size(); ++i)
+        if (p->slots[i].state == 0 && p->slots[i].rows == 0 && p->slots[i].waiters == 0) {
+          p->open_slot = i;
+          p->slots[i].batch_id = p->next_batch++;
+          p->batch_slot[p->slots[i].batch_id] = i;
+          break;
+        }
+      if (p->open_slot < 0) {
+        p->cv_free.wait(lk);  // every slot is in flight or waiting to be collected
+        continue;
+      }
+    }
+    break;
+  }
+  Slot& s = p->slots[p->open_slot];
+  if (s.rows == 0) s.first_submit = std::chrono::steady_clock::now();
+  const int64_t off = s.rows;
+  pack_rows(s.h_in + off * row_bytes, rows, n_rows, row_stride_bytes, row_bytes);
+  s.rows += n_rows;
+  s.waiters += 1;
+  *ticket = (s.batch_id << 24) | (uint64_t)off;
+  if (s.rows >= p->ring_cap) {
+    s.state = 1;
+    p->sealed.push_back(p->open_slot);
+    p->open_slot = -1;
+  }
+  p->cv_work.notify_one();
+  // remember how many rows this ticket covers (low 24 bits hold the offset; the count travels in a side map)
+  return B2S_OK;
+}
+
+extern "C" int b2s_flush(b2s_plan_t p) {
+  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+  std::unique_lock<std::mutex> lk(p->mu);
+  if (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0) {
+    p->slots[p->open_slot].state = 1;
+    p->sealed.push_back(p->open_slot);
+    p->open_slot = -1;
+    p->cv_work.notify_one();
+  }
+  return B2S_OK;
+}
+
+extern "C" int b2s_wait(b2s_plan_t p, uint64_t ticket, void* out, int64_t out_bytes, int32_t* row_status, b2s_stats* stats) {
+  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+  const uint64_t batch = ticket >> 24;
+  const int64_t off = (int64_t)(ticket & ((1u << 24) - 1));
+  const int64_t n_rows = out_bytes / ((int64_t)p->out_cols * 4);
+  std::unique_lock<std::mutex> lk(p->mu);
+  auto it = p->batch_slot.find(batch);
+  if (it == p->batch_slot.end()) return fail(B2S_ERR_INVALID, "unknown ticket");
+  Slot& s = p->slots[it->second];
+  p->cv_done.wait(lk, [&] { return s.state == 3 && s.batch_id == batch; });
+  if (off + n_rows > s.rows) return fail(B2S_ERR_INVALID, "ticket range exceeds its batch");
+  memcpy(out, s.h_out + (size_t)off * p->out_cols * 4, (size_t)n_rows * p->out_cols * 4);
+  const int32_t* hs = (const int32_t*)(s.h_out + (size_t)p->ring_cap * p->out_cols * 4) + off;
+  if (row_status) memcpy(row_status, hs, (size_t)n_rows * 4);
+  if (stats) {
+    *stats = s.stats;
+    int bad = 0;
+    for (int64_t r = 0; r < n_rows; ++r) bad += (hs[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
+    stats->nonfinite_rows = bad;
+  }
+  if (--s.waiters == 0) {  // last collector frees the slot
+    p->batch_slot.erase(it);
+    s.rows = 0;
+    s.state = 0;
+    p->cv_free.notify_all();
+  }
+  return B2S_OK;
+}
+
+extern "C" int b2s_plan_destroy(b2s_plan_t p) {
+  if (!p) return B2S_OK;
+  if (p->dispatcher.joinable()) {
+    {
+      std::lock_guard<std::mutex> lk(p->mu);
+      p->stop = true;
+      p->cv_work.notify_all();
+    }
+    p->dispatcher.join();
+  }
+  for (auto& s : p->slots) {
+    cudaFreeHost(s.h_in);
+    cudaFreeHost(s.h_out);
+    cudaFree(s.d_in);
+    cudaFree(s.d_out);
+    cudaFree(s.d_status);
+    cudaEventDestroy(s.e0);
+    cudaEventDestroy(s.e1);
+    cudaEventDestroy(s.e2);
+    cudaEventDestroy(s.e3);
+  }
+  if (p->ring_stream) cudaStreamDestroy(p->ring_stream);
+  if (p->h_stage_in) {
+    cudaFreeHost(p->h_stage_in);
+    cudaFreeHost(p->h_stage_out);
+    cudaFree(p->d_stage_in);
+    cudaFree(p->d_stage_out);
+    cudaFree(p->d_stage_status);
+  }
+  for (int i = 0; i < 4; ++i)
+    if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+  if (p->d_blob) cudaFree(p->d_blob);
+  delete p;
+  return B2S_OK;
+}
+
+// ------------------------------------------------------------------------------------------ memory helpers
+extern "C" void* b2s_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    fail(B2S_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+extern "C" int b2s_free_pinned(void* p) {
+  CUDA_TRY(cudaFreeHost(p));
+  return B2S_OK;
+}
+extern "C" void* b2s_device_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    fail(B2S_ERR_CUDA, "cudaMalloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+extern "C" int b2s_device_free(void* p) {
+  CUDA_TRY(cudaFree(p));
+  return B2S_OK;
+}
+extern "C" int b2s_memcpy_h2d(void* d, const void* h, size_t bytes) {
+  CUDA_TRY(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
+  return B2S_OK;
+}
+extern "C" int b2s_memcpy_d2h(void* h, const void* d, size_t bytes) {
+  CUDA_TRY(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
+  return B2S_OK;
+}
+extern "C" int b2s_device_sync(void) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  return B2S_OK;
+}
