@@ -96,7 +96,8 @@ def flow3_workload(n_rows=4096, n_num=56, n_cat=8, seed=2, n_models=1, cats_per=
     X[:, n_num:] = rng.integers(0, cats_per, size=(n_rows, n_cat)).astype(np.float32)
     mrng = np.random.default_rng(seed * 10 + 1)
     nan_mask = mrng.random((n_rows, n_num)) < nan_frac
-    means = np.nanmean(np.where(nan_mask, np.nan, X[:, :n_num].astype(np.float64)), axis=0)
+    kept = np.where(nan_mask, 0.0, X[:, :n_num].astype(np.float64))
+    means = kept.sum(axis=0) / np.maximum((~nan_mask).sum(axis=0), 1)  # column mean of the observed values
     X[:, :n_num][nan_mask] = np.nan
     oov = mrng.random((n_rows, n_cat)) < oov_frac
     X[:, n_num:][oov] = 7.0

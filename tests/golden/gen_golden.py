@@ -33,7 +33,10 @@ def main():
             continue
         try:
             res = fn(api)
+            skips = [tuple(s) for s in getattr(fn, "GOLDEN_SKIP", [])]
             for path, want in getattr(fn, "EXPECT", {}).items():
+                if any(path[: len(s)] == s for s in skips):
+                    continue  # environment-dependent key (documented at the scenario)
                 got = scenarios.dig(res, path)
                 assert got == want, f"{fn.__name__}{path}: reference gave {got!r}, its own test expects {want!r}"
             out[fn.__name__] = res
