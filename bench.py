@@ -77,6 +77,12 @@ def _cpu_worker(args):
     import logging
 
     logging.disable(logging.CRITICAL)
+    try:  # one BLAS/OpenMP thread per worker process: P workers already cover the cores
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(1)
+    except Exception:
+        pass
     from tests import api_oracle
 
     wl = make_workload(name, max(n_events, 8) if name.startswith("flow3") else 64, seed)
@@ -106,7 +112,8 @@ def cpu_baseline(name, seconds, procs=None):
     n_cal = 300 if name.startswith("flow3") else 40
     n, dt = _cpu_worker((name, n_cal, 2))
     rate1 = n / dt
-    per_proc = int(max(n_cal, min(rate1 * seconds * 0.8, 200000)))
+    # with P busy processes each one runs slower than alone (shared caches / SMT): budget for ~2x
+    per_proc = int(max(n_cal, min(rate1 * seconds * 0.5, 200000)))
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctx.Pool(procs) as pool:
@@ -269,7 +276,8 @@ def main():
         bufs.append(torch.roll(base, shifts=i * 977, dims=0).cuda())
     out = torch.empty(B * plan.out_cols, dtype=torch.float32, device="cuda")
     gathered = torch.empty(world * B * plan.out_cols, dtype=torch.float32, device="cuda") if world > 1 else None
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-NULL) stream: kernels, NCCL and the timing events all ride on it
+    torch.cuda.set_stream(stream)
 
     def step(i):
         plan.run_device(bufs[i % nbuf].data_ptr(), B, row_bytes, out.data_ptr(), None, stream.cuda_stream)

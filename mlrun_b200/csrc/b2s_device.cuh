@@ -89,6 +89,9 @@ struct KParams {
   int32_t sm_fill, sm_flags, sm_mapoff, sm_catoff, sm_catval, sm_wnum, sm_wcat, sm_tiles, sm_exp, sm_pred,
       sm_outsrc, sm_outkind, sm_outarg, sm_total;
   int32_t n_cat, n_maps;
+  int32_t tpr;                // LINEAR: threads per row (slices of the row's 16-byte chunks)
+  int32_t sm_part, sm_pst, sm_chunk;
+  const uint8_t* chunk_kind;  // [ceil(n_in/4)] 0 = four plain numeric columns (fast path), 1 = generic
 };
 
 // ------------------------------------------------------------------------------------------ helpers
@@ -244,7 +247,7 @@ __device__ __forceinline__ void vote_and_store(const KParams& p, const double* _
 // ------------------------------------------------------------------------------------------ the kernel
 // NS = number of score slots held in registers per thread (LINEAR: all models' scores; TREES: one model's).
 template <int MODE, int NS>
-__global__ void __launch_bounds__(256) rows_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(512) rows_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* s_fill = reinterpret_cast<float*>(smem + p.sm_fill);
   uint32_t* s_flags = reinterpret_cast<uint32_t*>(smem + p.sm_flags);
@@ -258,6 +261,9 @@ __global__ void __launch_bounds__(256) rows_kernel(const __grid_constant__ KPara
   double* s_pred = reinterpret_cast<double*>(smem + p.sm_pred);
   int32_t* s_outsrc = reinterpret_cast<int32_t*>(smem + p.sm_outsrc);
   int32_t* s_outkind = reinterpret_cast<int32_t*>(smem + p.sm_outkind);
+  double* s_part = reinterpret_cast<double*>(smem + p.sm_part);
+  uint32_t* s_pst = reinterpret_cast<uint32_t*>(smem + p.sm_pst);
+  uint8_t* s_chunk = reinterpret_cast<uint8_t*>(smem + p.sm_chunk);
   float* s_outarg = reinterpret_cast<float*>(smem + p.sm_outarg);
 
   const int tid = threadIdx.x;
@@ -283,6 +289,7 @@ __global__ void __launch_bounds__(256) rows_kernel(const __grid_constant__ KPara
   }
   if (MODE == MODE_LINEAR) {
     for (int i = tid; i < p.n_cat; i += nthr) s_catval[i] = p.cat_val[i];
+    for (int i = tid; i < ((p.n_in + 3) >> 2); i += nthr) s_chunk[i] = p.chunk_kind[i];
     for (int i = tid; i < p.n_in * NS; i += nthr) s_wnum[i] = p.wnum[i];
     for (int i = tid; i < p.n_cat * NS; i += nthr) s_wcat[i] = p.wcat[i];
   } else {
@@ -320,55 +327,97 @@ __global__ void __launch_bounds__(256) rows_kernel(const __grid_constant__ KPara
     const int64_t row0 = t * TR;
 
     if (MODE == MODE_LINEAR) {
-      // -------- one thread per row: stage 1 + folded one-hot + fp64 dot for all NS scores
-      const int r = tid;
+      // -------- TPR threads per row.  Thread (q, r) owns a contiguous slice of row r's 16-byte chunks;
+      // q = tid / TR, so a warp is uniform in q: all its lanes work on the same columns (table reads are
+      // broadcasts) of 32 consecutive rows (conflict-free LDS.128 with pitch = 16 mod 128 bytes).
+      const int q = tid / TR;
+      const int r = tid - q * TR;
       const int64_t row = row0 + r;
-      if (r < TR && row < p.n_rows) {
-        double acc[NS];
+      double acc[NS];
 #pragma unroll
-        for (int k = 0; k < NS; ++k) acc[k] = p.bias[k];
-        uint32_t st = 0;
+      for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+      uint32_t st = 0;
+      if (row < p.n_rows) {
         const float* xr = tile + r * p.pitch;
-        for (int c = 0; c < p.n_in; c += 4) {
-          float xs[4];
-          if (p.vec_ok) {
-            float4 v = *reinterpret_cast<const float4*>(xr + c);
-            xs[0] = v.x; xs[1] = v.y; xs[2] = v.z; xs[3] = v.w;
-          } else {
+        const int nch = (p.n_in + 3) >> 2;
+        const int cps = (nch + p.tpr - 1) / p.tpr;
+        const int ch_end = min(nch, (q + 1) * cps);
+        for (int ch = q * cps; ch < ch_end; ++ch) {
+          const int c = ch << 2;
+          const float4 v = *reinterpret_cast<const float4*>(xr + c);  // pad words are never used
+          if (s_chunk[ch] == 0) {
+            // fast path: 4 plain numeric columns (copied, no maps, no categories)
+            const float4 f = *reinterpret_cast<const float4*>(s_fill + c);
+            const float x0 = (v.x != v.x) ? f.x : v.x;
+            const float x1 = (v.y != v.y) ? f.y : v.y;
+            const float x2 = (v.z != v.z) ? f.z : v.z;
+            const float x3 = (v.w != v.w) ? f.w : v.w;
+            if (!(is_finite_f(x0) && is_finite_f(x1) && is_finite_f(x2) && is_finite_f(x3))) st |= 1u;
+            const double* w = s_wnum + c * NS;
+            const double d0 = (double)x0, d1 = (double)x1, d2 = (double)x2, d3 = (double)x3;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) xs[u] = (c + u < p.n_in) ? xr[c + u] : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int cc = c + u;
-            if (cc >= p.n_in) break;
-            float x = xs[u];
-            const float f = s_fill[cc];
-            x = (x != x) ? f : x;  // Imputer: NaN -> fill (fill is NaN for columns without one)
-            const uint32_t fl = s_flags[cc];
-            if (fl & COL_HAS_MAP) x = apply_maps(x, p.maps, s_mapoff[cc], s_mapoff[cc + 1]);
-            if (fl & COL_COPIED) {
-              if (!is_finite_f(x)) st |= 1u;
-              const double xd = (double)x;
-              const double* w = s_wnum + cc * NS;
-#pragma unroll
-              for (int k = 0; k < NS; ++k) acc[k] = fma(w[k], xd, acc[k]);
+            for (int k = 0; k < NS; ++k) {
+              double a = acc[k];
+              a = fma(w[k], d0, a);
+              a = fma(w[NS + k], d1, a);
+              a = fma(w[2 * NS + k], d2, a);
+              a = fma(w[3 * NS + k], d3, a);
+              acc[k] = a;
             }
-            if (fl & COL_HAS_CAT) {
-              for (int j = s_catoff[cc]; j < s_catoff[cc + 1]; ++j) {
-                if (x == s_catval[j]) {  // OneHotEncoder: value == category -> that column is 1
-                  const double* w = s_wcat + j * NS;
+          } else {
+            const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                  for (int k = 0; k < NS; ++k) acc[k] += w[k];
+            for (int u = 0; u < 4; ++u) {
+              const int cc = c + u;
+              if (cc >= p.n_in) break;
+              float x = xs[u];
+              const float f = s_fill[cc];
+              x = (x != x) ? f : x;  // Imputer: NaN -> fill (fill is NaN for columns without one)
+              const uint32_t fl = s_flags[cc];
+              if (fl & COL_HAS_MAP) x = apply_maps(x, p.maps, s_mapoff[cc], s_mapoff[cc + 1]);
+              if (fl & COL_COPIED) {
+                if (!is_finite_f(x)) st |= 1u;
+                const double xd = (double)x;
+                const double* w = s_wnum + cc * NS;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) acc[k] = fma(w[k], xd, acc[k]);
+              }
+              if (fl & COL_HAS_CAT) {
+                const int j1 = s_catoff[cc + 1];
+                for (int j = s_catoff[cc]; j < j1; ++j) {
+                  if (x == s_catval[j]) {  // OneHotEncoder: value == category -> that column is 1
+                    const double* w = s_wcat + j * NS;
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) acc[k] += w[k];
+                  }
                 }
               }
             }
           }
         }
+      }
+      if (p.tpr > 1) {  // combine the row's slices in a fixed order (deterministic fp64 sum)
+        double* part = s_part + (size_t)(q * TR + r) * NS;
+        if (q > 0) {
+#pragma unroll
+          for (int k = 0; k < NS; ++k) part[k] = acc[k];
+          s_pst[q * TR + r] = st;
+        }
+        __syncthreads();
+        if (q == 0) {
+          for (int qq = 1; qq < p.tpr; ++qq) {
+            const double* o = s_part + (size_t)(qq * TR + r) * NS;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) acc[k] += o[k];
+            st |= s_pst[qq * TR + r];
+          }
+        }
+      }
+      if (q == 0 && row < p.n_rows) {
         // links + vote index the scores dynamically: do that on a copy so acc[] stays in registers
         double sl[NS];
 #pragma unroll
-        for (int k = 0; k < NS; ++k) sl[k] = acc[k];
+        for (int k = 0; k < NS; ++k) sl[k] = acc[k] + p.bias[k];
         double pred[kMaxModels];
         for (int m = 0; m < p.n_models; ++m) {
           const ModelDesc md = p.models[m];

@@ -160,10 +160,10 @@ static cudaError_t launch_rows(const KParams& kp, int grid, int block, cudaStrea
   return cudaGetLastError();
 }
 
-static cudaError_t launch_plan(b2s_plan_s* p, const KParams& kp, int grid, cudaStream_t st) {
+static cudaError_t launch_plan(b2s_plan_s* p, const KParams& kp, int grid, int block, cudaStream_t st) {
   G.launches.fetch_add(1, std::memory_order_relaxed);
 #define B2S_CASE(M, N) \
-  if (p->mode == M && p->NS == N) return launch_rows<M, N>(kp, grid, p->block, st);
+  if (p->mode == M && p->NS == N) return launch_rows<M, N>(kp, grid, block, st);
   B2S_CASE(MODE_LINEAR, 1) B2S_CASE(MODE_LINEAR, 2) B2S_CASE(MODE_LINEAR, 4) B2S_CASE(MODE_LINEAR, 8)
   B2S_CASE(MODE_LINEAR, 16) B2S_CASE(MODE_LINEAR, 32)
   B2S_CASE(MODE_TREES, 1) B2S_CASE(MODE_TREES, 4) B2S_CASE(MODE_TREES, 8) B2S_CASE(MODE_TREES, 16)
@@ -511,6 +511,12 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
   }
   if (bias.empty()) bias.assign(1, 0.0);
 
+  std::vector<uint8_t> chunk_kind((n_in + 3) / 4, 1);
+  for (int ch = 0; ch < (int)chunk_kind.size(); ++ch) {
+    bool fast = (ch * 4 + 3 < n_in);
+    for (int u = 0; fast && u < 4; ++u) fast = (flags[ch * 4 + u] == COL_COPIED);
+    chunk_kind[ch] = fast ? 0 : 1;
+  }
   // ---- upload one blob
   BlobBuilder bb;
   const size_t o_fill = bb.add(p->fill), o_flags = bb.add(flags), o_mapoff = bb.add(map_off), o_maps = bb.add(maps),
@@ -518,7 +524,8 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
                o_catoff = bb.add(cat_off), o_catval = bb.add(cat_val), o_wnum = bb.add(wnum), o_wcat = bb.add(wcat),
                o_bias = bb.add(bias), o_models = bb.add(descs), o_classes = bb.add(classes),
                o_votew = bb.add(p->vote_w), o_wgen = bb.add(wgen), o_nodes = bb.add(nodes), o_leaf = bb.add(leaf),
-               o_troot = bb.add(tree_root), o_tslot = bb.add(tree_slot), o_tscale = bb.add(tree_scale);
+               o_troot = bb.add(tree_root), o_tslot = bb.add(tree_slot), o_tscale = bb.add(tree_scale),
+               o_chunk = bb.add(chunk_kind);
   CUDA_TRY(cudaSetDevice(G.device));
   CUDA_TRY(cudaMalloc(&p->d_blob, bb.data.size()));
   CUDA_TRY(cudaMemcpy(p->d_blob, bb.data.data(), bb.data.size(), cudaMemcpyHostToDevice));
@@ -559,6 +566,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
   k.tree_root = (const int32_t*)(B + o_troot);
   k.tree_slot = (const int32_t*)(B + o_tslot);
   k.tree_scale = (const double*)(B + o_tscale);
+  k.chunk_kind = (const uint8_t*)(B + o_chunk);
 
   // ---- launch geometry + shared-memory carve-up
   // pitch (words): rows 16B aligned and (pitch/4) odd -> conflict-free LDS.128 for one-thread-per-row
@@ -569,9 +577,13 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
   const int smem_cap = (int)G.prop.sharedMemPerBlockOptin;
   const int sms = G.prop.multiProcessorCount;
   int block, tile_rows, stages, blocks_per_sm;
+  int tpr = 1;
   if (p->mode == MODE_LINEAR) {
-    block = 128;
-    tile_rows = block;
+    tpr = NS <= 8 ? 4 : (NS == 16 ? 2 : 1);
+    const int nch = (n_in + 3) / 4;
+    while (tpr > 1 && nch < tpr * 2) tpr /= 2;
+    tile_rows = 128;
+    block = tile_rows * tpr;
     stages = 3;
     blocks_per_sm = 2;
   } else if (p->mode == MODE_TREES) {
@@ -603,6 +615,9 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
     k.sm_outkind = take((size_t)n_out * 4);
     k.sm_outarg = take((size_t)n_out * 4);
     k.sm_pred = take(p->mode == MODE_TREES ? (size_t)tr * k.models_pow2 * 8 : 16);
+    k.sm_chunk = take((size_t)(n_in + 3) / 4 + 16);
+    k.sm_part = take((p->mode == MODE_LINEAR && tpr > 1) ? (size_t)tr * tpr * NS * 8 : 16);
+    k.sm_pst = take((p->mode == MODE_LINEAR && tpr > 1) ? (size_t)tr * tpr * 4 : 16);
     k.sm_exp = take((p->mode != MODE_LINEAR && need_expand) ? (size_t)tr * exp_pitch * 4 : 16);
     k.sm_tiles = take((size_t)st * tr * pitch * 4);
     return (int)align_up(off, 16);
@@ -629,6 +644,8 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
     if (total > smem_cap) return fail(B2S_ERR_UNSUPPORTED, "plan needs %d B shared memory > %d B", total, smem_cap);
   }
   if (p->mode == MODE_TREES) block = std::max(32, tile_rows * k.models_pow2);
+  if (p->mode == MODE_LINEAR) block = tile_rows * tpr;
+  k.tpr = tpr;
   k.sm_total = total;
   k.tile_rows = tile_rows;
   k.pitch = pitch;
@@ -662,9 +679,17 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
   k.out = (float*)d_out;
   k.status = d_status;
   k.vec_ok = ((p->n_in % 4) == 0 && (stride % 16) == 0 && ((uintptr_t)d_rows % 16) == 0) ? 1 : 0;
+  // small batches: shrink the tile so that every SM gets work (latency path); the shared-memory
+  // carve-up was sized for the largest tile, so any smaller power-of-two tile fits
+  int block = p->block;
+  if (p->mode != MODE_STORE) {
+    const int per_row = p->block / k.tile_rows;
+    while (k.tile_rows > 32 && (n_rows + k.tile_rows - 1) / k.tile_rows < (int64_t)G.prop.multiProcessorCount) k.tile_rows /= 2;
+    block = k.tile_rows * per_row;
+  }
   const int64_t tiles = (n_rows + k.tile_rows - 1) / k.tile_rows;
   const int grid = (int)std::min<int64_t>(p->grid, tiles);
-  cudaError_t e = launch_plan(p, k, grid, st);
+  cudaError_t e = launch_plan(p, k, grid, block, st);
   if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return B2S_OK;
 }
