@@ -1,0 +1,253 @@
+// b2s_rowwarp.cuh -- the HBM-bound linear path: a register-resident "row-warp" kernel (sm_100a).
+//
+// Imputer -> OneHotEncoder -> {linear scorers} -> vote is a (B x F)·(F x NS) product with a tiny NS
+// (1..8 scores), i.e. a streaming, HBM-bound row reduction -- not GEMM-shaped work, so no tensor cores.
+// Layout of the work:
+//
+//   * L = F/4 lanes own one event row: lane j loads the row's j-th 16-byte chunk straight from HBM
+//     (one coalesced LDG.128 per lane, 32/L consecutive rows per warp instruction, no shared-memory
+//     staging: every byte is read exactly once and used from registers);
+//   * each lane keeps the weights of *its* 4 columns for all NS scores, and their Imputer fills, in
+//     registers for the whole kernel (persistent warps, grid = SMs x resident blocks);
+//   * U rows are in flight per lane (U independent LDG.128s), giving V = U*NS partial sums per lane;
+//     the cross-lane sum is a reduce-scatter butterfly (V/2 + V/4 + ... shuffles instead of V*log2 L),
+//     fp64 throughout, after which lane i holds the finished score (row i / NS, score i % NS);
+//   * categorical (one-hot) columns are handed to the lanes of the row round-robin with 4 shuffles, so
+//     that each lane resolves at most CS categories-lookups per row; the one-hot row is never built:
+//     "onehot(x) . w" is the gather  w[cat_base + index_of(x)];
+//   * epilogue: bias, link, VotingEnsemble mean (a second, log2 NS-step butterfly) or the generic
+//     link / majority-vote path on one lane per row; 4-byte coalesced stores.
+#pragma once
+#include "b2s_device.cuh"
+
+namespace b2s {
+
+struct RWParams {
+  const char* rows;
+  int64_t row_stride;
+  int64_t n_rows;
+  float* out;
+  int32_t* status;
+  int32_t n_in, nch, out_cols, n_models, vote_kind, out_is_int, fast_epilogue, n_cat_slots;
+  // per-lane tables (global, read once per warp at kernel start); index = lane_in_row
+  const float* fill;        // [L*4]
+  const uint32_t* copied;   // [L]   bit u: column 4*lane+u feeds a COPY output
+  const double* w;          // [L*4*NS] weights of the lane's 4 columns
+  const int32_t* cat_src;   // [CS*L] lane_in_row that holds the categorical column handled in slot s (-1: none)
+  const int32_t* cat_comp;  // [CS*L] component (0..3) of that lane's chunk
+  const int32_t* cat_base;  // [CS*L] first entry in cat_val / wcat
+  const int32_t* cat_n;     // [CS*L] number of categories
+  const float* cat_val;     // [n_cat]
+  const double* wcat;       // [n_cat*NS]
+  const double* bias;       // [NS]
+  const double* vote_w;     // [n_models]
+  const ModelDesc* models;
+  const int32_t* classes;
+  int32_t n_cat;
+};
+
+__device__ __forceinline__ float4 ldg_stream(const void* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int off) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(0xffffffffu, lo, off);
+  hi = __shfl_xor_sync(0xffffffffu, hi, off);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_idx_d(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src);
+  hi = __shfl_sync(0xffffffffu, hi, src);
+  return __hiloint2double(hi, lo);
+}
+
+constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x / 2); }
+
+// L lanes per row, NS score slots, U rows in flight per lane-group, CS categorical slots per lane
+template <int L, int NS, int U, int CS>
+__global__ void __launch_bounds__(256) rowwarp_kernel(const __grid_constant__ RWParams p) {
+  constexpr int RPW = 32 / L;          // rows per warp instruction
+  constexpr int V = U * NS;            // partial sums per lane
+  constexpr int VH = V < L ? V : L;    // values that take part in the halving phase
+  static_assert(V <= L, "U is chosen so that U*NS <= L");
+  constexpr int REP = L / V;           // lanes holding replicas of one finished value
+  constexpr int GROUP = U * RPW;       // rows per warp iteration
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* s_catval = reinterpret_cast<float*>(smem);
+  double* s_wcat = reinterpret_cast<double*>(smem + ((p.n_cat * 4 + 15) / 16) * 16);
+  for (int i = threadIdx.x; i < p.n_cat; i += blockDim.x) s_catval[i] = p.cat_val[i];
+  for (int i = threadIdx.x; i < p.n_cat * NS; i += blockDim.x) s_wcat[i] = p.wcat[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int lir = lane & (L - 1);  // lane in row
+  const int half = lane / L;       // which of the RPW rows of a warp instruction
+  const bool has_chunk = lir < p.nch;
+
+  // ---- per-lane constants, resident in registers for the whole kernel
+  float fill[4];
+  double w[4][NS];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    fill[u] = p.fill[lir * 4 + u];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) w[u][k] = p.w[(lir * 4 + u) * NS + k];
+  }
+  const uint32_t copied = p.copied[lir];
+  constexpr int CSA = CS > 0 ? CS : 1;
+  int cat_src[CSA], cat_comp[CSA], cat_base[CSA], cat_n[CSA];
+#pragma unroll
+  for (int s = 0; s < CS; ++s) {
+    cat_src[s] = p.cat_src[s * L + lir];
+    cat_comp[s] = p.cat_comp[s * L + lir];
+    cat_base[s] = p.cat_base[s * L + lir];
+    cat_n[s] = p.cat_n[s * L + lir];
+  }
+  // after the butterfly this lane owns value index `own` = (row slot, score slot)
+  const int own = lir / REP;
+  const int own_i = own / NS, own_k = own % NS;
+  const double my_bias = p.bias[own_k];
+  const double my_vw = (p.vote_kind == 1) ? p.vote_w[own_k < p.n_models ? own_k : 0] : 1.0;
+
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t n_groups = (p.n_rows + GROUP - 1) / GROUP;
+  const int64_t gstride = (int64_t)gridDim.x * warps_per_block;
+  for (int64_t g = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); g < n_groups; g += gstride) {
+    const int64_t base = g * GROUP;
+    // ---- U independent 16-byte loads per lane
+    float4 x[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const int64_t row = base + i * RPW + half;
+      if (has_chunk && row < p.n_rows)
+        x[i] = ldg_stream(p.rows + row * p.row_stride + lir * 16);
+      else
+        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    double v[V];
+    uint32_t bad = 0;  // bit i: a non-finite value reached a model input in row slot i
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+      double a[NS];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) a[k] = 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float xv = xs[u];
+        xv = (xv != xv) ? fill[u] : xv;  // Imputer (fill is NaN where the column has none)
+        xs[u] = xv;
+        const bool cp = (copied >> u) & 1u;
+        if (cp && !is_finite_f(xv)) bad |= (1u << i);
+        const double xd = cp ? (double)xv : 0.0;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) a[k] = fma(w[u][k], xd, a[k]);
+      }
+      if (CS > 0 && p.n_cat_slots > 0) {
+        // hand the categorical columns of this row to the lanes of the row, one component per round
+#pragma unroll
+        for (int s = 0; s < CS; ++s) {
+          float xc = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float t = __shfl_sync(0xffffffffu, xs[c], half * L + (cat_src[s] < 0 ? 0 : cat_src[s]));
+            if (cat_comp[s] == c) xc = t;
+          }
+          if (cat_src[s] >= 0) {
+            int j = -1;
+            for (int jj = 0; jj < cat_n[s]; ++jj)
+              if (xc == s_catval[cat_base[s] + jj]) j = jj;  // categories are de-duplicated: one match at most
+            if (j >= 0) {
+              const double* wc = s_wcat + (size_t)(cat_base[s] + j) * NS;
+#pragma unroll
+              for (int k = 0; k < NS; ++k) a[k] += wc[k];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NS; ++k) v[i * NS + k] = a[k];
+    }
+    // ---- reduce-scatter butterfly over the L lanes of a row (fp64)
+    {
+      int n = VH;
+#pragma unroll
+      for (int off = L / 2; off >= 1; off >>= 1) {
+        if (n > 1) {
+          const bool upper = (lir & off) != 0;
+          const int hn = n / 2;
+#pragma unroll
+          for (int j = 0; j < V / 2; ++j) {
+            if (j < hn) {
+              const double keep = upper ? v[j + hn] : v[j];
+              const double send = upper ? v[j] : v[j + hn];
+              v[j] = keep + shfl_xor_d(send, off);
+            }
+          }
+          n = hn;
+        } else {
+          v[0] += shfl_xor_d(v[0], off);
+        }
+      }
+    }
+    // non-finite flags of every row slot, for all lanes at once
+    uint32_t badmask[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) badmask[i] = __ballot_sync(0xffffffffu, (bad >> i) & 1u);
+    uint32_t my_bad = 0;
+#pragma unroll
+    for (int i = 0; i < U; ++i)
+      if (i == own_i) my_bad = (badmask[i] >> (half * L)) & (L == 32 ? 0xffffffffu : ((1u << L) - 1u));
+
+    const int64_t my_row = base + own_i * RPW + half;
+    double s = v[0] + my_bias;
+    if (p.fast_epilogue) {
+      // identity links, one score per model: VOTE_NONE writes every score, VOTE_MEAN sums w_k * s_k
+      if (p.vote_kind == 1) {
+        s *= my_vw;
+        if (own_k >= p.n_models) s = 0.0;
+#pragma unroll
+        for (int off = 1; off < NS; off <<= 1) s += shfl_xor_d(s, off * REP);
+        if (own_k == 0 && (lir % REP) == 0 && my_row < p.n_rows) {
+          p.out[my_row] = (float)s;
+          if (p.status) p.status[my_row] = my_bad ? 1 : 0;
+        }
+      } else {
+        if ((lir % REP) == 0 && own_k < p.n_models && my_row < p.n_rows) {
+          p.out[my_row * p.out_cols + own_k] = (float)s;
+          if (p.status && own_k == 0) p.status[my_row] = my_bad ? 1 : 0;
+        }
+      }
+    } else {
+      // generic epilogue: collect the row's NS scores on its first lane, then links + vote there
+      double sc[NS];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) sc[k] = shfl_idx_d(s, half * L + (own_i * NS + k) * REP);
+      if (own_k == 0 && (lir % REP) == 0 && my_row < p.n_rows) {
+        double pred[kMaxModels];
+        for (int m = 0; m < p.n_models; ++m) {
+          const ModelDesc md = p.models[m];
+          pred[m] = apply_link(md, sc + md.score_off, p.classes);
+        }
+        KParams kp;  // vote_and_store only reads these fields
+        kp.out = p.out;
+        kp.out_cols = p.out_cols;
+        kp.n_models = p.n_models;
+        kp.vote_kind = p.vote_kind;
+        kp.out_is_int = p.out_is_int;
+        kp.vote_w = p.vote_w;
+        kp.status = p.status;
+        vote_and_store(kp, pred, my_row, my_bad ? 1u : 0u);
+      }
+    }
+  }
+}
+
+}  // namespace b2s

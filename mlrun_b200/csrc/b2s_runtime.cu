@@ -21,6 +21,7 @@
 
 #include "../../include/b200serve.h"
 #include "b2s_device.cuh"
+#include "b2s_rowwarp.cuh"
 
 using namespace b2s;
 
@@ -111,6 +112,10 @@ struct b2s_plan_s {
   size_t blob_bytes = 0;
   int grid = 0, block = 0;
   int kernels_per_batch = 1;
+  // row-warp kernel (register-resident linear path)
+  bool rw_ok = false;
+  int rw_L = 0, rw_NS = 0, rw_U = 0, rw_CS = 0, rw_grid = 0, rw_smem = 0;
+  RWParams rw{};
   // host staging for run_host
   char* h_stage_in = nullptr;
   char* h_stage_out = nullptr;
@@ -169,6 +174,28 @@ static cudaError_t launch_plan(b2s_plan_s* p, const KParams& kp, int grid, int b
   B2S_CASE(MODE_TREES, 1) B2S_CASE(MODE_TREES, 4) B2S_CASE(MODE_TREES, 8) B2S_CASE(MODE_TREES, 16)
   B2S_CASE(MODE_STORE, 1)
 #undef B2S_CASE
+  return cudaErrorInvalidValue;
+}
+
+template <int L, int NS, int CS>
+static cudaError_t launch_rw_t(const RWParams& rp, int grid, int smem, cudaStream_t st, bool query, int* occ) {
+  constexpr int U0 = L / NS < 1 ? 1 : L / NS;
+  constexpr int U = U0 > 8 ? 8 : U0;
+  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowwarp_kernel<L, NS, U, CS>, 256, smem);
+  rowwarp_kernel<L, NS, U, CS><<<grid, 256, smem, st>>>(rp);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_rw(int L, int NS, int CS, const RWParams& rp, int grid, int smem, cudaStream_t st,
+                             bool query = false, int* occ = nullptr) {
+#define RW_CASE(l, n, c) \
+  if (L == l && NS == n && CS == c) return launch_rw_t<l, n, c>(rp, grid, smem, st, query, occ);
+#define RW_NS(l, c) RW_CASE(l, 1, c) RW_CASE(l, 2, c) RW_CASE(l, 4, c) RW_CASE(l, 8, c)
+#define RW_L(c) RW_NS(8, c) RW_NS(16, c) RW_NS(32, c)
+  RW_L(0) RW_L(1) RW_L(2)
+#undef RW_L
+#undef RW_NS
+#undef RW_CASE
   return cudaErrorInvalidValue;
 }
 
@@ -517,6 +544,52 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
     for (int u = 0; fast && u < 4; ++u) fast = (flags[ch * 4 + u] == COL_COPIED);
     chunk_kind[ch] = fast ? 0 : 1;
   }
+  // ---- row-warp kernel tables (linear plans over <= 128 columns without MapValues)
+  std::vector<float> rw_fill;
+  std::vector<uint32_t> rw_copied;
+  std::vector<double> rw_w;
+  std::vector<int32_t> rw_csrc, rw_ccomp, rw_cbase, rw_cn;
+  {
+    const int nch = (n_in + 3) / 4;
+    int L = nch <= 8 ? 8 : (nch <= 16 ? 16 : 32);
+    std::vector<int> cat_cols;
+    int max_cats = 0;
+    if (p->mode == MODE_LINEAR)
+      for (int c = 0; c < n_in; ++c)
+        if (cat_off[c + 1] > cat_off[c]) {
+          cat_cols.push_back(c);
+          max_cats = std::max(max_cats, cat_off[c + 1] - cat_off[c]);
+        }
+    const int CS = (int)((cat_cols.size() + L - 1) / L);
+    const bool env_off = getenv("B2S_NO_ROWWARP") != nullptr;
+    if (!env_off && p->mode == MODE_LINEAR && !any_map && (n_in % 4) == 0 && nch <= 32 && NS <= 8 && NS <= L && CS <= 2 && max_cats <= 64) {
+      p->rw_ok = true;
+      p->rw_L = L;
+      p->rw_NS = NS;
+      p->rw_CS = CS;
+      rw_fill.assign((size_t)L * 4, std::numeric_limits<float>::quiet_NaN());
+      rw_copied.assign(L, 0);
+      rw_w.assign((size_t)L * 4 * NS, 0.0);
+      for (int c = 0; c < n_in; ++c) {
+        rw_fill[c] = p->fill[c];
+        if (flags[c] & COL_COPIED) rw_copied[c / 4] |= (1u << (c % 4));
+        for (int kk = 0; kk < NS; ++kk) rw_w[(size_t)c * NS + kk] = wnum[(size_t)c * NS + kk];
+      }
+      const int slots = std::max(CS, 1);
+      rw_csrc.assign((size_t)slots * L, -1);
+      rw_ccomp.assign((size_t)slots * L, 0);
+      rw_cbase.assign((size_t)slots * L, 0);
+      rw_cn.assign((size_t)slots * L, 0);
+      for (size_t i = 0; i < cat_cols.size(); ++i) {
+        const int c = cat_cols[i];
+        const size_t at = (i / L) * L + (i % L);
+        rw_csrc[at] = c / 4;
+        rw_ccomp[at] = c % 4;
+        rw_cbase[at] = cat_off[c];
+        rw_cn[at] = cat_off[c + 1] - cat_off[c];
+      }
+    }
+  }
   // ---- upload one blob
   BlobBuilder bb;
   const size_t o_fill = bb.add(p->fill), o_flags = bb.add(flags), o_mapoff = bb.add(map_off), o_maps = bb.add(maps),
@@ -525,7 +598,9 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
                o_bias = bb.add(bias), o_models = bb.add(descs), o_classes = bb.add(classes),
                o_votew = bb.add(p->vote_w), o_wgen = bb.add(wgen), o_nodes = bb.add(nodes), o_leaf = bb.add(leaf),
                o_troot = bb.add(tree_root), o_tslot = bb.add(tree_slot), o_tscale = bb.add(tree_scale),
-               o_chunk = bb.add(chunk_kind);
+               o_chunk = bb.add(chunk_kind), o_rwfill = bb.add(rw_fill), o_rwcop = bb.add(rw_copied),
+               o_rww = bb.add(rw_w), o_rwcs = bb.add(rw_csrc), o_rwcc = bb.add(rw_ccomp), o_rwcb = bb.add(rw_cbase),
+               o_rwcn = bb.add(rw_cn);
   CUDA_TRY(cudaSetDevice(G.device));
   CUDA_TRY(cudaMalloc(&p->d_blob, bb.data.size()));
   CUDA_TRY(cudaMemcpy(p->d_blob, bb.data.data(), bb.data.size(), cudaMemcpyHostToDevice));
@@ -656,6 +731,43 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
   int occ = std::max(1, std::min(blocks_per_sm, smem_cap / std::max(total, 1)));
   p->grid = sms * occ;
 
+  if (p->rw_ok) {
+    RWParams& r = p->rw;
+    memset(&r, 0, sizeof(r));
+    r.n_in = n_in;
+    r.nch = (n_in + 3) / 4;
+    r.out_cols = p->out_cols;
+    r.n_models = M;
+    r.vote_kind = p->vote_kind;
+    r.out_is_int = p->out_is_int;
+    r.n_cat_slots = p->rw_CS;
+    r.n_cat = (int)cat_val.size();
+    bool simple = true;
+    for (auto& m : p->models) simple = simple && m.link == B2S_LINK_IDENTITY && m.n_scores == 1;
+    r.fast_epilogue = (simple && p->vote_kind != B2S_VOTE_MAJORITY) ? 1 : 0;
+    r.fill = (const float*)(B + o_rwfill);
+    r.copied = (const uint32_t*)(B + o_rwcop);
+    r.w = (const double*)(B + o_rww);
+    r.cat_src = (const int32_t*)(B + o_rwcs);
+    r.cat_comp = (const int32_t*)(B + o_rwcc);
+    r.cat_base = (const int32_t*)(B + o_rwcb);
+    r.cat_n = (const int32_t*)(B + o_rwcn);
+    r.cat_val = k.cat_val;
+    r.wcat = k.wcat;
+    r.bias = k.bias;
+    r.vote_w = k.vote_w;
+    r.models = k.models;
+    r.classes = k.classes;
+    p->rw_smem = (int)(align_up((size_t)r.n_cat * 4, 16) + (size_t)std::max(r.n_cat, 1) * NS * 8 + 16);
+    int occ = 0;
+    cudaError_t e = launch_rw(p->rw_L, p->rw_NS, p->rw_CS, r, 0, p->rw_smem, nullptr, true, &occ);
+    if (e != cudaSuccess || occ < 1) {
+      cudaGetLastError();
+      p->rw_ok = false;
+    } else {
+      p->rw_grid = sms * occ;
+    }
+  }
   for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&p->ev[i]));
   p->finalized = true;
   return B2S_OK;
@@ -679,6 +791,22 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
   k.out = (float*)d_out;
   k.status = d_status;
   k.vec_ok = ((p->n_in % 4) == 0 && (stride % 16) == 0 && ((uintptr_t)d_rows % 16) == 0) ? 1 : 0;
+  if (p->rw_ok && k.vec_ok) {
+    RWParams r = p->rw;
+    r.rows = (const char*)d_rows;
+    r.row_stride = stride;
+    r.n_rows = n_rows;
+    r.out = (float*)d_out;
+    r.status = d_status;
+    const int rpw = 32 / p->rw_L;
+    const int u = std::min(8, std::max(1, p->rw_L / p->rw_NS));
+    const int64_t groups = (n_rows + (int64_t)u * rpw - 1) / ((int64_t)u * rpw);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->rw_grid, (groups + 7) / 8));
+    G.launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = launch_rw(p->rw_L, p->rw_NS, p->rw_CS, r, grid, p->rw_smem, st);
+    if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "row-warp kernel launch failed: %s", cudaGetErrorString(e));
+    return B2S_OK;
+  }
   // small batches: shrink the tile so that every SM gets work (latency path); the shared-memory
   // carve-up was sized for the largest tile, so any smaller power-of-two tile fits
   int block = p->block;
