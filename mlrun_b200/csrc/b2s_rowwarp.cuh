@@ -4,19 +4,21 @@
 // (1..8 scores), i.e. a streaming, HBM-bound row reduction -- not GEMM-shaped work, so no tensor cores.
 // Layout of the work:
 //
-//   * L = F/4 lanes own one event row: lane j loads the row's j-th 16-byte chunk straight from HBM
-//     (one coalesced LDG.128 per lane, 32/L consecutive rows per warp instruction, no shared-memory
-//     staging: every byte is read exactly once and used from registers);
-//   * each lane keeps the weights of *its* 4 columns for all NS scores, and their Imputer fills, in
-//     registers for the whole kernel (persistent warps, grid = SMs x resident blocks);
-//   * U rows are in flight per lane (U independent LDG.128s), giving V = U*NS partial sums per lane;
-//     the cross-lane sum is a reduce-scatter butterfly (V/2 + V/4 + ... shuffles instead of V*log2 L),
-//     fp64 throughout, after which lane i holds the finished score (row i / NS, score i % NS);
-//   * categorical (one-hot) columns are handed to the lanes of the row round-robin with 4 shuffles, so
-//     that each lane resolves at most CS categories-lookups per row; the one-hot row is never built:
+//   * L lanes own one event row; lane j loads CPL 16-byte chunks of it (chunks j, j+L) straight from
+//     HBM -- coalesced LDG.128s covering whole 128-byte lines, 32/L consecutive rows per warp
+//     instruction, no shared-memory staging: every byte is read exactly once and used from registers;
+//   * each lane keeps the weights of *its* 4*CPL columns for all NS scores, and their Imputer fills,
+//     in registers for the whole kernel (persistent warps, grid = SMs x resident blocks);
+//   * U row slots are in flight per lane (U*CPL independent loads), giving V = U*NS partial sums per
+//     lane; the cross-lane sum is a reduce-scatter butterfly (V/2 + V/4 + ... exchanges instead of
+//     V*log2 L), fp64 throughout, after which lane i holds one finished score (row i / NS, score i % NS);
+//   * categorical (one-hot) columns are handed to the lanes of the row round-robin with shuffles, so
+//     that each lane resolves at most CS category look-ups per row; the one-hot row is never built:
 //     "onehot(x) . w" is the gather  w[cat_base + index_of(x)];
+//   * a non-finite model input shows up as a non-finite score (NaN/Inf survive every fma, also with a
+//     zero weight), so the per-row status costs one test on the finished score;
 //   * epilogue: bias, link, VotingEnsemble mean (a second, log2 NS-step butterfly) or the generic
-//     link / majority-vote path on one lane per row; 4-byte coalesced stores.
+//     link / majority-vote path on one lane per row; coalesced 4-byte stores.
 #pragma once
 #include "b2s_device.cuh"
 
@@ -29,12 +31,13 @@ struct RWParams {
   float* out;
   int32_t* status;
   int32_t n_in, nch, out_cols, n_models, vote_kind, out_is_int, fast_epilogue, n_cat_slots;
-  // per-lane tables (global, read once per warp at kernel start); index = lane_in_row
-  const float* fill;        // [L*4]
-  const uint32_t* copied;   // [L]   bit u: column 4*lane+u feeds a COPY output
-  const double* w;          // [L*4*NS] weights of the lane's 4 columns
-  const int32_t* cat_src;   // [CS*L] lane_in_row that holds the categorical column handled in slot s (-1: none)
-  const int32_t* cat_comp;  // [CS*L] component (0..3) of that lane's chunk
+  // per-lane tables (global, read once per warp at kernel start); column c lives in lane (c/4) % L,
+  // chunk slot (c/4) / L, component c % 4
+  const float* fill;        // [CPL*L*4]   index (slot*L + lane)*4 + comp
+  const uint32_t* copied;   // [CPL*L]     bit u: that column feeds a COPY output
+  const double* w;          // [CPL*L*4*NS]
+  const int32_t* cat_src;   // [CS*L] source position (slot*L + lane) of the categorical column a lane resolves; -1 none
+  const int32_t* cat_comp;  // [CS*L] component (0..3) inside that chunk
   const int32_t* cat_base;  // [CS*L] first entry in cat_val / wcat
   const int32_t* cat_n;     // [CS*L] number of categories
   const float* cat_val;     // [n_cat]
@@ -66,18 +69,18 @@ __device__ __forceinline__ double shfl_idx_d(double v, int src) {
   hi = __shfl_sync(0xffffffffu, hi, src);
   return __hiloint2double(hi, lo);
 }
+__device__ __forceinline__ bool is_finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
 
-constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x / 2); }
-
-// L lanes per row, NS score slots, U rows in flight per lane-group, CS categorical slots per lane
-template <int L, int NS, int U, int CS>
-__global__ void __launch_bounds__(256) rowwarp_kernel(const __grid_constant__ RWParams p) {
-  constexpr int RPW = 32 / L;          // rows per warp instruction
-  constexpr int V = U * NS;            // partial sums per lane
-  constexpr int VH = V < L ? V : L;    // values that take part in the halving phase
+// L lanes per row, CPL chunks per lane, NS score slots, U row slots in flight, CS categorical slots per lane
+template <int L, int CPL, int NS, int U, int CS>
+__global__ void __launch_bounds__(128, 4) rowwarp_kernel(const __grid_constant__ RWParams p) {
+  constexpr int RPW = 32 / L;  // rows per warp instruction
+  constexpr int V = U * NS;    // partial sums per lane
   static_assert(V <= L, "U is chosen so that U*NS <= L");
-  constexpr int REP = L / V;           // lanes holding replicas of one finished value
-  constexpr int GROUP = U * RPW;       // rows per warp iteration
+  constexpr int REP = L / V;       // lanes holding replicas of one finished value
+  constexpr int GROUP = U * RPW;   // rows per warp iteration
+  constexpr int CSA = CS > 0 ? CS : 1;
+  constexpr int KC = 4;            // categories cached in registers per categorical slot
 
   extern __shared__ __align__(16) unsigned char smem[];
   float* s_catval = reinterpret_cast<float*>(smem);
@@ -89,26 +92,35 @@ __global__ void __launch_bounds__(256) rowwarp_kernel(const __grid_constant__ RW
   const int lane = threadIdx.x & 31;
   const int lir = lane & (L - 1);  // lane in row
   const int half = lane / L;       // which of the RPW rows of a warp instruction
-  const bool has_chunk = lir < p.nch;
 
   // ---- per-lane constants, resident in registers for the whole kernel
-  float fill[4];
-  double w[4][NS];
+  float fill[CPL][4];
+  double w[CPL][4][NS];
+  uint32_t copied[CPL];
+  bool has_chunk[CPL];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    fill[u] = p.fill[lir * 4 + u];
+  for (int c = 0; c < CPL; ++c) {
+    const int pos = c * L + lir;
+    has_chunk[c] = pos < p.nch;
+    copied[c] = p.copied[pos];
 #pragma unroll
-    for (int k = 0; k < NS; ++k) w[u][k] = p.w[(lir * 4 + u) * NS + k];
+    for (int u = 0; u < 4; ++u) {
+      fill[c][u] = p.fill[pos * 4 + u];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) w[c][u][k] = p.w[(pos * 4 + u) * NS + k];
+    }
   }
-  const uint32_t copied = p.copied[lir];
-  constexpr int CSA = CS > 0 ? CS : 1;
-  int cat_src[CSA], cat_comp[CSA], cat_base[CSA], cat_n[CSA];
+  int cat_lane[CSA], cat_sel[CSA], cat_base[CSA], cat_n[CSA];
+  float cat_c[CSA][KC];
 #pragma unroll
   for (int s = 0; s < CS; ++s) {
-    cat_src[s] = p.cat_src[s * L + lir];
-    cat_comp[s] = p.cat_comp[s * L + lir];
+    const int src = p.cat_src[s * L + lir];
+    cat_lane[s] = src < 0 ? -1 : (src % L);
+    cat_sel[s] = src < 0 ? -1 : (src / L) * 4 + p.cat_comp[s * L + lir];  // which of the CPL*4 values
     cat_base[s] = p.cat_base[s * L + lir];
     cat_n[s] = p.cat_n[s * L + lir];
+#pragma unroll
+    for (int j = 0; j < KC; ++j) cat_c[s][j] = (src >= 0 && j < cat_n[s]) ? p.cat_val[cat_base[s] + j] : __int_as_float(0x7fc00000);
   }
   // after the butterfly this lane owns value index `own` = (row slot, score slot)
   const int own = lir / REP;
@@ -121,54 +133,63 @@ __global__ void __launch_bounds__(256) rowwarp_kernel(const __grid_constant__ RW
   const int64_t gstride = (int64_t)gridDim.x * warps_per_block;
   for (int64_t g = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); g < n_groups; g += gstride) {
     const int64_t base = g * GROUP;
-    // ---- U independent 16-byte loads per lane
-    float4 x[U];
+    const bool full = base + GROUP <= p.n_rows;
+    const char* gp = p.rows + (base + half) * p.row_stride + lir * 16;
+    // ---- U*CPL independent 16-byte loads per lane
+    float4 x[U][CPL];
 #pragma unroll
     for (int i = 0; i < U; ++i) {
-      const int64_t row = base + i * RPW + half;
-      if (has_chunk && row < p.n_rows)
-        x[i] = ldg_stream(p.rows + row * p.row_stride + lir * 16);
-      else
-        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        if (has_chunk[c] && (full || base + i * RPW + half < p.n_rows))
+          x[i][c] = ldg_stream(gp + (int64_t)i * RPW * p.row_stride + c * (L * 16));
+        else
+          x[i][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     double v[V];
-    uint32_t bad = 0;  // bit i: a non-finite value reached a model input in row slot i
 #pragma unroll
     for (int i = 0; i < U; ++i) {
-      float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+      float xs[CPL * 4];
       double a[NS];
 #pragma unroll
       for (int k = 0; k < NS; ++k) a[k] = 0.0;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float xv = xs[u];
-        xv = (xv != xv) ? fill[u] : xv;  // Imputer (fill is NaN where the column has none)
-        xs[u] = xv;
-        const bool cp = (copied >> u) & 1u;
-        if (cp && !is_finite_f(xv)) bad |= (1u << i);
-        const double xd = cp ? (double)xv : 0.0;
+      for (int c = 0; c < CPL; ++c) {
+        const float xr[4] = {x[i][c].x, x[i][c].y, x[i][c].z, x[i][c].w};
 #pragma unroll
-        for (int k = 0; k < NS; ++k) a[k] = fma(w[u][k], xd, a[k]);
+        for (int u = 0; u < 4; ++u) {
+          float xv = xr[u];
+          xv = (xv != xv) ? fill[c][u] : xv;  // Imputer (fill is NaN where the column has none)
+          xs[c * 4 + u] = xv;
+          const double xd = ((copied[c] >> u) & 1u) ? (double)xv : 0.0;
+#pragma unroll
+          for (int k = 0; k < NS; ++k) a[k] = fma(w[c][u][k], xd, a[k]);
+        }
       }
       if (CS > 0 && p.n_cat_slots > 0) {
-        // hand the categorical columns of this row to the lanes of the row, one component per round
+        // hand the categorical columns of this row to the lanes of the row, one value position per round
 #pragma unroll
         for (int s = 0; s < CS; ++s) {
           float xc = 0.f;
+          const int src_lane = half * L + (cat_lane[s] < 0 ? 0 : cat_lane[s]);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float t = __shfl_sync(0xffffffffu, xs[c], half * L + (cat_src[s] < 0 ? 0 : cat_src[s]));
-            if (cat_comp[s] == c) xc = t;
+          for (int c = 0; c < CPL * 4; ++c) {
+            const float t = __shfl_sync(0xffffffffu, xs[c], src_lane);
+            if (cat_sel[s] == c) xc = t;
           }
-          if (cat_src[s] >= 0) {
-            int j = -1;
-            for (int jj = 0; jj < cat_n[s]; ++jj)
-              if (xc == s_catval[cat_base[s] + jj]) j = jj;  // categories are de-duplicated: one match at most
-            if (j >= 0) {
-              const double* wc = s_wcat + (size_t)(cat_base[s] + j) * NS;
+          int j = -1;
+          if (cat_n[s] <= KC) {  // categories cached in registers (NaN padding never matches)
 #pragma unroll
-              for (int k = 0; k < NS; ++k) a[k] += wc[k];
-            }
+            for (int q = KC - 1; q >= 0; --q) j = (xc == cat_c[s][q]) ? q : j;
+          } else if (cat_lane[s] >= 0) {
+            for (int q = 0; q < cat_n[s]; ++q)
+              if (xc == s_catval[cat_base[s] + q]) j = q;  // categories are de-duplicated: one match at most
+          }
+          if (j >= 0) {
+            const double* wc = s_wcat + (size_t)(cat_base[s] + j) * NS;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) a[k] += wc[k];
           }
         }
       }
@@ -177,7 +198,7 @@ __global__ void __launch_bounds__(256) rowwarp_kernel(const __grid_constant__ RW
     }
     // ---- reduce-scatter butterfly over the L lanes of a row (fp64)
     {
-      int n = VH;
+      int n = V;
 #pragma unroll
       for (int off = L / 2; off >= 1; off >>= 1) {
         if (n > 1) {
@@ -197,17 +218,12 @@ __global__ void __launch_bounds__(256) rowwarp_kernel(const __grid_constant__ RW
         }
       }
     }
-    // non-finite flags of every row slot, for all lanes at once
-    uint32_t badmask[U];
-#pragma unroll
-    for (int i = 0; i < U; ++i) badmask[i] = __ballot_sync(0xffffffffu, (bad >> i) & 1u);
-    uint32_t my_bad = 0;
-#pragma unroll
-    for (int i = 0; i < U; ++i)
-      if (i == own_i) my_bad = (badmask[i] >> (half * L)) & (L == 32 ? 0xffffffffu : ((1u << L) - 1u));
-
     const int64_t my_row = base + own_i * RPW + half;
     double s = v[0] + my_bias;
+    // a row is bad when any of its scores is non-finite; the NS score lanes of a row sit REP apart
+    uint32_t my_bad = is_finite_d(s) ? 0u : 1u;
+#pragma unroll
+    for (int off = 1; off < NS; off <<= 1) my_bad |= __shfl_xor_sync(0xffffffffu, my_bad, off * REP);
     if (p.fast_epilogue) {
       // identity links, one score per model: VOTE_NONE writes every score, VOTE_MEAN sums w_k * s_k
       if (p.vote_kind == 1) {
@@ -217,12 +233,12 @@ __global__ void __launch_bounds__(256) rowwarp_kernel(const __grid_constant__ RW
         for (int off = 1; off < NS; off <<= 1) s += shfl_xor_d(s, off * REP);
         if (own_k == 0 && (lir % REP) == 0 && my_row < p.n_rows) {
           p.out[my_row] = (float)s;
-          if (p.status) p.status[my_row] = my_bad ? 1 : 0;
+          if (p.status) p.status[my_row] = (int32_t)my_bad;
         }
       } else {
         if ((lir % REP) == 0 && own_k < p.n_models && my_row < p.n_rows) {
           p.out[my_row * p.out_cols + own_k] = (float)s;
-          if (p.status && own_k == 0) p.status[my_row] = my_bad ? 1 : 0;
+          if (p.status && own_k == 0) p.status[my_row] = (int32_t)my_bad;
         }
       }
     } else {
@@ -244,7 +260,7 @@ __global__ void __launch_bounds__(256) rowwarp_kernel(const __grid_constant__ RW
         kp.out_is_int = p.out_is_int;
         kp.vote_w = p.vote_w;
         kp.status = p.status;
-        vote_and_store(kp, pred, my_row, my_bad ? 1u : 0u);
+        vote_and_store(kp, pred, my_row, my_bad);
       }
     }
   }

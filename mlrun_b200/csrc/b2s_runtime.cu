@@ -114,7 +114,7 @@ struct b2s_plan_s {
   int kernels_per_batch = 1;
   // row-warp kernel (register-resident linear path)
   bool rw_ok = false;
-  int rw_L = 0, rw_NS = 0, rw_U = 0, rw_CS = 0, rw_grid = 0, rw_smem = 0;
+  int rw_L = 0, rw_CPL = 1, rw_NS = 0, rw_U = 0, rw_CS = 0, rw_grid = 0, rw_smem = 0;
   RWParams rw{};
   // host staging for run_host
   char* h_stage_in = nullptr;
@@ -177,24 +177,33 @@ static cudaError_t launch_plan(b2s_plan_s* p, const KParams& kp, int grid, int b
   return cudaErrorInvalidValue;
 }
 
-template <int L, int NS, int CS>
+constexpr int rw_u(int L, int CPL, int NS) {
+  // row slots in flight per lane: bounded by the butterfly (U*NS <= L) and by the register budget
+  int cap = (NS >= 8 ? 2 : (NS >= 4 ? 4 : 8)) / CPL;
+  int u = L / NS < cap ? L / NS : cap;
+  return u < 1 ? 1 : u;
+}
+
+template <int L, int CPL, int NS, int CS>
 static cudaError_t launch_rw_t(const RWParams& rp, int grid, int smem, cudaStream_t st, bool query, int* occ) {
-  constexpr int U0 = L / NS < 1 ? 1 : L / NS;
-  constexpr int U = U0 > 8 ? 8 : U0;
-  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowwarp_kernel<L, NS, U, CS>, 256, smem);
-  rowwarp_kernel<L, NS, U, CS><<<grid, 256, smem, st>>>(rp);
+  constexpr int U = rw_u(L, CPL, NS);
+  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowwarp_kernel<L, CPL, NS, U, CS>, 128, smem);
+  rowwarp_kernel<L, CPL, NS, U, CS><<<grid, 128, smem, st>>>(rp);
   return cudaGetLastError();
 }
 
-static cudaError_t launch_rw(int L, int NS, int CS, const RWParams& rp, int grid, int smem, cudaStream_t st,
+static cudaError_t launch_rw(int L, int CPL, int NS, int CS, const RWParams& rp, int grid, int smem, cudaStream_t st,
                              bool query = false, int* occ = nullptr) {
-#define RW_CASE(l, n, c) \
-  if (L == l && NS == n && CS == c) return launch_rw_t<l, n, c>(rp, grid, smem, st, query, occ);
-#define RW_NS(l, c) RW_CASE(l, 1, c) RW_CASE(l, 2, c) RW_CASE(l, 4, c) RW_CASE(l, 8, c)
-#define RW_L(c) RW_NS(8, c) RW_NS(16, c) RW_NS(32, c)
-  RW_L(0) RW_L(1) RW_L(2)
-#undef RW_L
-#undef RW_NS
+#define RW_CASE(l, cp, n, c) \
+  if (L == l && CPL == cp && NS == n && CS == c) return launch_rw_t<l, cp, n, c>(rp, grid, smem, st, query, occ);
+#define RW_SHAPES(c)                                                                          \
+  RW_CASE(8, 1, 1, c) RW_CASE(8, 1, 2, c) RW_CASE(8, 1, 4, c) RW_CASE(8, 1, 8, c)             \
+  RW_CASE(8, 2, 1, c) RW_CASE(8, 2, 2, c) RW_CASE(8, 2, 4, c)                                 \
+  RW_CASE(16, 1, 8, c)                                                                        \
+  RW_CASE(16, 2, 1, c) RW_CASE(16, 2, 2, c) RW_CASE(16, 2, 4, c)                              \
+  RW_CASE(32, 1, 8, c)
+  RW_SHAPES(0) RW_SHAPES(1) RW_SHAPES(2)
+#undef RW_SHAPES
 #undef RW_CASE
   return cudaErrorInvalidValue;
 }
@@ -551,7 +560,14 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
   std::vector<int32_t> rw_csrc, rw_ccomp, rw_cbase, rw_cn;
   {
     const int nch = (n_in + 3) / 4;
-    int L = nch <= 8 ? 8 : (nch <= 16 ? 16 : 32);
+    int L, CPL;
+    if (NS <= 4) {
+      L = nch <= 16 ? 8 : 16;
+      CPL = nch <= 8 ? 1 : 2;
+    } else {
+      L = nch <= 8 ? 8 : (nch <= 16 ? 16 : 32);
+      CPL = 1;
+    }
     std::vector<int> cat_cols;
     int max_cats = 0;
     if (p->mode == MODE_LINEAR)
@@ -562,18 +578,23 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
         }
     const int CS = (int)((cat_cols.size() + L - 1) / L);
     const bool env_off = getenv("B2S_NO_ROWWARP") != nullptr;
-    if (!env_off && p->mode == MODE_LINEAR && !any_map && (n_in % 4) == 0 && nch <= 32 && NS <= 8 && NS <= L && CS <= 2 && max_cats <= 64) {
+    if (!env_off && p->mode == MODE_LINEAR && !any_map && (n_in % 4) == 0 && nch <= L * CPL && NS <= 8 && CS <= 2 && max_cats <= 64) {
       p->rw_ok = true;
       p->rw_L = L;
+      p->rw_CPL = CPL;
       p->rw_NS = NS;
       p->rw_CS = CS;
-      rw_fill.assign((size_t)L * 4, std::numeric_limits<float>::quiet_NaN());
-      rw_copied.assign(L, 0);
-      rw_w.assign((size_t)L * 4 * NS, 0.0);
+      p->rw_U = rw_u(L, CPL, NS);
+      const int npos = L * CPL;
+      rw_fill.assign((size_t)npos * 4, std::numeric_limits<float>::quiet_NaN());
+      rw_copied.assign(npos, 0);
+      rw_w.assign((size_t)npos * 4 * NS, 0.0);
+      auto pos_of = [&](int c) { const int ch = c / 4; return (ch / L) * L + (ch % L); };
       for (int c = 0; c < n_in; ++c) {
-        rw_fill[c] = p->fill[c];
-        if (flags[c] & COL_COPIED) rw_copied[c / 4] |= (1u << (c % 4));
-        for (int kk = 0; kk < NS; ++kk) rw_w[(size_t)c * NS + kk] = wnum[(size_t)c * NS + kk];
+        const int pos = pos_of(c), u = c % 4;
+        rw_fill[(size_t)pos * 4 + u] = p->fill[c];
+        if (flags[c] & COL_COPIED) rw_copied[pos] |= (1u << u);
+        for (int kk = 0; kk < NS; ++kk) rw_w[((size_t)pos * 4 + u) * NS + kk] = wnum[(size_t)c * NS + kk];
       }
       const int slots = std::max(CS, 1);
       rw_csrc.assign((size_t)slots * L, -1);
@@ -583,7 +604,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       for (size_t i = 0; i < cat_cols.size(); ++i) {
         const int c = cat_cols[i];
         const size_t at = (i / L) * L + (i % L);
-        rw_csrc[at] = c / 4;
+        rw_csrc[at] = pos_of(c);
         rw_ccomp[at] = c % 4;
         rw_cbase[at] = cat_off[c];
         rw_cn[at] = cat_off[c + 1] - cat_off[c];
@@ -760,7 +781,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
     r.classes = k.classes;
     p->rw_smem = (int)(align_up((size_t)r.n_cat * 4, 16) + (size_t)std::max(r.n_cat, 1) * NS * 8 + 16);
     int occ = 0;
-    cudaError_t e = launch_rw(p->rw_L, p->rw_NS, p->rw_CS, r, 0, p->rw_smem, nullptr, true, &occ);
+    cudaError_t e = launch_rw(p->rw_L, p->rw_CPL, p->rw_NS, p->rw_CS, r, 0, p->rw_smem, nullptr, true, &occ);
     if (e != cudaSuccess || occ < 1) {
       cudaGetLastError();
       p->rw_ok = false;
@@ -799,11 +820,11 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
     r.out = (float*)d_out;
     r.status = d_status;
     const int rpw = 32 / p->rw_L;
-    const int u = std::min(8, std::max(1, p->rw_L / p->rw_NS));
+    const int u = p->rw_U;
     const int64_t groups = (n_rows + (int64_t)u * rpw - 1) / ((int64_t)u * rpw);
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->rw_grid, (groups + 7) / 8));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->rw_grid, (groups + 3) / 4));
     G.launches.fetch_add(1, std::memory_order_relaxed);
-    cudaError_t e = launch_rw(p->rw_L, p->rw_NS, p->rw_CS, r, grid, p->rw_smem, st);
+    cudaError_t e = launch_rw(p->rw_L, p->rw_CPL, p->rw_NS, p->rw_CS, r, grid, p->rw_smem, st);
     if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "row-warp kernel launch failed: %s", cudaGetErrorString(e));
     return B2S_OK;
   }
