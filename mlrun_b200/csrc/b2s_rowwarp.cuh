@@ -47,6 +47,7 @@ struct RWParams {
   const ModelDesc* models;
   const int32_t* classes;
   int32_t n_cat;
+  uint32_t cat_pos_mask;  // bit (slot*4+comp): some lane holds a categorical column at that chunk position
 };
 
 __device__ __forceinline__ float4 ldg_stream(const void* p) {
@@ -73,7 +74,7 @@ __device__ __forceinline__ bool is_finite_d(double x) { return fabs(x) <= 1.7976
 
 // L lanes per row, CPL chunks per lane, NS score slots, U row slots in flight, CS categorical slots per lane
 template <int L, int CPL, int NS, int U, int CS>
-__global__ void __launch_bounds__(128, 4) rowwarp_kernel(const __grid_constant__ RWParams p) {
+__global__ void __launch_bounds__(128, 3) rowwarp_kernel(const __grid_constant__ RWParams p) {
   constexpr int RPW = 32 / L;  // rows per warp instruction
   constexpr int V = U * NS;    // partial sums per lane
   static_assert(V <= L, "U is chosen so that U*NS <= L");
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(128, 4) rowwarp_kernel(const __grid_constant__
   double* s_wcat = reinterpret_cast<double*>(smem + ((p.n_cat * 4 + 15) / 16) * 16);
   for (int i = threadIdx.x; i < p.n_cat; i += blockDim.x) s_catval[i] = p.cat_val[i];
   for (int i = threadIdx.x; i < p.n_cat * NS; i += blockDim.x) s_wcat[i] = p.wcat[i];
+  for (int i = threadIdx.x; i < NS; i += blockDim.x) s_wcat[p.n_cat * NS + i] = 0.0;
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -96,15 +98,15 @@ __global__ void __launch_bounds__(128, 4) rowwarp_kernel(const __grid_constant__
   // ---- per-lane constants, resident in registers for the whole kernel
   float fill[CPL][4];
   double w[CPL][4][NS];
-  uint32_t copied[CPL];
+  uint32_t cmask[CPL][4];  // all-ones where the column feeds a COPY output, else 0 (x & 0 = +0.0f)
   bool has_chunk[CPL];
 #pragma unroll
   for (int c = 0; c < CPL; ++c) {
     const int pos = c * L + lir;
     has_chunk[c] = pos < p.nch;
-    copied[c] = p.copied[pos];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
+      cmask[c][u] = ((p.copied[pos] >> u) & 1u) ? 0xffffffffu : 0u;
       fill[c][u] = p.fill[pos * 4 + u];
 #pragma unroll
       for (int k = 0; k < NS; ++k) w[c][u][k] = p.w[(pos * 4 + u) * NS + k];
@@ -131,22 +133,34 @@ __global__ void __launch_bounds__(128, 4) rowwarp_kernel(const __grid_constant__
   const int warps_per_block = blockDim.x >> 5;
   const int64_t n_groups = (p.n_rows + GROUP - 1) / GROUP;
   const int64_t gstride = (int64_t)gridDim.x * warps_per_block;
-  for (int64_t g = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); g < n_groups; g += gstride) {
+  const int64_t row_step = (int64_t)RPW * p.row_stride;
+  // U*CPL independent 16-byte loads per lane; the next group's loads are issued before this group's math
+  auto load_group = [&](int64_t g, float4 (&dst)[U][CPL]) {
     const int64_t base = g * GROUP;
     const bool full = base + GROUP <= p.n_rows;
     const char* gp = p.rows + (base + half) * p.row_stride + lir * 16;
-    // ---- U*CPL independent 16-byte loads per lane
-    float4 x[U][CPL];
 #pragma unroll
     for (int i = 0; i < U; ++i) {
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
         if (has_chunk[c] && (full || base + i * RPW + half < p.n_rows))
-          x[i][c] = ldg_stream(gp + (int64_t)i * RPW * p.row_stride + c * (L * 16));
+          dst[i][c] = ldg_stream(gp + i * row_step + c * (L * 16));
         else
-          x[i][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          dst[i][c] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+  };
+  int64_t g = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  float4 xn[U][CPL];
+  if (g < n_groups) load_group(g, xn);
+  for (; g < n_groups; g += gstride) {
+    const int64_t base = g * GROUP;
+    float4 x[U][CPL];
+#pragma unroll
+    for (int i = 0; i < U; ++i)
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) x[i][c] = xn[i][c];
+    if (g + gstride < n_groups) load_group(g + gstride, xn);
     double v[V];
 #pragma unroll
     for (int i = 0; i < U; ++i) {
@@ -162,7 +176,7 @@ __global__ void __launch_bounds__(128, 4) rowwarp_kernel(const __grid_constant__
           float xv = xr[u];
           xv = (xv != xv) ? fill[c][u] : xv;  // Imputer (fill is NaN where the column has none)
           xs[c * 4 + u] = xv;
-          const double xd = ((copied[c] >> u) & 1u) ? (double)xv : 0.0;
+          const double xd = (double)__uint_as_float(__float_as_uint(xv) & cmask[c][u]);
 #pragma unroll
           for (int k = 0; k < NS; ++k) a[k] = fma(w[c][u][k], xd, a[k]);
         }
@@ -175,22 +189,22 @@ __global__ void __launch_bounds__(128, 4) rowwarp_kernel(const __grid_constant__
           const int src_lane = half * L + (cat_lane[s] < 0 ? 0 : cat_lane[s]);
 #pragma unroll
           for (int c = 0; c < CPL * 4; ++c) {
-            const float t = __shfl_sync(0xffffffffu, xs[c], src_lane);
-            if (cat_sel[s] == c) xc = t;
+            if ((p.cat_pos_mask >> c) & 1u) {  // warp-uniform: skip positions without categorical columns
+              const float t = __shfl_sync(0xffffffffu, xs[c], src_lane);
+              if (cat_sel[s] == c) xc = t;
+            }
           }
-          int j = -1;
+          int j = p.n_cat;  // row n_cat of s_wcat is all zeros: "no category matched" (or no column here)
           if (cat_n[s] <= KC) {  // categories cached in registers (NaN padding never matches)
 #pragma unroll
-            for (int q = KC - 1; q >= 0; --q) j = (xc == cat_c[s][q]) ? q : j;
+            for (int q = KC - 1; q >= 0; --q) j = (xc == cat_c[s][q]) ? cat_base[s] + q : j;
           } else if (cat_lane[s] >= 0) {
             for (int q = 0; q < cat_n[s]; ++q)
-              if (xc == s_catval[cat_base[s] + q]) j = q;  // categories are de-duplicated: one match at most
+              if (xc == s_catval[cat_base[s] + q]) j = cat_base[s] + q;  // de-duplicated: one match at most
           }
-          if (j >= 0) {
-            const double* wc = s_wcat + (size_t)(cat_base[s] + j) * NS;
+          const double* wc = s_wcat + (size_t)j * NS;
 #pragma unroll
-            for (int k = 0; k < NS; ++k) a[k] += wc[k];
-          }
+          for (int k = 0; k < NS; ++k) a[k] += wc[k];
         }
       }
 #pragma unroll

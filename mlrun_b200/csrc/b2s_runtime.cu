@@ -558,6 +558,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
   std::vector<uint32_t> rw_copied;
   std::vector<double> rw_w;
   std::vector<int32_t> rw_csrc, rw_ccomp, rw_cbase, rw_cn;
+  uint32_t rw_cat_pos_mask = 0;
   {
     const int nch = (n_in + 3) / 4;
     int L, CPL;
@@ -605,6 +606,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
         const int c = cat_cols[i];
         const size_t at = (i / L) * L + (i % L);
         rw_csrc[at] = pos_of(c);
+        rw_cat_pos_mask |= 1u << ((pos_of(c) / L) * 4 + (c % 4));
         rw_ccomp[at] = c % 4;
         rw_cbase[at] = cat_off[c];
         rw_cn[at] = cat_off[c + 1] - cat_off[c];
@@ -779,7 +781,8 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
     r.vote_w = k.vote_w;
     r.models = k.models;
     r.classes = k.classes;
-    p->rw_smem = (int)(align_up((size_t)r.n_cat * 4, 16) + (size_t)std::max(r.n_cat, 1) * NS * 8 + 16);
+    p->rw_smem = (int)(align_up((size_t)r.n_cat * 4, 16) + (size_t)(r.n_cat + 1) * NS * 8 + 16);
+    r.cat_pos_mask = rw_cat_pos_mask;
     int occ = 0;
     cudaError_t e = launch_rw(p->rw_L, p->rw_CPL, p->rw_NS, p->rw_CS, r, 0, p->rw_smem, nullptr, true, &occ);
     if (e != cudaSuccess || occ < 1) {
