@@ -136,18 +136,31 @@ __device__ __forceinline__ void issue_tile(const KParams& p, float* tile, int64_
   int64_t left = p.n_rows - row0;
   int rows = left < p.tile_rows ? (left < 0 ? 0 : (int)left) : p.tile_rows;
   const char* base = p.rows + row0 * p.row_stride;
+  // (row, chunk) walk without per-iteration division
   if (p.vec_ok) {
     const int cpr = p.n_in >> 2;  // 16-byte chunks per row
-    const int total = rows * cpr;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      int r = i / cpr, c = i - r * cpr;
+    int r = threadIdx.x / cpr, c = threadIdx.x - r * cpr;
+    const int dr = blockDim.x / cpr, dc = blockDim.x - dr * cpr;
+    while (r < rows) {
       cp_async16(tile + r * p.pitch + c * 4, base + (int64_t)r * p.row_stride + c * 16);
+      r += dr;
+      c += dc;
+      if (c >= cpr) {
+        c -= cpr;
+        ++r;
+      }
     }
   } else {
-    const int total = rows * p.n_in;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      int r = i / p.n_in, c = i - r * p.n_in;
+    int r = threadIdx.x / p.n_in, c = threadIdx.x - r * p.n_in;
+    const int dr = blockDim.x / p.n_in, dc = blockDim.x - dr * p.n_in;
+    while (r < rows) {
       cp_async4(tile + r * p.pitch + c, base + (int64_t)r * p.row_stride + c * 4);
+      r += dr;
+      c += dc;
+      if (c >= p.n_in) {
+        c -= p.n_in;
+        ++r;
+      }
     }
   }
 }

@@ -22,6 +22,7 @@
 #include "../../include/b200serve.h"
 #include "b2s_device.cuh"
 #include "b2s_rowwarp.cuh"
+#include "b2s_rowthread.cuh"
 
 using namespace b2s;
 
@@ -116,6 +117,10 @@ struct b2s_plan_s {
   bool rw_ok = false;
   int rw_L = 0, rw_CPL = 1, rw_NS = 0, rw_U = 0, rw_CS = 0, rw_grid = 0, rw_smem = 0;
   RWParams rw{};
+  // row-thread kernel (constant-bank operands)
+  bool rt_ok = false;
+  int rt_NCH = 0, rt_NS = 0, rt_grid = 0, rt_smem = 0, rt_tile_rows = 128, rt_pitch = 0, rt_stages = 2;
+  std::vector<char> rt_blob;  // an RTParams<NCH, NS>
   // host staging for run_host
   char* h_stage_in = nullptr;
   char* h_stage_out = nullptr;
@@ -206,6 +211,123 @@ static cudaError_t launch_rw(int L, int CPL, int NS, int CS, const RWParams& rp,
 #undef RW_SHAPES
 #undef RW_CASE
   return cudaErrorInvalidValue;
+}
+
+struct RTTables {  // what rt_build needs from finalize
+  int n_in, n_out_cols, n_models, vote_kind, out_is_int, fast_epilogue, NS;
+  const std::vector<float>* fill;
+  const std::vector<uint32_t>* flags;
+  const std::vector<double>* wnum;  // [n_in][NS]
+  const std::vector<double>* bias;
+  const std::vector<double>* vote_w;
+  const std::vector<int32_t>* cat_off;
+  const std::vector<float>* cat_val;
+  const double* d_wcat;
+  const double* d_vote_w;
+  const ModelDesc* d_models;
+  const int32_t* d_classes;
+};
+
+template <int NCH, int NS>
+static void rt_build(b2s_plan_s* p, const RTTables& t) {
+  using P = RTParams<NCH, NS>;
+  p->rt_blob.assign(sizeof(P), 0);
+  P& r = *reinterpret_cast<P*>(p->rt_blob.data());
+  r.n_in = t.n_in;
+  r.out_cols = t.n_out_cols;
+  r.n_models = t.n_models;
+  r.vote_kind = t.vote_kind;
+  r.out_is_int = t.out_is_int;
+  r.fast_epilogue = t.fast_epilogue;
+  r.wcat = t.d_wcat;
+  r.vote_w_g = t.d_vote_w;
+  r.models = t.d_models;
+  r.classes = t.d_classes;
+  for (int c = 0; c < NCH * 4; ++c) {
+    r.fill[c] = std::numeric_limits<float>::quiet_NaN();
+    r.cmask[c] = 0;
+    for (int k = 0; k < NS; ++k) r.w[c][k] = 0.0;
+  }
+  for (int c = 0; c < t.n_in; ++c) {
+    r.fill[c] = (*t.fill)[c];
+    r.cmask[c] = ((*t.flags)[c] & COL_COPIED) ? 0xffffffffu : 0u;
+    for (int k = 0; k < NS; ++k) r.w[c][k] = (*t.wnum)[(size_t)c * NS + k];
+  }
+  for (int k = 0; k < NS; ++k) {
+    r.bias[k] = k < (int)t.bias->size() ? (*t.bias)[k] : 0.0;
+    r.vote_w[k] = k < (int)t.vote_w->size() ? (*t.vote_w)[k] : 0.0;
+  }
+  int ncc = 0;
+  for (int c = 0; c < t.n_in; ++c)
+    if ((*t.cat_off)[c + 1] > (*t.cat_off)[c]) {
+      r.cat_col[ncc] = c;
+      r.cat_base[ncc] = (*t.cat_off)[c];
+      r.cat_cnt[ncc] = (*t.cat_off)[c + 1] - (*t.cat_off)[c];
+      ++ncc;
+    }
+  r.n_cat_cols = ncc;
+  r.n_cat = (int)t.cat_val->size();
+  for (int i = 0; i < r.n_cat; ++i) r.cat_val[i] = (*t.cat_val)[i];
+}
+
+template <int NCH, int NS>
+static cudaError_t rt_launch_t(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
+                               int vec_ok, cudaStream_t st, bool query, int* occ) {
+  using P = RTParams<NCH, NS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)G.prop.sharedMemPerBlockOptin);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS>, 128, p->rt_smem);
+  P r = *reinterpret_cast<const P*>(p->rt_blob.data());
+  r.rows = (const char*)rows;
+  r.row_stride = stride;
+  r.n_rows = n_rows;
+  r.out = (float*)out;
+  r.status = status;
+  r.vec_ok = vec_ok;
+  r.pitch = p->rt_pitch;
+  r.stages = p->rt_stages;
+  int tr = p->rt_tile_rows;
+  while (tr > 32 && (n_rows + tr - 1) / tr < (int64_t)G.prop.multiProcessorCount) tr /= 2;
+  r.tile_rows = tr;
+  const int64_t tiles = (n_rows + tr - 1) / tr;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->rt_grid, tiles));
+  rowthread_kernel<NCH, NS><<<grid, tr, p->rt_smem, st>>>(r);
+  return cudaGetLastError();
+}
+
+#define RT_DISPATCH(FN, ...)                                                              \
+  do {                                                                                    \
+    const int nch_ = p->rt_NCH, ns_ = p->rt_NS;                                           \
+    if (nch_ == 4 && ns_ == 1) return FN<4, 1>(__VA_ARGS__);                              \
+    if (nch_ == 4 && ns_ == 2) return FN<4, 2>(__VA_ARGS__);                              \
+    if (nch_ == 4 && ns_ == 4) return FN<4, 4>(__VA_ARGS__);                              \
+    if (nch_ == 4 && ns_ == 8) return FN<4, 8>(__VA_ARGS__);                              \
+    if (nch_ == 8 && ns_ == 1) return FN<8, 1>(__VA_ARGS__);                              \
+    if (nch_ == 8 && ns_ == 2) return FN<8, 2>(__VA_ARGS__);                              \
+    if (nch_ == 8 && ns_ == 4) return FN<8, 4>(__VA_ARGS__);                              \
+    if (nch_ == 8 && ns_ == 8) return FN<8, 8>(__VA_ARGS__);                              \
+    if (nch_ == 16 && ns_ == 1) return FN<16, 1>(__VA_ARGS__);                            \
+    if (nch_ == 16 && ns_ == 2) return FN<16, 2>(__VA_ARGS__);                            \
+    if (nch_ == 16 && ns_ == 4) return FN<16, 4>(__VA_ARGS__);                            \
+    if (nch_ == 16 && ns_ == 8) return FN<16, 8>(__VA_ARGS__);                            \
+    if (nch_ == 32 && ns_ == 1) return FN<32, 1>(__VA_ARGS__);                            \
+    if (nch_ == 32 && ns_ == 2) return FN<32, 2>(__VA_ARGS__);                            \
+    if (nch_ == 32 && ns_ == 4) return FN<32, 4>(__VA_ARGS__);                            \
+    if (nch_ == 32 && ns_ == 8) return FN<32, 8>(__VA_ARGS__);                            \
+  } while (0)
+
+static cudaError_t rt_launch(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
+                             int vec_ok, cudaStream_t st, bool query = false, int* occ = nullptr) {
+  RT_DISPATCH(rt_launch_t, p, rows, stride, n_rows, out, status, vec_ok, st, query, occ);
+  return cudaErrorInvalidValue;
+}
+static void rt_build_any(b2s_plan_s* p, const RTTables& t) {
+  RT_DISPATCH(rt_build, p, t);
 }
 
 // ------------------------------------------------------------------------------------------ C-ABI: library
@@ -792,6 +914,38 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       p->rw_grid = sms * occ;
     }
   }
+  {
+    const char* pick = getenv("B2S_LINEAR_KERNEL");  // rowthread (default) | rowwarp | generic  (A/B runs)
+    const std::string want = pick ? pick : "rowthread";
+    int n_cat_cols = 0;
+    for (int c = 0; c < n_in; ++c) n_cat_cols += (cat_off[c + 1] > cat_off[c]) ? 1 : 0;
+    if (want != "rowwarp") p->rw_ok = p->rw_ok && (want == "rowwarp");
+    if (want == "rowthread" && p->mode == MODE_LINEAR && !any_map && n_in <= 128 && NS <= 8 &&
+        n_cat_cols <= kRTMaxCatCols && (int)cat_val.size() <= kRTMaxCats) {
+      const int nch = (n_in + 3) / 4;
+      p->rt_NCH = nch <= 4 ? 4 : (nch <= 8 ? 8 : (nch <= 16 ? 16 : 32));
+      p->rt_NS = NS;
+      bool simple = true;
+      for (auto& m : p->models) simple = simple && m.link == B2S_LINK_IDENTITY && m.n_scores == 1;
+      RTTables t{n_in, p->out_cols, M, p->vote_kind, p->out_is_int, (simple && p->vote_kind != B2S_VOTE_MAJORITY) ? 1 : 0, NS,
+                 &p->fill, &flags, &wnum, &bias, &p->vote_w, &cat_off, &cat_val, k.wcat, k.vote_w, k.models, k.classes};
+      rt_build_any(p, t);
+      int rpitch = p->rt_NCH * 4 + 4;
+      if (((rpitch / 4) & 1) == 0) rpitch += 4;
+      p->rt_pitch = rpitch;
+      const char* stg = getenv("B2S_RT_STAGES");
+      p->rt_stages = stg ? std::max(2, std::min(4, atoi(stg))) : 2;
+      p->rt_tile_rows = 128;
+      p->rt_smem = (int)(align_up((size_t)(cat_val.size() + 1) * NS * 8, 16) + (size_t)p->rt_stages * 128 * rpitch * 4);
+      int occ = 0;
+      if (p->rt_smem <= smem_cap && rt_launch(p, nullptr, 0, 0, nullptr, nullptr, 0, nullptr, true, &occ) == cudaSuccess && occ >= 1) {
+        p->rt_ok = true;
+        p->rt_grid = sms * occ;
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
   for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&p->ev[i]));
   p->finalized = true;
   return B2S_OK;
@@ -815,6 +969,12 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
   k.out = (float*)d_out;
   k.status = d_status;
   k.vec_ok = ((p->n_in % 4) == 0 && (stride % 16) == 0 && ((uintptr_t)d_rows % 16) == 0) ? 1 : 0;
+  if (p->rt_ok) {
+    G.launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = rt_launch(p, d_rows, stride, n_rows, d_out, d_status, k.vec_ok, st);
+    if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "row-thread kernel launch failed: %s", cudaGetErrorString(e));
+    return B2S_OK;
+  }
   if (p->rw_ok && k.vec_ok) {
     RWParams r = p->rw;
     r.rows = (const char*)d_rows;
