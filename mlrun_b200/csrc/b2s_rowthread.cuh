@@ -1,22 +1,26 @@
-// b2s_rowthread.cuh -- linear path, one thread per event row, every table operand in the constant bank.
+// b2s_rowthread.cuh -- linear path: row slices per thread, every table operand in the constant bank.
 //
 //   HBM rows --cp.async 16 B (LDGSTS), STAGES-deep ring--> shared-memory tile, pitch = 16 mod 128 bytes
-//   thread r reads row r with conflict-free LDS.128 and runs a fully unrolled column loop whose
-//   per-column operands (Imputer fill, copy mask, the NS fp64 weights) are *immediate constant-bank
-//   operands* of the FSEL / LOP3 / DFMA instructions: the plan's tables travel as a __grid_constant__
-//   kernel parameter, so the inner loop has no table loads and no cross-lane traffic at all:
+//   TPR threads share one event row: thread (q, r) -- q = tid / tile_rows, so a warp is uniform in q --
+//   owns the 16-byte chunks [q*NCH/TPR, (q+1)*NCH/TPR) of row r, read with conflict-free LDS.128.
+//   The column loop is fully unrolled and its per-column operands (Imputer fill, copy mask, the NS fp64
+//   weights) are constant-bank operands: the plan's tables travel as a __grid_constant__ kernel
+//   parameter, so the inner loop has no table loads and no cross-lane traffic:
 //        FSETP+FSEL (NaN -> fill)   LOP3 (drop non-copied columns)   F2F   NS x DFMA     per value
-//   one-hot columns are a short second loop over the categorical columns (value re-read from the
-//   tile, category index by compares against constant-bank categories, weights gathered from shared
-//   memory; a zero row stands for "no category matched"); bias, link, vote and the 4-byte store are
-//   per-thread.  A non-finite model input surfaces as a non-finite score (NaN/Inf survive fma even
-//   with a zero weight), which is what the per-row status tests.
+//   one-hot columns: "onehot(x) . w" is the gather w[cat_base + index_of(x)] -- the value is re-read from
+//   the tile, the category index comes from compares against constant-bank categories, the weights
+//   from shared memory (a zero row stands for "no category matched"); the row is never expanded.
+//   The TPR partial sums of a row are combined in shared memory in a fixed order (deterministic fp64);
+//   bias, link, vote and the coalesced 4-byte store are done by the row's q = 0 thread.  A non-finite
+//   model input surfaces as a non-finite score (NaN/Inf survive fma even with a zero weight), which is
+//   what the per-row status tests.
 #pragma once
 #include "b2s_device.cuh"
 
 namespace b2s {
 
-constexpr int kRTMaxCatCols = 32;
+constexpr int kRTMaxCatCols = 16;
+constexpr int kRTCatsInline = 4;   // categories compared as constant operands
 constexpr int kRTMaxCats = 256;
 
 template <int NCH, int NS>
@@ -40,51 +44,93 @@ struct RTParams {
   int32_t cat_col[kRTMaxCatCols];   // input column of each categorical column
   int32_t cat_base[kRTMaxCatCols];  // first category (index into cat_val / wcat)
   int32_t cat_cnt[kRTMaxCatCols];
+  float cat_fill[kRTMaxCatCols];
+  float cat_inl[kRTMaxCatCols][kRTCatsInline];  // first categories, NaN padded (never match)
   float cat_val[kRTMaxCats];
 };
 
-template <int NCH, int NS>
-__global__ void __launch_bounds__(128) rowthread_kernel(const __grid_constant__ RTParams<NCH, NS> p) {
+// dot products of the chunks [CH0, CH1) of one row with all NS weight columns
+template <int NCH, int NS, int CH0, int CH1>
+__device__ __forceinline__ void rt_slice(const RTParams<NCH, NS>& p, const float* __restrict__ xr, double (&acc)[NS]) {
+  constexpr int BATCH = 4;  // chunks converted before their DFMAs are issued (ILP)
+#pragma unroll
+  for (int b = CH0; b < CH1; b += BATCH) {
+    double xd[BATCH * 4];
+#pragma unroll
+    for (int cb = 0; cb < BATCH; ++cb) {
+      const int ch = b + cb;
+      if (ch < CH1) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + ch * 4);
+        const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = ch * 4 + u;
+          float x = xs[u];
+          x = (x != x) ? p.fill[c] : x;                                               // Imputer
+          xd[cb * 4 + u] = (double)__uint_as_float(__float_as_uint(x) & p.cmask[c]);  // non-copied -> +0
+        }
+      }
+    }
+#pragma unroll
+    for (int cb = 0; cb < BATCH; ++cb) {
+      const int ch = b + cb;
+      if (ch < CH1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = ch * 4 + u;
+#pragma unroll
+          for (int k = 0; k < NS; ++k) acc[k] = fma(p.w[c][k], xd[cb * 4 + u], acc[k]);
+        }
+      }
+    }
+  }
+}
+
+template <int NCH, int NS, int TPR>
+__global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : 3) rowthread_kernel(const __grid_constant__ RTParams<NCH, NS> p) {
+  static_assert(NCH % TPR == 0, "chunks must split evenly over the row's threads");
+  constexpr int CPT = NCH / TPR;  // chunks per thread
   extern __shared__ __align__(16) unsigned char smem[];
   double* s_wcat = reinterpret_cast<double*>(smem);
-  float* s_tiles = reinterpret_cast<float*>(smem + (((size_t)(p.n_cat + 1) * NS * 8 + 15) / 16) * 16);
+  const size_t wcat_bytes = (((size_t)(p.n_cat + 1) * NS * 8 + 15) / 16) * 16;
+  double* s_part = reinterpret_cast<double*>(smem + wcat_bytes);  // [(TPR-1)][128][NS]
+  float* s_tiles = reinterpret_cast<float*>(smem + wcat_bytes + (size_t)(TPR - 1) * 128 * NS * 8);
 
   const int tid = threadIdx.x;
   const int TR = p.tile_rows;
   const int S = p.stages;
   const int tile_words = TR * p.pitch;
   const int64_t n_tiles = (p.n_rows + TR - 1) / TR;
+  const int q = tid / TR;       // slice of the row (warp-uniform: TR is a multiple of 32)
+  const int r = tid - q * TR;   // row inside the tile
 
-  const int cprv = p.n_in >> 2;  // 16-byte chunks per row
-  const int r0v = cprv ? tid / cprv : 0, c0v = cprv ? tid - r0v * cprv : 0;
-  const int drv = cprv ? (int)blockDim.x / cprv : 0, dcv = cprv ? (int)blockDim.x - drv * cprv : 0;
-  const int r0s = tid / p.n_in, c0s = tid - r0s * p.n_in;
-  const int drs = (int)blockDim.x / p.n_in, dcs = (int)blockDim.x - drs * p.n_in;
+  // (row, chunk) walk of the tile loader without per-iteration division
+  const int cprv = p.vec_ok ? (p.n_in >> 2) : p.n_in;  // units per row: 16-byte chunks or 4-byte words
+  const int r0 = tid / cprv, c0 = tid - r0 * cprv;
+  const int dr = (int)blockDim.x / cprv, dc = (int)blockDim.x - dr * cprv;
   auto issue = [&](float* tile, int64_t row0) {
     int64_t left = p.n_rows - row0;
     const int rows = left < TR ? (left < 0 ? 0 : (int)left) : TR;
     const char* base = p.rows + row0 * p.row_stride;
-    // (row, chunk) walk without per-iteration division: thread i starts at i and advances by blockDim.x
+    int rr = r0, cc = c0;
     if (p.vec_ok) {
-      int r = r0v, c = c0v;
-      while (r < rows) {
-        cp_async16(tile + r * p.pitch + c * 4, base + (int64_t)r * p.row_stride + c * 16);
-        r += drv;
-        c += dcv;
-        if (c >= cprv) {
-          c -= cprv;
-          ++r;
+      while (rr < rows) {
+        cp_async16(tile + rr * p.pitch + cc * 4, base + (int64_t)rr * p.row_stride + cc * 16);
+        rr += dr;
+        cc += dc;
+        if (cc >= cprv) {
+          cc -= cprv;
+          ++rr;
         }
       }
     } else {
-      int r = r0s, c = c0s;
-      while (r < rows) {
-        cp_async4(tile + r * p.pitch + c, base + (int64_t)r * p.row_stride + c * 4);
-        r += drs;
-        c += dcs;
-        if (c >= p.n_in) {
-          c -= p.n_in;
-          ++r;
+      while (rr < rows) {
+        cp_async4(tile + rr * p.pitch + cc, base + (int64_t)rr * p.row_stride + cc * 4);
+        rr += dr;
+        cc += dc;
+        if (cc >= cprv) {
+          cc -= cprv;
+          ++rr;
         }
       }
     }
@@ -103,7 +149,7 @@ __global__ void __launch_bounds__(128) rowthread_kernel(const __grid_constant__ 
     if (S == 2) cp_async_wait<0>();
     else if (S == 3) cp_async_wait<1>();
     else cp_async_wait<2>();
-    __syncthreads();
+    __syncthreads();  // tile visible to everybody; everybody is done with the previous tile and s_part
     {
       const int64_t tn = t + (int64_t)(S - 1) * gridDim.x;
       int sn = stage + S - 1;
@@ -112,41 +158,60 @@ __global__ void __launch_bounds__(128) rowthread_kernel(const __grid_constant__ 
       cp_async_commit();
     }
     const float* tile = s_tiles + stage * tile_words;
-    const int64_t row = t * TR + tid;
-    if (tid < TR && row < p.n_rows) {
-      const float* xr = tile + tid * p.pitch;
-      double acc[NS];
+    const int64_t row = t * TR + r;
+    const bool live = row < p.n_rows;
+    const float* xr = tile + r * p.pitch;
+    double acc[NS];
 #pragma unroll
-      for (int k = 0; k < NS; ++k) acc[k] = p.bias[k];
+    for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+    if (live) {
+      // the slice index is warp-uniform; each case has compile-time column indices (constant operands)
+      if (TPR == 1 || q == 0) rt_slice<NCH, NS, 0, CPT>(p, xr, acc);
+      else if (q == 1) rt_slice<NCH, NS, (TPR > 1 ? CPT : 0), (TPR > 1 ? 2 * CPT : 0)>(p, xr, acc);
+      else if (q == 2) rt_slice<NCH, NS, (TPR > 2 ? 2 * CPT : 0), (TPR > 2 ? 3 * CPT : 0)>(p, xr, acc);
+      else rt_slice<NCH, NS, (TPR > 3 ? 3 * CPT : 0), (TPR > 3 ? 4 * CPT : 0)>(p, xr, acc);
+      // one-hot columns, dealt round-robin to the row's threads
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        const float4 v = *reinterpret_cast<const float4*>(xr + ch * 4);
-        const float xs[4] = {v.x, v.y, v.z, v.w};
+      for (int cc = 0; cc < kRTMaxCatCols; ++cc) {
+        if (cc < p.n_cat_cols && (cc % TPR) == q) {
+          float x = xr[p.cat_col[cc]];
+          x = (x != x) ? p.cat_fill[cc] : x;
+          int j = p.n_cat;  // the zero row: no category matched
+          if (p.cat_cnt[cc] <= kRTCatsInline) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = ch * 4 + u;
-          float x = xs[u];
-          x = (x != x) ? p.fill[c] : x;                                           // Imputer
-          const double xd = (double)__uint_as_float(__float_as_uint(x) & p.cmask[c]);  // non-copied -> +0
+            for (int qq = kRTCatsInline - 1; qq >= 0; --qq) j = (x == p.cat_inl[cc][qq]) ? p.cat_base[cc] + qq : j;
+          } else {
+            for (int qq = 0; qq < p.cat_cnt[cc]; ++qq) j = (x == p.cat_val[p.cat_base[cc] + qq]) ? p.cat_base[cc] + qq : j;
+          }
+          const double* wc = s_wcat + (size_t)j * NS;
 #pragma unroll
-          for (int k = 0; k < NS; ++k) acc[k] = fma(p.w[c][k], xd, acc[k]);
+          for (int k = 0; k < NS; ++k) acc[k] += wc[k];
         }
       }
-      // one-hot columns: onehot(x) . w  ==  w[cat_base + index_of(x)]
-      for (int cc = 0; cc < p.n_cat_cols; ++cc) {
-        const int col = p.cat_col[cc];
-        float x = xr[col];
-        x = (x != x) ? p.fill[col] : x;
-        const int b0 = p.cat_base[cc], n = p.cat_cnt[cc];
-        int j = p.n_cat;  // the zero row: no category matched
-        for (int q = 0; q < n; ++q) j = (x == p.cat_val[b0 + q]) ? b0 + q : j;
-        const double* wc = s_wcat + (size_t)j * NS;
+    }
+    if (TPR > 1) {  // combine the row's slices in a fixed order (deterministic fp64 sum)
+      if (q > 0) {
+        double* part = s_part + ((size_t)(q - 1) * 128 + r) * NS;
 #pragma unroll
-        for (int k = 0; k < NS; ++k) acc[k] += wc[k];
+        for (int k = 0; k < NS; ++k) part[k] = acc[k];
       }
+      __syncthreads();
+      if (q == 0) {
+#pragma unroll
+        for (int qq = 1; qq < TPR; ++qq) {
+          const double* o = s_part + ((size_t)(qq - 1) * 128 + r) * NS;
+#pragma unroll
+          for (int k = 0; k < NS; ++k) acc[k] += o[k];
+        }
+      }
+    }
+    if (q == 0 && live) {
       uint32_t st = 0;
 #pragma unroll
-      for (int k = 0; k < NS; ++k) st |= (fabs(acc[k]) <= 1.7976931348623157e308) ? 0u : 1u;
+      for (int k = 0; k < NS; ++k) {
+        acc[k] += p.bias[k];
+        st |= (fabs(acc[k]) <= 1.7976931348623157e308) ? 0u : 1u;
+      }
       if (p.fast_epilogue) {
         if (p.vote_kind == 1) {  // VotingEnsemble._mean_vote: sum_m w[m] * pred[m], model order
           double s = 0.0;

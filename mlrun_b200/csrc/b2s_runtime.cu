@@ -228,6 +228,8 @@ struct RTTables {  // what rt_build needs from finalize
   const int32_t* d_classes;
 };
 
+constexpr int rt_tpr(int NCH) { return NCH >= 16 ? 4 : (NCH >= 8 ? 2 : 1); }
+
 template <int NCH, int NS>
 static void rt_build(b2s_plan_s* p, const RTTables& t) {
   using P = RTParams<NCH, NS>;
@@ -263,6 +265,9 @@ static void rt_build(b2s_plan_s* p, const RTTables& t) {
       r.cat_col[ncc] = c;
       r.cat_base[ncc] = (*t.cat_off)[c];
       r.cat_cnt[ncc] = (*t.cat_off)[c + 1] - (*t.cat_off)[c];
+      r.cat_fill[ncc] = (*t.fill)[c];
+      for (int q = 0; q < kRTCatsInline; ++q)
+        r.cat_inl[ncc][q] = q < r.cat_cnt[ncc] ? (*t.cat_val)[r.cat_base[ncc] + q] : std::numeric_limits<float>::quiet_NaN();
       ++ncc;
     }
   r.n_cat_cols = ncc;
@@ -276,12 +281,14 @@ static cudaError_t rt_launch_t(b2s_plan_s* p, const void* rows, int64_t stride, 
   using P = RTParams<NCH, NS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    constexpr int TPR = rt_tpr(NCH);
+    cudaError_t e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)G.prop.sharedMemPerBlockOptin);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS>, 128, p->rt_smem);
+  constexpr int TPRq = rt_tpr(NCH);
+  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS, TPRq>, 128 * TPRq, p->rt_smem);
   P r = *reinterpret_cast<const P*>(p->rt_blob.data());
   r.rows = (const char*)rows;
   r.row_stride = stride;
@@ -296,7 +303,7 @@ static cudaError_t rt_launch_t(b2s_plan_s* p, const void* rows, int64_t stride, 
   r.tile_rows = tr;
   const int64_t tiles = (n_rows + tr - 1) / tr;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->rt_grid, tiles));
-  rowthread_kernel<NCH, NS><<<grid, tr, p->rt_smem, st>>>(r);
+  rowthread_kernel<NCH, NS, TPRq><<<grid, tr * TPRq, p->rt_smem, st>>>(r);
   return cudaGetLastError();
 }
 
@@ -936,7 +943,8 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       const char* stg = getenv("B2S_RT_STAGES");
       p->rt_stages = stg ? std::max(2, std::min(4, atoi(stg))) : 2;
       p->rt_tile_rows = 128;
-      p->rt_smem = (int)(align_up((size_t)(cat_val.size() + 1) * NS * 8, 16) + (size_t)p->rt_stages * 128 * rpitch * 4);
+      p->rt_smem = (int)(align_up((size_t)(cat_val.size() + 1) * NS * 8, 16) + (size_t)(rt_tpr(p->rt_NCH) - 1) * 128 * NS * 8 +
+                         (size_t)p->rt_stages * 128 * rpitch * 4);
       int occ = 0;
       if (p->rt_smem <= smem_cap && rt_launch(p, nullptr, 0, 0, nullptr, nullptr, 0, nullptr, true, &occ) == cudaSuccess && occ >= 1) {
         p->rt_ok = true;
