@@ -87,7 +87,7 @@ __device__ __forceinline__ void rt_slice(const RTParams<NCH, NS>& p, const float
 }
 
 template <int NCH, int NS, int TPR>
-__global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : 3) rowthread_kernel(const __grid_constant__ RTParams<NCH, NS> p) {
+__global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) rowthread_kernel(const __grid_constant__ RTParams<NCH, NS> p) {
   static_assert(NCH % TPR == 0, "chunks must split evenly over the row's threads");
   constexpr int CPT = NCH / TPR;  // chunks per thread
   extern __shared__ __align__(16) unsigned char smem[];
@@ -170,23 +170,21 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : 3) rowthread_kernel(
       else if (q == 1) rt_slice<NCH, NS, (TPR > 1 ? CPT : 0), (TPR > 1 ? 2 * CPT : 0)>(p, xr, acc);
       else if (q == 2) rt_slice<NCH, NS, (TPR > 2 ? 2 * CPT : 0), (TPR > 2 ? 3 * CPT : 0)>(p, xr, acc);
       else rt_slice<NCH, NS, (TPR > 3 ? 3 * CPT : 0), (TPR > 3 ? 4 * CPT : 0)>(p, xr, acc);
-      // one-hot columns, dealt round-robin to the row's threads
+      // one-hot columns, dealt round-robin to the row's threads (table operands: indexed constant loads)
+      for (int cc = (TPR > 1 ? q : 0); cc < p.n_cat_cols; cc += TPR) {
+        float x = xr[p.cat_col[cc]];
+        x = (x != x) ? p.cat_fill[cc] : x;
+        const int b0 = p.cat_base[cc];
+        int j = p.n_cat;  // the zero row: no category matched
+        if (p.cat_cnt[cc] <= kRTCatsInline) {
 #pragma unroll
-      for (int cc = 0; cc < kRTMaxCatCols; ++cc) {
-        if (cc < p.n_cat_cols && (cc % TPR) == q) {
-          float x = xr[p.cat_col[cc]];
-          x = (x != x) ? p.cat_fill[cc] : x;
-          int j = p.n_cat;  // the zero row: no category matched
-          if (p.cat_cnt[cc] <= kRTCatsInline) {
-#pragma unroll
-            for (int qq = kRTCatsInline - 1; qq >= 0; --qq) j = (x == p.cat_inl[cc][qq]) ? p.cat_base[cc] + qq : j;
-          } else {
-            for (int qq = 0; qq < p.cat_cnt[cc]; ++qq) j = (x == p.cat_val[p.cat_base[cc] + qq]) ? p.cat_base[cc] + qq : j;
-          }
-          const double* wc = s_wcat + (size_t)j * NS;
-#pragma unroll
-          for (int k = 0; k < NS; ++k) acc[k] += wc[k];
+          for (int qq = kRTCatsInline - 1; qq >= 0; --qq) j = (x == p.cat_inl[cc][qq]) ? b0 + qq : j;
+        } else {
+          for (int qq = 0; qq < p.cat_cnt[cc]; ++qq) j = (x == p.cat_val[b0 + qq]) ? b0 + qq : j;
         }
+        const double* wc = s_wcat + (size_t)j * NS;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) acc[k] += wc[k];
       }
     }
     if (TPR > 1) {  // combine the row's slices in a fixed order (deterministic fp64 sum)

@@ -119,7 +119,7 @@ struct b2s_plan_s {
   RWParams rw{};
   // row-thread kernel (constant-bank operands)
   bool rt_ok = false;
-  int rt_NCH = 0, rt_NS = 0, rt_grid = 0, rt_smem = 0, rt_tile_rows = 128, rt_pitch = 0, rt_stages = 2;
+  int rt_NCH = 0, rt_NS = 0, rt_TPR = 1, rt_grid = 0, rt_smem = 0, rt_tile_rows = 128, rt_pitch = 0, rt_stages = 2;
   std::vector<char> rt_blob;  // an RTParams<NCH, NS>
   // host staging for run_host
   char* h_stage_in = nullptr;
@@ -275,20 +275,18 @@ static void rt_build(b2s_plan_s* p, const RTTables& t) {
   for (int i = 0; i < r.n_cat; ++i) r.cat_val[i] = (*t.cat_val)[i];
 }
 
-template <int NCH, int NS>
-static cudaError_t rt_launch_t(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
-                               int vec_ok, cudaStream_t st, bool query, int* occ) {
+template <int NCH, int NS, int TPR>
+static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
+                                int vec_ok, cudaStream_t st, bool query, int* occ) {
   using P = RTParams<NCH, NS>;
   static bool attr_set = false;
   if (!attr_set) {
-    constexpr int TPR = rt_tpr(NCH);
     cudaError_t e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)G.prop.sharedMemPerBlockOptin);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  constexpr int TPRq = rt_tpr(NCH);
-  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS, TPRq>, 128 * TPRq, p->rt_smem);
+  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS, TPR>, 128 * TPR, p->rt_smem);
   P r = *reinterpret_cast<const P*>(p->rt_blob.data());
   r.rows = (const char*)rows;
   r.row_stride = stride;
@@ -303,8 +301,17 @@ static cudaError_t rt_launch_t(b2s_plan_s* p, const void* rows, int64_t stride, 
   r.tile_rows = tr;
   const int64_t tiles = (n_rows + tr - 1) / tr;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->rt_grid, tiles));
-  rowthread_kernel<NCH, NS, TPRq><<<grid, tr * TPRq, p->rt_smem, st>>>(r);
+  rowthread_kernel<NCH, NS, TPR><<<grid, tr * TPR, p->rt_smem, st>>>(r);
   return cudaGetLastError();
+}
+
+template <int NCH, int NS>
+static cudaError_t rt_launch_t(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
+                               int vec_ok, cudaStream_t st, bool query, int* occ) {
+  if (p->rt_TPR == 1) return rt_launch_tt<NCH, NS, 1>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ);
+  if (NCH >= 8 && p->rt_TPR == 2) return rt_launch_tt<NCH, NS, (NCH >= 8 ? 2 : 1)>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ);
+  if (NCH >= 16 && p->rt_TPR == 4) return rt_launch_tt<NCH, NS, (NCH >= 16 ? 4 : 1)>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ);
+  return cudaErrorInvalidValue;
 }
 
 #define RT_DISPATCH(FN, ...)                                                              \
@@ -943,7 +950,11 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       const char* stg = getenv("B2S_RT_STAGES");
       p->rt_stages = stg ? std::max(2, std::min(4, atoi(stg))) : 2;
       p->rt_tile_rows = 128;
-      p->rt_smem = (int)(align_up((size_t)(cat_val.size() + 1) * NS * 8, 16) + (size_t)(rt_tpr(p->rt_NCH) - 1) * 128 * NS * 8 +
+      const char* tprs = getenv("B2S_RT_TPR");
+      p->rt_TPR = tprs ? atoi(tprs) : rt_tpr(p->rt_NCH);
+      if (p->rt_TPR != 1 && p->rt_TPR != 2 && p->rt_TPR != 4) p->rt_TPR = 1;
+      while (p->rt_TPR > 1 && (p->rt_NCH < 4 * p->rt_TPR)) p->rt_TPR /= 2;
+      p->rt_smem = (int)(align_up((size_t)(cat_val.size() + 1) * NS * 8, 16) + (size_t)(p->rt_TPR - 1) * 128 * NS * 8 +
                          (size_t)p->rt_stages * 128 * rpitch * 4);
       int occ = 0;
       if (p->rt_smem <= smem_cap && rt_launch(p, nullptr, 0, 0, nullptr, nullptr, 0, nullptr, true, &occ) == cudaSuccess && occ >= 1) {
