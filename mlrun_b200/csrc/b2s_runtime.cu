@@ -228,7 +228,8 @@ struct RTTables {  // what rt_build needs from finalize
   const int32_t* d_classes;
 };
 
-constexpr int rt_tpr(int NCH) { return NCH >= 16 ? 4 : (NCH >= 8 ? 2 : 1); }
+// threads per row: measured on B200 (profiles/r1_kernel_log.md): 2 beats 1 (more warps) and 4 (combine overhead)
+constexpr int rt_tpr(int NCH) { return NCH >= 8 ? 2 : 1; }
 
 template <int NCH, int NS>
 static void rt_build(b2s_plan_s* p, const RTTables& t) {
