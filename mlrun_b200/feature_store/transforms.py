@@ -14,6 +14,7 @@ import math
 import re
 import uuid
 
+from ..serving.resolve import MLRunInvalidArgumentError
 from ..serving.step_meta import StepMeta
 
 
@@ -77,7 +78,7 @@ class OneHotEncoder(_Step):
         for key, values in mapping.items():
             for val in values:
                 if isinstance(val, bool) or not (isinstance(val, (str, int)) or type(val).__module__ == "numpy" and "int" in type(val).__name__):
-                    raise ValueError("For OneHotEncoder you must provide int or string mapping list")
+                    raise MLRunInvalidArgumentError("For OneHotEncoder you must provide int or string mapping list")
             mapping[key] = list(dict.fromkeys(values))
         self.mapping = mapping
 
@@ -137,7 +138,7 @@ class DropFeatures(_Step):
     def _do_event(self, event):
         for f in self.features:
             if f not in event:
-                raise ValueError(f"The ingesting data doesn't contain a feature named '{f}'")
+                raise MLRunInvalidArgumentError(f"The ingesting data doesn't contain a feature named '{f}'")
             del event[f]
         return event
 
@@ -154,7 +155,7 @@ class DateExtractor(_Step):
         import pandas as pd
 
         if self.timestamp_col not in event:
-            raise ValueError(f"{self.timestamp_col} does not exist in the event")
+            raise MLRunInvalidArgumentError(f"{self.timestamp_col} does not exist in the event")
         ts = pd.Timestamp(event[self.timestamp_col])
         for part in self.parts:
             event[f"{self.timestamp_col}_{part}"] = getattr(ts, part)

@@ -1,0 +1,93 @@
+"""The product's serving API on the GPU: the reference's graph-building calls, per-event `server.test`,
+and the engine's batched `run_batch` / `run_events`, checked against the golden outputs of the REAL
+reference and against the CPU oracle.  `-m gpu`."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from mlrun_b200.lowering import LoweringError  # noqa: E402
+from mlrun_b200.synthetic import flow3_workload, tree_workload  # noqa: E402
+from oracle import batch as obatch  # noqa: E402
+from tests import api_b200, api_oracle, scenarios  # noqa: E402
+from tests.compare import assert_same  # noqa: E402
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "scenarios.json")))
+RTOL, ATOL = 1e-5, 1e-5
+
+
+@pytest.mark.parametrize("name", ["flow3_linear_events", "flow3_ensemble_events", "tree_ensemble_batch"])
+def test_device_scenarios_match_reference_golden(name):
+    """same scenario code as the oracle / reference runs, through mlrun_b200's API: every predict is a CUDA plan"""
+    got = json.loads(json.dumps(getattr(scenarios, name)(api_b200), default=str))
+    want = GOLDEN[name]
+    assert_same(got, want, name, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("n_models", [1, 4])
+@pytest.mark.parametrize("engine", ["sync", "async"])
+def test_flow3_run_batch_equals_per_event_and_oracle(n_models, engine):
+    wl = flow3_workload(n_rows=2048, n_num=56, n_cat=8, seed=9, n_models=n_models)
+    server = wl.build_server(api_b200, engine=engine)
+    out, status = server.run_batch(wl.X, names=wl.names, with_status=True)
+    ref = obatch.flow3(wl)["out"]
+    np.testing.assert_allclose(out[:, 0], ref, rtol=RTOL, atol=ATOL)
+    assert not status.any()
+    path = "/" if n_models == 1 else "/v2/models/infer"
+    rows = wl.rows_as_dicts(limit=32)
+    for i, row in enumerate(rows):  # per-event contract: feature steps on the host, predict on the device
+        got = server.test(path=path, body=dict(row))["outputs"][0]
+        assert abs(got - ref[i]) <= ATOL + RTOL * abs(ref[i])
+    resp = server.run_events(rows)
+    np.testing.assert_allclose([r["outputs"][0] for r in resp], ref[:32], rtol=RTOL, atol=ATOL)
+    assert resp[0]["model_name"] == ("linear" if n_models == 1 else "ensemble")
+
+
+def test_run_events_reports_bad_rows_as_400():
+    wl = flow3_workload(n_rows=16, n_num=12, n_cat=4, seed=1, n_models=1)
+    fn = api_b200.new_function("t", kind="serving")
+    graph = fn.set_topology("flow", engine="sync")
+    graph.to(api_b200.OneHotEncoder(mapping={k: list(v) for k, v in wl.onehot_mapping.items()}), name="onehot").to(
+        api_b200.FeatureRowModelServer(name="linear", model=wl.sklearn_models()[0]), name="linear")
+    server = fn.to_mock_server()
+    rows = wl.rows_as_dicts()
+    resp = server.run_events(rows)
+    has_nan = np.isnan(wl.X[:, :12]).any(axis=1)
+    assert has_nan.any() and not has_nan.all()
+    for bad, r in zip(has_nan, resp):
+        assert (getattr(r, "status_code", 200) == 400) == bool(bad)
+    # the reference gives the same event a 400 too (scikit-learn rejects the NaN inside predict)
+    oserver_fn = api_oracle.new_function("t", kind="serving")
+    g = oserver_fn.set_topology("flow", engine="sync")
+    g.to(api_oracle.OneHotEncoder(mapping={k: list(v) for k, v in wl.onehot_mapping.items()}), name="onehot").to(
+        api_oracle.FeatureRowModelServer(name="linear", model=wl.sklearn_models()[0]), name="linear")
+    oserver = oserver_fn.to_mock_server()
+    i = int(np.argmax(has_nan))
+    assert oserver.test(body=dict(rows[i]), silent=True).status_code == 400
+
+
+def test_router_of_tree_models_run_batch_and_single_route():
+    wl = tree_workload(n_rows=1024, n_feat=24, n_models=4, n_trees=10, depth=4, seed=6, n_fit=800)
+    server = wl.build_server(api_b200)
+    ref = obatch.tree_ensemble(wl)
+    out = server.run_batch(wl.X)
+    np.testing.assert_allclose(out[:, 0], ref["out"], rtol=RTOL, atol=ATOL)
+    one = server.test("/v2/models/m2/infer", body={"inputs": wl.X[:8].astype(np.float64).tolist()})
+    np.testing.assert_allclose(one["outputs"], ref["per_model"][:8, 1], rtol=RTOL, atol=ATOL)
+    assert one["model_name"] == "m2"
+    ens = server.test("/v2/models/infer", body={"inputs": wl.X[:8].astype(np.float64).tolist()})
+    np.testing.assert_allclose(ens["outputs"], ref["out"][:8], rtol=RTOL, atol=ATOL)
+    assert ens["model_name"] == "VotingEnsemble" and ens["model_version"] == "v1"
+
+
+def test_unlowerable_graph_is_a_hard_error():
+    fn = api_b200.new_function("t", kind="serving")
+    graph = fn.set_topology("flow", engine="sync")
+    graph.to(name="py", handler="(event)").to(api_b200.Imputer(default_value=0.0), name="imp")
+    server = fn.to_mock_server()
+    with pytest.raises(LoweringError):
+        server.run_batch(np.zeros((4, 3), dtype=np.float32), names=["a", "b", "c"])
