@@ -53,22 +53,18 @@ def make_workload(name, n_rows, seed=2):
     return tree_workload(n_rows=n_rows, n_feat=128, n_models=4, n_trees=100, depth=6, seed=3, n_fit=2000, max_features=32)
 
 
-def build_plan(name, wl):
-    from mlrun_b200 import _native as nat
-    from mlrun_b200 import packing
-    from mlrun_b200.feature_store.steps import Imputer, OneHotEncoder
-    from mlrun_b200.lowering import ColumnProgram
+def build_server(name, wl):
+    """the serving graph, built with the reference's own plugin calls on mlrun_b200, and its fused plan"""
+    from mlrun_b200 import api
 
     if name.startswith("flow3"):
-        prog = ColumnProgram(wl.names)
-        prog.apply(Imputer(mapping=dict(wl.impute_mapping), default_value=wl.impute_default))
-        prog.apply(OneHotEncoder(mapping={k: list(v) for k, v in wl.onehot_mapping.items()}))
-        models = [packing.pack_model(m) for m in wl.sklearn_models()]
-        vote = (nat.VOTE_MEAN, [1.0 / len(models)] * len(models)) if len(models) > 1 else None
-        return prog.build_plan(models, vote=vote)
-    prog = ColumnProgram([f"f{i}" for i in range(wl.X.shape[1])])
-    models = [packing.pack_model(m) for m in wl.models]
-    return prog.build_plan(models, vote=(nat.VOTE_MEAN, [1.0 / len(models)] * len(models)))
+        server = wl.build_server(api, engine="sync")
+        names = wl.names
+    else:
+        server = wl.build_server(api)
+        names = [f"f{i}" for i in range(wl.X.shape[1])]
+    compiled = server.compile(names)
+    return server, compiled.plan, names
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline (oracle)
@@ -101,13 +97,25 @@ def _cpu_worker(args):
     return n_events, time.perf_counter() - t0
 
 
+def usable_cores():
+    """host threads this process may really use: affinity mask, capped by the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def cpu_baseline(name, seconds, procs=None):
     """the reference's per-event path (restated: oracle/) on all host cores: P independent worker
     processes, like nuclio's N workers (mlrun/runtimes/nuclio/serving.py:59), each pushing one
     MockEvent per row through GraphServer.run (sync engine)."""
     import multiprocessing as mp
 
-    procs = procs or len(os.sched_getaffinity(0))
+    procs = procs or usable_cores()
     # calibrate on one process, then size the sample to the time budget
     n_cal = 300 if name.startswith("flow3") else 40
     n, dt = _cpu_worker((name, n_cal, 2))
@@ -264,7 +272,7 @@ def main():
     info = nat.device_info()
 
     wl = make_workload(name, 65536, seed=2 + rank)
-    plan = build_plan(name, wl)
+    server, plan, names = build_server(name, wl)
     F = wl.X.shape[1]
     # inputs resident in HBM: NBUF distinct batches, rotated, so that consecutive steps never re-read L2-resident rows
     row_bytes = F * 4
@@ -329,12 +337,12 @@ def main():
         for j, h in enumerate(hin):
             h[:] = np.roll(base[:Be].numpy(), j * 131, axis=0)
         for j in range(3):
-            plan.run(hin[j % 2])
+            server.run_batch(hin[j % 2], names=names)
         sync()
         n_e2e = max(5, min(args.steps, 20))
         t0 = time.perf_counter()
         for j in range(n_e2e):
-            res, st = plan.run(hin[j % 2], with_stats=True)
+            res, sts = server.run_batch(hin[j % 2], names=names, with_status=True)
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], device="cuda")
@@ -342,8 +350,8 @@ def main():
             dt = float(t.item())
         e2e = {"value": world * Be * n_e2e / dt, "unit": "events/s", "h2d_bytes_per_step": Be * row_bytes,
                "d2h_bytes_per_step": Be * (plan.out_cols + 1) * 4, "batch": Be, "steps": n_e2e,
-               "api": "DevicePlan.run (b2s_run_host): pinned host rows -> H2D -> fused kernel -> D2H outputs+status",
-               "last_step_ms": {"h2d": st["h2d_ms"], "kernel": st["kernel_ms"], "d2h": st["d2h_ms"]}}
+               "api": "GraphServer.run_batch (public API) -> b2s_run_host: pinned host rows -> H2D -> fused kernel -> "
+                      "D2H outputs + per-row status"}
 
     if rank == 0:
         peak, peak_src = measured_peak()

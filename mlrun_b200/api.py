@@ -1,0 +1,32 @@
+"""One flat namespace with the reference's plugin names (what `tests/scenarios.py`, `bench.py` and
+`mlrun_b200.synthetic` workloads build graphs with)."""
+
+from .feature_store.transforms import (  # noqa: F401
+    DateExtractor,
+    DropFeatures,
+    FeaturesetValidator,
+    Imputer,
+    MapValues,
+    OneHotEncoder,
+    SetEventMetadata,
+    _Step as MapClass,
+)
+from .serving import (  # noqa: F401
+    FeatureRowModelServer,
+    FeatureRowVotingEnsemble,
+    GraphContext,
+    GraphServer,
+    MockEvent,
+    MockTrigger,
+    ModelRouter,
+    ParallelRun,
+    RouterStep,
+    SKLearnModelServer,
+    TaskStep,
+    V2ModelServer,
+    VotingEnsemble,
+    create_graph_server,
+    new_function,
+)
+
+NAME = "mlrun_b200"
