@@ -23,6 +23,7 @@
 #include "b2s_device.cuh"
 #include "b2s_rowwarp.cuh"
 #include "b2s_rowthread.cuh"
+#include "b2s_trees2.cuh"
 
 using namespace b2s;
 
@@ -121,6 +122,14 @@ struct b2s_plan_s {
   bool rt_ok = false;
   int rt_NCH = 0, rt_NS = 0, rt_TPR = 1, rt_grid = 0, rt_smem = 0, rt_tile_rows = 128, rt_pitch = 0, rt_stages = 2;
   std::vector<char> rt_blob;  // an RTParams<NCH, NS>
+  // shared-memory-resident tree kernel
+  bool t2_ok = false;
+  int t2_NS = 1, t2_grid = 0, t2_block = 512, t2_smem = 0;
+  T2Params t2{};
+  char* d_t2_blob = nullptr;
+  double* d_pred = nullptr;
+  int32_t* d_row_bad = nullptr;
+  int64_t pred_rows = 0;
   // host staging for run_host
   char* h_stage_in = nullptr;
   char* h_stage_out = nullptr;
@@ -966,6 +975,114 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       }
     }
   }
+  if (p->mode == MODE_TREES && !need_expand && getenv("B2S_NO_TREES2") == nullptr) {
+    // re-pack every model as complete heap-ordered trees; one model must fit one CTA's shared memory
+    bool ok = true;
+    std::vector<int> depth(M, 0);
+    size_t max_table = 0;
+    for (int mi = 0; mi < M && ok; ++mi) {
+      auto& m = p->models[mi];
+      if (m.kind != MK_TREES) { ok = false; break; }
+      const int nt = (int)m.tree_slot.size();
+      for (int t = 0; t < nt; ++t) {
+        const int base = m.tree_offset[t];
+        std::vector<std::pair<int, int>> stack{{0, 0}};
+        while (!stack.empty()) {
+          auto [node, d] = stack.back();
+          stack.pop_back();
+          depth[mi] = std::max(depth[mi], d);
+          if (m.feature[base + node] >= 0) {
+            stack.push_back({m.left[base + node], d + 1});
+            stack.push_back({m.right[base + node], d + 1});
+          }
+        }
+      }
+      if (depth[mi] > 8) ok = false;
+      const size_t ni = ((size_t)1 << depth[mi]) - 1, nl = (size_t)1 << depth[mi];
+      max_table = std::max(max_table, align_up((size_t)nt * ni * 8, 16) + (size_t)nt * nl * 8);
+    }
+    const int TR2 = 64, G2 = 8, ST2 = 2;
+    const int NS2 = p->NS <= 1 ? 1 : (p->NS <= 4 ? 4 : 0);
+    const size_t part_bytes = (size_t)(G2 - 1) * TR2 * std::max(NS2, 1) * 8;
+    const size_t tiles_bytes = (size_t)ST2 * TR2 * pitch * 4;
+    const size_t total2 = align_up(max_table, 16) + align_up(part_bytes, 16) + tiles_bytes;
+    if (ok && NS2 > 0 && total2 <= (size_t)smem_cap && M <= sms) {
+      BlobBuilder tb;
+      std::vector<T2Model> t2m(M);
+      std::vector<size_t> o_nodes(M), o_leaves(M), o_slot(M), o_scale(M);
+      for (int mi = 0; mi < M; ++mi) {
+        auto& m = p->models[mi];
+        const int nt = (int)m.tree_slot.size();
+        const int D = depth[mi];
+        const int ni = (1 << D) - 1, nl = 1 << D;
+        std::vector<HeapNode> hn((size_t)nt * std::max(ni, 1), HeapNode{0, std::numeric_limits<float>::infinity()});
+        std::vector<double> hl((size_t)nt * nl, 0.0);
+        for (int t = 0; t < nt; ++t) {
+          const int base = m.tree_offset[t];
+          struct It { int heap, d, src; };
+          std::vector<It> stack{{0, 0, 0}};
+          while (!stack.empty()) {
+            It it = stack.back();
+            stack.pop_back();
+            const bool leaf = m.feature[base + it.src] < 0;
+            if (it.d == D) {
+              hl[(size_t)t * nl + (it.heap - ni)] = m.leaf_value[base + it.src];
+              continue;
+            }
+            if (leaf) {  // pad: a threshold of +inf sends every finite value left; both sides carry the leaf
+              hn[(size_t)t * ni + it.heap] = HeapNode{0, std::numeric_limits<float>::infinity()};
+              stack.push_back({2 * it.heap + 1, it.d + 1, it.src});
+              stack.push_back({2 * it.heap + 2, it.d + 1, it.src});
+            } else {
+              hn[(size_t)t * ni + it.heap] = HeapNode{m.feature[base + it.src], m.threshold[base + it.src]};
+              stack.push_back({2 * it.heap + 1, it.d + 1, m.left[base + it.src]});
+              stack.push_back({2 * it.heap + 2, it.d + 1, m.right[base + it.src]});
+            }
+          }
+        }
+        o_nodes[mi] = tb.add(hn);
+        o_leaves[mi] = tb.add(hl);
+        o_slot[mi] = tb.add(m.tree_slot);
+        o_scale[mi] = tb.add(m.tree_scale);
+        t2m[mi].n_trees = nt;
+        t2m[mi].depth = D;
+        t2m[mi].n_internal = ni;
+        t2m[mi].n_leaves = nl;
+      }
+      const size_t o_models2 = align_up(tb.data.size(), 16);
+      tb.data.resize(o_models2 + sizeof(T2Model) * M);
+      CUDA_TRY(cudaMalloc(&p->d_t2_blob, tb.data.size()));
+      for (int mi = 0; mi < M; ++mi) {
+        t2m[mi].nodes = (const HeapNode*)(p->d_t2_blob + o_nodes[mi]);
+        t2m[mi].leaves = (const double*)(p->d_t2_blob + o_leaves[mi]);
+        t2m[mi].slot = (const int32_t*)(p->d_t2_blob + o_slot[mi]);
+        t2m[mi].scale = (const double*)(p->d_t2_blob + o_scale[mi]);
+      }
+      memcpy(tb.data.data() + o_models2, t2m.data(), sizeof(T2Model) * M);
+      CUDA_TRY(cudaMemcpy(p->d_t2_blob, tb.data.data(), tb.data.size(), cudaMemcpyHostToDevice));
+      T2Params& t = p->t2;
+      memset(&t, 0, sizeof(t));
+      t.n_in = n_in;
+      t.n_models = M;
+      t.tile_rows = TR2;
+      t.pitch = pitch;
+      t.stages = ST2;
+      t.groups = G2;
+      t.t2 = (const T2Model*)(p->d_t2_blob + o_models2);
+      t.models = k.models;
+      t.classes = k.classes;
+      t.bias = k.bias;
+      t.sm_tables = 0;
+      t.sm_part = (int)align_up(max_table, 16);
+      t.sm_tiles = (int)(align_up(max_table, 16) + align_up(part_bytes, 16));
+      p->t2_smem = (int)total2;
+      p->t2_NS = NS2;
+      p->t2_block = TR2 * G2;
+      p->t2_grid = std::max(M, (sms / M) * M);
+      p->t2_ok = true;
+      p->kernels_per_batch = 2;
+    }
+  }
   for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&p->ev[i]));
   p->finalized = true;
   return B2S_OK;
@@ -989,6 +1106,40 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
   k.out = (float*)d_out;
   k.status = d_status;
   k.vec_ok = ((p->n_in % 4) == 0 && (stride % 16) == 0 && ((uintptr_t)d_rows % 16) == 0) ? 1 : 0;
+  if (p->t2_ok) {
+    if (n_rows > p->pred_rows) {
+      if (p->d_pred) { cudaFree(p->d_pred); cudaFree(p->d_row_bad); }
+      p->pred_rows = std::max<int64_t>(n_rows, 65536);
+      CUDA_TRY(cudaMalloc(&p->d_pred, (size_t)p->pred_rows * p->kp.n_models * 8));
+      CUDA_TRY(cudaMalloc(&p->d_row_bad, (size_t)p->pred_rows * 4));
+    }
+    T2Params t = p->t2;
+    t.rows = (const char*)d_rows;
+    t.row_stride = stride;
+    t.n_rows = n_rows;
+    t.pred = p->d_pred;
+    t.row_bad = p->d_row_bad;
+    t.vec_ok = k.vec_ok;
+    static bool t2_attr = false;
+    if (!t2_attr) {
+      CUDA_TRY(cudaFuncSetAttribute(trees_model_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.prop.sharedMemPerBlockOptin));
+      CUDA_TRY(cudaFuncSetAttribute(trees_model_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.prop.sharedMemPerBlockOptin));
+      t2_attr = true;
+    }
+    const int64_t tiles2 = (n_rows + t.tile_rows - 1) / t.tile_rows;
+    const int M2 = p->kp.n_models;
+    const int grid2 = (int)std::max<int64_t>(M2, std::min<int64_t>(p->t2_grid, tiles2 * M2));
+    G.launches.fetch_add(2, std::memory_order_relaxed);
+    if (p->t2_NS == 1) trees_model_kernel<1><<<grid2, p->t2_block, p->t2_smem, st>>>(t);
+    else trees_model_kernel<4><<<grid2, p->t2_block, p->t2_smem, st>>>(t);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return fail(B2S_ERR_CUDA, "tree kernel launch failed: %s", cudaGetErrorString(e2));
+    const int vgrid = (int)std::max<int64_t>(1, std::min<int64_t>(4 * G.prop.multiProcessorCount, (n_rows + 255) / 256));
+    vote_kernel<<<vgrid, 256, 0, st>>>(k, p->d_pred, p->d_row_bad);
+    e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return fail(B2S_ERR_CUDA, "vote kernel launch failed: %s", cudaGetErrorString(e2));
+    return B2S_OK;
+  }
   if (p->rt_ok) {
     G.launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = rt_launch(p, d_rows, stride, n_rows, d_out, d_status, k.vec_ok, st);
@@ -1323,6 +1474,8 @@ extern "C" int b2s_plan_destroy(b2s_plan_t p) {
   for (int i = 0; i < 4; ++i)
     if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   if (p->d_blob) cudaFree(p->d_blob);
+  if (p->d_t2_blob) cudaFree(p->d_t2_blob);
+  if (p->d_pred) { cudaFree(p->d_pred); cudaFree(p->d_row_bad); }
   delete p;
   return B2S_OK;
 }
