@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="wall budget of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 ensemble-merge: p2p = votes stored into every rank's buffer from the kernel epilogue over "
+                         "NVLink peer memory (fused); nccl = a separate all_gather per step")
     return ap.parse_args()
 
 
@@ -286,10 +289,29 @@ def main():
     gathered = torch.empty(world * B * plan.out_cols, dtype=torch.float32, device="cuda") if world > 1 else None
     stream = torch.cuda.Stream()  # a real (non-NULL) stream: kernels, NCCL and the timing events all ride on it
     torch.cuda.set_stream(stream)
+    merge = args.merge if world > 1 else "none"
+    merged_buf = None
+    if merge == "p2p":
+        # every rank owns a (world*B, out_cols) response buffer; the kernels of ALL ranks store their shard's votes
+        # into ALL of them over NVLink peer mappings (CUDA IPC), so no collective runs in the step
+        try:
+            merged_buf = nat.DeviceBuffer(world * B * plan.out_cols * 4)
+            handles = [None] * world
+            dist.all_gather_object(handles, nat.ipc_export(merged_buf.ptr))
+            peers = [merged_buf.ptr if r == rank else nat.ipc_open(handles[r]) for r in range(world)]
+            plan.set_merge_targets(peers, rank * B)
+        except Exception as exc:  # noqa: BLE001 -- no peer access on this box: use the NCCL merge
+            print(f"[rank {rank}] p2p merge unavailable ({exc}); using nccl", file=sys.stderr)
+            merge = "nccl"
+        flags = torch.tensor([1 if merge == "p2p" else 0], device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if int(flags.item()) == 0 and merge == "p2p":
+            plan.set_merge_targets([], 0)
+            merge = "nccl"
 
     def step(i):
         plan.run_device(bufs[i % nbuf].data_ptr(), B, row_bytes, out.data_ptr(), None, stream.cuda_stream)
-        if world > 1:  # ensemble-merge: every rank ends up with every shard's votes (4 B/event)
+        if merge == "nccl":  # ensemble-merge: every rank ends up with every shard's votes (4 B/event)
             dist.all_gather_into_tensor(gathered, out)
 
     def sync():
@@ -318,6 +340,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    merge_check = None
+    if merge == "p2p":
+        # every rank must now hold every shard: compare a checksum of each rank's own shard with what landed here
+        full = merged_buf.download(np.float32, (world * B, plan.out_cols))
+        mine = torch.tensor(full[rank * B:(rank + 1) * B].astype(np.float64).sum(axis=0)[:1], device="cuda")
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        got = [float(full[r * B:(r + 1) * B].astype(np.float64).sum(axis=0)[0]) for r in range(world)]
+        merge_check = all(abs(got[r] - float(sums[r].item())) <= 1e-6 * max(1.0, abs(got[r])) for r in range(world))
+        plan.set_merge_targets([], 0)  # the single-GPU measurements below write locally again
 
     # kernel-only time of the dominant kernel (no collective), for the roofline
     kms = plan.time_device([b.data_ptr() for b in bufs], B, row_bytes, out.data_ptr(), max(args.steps, 10)) / max(args.steps, 10)
@@ -363,7 +395,10 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 in / f64 accumulate", "data": "synthetic",
             "config": {"workload": workload_desc(name), "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"event-sharded x{world}" + (" + NCCL all-gather of votes" if world > 1 else ""),
+                       "parallelism": f"event-sharded x{world}" + {"none": "", "nccl": " + NCCL all-gather of votes per step",
+                                                                    "p2p": " + fused P2P ensemble-merge (votes stored to every "
+                                                                           "rank over NVLink from the kernel epilogue)"}[merge],
+                       "merge_verified": merge_check,
                        "l2": f"{nbuf} rotating input buffers of {B * row_bytes / 1e6:.0f} MB (> 126 MB L2 between re-reads)",
                        "device": info["name"], "grid_block": None},
             "p50_step_latency_us": {"batch": 4096, "p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),

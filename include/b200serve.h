@@ -152,6 +152,17 @@ int b2s_wait(b2s_plan_t plan, uint64_t ticket, void* out, int64_t out_bytes, int
 /* force the open batch out now (drain callback, serving/server.py:353-384) */
 int b2s_flush(b2s_plan_t plan);
 
+/* ---- multi-GPU: fused ensemble-merge ----------------------------------------------------------------
+ * One process per GPU, events sharded by rows (they are independent: VotingEnsemble reduces across models,
+ * serving/routers.py:797-810).  The only exchange is the merge of every shard's votes into the full
+ * response.  Instead of a separate all-gather, a plan can be given the output buffers of all ranks
+ * (peer-mapped over NVLink with the IPC calls below); its kernels then store each output row into every
+ * target at row `row_offset + row` straight from the epilogue.  n_peers = 0 restores local output. */
+int b2s_plan_set_merge_targets(b2s_plan_t plan, void* const* peer_out, int32_t n_peers, int64_t row_offset);
+int b2s_ipc_export(void* dptr, void* handle64 /* 64 bytes out */);
+int b2s_ipc_open(const void* handle64, void** dptr_out);
+int b2s_ipc_close(void* dptr);
+
 /* pinned host memory for zero-extra-copy submits and for bench.py's e2e leg */
 void* b2s_alloc_pinned(size_t bytes);
 int b2s_free_pinned(void* p);

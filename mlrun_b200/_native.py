@@ -67,6 +67,10 @@ SIGNATURES = {
     "b2s_submit": (C.c_int, [_vp, _vp, _i64, _i64, C.POINTER(_u64)]),
     "b2s_wait": (C.c_int, [_vp, _u64, _vp, _i64, _vp, C.POINTER(Stats)]),
     "b2s_flush": (C.c_int, [_vp]),
+    "b2s_plan_set_merge_targets": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i64]),
+    "b2s_ipc_export": (C.c_int, [_vp, _vp]),
+    "b2s_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "b2s_ipc_close": (C.c_int, [_vp]),
     "b2s_alloc_pinned": (_vp, [C.c_size_t]),
     "b2s_free_pinned": (C.c_int, [_vp]),
     "b2s_device_alloc": (_vp, [C.c_size_t]),
@@ -171,6 +175,19 @@ class DeviceBuffer:
             self.free()
         except Exception:
             pass
+
+
+def ipc_export(dptr):
+    """64-byte CUDA IPC handle of a buffer from DeviceBuffer / b2s_device_alloc"""
+    buf = C.create_string_buffer(64)
+    check(load().b2s_ipc_export(dptr, buf))
+    return bytes(buf.raw)
+
+
+def ipc_open(handle):
+    out = C.c_void_p()
+    check(load().b2s_ipc_open(C.create_string_buffer(handle, 64), C.byref(out)))
+    return out.value
 
 
 def pinned_empty(shape, dtype=np.float32):

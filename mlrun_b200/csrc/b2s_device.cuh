@@ -89,6 +89,11 @@ struct KParams {
   int32_t sm_fill, sm_flags, sm_mapoff, sm_catoff, sm_catval, sm_wnum, sm_wcat, sm_tiles, sm_exp, sm_pred,
       sm_outsrc, sm_outkind, sm_outarg, sm_total;
   int32_t n_cat, n_maps;
+  // ensemble-merge targets: when n_peers > 0 every output row is stored into each peer's buffer (own GPU
+  // included) at row `peer_off + row` -- NVLink P2P stores from the epilogue replace a separate all-gather
+  float* peers[8];
+  int64_t peer_off;
+  int32_t n_peers;
   int32_t tpr;                // LINEAR: threads per row (slices of the row's 16-byte chunks)
   int32_t sm_part, sm_pst, sm_chunk;
   const uint8_t* chunk_kind;  // [ceil(n_in/4)] 0 = four plain numeric columns (fast path), 1 = generic
@@ -202,22 +207,28 @@ __device__ __forceinline__ double apply_link(const ModelDesc& md, const double* 
   }
 }
 
+// one 4-byte output word of row `row`: local buffer, or every merge target (fused ensemble-merge)
+template <typename P>
+__device__ __forceinline__ void store_word(const P& p, int64_t row, int col, uint32_t bits) {
+  if (p.n_peers == 0) {
+    reinterpret_cast<uint32_t*>(p.out)[row * p.out_cols + col] = bits;
+  } else {
+    for (int g = 0; g < p.n_peers; ++g)
+      reinterpret_cast<uint32_t*>(p.peers[g])[(p.peer_off + row) * p.out_cols + col] = bits;
+  }
+}
+
 // VotingEnsemble reduce over per-model predictions (serving/routers.py:708-741); writes out_cols words.
 __device__ __forceinline__ void vote_and_store(const KParams& p, const double* __restrict__ pred, int64_t row,
                                                uint32_t st) {
-  float* o = p.out + row * p.out_cols;
   const int M = p.n_models;
   if (p.vote_kind == 0) {  // B2S_VOTE_NONE: every model's prediction
-    for (int m = 0; m < M; ++m) {
-      if (p.out_is_int)
-        reinterpret_cast<int32_t*>(o)[m] = (int32_t)pred[m];
-      else
-        o[m] = (float)pred[m];
-    }
+    for (int m = 0; m < M; ++m)
+      store_word(p, row, m, p.out_is_int ? (uint32_t)(int32_t)pred[m] : __float_as_uint((float)pred[m]));
   } else if (p.vote_kind == 1) {  // _mean_vote: (n,m) @ w(m) in fp64, model order
     double acc = 0.0;
     for (int m = 0; m < M; ++m) acc = __dadd_rn(acc, __dmul_rn(pred[m], p.vote_w[m]));
-    o[0] = (float)acc;
+    store_word(p, row, 0, __float_as_uint((float)acc));
   } else {  // _majority_vote: tallies per class in fp64 (model order), argmax with first-max tie break
     int maxlab = -1;
     for (int m = 0; m < M; ++m) {
@@ -252,7 +263,7 @@ __device__ __forceinline__ void vote_and_store(const KParams& p, const double* _
       }
       if (c0 <= maxlab && (best_c < 0 || 0.0 > best_t || (0.0 == best_t && c0 < best_c))) best_c = c0;
     }
-    reinterpret_cast<int32_t*>(o)[0] = best_c < 0 ? 0 : best_c;
+    store_word(p, row, 0, (uint32_t)(best_c < 0 ? 0 : best_c));
   }
   if (p.status) p.status[row] = (int32_t)st;
 }

@@ -32,6 +32,9 @@ struct RTParams {
   int32_t* status;
   int32_t n_in, out_cols, n_models, vote_kind, out_is_int, fast_epilogue, tile_rows, pitch, stages, vec_ok;
   int32_t n_cat_cols, n_cat;
+  float* peers[8];   // ensemble-merge targets (see KParams)
+  int64_t peer_off;
+  int32_t n_peers;
   const double* wcat;       // [n_cat][NS] (global; copied to shared memory, plus a zero row)
   const double* vote_w_g;   // generic epilogue
   const ModelDesc* models;
@@ -215,11 +218,11 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) 
           double s = 0.0;
 #pragma unroll
           for (int k = 0; k < NS; ++k) s = __dadd_rn(s, __dmul_rn(acc[k], p.vote_w[k]));
-          p.out[row] = (float)s;
+          store_word(p, row, 0, __float_as_uint((float)s));
         } else {
 #pragma unroll
           for (int k = 0; k < NS; ++k)
-            if (k < p.n_models) p.out[row * p.out_cols + k] = (float)acc[k];
+            if (k < p.n_models) store_word(p, row, k, __float_as_uint((float)acc[k]));
         }
         if (p.status) p.status[row] = (int32_t)st;
       } else {
@@ -239,6 +242,9 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) 
         kp.out_is_int = p.out_is_int;
         kp.vote_w = p.vote_w_g;
         kp.status = p.status;
+        kp.n_peers = p.n_peers;
+        kp.peer_off = p.peer_off;
+        for (int g = 0; g < p.n_peers; ++g) kp.peers[g] = p.peers[g];
         vote_and_store(kp, pred, row, st);
       }
     }

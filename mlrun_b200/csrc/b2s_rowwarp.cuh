@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(128, 3) rowwarp_kernel(const __grid_constant__
         kp.out_is_int = p.out_is_int;
         kp.vote_w = p.vote_w;
         kp.status = p.status;
+        kp.n_peers = 0;
         vote_and_store(kp, pred, my_row, my_bad);
       }
     }

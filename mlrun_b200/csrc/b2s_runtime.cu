@@ -122,6 +122,9 @@ struct b2s_plan_s {
   bool rt_ok = false;
   int rt_NCH = 0, rt_NS = 0, rt_TPR = 1, rt_grid = 0, rt_smem = 0, rt_tile_rows = 128, rt_pitch = 0, rt_stages = 2;
   std::vector<char> rt_blob;  // an RTParams<NCH, NS>
+  // fused ensemble-merge targets (P2P)
+  std::vector<void*> peers;
+  int64_t peer_off = 0;
   // shared-memory-resident tree kernel
   bool t2_ok = false;
   int t2_NS = 1, t2_grid = 0, t2_block = 512, t2_smem = 0;
@@ -304,6 +307,9 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   r.out = (float*)out;
   r.status = status;
   r.vec_ok = vec_ok;
+  r.n_peers = (int)p->peers.size();
+  r.peer_off = p->peer_off;
+  for (int g = 0; g < r.n_peers; ++g) r.peers[g] = (float*)p->peers[g];
   r.pitch = p->rt_pitch;
   r.stages = p->rt_stages;
   int tr = p->rt_tile_rows;
@@ -1106,6 +1112,9 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
   k.out = (float*)d_out;
   k.status = d_status;
   k.vec_ok = ((p->n_in % 4) == 0 && (stride % 16) == 0 && ((uintptr_t)d_rows % 16) == 0) ? 1 : 0;
+  k.n_peers = (int)p->peers.size();
+  k.peer_off = p->peer_off;
+  for (int g = 0; g < k.n_peers; ++g) k.peers[g] = (float*)p->peers[g];
   if (p->t2_ok) {
     if (n_rows > p->pred_rows) {
       if (p->d_pred) { cudaFree(p->d_pred); cudaFree(p->d_row_bad); }
@@ -1146,7 +1155,7 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
     if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "row-thread kernel launch failed: %s", cudaGetErrorString(e));
     return B2S_OK;
   }
-  if (p->rw_ok && k.vec_ok) {
+  if (p->rw_ok && k.vec_ok && k.n_peers == 0) {
     RWParams r = p->rw;
     r.rows = (const char*)d_rows;
     r.row_stride = stride;
@@ -1477,6 +1486,31 @@ extern "C" int b2s_plan_destroy(b2s_plan_t p) {
   if (p->d_t2_blob) cudaFree(p->d_t2_blob);
   if (p->d_pred) { cudaFree(p->d_pred); cudaFree(p->d_row_bad); }
   delete p;
+  return B2S_OK;
+}
+
+// ------------------------------------------------------------------------------------------ multi-GPU merge
+extern "C" int b2s_plan_set_merge_targets(b2s_plan_t p, void* const* peer_out, int32_t n_peers, int64_t row_offset) {
+  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+  if (n_peers < 0 || n_peers > 8 || row_offset < 0) return fail(B2S_ERR_INVALID, "bad merge targets");
+  if (p->mode == MODE_STORE && n_peers > 0) return fail(B2S_ERR_UNSUPPORTED, "transform-only plans have no vote to merge");
+  p->peers.assign(peer_out, peer_out + n_peers);
+  p->peer_off = row_offset;
+  return B2S_OK;
+}
+extern "C" int b2s_ipc_export(void* dptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), dptr));
+  return B2S_OK;
+}
+extern "C" int b2s_ipc_open(const void* handle64, void** dptr_out) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  CUDA_TRY(cudaIpcOpenMemHandle(dptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return B2S_OK;
+}
+extern "C" int b2s_ipc_close(void* dptr) {
+  CUDA_TRY(cudaIpcCloseMemHandle(dptr));
   return B2S_OK;
 }
 

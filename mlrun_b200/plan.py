@@ -187,6 +187,11 @@ class DevicePlan:
     def run_device(self, d_rows, n_rows, row_stride, d_out, d_status=None, stream=None):
         nat.check(self._lib.b2s_run_device(self._h, d_rows, n_rows, row_stride, d_out, d_status, stream))
 
+    def set_merge_targets(self, peer_ptrs, row_offset):
+        """fused ensemble-merge: every output row is stored into each peer buffer at row_offset + row"""
+        arr = (C.c_void_p * max(len(peer_ptrs), 1))(*peer_ptrs)
+        nat.check(self._lib.b2s_plan_set_merge_targets(self._h, arr, len(peer_ptrs), int(row_offset)))
+
     def time_device(self, d_row_ptrs, n_rows, row_stride, d_out, iters):
         """CUDA-event time (ms) of `iters` back-to-back launches over rotating input buffers"""
         arr = (C.c_void_p * len(d_row_ptrs))(*d_row_ptrs)
