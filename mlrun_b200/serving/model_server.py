@@ -24,9 +24,9 @@ def now_date():
 class V2ModelServer(StepMeta):
     def __init__(self, context=None, name=None, model_path=None, model=None, protocol=None, input_path=None,
                  result_path=None, **kwargs):
-        self.name, _, self.version = (name or "").partition(":") if name else (name, "", "")
-        if not name:
-            self.name, self.version = name, ""
+        self.name, self.version = name, ""
+        if name and ":" in name:  # "<model>:<version>" keys come from /versions/<ver>/ URLs
+            self.name, self.version = name.split(":", 1)
         self.context = context
         self.ready = False
         self.error = ""
