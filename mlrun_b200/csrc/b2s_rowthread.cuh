@@ -32,6 +32,7 @@ struct RTParams {
   int32_t* status;
   int32_t n_in, out_cols, n_models, vote_kind, out_is_int, fast_epilogue, tile_rows, pitch, stages, vec_ok;
   int32_t n_cat_cols, n_cat;
+  int32_t use_bulk;  // tile rows are fetched with cp.async.bulk (TMA, 1-D) + mbarrier instead of LDGSTS
   float* peers[8];   // ensemble-merge targets (see KParams)
   int64_t peer_off;
   int32_t n_peers;
@@ -89,6 +90,34 @@ __device__ __forceinline__ void rt_slice(const RTParams<NCH, NS>& p, const float
   }
 }
 
+// ---- TMA (bulk async copy) + mbarrier helpers: one 1-D bulk copy per event row lands in the padded tile
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
 template <int NCH, int NS, int TPR>
 __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) rowthread_kernel(const __grid_constant__ RTParams<NCH, NS> p) {
   static_assert(NCH % TPR == 0, "chunks must split evenly over the row's threads");
@@ -139,17 +168,43 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) 
     }
   };
 
+  // bulk (TMA) variant: one mbarrier per stage; row `tid` of the tile is fetched by thread `tid`
+  __shared__ __align__(8) uint64_t s_bar[4];
+  const bool bulk = p.use_bulk && p.vec_ok;
+  const uint32_t row_bytes = (uint32_t)p.n_in * 4u;
+  auto issue_bulk = [&](int st, int64_t row0) {
+    int64_t left = p.n_rows - row0;
+    const int rows = left < TR ? (left < 0 ? 0 : (int)left) : TR;
+    if (tid == 0) mbar_expect_tx(&s_bar[st], (uint32_t)rows * row_bytes);
+    if (tid < rows)
+      bulk_load(s_tiles + st * tile_words + tid * p.pitch, p.rows + (row0 + tid) * p.row_stride, row_bytes, &s_bar[st]);
+  };
+  if (bulk) {
+    if (tid == 0) {
+      for (int s = 0; s < S; ++s) mbar_init(&s_bar[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
   for (int s = 0; s < S - 1; ++s) {
     const int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-    if (t < n_tiles) issue(s_tiles + s * tile_words, t * TR);
-    cp_async_commit();
+    if (bulk) {
+      issue_bulk(s, t * TR);
+    } else {
+      if (t < n_tiles) issue(s_tiles + s * tile_words, t * TR);
+      cp_async_commit();
+    }
   }
+  uint32_t phase_bits = 0;  // bit s: parity to wait for on stage s
   for (int i = tid; i < p.n_cat * NS; i += blockDim.x) s_wcat[i] = p.wcat[i];
   for (int i = tid; i < NS; i += blockDim.x) s_wcat[p.n_cat * NS + i] = 0.0;
 
   int stage = 0;
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    if (S == 2) cp_async_wait<0>();
+    if (bulk) {
+      mbar_wait(&s_bar[stage], (phase_bits >> stage) & 1u);
+      phase_bits ^= (1u << stage);
+    } else if (S == 2) cp_async_wait<0>();
     else if (S == 3) cp_async_wait<1>();
     else cp_async_wait<2>();
     __syncthreads();  // tile visible to everybody; everybody is done with the previous tile and s_part
@@ -157,8 +212,12 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) 
       const int64_t tn = t + (int64_t)(S - 1) * gridDim.x;
       int sn = stage + S - 1;
       if (sn >= S) sn -= S;
-      if (tn < n_tiles) issue(s_tiles + sn * tile_words, tn * TR);
-      cp_async_commit();
+      if (bulk) {
+        issue_bulk(sn, tn * TR);  // rows = 0 past the end: the barrier completes on the arrive alone
+      } else {
+        if (tn < n_tiles) issue(s_tiles + sn * tile_words, tn * TR);
+        cp_async_commit();
+      }
     }
     const float* tile = s_tiles + stage * tile_words;
     const int64_t row = t * TR + r;

@@ -312,6 +312,10 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   for (int g = 0; g < r.n_peers; ++g) r.peers[g] = (float*)p->peers[g];
   r.pitch = p->rt_pitch;
   r.stages = p->rt_stages;
+  {
+    static const int bulk_env = getenv("B2S_TMA") ? atoi(getenv("B2S_TMA")) : 0;
+    r.use_bulk = bulk_env;
+  }
   int tr = p->rt_tile_rows;
   while (tr > 32 && (n_rows + tr - 1) / tr < (int64_t)G.prop.multiProcessorCount) tr /= 2;
   r.tile_rows = tr;
