@@ -118,13 +118,14 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                : "memory");
 }
 
-template <int NCH, int NS, int TPR>
+template <int NCH, int NS, int TPR, bool BULK>
 __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) rowthread_kernel(const __grid_constant__ RTParams<NCH, NS> p) {
   static_assert(NCH % TPR == 0, "chunks must split evenly over the row's threads");
   constexpr int CPT = NCH / TPR;  // chunks per thread
   extern __shared__ __align__(16) unsigned char smem[];
-  double* s_wcat = reinterpret_cast<double*>(smem);
-  const size_t wcat_bytes = (((size_t)(p.n_cat + 1) * NS * 8 + 15) / 16) * 16;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem);  // 4 mbarriers (bulk variant); 64 bytes reserved
+  double* s_wcat = reinterpret_cast<double*>(smem + 64);
+  const size_t wcat_bytes = 64 + (((size_t)(p.n_cat + 1) * NS * 8 + 15) / 16) * 16;
   double* s_part = reinterpret_cast<double*>(smem + wcat_bytes);  // [(TPR-1)][128][NS]
   float* s_tiles = reinterpret_cast<float*>(smem + wcat_bytes + (size_t)(TPR - 1) * 128 * NS * 8);
 
@@ -169,8 +170,7 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) 
   };
 
   // bulk (TMA) variant: one mbarrier per stage; row `tid` of the tile is fetched by thread `tid`
-  __shared__ __align__(8) uint64_t s_bar[4];
-  const bool bulk = p.use_bulk && p.vec_ok;
+  constexpr bool bulk = BULK;
   const uint32_t row_bytes = (uint32_t)p.n_in * 4u;
   auto issue_bulk = [&](int st, int64_t row0) {
     int64_t left = p.n_rows - row0;

@@ -294,12 +294,15 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   using P = RTParams<NCH, NS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)G.prop.sharedMemPerBlockOptin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)G.prop.sharedMemPerBlockOptin);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS, TPR>, 128 * TPR, p->rt_smem);
+  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS, TPR, false>, 128 * TPR, p->rt_smem);
   P r = *reinterpret_cast<const P*>(p->rt_blob.data());
   r.rows = (const char*)rows;
   r.row_stride = stride;
@@ -321,7 +324,10 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   r.tile_rows = tr;
   const int64_t tiles = (n_rows + tr - 1) / tr;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->rt_grid, tiles));
-  rowthread_kernel<NCH, NS, TPR><<<grid, tr * TPR, p->rt_smem, st>>>(r);
+  if (r.use_bulk && vec_ok)
+    rowthread_kernel<NCH, NS, TPR, true><<<grid, tr * TPR, p->rt_smem, st>>>(r);
+  else
+    rowthread_kernel<NCH, NS, TPR, false><<<grid, tr * TPR, p->rt_smem, st>>>(r);
   return cudaGetLastError();
 }
 
@@ -974,7 +980,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       p->rt_TPR = tprs ? atoi(tprs) : rt_tpr(p->rt_NCH);
       if (p->rt_TPR != 1 && p->rt_TPR != 2 && p->rt_TPR != 4) p->rt_TPR = 1;
       while (p->rt_TPR > 1 && (p->rt_NCH < 4 * p->rt_TPR)) p->rt_TPR /= 2;
-      p->rt_smem = (int)(align_up((size_t)(cat_val.size() + 1) * NS * 8, 16) + (size_t)(p->rt_TPR - 1) * 128 * NS * 8 +
+      p->rt_smem = (int)(64 + align_up((size_t)(cat_val.size() + 1) * NS * 8, 16) + (size_t)(p->rt_TPR - 1) * 128 * NS * 8 +
                          (size_t)p->rt_stages * 128 * rpitch * 4);
       int occ = 0;
       if (p->rt_smem <= smem_cap && rt_launch(p, nullptr, 0, 0, nullptr, nullptr, 0, nullptr, true, &occ) == cudaSuccess && occ >= 1) {
