@@ -200,6 +200,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_traffic(name, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this workload
+    (profiles/traffic.json, bytes per event), scaled to this launch; None if no capture is on file"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        rec = json.load(open(p)).get(name)
+        return rec["dram_bytes_per_event"] * B if rec else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -400,11 +411,11 @@ def main():
                                                                            "rank over NVLink from the kernel epilogue)"}[merge],
                        "merge_verified": merge_check,
                        "l2": f"{nbuf} rotating input buffers of {B * row_bytes / 1e6:.0f} MB (> 126 MB L2 between re-reads)",
-                       "device": info["name"], "grid_block": None},
+                       "device": info["name"], "kernel": plan.kernel},
             "p50_step_latency_us": {"batch": 4096, "p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                                     "how": "CUDA events around one fused-kernel launch, 300 samples"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "b2s::rows_kernel", "algorithmic_bytes_per_event": bpe,
+                         "traffic": measured_traffic(name, B), "kernel": plan.kernel, "algorithmic_bytes_per_event": bpe,
                          "kernel_ms_per_launch": kms, "peak_source": peak_src},
             "gpu_launches": int(launches),
             "clocks": clocks,

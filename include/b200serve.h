@@ -128,6 +128,8 @@ int b2s_plan_add_tree_model(b2s_plan_t plan, int32_t n_trees, const int32_t* tre
 int b2s_plan_set_vote(b2s_plan_t plan, int32_t vote_kind, const double* weights, int32_t n_weights);
 /* Upload tables to HBM, pick kernels, size staging buffers.  After this the plan is immutable. */
 int b2s_plan_finalize(b2s_plan_t plan);
+/* name + template parameters of the kernel family the plan launches (diagnostics / bench provenance) */
+const char* b2s_plan_kernel(b2s_plan_t plan);
 /* out_cols 4-byte words per output row; out_is_int != 0 when they are int32 labels */
 int b2s_plan_out_info(b2s_plan_t plan, int32_t* out_cols, int32_t* out_is_int);
 

@@ -62,6 +62,7 @@ SIGNATURES = {
     "b2s_plan_set_vote": (C.c_int, [_vp, _i32, _pf64, _i32]),
     "b2s_plan_finalize": (C.c_int, [_vp]),
     "b2s_plan_out_info": (C.c_int, [_vp, _pi32, _pi32]),
+    "b2s_plan_kernel": (C.c_char_p, [_vp]),
     "b2s_run_device": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "b2s_run_host": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, C.POINTER(Stats)]),
     "b2s_submit": (C.c_int, [_vp, _vp, _i64, _i64, C.POINTER(_u64)]),

@@ -316,7 +316,7 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   r.pitch = p->rt_pitch;
   r.stages = p->rt_stages;
   {
-    static const int bulk_env = getenv("B2S_TMA") ? atoi(getenv("B2S_TMA")) : 0;
+    static const int bulk_env = getenv("B2S_TMA") ? atoi(getenv("B2S_TMA")) : 1;  // TMA tile loads by default
     r.use_bulk = bulk_env;
   }
   int tr = p->rt_tile_rows;
@@ -1102,6 +1102,18 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
   for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&p->ev[i]));
   p->finalized = true;
   return B2S_OK;
+}
+
+// which kernel family a finalized plan launches (so that a silent fallback cannot hide in a benchmark)
+extern "C" const char* b2s_plan_kernel(b2s_plan_t p) {
+  if (!p || !p->finalized) return "";
+  static thread_local char buf[160];
+  const bool bulk = getenv("B2S_TMA") ? atoi(getenv("B2S_TMA")) != 0 : true;
+  if (p->t2_ok) snprintf(buf, sizeof(buf), "trees_model_kernel<%d> + vote_kernel (models resident in shared memory)", p->t2_NS);
+  else if (p->rt_ok) snprintf(buf, sizeof(buf), "rowthread_kernel<NCH=%d,NS=%d,TPR=%d,%s>", p->rt_NCH, p->rt_NS, p->rt_TPR, bulk ? "TMA bulk loads" : "cp.async loads");
+  else if (p->rw_ok) snprintf(buf, sizeof(buf), "rowwarp_kernel<L=%d,CPL=%d,NS=%d,U=%d,CS=%d>", p->rw_L, p->rw_CPL, p->rw_NS, p->rw_U, p->rw_CS);
+  else snprintf(buf, sizeof(buf), "rows_kernel<%s,NS=%d>", p->mode == MODE_LINEAR ? "LINEAR" : (p->mode == MODE_TREES ? "TREES" : "STORE"), p->NS);
+  return buf;
 }
 
 extern "C" int b2s_plan_out_info(b2s_plan_t p, int32_t* out_cols, int32_t* out_is_int) {

@@ -137,6 +137,11 @@ class DevicePlan:
         return self
 
     @property
+    def kernel(self):
+        """which CUDA kernel family this plan launches"""
+        return self._lib.b2s_plan_kernel(self._h).decode()
+
+    @property
     def out_dtype(self):
         return np.int32 if self.out_is_int else np.float32
 
