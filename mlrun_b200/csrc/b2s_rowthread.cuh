@@ -15,6 +15,9 @@
 //   model input surfaces as a non-finite score (NaN/Inf survive fma even with a zero weight), which is
 //   what the per-row status tests.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is resolved at run time by the host)
+#include <type_traits>
+
 #include "b2s_device.cuh"
 
 namespace b2s {
@@ -53,9 +56,28 @@ struct RTParams {
   float cat_val[kRTMaxCats];
 };
 
+// how a thread finds the 16-byte chunks of its row inside the shared-memory tile
+struct RowPadded {  // LDGSTS / per-row bulk copies: rows `pitch` words apart (pitch = 16 mod 128 bytes)
+  const float* xr;
+  __device__ __forceinline__ float4 chunk(int ch) const { return *reinterpret_cast<const float4*>(xr + ch * 4); }
+  __device__ __forceinline__ float at(int col) const { return xr[col]; }
+};
+struct RowSwizzled {  // 2-D TMA boxes of 32 floats x TR rows, SWIZZLE_128B: chunk j of row r sits at j ^ (r & 7)
+  const float* box0;  // row r of box 0
+  int box_words;      // TR * 32
+  int r7s;            // (r & 7) << 2, in floats
+  __device__ __forceinline__ float4 chunk(int ch) const {
+    return *reinterpret_cast<const float4*>(box0 + (ch >> 3) * box_words + (((ch & 7) << 2) ^ r7s));
+  }
+  __device__ __forceinline__ float at(int col) const {
+    const int ch = col >> 2;
+    return box0[(ch >> 3) * box_words + ((((ch & 7) << 2) ^ r7s) | (col & 3))];
+  }
+};
+
 // dot products of the chunks [CH0, CH1) of one row with all NS weight columns
-template <int NCH, int NS, int CH0, int CH1>
-__device__ __forceinline__ void rt_slice(const RTParams<NCH, NS>& p, const float* __restrict__ xr, double (&acc)[NS]) {
+template <int NCH, int NS, int CH0, int CH1, typename Row>
+__device__ __forceinline__ void rt_slice(const RTParams<NCH, NS>& p, const Row& xr, double (&acc)[NS]) {
   constexpr int BATCH = 4;  // chunks converted before their DFMAs are issued (ILP)
 #pragma unroll
   for (int b = CH0; b < CH1; b += BATCH) {
@@ -64,7 +86,7 @@ __device__ __forceinline__ void rt_slice(const RTParams<NCH, NS>& p, const float
     for (int cb = 0; cb < BATCH; ++cb) {
       const int ch = b + cb;
       if (ch < CH1) {
-        const float4 v = *reinterpret_cast<const float4*>(xr + ch * 4);
+        const float4 v = xr.chunk(ch);
         const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -118,8 +140,18 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                : "memory");
 }
 
-template <int NCH, int NS, int TPR, bool BULK>
-__global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) rowthread_kernel(const __grid_constant__ RTParams<NCH, NS> p) {
+__device__ __forceinline__ void tensor_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          (uint32_t)__cvta_generic_to_shared(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"((uint32_t)__cvta_generic_to_shared(bar))
+      : "memory");
+}
+
+// LM: how tiles reach shared memory -- 0 LDGSTS (cp.async), 1 one TMA bulk copy per row, 2 TMA tensor-map boxes (swizzled)
+template <int NCH, int NS, int TPR, int LM>
+__global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4))
+    rowthread_kernel(const __grid_constant__ RTParams<NCH, NS> p, const __grid_constant__ CUtensorMap tmap) {
   static_assert(NCH % TPR == 0, "chunks must split evenly over the row's threads");
   constexpr int CPT = NCH / TPR;  // chunks per thread
   extern __shared__ __align__(16) unsigned char smem[];
@@ -128,11 +160,15 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) 
   const size_t wcat_bytes = 64 + (((size_t)(p.n_cat + 1) * NS * 8 + 15) / 16) * 16;
   double* s_part = reinterpret_cast<double*>(smem + wcat_bytes);  // [(TPR-1)][128][NS]
   float* s_tiles = reinterpret_cast<float*>(smem + wcat_bytes + (size_t)(TPR - 1) * 128 * NS * 8);
+  if (LM == 2) {  // swizzled TMA boxes need a 1024-byte aligned base (the host reserved the slack)
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(s_tiles);
+    s_tiles += ((1024u - (a & 1023u)) & 1023u) >> 2;
+  }
 
   const int tid = threadIdx.x;
   const int TR = p.tile_rows;
   const int S = p.stages;
-  const int tile_words = TR * p.pitch;
+  const int tile_words = (LM == 2) ? TR * NCH * 4 : TR * p.pitch;
   const int64_t n_tiles = (p.n_rows + TR - 1) / TR;
   const int q = tid / TR;       // slice of the row (warp-uniform: TR is a multiple of 32)
   const int r = tid - q * TR;   // row inside the tile
@@ -170,14 +206,28 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) 
   };
 
   // bulk (TMA) variant: one mbarrier per stage; row `tid` of the tile is fetched by thread `tid`
-  constexpr bool bulk = BULK;
+  constexpr bool bulk = LM != 0;
   const uint32_t row_bytes = (uint32_t)p.n_in * 4u;
   auto issue_bulk = [&](int st, int64_t row0) {
     int64_t left = p.n_rows - row0;
     const int rows = left < TR ? (left < 0 ? 0 : (int)left) : TR;
-    if (tid == 0) mbar_expect_tx(&s_bar[st], (uint32_t)rows * row_bytes);
-    if (tid < rows)
-      bulk_load(s_tiles + st * tile_words + tid * p.pitch, p.rows + (row0 + tid) * p.row_stride, row_bytes, &s_bar[st]);
+    if (LM == 2) {
+      // one thread, NCH/8 box copies of (32 floats x TR rows); rows past the end are zero-filled by the TMA unit
+      if (tid == 0) {
+        if (rows > 0) {
+          mbar_expect_tx(&s_bar[st], (uint32_t)(NCH / 8) * (uint32_t)TR * 128u);
+#pragma unroll
+          for (int b = 0; b < NCH / 8; ++b)
+            tensor_load_2d(s_tiles + st * tile_words + b * TR * 32, &tmap, b * 32, (int)row0, &s_bar[st]);
+        } else {
+          mbar_expect_tx(&s_bar[st], 0);
+        }
+      }
+    } else {
+      if (tid == 0) mbar_expect_tx(&s_bar[st], (uint32_t)rows * row_bytes);
+      if (tid < rows)
+        bulk_load(s_tiles + st * tile_words + tid * p.pitch, p.rows + (row0 + tid) * p.row_stride, row_bytes, &s_bar[st]);
+    }
   };
   if (bulk) {
     if (tid == 0) {
@@ -222,7 +272,15 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) 
     const float* tile = s_tiles + stage * tile_words;
     const int64_t row = t * TR + r;
     const bool live = row < p.n_rows;
-    const float* xr = tile + r * p.pitch;
+    using Row = typename std::conditional<LM == 2, RowSwizzled, RowPadded>::type;
+    Row xr;
+    if constexpr (LM == 2) {
+      xr.box0 = tile + r * 32;
+      xr.box_words = TR * 32;
+      xr.r7s = (r & 7) << 2;
+    } else {
+      xr.xr = tile + r * p.pitch;
+    }
     double acc[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) acc[k] = 0.0;
@@ -234,7 +292,7 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)) 
       else rt_slice<NCH, NS, (TPR > 3 ? 3 * CPT : 0), (TPR > 3 ? 4 * CPT : 0)>(p, xr, acc);
       // one-hot columns, dealt round-robin to the row's threads (table operands: indexed constant loads)
       for (int cc = (TPR > 1 ? q : 0); cc < p.n_cat_cols; cc += TPR) {
-        float x = xr[p.cat_col[cc]];
+        float x = xr.at(p.cat_col[cc]);
         x = (x != x) ? p.cat_fill[cc] : x;
         const int b0 = p.cat_base[cc];
         int j = p.n_cat;  // the zero row: no category matched

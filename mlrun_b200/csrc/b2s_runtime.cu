@@ -225,6 +225,35 @@ static cudaError_t launch_rw(int L, int CPL, int NS, int CS, const RWParams& rp,
   return cudaErrorInvalidValue;
 }
 
+// cuTensorMapEncodeTiled, resolved at run time (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      sym = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(sym);
+  }();
+  return fn;
+}
+// rows viewed as a 2-D float32 tensor {n_in, n_rows}; boxes of 32 floats x tile_rows, 128-byte swizzle
+static bool encode_rows_map(CUtensorMap* map, const void* rows, int64_t n_rows, int64_t stride, int n_in, int tile_rows) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)n_in, (cuuint64_t)n_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)stride};
+  cuuint32_t box[2] = {32u, (cuuint32_t)tile_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(rows), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct RTTables {  // what rt_build needs from finalize
   int n_in, n_out_cols, n_models, vote_kind, out_is_int, fast_epilogue, NS;
   const std::vector<float>* fill;
@@ -288,21 +317,26 @@ static void rt_build(b2s_plan_s* p, const RTTables& t) {
   for (int i = 0; i < r.n_cat; ++i) r.cat_val[i] = (*t.cat_val)[i];
 }
 
+static int rt_load_mode() {  // B2S_TMA: 0 cp.async (LDGSTS), 1 one TMA bulk copy per row, 2 TMA tensor-map boxes (default)
+  static const int mode = getenv("B2S_TMA") ? atoi(getenv("B2S_TMA")) : 2;
+  return mode;
+}
+
 template <int NCH, int NS, int TPR>
 static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
                                 int vec_ok, cudaStream_t st, bool query, int* occ) {
   using P = RTParams<NCH, NS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)G.prop.sharedMemPerBlockOptin);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)G.prop.sharedMemPerBlockOptin);
+    const int cap = (int)G.prop.sharedMemPerBlockOptin;
+    cudaError_t e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess && NCH >= 8)
+      e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, (NCH >= 8 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS, TPR, false>, 128 * TPR, p->rt_smem);
+  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS, TPR, 0>, 128 * TPR, p->rt_smem);
   P r = *reinterpret_cast<const P*>(p->rt_blob.data());
   r.rows = (const char*)rows;
   r.row_stride = stride;
@@ -315,19 +349,22 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   for (int g = 0; g < r.n_peers; ++g) r.peers[g] = (float*)p->peers[g];
   r.pitch = p->rt_pitch;
   r.stages = p->rt_stages;
-  {
-    static const int bulk_env = getenv("B2S_TMA") ? atoi(getenv("B2S_TMA")) : 1;  // TMA tile loads by default
-    r.use_bulk = bulk_env;
-  }
   int tr = p->rt_tile_rows;
   while (tr > 32 && (n_rows + tr - 1) / tr < (int64_t)G.prop.multiProcessorCount) tr /= 2;
   r.tile_rows = tr;
   const int64_t tiles = (n_rows + tr - 1) / tr;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->rt_grid, tiles));
-  if (r.use_bulk && vec_ok)
-    rowthread_kernel<NCH, NS, TPR, true><<<grid, tr * TPR, p->rt_smem, st>>>(r);
+  int mode = vec_ok ? rt_load_mode() : 0;
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (mode == 2 && !(NCH >= 8 && p->n_in == NCH * 4 && encode_rows_map(&tmap, rows, n_rows, stride, p->n_in, tr))) mode = 1;
+  r.use_bulk = mode;
+  if (mode == 2)
+    rowthread_kernel<NCH, NS, TPR, (NCH >= 8 ? 2 : 1)><<<grid, tr * TPR, p->rt_smem, st>>>(r, tmap);
+  else if (mode == 1)
+    rowthread_kernel<NCH, NS, TPR, 1><<<grid, tr * TPR, p->rt_smem, st>>>(r, tmap);
   else
-    rowthread_kernel<NCH, NS, TPR, false><<<grid, tr * TPR, p->rt_smem, st>>>(r);
+    rowthread_kernel<NCH, NS, TPR, 0><<<grid, tr * TPR, p->rt_smem, st>>>(r, tmap);
   return cudaGetLastError();
 }
 
@@ -980,7 +1017,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       p->rt_TPR = tprs ? atoi(tprs) : rt_tpr(p->rt_NCH);
       if (p->rt_TPR != 1 && p->rt_TPR != 2 && p->rt_TPR != 4) p->rt_TPR = 1;
       while (p->rt_TPR > 1 && (p->rt_NCH < 4 * p->rt_TPR)) p->rt_TPR /= 2;
-      p->rt_smem = (int)(64 + align_up((size_t)(cat_val.size() + 1) * NS * 8, 16) + (size_t)(p->rt_TPR - 1) * 128 * NS * 8 +
+      p->rt_smem = (int)(1024 + 64 + align_up((size_t)(cat_val.size() + 1) * NS * 8, 16) + (size_t)(p->rt_TPR - 1) * 128 * NS * 8 +
                          (size_t)p->rt_stages * 128 * rpitch * 4);
       int occ = 0;
       if (p->rt_smem <= smem_cap && rt_launch(p, nullptr, 0, 0, nullptr, nullptr, 0, nullptr, true, &occ) == cudaSuccess && occ >= 1) {
@@ -1108,9 +1145,10 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
 extern "C" const char* b2s_plan_kernel(b2s_plan_t p) {
   if (!p || !p->finalized) return "";
   static thread_local char buf[160];
-  const bool bulk = getenv("B2S_TMA") ? atoi(getenv("B2S_TMA")) != 0 : true;
+  int lm = rt_load_mode();
+  if (lm == 2 && !(p->rt_NCH >= 8 && p->n_in == p->rt_NCH * 4 && tensor_map_encoder())) lm = 1;
   if (p->t2_ok) snprintf(buf, sizeof(buf), "trees_model_kernel<%d> + vote_kernel (models resident in shared memory)", p->t2_NS);
-  else if (p->rt_ok) snprintf(buf, sizeof(buf), "rowthread_kernel<NCH=%d,NS=%d,TPR=%d,%s>", p->rt_NCH, p->rt_NS, p->rt_TPR, bulk ? "TMA bulk loads" : "cp.async loads");
+  else if (p->rt_ok) snprintf(buf, sizeof(buf), "rowthread_kernel<NCH=%d,NS=%d,TPR=%d,%s>", p->rt_NCH, p->rt_NS, p->rt_TPR, lm == 2 ? "TMA tensor-map loads" : (lm == 1 ? "TMA bulk loads" : "cp.async loads"));
   else if (p->rw_ok) snprintf(buf, sizeof(buf), "rowwarp_kernel<L=%d,CPL=%d,NS=%d,U=%d,CS=%d>", p->rw_L, p->rw_CPL, p->rw_NS, p->rw_U, p->rw_CS);
   else snprintf(buf, sizeof(buf), "rows_kernel<%s,NS=%d>", p->mode == MODE_LINEAR ? "LINEAR" : (p->mode == MODE_TREES ? "TREES" : "STORE"), p->NS);
   return buf;
