@@ -44,8 +44,12 @@ struct RTParams {
   const ModelDesc* models;
   const int32_t* classes;
   double w[NCH * 4][NS];    // constant-bank operands
-  float fill[NCH * 4];      // NaN: column not imputed
-  uint32_t cmask[NCH * 4];  // all-ones: column feeds a COPY output
+  // Imputer + "column is not a model input" in one compare/select:  x = !(|x| <= lim[c]) ? fill[c] : x
+  //   model input, imputed:      lim = +Inf, fill = the Imputer value (only NaN fails the compare)
+  //   model input, not imputed:  lim = +Inf, fill = NaN
+  //   one-hot source / dropped:  lim = -1,   fill = +0   (every value is replaced, so Inf * 0 cannot appear)
+  float fill[NCH * 4];
+  float lim[NCH * 4];
   double bias[NS];
   double vote_w[NS];
   int32_t cat_col[kRTMaxCatCols];   // input column of each categorical column
@@ -53,6 +57,8 @@ struct RTParams {
   int32_t cat_cnt[kRTMaxCatCols];
   float cat_fill[kRTMaxCatCols];
   float cat_inl[kRTMaxCatCols][kRTCatsInline];  // first categories, NaN padded (never match)
+  int32_t cat_first[kRTMaxCatCols];  // dense columns: the categories are the integers first, first+1, ...
+  int32_t cat_dense[kRTMaxCatCols];
   float cat_val[kRTMaxCats];
 };
 
@@ -92,8 +98,8 @@ __device__ __forceinline__ void rt_slice(const RTParams<NCH, NS>& p, const Row& 
         for (int u = 0; u < 4; ++u) {
           const int c = ch * 4 + u;
           float x = xs[u];
-          x = (x != x) ? p.fill[c] : x;                                               // Imputer
-          xd[cb * 4 + u] = (double)__uint_as_float(__float_as_uint(x) & p.cmask[c]);  // non-copied -> +0
+          x = !(fabsf(x) <= p.lim[c]) ? p.fill[c] : x;  // Imputer / non-input -> +0 (see RTParams)
+          xd[cb * 4 + u] = (double)x;
         }
       }
     }
@@ -109,6 +115,34 @@ __device__ __forceinline__ void rt_slice(const RTParams<NCH, NS>& p, const Row& 
         }
       }
     }
+  }
+}
+
+// one-hot columns Q0, Q0+TPR, ... of one row: "onehot(x) . w" is a gather from the shared-memory weight rows.
+// Called from a warp-uniform branch with a literal Q0, so the column counter and every table lookup stay
+// in the uniform datapath.
+template <int NCH, int NS, int Q0, int TPR, typename Row>
+__device__ __forceinline__ void rt_cats(const RTParams<NCH, NS>& p, const Row& xr, const double* __restrict__ s_wcat,
+                                        double (&acc)[NS]) {
+  for (int cc = Q0; cc < p.n_cat_cols; cc += TPR) {
+    float x = xr.at(p.cat_col[cc]);
+    x = (x != x) ? p.cat_fill[cc] : x;
+    const int b0 = p.cat_base[cc];
+    const int cnt = p.cat_cnt[cc];
+    int j = p.n_cat;  // the zero row: no category matched
+    if (p.cat_dense[cc]) {
+      const int i = __float2int_rz(x);  // saturating; NaN -> 0 and fails the equality below
+      const unsigned jj = (unsigned)(i - p.cat_first[cc]);
+      j = ((float)i == x && jj < (unsigned)cnt) ? b0 + (int)jj : j;
+    } else if (cnt <= kRTCatsInline) {
+#pragma unroll
+      for (int qq = kRTCatsInline - 1; qq >= 0; --qq) j = (x == p.cat_inl[cc][qq]) ? b0 + qq : j;
+    } else {
+      for (int qq = 0; qq < cnt; ++qq) j = (x == p.cat_val[b0 + qq]) ? b0 + qq : j;
+    }
+    const double* wc = s_wcat + (size_t)j * NS;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) acc[k] += wc[k];
   }
 }
 
@@ -286,25 +320,19 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4))
     for (int k = 0; k < NS; ++k) acc[k] = 0.0;
     if (live) {
       // the slice index is warp-uniform; each case has compile-time column indices (constant operands)
-      if (TPR == 1 || q == 0) rt_slice<NCH, NS, 0, CPT>(p, xr, acc);
-      else if (q == 1) rt_slice<NCH, NS, (TPR > 1 ? CPT : 0), (TPR > 1 ? 2 * CPT : 0)>(p, xr, acc);
-      else if (q == 2) rt_slice<NCH, NS, (TPR > 2 ? 2 * CPT : 0), (TPR > 2 ? 3 * CPT : 0)>(p, xr, acc);
-      else rt_slice<NCH, NS, (TPR > 3 ? 3 * CPT : 0), (TPR > 3 ? 4 * CPT : 0)>(p, xr, acc);
-      // one-hot columns, dealt round-robin to the row's threads (table operands: indexed constant loads)
-      for (int cc = (TPR > 1 ? q : 0); cc < p.n_cat_cols; cc += TPR) {
-        float x = xr.at(p.cat_col[cc]);
-        x = (x != x) ? p.cat_fill[cc] : x;
-        const int b0 = p.cat_base[cc];
-        int j = p.n_cat;  // the zero row: no category matched
-        if (p.cat_cnt[cc] <= kRTCatsInline) {
-#pragma unroll
-          for (int qq = kRTCatsInline - 1; qq >= 0; --qq) j = (x == p.cat_inl[cc][qq]) ? b0 + qq : j;
-        } else {
-          for (int qq = 0; qq < p.cat_cnt[cc]; ++qq) j = (x == p.cat_val[b0 + qq]) ? b0 + qq : j;
-        }
-        const double* wc = s_wcat + (size_t)j * NS;
-#pragma unroll
-        for (int k = 0; k < NS; ++k) acc[k] += wc[k];
+      // (the row's one-hot columns are dealt round-robin to its threads)
+      if (TPR == 1 || q == 0) {
+        rt_slice<NCH, NS, 0, CPT>(p, xr, acc);
+        rt_cats<NCH, NS, 0, TPR>(p, xr, s_wcat, acc);
+      } else if (q == 1) {
+        rt_slice<NCH, NS, (TPR > 1 ? CPT : 0), (TPR > 1 ? 2 * CPT : 0)>(p, xr, acc);
+        rt_cats<NCH, NS, (TPR > 1 ? 1 : 0), TPR>(p, xr, s_wcat, acc);
+      } else if (q == 2) {
+        rt_slice<NCH, NS, (TPR > 2 ? 2 * CPT : 0), (TPR > 2 ? 3 * CPT : 0)>(p, xr, acc);
+        rt_cats<NCH, NS, (TPR > 2 ? 2 : 0), TPR>(p, xr, s_wcat, acc);
+      } else {
+        rt_slice<NCH, NS, (TPR > 3 ? 3 * CPT : 0), (TPR > 3 ? 4 * CPT : 0)>(p, xr, acc);
+        rt_cats<NCH, NS, (TPR > 3 ? 3 : 0), TPR>(p, xr, s_wcat, acc);
       }
     }
     if (TPR > 1) {  // combine the row's slices in a fixed order (deterministic fp64 sum)

@@ -288,13 +288,14 @@ static void rt_build(b2s_plan_s* p, const RTTables& t) {
   r.models = t.d_models;
   r.classes = t.d_classes;
   for (int c = 0; c < NCH * 4; ++c) {
-    r.fill[c] = std::numeric_limits<float>::quiet_NaN();
-    r.cmask[c] = 0;
+    r.fill[c] = 0.0f;
+    r.lim[c] = -1.0f;
     for (int k = 0; k < NS; ++k) r.w[c][k] = 0.0;
   }
   for (int c = 0; c < t.n_in; ++c) {
-    r.fill[c] = (*t.fill)[c];
-    r.cmask[c] = ((*t.flags)[c] & COL_COPIED) ? 0xffffffffu : 0u;
+    const bool input = ((*t.flags)[c] & COL_COPIED) != 0;  // the column reaches the models as a number
+    r.fill[c] = input ? (*t.fill)[c] : 0.0f;
+    r.lim[c] = input ? std::numeric_limits<float>::infinity() : -1.0f;
     for (int k = 0; k < NS; ++k) r.w[c][k] = (*t.wnum)[(size_t)c * NS + k];
   }
   for (int k = 0; k < NS; ++k) {
@@ -310,6 +311,13 @@ static void rt_build(b2s_plan_s* p, const RTTables& t) {
       r.cat_fill[ncc] = (*t.fill)[c];
       for (int q = 0; q < kRTCatsInline; ++q)
         r.cat_inl[ncc][q] = q < r.cat_cnt[ncc] ? (*t.cat_val)[r.cat_base[ncc] + q] : std::numeric_limits<float>::quiet_NaN();
+      {  // consecutive small integers (the usual integer codes): the index is a conversion, not a search
+        const float f0 = (*t.cat_val)[r.cat_base[ncc]];
+        bool dense = f0 == std::floor(f0) && std::fabs(f0) < 8388608.0f;
+        for (int q = 0; dense && q < r.cat_cnt[ncc]; ++q) dense = (*t.cat_val)[r.cat_base[ncc] + q] == f0 + (float)q;
+        r.cat_dense[ncc] = dense ? 1 : 0;
+        r.cat_first[ncc] = dense ? (int)f0 : 0;
+      }
       ++ncc;
     }
   r.n_cat_cols = ncc;
