@@ -53,6 +53,8 @@ struct RTParams {
   double bias[NS];
   double vote_w[NS];
   int32_t cat_col[kRTMaxCatCols];   // input column of each categorical column
+  int32_t cat_off[kRTMaxCatCols];   // where the column's word sits in a tile row (Row::at2; per launch)
+  int32_t cat_sw[kRTMaxCatCols];
   int32_t cat_base[kRTMaxCatCols];  // first category (index into cat_val / wcat)
   int32_t cat_cnt[kRTMaxCatCols];
   float cat_fill[kRTMaxCatCols];
@@ -66,7 +68,7 @@ struct RTParams {
 struct RowPadded {  // LDGSTS / per-row bulk copies: rows `pitch` words apart (pitch = 16 mod 128 bytes)
   const float* xr;
   __device__ __forceinline__ float4 chunk(int ch) const { return *reinterpret_cast<const float4*>(xr + ch * 4); }
-  __device__ __forceinline__ float at(int col) const { return xr[col]; }
+  __device__ __forceinline__ float at2(int off, int) const { return xr[off]; }
 };
 struct RowSwizzled {  // 2-D TMA boxes of 32 floats x TR rows, SWIZZLE_128B: chunk j of row r sits at j ^ (r & 7)
   const float* box0;  // row r of box 0
@@ -75,10 +77,8 @@ struct RowSwizzled {  // 2-D TMA boxes of 32 floats x TR rows, SWIZZLE_128B: chu
   __device__ __forceinline__ float4 chunk(int ch) const {
     return *reinterpret_cast<const float4*>(box0 + (ch >> 3) * box_words + (((ch & 7) << 2) ^ r7s));
   }
-  __device__ __forceinline__ float at(int col) const {
-    const int ch = col >> 2;
-    return box0[(ch >> 3) * box_words + ((((ch & 7) << 2) ^ r7s) | (col & 3))];
-  }
+  // off = (ch >> 3) * box_words + (col & 3), sw = (ch & 7) << 2 with ch = col >> 2 (set per launch by the host)
+  __device__ __forceinline__ float at2(int off, int sw) const { return box0[off + (sw ^ r7s)]; }
 };
 
 // dot products of the chunks [CH0, CH1) of one row with all NS weight columns
@@ -118,27 +118,40 @@ __device__ __forceinline__ void rt_slice(const RTParams<NCH, NS>& p, const Row& 
   }
 }
 
+// category search for a column whose categories are not consecutive integers (kept out of line: rare)
+template <int NCH, int NS>
+__device__ __noinline__ int rt_cat_search(const RTParams<NCH, NS>& p, int cc, float x) {
+  const int b0 = p.cat_base[cc], cnt = p.cat_cnt[cc];
+  int j = p.n_cat;
+  if (cnt <= kRTCatsInline) {
+#pragma unroll
+    for (int qq = kRTCatsInline - 1; qq >= 0; --qq) j = (x == p.cat_inl[cc][qq]) ? b0 + qq : j;
+  } else {
+    for (int qq = cnt - 1; qq >= 0; --qq) j = (x == p.cat_val[b0 + qq]) ? b0 + qq : j;
+  }
+  return j;
+}
+
 // one-hot columns Q0, Q0+TPR, ... of one row: "onehot(x) . w" is a gather from the shared-memory weight rows.
-// Called from a warp-uniform branch with a literal Q0, so the column counter and every table lookup stay
-// in the uniform datapath.
+// Fully unrolled with literal column slots (the caller's branch on the slice index is warp-uniform), so every
+// table entry is a constant-bank operand and the address arithmetic stays in the uniform datapath.
 template <int NCH, int NS, int Q0, int TPR, typename Row>
 __device__ __forceinline__ void rt_cats(const RTParams<NCH, NS>& p, const Row& xr, const double* __restrict__ s_wcat,
                                         double (&acc)[NS]) {
-  for (int cc = Q0; cc < p.n_cat_cols; cc += TPR) {
-    float x = xr.at(p.cat_col[cc]);
+  constexpr int ITERS = (kRTMaxCatCols - Q0 + TPR - 1) / TPR;
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int cc = Q0 + it * TPR;
+    if (cc >= p.n_cat_cols) break;
+    float x = xr.at2(p.cat_off[cc], p.cat_sw[cc]);
     x = (x != x) ? p.cat_fill[cc] : x;
-    const int b0 = p.cat_base[cc];
-    const int cnt = p.cat_cnt[cc];
-    int j = p.n_cat;  // the zero row: no category matched
-    if (p.cat_dense[cc]) {
+    int j;
+    if (p.cat_dense[cc]) {  // integer codes first, first+1, ...: the index is a conversion
       const int i = __float2int_rz(x);  // saturating; NaN -> 0 and fails the equality below
       const unsigned jj = (unsigned)(i - p.cat_first[cc]);
-      j = ((float)i == x && jj < (unsigned)cnt) ? b0 + (int)jj : j;
-    } else if (cnt <= kRTCatsInline) {
-#pragma unroll
-      for (int qq = kRTCatsInline - 1; qq >= 0; --qq) j = (x == p.cat_inl[cc][qq]) ? b0 + qq : j;
+      j = ((float)i == x && jj < (unsigned)p.cat_cnt[cc]) ? p.cat_base[cc] + (int)jj : p.n_cat;  // n_cat: the zero row
     } else {
-      for (int qq = 0; qq < cnt; ++qq) j = (x == p.cat_val[b0 + qq]) ? b0 + qq : j;
+      j = rt_cat_search(p, cc, x);
     }
     const double* wc = s_wcat + (size_t)j * NS;
 #pragma unroll

@@ -367,6 +367,11 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   memset(&tmap, 0, sizeof(tmap));
   if (mode == 2 && !(NCH >= 8 && p->n_in == NCH * 4 && encode_rows_map(&tmap, rows, n_rows, stride, p->n_in, tr))) mode = 1;
   r.use_bulk = mode;
+  for (int cc = 0; cc < r.n_cat_cols; ++cc) {  // tile-relative position of each categorical column
+    const int col = r.cat_col[cc], ch = col >> 2;
+    r.cat_off[cc] = mode == 2 ? (ch >> 3) * (tr * 32) + (col & 3) : col;
+    r.cat_sw[cc] = mode == 2 ? (ch & 7) << 2 : 0;
+  }
   if (mode == 2)
     rowthread_kernel<NCH, NS, TPR, (NCH >= 8 ? 2 : 1)><<<grid, tr * TPR, p->rt_smem, st>>>(r, tmap);
   else if (mode == 1)
