@@ -25,6 +25,9 @@ namespace b2s {
 constexpr int kRTMaxCatCols = 16;
 constexpr int kRTCatsInline = 4;   // categories compared as constant operands
 constexpr int kRTMaxCats = 256;
+#ifndef RT_R2_MINB
+#define RT_R2_MINB 4  // resident CTAs the two-rows-per-thread variant is compiled for
+#endif
 
 template <int NCH, int NS>
 struct RTParams {
@@ -35,6 +38,7 @@ struct RTParams {
   int32_t* status;
   int32_t n_in, out_cols, n_models, vote_kind, out_is_int, fast_epilogue, tile_rows, pitch, stages, vec_ok;
   int32_t n_cat_cols, n_cat;
+  int32_t one_sync;  // single-barrier tile loop (tensor-map loader, TPR > 1)
   int32_t use_bulk;  // tile rows are fetched with cp.async.bulk (TMA, 1-D) + mbarrier instead of LDGSTS
   float* peers[8];   // ensemble-merge targets (see KParams)
   int64_t peer_off;
@@ -81,25 +85,29 @@ struct RowSwizzled {  // 2-D TMA boxes of 32 floats x TR rows, SWIZZLE_128B: chu
   __device__ __forceinline__ float at2(int off, int sw) const { return box0[off + (sw ^ r7s)]; }
 };
 
-// dot products of the chunks [CH0, CH1) of one row with all NS weight columns
-template <int NCH, int NS, int CH0, int CH1, typename Row>
-__device__ __forceinline__ void rt_slice(const RTParams<NCH, NS>& p, const Row& xr, double (&acc)[NS]) {
-  constexpr int BATCH = 4;  // chunks converted before their DFMAs are issued (ILP)
+// dot products of the chunks [CH0, CH1) of RPT rows with all NS weight columns (the weights, fills and limits
+// are constant-bank / uniform-register operands: with RPT = 2 each is fetched once for two rows)
+template <int NCH, int NS, int CH0, int CH1, int RPT, typename Row>
+__device__ __forceinline__ void rt_slice(const RTParams<NCH, NS>& p, const Row (&xr)[RPT], double (&acc)[RPT][NS]) {
+  constexpr int BATCH = RPT == 1 ? 4 : 2;  // chunks converted before their DFMAs are issued (ILP)
 #pragma unroll
   for (int b = CH0; b < CH1; b += BATCH) {
-    double xd[BATCH * 4];
+    double xd[RPT][BATCH * 4];
 #pragma unroll
     for (int cb = 0; cb < BATCH; ++cb) {
       const int ch = b + cb;
       if (ch < CH1) {
-        const float4 v = xr.chunk(ch);
-        const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = ch * 4 + u;
-          float x = xs[u];
-          x = !(fabsf(x) <= p.lim[c]) ? p.fill[c] : x;  // Imputer / non-input -> +0 (see RTParams)
-          xd[cb * 4 + u] = (double)x;
+        for (int i = 0; i < RPT; ++i) {
+          const float4 v = xr[i].chunk(ch);
+          const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = ch * 4 + u;
+            float x = xs[u];
+            x = !(fabsf(x) <= p.lim[c]) ? p.fill[c] : x;  // Imputer / non-input -> +0 (see RTParams)
+            xd[i][cb * 4 + u] = (double)x;
+          }
         }
       }
     }
@@ -111,7 +119,9 @@ __device__ __forceinline__ void rt_slice(const RTParams<NCH, NS>& p, const Row& 
         for (int u = 0; u < 4; ++u) {
           const int c = ch * 4 + u;
 #pragma unroll
-          for (int k = 0; k < NS; ++k) acc[k] = fma(p.w[c][k], xd[cb * 4 + u], acc[k]);
+          for (int k = 0; k < NS; ++k)
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) acc[i][k] = fma(p.w[c][k], xd[i][cb * 4 + u], acc[i][k]);
         }
       }
     }
@@ -135,27 +145,30 @@ __device__ __noinline__ int rt_cat_search(const RTParams<NCH, NS>& p, int cc, fl
 // one-hot columns Q0, Q0+TPR, ... of one row: "onehot(x) . w" is a gather from the shared-memory weight rows.
 // Fully unrolled with literal column slots (the caller's branch on the slice index is warp-uniform), so every
 // table entry is a constant-bank operand and the address arithmetic stays in the uniform datapath.
-template <int NCH, int NS, int Q0, int TPR, typename Row>
-__device__ __forceinline__ void rt_cats(const RTParams<NCH, NS>& p, const Row& xr, const double* __restrict__ s_wcat,
-                                        double (&acc)[NS]) {
+template <int NCH, int NS, int Q0, int TPR, int RPT, typename Row>
+__device__ __forceinline__ void rt_cats(const RTParams<NCH, NS>& p, const Row (&xr)[RPT], const double* __restrict__ s_wcat,
+                                        double (&acc)[RPT][NS]) {
   constexpr int ITERS = (kRTMaxCatCols - Q0 + TPR - 1) / TPR;
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int cc = Q0 + it * TPR;
     if (cc >= p.n_cat_cols) break;
-    float x = xr.at2(p.cat_off[cc], p.cat_sw[cc]);
-    x = (x != x) ? p.cat_fill[cc] : x;
-    int j;
-    if (p.cat_dense[cc]) {  // integer codes first, first+1, ...: the index is a conversion
-      const int i = __float2int_rz(x);  // saturating; NaN -> 0 and fails the equality below
-      const unsigned jj = (unsigned)(i - p.cat_first[cc]);
-      j = ((float)i == x && jj < (unsigned)p.cat_cnt[cc]) ? p.cat_base[cc] + (int)jj : p.n_cat;  // n_cat: the zero row
-    } else {
-      j = rt_cat_search(p, cc, x);
-    }
-    const double* wc = s_wcat + (size_t)j * NS;
 #pragma unroll
-    for (int k = 0; k < NS; ++k) acc[k] += wc[k];
+    for (int i = 0; i < RPT; ++i) {
+      float x = xr[i].at2(p.cat_off[cc], p.cat_sw[cc]);
+      x = (x != x) ? p.cat_fill[cc] : x;
+      int j;
+      if (p.cat_dense[cc]) {  // integer codes first, first+1, ...: the index is a conversion
+        const int v = __float2int_rz(x);  // saturating; NaN -> 0 and fails the equality below
+        const unsigned jj = (unsigned)(v - p.cat_first[cc]);
+        j = ((float)v == x && jj < (unsigned)p.cat_cnt[cc]) ? p.cat_base[cc] + (int)jj : p.n_cat;  // n_cat: the zero row
+      } else {
+        j = rt_cat_search(p, cc, x);
+      }
+      const double* wc = s_wcat + (size_t)j * NS;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) acc[i][k] += wc[k];
+    }
   }
 }
 
@@ -195,18 +208,47 @@ __device__ __forceinline__ void tensor_load_2d(void* smem_dst, const CUtensorMap
       : "memory");
 }
 
+// classifier links / majority vote / integer outputs: the generic per-row epilogue (out of line)
+template <int NCH, int NS>
+__device__ __noinline__ void rt_generic_epilogue(const RTParams<NCH, NS>& p, const double* sl, int64_t row, uint32_t st) {
+  double pred[kMaxModels];
+  for (int m = 0; m < p.n_models; ++m) {
+    const ModelDesc md = p.models[m];
+    pred[m] = apply_link(md, sl + md.score_off, p.classes);
+  }
+  KParams kp;  // vote_and_store only reads these fields
+  kp.out = p.out;
+  kp.out_cols = p.out_cols;
+  kp.n_models = p.n_models;
+  kp.vote_kind = p.vote_kind;
+  kp.out_is_int = p.out_is_int;
+  kp.vote_w = p.vote_w_g;
+  kp.status = p.status;
+  kp.n_peers = p.n_peers;
+  kp.peer_off = p.peer_off;
+  for (int g = 0; g < p.n_peers; ++g) kp.peers[g] = p.peers[g];
+  vote_and_store(kp, pred, row, st);
+}
+
 // LM: how tiles reach shared memory -- 0 LDGSTS (cp.async), 1 one TMA bulk copy per row, 2 TMA tensor-map boxes (swizzled)
-template <int NCH, int NS, int TPR, int LM>
-__global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4))
+// RPT: rows per thread (2 only with LM = 2): a tile of TR rows is worked on by TR / RPT * TPR threads
+template <int NCH, int NS, int TPR, int LM, int RPT = 1>
+__global__ void __launch_bounds__(128 * TPR / RPT, RPT == 2 ? RT_R2_MINB : (TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4)))
     rowthread_kernel(const __grid_constant__ RTParams<NCH, NS> p, const __grid_constant__ CUtensorMap tmap) {
   static_assert(NCH % TPR == 0, "chunks must split evenly over the row's threads");
+  static_assert(RPT == 1 || LM == 2, "two rows per thread needs the tensor-map loader (one issuing thread)");
   constexpr int CPT = NCH / TPR;  // chunks per thread
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem);  // 4 mbarriers (bulk variant); 64 bytes reserved
   double* s_wcat = reinterpret_cast<double*>(smem + 64);
   const size_t wcat_bytes = 64 + (((size_t)(p.n_cat + 1) * NS * 8 + 15) / 16) * 16;
-  double* s_part = reinterpret_cast<double*>(smem + wcat_bytes);  // [(TPR-1)][128][NS]
-  float* s_tiles = reinterpret_cast<float*>(smem + wcat_bytes + (size_t)(TPR - 1) * 128 * NS * 8);
+  // With the tensor-map loader and TPR > 1 the tile loop has ONE barrier per tile (between the partial sums
+  // and their combination): that barrier also proves the tile's stage is drained, so the next load into it is
+  // issued right there, and the partial sums are double-buffered instead of fenced by a second barrier.
+  const bool one_sync = (LM == 2) && TPR > 1 && p.one_sync;
+  constexpr size_t part_words = (size_t)(TPR - 1) * 128 * NS;
+  double* s_part = reinterpret_cast<double*>(smem + wcat_bytes);  // [one_sync ? 2 : 1][(TPR-1)][128][NS]
+  float* s_tiles = reinterpret_cast<float*>(smem + wcat_bytes + (one_sync ? 2 : 1) * part_words * 8);
   if (LM == 2) {  // swizzled TMA boxes need a 1024-byte aligned base (the host reserved the slack)
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(s_tiles);
     s_tiles += ((1024u - (a & 1023u)) & 1023u) >> 2;
@@ -217,8 +259,9 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4))
   const int S = p.stages;
   const int tile_words = (LM == 2) ? TR * NCH * 4 : TR * p.pitch;
   const int64_t n_tiles = (p.n_rows + TR - 1) / TR;
-  const int q = tid / TR;       // slice of the row (warp-uniform: TR is a multiple of 32)
-  const int r = tid - q * TR;   // row inside the tile
+  const int TRT = TR / RPT;     // threads per slice; thread r works on rows r, r + TRT, ...
+  const int q = tid / TRT;      // slice of the row (warp-uniform: TRT is a multiple of 32)
+  const int r = tid - q * TRT;  // first row inside the tile
 
   // (row, chunk) walk of the tile loader without per-iteration division
   const int cprv = p.vec_ok ? (p.n_in >> 2) : p.n_in;  // units per row: 16-byte chunks or 4-byte words
@@ -283,7 +326,7 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4))
     }
     __syncthreads();
   }
-  for (int s = 0; s < S - 1; ++s) {
+  for (int s = 0; s < (one_sync ? S : S - 1); ++s) {
     const int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
     if (bulk) {
       issue_bulk(s, t * TR);
@@ -295,8 +338,10 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4))
   uint32_t phase_bits = 0;  // bit s: parity to wait for on stage s
   for (int i = tid; i < p.n_cat * NS; i += blockDim.x) s_wcat[i] = p.wcat[i];
   for (int i = tid; i < NS; i += blockDim.x) s_wcat[p.n_cat * NS + i] = 0.0;
+  if (one_sync) __syncthreads();  // the weight rows are read before the loop's first barrier
 
   int stage = 0;
+  uint32_t iter = 0;
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     if (bulk) {
       mbar_wait(&s_bar[stage], (phase_bits >> stage) & 1u);
@@ -304,8 +349,8 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4))
     } else if (S == 2) cp_async_wait<0>();
     else if (S == 3) cp_async_wait<1>();
     else cp_async_wait<2>();
-    __syncthreads();  // tile visible to everybody; everybody is done with the previous tile and s_part
-    {
+    if (!one_sync) {
+      __syncthreads();  // tile visible to everybody; everybody is done with the previous tile and s_part
       const int64_t tn = t + (int64_t)(S - 1) * gridDim.x;
       int sn = stage + S - 1;
       if (sn >= S) sn -= S;
@@ -317,21 +362,26 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4))
       }
     }
     const float* tile = s_tiles + stage * tile_words;
-    const int64_t row = t * TR + r;
-    const bool live = row < p.n_rows;
+    const bool any_live = t * TR + r < p.n_rows;  // rows past the end were zero-filled (TMA) or are skipped
     using Row = typename std::conditional<LM == 2, RowSwizzled, RowPadded>::type;
-    Row xr;
-    if constexpr (LM == 2) {
-      xr.box0 = tile + r * 32;
-      xr.box_words = TR * 32;
-      xr.r7s = (r & 7) << 2;
-    } else {
-      xr.xr = tile + r * p.pitch;
-    }
-    double acc[NS];
+    Row xr[RPT];
 #pragma unroll
-    for (int k = 0; k < NS; ++k) acc[k] = 0.0;
-    if (live) {
+    for (int i = 0; i < RPT; ++i) {
+      const int ri = r + i * TRT;
+      if constexpr (LM == 2) {
+        xr[i].box0 = tile + ri * 32;
+        xr[i].box_words = TR * 32;
+        xr[i].r7s = (r & 7) << 2;  // TRT is a multiple of 8: every row of the thread has the same swizzle phase
+      } else {
+        xr[i].xr = tile + ri * p.pitch;
+      }
+    }
+    double acc[RPT][NS];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+      for (int k = 0; k < NS; ++k) acc[i][k] = 0.0;
+    if (any_live) {
       // the slice index is warp-uniform; each case has compile-time column indices (constant operands)
       // (the row's one-hot columns are dealt round-robin to its threads)
       if (TPR == 1 || q == 0) {
@@ -349,64 +399,60 @@ __global__ void __launch_bounds__(128 * TPR, TPR >= 4 ? 2 : (TPR == 2 ? 3 : 4))
       }
     }
     if (TPR > 1) {  // combine the row's slices in a fixed order (deterministic fp64 sum)
+      double* s_part_cur = s_part + (one_sync ? (size_t)(iter & 1) * part_words : 0);
       if (q > 0) {
-        double* part = s_part + ((size_t)(q - 1) * 128 + r) * NS;
 #pragma unroll
-        for (int k = 0; k < NS; ++k) part[k] = acc[k];
+        for (int i = 0; i < RPT; ++i) {
+          double* part = s_part_cur + ((size_t)(q - 1) * 128 + r + i * TRT) * NS;
+#pragma unroll
+          for (int k = 0; k < NS; ++k) part[k] = acc[i][k];
+        }
       }
       __syncthreads();
+      if (one_sync) issue_bulk(stage, (t + (int64_t)S * gridDim.x) * TR);  // every read of this stage is behind the barrier
       if (q == 0) {
 #pragma unroll
-        for (int qq = 1; qq < TPR; ++qq) {
-          const double* o = s_part + ((size_t)(qq - 1) * 128 + r) * NS;
+        for (int i = 0; i < RPT; ++i)
 #pragma unroll
-          for (int k = 0; k < NS; ++k) acc[k] += o[k];
-        }
+          for (int qq = 1; qq < TPR; ++qq) {
+            const double* o = s_part_cur + ((size_t)(qq - 1) * 128 + r + i * TRT) * NS;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) acc[i][k] += o[k];
+          }
       }
     }
-    if (q == 0 && live) {
-      uint32_t st = 0;
 #pragma unroll
-      for (int k = 0; k < NS; ++k) {
-        acc[k] += p.bias[k];
-        st |= (fabs(acc[k]) <= 1.7976931348623157e308) ? 0u : 1u;
-      }
-      if (p.fast_epilogue) {
-        if (p.vote_kind == 1) {  // VotingEnsemble._mean_vote: sum_m w[m] * pred[m], model order
-          double s = 0.0;
+    for (int i = 0; i < RPT; ++i) {
+      const int64_t row = t * TR + r + i * TRT;
+      if (q == 0 && row < p.n_rows) {
+        uint32_t st = 0;
 #pragma unroll
-          for (int k = 0; k < NS; ++k) s = __dadd_rn(s, __dmul_rn(acc[k], p.vote_w[k]));
-          store_word(p, row, 0, __float_as_uint((float)s));
+        for (int k = 0; k < NS; ++k) {
+          acc[i][k] += p.bias[k];
+          st |= (fabs(acc[i][k]) <= 1.7976931348623157e308) ? 0u : 1u;
+        }
+        if (p.fast_epilogue) {
+          if (p.vote_kind == 1) {  // VotingEnsemble._mean_vote: sum_m w[m] * pred[m], model order
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) s = __dadd_rn(s, __dmul_rn(acc[i][k], p.vote_w[k]));
+            store_word(p, row, 0, __float_as_uint((float)s));
+          } else {
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+              if (k < p.n_models) store_word(p, row, k, __float_as_uint((float)acc[i][k]));
+          }
+          if (p.status) p.status[row] = (int32_t)st;
         } else {
+          double sl[NS];
 #pragma unroll
-          for (int k = 0; k < NS; ++k)
-            if (k < p.n_models) store_word(p, row, k, __float_as_uint((float)acc[k]));
+          for (int k = 0; k < NS; ++k) sl[k] = acc[i][k];
+          rt_generic_epilogue(p, sl, row, st);
         }
-        if (p.status) p.status[row] = (int32_t)st;
-      } else {
-        double sl[NS];
-#pragma unroll
-        for (int k = 0; k < NS; ++k) sl[k] = acc[k];
-        double pred[kMaxModels];
-        for (int m = 0; m < p.n_models; ++m) {
-          const ModelDesc md = p.models[m];
-          pred[m] = apply_link(md, sl + md.score_off, p.classes);
-        }
-        KParams kp;  // vote_and_store only reads these fields
-        kp.out = p.out;
-        kp.out_cols = p.out_cols;
-        kp.n_models = p.n_models;
-        kp.vote_kind = p.vote_kind;
-        kp.out_is_int = p.out_is_int;
-        kp.vote_w = p.vote_w_g;
-        kp.status = p.status;
-        kp.n_peers = p.n_peers;
-        kp.peer_off = p.peer_off;
-        for (int g = 0; g < p.n_peers; ++g) kp.peers[g] = p.peers[g];
-        vote_and_store(kp, pred, row, st);
       }
     }
     ++stage;
+    ++iter;
     if (stage == S) stage = 0;
   }
   cp_async_wait<0>();

@@ -120,7 +120,7 @@ struct b2s_plan_s {
   RWParams rw{};
   // row-thread kernel (constant-bank operands)
   bool rt_ok = false;
-  int rt_NCH = 0, rt_NS = 0, rt_TPR = 1, rt_grid = 0, rt_smem = 0, rt_tile_rows = 128, rt_pitch = 0, rt_stages = 2;
+  int rt_NCH = 0, rt_NS = 0, rt_TPR = 1, rt_grid = 0, rt_smem = 0, rt_tile_rows = 128, rt_pitch = 0, rt_stages = 2, rt_RPT = 1;
   std::vector<char> rt_blob;  // an RTParams<NCH, NS>
   // fused ensemble-merge targets (P2P)
   std::vector<void*> peers;
@@ -334,17 +334,31 @@ template <int NCH, int NS, int TPR>
 static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
                                 int vec_ok, cudaStream_t st, bool query, int* occ) {
   using P = RTParams<NCH, NS>;
+  constexpr int LMT = NCH >= 8 ? 2 : 1;  // the tensor-map variants exist for rows of >= 128 bytes
+  constexpr int R2 = NCH >= 8 ? 2 : 1;
   static bool attr_set = false;
   if (!attr_set) {
     const int cap = (int)G.prop.sharedMemPerBlockOptin;
     cudaError_t e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    if (e == cudaSuccess && NCH >= 8)
-      e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, (NCH >= 8 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess && NCH >= 8) {
+      e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, LMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, LMT, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    }
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS, TPR, 0>, 128 * TPR, p->rt_smem);
+  const bool tmap_ok = NCH >= 8 && p->n_in == NCH * 4 && tensor_map_encoder() != nullptr;
+  if (query) {  // occupancy of the variant an aligned launch takes
+    const int mode = rt_load_mode() == 2 && !tmap_ok ? 1 : rt_load_mode();
+    if (mode == 2 && p->rt_RPT == 2)
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS, TPR, LMT, R2>,
+                                                           p->rt_tile_rows / 2 * TPR, p->rt_smem);
+    if (mode == 2)
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS, TPR, LMT>, p->rt_tile_rows * TPR, p->rt_smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, rowthread_kernel<NCH, NS, TPR, 0>, p->rt_tile_rows * TPR, p->rt_smem);
+  }
   P r = *reinterpret_cast<const P*>(p->rt_blob.data());
   r.rows = (const char*)rows;
   r.row_stride = stride;
@@ -357,23 +371,34 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   for (int g = 0; g < r.n_peers; ++g) r.peers[g] = (float*)p->peers[g];
   r.pitch = p->rt_pitch;
   r.stages = p->rt_stages;
+  int mode = vec_ok ? rt_load_mode() : 0;
+  if (mode == 2 && !tmap_ok) mode = 1;
+  int rpt = (mode == 2) ? p->rt_RPT : 1;
   int tr = p->rt_tile_rows;
-  while (tr > 32 && (n_rows + tr - 1) / tr < (int64_t)G.prop.multiProcessorCount) tr /= 2;
+  while (tr > 32 * rpt && (n_rows + tr - 1) / tr < (int64_t)G.prop.multiProcessorCount) tr /= 2;
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (mode == 2 && !encode_rows_map(&tmap, rows, n_rows, stride, p->n_in, tr)) {
+    mode = 1;
+    rpt = 1;
+  }
   r.tile_rows = tr;
   const int64_t tiles = (n_rows + tr - 1) / tr;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->rt_grid, tiles));
-  int mode = vec_ok ? rt_load_mode() : 0;
-  alignas(64) CUtensorMap tmap;
-  memset(&tmap, 0, sizeof(tmap));
-  if (mode == 2 && !(NCH >= 8 && p->n_in == NCH * 4 && encode_rows_map(&tmap, rows, n_rows, stride, p->n_in, tr))) mode = 1;
   r.use_bulk = mode;
+  {
+    static const int one_sync = getenv("B2S_RT_ONESYNC") ? atoi(getenv("B2S_RT_ONESYNC")) : 0;
+    r.one_sync = one_sync;
+  }
   for (int cc = 0; cc < r.n_cat_cols; ++cc) {  // tile-relative position of each categorical column
     const int col = r.cat_col[cc], ch = col >> 2;
     r.cat_off[cc] = mode == 2 ? (ch >> 3) * (tr * 32) + (col & 3) : col;
     r.cat_sw[cc] = mode == 2 ? (ch & 7) << 2 : 0;
   }
-  if (mode == 2)
-    rowthread_kernel<NCH, NS, TPR, (NCH >= 8 ? 2 : 1)><<<grid, tr * TPR, p->rt_smem, st>>>(r, tmap);
+  if (mode == 2 && rpt == 2)
+    rowthread_kernel<NCH, NS, TPR, LMT, R2><<<grid, tr / 2 * TPR, p->rt_smem, st>>>(r, tmap);
+  else if (mode == 2)
+    rowthread_kernel<NCH, NS, TPR, LMT><<<grid, tr * TPR, p->rt_smem, st>>>(r, tmap);
   else if (mode == 1)
     rowthread_kernel<NCH, NS, TPR, 1><<<grid, tr * TPR, p->rt_smem, st>>>(r, tmap);
   else
@@ -1025,13 +1050,22 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       p->rt_pitch = rpitch;
       const char* stg = getenv("B2S_RT_STAGES");
       p->rt_stages = stg ? std::max(2, std::min(4, atoi(stg))) : 2;
-      p->rt_tile_rows = 128;
+      const char* tile_env = getenv("B2S_RT_TILE");  // rows per tile: 64 | 128
+      p->rt_tile_rows = tile_env && atoi(tile_env) == 64 ? 64 : 128;
+      const char* rpt_env = getenv("B2S_RT_RPT");  // rows per thread: 1 | 2 (2: tensor-map loads only)
+      p->rt_RPT = rpt_env && atoi(rpt_env) == 2 && p->rt_NCH >= 8 ? 2 : 1;
       const char* tprs = getenv("B2S_RT_TPR");
       p->rt_TPR = tprs ? atoi(tprs) : rt_tpr(p->rt_NCH);
       if (p->rt_TPR != 1 && p->rt_TPR != 2 && p->rt_TPR != 4) p->rt_TPR = 1;
       while (p->rt_TPR > 1 && (p->rt_NCH < 4 * p->rt_TPR)) p->rt_TPR /= 2;
-      p->rt_smem = (int)(1024 + 64 + align_up((size_t)(cat_val.size() + 1) * NS * 8, 16) + (size_t)(p->rt_TPR - 1) * 128 * NS * 8 +
-                         (size_t)p->rt_stages * 128 * rpitch * 4);
+      {
+        const size_t fixed = 1024 + 64 + align_up((size_t)(cat_val.size() + 1) * NS * 8, 16);
+        const size_t part = (size_t)(p->rt_TPR - 1) * 128 * NS * 8;
+        // padded tiles + one partial-sum buffer (LDGSTS / per-row bulk), or swizzled tiles + two (tensor map)
+        const size_t padded = fixed + part + (size_t)p->rt_stages * p->rt_tile_rows * rpitch * 4;
+        const size_t swizzled = fixed + 2 * part + (size_t)p->rt_stages * p->rt_tile_rows * p->rt_NCH * 16;
+        p->rt_smem = (int)std::max(padded, swizzled);
+      }
       int occ = 0;
       if (p->rt_smem <= smem_cap && rt_launch(p, nullptr, 0, 0, nullptr, nullptr, 0, nullptr, true, &occ) == cudaSuccess && occ >= 1) {
         p->rt_ok = true;
@@ -1161,7 +1195,7 @@ extern "C" const char* b2s_plan_kernel(b2s_plan_t p) {
   int lm = rt_load_mode();
   if (lm == 2 && !(p->rt_NCH >= 8 && p->n_in == p->rt_NCH * 4 && tensor_map_encoder())) lm = 1;
   if (p->t2_ok) snprintf(buf, sizeof(buf), "trees_model_kernel<%d> + vote_kernel (models resident in shared memory)", p->t2_NS);
-  else if (p->rt_ok) snprintf(buf, sizeof(buf), "rowthread_kernel<NCH=%d,NS=%d,TPR=%d,%s>", p->rt_NCH, p->rt_NS, p->rt_TPR, lm == 2 ? "TMA tensor-map loads" : (lm == 1 ? "TMA bulk loads" : "cp.async loads"));
+  else if (p->rt_ok) snprintf(buf, sizeof(buf), "rowthread_kernel<NCH=%d,NS=%d,TPR=%d,RPT=%d,%s>", p->rt_NCH, p->rt_NS, p->rt_TPR, lm == 2 ? p->rt_RPT : 1, lm == 2 ? "TMA tensor-map loads" : (lm == 1 ? "TMA bulk loads" : "cp.async loads"));
   else if (p->rw_ok) snprintf(buf, sizeof(buf), "rowwarp_kernel<L=%d,CPL=%d,NS=%d,U=%d,CS=%d>", p->rw_L, p->rw_CPL, p->rw_NS, p->rw_U, p->rw_CS);
   else snprintf(buf, sizeof(buf), "rows_kernel<%s,NS=%d>", p->mode == MODE_LINEAR ? "LINEAR" : (p->mode == MODE_TREES ? "TREES" : "STORE"), p->NS);
   return buf;
