@@ -2,16 +2,15 @@
 //
 // A root->leaf walk is a chain of dependent gathers; from L2 (the generic kernel, tables ~1 MB for
 // 4 x 100 depth-6 trees) every level costs ~250 cycles.  Here each persistent CTA owns ONE model of the
-// router: its trees are re-packed on the host into complete (heap-ordered) depth-D trees -- 8-byte
-// internal nodes {feature, float32 threshold}, children implicit (2i+1 + go_right), fp64 leaves -- about
-// 1 KB per depth-6 tree, ~100 KB per 100-tree model, copied to shared memory once per kernel.  Rows
-// stream through a cp.async ring (same padded tile as the linear kernels); thread (g, r) walks the trees
-// t = g, g+G, ... of row r, so one level is two LDS (node, feature value) + compare + index update.
-// The G partial sums of a row are combined in shared memory in a fixed order; the link function
-// (identity / >0 / >=0 / argmax) is applied per model and the prediction goes to a small fp64 buffer
-// pred[row][model]; `vote_kernel` then applies the VotingEnsemble reduce (routers.py:708-741) and the
-// row status.  Rows are read once per model (M x 4*n_in bytes/event, mostly from L2): the path is
-// bound by shared-memory gather throughput, not by HBM.
+// router: its trees are re-packed on the host into complete (heap-ordered) depth-D trees, ~1 KB per
+// depth-6 tree, ~100 KB per 100-tree model, copied to shared memory once per kernel (layout below).
+// Rows land row-major through cp.async and are transposed in shared memory; thread (g, r) walks the trees
+// t = g, g+G, ... of row r, four walks in flight, so one level is three conflict-free LDS (feature offset,
+// threshold, feature value) + compare + index update.  The G partial sums of a row are combined in shared
+// memory in a fixed order; the link function (identity / >0 / >=0 / argmax) is applied per model and the
+// prediction goes to a small fp64 buffer pred[row][model]; `vote_kernel` then applies the VotingEnsemble
+// reduce (routers.py:708-741) and the row status.  Rows are read once per model (M x 4*n_in bytes/event,
+// mostly from L2): the path is bound by shared-memory gather throughput (wavefronts), not by HBM.
 #pragma once
 #include "b2s_device.cuh"
 
@@ -44,6 +43,15 @@ struct T2Params {
   int32_t sm_tables, sm_part, sm_tiles;  // byte offsets
 };
 
+// Shared-memory layout of one model (built once per CTA from the T2Model arrays):
+//   s_foff[t][1..NI]  byte offset of the node's feature column inside the transposed tile (feature * TR * 4)
+//   s_thr [t][1..NI]  float32 threshold                      (1-based heap: children of n are 2n, 2n+1)
+//   s_leaf[t][NL]     tree_scale * leaf value (fp64; the product the scalar path computes per visit)
+//   s_slot[t]         score slot of the tree (multi-class models)
+// The event tile is TRANSPOSED in shared memory (xt[feature][row]): the 32 lanes of a warp are 32 consecutive
+// rows walking the same tree, so the feature gather hits 32 different banks whatever features the lanes are
+// at; with row-major tiles (pitch = 4 words mod 32) the same gather is a 4-way bank conflict.  Node words of
+// one level are consecutive 4-byte words: lanes at different nodes of a level never conflict either.
 template <int NS>
 __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant__ T2Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -53,25 +61,27 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
   const int nparts = (gridDim.x - m + p.n_models - 1) / p.n_models;  // CTAs working on model m
   const T2Model tm = p.t2[m];
   const ModelDesc md = p.models[m];
-
-  // ---- the model's tables -> shared memory (once)
-  HeapNode* s_nodes = reinterpret_cast<HeapNode*>(smem + p.sm_tables);
-  const int n_nodes = tm.n_trees * tm.n_internal;
-  double* s_leaves = reinterpret_cast<double*>(smem + p.sm_tables + (((size_t)n_nodes * 8 + 15) / 16) * 16);
-  const int n_leaves = tm.n_trees * tm.n_leaves;
-  {
-    const int2* src = reinterpret_cast<const int2*>(tm.nodes);
-    int2* dst = reinterpret_cast<int2*>(s_nodes);
-    for (int i = tid; i < n_nodes; i += blockDim.x) dst[i] = __ldg(src + i);
-    for (int i = tid; i < n_leaves; i += blockDim.x) s_leaves[i] = __ldg(tm.leaves + i);
-  }
-  double* s_part = reinterpret_cast<double*>(smem + p.sm_part);  // [groups][tile_rows][NS]
-  float* s_tiles = reinterpret_cast<float*>(smem + p.sm_tiles);
-
   const int TR = p.tile_rows;
   const int G = p.groups;
-  const int S = p.stages;
-  const int tile_words = TR * p.pitch;
+  const int NI = tm.n_internal, NL = tm.n_leaves, NT = tm.n_trees;
+
+  // ---- the model's tables -> shared memory (once)
+  const int n_nodes = NT * NI;
+  int32_t* s_foff = reinterpret_cast<int32_t*>(smem + p.sm_tables);
+  float* s_thr = reinterpret_cast<float*>(s_foff + n_nodes);
+  double* s_leaf = reinterpret_cast<double*>(smem + p.sm_tables + (((size_t)n_nodes * 8 + 15) / 16) * 16);
+  int32_t* s_slot = reinterpret_cast<int32_t*>(s_leaf + (size_t)NT * NL);
+  for (int i = tid; i < n_nodes; i += blockDim.x) {
+    const HeapNode nd = tm.nodes[i];
+    s_foff[i] = nd.feature * TR * 4;
+    s_thr[i] = nd.threshold;
+  }
+  for (int i = tid; i < NT * NL; i += blockDim.x) s_leaf[i] = __dmul_rn(tm.scale[i / NL], tm.leaves[i]);
+  for (int i = tid; i < NT; i += blockDim.x) s_slot[i] = tm.slot[i];
+  double* s_part = reinterpret_cast<double*>(smem + p.sm_part);  // [groups - 1][tile_rows][NS]
+  float* s_stage = reinterpret_cast<float*>(smem + p.sm_tiles);  // row-major landing tile (cp.async)
+  float* s_xt = s_stage + (size_t)TR * p.pitch;                  // transposed tile [n_in][TR]
+
   const int64_t n_tiles = (p.n_rows + TR - 1) / TR;
   const int g = tid / TR;  // tree group (warp-uniform: TR is a multiple of 32)
   const int r = tid - g * TR;
@@ -79,16 +89,16 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
   const int cprv = p.vec_ok ? (p.n_in >> 2) : p.n_in;
   const int r0 = tid / cprv, c0 = tid - r0 * cprv;
   const int dr = (int)blockDim.x / cprv, dc = (int)blockDim.x - dr * cprv;
-  auto issue = [&](float* tile, int64_t row0) {
+  auto issue = [&](int64_t row0) {
     int64_t left = p.n_rows - row0;
     const int rows = left < TR ? (left < 0 ? 0 : (int)left) : TR;
     const char* base = p.rows + row0 * p.row_stride;
     int rr = r0, cc = c0;
     while (rr < rows) {
       if (p.vec_ok)
-        cp_async16(tile + rr * p.pitch + cc * 4, base + (int64_t)rr * p.row_stride + cc * 16);
+        cp_async16(s_stage + rr * p.pitch + cc * 4, base + (int64_t)rr * p.row_stride + cc * 16);
       else
-        cp_async4(tile + rr * p.pitch + cc, base + (int64_t)rr * p.row_stride + cc * 4);
+        cp_async4(s_stage + rr * p.pitch + cc, base + (int64_t)rr * p.row_stride + cc * 4);
       rr += dr;
       cc += dc;
       if (cc >= cprv) {
@@ -98,43 +108,94 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
     }
   };
 
-  for (int s = 0; s < S - 1; ++s) {
-    const int64_t t = (int64_t)part + (int64_t)s * nparts;
-    if (t < n_tiles) issue(s_tiles + s * tile_words, t * TR);
-    cp_async_commit();
-  }
-  int stage = 0;
+  if ((int64_t)part < n_tiles) issue((int64_t)part * TR);
+  cp_async_commit();
+  const char* xt_r = reinterpret_cast<const char*>(s_xt + r);
+  const int leaf_bias = NL;  // n - NL is the leaf index
   for (int64_t t = part; t < n_tiles; t += nparts) {
-    if (S == 2) cp_async_wait<0>();
-    else cp_async_wait<1>();
-    __syncthreads();  // tile (and, first time round, the tables) visible; previous tile fully consumed
+    cp_async_wait<0>();
+    __syncthreads();  // landing tile (and, first time round, the tables) visible; the previous walk is over
+    {                 // transpose: lanes take consecutive rows, so both the LDS and the STS are conflict-free
+      const int64_t left = p.n_rows - t * TR;
+      const int rows = left < TR ? (int)left : TR;
+      if ((p.n_in & 3) == 0) {  // one 16-byte LDS per (row, chunk), four 4-byte STS
+        for (int i = tid; i < (p.n_in >> 2) * TR; i += blockDim.x) {
+          const int c = i / TR, rr = i - c * TR;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rr < rows) v = *reinterpret_cast<const float4*>(s_stage + rr * p.pitch + c * 4);
+          float* o = s_xt + (size_t)(c * 4) * TR + rr;
+          o[0] = v.x;
+          o[TR] = v.y;
+          o[2 * TR] = v.z;
+          o[3 * TR] = v.w;
+        }
+      } else {
+        for (int i = tid; i < p.n_in * TR; i += blockDim.x) {
+          const int f = i / TR, rr = i - f * TR;
+          s_xt[i] = rr < rows ? s_stage[rr * p.pitch + f] : 0.0f;
+        }
+      }
+    }
+    __syncthreads();  // transposed tile visible; landing tile free
     {
-      const int64_t tn = t + (int64_t)(S - 1) * nparts;
-      int sn = stage + S - 1;
-      if (sn >= S) sn -= S;
-      if (tn < n_tiles) issue(s_tiles + sn * tile_words, tn * TR);
+      const int64_t tn = t + nparts;
+      if (tn < n_tiles) issue(tn * TR);
       cp_async_commit();
     }
-    const float* xr = s_tiles + stage * tile_words + r * p.pitch;
     const int64_t row = t * TR + r;
     const bool live = row < p.n_rows;
     double acc[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) acc[k] = 0.0;
     if (live) {
-      for (int tr = g; tr < tm.n_trees; tr += G) {
-        const HeapNode* tn = s_nodes + tr * tm.n_internal;
-        int node = 0;
-        for (int d = 0; d < tm.depth; ++d) {
-          const HeapNode nd = tn[node];
-          const float x = xr[nd.feature];
-          node = 2 * node + 1 + ((x <= nd.threshold) ? 0 : 1);  // sklearn: left when x <= threshold
-        }
-        const double v = __dmul_rn(tm.scale[tr], s_leaves[tr * tm.n_leaves + (node - tm.n_internal)]);
-        const int slot = tm.slot[tr];
+      constexpr int U = 4;  // independent root->leaf walks in flight per thread (ILP over the LDS latency)
+      int tr = g;
+      for (; tr + (U - 1) * G < NT; tr += U * G) {
+        int n4[U];
 #pragma unroll
-        for (int k = 0; k < NS; ++k)
-          if (k == slot) acc[k] = __dadd_rn(acc[k], v);
+        for (int u = 0; u < U; ++u) n4[u] = 4;  // node 1 (byte index)
+        for (int d = 0; d < tm.depth; ++d) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int at = (tr + u * G) * NI * 4 - 4 + n4[u];  // 1-based
+            const int foff = *reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(s_foff) + at);
+            const float thr = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_thr) + at);
+            const float x = *reinterpret_cast<const float*>(xt_r + foff);
+            n4[u] = 2 * n4[u] + ((x <= thr) ? 0 : 4);  // sklearn: left when x <= threshold
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int tu = tr + u * G;
+          const double v = s_leaf[tu * NL + (n4[u] >> 2) - leaf_bias];
+          if (NS == 1) {
+            acc[0] = __dadd_rn(acc[0], v);
+          } else {
+            const int slot = s_slot[tu];
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+              if (k == slot) acc[k] = __dadd_rn(acc[k], v);
+          }
+        }
+      }
+      for (; tr < NT; tr += G) {  // remaining trees of the group, one at a time (same order of additions)
+        int n4 = 4;
+        for (int d = 0; d < tm.depth; ++d) {
+          const int at = tr * NI * 4 - 4 + n4;
+          const int foff = *reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(s_foff) + at);
+          const float thr = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_thr) + at);
+          const float x = *reinterpret_cast<const float*>(xt_r + foff);
+          n4 = 2 * n4 + ((x <= thr) ? 0 : 4);
+        }
+        const double v = s_leaf[tr * NL + (n4 >> 2) - leaf_bias];
+        if (NS == 1) {
+          acc[0] = __dadd_rn(acc[0], v);
+        } else {
+          const int slot = s_slot[tr];
+#pragma unroll
+          for (int k = 0; k < NS; ++k)
+            if (k == slot) acc[k] = __dadd_rn(acc[k], v);
+        }
       }
     }
     if (g > 0) {
@@ -153,14 +214,12 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
         for (int k = 0; k < NS; ++k) sc[k] += o[k];
       }
       p.pred[row * p.n_models + m] = apply_link(md, sc, p.classes);
-      if (m == 0) {
-        int bad = 0;
-        for (int j = 0; j < p.n_in; ++j) bad |= is_finite_f(xr[j]) ? 0 : 1;
-        p.row_bad[row] = bad;
-      }
     }
-    ++stage;
-    if (stage == S) stage = 0;
+    if (m == 0 && g == 1 && live) {  // a second warp group scans the row for non-finite inputs (conflict-free)
+      int bad = 0;
+      for (int j = 0; j < p.n_in; ++j) bad |= is_finite_f(s_xt[j * TR + r]) ? 0 : 1;
+      p.row_bad[row] = bad;
+    }
   }
   cp_async_wait<0>();
 }
