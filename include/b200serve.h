@@ -179,6 +179,66 @@ int b2s_device_sync(void);
 int b2s_time_device(b2s_plan_t plan, const void* const* d_rows, int32_t n_bufs, int64_t n_rows,
                     int64_t row_stride_bytes, void* d_out, int32_t n_iters, float* total_ms);
 
+/* ---- columnar ingest: feature-set transforms over DataFrame-shaped data -------------------------------
+ * Replaces the row-at-a-time walk of a feature-set graph by the storey engine
+ * (feature_store/ingestion.py:38-127 init_featureset_graph; datastore/sources.py:886-895 DataframeSource emits one
+ * dict per row; datastore/targets.py:1856-1868 ReduceToDataFrame re-assembles them).  Data is columnar on both
+ * sides, like the DataFrame it comes from: an input/output "slot" is n_rows 4-byte words (float32 / int32); an
+ * 8-byte column (datetime64[ns] as int64) takes two adjacent slots.  The plan is a list of column ops; every op
+ * reads one input column and writes 0..n output columns; output slots are numbered in the order ops are added.
+ * Float sources take an optional Imputer fill first (Imputer._impute, feature_store/steps.py:397-406).
+ * `check` bits (1: min, 2: max) attach MinMaxValidator.check (mlrun/features.py:292-321) to the op's result:
+ * violating rows are counted (the reference's FeaturesetValidator only prints them, steps.py:117-128). */
+typedef struct b2s_cols_s* b2s_cols_t;
+#define B2S_COL_F32 0
+#define B2S_COL_I32 1
+#define B2S_COL_I64 2
+/* date parts of DateExtractor._do_storey (steps.py:593-602: getattr(pd.Timestamp(ts), part)) computed on the device */
+#define B2S_DATE_YEAR 0
+#define B2S_DATE_MONTH 1
+#define B2S_DATE_DAY 2
+#define B2S_DATE_HOUR 3
+#define B2S_DATE_MINUTE 4
+#define B2S_DATE_SECOND 5
+#define B2S_DATE_DAY_OF_WEEK 6 /* Monday = 0 */
+#define B2S_DATE_DAY_OF_YEAR 7
+#define B2S_DATE_QUARTER 8
+
+int b2s_cols_create(int32_t n_in_slots, b2s_cols_t* out);
+int b2s_cols_destroy(b2s_cols_t plan);
+/* pass a column through (keep != 0) and/or validate it; keep == 0 is a column DropFeatures removed
+ * (steps.py:721-729) that a validator placed before the drop still sees. */
+int b2s_cols_add_copy(b2s_cols_t plan, int32_t src_slot, int32_t kind, int32_t has_fill, float fill, int32_t keep,
+                      int32_t check, double cmin, double cmax, int32_t* out_slot, int32_t* check_counter);
+/* MapValues._map_value (steps.py:189-201): first i with lo[i] <= v < hi[i] -> vals[i]; no hit: v passes through
+ * and counters[miss_counter] counts the row.  The output slot holds float32. */
+int b2s_cols_add_range_map(b2s_cols_t plan, int32_t src_slot, int32_t kind, int32_t has_fill, float fill, const double* lo,
+                           const double* hi, const double* vals, int32_t n, int32_t check, double cmin, double cmax,
+                           int32_t* out_slot, int32_t* miss_counter, int32_t* check_counter);
+/* MapValues exact-match branch (steps.py:200-201): v == keys[i] -> vals[i]. */
+int b2s_cols_add_value_map(b2s_cols_t plan, int32_t src_slot, int32_t kind, int32_t has_fill, float fill, const double* keys,
+                           const double* vals, int32_t n, int32_t check, double cmin, double cmax, int32_t* out_slot,
+                           int32_t* miss_counter, int32_t* check_counter);
+/* OneHotEncoder._encode (steps.py:453-470): n int32 0/1 output slots, in category order; a value matching no
+ * category gives all zeros and is counted (the reference logs a warning). */
+int b2s_cols_add_onehot(b2s_cols_t plan, int32_t src_slot, int32_t kind, int32_t has_fill, float fill, const double* cats,
+                        int32_t n, int32_t* first_out_slot, int32_t* miss_counter);
+/* DateExtractor: src_slot is an 8-byte nanosecond timestamp; the int32 output is -1 for NaT (counted). */
+int b2s_cols_add_date_part(b2s_cols_t plan, int32_t src_slot, int32_t part, int32_t* out_slot, int32_t* nat_counter);
+int b2s_cols_finalize(b2s_cols_t plan);
+int b2s_cols_info(b2s_cols_t plan, int32_t* n_out_slots, int32_t* n_counters);
+/* Device-resident run: slot s of the input starts at d_in + s * in_slot_stride (bytes, multiple of 8, >= 4 * n_rows);
+ * d_counters (n_counters uint64, zeroed by the caller) accumulates.  Asynchronous on `stream`. */
+int b2s_cols_run_device(b2s_cols_t plan, const void* d_in, int64_t in_slot_stride, int64_t n_rows, void* d_out,
+                        int64_t out_slot_stride, uint64_t* d_counters, void* stream);
+/* Host run: one pointer per input slot the plan reads (an 8-byte column: pointer at its first slot), one per output
+ * slot (NULL at the second slot of an 8-byte column): H2D per column -> kernel -> D2H per column. */
+int b2s_cols_run_host(b2s_cols_t plan, const void* const* h_in_slots, int64_t n_rows, void* const* h_out_slots,
+                      uint64_t* counters, b2s_stats* stats);
+/* n_iters back-to-back device runs over rotating inputs, CUDA-event timed (bench.py) */
+int b2s_cols_time_device(b2s_cols_t plan, const void* const* d_in, int32_t n_bufs, int64_t in_slot_stride, int64_t n_rows,
+                         void* d_out, int64_t out_slot_stride, uint64_t* d_counters, int32_t n_iters, float* total_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,9 @@ OUT_COPY, OUT_ONEHOT = 0, 1
 LINK_IDENTITY, LINK_BINARY_GT, LINK_BINARY_GE, LINK_ARGMAX = 0, 1, 2, 3
 VOTE_NONE, VOTE_MEAN, VOTE_MAJORITY = 0, 1, 2
 ROW_NONFINITE_INPUT, ROW_BAD_LABEL = 1, 2
+COL_F32, COL_I32, COL_I64 = 0, 1, 2
+DATE_PARTS = {"year": 0, "month": 1, "day": 2, "hour": 3, "minute": 4, "second": 5, "day_of_week": 6, "dayofweek": 6,
+              "weekday": 6, "day_of_year": 7, "dayofyear": 7, "quarter": 8}
 
 
 class NativeError(RuntimeError):
@@ -80,6 +83,21 @@ SIGNATURES = {
     "b2s_memcpy_d2h": (C.c_int, [_vp, _vp, C.c_size_t]),
     "b2s_device_sync": (C.c_int, []),
     "b2s_time_device": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i64, _i64, _vp, _i32, _pf32]),
+    # columnar ingest
+    "b2s_cols_create": (C.c_int, [_i32, C.POINTER(_vp)]),
+    "b2s_cols_destroy": (C.c_int, [_vp]),
+    "b2s_cols_add_copy": (C.c_int, [_vp, _i32, _i32, _i32, C.c_float, _i32, _i32, C.c_double, C.c_double, _pi32, _pi32]),
+    "b2s_cols_add_range_map": (C.c_int, [_vp, _i32, _i32, _i32, C.c_float, _pf64, _pf64, _pf64, _i32, _i32, C.c_double,
+                                         C.c_double, _pi32, _pi32, _pi32]),
+    "b2s_cols_add_value_map": (C.c_int, [_vp, _i32, _i32, _i32, C.c_float, _pf64, _pf64, _i32, _i32, C.c_double, C.c_double,
+                                         _pi32, _pi32, _pi32]),
+    "b2s_cols_add_onehot": (C.c_int, [_vp, _i32, _i32, _i32, C.c_float, _pf64, _i32, _pi32, _pi32]),
+    "b2s_cols_add_date_part": (C.c_int, [_vp, _i32, _i32, _pi32, _pi32]),
+    "b2s_cols_finalize": (C.c_int, [_vp]),
+    "b2s_cols_info": (C.c_int, [_vp, _pi32, _pi32]),
+    "b2s_cols_run_device": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "b2s_cols_run_host": (C.c_int, [_vp, C.POINTER(_vp), _i64, C.POINTER(_vp), C.POINTER(_u64), C.POINTER(Stats)]),
+    "b2s_cols_time_device": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i64, _i64, _vp, _i64, _vp, _i32, _pf32]),
 }
 
 _lib = None

@@ -1,0 +1,237 @@
+// b2s_columns.cuh -- columnar feature-set transforms (sm_100a): the device side of the ingest path.
+//
+// Replaces, for DataFrame-shaped input, the reference's row-at-a-time walk of the feature-set graph
+// (feature_store/ingestion.py:38-127: DataFrame -> storey.DataframeSource -> one dict per row -> Imputer /
+// MapValues / OneHotEncoder / DateExtractor / DropFeatures / FeaturesetValidator -> ReduceToDataFrame).
+// Data stays COLUMNAR end to end, as a DataFrame already is: an input "slot" is n_rows 4-byte words (float32 or
+// int32; an int64 column is two adjacent slots), an output slot likewise.  The lowered graph is a list of
+// column ops, each reading one input column and writing 0..n output columns; a work item is (op, chunk of
+// rows); persistent CTAs take items round-robin, so neighbouring CTAs stream different columns of the same
+// row range.  Every access is a fully coalesced 4-byte-per-lane (or 8-byte) load/store: each input word is
+// read once, each output word written once -- the kernel is a pure HBM stream.
+// Compares run in fp64 against fp64 tables: float32/int32 values convert exactly, so range edges and category
+// matches agree bit for bit with the reference's Python comparisons.  Violations / unmatched values are counted
+// per op with one atomic per CTA-item (the reference only prints them).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b2s {
+
+enum ColKind : int32_t {
+  CK_COPY32 = 0,  // 4-byte word, no interpretation (int32 counters, codes)
+  CK_COPY64 = 1,  // 8-byte word (timestamps kept in the output)
+  CK_F32 = 2,     // float32 with Imputer fill
+  CK_RANGE = 3,   // MapValues ranges: first lo <= v < hi -> val, else v passes through (counted)
+  CK_VALUE = 4,   // MapValues dict: v == key -> val, else v passes through (counted)
+  CK_ONEHOT = 5,  // OneHotEncoder: n int32 0/1 columns
+  CK_DATE = 6,    // DateExtractor part of an int64 nanosecond timestamp -> int32
+  CK_CHECK = 7,   // validator only (column dropped from the output but still checked)
+};
+
+enum DatePart : int32_t {
+  DP_YEAR = 0, DP_MONTH, DP_DAY, DP_HOUR, DP_MINUTE, DP_SECOND, DP_DAY_OF_WEEK, DP_DAY_OF_YEAR, DP_QUARTER,
+};
+
+struct ColOp {
+  int32_t kind;
+  int32_t src;       // input slot
+  int32_t dst;       // first output slot (-1: none)
+  int32_t n;         // table entries / categories
+  int32_t src_int;   // source words are int32 (never missing)
+  int32_t has_fill;  // Imputer value for a missing (NaN) float source, applied before anything else
+  float fill;
+  int32_t part;      // CK_DATE
+  int32_t tab;       // offset (doubles) into the table array: RANGE lo[n] hi[n] val[n]; VALUE key[n] val[n]; ONEHOT cat[n]
+  int32_t check;     // bit 0: min, bit 1: max  (MinMaxValidator.check, mlrun/features.py:292-321)
+  int32_t counter;   // counters[counter] += rows violating the check
+  int32_t miss;      // counters[miss] += rows that matched no range / key (RANGE, VALUE) or were NaT (DATE); -1: none
+  double cmin, cmax;
+};
+
+struct ColParams {
+  const char* in;   // input slots: slot s starts at in + s * in_stride
+  int64_t in_stride;
+  char* out;
+  int64_t out_stride;
+  int64_t n_rows;
+  const ColOp* ops;
+  int32_t n_ops;
+  const double* tab;
+  unsigned long long* counters;
+};
+
+constexpr int kColThreads = 256;
+constexpr int kColUnroll = 4;                              // independent loads in flight per thread
+constexpr int kColChunk = kColThreads * kColUnroll * 4;    // rows per work item (4096)
+
+__device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b) {
+  int64_t q = a / b;
+  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+// proleptic Gregorian calendar fields of a day count since 1970-01-01 (days-from-civil inverse)
+__device__ __forceinline__ void civil_from_days(int64_t z, int& y, int& m, int& d, int& doy) {
+  z += 719468;
+  const int64_t era = floor_div(z, 146097);
+  const int doe = (int)(z - era * 146097);                                  // [0, 146096]
+  const int yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;    // [0, 399]
+  const int doy_mar = doe - (365 * yoe + yoe / 4 - yoe / 100);              // [0, 365], year starting 1 March
+  const int mp = (5 * doy_mar + 2) / 153;                                   // [0, 11]
+  d = doy_mar - (153 * mp + 2) / 5 + 1;
+  m = mp < 10 ? mp + 3 : mp - 9;
+  y = (int)(yoe + era * 400) + (m <= 2 ? 1 : 0);
+  const bool leap = (y % 4 == 0 && y % 100 != 0) || y % 400 == 0;
+  const int cum[12] = {0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334};
+  doy = cum[m - 1] + d + ((leap && m > 2) ? 1 : 0);
+}
+
+__device__ __forceinline__ int32_t date_part(int64_t ns, int part) {
+  const int64_t secs = floor_div(ns, 1000000000LL);
+  const int64_t days = floor_div(secs, 86400);
+  const int sod = (int)(secs - days * 86400);
+  switch (part) {
+    case DP_HOUR: return sod / 3600;
+    case DP_MINUTE: return (sod % 3600) / 60;
+    case DP_SECOND: return sod % 60;
+    case DP_DAY_OF_WEEK: return (int)(((days % 7) + 7 + 3) % 7);  // 1970-01-01 was a Thursday; Monday = 0
+    default: break;
+  }
+  int y, m, d, doy;
+  civil_from_days(days, y, m, d, doy);
+  switch (part) {
+    case DP_YEAR: return y;
+    case DP_MONTH: return m;
+    case DP_DAY: return d;
+    case DP_DAY_OF_YEAR: return doy;
+    default: return (m - 1) / 3 + 1;  // DP_QUARTER
+  }
+}
+
+__global__ void __launch_bounds__(kColThreads) columns_kernel(const __grid_constant__ ColParams p) {
+  __shared__ unsigned int s_cnt[2];
+  const int tid = threadIdx.x;
+  const int64_t n_chunks = (p.n_rows + kColChunk - 1) / kColChunk;
+  const int64_t n_items = n_chunks * p.n_ops;
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int64_t chunk = item / p.n_ops;
+    const ColOp op = p.ops[item - chunk * p.n_ops];
+    const int64_t row0 = chunk * kColChunk;
+    const int64_t rows = (p.n_rows - row0 < kColChunk) ? (p.n_rows - row0) : kColChunk;
+    const char* src = p.in + (int64_t)op.src * p.in_stride;
+    char* dst = op.dst >= 0 ? p.out + (int64_t)op.dst * p.out_stride : nullptr;
+    const double* tab = p.tab + op.tab;
+    unsigned int bad = 0, miss = 0;
+    if (op.check || op.miss >= 0) {
+      if (tid < 2) s_cnt[tid] = 0;
+      __syncthreads();
+    }
+
+    if (op.kind == CK_COPY64 || op.kind == CK_DATE) {
+      const int64_t* s = reinterpret_cast<const int64_t*>(src) + row0;
+      for (int base = tid; base < rows; base += kColThreads * kColUnroll) {
+        int64_t v[kColUnroll];
+#pragma unroll
+        for (int u = 0; u < kColUnroll; ++u) {
+          const int i = base + u * kColThreads;
+          v[u] = i < rows ? s[i] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kColUnroll; ++u) {
+          const int i = base + u * kColThreads;
+          if (i >= rows) continue;
+          if (op.kind == CK_COPY64) {
+            reinterpret_cast<int64_t*>(dst)[row0 + i] = v[u];
+          } else {
+            const bool nat = v[u] == INT64_MIN;  // NaT
+            miss += nat ? 1u : 0u;
+            reinterpret_cast<int32_t*>(dst)[row0 + i] = nat ? -1 : date_part(v[u], op.part);
+          }
+        }
+      }
+    } else {
+      const uint32_t* s = reinterpret_cast<const uint32_t*>(src) + row0;
+      for (int base = tid; base < rows; base += kColThreads * kColUnroll) {
+        uint32_t w[kColUnroll];
+#pragma unroll
+        for (int u = 0; u < kColUnroll; ++u) {
+          const int i = base + u * kColThreads;
+          w[u] = i < rows ? s[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kColUnroll; ++u) {
+          const int i = base + u * kColThreads;
+          if (i >= rows) continue;
+          uint32_t bits = w[u];
+          if (op.kind == CK_COPY32 && !op.check) {
+            reinterpret_cast<uint32_t*>(dst)[row0 + i] = bits;
+            continue;
+          }
+          double x;
+          if (op.src_int) {
+            x = (double)(int32_t)bits;
+          } else {
+            float f = __uint_as_float(bits);
+            if (op.has_fill && f != f) f = op.fill;  // Imputer._impute (steps.py:397-406)
+            bits = __float_as_uint(f);
+            x = (double)f;
+          }
+          if (op.kind == CK_RANGE || op.kind == CK_VALUE) {  // MapValues._map_value (steps.py:189-201)
+            bool hit = false;
+            double val = x;
+            if (op.kind == CK_RANGE) {
+              for (int q = op.n - 1; q >= 0; --q) {  // first match in mapping order wins
+                const bool in = x >= tab[q] && x < tab[op.n + q];
+                val = in ? tab[2 * op.n + q] : val;
+                hit |= in;
+              }
+            } else {
+              for (int q = op.n - 1; q >= 0; --q) {
+                const bool in = x == tab[q];
+                val = in ? tab[op.n + q] : val;
+                hit |= in;
+              }
+            }
+            miss += hit ? 0u : 1u;
+            x = val;
+            reinterpret_cast<float*>(dst)[row0 + i] = (float)val;
+          } else if (op.kind == CK_ONEHOT) {  // OneHotEncoder._encode (steps.py:453-470): unknown -> all zeros
+            bool any = false;
+            for (int q = 0; q < op.n; ++q) {
+              const bool is = x == tab[q];
+              any |= is;
+              reinterpret_cast<int32_t*>(dst + (int64_t)q * p.out_stride)[row0 + i] = is ? 1 : 0;
+            }
+            miss += any ? 0u : 1u;
+          } else if (op.kind != CK_CHECK) {  // CK_F32 (imputed) or checked CK_COPY32
+            reinterpret_cast<uint32_t*>(dst)[row0 + i] = bits;
+          }
+          if (op.check) {
+            const bool lo_bad = (op.check & 1) && x < op.cmin;
+            const bool hi_bad = (op.check & 2) && x > op.cmax;
+            bad += (lo_bad || hi_bad) ? 1u : 0u;
+          }
+        }
+      }
+    }
+    if (op.check || op.miss >= 0) {
+      // one shared-memory atomic per warp, one global atomic per item
+      for (int o = 16; o > 0; o >>= 1) {
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        miss += __shfl_xor_sync(0xffffffffu, miss, o);
+      }
+      if ((tid & 31) == 0) {
+        if (bad) atomicAdd(&s_cnt[0], bad);
+        if (miss) atomicAdd(&s_cnt[1], miss);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        if (op.check && s_cnt[0]) atomicAdd(&p.counters[op.counter], (unsigned long long)s_cnt[0]);
+        if (op.miss >= 0 && s_cnt[1]) atomicAdd(&p.counters[op.miss], (unsigned long long)s_cnt[1]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace b2s

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/b200serve.h"
+#include "b2s_internal.h"
 #include "b2s_device.cuh"
 #include "b2s_rowwarp.cuh"
 #include "b2s_rowthread.cuh"
@@ -30,6 +31,15 @@ using namespace b2s;
 // ------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+int b2s_int_fail(int code, const char* fmt, ...) {
   char buf[1024];
   va_list ap;
   va_start(ap, fmt);
@@ -58,6 +68,12 @@ struct Global {
   std::mutex mu;
 };
 static Global G;
+
+bool b2s_int_inited() { return G.inited; }
+int b2s_int_device() { return G.device; }
+int b2s_int_sm_count() { return G.prop.multiProcessorCount; }
+cudaStream_t b2s_int_stream() { return G.stream; }
+void b2s_int_count_launches(int n) { G.launches.fetch_add(n, std::memory_order_relaxed); }
 
 static int64_t cfg_get(const std::string& cfg, const char* key, int64_t dflt) {
   size_t pos = cfg.find(std::string(key) + "=");

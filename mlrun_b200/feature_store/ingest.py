@@ -1,0 +1,489 @@
+"""Feature-set ingestion on the device: DataFrame in -> transformed DataFrame out.
+
+Plugin-API mirror of the reference's ingest caller for in-memory frames: `FeatureSet(...).graph.to(...)`,
+`FeatureSet.ingest(df)` (mlrun/feature_store/feature_set.py:1004-1090) -> `init_featureset_graph`
+(mlrun/feature_store/ingestion.py:38-127), which pushes the frame ROW BY ROW through the step DAG
+(storey.DataframeSource, datastore/sources.py:886-895) and re-assembles a frame (ReduceToDataFrame,
+datastore/targets.py:1856-1868).  Here the steps are walked symbolically over the frame's schema
+(`FrameProgram`, same per-row semantics) and lowered to ONE columnar device plan (`mlrun_b200.columns`); the frame's
+columns go to the GPU as they are (contiguous typed arrays) and the result columns come back the same way.
+
+Out of scope (control plane / storage): targets, feature-set metadata / stats inference, sources other than a
+DataFrame.  Steps or dtypes the device cannot hold raise `LoweringError`: there is no per-row Python fallback.
+"""
+
+import math
+
+import numpy as np
+
+from .. import _native as nat
+from ..columns import F32, I32, I64, ColumnsPlan
+from ..lowering import LoweringError
+from ..serving.resolve import MLRunInvalidArgumentError
+
+_INT_DTYPES = ("int8", "int16", "int32", "uint8", "uint16", "bool")
+
+
+class MinMaxValidator:
+    """mlrun/features.py:265-321 -- range check whose only effect is a report (check_type is metadata here)"""
+
+    kind = "minmax"
+
+    def __init__(self, check_type=None, severity=None, min=None, max=None):
+        self.check_type = check_type
+        self.severity = severity
+        self.min = min
+        self.max = max
+
+    def check(self, value):
+        try:
+            if self.min is not None and value < self.min:
+                return False, {"message": "value is smaller than min", "min": self.min, "value": str(value)}
+            if self.max is not None and value > self.max:
+                return False, {"message": "value is greater than max", "max": self.max, "value": str(value)}
+        except Exception as err:  # noqa: BLE001 -- the reference reports comparison errors as violations
+            return False, {"message": str(err), "type": self.kind}
+        return True, {}
+
+
+def _num(v, what):
+    if isinstance(v, bool) or not isinstance(v, (int, float, np.integer, np.floating)):
+        raise LoweringError(f"{what}: {v!r} is not numeric -- string / object values are not held on the device")
+    return float(v)
+
+
+def _f32_exact(v, what):
+    v = _num(v, what)
+    if math.isfinite(v) and float(np.float32(v)) != v:
+        raise LoweringError(f"{what}: {v!r} is not exactly representable in the float32 output column")
+    return v
+
+
+class _Col:
+    """one column of the event as the steps see it"""
+
+    __slots__ = ("name", "slot", "kind", "fill", "op", "arg", "check", "group")
+
+    def __init__(self, name, slot, kind):
+        self.name, self.slot, self.kind = name, slot, kind
+        self.fill = None    # Imputer value (float sources)
+        self.op = None      # None | "range" | "value" | "onehot" | "date"
+        self.arg = None     # ranges / mapping / category index / date part
+        self.check = None   # (min, max, validator)
+        self.group = None   # one-hot group: the _Group shared by the expanded columns
+
+
+class _Group:
+    def __init__(self, src, cats):
+        self.src, self.cats = src, cats
+        self.first_out = None
+        self.miss = None
+
+
+def frame_schema(df):
+    """[(column name, kind)] of a DataFrame, or LoweringError for dtypes the device does not take as they are"""
+    schema = []
+    for name in df.columns:
+        dt = df[name].dtype
+        s = str(dt)
+        if s == "float32":
+            kind = F32
+        elif s in _INT_DTYPES:
+            kind = I32
+        elif s.startswith("datetime64"):
+            kind = I64
+        else:
+            raise LoweringError(
+                f"column {name!r} has dtype {s}: the device takes float32, (u)int8/16/32, bool and datetime64 columns; "
+                "cast float64/int64 columns explicitly (a silent down-cast would change values)")
+        schema.append((str(name), kind))
+    return schema
+
+
+class FrameProgram:
+    """symbolic execution of feature-store steps over the frame's columns, with the storey engine's per-row
+    semantics (feature_store/steps.py `_do_storey` methods)"""
+
+    def __init__(self, schema):
+        self.schema = list(schema)
+        names = [n for n, _ in self.schema]
+        if len(set(names)) != len(names):
+            raise LoweringError("duplicate column names")
+        self.cols, slot = [], 0
+        for name, kind in self.schema:
+            self.cols.append(_Col(name, slot, kind))
+            slot += 2 if kind == I64 else 1
+        self.n_in_slots = slot
+        self.in_slot = {c.name: c.slot for c in self.cols}
+        self.checked_dropped = []
+        self.validators = []
+        self.steps = []
+
+    # ---- step handlers ------------------------------------------------------------------------
+    def imputer(self, step):
+        """Imputer._impute (steps.py:397-406): every missing value -> mapping.get(feature, default_value)"""
+        mapping, default = step.mapping or {}, step.default_value
+        for c in self.cols:
+            fill = mapping.get(c.name, default)
+            if fill is None:
+                continue  # NaN -> None: still missing when the frame is re-assembled
+            if c.kind == I32 or c.op in ("onehot", "date"):
+                continue  # integers are never missing
+            if c.kind == I64:
+                raise LoweringError(f"Imputer would replace NaT in the timestamp column {c.name!r}: not held on the device")
+            if c.op is not None:
+                raise LoweringError(f"Imputer after MapValues on column {c.name!r} is not lowered")
+            if c.fill is None:
+                c.fill = _f32_exact(fill, f"Imputer fill for {c.name!r}")
+
+    def map_values(self, step):
+        """MapValues._do_storey (steps.py:203-216)"""
+        mapped = []
+        for c in self.cols:
+            if c.name not in step.mapping:
+                continue
+            if c.op is not None or c.kind == I64:
+                raise LoweringError(f"MapValues on the derived / timestamp column {c.name!r} is not lowered")
+            fmap = step.mapping[c.name]
+            m = _Col(f"{c.name}_{step.suffix}" if step.with_original_features else c.name, c.slot, c.kind)
+            m.fill = c.fill
+            if "ranges" in fmap:
+                if len(fmap) > 1:
+                    raise LoweringError("MapValues mixing ranges and value replacements is rejected by the reference")
+                m.op, m.arg = "range", []
+                for val, (lo, hi) in fmap["ranges"].items():
+                    lo = -math.inf if lo == "-inf" else _num(lo, f"MapValues range of {c.name!r}")
+                    hi = math.inf if hi == "inf" else _num(hi, f"MapValues range of {c.name!r}")
+                    m.arg.append((lo, hi, _f32_exact(val, f"MapValues range label of {c.name!r}"), val))
+            else:
+                m.op = "value"
+                m.arg = [(_num(k, f"MapValues key of {c.name!r}"), _f32_exact(v, f"MapValues value of {c.name!r}"), v)
+                         for k, v in fmap.items()]
+            mapped.append(m)
+        # storey mode emits the mapped features first, then (optionally) the untouched event
+        self.cols = mapped + (self.cols if step.with_original_features else [])
+
+    def one_hot(self, step):
+        """OneHotEncoder._do_storey (steps.py:473-478): the feature is replaced in place by one field per category"""
+        new = []
+        for c in self.cols:
+            cats = step.mapping.get(c.name)
+            if not cats:
+                new.append(c)
+                continue
+            if c.op is not None or c.kind == I64:
+                raise LoweringError(f"OneHotEncoder on the derived / timestamp column {c.name!r} is not lowered")
+            if c.kind != I32:
+                # a float value equal to an integer category makes the reference add a stray "<col>_<value>" field next
+                # to the encoded ones (steps.py:462-470 writes encoding[f"{feature}_{value}"] for the float spelling)
+                raise LoweringError(f"OneHotEncoder source {c.name!r} must be an integer column (cast the codes to int32)")
+            cats = list(dict.fromkeys(cats))
+            for v in cats:
+                if isinstance(v, bool) or not isinstance(v, (int, np.integer)):
+                    raise LoweringError(f"OneHotEncoder categories of {c.name!r} must be integers on the device (got {v!r})")
+            g = _Group(c, [float(v) for v in cats])
+            for i, v in enumerate(cats):
+                e = _Col(f"{c.name}_{step._sanitized_category(v)}", c.slot, c.kind)
+                e.op, e.arg, e.group = "onehot", i, g
+                new.append(e)
+        self.cols = new
+
+    def date_extractor(self, step):
+        """DateExtractor._do_storey (steps.py:593-602)"""
+        ts = next((c for c in self.cols if c.name == step.timestamp_col), None)
+        if ts is None:
+            raise MLRunInvalidArgumentError(f"{step.timestamp_col} does not exist in the event")
+        if ts.kind != I64 or ts.op is not None:
+            raise LoweringError(f"DateExtractor needs {step.timestamp_col!r} to be a datetime64 column")
+        for part in step.parts:
+            if part not in nat.DATE_PARTS:
+                raise LoweringError(f"DateExtractor part {part!r} is not computed on the device (have {sorted(nat.DATE_PARTS)})")
+            name = f"{step.timestamp_col}_{part}"
+            e = _Col(name, ts.slot, I64)
+            e.op, e.arg = "date", nat.DATE_PARTS[part]
+            at = next((i for i, c in enumerate(self.cols) if c.name == name), None)
+            if at is None:
+                self.cols.append(e)
+            else:
+                self.cols[at] = e  # the event already had that key: overwritten in place
+
+    def drop_features(self, step):
+        """DropFeatures._do_storey (steps.py:721-729)"""
+        drop = set(step.features)
+        have = {c.name for c in self.cols}
+        for f in step.features:
+            if f not in have:
+                raise MLRunInvalidArgumentError(f"The ingesting data doesn't contain a feature named '{f}'")
+        for c in self.cols:
+            if c.name in drop and c.check is not None:
+                if c.op in ("onehot", "date"):
+                    raise LoweringError(f"validated derived column {c.name!r} cannot be dropped on the device")
+                self.checked_dropped.append(c)
+        self.cols = [c for c in self.cols if c.name not in drop]
+
+    def validator(self, step):
+        """FeaturesetValidator._do_storey (steps.py:117-128): report only; here violations are counted"""
+        for name, v in step._validators.items():
+            c = next((c for c in self.cols if c.name == name), None)
+            if c is None:
+                continue  # `if name in body`
+            if getattr(v, "kind", "minmax") != "minmax" and not hasattr(v, "min"):
+                raise LoweringError(f"validator of {name!r}: only MinMaxValidator is lowered")
+            if c.op in ("onehot", "date") or c.kind == I64:
+                raise LoweringError(f"validator on the derived / timestamp column {name!r} is not lowered")
+            if c.check is not None:
+                raise LoweringError(f"column {name!r} is validated twice")
+            lo = None if v.min is None else _num(v.min, f"validator min of {name!r}")
+            hi = None if v.max is None else _num(v.max, f"validator max of {name!r}")
+            c.check = (lo, hi, v)
+        self.validators.append(step)
+
+    def apply(self, step):
+        handler = {"Imputer": self.imputer, "MapValues": self.map_values, "OneHotEncoder": self.one_hot,
+                   "DateExtractor": self.date_extractor, "DropFeatures": self.drop_features,
+                   "FeaturesetValidator": self.validator}.get(type(step).__name__)
+        if handler is None:
+            raise LoweringError(f"step {type(step).__name__} is not lowered to the columnar device plan")
+        handler(step)
+        self.steps.append(type(step).__name__)
+        if len({c.name for c in self.cols}) != len(self.cols):
+            raise LoweringError("two output columns share a name")  # a dict would keep one: not reproduced
+        return self
+
+    # ---- plan ----------------------------------------------------------------------------------
+    def build(self):
+        return IngestPlan(self)
+
+
+class IngestPlan:
+    """the device plan of a FrameProgram + the frame boundary (DataFrame columns <-> slots)"""
+
+    def __init__(self, prog):
+        self.prog = prog
+        self.schema = prog.schema
+        plan = ColumnsPlan(prog.n_in_slots)
+        self.out = []  # per output column: (name, slot, how, col)
+        self.checks = []  # (counter, column name, validator)
+        self.miss = []    # (counter, column name, what)
+        for c in prog.cols:
+            chk = None if c.check is None else c.check[:2]
+            if c.op is None:
+                slot, cnt = plan.add_copy(c.slot, c.kind, fill=c.fill, keep=True, check=chk)
+                how = {F32: "f32", I32: "i32", I64: "dt"}[c.kind]
+            elif c.op == "range":
+                slot, miss, cnt = plan.add_range_map(c.slot, c.kind, [r[:3] for r in c.arg], fill=c.fill, check=chk)
+                self.miss.append((miss, c.name, "matched no range"))
+                how = ("map", miss, all(isinstance(r[3], (int, np.integer)) and not isinstance(r[3], bool) for r in c.arg))
+            elif c.op == "value":
+                slot, miss, cnt = plan.add_value_map(c.slot, c.kind, {k: v for k, v, _ in c.arg}, fill=c.fill, check=chk)
+                self.miss.append((miss, c.name, "matched no key"))
+                how = ("map", miss, all(isinstance(r[2], (int, np.integer)) and not isinstance(r[2], bool) for r in c.arg))
+            elif c.op == "onehot":
+                g = c.group
+                if g.first_out is None:
+                    g.first_out, g.miss = plan.add_onehot(g.src.slot, g.src.kind, g.cats, fill=g.src.fill)
+                    self.miss.append((g.miss, g.src.name, "matched no category"))
+                slot, cnt, how = g.first_out + c.arg, -1, "i32"
+            else:  # date
+                slot, miss = plan.add_date_part(c.slot, c.arg)
+                self.miss.append((miss, c.name, "NaT"))
+                cnt, how = -1, ("date", miss)
+            if cnt >= 0:
+                self.checks.append((cnt, c.name, c.check[2]))
+            self.out.append((c.name, slot, how))
+        for c in prog.checked_dropped:
+            chk = c.check[:2]
+            if c.op is None:
+                _, cnt = plan.add_copy(c.slot, c.kind, fill=c.fill, keep=False, check=chk)
+            else:
+                raise LoweringError(f"validated then dropped mapped column {c.name!r} is not lowered")
+            self.checks.append((cnt, c.name, c.check[2]))
+        self.plan = plan.finalize()
+        self.counters = None
+        self.violations = {}
+        self.unmatched = {}
+        self.stats = None
+
+    @property
+    def out_names(self):
+        return [o[0] for o in self.out]
+
+    def _inputs(self, df):
+        ins, keep = {}, []
+        for name, kind in self.schema:
+            a = df[name].to_numpy()
+            if kind == I64:
+                a = a.astype("datetime64[ns]", copy=False).view(np.int64)
+            elif kind == I32 and a.dtype != np.int32:
+                a = a.astype(np.int32)
+            a = np.ascontiguousarray(a)
+            keep.append(a)
+            ins[self.prog.in_slot[name]] = a
+        return ins, keep
+
+    def run(self, df, reference_dtypes=False):
+        """transform the frame; returns a new DataFrame with the same index.  `reference_dtypes=True` widens integer
+        results to int64 (what a frame re-assembled from Python ints has) at the price of a host-side copy."""
+        import pandas as pd
+
+        if frame_schema(df) != self.schema:
+            raise ValueError("the frame does not carry the schema this plan was lowered for")
+        n = len(df)
+        ins, _keep = self._inputs(df)
+        bufs, outs = {}, {}
+        for name, slot, how in self.out:
+            if how == "dt":
+                bufs[name] = np.empty(n, dtype=np.int64)
+            elif how == "f32" or (isinstance(how, tuple) and how[0] == "map"):
+                bufs[name] = np.empty(n, dtype=np.float32)
+            else:
+                bufs[name] = np.empty(n, dtype=np.int32)
+            outs[slot] = bufs[name]
+        # slots written by the device but not part of the result (dropped one-hot members) still need a landing buffer
+        for s in range(self.plan.n_out):
+            if s not in outs and not self._second_half(s):
+                outs[s] = np.empty(n, dtype=np.int32)
+        self.counters, self.stats = self.plan.run_host(ins, n, outs, with_stats=True)
+        data = {}
+        for name, _slot, how in self.out:
+            a = bufs[name]
+            if how == "dt":
+                a = a.view("datetime64[ns]")
+            elif isinstance(how, tuple) and how[0] == "map":
+                if how[2] and self.counters[how[1]] == 0:
+                    a = a.astype(np.int64 if reference_dtypes else np.int32)  # every row got an integer label
+            elif isinstance(how, tuple) and how[0] == "date":
+                if self.counters[how[1]]:
+                    a = np.where(a < 0, np.nan, a.astype(np.float64))  # NaT rows
+                elif reference_dtypes:
+                    a = a.astype(np.int64)
+            elif how == "i32" and reference_dtypes:
+                a = a.astype(np.int64)
+            data[name] = a
+        self.violations = {name: int(self.counters[cnt]) for cnt, name, _v in self.checks}
+        self.unmatched = {name: int(self.counters[cnt]) for cnt, name, _w in self.miss if self.counters[cnt]}
+        for cnt, name, v in self.checks:
+            if self.counters[cnt]:
+                print(f"{v.severity}! {name} has {int(self.counters[cnt])} values outside [{v.min}, {v.max}]")
+        for step in self.prog.validators:
+            step.violations = getattr(step, "violations", 0) + sum(
+                int(self.counters[cnt]) for cnt, name, v in self.checks if v in step._validators.values())
+        return pd.DataFrame(data, index=df.index, copy=False)
+
+    def _second_half(self, s):
+        return any(how == "dt" and slot + 1 == s for _n, slot, how in self.out)
+
+
+def lower_steps(steps, df_or_schema):
+    schema = df_or_schema if isinstance(df_or_schema, list) else frame_schema(df_or_schema)
+    prog = FrameProgram(schema)
+    for s in steps:
+        prog.apply(s)
+    return prog.build()
+
+
+# ------------------------------------------------------------------------------------------ FeatureSet mirror
+class Entity:
+    def __init__(self, name=None, value_type=None, description=None, labels=None):
+        self.name, self.value_type, self.description, self.labels = name, value_type, description, labels or {}
+
+
+class Feature:
+    """mlrun/features.py:92-150: only what validation reads"""
+
+    def __init__(self, value_type=None, dims=None, description=None, aggregate=None, name=None, validator=None,
+                 default=None, labels=None):
+        self.name, self.value_type, self.description, self.validator = name or "", value_type, description, validator
+        self.default, self.labels = default, labels or {}
+
+
+class FeatureSet:
+    """the part of mlrun.feature_store.FeatureSet the ingest path touches (feature_set.py:319-520, 1004-1090):
+    a named transformation graph (`.graph`, `.add_step`/`graph.to`), entities that become the frame's index
+    (ingestion.py:84-87 `entities_to_index`) and `ingest(df)`"""
+
+    def __init__(self, name=None, description=None, entities=None, timestamp_key=None, engine=None, label_column=None,
+                 relations=None, passthrough=None):
+        from ..serving.graph import RootFlowStep
+
+        self.name = name
+        self.description = description
+        self.entities = [Entity(e) if isinstance(e, str) else e for e in (entities or [])]
+        self.timestamp_key = timestamp_key
+        self.engine = engine or "storey"
+        self.label_column = label_column
+        self.passthrough = passthrough
+        self.features = {}
+        self._graph = RootFlowStep()
+        self._graph.engine = "sync"  # steps are only resolved here; the device plan replaces the executor
+        self._plan = None
+        self._plan_key = None
+
+    @property
+    def graph(self):
+        return self._graph
+
+    def __getitem__(self, name):
+        return self.features[name]
+
+    def __setitem__(self, key, item):
+        self.add_feature(item, key)
+
+    def add_feature(self, feature, name=None):
+        """feature_set.py:646-656 -- `fset["bid"] = Feature(validator=MinMaxValidator(min=52, severity="info"))`"""
+        name = name or feature.name
+        if not name:
+            raise MLRunInvalidArgumentError("feature name must be specified")
+        feature.name = name
+        self.features[name] = feature
+
+    def add_step(self, *args, **kwargs):
+        last = self._graph
+        names = list(self._graph.steps.keys()) if hasattr(self._graph, "steps") else []
+        if names:
+            last = self._graph[names[-1]]
+        return last.to(*args, **kwargs)
+
+    def _step_objects(self, namespace):
+        from ..serving.compiler import _chain, _transform_object
+        from ..serving.host import create_graph_server
+        from . import transforms
+
+        ns = {k: getattr(transforms, k) for k in dir(transforms) if not k.startswith("_")}
+        ns.update(namespace or {})
+        server = create_graph_server(graph=self._graph, parameters={})
+        server.init_states(context=None, namespace=ns)
+        server.init_object(ns)
+        objs = [_transform_object(s) for s in _chain(self._graph)]
+        for o in objs:
+            # FeaturesetValidator.__init__ (steps.py:94-116) takes its validators from the feature set's features
+            if type(o).__name__ == "FeaturesetValidator" and not o._validators and o.featureset in (".", self.name):
+                o._validators = {k: f.validator for k, f in self.features.items()
+                                 if f.validator is not None and (not o.columns or k in o.columns)}
+        return objs
+
+    def ingest(self, source=None, targets=None, namespace=None, return_df=True, reference_dtypes=False, **kwargs):
+        """DataFrame -> transformed DataFrame through one device plan (targets are out of scope: pass none)"""
+        if targets:
+            raise LoweringError("targets are storage (out of scope): ingest returns the frame")
+        if not (hasattr(source, "columns") and hasattr(source, "index")):
+            raise MLRunInvalidArgumentError("illegal source")  # ingestion.py:77-78; only frames are taken here
+        df = source
+        keys = [e.name for e in self.entities]
+        if keys and all(k in df.columns for k in keys):
+            df = df.set_index(keys)
+        key = tuple((str(c), str(t)) for c, t in zip(df.columns, df.dtypes))
+        if self._plan is None or self._plan_key != key:
+            self._plan = lower_steps(self._step_objects(namespace), df)
+            self._plan_key = key
+        out = self._plan.run(df, reference_dtypes=reference_dtypes)
+        return out if return_df else None
+
+    @property
+    def plan(self):
+        return self._plan
+
+
+def ingest(featureset=None, source=None, targets=None, namespace=None, return_df=True, **kwargs):
+    """module-level spelling, mlrun.feature_store.api.ingest (feature_store/api.py:404-520)"""
+    return featureset.ingest(source, targets=targets, namespace=namespace, return_df=return_df, **kwargs)

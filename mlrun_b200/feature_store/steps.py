@@ -8,3 +8,4 @@ from .transforms import (  # noqa: F401
     OneHotEncoder,
     SetEventMetadata,
 )
+from .ingest import MinMaxValidator  # noqa: F401,E402

@@ -172,3 +172,71 @@ class IngestWorkload:
 def events_matrix(n_rows, n_feat=64, seed=4):
     rng = np.random.default_rng(seed)
     return rng.normal(size=(n_rows, n_feat)).astype(np.float32)
+
+
+@dataclass
+class IngestWorkload:
+    """feature-set ingest of SURVEY.md 8(d) config 5: 256 four-byte input slots per row, six steps"""
+
+    df: object
+    f32_cols: list
+    cat_cols: list
+    counter_cols: list
+    means: dict
+    mapped_cols: list
+    onehot_cols: list
+    checked_cols: list
+
+    RANGES = {0: ["-inf", -1.0], 1: [-1.0, 0.0], 2: [0.0, 1.0], 3: [1.0, "inf"]}
+
+    def build_steps(self, api):
+        """`api` provides the step classes (mlrun_b200.feature_store.steps / oracle.transforms) + MinMaxValidator"""
+        validators = {c: api.MinMaxValidator(severity="info", min=-2.5, max=2.5) for c in self.checked_cols}
+        return [
+            api.Imputer(mapping=dict(self.means)),
+            api.MapValues(mapping={c: {"ranges": dict(self.RANGES)} for c in self.mapped_cols}, with_original_features=True),
+            api.OneHotEncoder(mapping={c: list(range(8)) for c in self.onehot_cols}),
+            api.DateExtractor(parts=["hour", "day_of_week"], timestamp_col="timestamp"),
+            api.DropFeatures(features=list(self.mapped_cols)),
+            api.FeaturesetValidator(validators=validators),
+        ]
+
+    @property
+    def in_bytes_per_row(self):
+        return 4 * (len(self.f32_cols) + len(self.cat_cols) + len(self.counter_cols) + 2)
+
+    @property
+    def out_bytes_per_row(self):
+        n = len(self.mapped_cols) + (len(self.f32_cols) - len(self.mapped_cols)) + (len(self.cat_cols) - len(self.onehot_cols))
+        n += 8 * len(self.onehot_cols) + len(self.counter_cols) + 2 + 2
+        return 4 * n
+
+
+def ingest_workload(n_rows=100_000, seed=5, n_f32=192, n_cat=48, n_counter=14, nan_frac=0.05):
+    """192 float32 columns ~N(0,1) with 5 % NaN, 48 int32 categorical codes (cardinality 8, 1 % out-of-vocabulary 9),
+    14 int32 counters, one datetime64[ns] timestamp (random seconds over 2015..2030).  Imputer fills = column means
+    rounded to float32; ranges on the first 16 float columns; one-hot over the first 8 categorical columns;
+    validators [-2.5, 2.5] on float columns 16..23."""
+    import pandas as pd
+
+    rng = np.random.default_rng(seed)
+    data = {}
+    f32_cols = [f"x{i}" for i in range(n_f32)]
+    means = {}
+    for c in f32_cols:
+        a = rng.normal(size=n_rows).astype(np.float32)
+        means[c] = float(np.float32(a.mean(dtype=np.float64)))
+        a[rng.random(n_rows) < nan_frac] = np.nan
+        data[c] = a
+    cat_cols = [f"c{i}" for i in range(n_cat)]
+    for c in cat_cols:
+        a = rng.integers(0, 8, size=n_rows).astype(np.int32)
+        a[rng.random(n_rows) < 0.01] = 9
+        data[c] = a
+    counter_cols = [f"n{i}" for i in range(n_counter)]
+    for c in counter_cols:
+        data[c] = rng.integers(0, 1 << 20, size=n_rows).astype(np.int32)
+    secs = rng.integers(1_420_070_400, 1_893_456_000, size=n_rows)  # 2015-01-01 .. 2030-01-01
+    data["timestamp"] = (secs * 1_000_000_000).astype("datetime64[ns]")
+    df = pd.DataFrame(data)
+    return IngestWorkload(df, f32_cols, cat_cols, counter_cols, means, f32_cols[:16], cat_cols[:8], f32_cols[16:24])

@@ -1,0 +1,104 @@
+"""Feature-set ingest path, CPU side: the vectorised oracle against the per-row oracle (the restatement of the
+reference's storey walk), and the symbolic lowering of the product against both (no GPU needed up to `finalize`)."""
+
+import contextlib
+import io
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from mlrun_b200 import _native as nat
+from mlrun_b200.feature_store import ingest as bi
+from mlrun_b200.feature_store import steps as bs
+from mlrun_b200.lowering import LoweringError
+from mlrun_b200.serving.resolve import MLRunInvalidArgumentError
+from mlrun_b200.synthetic import ingest_workload
+from oracle import ingest as oi
+from oracle import transforms as ot
+
+
+def _quiet(fn, *a):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a)
+
+
+def test_vectorised_oracle_matches_the_per_row_walk():
+    wl = ingest_workload(n_rows=700, seed=51)
+    rows, n_viol = _quiet(oi.ingest_rows, wl.build_steps(ot), wl.df)
+    cols, viol = oi.ingest_columns(wl.build_steps(ot), wl.df)
+    pd.testing.assert_frame_equal(rows, cols, check_dtype=False)
+    assert n_viol == sum(viol.values()) > 0
+    assert rows.shape[1] * 4 + 4 == wl.out_bytes_per_row  # the timestamp is one 8-byte column
+
+
+def test_oracle_edge_values():
+    """unmatched range / key values pass through (and make the column float), unknown categories encode to zeros,
+    dates before 1970 and leap days"""
+    df = pd.DataFrame({
+        "v": np.array([-3.5, 0.0, 7.0, 10.0, 25.0, np.nan], dtype=np.float32),
+        "k": np.array([1, 2, 1, 1, 3, 2], dtype=np.int32),
+        "c": np.array([0, 1, 2, 9, 1, 0], dtype=np.int32),
+        "timestamp": pd.to_datetime(["1969-12-31 23:59:59", "1970-01-01 00:00:00", "2000-02-29 13:14:15", "2024-12-31 00:00:01",
+                                     "1900-03-01 00:00:00", "2038-01-19 03:14:08"]).astype("datetime64[ns]"),
+    })
+    steps = [
+        ot.MapValues(mapping={"v": {"ranges": {5: ["-inf", 0], 6: [0, 10], 7: [5, 20]}}, "k": {1: 10}}, with_original_features=True),
+        ot.OneHotEncoder(mapping={"c": [0, 1, 2]}),
+        ot.DateExtractor(parts=["year", "month", "day", "hour", "minute", "second", "day_of_week", "day_of_year", "quarter"]),
+    ]
+    rows, _ = _quiet(oi.ingest_rows, steps, df)
+    cols, _ = oi.ingest_columns(steps, df)
+    pd.testing.assert_frame_equal(rows, cols, check_dtype=False)
+    assert rows["v_mapped"].tolist()[:5] == [5, 6, 6, 7, 25.0] and np.isnan(rows["v_mapped"][5])
+    assert rows["k_mapped"].tolist() == [10, 2, 10, 10, 3, 2]
+    assert rows.loc[3, ["c_0", "c_1", "c_2"]].tolist() == [0, 0, 0]
+    assert rows["timestamp_day_of_week"].tolist() == [2, 3, 1, 1, 3, 1]
+    assert rows["timestamp_day_of_year"].tolist() == [365, 1, 60, 366, 60, 19]
+
+
+def test_lowering_reproduces_the_event_layout():
+    wl = ingest_workload(n_rows=50, seed=52)
+    prog = bi.FrameProgram(bi.frame_schema(wl.df))
+    for s in wl.build_steps(bs):
+        prog.apply(s)
+    want, _ = _quiet(oi.ingest_rows, wl.build_steps(ot), wl.df)
+    assert [c.name for c in prog.cols] == list(want.columns)
+    assert prog.n_in_slots * 4 == wl.in_bytes_per_row == 1024
+
+
+def test_lowering_rejects_what_the_device_cannot_hold():
+    wl = ingest_workload(n_rows=8, seed=53)
+    schema = bi.frame_schema(wl.df)
+    with pytest.raises(LoweringError, match="not numeric"):
+        bi.FrameProgram(schema).apply(bs.MapValues(mapping={"x0": {"ranges": {"child": [0, 30]}}}))
+    with pytest.raises(LoweringError, match="integers"):
+        bi.FrameProgram(schema).apply(bs.OneHotEncoder(mapping={"c0": ["a", "b"]}))
+    with pytest.raises(LoweringError, match="must be an integer column"):
+        bi.FrameProgram(schema).apply(bs.OneHotEncoder(mapping={"x0": [0, 1]}))
+    with pytest.raises(LoweringError, match="not computed on the device"):
+        bi.FrameProgram(schema).apply(bs.DateExtractor(parts=["is_leap_year"]))
+    with pytest.raises(MLRunInvalidArgumentError, match="doesn't contain a feature named 'nope'"):
+        bi.FrameProgram(schema).apply(bs.DropFeatures(features=["nope"]))
+    with pytest.raises(MLRunInvalidArgumentError, match="ts does not exist"):
+        bi.FrameProgram(schema).apply(bs.DateExtractor(parts=["hour"], timestamp_col="ts"))
+    with pytest.raises(LoweringError, match="float64"):
+        bi.frame_schema(pd.DataFrame({"a": [1.0, 2.0]}))
+    with pytest.raises(LoweringError, match="exactly representable"):
+        bi.FrameProgram(schema).apply(bs.Imputer(mapping={"x0": 0.1}))
+
+
+def test_feature_set_mirror_resolves_steps_and_fails_loudly_without_a_gpu():
+    import torch
+
+    fs = bi.FeatureSet("cfg5", entities=["id"])
+    fs.graph.to(class_name="Imputer", mapping={"a": 1.0}).to(class_name="OneHotEncoder", mapping={"c": [0, 1]})
+    assert [type(o).__name__ for o in fs._step_objects(None)] == ["Imputer", "OneHotEncoder"]
+    df = pd.DataFrame({"id": np.arange(4, dtype=np.int32), "a": np.array([1, np.nan, 3, 4], dtype=np.float32),
+                       "c": np.array([0, 1, 1, 5], dtype=np.int32)})
+    with pytest.raises(MLRunInvalidArgumentError, match="illegal source"):
+        fs.ingest("file.csv")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(nat.NativeError, match="no CUDA device|CPU fallback"):
+        fs.ingest(df)
