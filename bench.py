@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-BYTES_PER_EVENT = {"flow3_ens4": 260, "flow3_linear": 260, "trees_ens4": 516}
+BYTES_PER_EVENT = {"flow3_ens4": 260, "flow3_linear": 260, "trees_ens4": 516, "ingest6": 2280}
 
 
 def parse():
@@ -47,7 +47,10 @@ def parse():
 
 # ------------------------------------------------------------------------------------------ workloads
 def make_workload(name, n_rows, seed=2):
-    from mlrun_b200.synthetic import flow3_workload, tree_workload
+    from mlrun_b200.synthetic import flow3_workload, ingest_workload, tree_workload
+
+    if name == "ingest6":
+        return ingest_workload(n_rows=n_rows, seed=seed + 3)
 
     if name == "flow3_ens4":
         return flow3_workload(n_rows=n_rows, n_num=56, n_cat=8, seed=seed, n_models=4)
@@ -84,6 +87,19 @@ def _cpu_worker(args):
         pass
     from tests import api_oracle
 
+    if name == "ingest6":
+        import contextlib
+        import io
+
+        from oracle import ingest as oingest
+        from oracle import transforms as otransforms
+
+        wl = make_workload(name, n_events, seed)
+        steps = wl.build_steps(otransforms)
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):  # the validator prints every violation
+            oingest.ingest_rows(steps, wl.df)
+        return n_events, time.perf_counter() - t0
     wl = make_workload(name, max(n_events, 8) if name.startswith("flow3") else 64, seed)
     if name.startswith("flow3"):
         server = wl.build_server(api_oracle)
@@ -120,7 +136,7 @@ def cpu_baseline(name, seconds, procs=None):
 
     procs = procs or usable_cores()
     # calibrate on one process, then size the sample to the time budget
-    n_cal = 300 if name.startswith("flow3") else 40
+    n_cal = 300 if name.startswith("flow3") else (200 if name == "ingest6" else 40)
     n, dt = _cpu_worker((name, n_cal, 2))
     rate1 = n / dt
     # with P busy processes each one runs slower than alone (shared caches / SMT): budget for ~2x
@@ -137,7 +153,10 @@ def cpu_baseline(name, seconds, procs=None):
         "unit": "events/s",
         "cores": procs,
         "kind": "port",
-        "sample": f"{total} events ({per_proc}/process x {procs} processes), one MockEvent per row through the "
+        "sample": (f"{total} rows ({per_proc}/process x {procs} processes), one dict per row through the six steps' "
+                   f"_do_storey (oracle restatement of the storey ingest walk); single-process rate {rate1:.0f} rows/s; "
+                   f"wall {wall:.1f}s") if name == "ingest6" else
+                  f"{total} events ({per_proc}/process x {procs} processes), one MockEvent per row through the "
                   f"oracle GraphServer (sync engine); single-process rate {rate1:.0f} events/s; wall {wall:.1f}s",
         "single_process_events_per_s": rate1,
     }
@@ -147,6 +166,17 @@ def cpu_vectorised(name, wl_small):
     """upper bound of a CPU implementation: vectorised numpy / scikit-learn on one core"""
     from oracle import batch as obatch
 
+    if name == "ingest6":
+        from oracle import ingest as oingest
+        from oracle import transforms as otransforms
+
+        steps = wl_small.build_steps(otransforms)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 1.5:
+            oingest.ingest_columns(steps, wl_small.df)
+            reps += 1
+        return reps * len(wl_small.df) / (time.perf_counter() - t0)
     fn = obatch.flow3 if name.startswith("flow3") else obatch.tree_ensemble
     fn(wl_small)
     t0 = time.perf_counter()
@@ -251,6 +281,9 @@ def workload_desc(name):
         "flow3_ens4": "3-step flow Imputer->OneHotEncoder->VotingEnsemble(4 linear models), 64-feat f32 (56 num + 8 cat x4 -> 88)",
         "flow3_linear": "3-step flow Imputer->OneHotEncoder->linear predict, 64-feat f32 (BASELINE configs[1])",
         "trees_ens4": "VotingEnsemble of 4 GradientBoostingRegressor(100 trees, depth 6), 128-feat f32 (BASELINE configs[2])",
+        "ingest6": "feature-set ingest, 256 four-byte slots/row (192 f32 + 62 int32 + datetime64): Imputer -> MapValues(ranges, 16 cols) "
+                   "-> OneHotEncoder(8 cols x 8) -> DateExtractor(hour, day_of_week) -> DropFeatures(16) -> FeaturesetValidator(8 cols) "
+                   "(BASELINE configs[4])",
     }[name]
 
 
@@ -265,6 +298,8 @@ def main():
         return
 
     name = args.workload
+    if name == "ingest6":
+        return main_ingest(args, rank, local_rank, world)
     B = args.batch or (262144 if name == "trees_ens4" else 1048576)
 
     cpu = None
@@ -419,6 +454,147 @@ def main():
                          "kernel_ms_per_launch": kms, "peak_source": peak_src},
             "gpu_launches": int(launches),
             "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main_ingest(args, rank, local_rank, world):
+    """config 5: the columnar feature-set plan.  Rows shard over ranks with no exchange at all (every rank ingests its
+    own partition, as the reference's N workers write their own target partitions)."""
+    name = "ingest6"
+    B = args.batch or 524288
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(name, args.cpu_seconds)
+        cpu["vectorised_numpy_events_per_s_1core"] = cpu_vectorised(name, make_workload(name, 65536))
+
+    import torch
+
+    from mlrun_b200 import _native as nat
+    from mlrun_b200.feature_store import ingest as bingest
+    from mlrun_b200.feature_store import steps as bsteps
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    nat.init(local_rank)
+    info = nat.device_info()
+    wl = make_workload(name, 65536, seed=2 + rank)
+    fset = bingest.FeatureSet("ingest6", timestamp_key="timestamp")
+    cur = fset.graph
+    for st in wl.build_steps(bsteps):
+        cur = cur.to(st)
+    for c, v in zip(wl.checked_cols, [bsteps.MinMaxValidator(severity="info", min=-2.5, max=2.5)] * len(wl.checked_cols)):
+        fset[c] = bingest.Feature(validator=v)
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        fset.ingest(wl.df.iloc[:4096])  # lowers the graph (public API) and warms the plan
+    iplan = fset.plan
+    plan = iplan.plan
+    stride = ((B * 4 + 255) // 256) * 256
+    ins, _keep = iplan._inputs(wl.df)
+    reps = int(np.ceil(B / len(wl.df)))
+    nbuf = 2  # 2 x 537 MB of distinct rows: consecutive steps never re-read L2-resident data
+    bufs = []
+    for j in range(nbuf):
+        host = np.zeros(plan.n_in * stride, dtype=np.uint8)
+        for slot, a in ins.items():
+            raw = np.tile(np.roll(a, j * 977), reps)[:B].view(np.uint8)
+            host[slot * stride: slot * stride + raw.size] = raw
+        bufs.append(torch.from_numpy(host).cuda())
+        del host
+    out = torch.empty(plan.n_out * stride, dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(max(plan.n_counters, 1), dtype=torch.int64, device="cuda")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+
+    def step(i):
+        plan.run_device(bufs[i % nbuf].data_ptr(), stride, B, out.data_ptr(), stride, cnt.data_ptr(), stream.cuda_stream)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sync()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    time.sleep(0.25)
+    l0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    sync()
+    t_wall1 = time.perf_counter()
+    launches = nat.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    n_it = max(args.steps, 10)
+    kms = plan.time_device([b.data_ptr() for b in bufs], stride, B, out.data_ptr(), stride, cnt.data_ptr(), n_it) / n_it
+    lat = []
+    for _ in range(20):
+        plan.time_device([bufs[0].data_ptr()], stride, 4096, out.data_ptr(), stride, cnt.data_ptr(), 1)
+    for _ in range(300):
+        lat.append(plan.time_device([bufs[0].data_ptr()], stride, 4096, out.data_ptr(), stride, cnt.data_ptr(), 1) * 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        frames = [wl.df, wl.df.iloc[::-1].reset_index(drop=True)]
+        with contextlib.redirect_stdout(io.StringIO()):
+            for j in range(2):
+                fset.ingest(frames[j % 2])
+            n_e2e = max(3, min(args.steps, 10))
+            t0 = time.perf_counter()
+            for j in range(n_e2e):
+                res = fset.ingest(frames[j % 2])
+            dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        Be = len(wl.df)
+        e2e = {"value": world * Be * n_e2e / dt, "unit": "events/s", "h2d_bytes_per_step": Be * wl.in_bytes_per_row,
+               "d2h_bytes_per_step": Be * wl.out_bytes_per_row, "batch": Be, "steps": n_e2e, "out_columns": int(res.shape[1]),
+               "api": "FeatureSet.ingest(DataFrame) (public API): frame columns -> H2D per column -> columns_kernel -> D2H per "
+                      "column -> DataFrame (pageable host memory; includes the frame (dis)assembly)"}
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bpe = wl.in_bytes_per_row + wl.out_bytes_per_row
+        achieved = bpe * B / (kms * 1e-3) / 1e9
+        line = {
+            "metric": "events/sec", "value": world * B * args.steps / (ms * 1e-3), "unit": "events/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 / int32 / int64 columns, fp64 compares", "data": "synthetic",
+            "config": {"workload": workload_desc(name), "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"row-sharded x{world}, no exchange",
+                       "l2": f"{nbuf} rotating columnar inputs of {B * wl.in_bytes_per_row / 1e6:.0f} MB (> 126 MB L2)",
+                       "device": info["name"], "kernel": "columns_kernel (b2s_columns.cuh)",
+                       "n_column_ops": len(iplan.out), "out_slots": plan.n_out},
+            "p50_step_latency_us": {"batch": 4096, "p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                                    "how": "CUDA events around one columns_kernel launch, 300 samples"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": measured_traffic(name, B), "kernel": "columns_kernel", "algorithmic_bytes_per_event": bpe,
+                         "kernel_ms_per_launch": kms, "peak_source": peak_src},
+            "gpu_launches": int(launches), "clocks": clocks,
         }
         if e2e:
             line["e2e"] = e2e

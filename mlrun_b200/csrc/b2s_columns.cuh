@@ -7,7 +7,7 @@
 // int32; an int64 column is two adjacent slots), an output slot likewise.  The lowered graph is a list of
 // column ops, each reading one input column and writing 0..n output columns; a work item is (op, chunk of
 // rows); persistent CTAs take items round-robin, so neighbouring CTAs stream different columns of the same
-// row range.  Every access is a fully coalesced 4-byte-per-lane (or 8-byte) load/store: each input word is
+// row range.  Every access is a fully coalesced 16-byte-per-lane load/store (4-byte on ragged tails): each input word is
 // read once, each output word written once -- the kernel is a pure HBM stream.
 // Compares run in fp64 against fp64 tables: float32/int32 values convert exactly, so range edges and category
 // matches agree bit for bit with the reference's Python comparisons.  Violations / unmatched values are counted
@@ -62,8 +62,9 @@ struct ColParams {
 };
 
 constexpr int kColThreads = 256;
-constexpr int kColUnroll = 4;                              // independent loads in flight per thread
-constexpr int kColChunk = kColThreads * kColUnroll * 4;    // rows per work item (4096)
+constexpr int kColVec = 4;                                  // rows per 16-byte access
+constexpr int kColUnroll = 4;                               // independent 16-byte loads in flight per thread
+constexpr int kColChunk = kColThreads * kColUnroll * kColVec;  // rows per work item (4096)
 
 __device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b) {
   int64_t q = a / b;
@@ -108,113 +109,173 @@ __device__ __forceinline__ int32_t date_part(int64_t ns, int part) {
   }
 }
 
+// one 4-byte source word -> the op's outputs (shared by the vector and the tail paths)
+__device__ __forceinline__ uint32_t col_word(const ColOp& op, const double* __restrict__ tab, uint32_t bits, double& x, bool& hit) {
+  hit = true;
+  if (op.src_int) {
+    x = (double)(int32_t)bits;
+  } else {
+    float f = __uint_as_float(bits);
+    if (op.has_fill && f != f) f = op.fill;  // Imputer._impute (steps.py:397-406)
+    bits = __float_as_uint(f);
+    x = (double)f;
+  }
+  if (op.kind == CK_RANGE) {  // MapValues._map_value (steps.py:189-201): first match in mapping order wins
+    double val = x;
+    hit = false;
+    for (int q = op.n - 1; q >= 0; --q) {
+      const bool in = x >= tab[q] && x < tab[op.n + q];
+      val = in ? tab[2 * op.n + q] : val;
+      hit |= in;
+    }
+    x = val;
+    bits = __float_as_uint((float)val);
+  } else if (op.kind == CK_VALUE) {
+    double val = x;
+    hit = false;
+    for (int q = op.n - 1; q >= 0; --q) {
+      const bool in = x == tab[q];
+      val = in ? tab[op.n + q] : val;
+      hit |= in;
+    }
+    x = val;
+    bits = __float_as_uint((float)val);
+  }
+  return bits;
+}
+
+__device__ __forceinline__ unsigned int col_check(const ColOp& op, double x) {
+  const bool lo_bad = (op.check & 1) && x < op.cmin;
+  const bool hi_bad = (op.check & 2) && x > op.cmax;
+  return (lo_bad || hi_bad) ? 1u : 0u;
+}
+
 __global__ void __launch_bounds__(kColThreads) columns_kernel(const __grid_constant__ ColParams p) {
   __shared__ unsigned int s_cnt[2];
   const int tid = threadIdx.x;
   const int64_t n_chunks = (p.n_rows + kColChunk - 1) / kColChunk;
   const int64_t n_items = n_chunks * p.n_ops;
+  // 16-byte accesses need 16-byte aligned slots (the strides the host path uses are multiples of 256)
+  const bool vec_ok = ((p.in_stride | p.out_stride) & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.in) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int64_t chunk = item / p.n_ops;
     const ColOp op = p.ops[item - chunk * p.n_ops];
     const int64_t row0 = chunk * kColChunk;
-    const int64_t rows = (p.n_rows - row0 < kColChunk) ? (p.n_rows - row0) : kColChunk;
+    const int rows = (int)((p.n_rows - row0 < kColChunk) ? (p.n_rows - row0) : kColChunk);
     const char* src = p.in + (int64_t)op.src * p.in_stride;
     char* dst = op.dst >= 0 ? p.out + (int64_t)op.dst * p.out_stride : nullptr;
     const double* tab = p.tab + op.tab;
     unsigned int bad = 0, miss = 0;
-    if (op.check || op.miss >= 0) {
+    const bool counts = op.check || op.miss >= 0;
+    if (counts) {
       if (tid < 2) s_cnt[tid] = 0;
       __syncthreads();
     }
 
     if (op.kind == CK_COPY64 || op.kind == CK_DATE) {
+      // 8-byte sources: two rows per 16-byte load
       const int64_t* s = reinterpret_cast<const int64_t*>(src) + row0;
-      for (int base = tid; base < rows; base += kColThreads * kColUnroll) {
-        int64_t v[kColUnroll];
+      const int pairs = vec_ok ? rows / 2 : 0;
+      for (int base = tid; base < pairs; base += kColThreads * kColUnroll) {
+        longlong2 v[kColUnroll];
 #pragma unroll
         for (int u = 0; u < kColUnroll; ++u) {
           const int i = base + u * kColThreads;
-          v[u] = i < rows ? s[i] : 0;
+          v[u] = i < pairs ? reinterpret_cast<const longlong2*>(s)[i] : make_longlong2(0, 0);
         }
 #pragma unroll
         for (int u = 0; u < kColUnroll; ++u) {
           const int i = base + u * kColThreads;
-          if (i >= rows) continue;
+          if (i >= pairs) continue;
           if (op.kind == CK_COPY64) {
-            reinterpret_cast<int64_t*>(dst)[row0 + i] = v[u];
+            reinterpret_cast<longlong2*>(reinterpret_cast<int64_t*>(dst) + row0)[i] = v[u];
           } else {
-            const bool nat = v[u] == INT64_MIN;  // NaT
-            miss += nat ? 1u : 0u;
-            reinterpret_cast<int32_t*>(dst)[row0 + i] = nat ? -1 : date_part(v[u], op.part);
+            const bool n0 = v[u].x == INT64_MIN, n1 = v[u].y == INT64_MIN;  // NaT
+            miss += (n0 ? 1u : 0u) + (n1 ? 1u : 0u);
+            int2 o;
+            o.x = n0 ? -1 : date_part(v[u].x, op.part);
+            o.y = n1 ? -1 : date_part(v[u].y, op.part);
+            reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(dst) + row0)[i] = o;
           }
+        }
+      }
+      for (int i = pairs * 2 + tid; i < rows; i += kColThreads) {  // tail / unaligned
+        const int64_t v = s[i];
+        if (op.kind == CK_COPY64) {
+          reinterpret_cast<int64_t*>(dst)[row0 + i] = v;
+        } else {
+          const bool nat = v == INT64_MIN;
+          miss += nat ? 1u : 0u;
+          reinterpret_cast<int32_t*>(dst)[row0 + i] = nat ? -1 : date_part(v, op.part);
         }
       }
     } else {
       const uint32_t* s = reinterpret_cast<const uint32_t*>(src) + row0;
-      for (int base = tid; base < rows; base += kColThreads * kColUnroll) {
-        uint32_t w[kColUnroll];
+      const int quads = vec_ok ? rows / kColVec : 0;
+      for (int base = tid; base < quads; base += kColThreads * kColUnroll) {
+        uint4 w[kColUnroll];
 #pragma unroll
         for (int u = 0; u < kColUnroll; ++u) {
           const int i = base + u * kColThreads;
-          w[u] = i < rows ? s[i] : 0u;
+          w[u] = i < quads ? reinterpret_cast<const uint4*>(s)[i] : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < kColUnroll; ++u) {
           const int i = base + u * kColThreads;
-          if (i >= rows) continue;
-          uint32_t bits = w[u];
+          if (i >= quads) continue;
           if (op.kind == CK_COPY32 && !op.check) {
-            reinterpret_cast<uint32_t*>(dst)[row0 + i] = bits;
+            reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(dst) + row0)[i] = w[u];
             continue;
           }
-          double x;
-          if (op.src_int) {
-            x = (double)(int32_t)bits;
-          } else {
-            float f = __uint_as_float(bits);
-            if (op.has_fill && f != f) f = op.fill;  // Imputer._impute (steps.py:397-406)
-            bits = __float_as_uint(f);
-            x = (double)f;
-          }
-          if (op.kind == CK_RANGE || op.kind == CK_VALUE) {  // MapValues._map_value (steps.py:189-201)
-            bool hit = false;
-            double val = x;
-            if (op.kind == CK_RANGE) {
-              for (int q = op.n - 1; q >= 0; --q) {  // first match in mapping order wins
-                const bool in = x >= tab[q] && x < tab[op.n + q];
-                val = in ? tab[2 * op.n + q] : val;
-                hit |= in;
-              }
-            } else {
-              for (int q = op.n - 1; q >= 0; --q) {
-                const bool in = x == tab[q];
-                val = in ? tab[op.n + q] : val;
-                hit |= in;
-              }
-            }
+          uint32_t in[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+          double x[4];
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            bool hit;
+            o[k] = col_word(op, tab, in[k], x[k], hit);
             miss += hit ? 0u : 1u;
-            x = val;
-            reinterpret_cast<float*>(dst)[row0 + i] = (float)val;
-          } else if (op.kind == CK_ONEHOT) {  // OneHotEncoder._encode (steps.py:453-470): unknown -> all zeros
-            bool any = false;
-            for (int q = 0; q < op.n; ++q) {
-              const bool is = x == tab[q];
-              any |= is;
-              reinterpret_cast<int32_t*>(dst + (int64_t)q * p.out_stride)[row0 + i] = is ? 1 : 0;
-            }
-            miss += any ? 0u : 1u;
-          } else if (op.kind != CK_CHECK) {  // CK_F32 (imputed) or checked CK_COPY32
-            reinterpret_cast<uint32_t*>(dst)[row0 + i] = bits;
+            if (op.check) bad += col_check(op, x[k]);
           }
-          if (op.check) {
-            const bool lo_bad = (op.check & 1) && x < op.cmin;
-            const bool hi_bad = (op.check & 2) && x > op.cmax;
-            bad += (lo_bad || hi_bad) ? 1u : 0u;
+          if (op.kind == CK_ONEHOT) {  // OneHotEncoder._encode (steps.py:453-470): unknown -> all zeros
+            bool any[4] = {false, false, false, false};
+            for (int q = 0; q < op.n; ++q) {
+              const double c = tab[q];
+              int4 oh;
+              oh.x = x[0] == c; oh.y = x[1] == c; oh.z = x[2] == c; oh.w = x[3] == c;
+              any[0] |= oh.x; any[1] |= oh.y; any[2] |= oh.z; any[3] |= oh.w;
+              reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(dst + (int64_t)q * p.out_stride) + row0)[i] = oh;
+            }
+            miss += (any[0] ? 0u : 1u) + (any[1] ? 0u : 1u) + (any[2] ? 0u : 1u) + (any[3] ? 0u : 1u);
+          } else if (op.kind != CK_CHECK) {
+            reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(dst) + row0)[i] = make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
       }
+      for (int i = quads * kColVec + tid; i < rows; i += kColThreads) {  // tail / unaligned
+        double x;
+        bool hit;
+        const uint32_t o = (op.kind == CK_COPY32 && !op.check) ? s[i] : col_word(op, tab, s[i], x, hit);
+        if (op.kind == CK_COPY32 && !op.check) {
+          reinterpret_cast<uint32_t*>(dst)[row0 + i] = o;
+          continue;
+        }
+        miss += hit ? 0u : 1u;
+        if (op.check) bad += col_check(op, x);
+        if (op.kind == CK_ONEHOT) {
+          bool any = false;
+          for (int q = 0; q < op.n; ++q) {
+            const bool is = x == tab[q];
+            any |= is;
+            reinterpret_cast<int32_t*>(dst + (int64_t)q * p.out_stride)[row0 + i] = is ? 1 : 0;
+          }
+          miss += any ? 0u : 1u;
+        } else if (op.kind != CK_CHECK) {
+          reinterpret_cast<uint32_t*>(dst)[row0 + i] = o;
+        }
+      }
     }
-    if (op.check || op.miss >= 0) {
+    if (counts) {
       // one shared-memory atomic per warp, one global atomic per item
       for (int o = 16; o > 0; o >>= 1) {
         bad += __shfl_xor_sync(0xffffffffu, bad, o);
