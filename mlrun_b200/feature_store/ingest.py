@@ -326,8 +326,11 @@ class IngestPlan:
         results to int64 (what a frame re-assembled from Python ints has) at the price of a host-side copy."""
         import pandas as pd
 
-        if frame_schema(df) != self.schema:
-            raise ValueError("the frame does not carry the schema this plan was lowered for")
+        key = (tuple(df.columns), tuple(df.dtypes))
+        if key != getattr(self, "_seen_key", None):  # same labels and dtypes as a frame already checked: skip the walk
+            if frame_schema(df) != self.schema:
+                raise ValueError("the frame does not carry the schema this plan was lowered for")
+            self._seen_key = key
         n = len(df)
         ins, _keep = self._inputs(df)
         bufs, outs = {}, {}
