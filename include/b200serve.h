@@ -239,6 +239,20 @@ int b2s_cols_run_host(b2s_cols_t plan, const void* const* h_in_slots, int64_t n_
 int b2s_cols_time_device(b2s_cols_t plan, const void* const* d_in, int32_t n_bufs, int64_t in_slot_stride, int64_t n_rows,
                          void* d_out, int64_t out_slot_stride, uint64_t* d_counters, int32_t n_iters, float* total_ms);
 
+/* ---- body codec (host code): the step on either side of the path for HTTP / stream triggers ------------
+ * GraphServer.run json-decodes the request body (serving/server.py:262-277) and _process_response json.dumps
+ * the result (:298-308).  b2s_json_parse_inputs finds the top-level "inputs" member of a V2 body and converts
+ * its numbers straight into float32 rows (row-major; a flat list is one scalar per event): the same values as
+ * np.asarray(json.loads(body)["inputs"], dtype=float32) (null counts as NaN).  [value_begin, value_end) is the
+ * member's text, so the caller can decode the small remainder of the body (id, model, operation) as usual.
+ * B2S_ERR_UNSUPPORTED: not such a body (strings / dicts / ragged rows) -- the caller falls back to json.loads. */
+int b2s_json_parse_inputs(const char* body, int64_t len, float* out, int64_t out_cap, int64_t* n_rows, int64_t* n_cols,
+                          int64_t* value_begin, int64_t* value_end);
+/* text of a result matrix exactly as json.dumps prints it: float32 values widened to double and printed with
+ * Python's repr (vals = float32*), or int32 labels (is_int); flat != 0 prints [v0, v1, ...] for n_cols == 1. */
+int b2s_json_format_outputs(const void* vals, int32_t is_int, int64_t n_rows, int64_t n_cols, int32_t flat, char* out,
+                            int64_t out_cap, int64_t* out_len);
+
 #ifdef __cplusplus
 }
 #endif

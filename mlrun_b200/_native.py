@@ -97,6 +97,10 @@ SIGNATURES = {
     "b2s_cols_info": (C.c_int, [_vp, _pi32, _pi32]),
     "b2s_cols_run_device": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "b2s_cols_run_host": (C.c_int, [_vp, C.POINTER(_vp), _i64, C.POINTER(_vp), C.POINTER(_u64), C.POINTER(Stats)]),
+    # body codec
+    "b2s_json_parse_inputs": (C.c_int, [C.c_char_p, _i64, _pf32, _i64, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
+                                        C.POINTER(_i64)]),
+    "b2s_json_format_outputs": (C.c_int, [_vp, _i32, _i64, _i64, _i32, C.c_char_p, _i64, C.POINTER(_i64)]),
     "b2s_cols_time_device": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i64, _i64, _vp, _i64, _vp, _i32, _pf32]),
 }
 

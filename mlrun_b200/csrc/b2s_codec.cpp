@@ -1,0 +1,321 @@
+// b2s_codec.cpp -- body codec of the serving boundary (host code, no CUDA).
+//
+// For HTTP / stream triggers the reference json-decodes every request body (GraphServer.run,
+// serving/server.py:262-277) and json.dumps every response (_process_response, :298-308); for V2 bodies
+// {"inputs": [[...], ...]} that is where a worker's time goes once the model is fast.
+// This file parses the "inputs" matrix of a body straight into float32 rows (the layout b2s_submit /
+// b2s_run_host take) and prints result matrices the way json.dumps does:
+//   * numbers are converted with std::from_chars<double> (correctly rounded, like Python's float()) and then
+//     rounded to float32 -- the same two roundings as np.asarray(json.loads(body)["inputs"], dtype=float32);
+//   * floats are printed with the shortest round-trip digits (std::to_chars) laid out by Python's repr rule
+//     (fixed notation for 1e-4 <= |x| < 1e16, else d.ddde+XX), so the text is byte-identical to json.dumps.
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+
+#include "../../include/b200serve.h"
+#include "b2s_internal.h"
+
+namespace {
+
+struct Cur {
+  const char* p;
+  const char* end;
+  void ws() {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+  }
+  bool eat(char c) {
+    ws();
+    if (p < end && *p == c) {
+      ++p;
+      return true;
+    }
+    return false;
+  }
+};
+
+bool skip_string(Cur& c) {  // at the opening quote
+  if (c.p >= c.end || *c.p != '"') return false;
+  ++c.p;
+  while (c.p < c.end) {
+    const char ch = *c.p++;
+    if (ch == '\\') {
+      if (c.p >= c.end) return false;
+      ++c.p;
+    } else if (ch == '"') {
+      return true;
+    }
+  }
+  return false;
+}
+
+bool skip_value(Cur& c, int depth = 0);
+
+bool skip_container(Cur& c, char open, char close, int depth) {
+  if (depth > 64) return false;
+  ++c.p;  // open
+  c.ws();
+  if (c.p < c.end && *c.p == close) {
+    ++c.p;
+    return true;
+  }
+  for (;;) {
+    c.ws();
+    if (open == '{') {
+      if (!skip_string(c)) return false;
+      if (!c.eat(':')) return false;
+    }
+    if (!skip_value(c, depth + 1)) return false;
+    c.ws();
+    if (c.p >= c.end) return false;
+    if (*c.p == ',') {
+      ++c.p;
+      continue;
+    }
+    if (*c.p == close) {
+      ++c.p;
+      return true;
+    }
+    return false;
+  }
+}
+
+bool skip_value(Cur& c, int depth) {
+  c.ws();
+  if (c.p >= c.end) return false;
+  const char ch = *c.p;
+  if (ch == '"') return skip_string(c);
+  if (ch == '{') return skip_container(c, '{', '}', depth);
+  if (ch == '[') return skip_container(c, '[', ']', depth);
+  const char* s = c.p;  // literal / number: up to a delimiter
+  while (c.p < c.end && *c.p != ',' && *c.p != ']' && *c.p != '}' && *c.p != ' ' && *c.p != '\t' && *c.p != '\n' && *c.p != '\r') ++c.p;
+  return c.p > s;
+}
+
+// one JSON number (json.loads grammar, plus the NaN / Infinity / -Infinity literals it accepts, plus null -> NaN)
+bool parse_number(Cur& c, float* out) {
+  c.ws();
+  const char* s = c.p;
+  if (s >= c.end) return false;
+  auto lit = [&](const char* w, float v) {
+    const size_t n = strlen(w);
+    if ((size_t)(c.end - s) >= n && memcmp(s, w, n) == 0) {
+      c.p = s + n;
+      *out = v;
+      return true;
+    }
+    return false;
+  };
+  if (*s == 'N') return lit("NaN", std::numeric_limits<float>::quiet_NaN());
+  if (*s == 'I') return lit("Infinity", std::numeric_limits<float>::infinity());
+  if (*s == 'n') return lit("null", std::numeric_limits<float>::quiet_NaN());
+  if (*s == '-' && s + 1 < c.end && s[1] == 'I') {
+    ++s;
+    if (lit("Infinity", -std::numeric_limits<float>::infinity())) return true;
+    return false;
+  }
+  const char* q = s;
+  bool integral = true;  // json.loads makes an int of it: "-0" is 0, not -0.0
+  if (q < c.end && *q == '-') ++q;
+  if (q >= c.end) return false;
+  if (*q == '0') {
+    ++q;
+  } else if (*q >= '1' && *q <= '9') {
+    while (q < c.end && *q >= '0' && *q <= '9') ++q;
+  } else {
+    return false;
+  }
+  if (q < c.end && *q == '.') {
+    integral = false;
+    ++q;
+    const char* f = q;
+    while (q < c.end && *q >= '0' && *q <= '9') ++q;
+    if (q == f) return false;
+  }
+  if (q < c.end && (*q == 'e' || *q == 'E')) {
+    integral = false;
+    ++q;
+    if (q < c.end && (*q == '+' || *q == '-')) ++q;
+    const char* e = q;
+    while (q < c.end && *q >= '0' && *q <= '9') ++q;
+    if (q == e) return false;
+  }
+  double d = 0.0;
+  const char* from = s;
+  auto r = std::from_chars(from, q, d);
+  if (r.ec == std::errc::result_out_of_range) {
+    d = (*s == '-') ? -HUGE_VAL : HUGE_VAL;  // json.loads gives +-inf for 1e999 (and 0.0 for 1e-999)
+    bool tiny = false;
+    for (const char* t = s; t < q; ++t)
+      if ((*t == 'e' || *t == 'E') && t + 1 < q && t[1] == '-') tiny = true;
+    if (tiny) d = (*s == '-') ? -0.0 : 0.0;
+  } else if (r.ec != std::errc() || r.ptr != q) {
+    return false;
+  }
+  if (integral && d == 0.0) d = 0.0;
+  *out = (float)d;
+  c.p = q;
+  return true;
+}
+
+// Python repr(float) of a double, into buf; returns the length
+int repr_double(double v, char* buf) {
+  if (std::isnan(v)) return (int)(stpcpy(buf, "NaN") - buf);  // json.dumps spelling
+  if (std::isinf(v)) return (int)(stpcpy(buf, v < 0 ? "-Infinity" : "Infinity") - buf);
+  char sci[40];
+  auto r = std::to_chars(sci, sci + sizeof(sci), v, std::chars_format::scientific);  // shortest round-trip digits
+  *r.ptr = 0;
+  char* o = buf;
+  const char* s = sci;
+  if (*s == '-') *o++ = *s++;
+  char digits[24];
+  int nd = 0;
+  digits[nd++] = *s++;
+  if (*s == '.') {
+    ++s;
+    while (*s && *s != 'e') digits[nd++] = *s++;
+  }
+  const int exp10 = atoi(s + 1);  // after 'e'
+  if (exp10 >= -4 && exp10 < 16) {
+    if (exp10 < 0) {
+      *o++ = '0';
+      *o++ = '.';
+      for (int i = 0; i < -exp10 - 1; ++i) *o++ = '0';
+      for (int i = 0; i < nd; ++i) *o++ = digits[i];
+    } else {
+      for (int i = 0; i <= exp10; ++i) *o++ = i < nd ? digits[i] : '0';
+      *o++ = '.';
+      if (nd > exp10 + 1) {
+        for (int i = exp10 + 1; i < nd; ++i) *o++ = digits[i];
+      } else {
+        *o++ = '0';
+      }
+    }
+  } else {
+    *o++ = digits[0];
+    if (nd > 1) {
+      *o++ = '.';
+      for (int i = 1; i < nd; ++i) *o++ = digits[i];
+    }
+    *o++ = 'e';
+    *o++ = exp10 < 0 ? '-' : '+';
+    const int a = exp10 < 0 ? -exp10 : exp10;
+    if (a < 10) *o++ = '0';
+    o += snprintf(o, 8, "%d", a);
+  }
+  return (int)(o - buf);
+}
+
+}  // namespace
+
+extern "C" int b2s_json_parse_inputs(const char* body, int64_t len, float* out, int64_t out_cap, int64_t* n_rows, int64_t* n_cols,
+                                     int64_t* value_begin, int64_t* value_end) {
+  if (!body || len <= 0 || !out || !n_rows || !n_cols) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+  Cur c{body, body + len};
+  if (!c.eat('{')) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "body is not a JSON object");
+  c.ws();
+  if (c.p < c.end && *c.p == '}') return b2s_int_fail(B2S_ERR_UNSUPPORTED, "no \"inputs\" member");
+  for (;;) {
+    c.ws();
+    const char* k = c.p;
+    if (!skip_string(c)) return b2s_int_fail(B2S_ERR_INVALID, "malformed JSON at offset %lld", (long long)(c.p - body));
+    const bool is_inputs = (c.p - k) == 8 && memcmp(k, "\"inputs\"", 8) == 0;
+    if (!c.eat(':')) return b2s_int_fail(B2S_ERR_INVALID, "malformed JSON at offset %lld", (long long)(c.p - body));
+    if (is_inputs) {
+      c.ws();
+      const char* v0 = c.p;
+      if (!c.eat('[')) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "\"inputs\" is not a list");
+      int64_t rows = 0, cols = -1, n = 0;
+      c.ws();
+      if (c.p < c.end && *c.p == ']') {
+        ++c.p;
+        cols = 0;
+      } else {
+        c.ws();
+        const bool nested = c.p < c.end && *c.p == '[';
+        for (;;) {
+          if (nested) {
+            if (!c.eat('[')) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "\"inputs\" mixes rows and scalars");
+            int64_t w = 0;
+            c.ws();
+            if (!(c.p < c.end && *c.p == ']')) {
+              for (;;) {
+                if (n >= out_cap) return b2s_int_fail(B2S_ERR_INVALID, "inputs do not fit the %lld-float buffer", (long long)out_cap);
+                if (!parse_number(c, out + n)) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "non-numeric input at offset %lld", (long long)(c.p - body));
+                ++n;
+                ++w;
+                if (c.eat(',')) continue;
+                break;
+              }
+            }
+            if (!c.eat(']')) return b2s_int_fail(B2S_ERR_INVALID, "malformed JSON at offset %lld", (long long)(c.p - body));
+            if (cols < 0) cols = w;
+            if (w != cols) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "ragged \"inputs\" rows (%lld vs %lld)", (long long)w, (long long)cols);
+          } else {  // a flat list: one scalar per event
+            if (n >= out_cap) return b2s_int_fail(B2S_ERR_INVALID, "inputs do not fit the %lld-float buffer", (long long)out_cap);
+            if (!parse_number(c, out + n)) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "non-numeric input at offset %lld", (long long)(c.p - body));
+            ++n;
+            cols = 1;
+          }
+          ++rows;
+          if (c.eat(',')) continue;
+          break;
+        }
+        if (!c.eat(']')) return b2s_int_fail(B2S_ERR_INVALID, "malformed JSON at offset %lld", (long long)(c.p - body));
+      }
+      *n_rows = rows;
+      *n_cols = cols < 0 ? 0 : cols;
+      if (value_begin) *value_begin = v0 - body;
+      if (value_end) *value_end = c.p - body;
+      return B2S_OK;
+    }
+    if (!skip_value(c)) return b2s_int_fail(B2S_ERR_INVALID, "malformed JSON at offset %lld", (long long)(c.p - body));
+    if (c.eat(',')) continue;
+    if (c.eat('}')) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "no \"inputs\" member");
+    return b2s_int_fail(B2S_ERR_INVALID, "malformed JSON at offset %lld", (long long)(c.p - body));
+  }
+}
+
+extern "C" int b2s_json_format_outputs(const void* vals, int32_t is_int, int64_t n_rows, int64_t n_cols, int32_t flat, char* out,
+                                       int64_t out_cap, int64_t* out_len) {
+  if (!vals || !out || !out_len || n_rows < 0 || n_cols < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+  if (flat && n_cols != 1) return b2s_int_fail(B2S_ERR_INVALID, "a flat list needs one value per row");
+  char* o = out;
+  char* const end = out + out_cap;
+  const float* f = static_cast<const float*>(vals);
+  const int32_t* iv = static_cast<const int32_t*>(vals);
+  auto room = [&](int n) { return o + n <= end; };
+  if (!room(2)) return b2s_int_fail(B2S_ERR_INVALID, "output buffer too small");
+  *o++ = '[';
+  for (int64_t r = 0; r < n_rows; ++r) {
+    if (r) {
+      if (!room(2)) return b2s_int_fail(B2S_ERR_INVALID, "output buffer too small");
+      *o++ = ',';
+      *o++ = ' ';
+    }
+    if (!flat) {
+      if (!room(1)) return b2s_int_fail(B2S_ERR_INVALID, "output buffer too small");
+      *o++ = '[';
+    }
+    for (int64_t k = 0; k < n_cols; ++k) {
+      if (!room(40)) return b2s_int_fail(B2S_ERR_INVALID, "output buffer too small");
+      if (k) {
+        *o++ = ',';
+        *o++ = ' ';
+      }
+      if (is_int) o += snprintf(o, 16, "%d", iv[r * n_cols + k]);
+      else o += repr_double((double)f[r * n_cols + k], o);
+    }
+    if (!flat) {
+      if (!room(1)) return b2s_int_fail(B2S_ERR_INVALID, "output buffer too small");
+      *o++ = ']';
+    }
+  }
+  if (!room(1)) return b2s_int_fail(B2S_ERR_INVALID, "output buffer too small");
+  *o++ = ']';
+  *out_len = o - out;
+  return B2S_OK;
+}

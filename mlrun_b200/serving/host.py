@@ -276,6 +276,32 @@ class GraphServer(Serde):
         return compiled.responses(out, status, self.context)
 
 
+    def run_json(self, body, event_id=None):
+        """wire-level batched entry for graphs whose root is a router / model server: a V2 body
+        `{"inputs": [[...], ...]}` (bytes / str) -> the Response GraphServer.run would answer for it (serving/server.py:
+        252-308), through the C body codec and ONE fused launch.  Bodies that are not a numeric matrix raise
+        `codec.NotV2Matrix` (use `run` for them)."""
+        import uuid
+
+        from ..lowering import LoweringError
+        from . import codec
+
+        compiled = self.compile()
+        name, version = compiled.responder
+        if not name:
+            raise LoweringError("run_json needs a graph that ends in a model server or a voting ensemble")
+        X, rest = codec.decode_body(body)
+        out, status = compiled.plan.run(np.ascontiguousarray(X), with_status=True)
+        if status.any():  # scikit-learn raises for the whole request (one event carries all rows)
+            return self.context.Response(body="ValueError: Input X contains NaN or infinity.", content_type="text/plain",
+                                         status_code=400)
+        response = {"id": event_id or rest.get("id") or uuid.uuid4().hex, "model_name": name, "outputs": None}
+        if version:
+            response["model_version"] = version
+        text = codec.format_outputs(out[:, 0] if out.shape[1] == 1 else out)
+        return self.context.Response(body=codec.dumps_with_outputs(response, text), content_type="application/json", status_code=200)
+
+
 def v2_serving_init(context, namespace=None):
     spec = json.loads(os.environ[SERVING_SPEC_ENV])
     server = GraphServer.from_dict(spec)

@@ -1,0 +1,88 @@
+"""Body codec (host code of libb200serve.so): same values as json.loads + np.asarray, same text as json.dumps."""
+
+import json
+import math
+
+import numpy as np
+import pytest
+
+from mlrun_b200.serving import codec
+
+
+def _ref(body):
+    return np.asarray(json.loads(body)["inputs"], dtype=np.float32)
+
+
+def test_parse_matches_json_loads_on_random_bodies():
+    rng = np.random.default_rng(11)
+    for rows, cols in [(1, 1), (3, 7), (64, 64), (257, 5)]:
+        X = rng.normal(size=(rows, cols)) * 10.0 ** rng.integers(-8, 9, size=(rows, cols))
+        body = json.dumps({"id": "abc", "inputs": X.tolist(), "model": "m1"})
+        got, (b, e) = codec.parse_inputs(body)
+        np.testing.assert_array_equal(got, _ref(body))
+        assert json.loads(body[b:e]) == X.tolist()
+        X2, rest = codec.decode_body(body.encode())
+        assert rest == {"id": "abc", "model": "m1"} and X2.shape == (rows, cols)
+
+
+def test_number_grammar_and_rounding():
+    texts = ["0", "-0", "5", "-17", "1.5", "0.1", "-2.5e-3", "1E5", "1e+5", "3.4028235e38", "3.4028236e38", "1e39", "-1e39",
+             "1e-46", "4.9e-324", "1e999", "-1e999", "1e-999", "123456789012345678901234567890", "0.30000000000000004",
+             "16777217", "1.00000005960464477539"]
+    body = '{"inputs": [[' + ", ".join(texts) + "]]}"
+    got, _ = codec.parse_inputs(body)
+    with np.errstate(over="ignore"):
+        want = _ref(body)
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))  # bit-exact, including -0.0
+    body = '{"inputs": [NaN, Infinity, -Infinity, null, 2]}'
+    got, _ = codec.parse_inputs(body)
+    assert got.shape == (5, 1) and np.isnan(got[0, 0]) and got[1, 0] == np.inf and got[2, 0] == -np.inf and np.isnan(got[3, 0])
+
+
+def test_layout_cases_and_whitespace():
+    nl, tab = chr(10), chr(9)
+    body = ('  {"a": {"inputs": [9]}, "s": "x\\"]\\\\", "inputs" :' + nl + " [ [1 , 2]," + tab + '[3,4] ] , "z": [1,{"q":[2]}]}')
+    assert json.loads(body)["inputs"] == [[1, 2], [3, 4]]
+    got, _ = codec.parse_inputs(body)
+    np.testing.assert_array_equal(got, [[1, 2], [3, 4]])
+    got, _ = codec.parse_inputs('{"inputs": []}')
+    assert got.shape == (0, 0)
+    got, _ = codec.parse_inputs('{"inputs": [[], []]}')
+    assert got.shape == (2, 0)
+    got, _ = codec.parse_inputs('{"inputs": [5]}')  # BASELINE configs[0] body
+    assert got.tolist() == [[5.0]]
+
+
+@pytest.mark.parametrize("body", ['{"inputs": [[1, 2], [3]]}', '{"inputs": [{"a": 1}]}', '{"inputs": ["x"]}', '{"x": 1}', "[1, 2]",
+                                  '{"inputs": [1, [2]]}', '{"inputs": 5}'])
+def test_bodies_for_the_per_event_path_are_reported(body):
+    json.loads(body)  # valid JSON
+    with pytest.raises(codec.NotV2Matrix):
+        codec.parse_inputs(body)
+
+
+@pytest.mark.parametrize("body", ['{"inputs": [[1, 2]', '{"inputs": [1,, 2]}', '{"inputs": [01]}', '{"inputs": [1.]}', '{inputs: [1]}'])
+def test_malformed_json_is_an_error(body):
+    with pytest.raises(json.JSONDecodeError):
+        json.loads(body)
+    with pytest.raises(Exception) as ei:
+        codec.parse_inputs(body)
+    assert not isinstance(ei.value, AssertionError)
+
+
+def test_format_is_byte_identical_to_json_dumps():
+    rng = np.random.default_rng(12)
+    vals = np.concatenate([
+        (rng.normal(size=3000) * 10.0 ** rng.integers(-12, 13, size=3000)).astype(np.float32),
+        np.array([0.0, -0.0, 1.0, -1.0, 100000.0, 1e16, 9999999.0, 1e-4, 9.999e-5, 1e-5, 123456.789, 3.4028235e38, 1e-45, 0.1,
+                  16777216.0, 1e15, 1e22], dtype=np.float32)])
+    assert codec.format_outputs(vals) == json.dumps([float(v) for v in vals]).encode()
+    m = vals[:3000].reshape(600, 5)
+    assert codec.format_outputs(m) == json.dumps(m.astype(np.float64).tolist()).encode()
+    labels = rng.integers(-5, 1000, size=777).astype(np.int32)
+    assert codec.format_outputs(labels) == json.dumps(labels.tolist()).encode()
+    specials = np.array([np.nan, np.inf, -np.inf], dtype=np.float32)
+    assert codec.format_outputs(specials) == json.dumps([math.nan, math.inf, -math.inf]).encode()
+    resp = {"id": "e1", "model_name": "ens", "outputs": None, "model_version": "v1"}
+    text = codec.dumps_with_outputs(resp, codec.format_outputs(vals[:4]))
+    assert text == json.dumps({**resp, "outputs": [float(v) for v in vals[:4]]}).encode()

@@ -91,3 +91,33 @@ def test_unlowerable_graph_is_a_hard_error():
     server = fn.to_mock_server()
     with pytest.raises(LoweringError):
         server.run_batch(np.zeros((4, 3), dtype=np.float32), names=["a", "b", "c"])
+
+
+def test_run_json_answers_like_the_reference_wire_path():
+    """bytes in -> bytes out through the C body codec + one fused launch, against the oracle's GraphServer.run on the
+    same JSON body (json.loads -> VotingEnsemble.do_event -> json.dumps)"""
+    from mlrun_b200.serving import codec
+
+    for kind in ("regression", "classification"):
+        wl = tree_workload(n_rows=300, n_feat=24, n_models=4, n_trees=10, depth=4, seed=7, n_fit=800, kind=kind)
+        body = json.dumps({"inputs": wl.X.astype(np.float64).tolist()}).encode()
+        server = wl.build_server(api_b200)
+        got = server.run_json(body, event_id="evt-1")
+        oserver = wl.build_server(api_oracle)
+        want = oserver.run(api_oracle.MockEvent(body=body, path="/v2/models/infer", event_id="evt-1", content_type="application/json"))
+        assert got.status_code == want.status_code == 200 and got.content_type == want.content_type
+        g, w = json.loads(got.body), json.loads(want.body)
+        assert list(g) == list(w) and g["id"] == w["id"] == "evt-1" and g["model_name"] == w["model_name"]
+        assert g["model_version"] == w["model_version"]
+        if kind == "classification":
+            assert g["outputs"] == w["outputs"] and all(isinstance(v, int) for v in g["outputs"])
+        else:
+            np.testing.assert_allclose(g["outputs"], w["outputs"], rtol=RTOL, atol=ATOL)
+            # the text itself is what json.dumps prints for those float32 votes
+            assert got.body == json.dumps({**g}).encode()
+    bad = wl.X.astype(np.float64).tolist()
+    bad[3][5] = float("nan")
+    resp = server.run_json(json.dumps({"inputs": bad}))
+    assert resp.status_code == 400 and "NaN" in resp.body
+    with pytest.raises(codec.NotV2Matrix):
+        server.run_json(json.dumps({"inputs": [{"f0": 1.0}]}))
