@@ -431,6 +431,30 @@ def main():
                "api": "GraphServer.run_batch (public API) -> b2s_run_host: pinned host rows -> H2D -> fused kernel -> "
                       "D2H outputs + per-row status"}
 
+    wire = None
+    if name == "trees_ens4" and rank == 0 and not args.no_e2e:
+        # wire level: a V2 JSON body of 4096 events -> JSON response, C body codec + one fused launch;
+        # beside it the reference's own decode/encode of the same body (json.loads -> np.asarray, json.dumps), model excluded
+        import json as _json
+
+        Bw = 4096
+        body = _json.dumps({"inputs": wl.X[:Bw].astype(np.float64).tolist()}).encode()
+        for _ in range(2):
+            resp = server.run_json(body, event_id="w")
+        n_w = 8
+        t0 = time.perf_counter()
+        for _ in range(n_w):
+            resp = server.run_json(body, event_id="w")
+        dt_w = (time.perf_counter() - t0) / n_w
+        t0 = time.perf_counter()
+        for _ in range(3):
+            np.asarray(_json.loads(body)["inputs"], dtype=np.float64)
+            _json.dumps({"id": "w", "model_name": "x", "outputs": [0.5] * Bw})
+        dt_py = (time.perf_counter() - t0) / 3
+        wire = {"value": Bw / dt_w, "unit": "events/s", "batch": Bw, "body_bytes": len(body), "response_bytes": len(resp.body),
+                "api": "GraphServer.run_json: JSON body -> b2s_json_parse_inputs -> fused plan -> b2s_json_format_outputs",
+                "python_json_codec_only_events_per_s": Bw / dt_py}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         bpe = BYTES_PER_EVENT[name]
@@ -457,6 +481,8 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if wire:
+            line["wire"] = wire
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -253,6 +253,27 @@ int b2s_json_parse_inputs(const char* body, int64_t len, float* out, int64_t out
 int b2s_json_format_outputs(const void* vals, int32_t is_int, int64_t n_rows, int64_t n_cols, int32_t flat, char* out,
                             int64_t out_cap, int64_t* out_len);
 
+/* ---- online feature table: real-time enrichment on the device -----------------------------------------
+ * EnrichmentModelRouter / EnrichmentVotingEnsemble.preprocess (serving/routers.py:1189-1196, 1335-1342) turn entity
+ * keys into feature vectors with OnlineVectorService.get (feature_store/feature_vector.py:975-1067): one online-store
+ * read per key, then None / NaN / Inf -> the impute policy's value (:1046-1052).  A b2s_table keeps the online table
+ * in HBM (64-bit keys -> rows of n_features float32) and resolves a batch of keys in one launch, writing the rows in
+ * the layout b2s_run_device reads.  impute[c] = NaN keeps column c as stored; rows of unknown keys are NaN (then
+ * imputed) and reported in found[] (the reference returns None for them). */
+typedef struct b2s_table_s* b2s_table_t;
+int b2s_table_create(const int64_t* keys, int64_t n_keys, const float* values, int32_t n_features, const float* impute,
+                     b2s_table_t* out);
+int b2s_table_destroy(b2s_table_t table);
+int b2s_table_info(b2s_table_t table, int64_t* n_keys, int32_t* n_features, int64_t* capacity);
+int b2s_table_lookup_device(b2s_table_t table, const int64_t* d_keys, int64_t n, float* d_rows, int64_t row_stride_bytes,
+                            int32_t* d_found, void* stream);
+int b2s_table_lookup_host(b2s_table_t table, const int64_t* keys, int64_t n, float* rows, int32_t* found, b2s_stats* stats);
+int b2s_table_time_device(b2s_table_t table, const int64_t* const* d_keys, int32_t n_bufs, int64_t n, float* d_rows,
+                          int64_t row_stride_bytes, int32_t* d_found, int32_t n_iters, float* total_ms);
+/* 64-bit FNV-1a of each string of a packed buffer (string i = bytes[offsets[i] .. offsets[i+1])): the key of a
+ * string-valued entity.  Host code. */
+int b2s_hash_strings(const char* bytes, const int64_t* offsets, int64_t n, int64_t* keys_out);
+
 #ifdef __cplusplus
 }
 #endif

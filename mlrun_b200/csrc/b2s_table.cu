@@ -1,0 +1,291 @@
+// b2s_table.cu -- device-resident online feature table: entity key -> feature vector (+ imputing), sm_100a.
+//
+// Replaces the lookup half of real-time feature enrichment: EnrichmentModelRouter / EnrichmentVotingEnsemble.preprocess
+// (mlrun/serving/routers.py:1189-1196, 1335-1342) call OnlineVectorService.get (mlrun/feature_store/feature_vector.py:
+// 975-1067), which emits every entity row into a storey graph that reads the online (NoSQL) store key by key, then fills
+// missing / NaN / Inf values from the impute policy (:1046-1052).  Here the online table lives in HBM: an open-addressing
+// hash table of 64-bit entity keys (linear probing, load factor <= 0.5, built once on the host) next to the
+// [n_keys][n_features] float32 matrix; one kernel launch resolves a batch of keys: each lane probes for one key, then
+// the warp copies the 32 rows it found with coalesced 16-byte accesses, imputing on the way, straight into the row
+// matrix the scoring plan reads (no host round trip between enrichment and predict).
+// Bound: HBM (random 4*F-byte row reads + the sequential output): algorithmic bytes = 8 (key) + 16 (slot) + 8*F per
+// query.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/b200serve.h"
+#include "b2s_internal.h"
+
+#define TAB_TRY(expr)                                                                                       \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess)                                                                                  \
+      return b2s_int_fail(B2S_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+namespace {
+
+struct Slot {
+  int64_t key;
+  int64_t row;  // -1: empty
+};
+
+__host__ __device__ inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+  x ^= x >> 30;
+  x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27;
+  x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31;
+  return x;
+}
+
+struct LookupParams {
+  const Slot* slots;
+  uint64_t mask;            // capacity - 1
+  const float* values;      // [n_keys][n_feat]
+  const float* impute;      // [n_feat]; NaN: keep the stored value
+  int32_t n_feat;
+  int32_t any_impute;
+  const int64_t* keys;      // [n]
+  int64_t n;
+  float* out;               // row i at out + i * out_stride (bytes)
+  int64_t out_stride;
+  int32_t* found;           // [n] 1 / 0 (rows of unknown keys are filled with NaN)
+};
+
+__global__ void __launch_bounds__(256) table_lookup_kernel(const __grid_constant__ LookupParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec = (p.n_feat & 3) == 0 && (p.out_stride & 15) == 0;
+  for (int64_t base = warp * 32; base < p.n; base += n_warps * 32) {
+    const int64_t q = base + lane;
+    int64_t row = -1;
+    if (q < p.n) {  // every lane probes for its own key
+      const int64_t key = p.keys[q];
+      uint64_t h = mix64((uint64_t)key) & p.mask;
+      for (;;) {
+        const Slot s = p.slots[h];
+        if (s.row < 0) break;
+        if (s.key == key) {
+          row = s.row;
+          break;
+        }
+        h = (h + 1) & p.mask;
+      }
+      if (p.found) p.found[q] = row >= 0 ? 1 : 0;
+    }
+    const int cnt = (int)((p.n - base < 32) ? (p.n - base) : 32);
+    for (int j = 0; j < cnt; ++j) {  // the warp copies query j's row together
+      const int64_t r = __shfl_sync(0xffffffffu, row, j);
+      float* dst = reinterpret_cast<float*>(reinterpret_cast<char*>(p.out) + (base + j) * p.out_stride);
+      const float* src = p.values + r * p.n_feat;
+      if (vec) {
+        for (int c = lane * 4; c < p.n_feat; c += 128) {
+          float4 v = r >= 0 ? *reinterpret_cast<const float4*>(src + c) : make_float4(NAN, NAN, NAN, NAN);
+          if (p.any_impute) {  // OnlineVectorService.get (:1046-1052): None / NaN / Inf -> impute value
+            const float4 f = *reinterpret_cast<const float4*>(p.impute + c);
+            v.x = (!(fabsf(v.x) <= 3.402823466e38f) && f.x == f.x) ? f.x : v.x;
+            v.y = (!(fabsf(v.y) <= 3.402823466e38f) && f.y == f.y) ? f.y : v.y;
+            v.z = (!(fabsf(v.z) <= 3.402823466e38f) && f.z == f.z) ? f.z : v.z;
+            v.w = (!(fabsf(v.w) <= 3.402823466e38f) && f.w == f.w) ? f.w : v.w;
+          }
+          *reinterpret_cast<float4*>(dst + c) = v;
+        }
+      } else {
+        for (int c = lane; c < p.n_feat; c += 32) {
+          float v = r >= 0 ? src[c] : NAN;
+          if (p.any_impute) {
+            const float f = p.impute[c];
+            v = (!(fabsf(v) <= 3.402823466e38f) && f == f) ? f : v;
+          }
+          dst[c] = v;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+struct b2s_table_s {
+  int64_t n_keys = 0;
+  int32_t n_feat = 0;
+  uint64_t cap = 0;
+  int any_impute = 0;
+  Slot* d_slots = nullptr;
+  float* d_values = nullptr;
+  float* d_impute = nullptr;
+  int grid = 0;
+  // host-call staging
+  std::mutex mu;
+  int64_t cap_rows = 0;
+  int64_t* d_keys = nullptr;
+  float* d_out = nullptr;
+  int32_t* d_found = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+extern "C" int b2s_table_create(const int64_t* keys, int64_t n_keys, const float* values, int32_t n_features, const float* impute,
+                                b2s_table_t* out) {
+  if (!keys || !values || !out || n_keys <= 0 || n_features <= 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+  if (!b2s_int_inited()) return b2s_int_fail(B2S_ERR_STATE, "b2s_init was not called (no CUDA device: there is no CPU fallback)");
+  uint64_t cap = 16;
+  while (cap < (uint64_t)n_keys * 2) cap <<= 1;
+  std::vector<Slot> slots(cap, Slot{0, -1});
+  for (int64_t i = 0; i < n_keys; ++i) {
+    uint64_t h = mix64((uint64_t)keys[i]) & (cap - 1);
+    while (slots[h].row >= 0) {
+      if (slots[h].key == keys[i]) return b2s_int_fail(B2S_ERR_INVALID, "duplicate entity key %lld (rows %lld and %lld)", (long long)keys[i], (long long)slots[h].row, (long long)i);
+      h = (h + 1) & (cap - 1);
+    }
+    slots[h] = Slot{keys[i], i};
+  }
+  auto* t = new b2s_table_s();
+  t->n_keys = n_keys;
+  t->n_feat = n_features;
+  t->cap = cap;
+  TAB_TRY(cudaSetDevice(b2s_int_device()));
+  TAB_TRY(cudaMalloc(&t->d_slots, cap * sizeof(Slot)));
+  TAB_TRY(cudaMemcpy(t->d_slots, slots.data(), cap * sizeof(Slot), cudaMemcpyHostToDevice));
+  TAB_TRY(cudaMalloc(&t->d_values, (size_t)n_keys * n_features * 4));
+  TAB_TRY(cudaMemcpy(t->d_values, values, (size_t)n_keys * n_features * 4, cudaMemcpyHostToDevice));
+  std::vector<float> imp(((size_t)n_features + 3) / 4 * 4, NAN);
+  if (impute)
+    for (int c = 0; c < n_features; ++c) {
+      imp[c] = impute[c];
+      if (impute[c] == impute[c]) t->any_impute = 1;
+    }
+  TAB_TRY(cudaMalloc(&t->d_impute, imp.size() * 4));
+  TAB_TRY(cudaMemcpy(t->d_impute, imp.data(), imp.size() * 4, cudaMemcpyHostToDevice));
+  int occ = 0;
+  TAB_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, table_lookup_kernel, 256, 0));
+  t->grid = b2s_int_sm_count() * std::max(occ, 1);
+  for (int i = 0; i < 4; ++i) TAB_TRY(cudaEventCreate(&t->ev[i]));
+  *out = t;
+  return B2S_OK;
+}
+
+static int launch_lookup(b2s_table_t t, const int64_t* d_keys, int64_t n, float* d_rows, int64_t row_stride, int32_t* d_found, cudaStream_t st) {
+  LookupParams p{};
+  p.slots = t->d_slots;
+  p.mask = t->cap - 1;
+  p.values = t->d_values;
+  p.impute = t->d_impute;
+  p.n_feat = t->n_feat;
+  p.any_impute = t->any_impute;
+  p.keys = d_keys;
+  p.n = n;
+  p.out = d_rows;
+  p.out_stride = row_stride;
+  p.found = d_found;
+  const int64_t warps = (n + 31) / 32;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(t->grid, (warps + 7) / 8));
+  b2s_int_count_launches(1);
+  table_lookup_kernel<<<grid, 256, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return b2s_int_fail(B2S_ERR_CUDA, "table lookup launch failed: %s", cudaGetErrorString(e));
+  return B2S_OK;
+}
+
+extern "C" int b2s_table_lookup_device(b2s_table_t t, const int64_t* d_keys, int64_t n, float* d_rows, int64_t row_stride_bytes,
+                                       int32_t* d_found, void* stream) {
+  if (!t) return b2s_int_fail(B2S_ERR_INVALID, "null table");
+  if (n < 0 || row_stride_bytes < (int64_t)t->n_feat * 4 || (row_stride_bytes & 3)) return b2s_int_fail(B2S_ERR_INVALID, "bad n / row stride");
+  if (n == 0) return B2S_OK;
+  TAB_TRY(cudaSetDevice(b2s_int_device()));
+  return launch_lookup(t, d_keys, n, d_rows, row_stride_bytes, d_found, stream ? (cudaStream_t)stream : b2s_int_stream());
+}
+
+extern "C" int b2s_table_lookup_host(b2s_table_t t, const int64_t* keys, int64_t n, float* rows, int32_t* found, b2s_stats* stats) {
+  if (!t || !keys || !rows || n < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+  if (n == 0) return B2S_OK;
+  std::lock_guard<std::mutex> lk(t->mu);
+  TAB_TRY(cudaSetDevice(b2s_int_device()));
+  if (n > t->cap_rows) {
+    if (t->d_keys) { cudaFree(t->d_keys); cudaFree(t->d_out); cudaFree(t->d_found); t->d_keys = nullptr; }
+    t->cap_rows = 0;
+    const int64_t cap = std::max<int64_t>(n, 4096);
+    TAB_TRY(cudaMalloc(&t->d_keys, cap * 8));
+    TAB_TRY(cudaMalloc(&t->d_out, (size_t)cap * t->n_feat * 4));
+    TAB_TRY(cudaMalloc(&t->d_found, cap * 4));
+    t->cap_rows = cap;
+  }
+  cudaStream_t st = b2s_int_stream();
+  const int64_t stride = (int64_t)t->n_feat * 4;
+  TAB_TRY(cudaEventRecord(t->ev[0], st));
+  TAB_TRY(cudaMemcpyAsync(t->d_keys, keys, n * 8, cudaMemcpyHostToDevice, st));
+  TAB_TRY(cudaEventRecord(t->ev[1], st));
+  if (int rc = launch_lookup(t, t->d_keys, n, t->d_out, stride, t->d_found, st)) return rc;
+  TAB_TRY(cudaEventRecord(t->ev[2], st));
+  TAB_TRY(cudaMemcpyAsync(rows, t->d_out, (size_t)n * stride, cudaMemcpyDeviceToHost, st));
+  if (found) TAB_TRY(cudaMemcpyAsync(found, t->d_found, n * 4, cudaMemcpyDeviceToHost, st));
+  TAB_TRY(cudaEventRecord(t->ev[3], st));
+  TAB_TRY(cudaStreamSynchronize(st));
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->rows = n;
+    cudaEventElapsedTime(&stats->h2d_ms, t->ev[0], t->ev[1]);
+    cudaEventElapsedTime(&stats->kernel_ms, t->ev[1], t->ev[2]);
+    cudaEventElapsedTime(&stats->d2h_ms, t->ev[2], t->ev[3]);
+    stats->kernels = 1;
+  }
+  return B2S_OK;
+}
+
+extern "C" int b2s_table_time_device(b2s_table_t t, const int64_t* const* d_keys, int32_t n_bufs, int64_t n, float* d_rows,
+                                     int64_t row_stride_bytes, int32_t* d_found, int32_t n_iters, float* total_ms) {
+  if (!t || !d_keys || n_bufs <= 0 || n_iters <= 0 || !total_ms) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+  TAB_TRY(cudaSetDevice(b2s_int_device()));
+  cudaStream_t st = b2s_int_stream();
+  std::lock_guard<std::mutex> lk(t->mu);
+  TAB_TRY(cudaEventRecord(t->ev[0], st));
+  for (int i = 0; i < n_iters; ++i)
+    if (int rc = launch_lookup(t, d_keys[i % n_bufs], n, d_rows, row_stride_bytes, d_found, st)) return rc;
+  TAB_TRY(cudaEventRecord(t->ev[1], st));
+  TAB_TRY(cudaStreamSynchronize(st));
+  TAB_TRY(cudaEventElapsedTime(total_ms, t->ev[0], t->ev[1]));
+  return B2S_OK;
+}
+
+extern "C" int b2s_table_info(b2s_table_t t, int64_t* n_keys, int32_t* n_features, int64_t* capacity) {
+  if (!t) return b2s_int_fail(B2S_ERR_INVALID, "null table");
+  if (n_keys) *n_keys = t->n_keys;
+  if (n_features) *n_features = t->n_feat;
+  if (capacity) *capacity = (int64_t)t->cap;
+  return B2S_OK;
+}
+
+extern "C" int b2s_table_destroy(b2s_table_t t) {
+  if (!t) return B2S_OK;
+  if (t->d_slots) cudaFree(t->d_slots);
+  if (t->d_values) cudaFree(t->d_values);
+  if (t->d_impute) cudaFree(t->d_impute);
+  if (t->d_keys) cudaFree(t->d_keys);
+  if (t->d_out) cudaFree(t->d_out);
+  if (t->d_found) cudaFree(t->d_found);
+  for (auto& e : t->ev)
+    if (e) cudaEventDestroy(e);
+  delete t;
+  return B2S_OK;
+}
+
+// FNV-1a over each string of a packed buffer: the 64-bit entity key of a string-valued entity (host code)
+extern "C" int b2s_hash_strings(const char* bytes, const int64_t* offsets, int64_t n, int64_t* keys_out) {
+  if (!bytes || !offsets || !keys_out || n < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+  for (int64_t i = 0; i < n; ++i) {
+    uint64_t h = 1469598103934665603ULL;
+    for (int64_t j = offsets[i]; j < offsets[i + 1]; ++j) {
+      h ^= (unsigned char)bytes[j];
+      h *= 1099511628211ULL;
+    }
+    keys_out[i] = (int64_t)h;
+  }
+  return B2S_OK;
+}

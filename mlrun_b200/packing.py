@@ -162,7 +162,9 @@ def pack_model(model):
     if hasattr(model, "coef_"):
         return "linear", pack_linear(model)
     if hasattr(model, "estimators_") or hasattr(model, "tree_"):
-        return "trees", pack_trees(model)
+        packed = pack_trees(model)
+        packed.n_features = int(getattr(model, "n_features_in_", 0)) or None  # the width predict() checks its input against
+        return "trees", packed
     raise UnsupportedModel(f"{type(model).__name__}: only linear and tree-ensemble estimators are lowered")
 
 

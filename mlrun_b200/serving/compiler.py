@@ -152,7 +152,12 @@ def compile_graph(graph, in_names=None, route=None):
 def _n_inputs(transforms, models):
     if transforms:
         raise LoweringError("a graph with feature steps needs the input column names (run_batch(X, names=[...]))")
-    kind, packed = models[0]
-    if kind == "linear":
-        return packed["W"].shape[1]
-    return int(packed.feature.max()) + 1
+    widths = []
+    for kind, packed in models:
+        if kind == "linear":
+            widths.append(packed["W"].shape[1])
+        else:
+            widths.append(getattr(packed, "n_features", None) or int(packed.feature.max()) + 1)
+    if len(set(widths)) != 1:
+        raise LoweringError(f"the router's models take different input widths {sorted(set(widths))}")
+    return widths[0]

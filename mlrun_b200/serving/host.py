@@ -276,6 +276,39 @@ class GraphServer(Serde):
         return compiled.responses(out, status, self.context)
 
 
+    def run_enriched(self, keys, with_status=False):
+        """batched enrichment + predict for a graph whose root is an Enrichment router: entity keys -> outputs with the
+        online-table gather (`b2s_table_lookup_device`) feeding the fused scoring plan (`b2s_run_device`) on the device --
+        two launches, no host round trip (replaces EnrichmentVotingEnsemble.preprocess + the per-model predicts,
+        serving/routers.py:1335-1342).  Unknown keys come back with status bit 4."""
+        from .. import _native as nat
+        from ..lowering import LoweringError
+
+        compiled = self.compile()
+        router = getattr(self.graph, "_object", None) if self.graph.kind == "router" else None
+        svc = getattr(router, "_feature_service", None)
+        if svc is None or not hasattr(svc, "table"):
+            raise LoweringError("run_enriched needs an EnrichmentModelRouter / EnrichmentVotingEnsemble at the root")
+        plan = compiled.plan
+        if plan.n_in != svc.table.n_feat:
+            raise LoweringError(f"the feature vector has {svc.table.n_feat} features, the models take {plan.n_in}")
+        k = np.ascontiguousarray(svc._encode_keys(keys), dtype=np.int64)
+        n = len(k)
+        d_keys = nat.DeviceBuffer(max(n, 1) * 8).upload(k)
+        d_rows = nat.DeviceBuffer(max(n, 1) * plan.n_in * 4)
+        d_found = nat.DeviceBuffer(max(n, 1) * 4)
+        d_out = nat.DeviceBuffer(max(n, 1) * plan.out_cols * 4)
+        d_status = nat.DeviceBuffer(max(n, 1) * 4)
+        svc.table.lookup_device(d_keys.ptr, n, d_rows.ptr, plan.n_in * 4, d_found.ptr)
+        plan.run_device(d_rows.ptr, n, plan.n_in * 4, d_out.ptr, d_status.ptr)
+        nat.load().b2s_device_sync()
+        out = d_out.download(plan.out_dtype, (n, plan.out_cols))
+        if not with_status:
+            return out
+        status = d_status.download(np.int32, (n,))
+        found = d_found.download(np.int32, (n,))
+        return out, status | np.where(found == 0, 4, 0).astype(np.int32)
+
     def run_json(self, body, event_id=None):
         """wire-level batched entry for graphs whose root is a router / model server: a V2 body
         `{"inputs": [[...], ...]}` (bytes / str) -> the Response GraphServer.run would answer for it (serving/server.py:

@@ -366,3 +366,43 @@ class VotingEnsemble(ParallelRun):
             self._model_logger.push(start, request, response.body)
         event.body = merge_result(self._result_path, original, response.body if response else None)
         return event
+
+
+class _EnrichmentMixin:
+    """EnrichmentModelRouter / EnrichmentVotingEnsemble (routers.py:1118-1196, 1199-1342): entity keys in, feature
+    vectors to the child models; the online read is one device launch (mlrun_b200.feature_store.online)"""
+
+    def _init_enrichment(self, feature_vector_uri, impute_policy):
+        self.feature_vector_uri = feature_vector_uri
+        self.impute_policy = impute_policy or {}
+        self._feature_service = None
+
+    def post_init(self, mode="sync"):
+        from ..feature_store.online import get_feature_vector
+
+        super().post_init(mode)
+        self._feature_service = get_feature_vector(self.feature_vector_uri).get_online_feature_service(
+            impute_policy=self.impute_policy)
+
+    def preprocess(self, event):
+        if isinstance(event.body, (str, bytes)):
+            event.body = json.loads(event.body)
+        event.body["inputs"] = self._feature_service.get(event.body["inputs"], as_list=True)
+        return event
+
+
+class EnrichmentModelRouter(_EnrichmentMixin, ModelRouter):
+    def __init__(self, context=None, name=None, routes=None, protocol=None, url_prefix=None, health_prefix=None,
+                 feature_vector_uri="", impute_policy=None, **kwargs):
+        super().__init__(context, name, routes, protocol, url_prefix, health_prefix, **kwargs)
+        self._init_enrichment(feature_vector_uri, impute_policy)
+
+
+class EnrichmentVotingEnsemble(_EnrichmentMixin, VotingEnsemble):
+    def __init__(self, context=None, name=None, routes=None, protocol=None, url_prefix=None, health_prefix=None,
+                 vote_type=None, executor_type=ParallelRunnerModes.thread, prediction_col_name=None, feature_vector_uri="",
+                 impute_policy=None, **kwargs):
+        super().__init__(context=context, name=name, routes=routes, protocol=protocol, url_prefix=url_prefix,
+                         health_prefix=health_prefix, vote_type=vote_type, executor_type=executor_type,
+                         prediction_col_name=prediction_col_name, **kwargs)
+        self._init_enrichment(feature_vector_uri, impute_policy)

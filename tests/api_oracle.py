@@ -25,6 +25,12 @@ DateExtractor = transforms.DateExtractor
 SetEventMetadata = transforms.SetEventMetadata
 SKLearnModelServer = model_servers.SKLearnModelServer
 NAME = "oracle"
+from oracle import enrichment as _enrichment  # noqa: E402
+
+EnrichmentModelRouter = _enrichment.EnrichmentModelRouter
+EnrichmentVotingEnsemble = _enrichment.EnrichmentVotingEnsemble
+register_feature_vector = _enrichment.register_feature_vector
+get_feature_vector = _enrichment.get_feature_vector
 
 
 class FeatureRowVotingEnsemble(VotingEnsemble):

@@ -1,0 +1,131 @@
+"""Real-time feature enrichment on the device (b2s_table_* + the Enrichment routers) vs the oracle.  Needs a B200."""
+
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from mlrun_b200 import _native as nat  # noqa: E402
+from mlrun_b200.feature_store import online as bo  # noqa: E402
+from oracle import enrichment as oe  # noqa: E402
+from tests import api_b200, api_oracle  # noqa: E402
+
+RTOL, ATOL = 1e-5, 1e-5
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    nat.init(0)
+    yield
+
+
+def _vectors(n_keys=500, n_feat=12, seed=1, key_kind="str", label=None):
+    """the same online rows as a product FeatureVector (frame) and an oracle FeatureVector (dict table)"""
+    rng = np.random.default_rng(seed)
+    feat = [f"f{i}" for i in range(n_feat)]
+    vals = rng.normal(size=(n_keys, n_feat)).astype(np.float32)
+    vals[rng.random(vals.shape) < 0.08] = np.nan
+    vals[rng.random(vals.shape) < 0.02] = np.inf
+    vals[rng.random(vals.shape) < 0.01] = -np.inf
+    vals[5] = 0.0
+    vals[6] = np.nan
+    if key_kind == "str":
+        keys = [f"ent-{i * 7919 % 100003}" for i in range(n_keys)]
+    elif key_kind == "int":
+        keys = [int(k) for k in rng.choice(10**12, size=n_keys, replace=False) - 5 * 10**11]
+    else:
+        keys = [(f"u{i % 37}", i) for i in range(n_keys)]
+    index_keys = ["ticker"] if key_kind != "tuple" else ["user", "seq"]
+    if key_kind == "tuple":
+        frame = pd.DataFrame(vals, columns=feat, index=pd.MultiIndex.from_tuples(keys, names=index_keys))
+    else:
+        frame = pd.DataFrame(vals, columns=feat, index=pd.Index(keys, name="ticker"))
+    bvec = bo.FeatureVector("vec", feat, index_keys, frame, label_column=label)
+    stats = bvec.get_stats_table()
+    table = {(k if isinstance(k, tuple) else (k,)): {feat[j]: float(vals[i, j]) for j in range(n_feat)} for i, k in enumerate(keys)}
+    ovec = oe.FeatureVector("vec", feat, index_keys, table, stats, label_column=label)
+    return bvec, ovec, keys, vals, feat
+
+
+def _same_rows(got, want):
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        if w is None or g is None:
+            assert g is None and w is None
+            continue
+        if isinstance(w, dict):
+            assert list(g) == list(w)
+            g, w = list(g.values()), list(w.values())
+        np.testing.assert_array_equal(np.array(g, dtype=np.float64), np.array(w, dtype=np.float64))
+
+
+@pytest.mark.parametrize("key_kind", ["str", "int", "tuple"])
+@pytest.mark.parametrize("policy", [None, {"*": "$mean"}, {"*": 0.5, "f1": "$max", "f2": -3}, {"f3": "$min"}])
+def test_online_service_get_matches_the_reference_semantics(key_kind, policy):
+    bvec, ovec, keys, vals, feat = _vectors(key_kind=key_kind)
+    bsvc = bvec.get_online_feature_service(impute_policy=policy)
+    osvc = ovec.get_online_feature_service(impute_policy=policy)
+    unknown = "nope" if key_kind == "str" else (123 if key_kind == "int" else ("zz", 1))
+    ask = keys[:40] + [unknown] + keys[100:110]
+    rows = [list(k) if isinstance(k, tuple) else [k] for k in ask]
+    _same_rows(bsvc.get(rows, as_list=True), osvc.get(rows, as_list=True))
+    dict_rows = [dict(zip(bvec.index_keys, r)) for r in rows[:8]]
+    _same_rows(bsvc.get(dict_rows), osvc.get(dict_rows))
+    with pytest.raises(ValueError, match="must be a list of lists or list of dicts"):
+        bsvc.get("GOOG")
+    with pytest.raises(ValueError, match="same size of the index_keys"):
+        bsvc.get([[1, 2, 3]])
+    bsvc.close()
+
+
+def test_impute_policy_errors_and_matrix_lookup():
+    bvec, ovec, keys, vals, feat = _vectors(n_keys=2000, n_feat=16, seed=3)
+    with pytest.raises(ValueError, match="in impute_policy but not in feature vector"):
+        bvec.get_online_feature_service(impute_policy={"nope": 1})
+    svc = bvec.get_online_feature_service(impute_policy={"*": "$mean"})
+    X, found = svc.get_matrix(keys[::-1] + ["ghost"])
+    assert found[:-1].all() and not found[-1]
+    stats = bvec.get_stats_table()
+    want = vals[::-1].copy()
+    mean = stats["mean"].to_numpy(dtype=np.float32)
+    bad = ~np.isfinite(want)
+    want[bad] = np.broadcast_to(mean, want.shape)[bad]
+    np.testing.assert_array_equal(X[:-1], want)
+    np.testing.assert_array_equal(X[-1], mean)  # unknown key: all-NaN row, imputed
+    with pytest.raises(ValueError, match="share a 64-bit hash|duplicated"):
+        dup = pd.DataFrame(vals[:2], columns=feat, index=pd.Index(["a", "a"], name="ticker"))
+        bo.FeatureVector("d", feat, ["ticker"], dup).get_online_feature_service()
+
+
+def _enriched_server(api, vec, policy, n_models, coefs):
+    from sklearn.linear_model import LinearRegression
+
+    api.register_feature_vector("store://vec", vec)
+    fn = api.new_function("enrich", kind="serving")
+    graph = fn.set_topology("router", api.EnrichmentVotingEnsemble(feature_vector_uri="store://vec", impute_policy=policy,
+                                                                    vote_type="regression", executor_type="array"))
+    for i in range(n_models):
+        m = LinearRegression()
+        m.coef_, m.intercept_, m.n_features_in_ = np.asarray(coefs[i], dtype=np.float64), 0.25 * i, len(coefs[i])
+        graph.add_route(f"m{i}", class_name="SKLearnModelServer", model=m, model_path="")
+    return fn.to_mock_server(namespace={"SKLearnModelServer": api.SKLearnModelServer})
+
+
+def test_enrichment_router_per_event_and_fused_batch():
+    bvec, ovec, keys, vals, feat = _vectors(n_keys=3000, n_feat=16, seed=4)
+    coefs = np.random.default_rng(5).normal(size=(4, 16))
+    policy = {"*": "$mean"}
+    bserver = _enriched_server(api_b200, bvec, policy, 4, coefs)
+    oserver = _enriched_server(api_oracle, ovec, policy, 4, coefs)
+    ask = [[k] for k in keys[10:42] if k not in (keys[5],)]
+    got = bserver.test("/v2/models/infer", body={"inputs": ask})
+    want = oserver.test("/v2/models/infer", body={"inputs": ask})
+    np.testing.assert_allclose(got["outputs"], want["outputs"], rtol=RTOL, atol=ATOL)
+    assert got["model_name"] == want["model_name"]
+    # batched engine path: keys -> gather kernel -> fused scoring plan, nothing returns to the host in between
+    out, status = bserver.run_enriched(keys + ["ghost"], with_status=True)
+    ref = oserver.test("/v2/models/infer", body={"inputs": [[k] for k in keys if k != keys[5]]})["outputs"]
+    mask = np.array([k != keys[5] for k in keys])
+    np.testing.assert_allclose(out[:-1, 0][mask], ref, rtol=RTOL, atol=ATOL)
+    assert (status[:-1] == 0).all() and status[-1] == 4
