@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-BYTES_PER_EVENT = {"flow3_ens4": 260, "flow3_linear": 260, "trees_ens4": 516, "ingest6": 2280}
+BYTES_PER_EVENT = {"flow3_ens4": 260, "flow3_linear": 260, "trees_ens4": 516, "ingest6": 2280, "enrich_ens4": 536}
 
 
 def parse():
@@ -87,6 +87,8 @@ def _cpu_worker(args):
         pass
     from tests import api_oracle
 
+    if name == "enrich_ens4":
+        return _enrich_cpu_worker((n_events, seed))
     if name == "ingest6":
         import contextlib
         import io
@@ -136,7 +138,7 @@ def cpu_baseline(name, seconds, procs=None):
 
     procs = procs or usable_cores()
     # calibrate on one process, then size the sample to the time budget
-    n_cal = 300 if name.startswith("flow3") else (200 if name == "ingest6" else 40)
+    n_cal = 300 if name.startswith("flow3") else (200 if name in ("ingest6", "enrich_ens4") else 40)
     n, dt = _cpu_worker((name, n_cal, 2))
     rate1 = n / dt
     # with P busy processes each one runs slower than alone (shared caches / SMT): budget for ~2x
@@ -281,6 +283,8 @@ def workload_desc(name):
         "flow3_ens4": "3-step flow Imputer->OneHotEncoder->VotingEnsemble(4 linear models), 64-feat f32 (56 num + 8 cat x4 -> 88)",
         "flow3_linear": "3-step flow Imputer->OneHotEncoder->linear predict, 64-feat f32 (BASELINE configs[1])",
         "trees_ens4": "VotingEnsemble of 4 GradientBoostingRegressor(100 trees, depth 6), 128-feat f32 (BASELINE configs[2])",
+        "enrich_ens4": "real-time enrichment: entity keys -> online feature table (4 Mi keys x 64 f32, 1 GiB in HBM) -> $mean imputing "
+                       "-> VotingEnsemble(4 linear models) (EnrichmentVotingEnsemble, SURVEY 8(f) #3)",
         "ingest6": "feature-set ingest, 256 four-byte slots/row (192 f32 + 62 int32 + datetime64): Imputer -> MapValues(ranges, 16 cols) "
                    "-> OneHotEncoder(8 cols x 8) -> DateExtractor(hour, day_of_week) -> DropFeatures(16) -> FeaturesetValidator(8 cols) "
                    "(BASELINE configs[4])",
@@ -300,6 +304,8 @@ def main():
     name = args.workload
     if name == "ingest6":
         return main_ingest(args, rank, local_rank, world)
+    if name == "enrich_ens4":
+        return main_enrich(args, rank, local_rank, world)
     B = args.batch or (262144 if name == "trees_ens4" else 1048576)
 
     cpu = None
@@ -620,6 +626,171 @@ def main_ingest(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(name, B), "kernel": "columns_kernel", "algorithmic_bytes_per_event": bpe,
                          "kernel_ms_per_launch": kms, "peak_source": peak_src},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _enrich_setup(api, n_keys, n_feat, seed):
+    """the same enrichment graph on either API (product / oracle)"""
+    import pandas as pd
+    from sklearn.linear_model import LinearRegression
+
+    rng = np.random.default_rng(seed)
+    feat = [f"f{i}" for i in range(n_feat)]
+    vals = rng.normal(size=(n_keys, n_feat)).astype(np.float32)
+    vals[rng.random(vals.shape) < 0.05] = np.nan
+    keys = rng.permutation(n_keys).astype(np.int64) * 7919 + 13
+    coefs = np.random.default_rng(seed + 1).normal(size=(4, n_feat))
+    return feat, vals, keys, coefs, pd, LinearRegression
+
+
+def _enrich_cpu_worker(args):
+    n_events, seed = args
+    import logging
+
+    logging.disable(logging.CRITICAL)
+    from oracle import enrichment as oenr
+    from tests import api_oracle
+
+    n_keys, n_feat = 20000, 64
+    feat, vals, keys, coefs, pd, LinearRegression = _enrich_setup(api_oracle, n_keys, n_feat, seed)
+    table = {(int(k),): dict(zip(feat, map(float, v))) for k, v in zip(keys, vals)}
+    stats = pd.DataFrame({"mean": np.nanmean(vals, axis=0).astype(np.float64)}, index=feat)
+    oenr.register_feature_vector("store://bench", oenr.FeatureVector("bench", feat, ["id"], table, stats))
+    fn = api_oracle.new_function("enrich", kind="serving")
+    graph = fn.set_topology("router", api_oracle.EnrichmentVotingEnsemble(feature_vector_uri="store://bench", impute_policy={"*": "$mean"},
+                                                                          vote_type="regression", executor_type="array"))
+    for i in range(4):
+        m = LinearRegression()
+        m.coef_, m.intercept_, m.n_features_in_ = coefs[i], 0.0, n_feat
+        graph.add_route(f"m{i}", class_name="SKLearnModelServer", model=m, model_path="")
+    server = fn.to_mock_server(namespace={"SKLearnModelServer": api_oracle.SKLearnModelServer})
+    ask = [int(k) for k in keys[np.random.default_rng(seed + 2).integers(0, n_keys, size=n_events)]]
+    t0 = time.perf_counter()
+    for k in ask:  # one event per entity, as a real-time caller sends them
+        server.test("/v2/models/infer", body={"inputs": [[k]]})
+    return n_events, time.perf_counter() - t0
+
+
+def main_enrich(args, rank, local_rank, world):
+    """SURVEY 8(f) #3: keys -> device hash table gather (+ imputing) -> fused scoring plan; two launches per step"""
+    name = "enrich_ens4"
+    B = args.batch or 1048576
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(name, args.cpu_seconds)
+
+    import torch
+
+    from mlrun_b200 import _native as nat
+    from mlrun_b200 import api
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    nat.init(local_rank)
+    info = nat.device_info()
+    n_keys, n_feat = 4 * 1048576, 64
+    feat, vals, keys, coefs, pd, LinearRegression = _enrich_setup(api, n_keys, n_feat, 2)
+    frame = pd.DataFrame(vals, columns=feat, index=pd.Index(keys, name="id"), copy=False)
+    api.register_feature_vector("store://bench", api.FeatureVector("bench", feat, ["id"], frame))
+    fn = api.new_function("enrich", kind="serving")
+    graph = fn.set_topology("router", api.EnrichmentVotingEnsemble(feature_vector_uri="store://bench", impute_policy={"*": "$mean"},
+                                                                   vote_type="regression", executor_type="array"))
+    for i in range(4):
+        m = LinearRegression()
+        m.coef_, m.intercept_, m.n_features_in_ = coefs[i], 0.0, n_feat
+        graph.add_route(f"m{i}", class_name="SKLearnModelServer", model=m, model_path="")
+    server = fn.to_mock_server(namespace={"SKLearnModelServer": api.SKLearnModelServer})
+    plan = server.compile().plan
+    table = server.graph._object._feature_service.table
+    rng = np.random.default_rng(3 + rank)
+    nbuf = 3
+    d_keys = [torch.from_numpy(keys[rng.integers(0, n_keys, size=B)]).cuda() for _ in range(nbuf)]
+    rows = torch.empty(B * n_feat, dtype=torch.float32, device="cuda")
+    out = torch.empty(B * plan.out_cols, dtype=torch.float32, device="cuda")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+
+    def step(i):
+        table.lookup_device(d_keys[i % nbuf].data_ptr(), B, rows.data_ptr(), n_feat * 4, None, stream.cuda_stream)
+        plan.run_device(rows.data_ptr(), B, n_feat * 4, out.data_ptr(), None, stream.cuda_stream)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sync()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    time.sleep(0.25)
+    l0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    sync()
+    t_wall1 = time.perf_counter()
+    launches = nat.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    n_it = max(args.steps, 10)
+    kms = table.time_device([k.data_ptr() for k in d_keys], B, rows.data_ptr(), n_feat * 4, n_it) / n_it
+    lat = []
+    for _ in range(20):
+        table.time_device([d_keys[0].data_ptr()], 4096, rows.data_ptr(), n_feat * 4, 1)
+    for _ in range(300):
+        lat.append(table.time_device([d_keys[0].data_ptr()], 4096, rows.data_ptr(), n_feat * 4, 1) * 1e3)
+    e2e = None
+    if not args.no_e2e:
+        Be = 262144
+        hk = [keys[rng.integers(0, n_keys, size=Be)] for _ in range(2)]
+        for j in range(2):
+            server.run_enriched(hk[j % 2])
+        n_e2e = max(5, min(args.steps, 20))
+        t0 = time.perf_counter()
+        for j in range(n_e2e):
+            res = server.run_enriched(hk[j % 2], with_status=True)
+        dt = time.perf_counter() - t0
+        e2e = {"value": world * Be * n_e2e / dt, "unit": "events/s", "h2d_bytes_per_step": Be * 8, "d2h_bytes_per_step": Be * 12,
+               "batch": Be, "steps": n_e2e, "api": "GraphServer.run_enriched(keys) (public API): host int64 keys -> H2D -> gather kernel -> "
+               "fused scoring plan -> D2H votes + status + found"}
+        del res
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bpe = BYTES_PER_EVENT[name]
+        achieved = bpe * B / (kms * 1e-3) / 1e9
+        line = {
+            "metric": "events/sec", "value": world * B * args.steps / (ms * 1e-3), "unit": "events/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 rows / int64 keys, f64 accumulate", "data": "synthetic",
+            "config": {"workload": workload_desc(name), "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"event-sharded x{world} (table replicated), no exchange",
+                       "l2": "uniformly random keys over a 1 GiB table + 256 MiB of slots (> 126 MB L2)", "device": info["name"],
+                       "kernel": f"table_lookup_kernel + {plan.kernel}"},
+            "p50_step_latency_us": {"batch": 4096, "p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                                    "how": "CUDA events around one table_lookup_kernel launch, 300 samples"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": measured_traffic(name, B), "kernel": "table_lookup_kernel",
+                         "algorithmic_bytes_per_event": bpe, "kernel_ms_per_launch": kms, "peak_source": peak_src},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if e2e:
