@@ -61,9 +61,15 @@ struct ColParams {
   unsigned long long* counters;
 };
 
-constexpr int kColThreads = 256;
+#ifndef B2S_COL_THREADS
+#define B2S_COL_THREADS 256
+#endif
+#ifndef B2S_COL_UNROLL
+#define B2S_COL_UNROLL 4
+#endif
+constexpr int kColThreads = B2S_COL_THREADS;
 constexpr int kColVec = 4;                                  // rows per 16-byte access
-constexpr int kColUnroll = 4;                               // independent 16-byte loads in flight per thread
+constexpr int kColUnroll = B2S_COL_UNROLL;                  // independent 16-byte loads in flight per thread
 constexpr int kColChunk = kColThreads * kColUnroll * kColVec;  // rows per work item (4096)
 
 __device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b) {
@@ -87,7 +93,7 @@ __device__ __forceinline__ void civil_from_days(int64_t z, int& y, int& m, int& 
   doy = cum[m - 1] + d + ((leap && m > 2) ? 1 : 0);
 }
 
-__device__ __forceinline__ int32_t date_part(int64_t ns, int part) {
+__device__ __noinline__ int32_t date_part(int64_t ns, int part) {
   const int64_t secs = floor_div(ns, 1000000000LL);
   const int64_t days = floor_div(secs, 86400);
   const int sod = (int)(secs - days * 86400);
@@ -150,6 +156,167 @@ __device__ __forceinline__ unsigned int col_check(const ColOp& op, double x) {
   return (lo_bad || hi_bad) ? 1u : 0u;
 }
 
+// ---- per-kind item bodies.  They are separate (non-inlined) functions so that the instruction footprint a CTA touches
+// is the body of the op it is working on (plain copies and imputed floats are ~85 % of a typical plan), not the union.
+
+// CK_COPY32 without a check: a 16-byte stream copy
+__device__ __noinline__ void item_copy32(const uint32_t* __restrict__ s, uint32_t* __restrict__ d, int rows, int quads, int tid) {
+  for (int base = tid; base < quads; base += kColThreads * kColUnroll) {
+    uint4 w[kColUnroll];
+#pragma unroll
+    for (int u = 0; u < kColUnroll; ++u) {
+      const int i = base + u * kColThreads;
+      w[u] = i < quads ? reinterpret_cast<const uint4*>(s)[i] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < kColUnroll; ++u) {
+      const int i = base + u * kColThreads;
+      if (i < quads) reinterpret_cast<uint4*>(d)[i] = w[u];
+    }
+  }
+  for (int i = quads * kColVec + tid; i < rows; i += kColThreads) d[i] = s[i];
+}
+
+// CK_F32 / checked CK_COPY32 / CK_CHECK: Imputer fill + MinMaxValidator count, no tables
+__device__ __noinline__ unsigned int item_plain(const ColOp& op, const uint32_t* __restrict__ s, uint32_t* __restrict__ d, int rows,
+                                                int quads, int tid) {
+  unsigned int bad = 0;
+  auto one = [&](uint32_t bits) {
+    double x;
+    if (op.src_int) {
+      x = (double)(int32_t)bits;
+    } else {
+      float f = __uint_as_float(bits);
+      if (op.has_fill && f != f) f = op.fill;  // Imputer._impute (steps.py:397-406)
+      bits = __float_as_uint(f);
+      x = (double)f;
+    }
+    if (op.check) bad += col_check(op, x);
+    return bits;
+  };
+  for (int base = tid; base < quads; base += kColThreads * kColUnroll) {
+    uint4 w[kColUnroll];
+#pragma unroll
+    for (int u = 0; u < kColUnroll; ++u) {
+      const int i = base + u * kColThreads;
+      w[u] = i < quads ? reinterpret_cast<const uint4*>(s)[i] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < kColUnroll; ++u) {
+      const int i = base + u * kColThreads;
+      if (i >= quads) continue;
+      uint4 o;
+      o.x = one(w[u].x);
+      o.y = one(w[u].y);
+      o.z = one(w[u].z);
+      o.w = one(w[u].w);
+      if (d) reinterpret_cast<uint4*>(d)[i] = o;
+    }
+  }
+  for (int i = quads * kColVec + tid; i < rows; i += kColThreads) {
+    const uint32_t o = one(s[i]);
+    if (d) d[i] = o;
+  }
+  return bad;
+}
+
+// CK_RANGE / CK_VALUE / CK_ONEHOT: table ops (rare: kept compact, one element at a time inside a 16-byte access)
+__device__ __noinline__ void item_table(const ColOp& op, const double* __restrict__ tab, const uint32_t* __restrict__ s, char* dst,
+                                        int64_t out_stride, int64_t row0, int rows, int quads, int tid, unsigned int& bad,
+                                        unsigned int& miss) {
+  auto one = [&](uint32_t bits, int64_t row, uint32_t* oh /* n outputs for one-hot, else 1 */) {
+    double x;
+    bool hit;
+    const uint32_t o = col_word(op, tab, bits, x, hit);
+    miss += hit ? 0u : 1u;
+    if (op.check) bad += col_check(op, x);
+    (void)row;
+    (void)oh;
+    return o;
+  };
+  if (op.kind == CK_ONEHOT) {  // OneHotEncoder._encode (steps.py:453-470): unknown -> all zeros
+    for (int i = tid; i < quads; i += kColThreads) {
+      const uint4 w = reinterpret_cast<const uint4*>(s)[i];
+      double x[4];
+      bool hit;
+      col_word(op, tab, w.x, x[0], hit);
+      col_word(op, tab, w.y, x[1], hit);
+      col_word(op, tab, w.z, x[2], hit);
+      col_word(op, tab, w.w, x[3], hit);
+      int any0 = 0, any1 = 0, any2 = 0, any3 = 0;
+      for (int q = 0; q < op.n; ++q) {
+        const double c = tab[q];
+        int4 oh;
+        oh.x = x[0] == c;
+        oh.y = x[1] == c;
+        oh.z = x[2] == c;
+        oh.w = x[3] == c;
+        any0 |= oh.x;
+        any1 |= oh.y;
+        any2 |= oh.z;
+        any3 |= oh.w;
+        reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(dst + (int64_t)q * out_stride) + row0)[i] = oh;
+      }
+      miss += 4u - (unsigned)(any0 + any1 + any2 + any3);
+    }
+    for (int i = quads * kColVec + tid; i < rows; i += kColThreads) {
+      double x;
+      bool hit;
+      col_word(op, tab, s[i], x, hit);
+      bool any = false;
+      for (int q = 0; q < op.n; ++q) {
+        const bool is = x == tab[q];
+        any |= is;
+        reinterpret_cast<int32_t*>(dst + (int64_t)q * out_stride)[row0 + i] = is ? 1 : 0;
+      }
+      miss += any ? 0u : 1u;
+    }
+    return;
+  }
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst) + row0;
+  for (int i = tid; i < quads; i += kColThreads) {
+    const uint4 w = reinterpret_cast<const uint4*>(s)[i];
+    uint4 o;
+    o.x = one(w.x, 0, nullptr);
+    o.y = one(w.y, 0, nullptr);
+    o.z = one(w.z, 0, nullptr);
+    o.w = one(w.w, 0, nullptr);
+    reinterpret_cast<uint4*>(d)[i] = o;
+  }
+  for (int i = quads * kColVec + tid; i < rows; i += kColThreads) d[i] = one(s[i], 0, nullptr);
+}
+
+// CK_COPY64 / CK_DATE: 8-byte sources, two rows per 16-byte load
+__device__ __noinline__ unsigned int item_wide(const ColOp& op, const int64_t* __restrict__ s, char* dst, int64_t row0, int rows,
+                                               bool vec_ok, int tid) {
+  unsigned int miss = 0;
+  const int pairs = vec_ok ? rows / 2 : 0;
+  for (int i = tid; i < pairs; i += kColThreads) {
+    const longlong2 v = reinterpret_cast<const longlong2*>(s)[i];
+    if (op.kind == CK_COPY64) {
+      reinterpret_cast<longlong2*>(reinterpret_cast<int64_t*>(dst) + row0)[i] = v;
+    } else {
+      const bool n0 = v.x == INT64_MIN, n1 = v.y == INT64_MIN;  // NaT
+      miss += (n0 ? 1u : 0u) + (n1 ? 1u : 0u);
+      int2 o;
+      o.x = n0 ? -1 : date_part(v.x, op.part);
+      o.y = n1 ? -1 : date_part(v.y, op.part);
+      reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(dst) + row0)[i] = o;
+    }
+  }
+  for (int i = pairs * 2 + tid; i < rows; i += kColThreads) {  // tail / unaligned
+    const int64_t v = s[i];
+    if (op.kind == CK_COPY64) {
+      reinterpret_cast<int64_t*>(dst)[row0 + i] = v;
+    } else {
+      const bool nat = v == INT64_MIN;
+      miss += nat ? 1u : 0u;
+      reinterpret_cast<int32_t*>(dst)[row0 + i] = nat ? -1 : date_part(v, op.part);
+    }
+  }
+  return miss;
+}
+
 __global__ void __launch_bounds__(kColThreads) columns_kernel(const __grid_constant__ ColParams p) {
   __shared__ unsigned int s_cnt[2];
   const int tid = threadIdx.x;
@@ -158,122 +325,48 @@ __global__ void __launch_bounds__(kColThreads) columns_kernel(const __grid_const
   // 16-byte accesses need 16-byte aligned slots (the strides the host path uses are multiples of 256)
   const bool vec_ok = ((p.in_stride | p.out_stride) & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.in) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+#ifdef B2S_COL_CHUNK_MAJOR
     const int64_t chunk = item / p.n_ops;
     const ColOp op = p.ops[item - chunk * p.n_ops];
+#else
+    // column-major item order: neighbouring CTAs stream neighbouring chunks of the SAME column, so the GPU works on a
+    // handful of long sequential streams at a time (DRAM row locality) instead of one short stream per CTA
+    const int64_t opi = item / n_chunks;
+    const int64_t chunk = item - opi * n_chunks;
+    const ColOp op = p.ops[opi];
+#endif
     const int64_t row0 = chunk * kColChunk;
     const int rows = (int)((p.n_rows - row0 < kColChunk) ? (p.n_rows - row0) : kColChunk);
     const char* src = p.in + (int64_t)op.src * p.in_stride;
     char* dst = op.dst >= 0 ? p.out + (int64_t)op.dst * p.out_stride : nullptr;
-    const double* tab = p.tab + op.tab;
     unsigned int bad = 0, miss = 0;
     const bool counts = op.check || op.miss >= 0;
     if (counts) {
       if (tid < 2) s_cnt[tid] = 0;
       __syncthreads();
     }
-
-    if (op.kind == CK_COPY64 || op.kind == CK_DATE) {
-      // 8-byte sources: two rows per 16-byte load
-      const int64_t* s = reinterpret_cast<const int64_t*>(src) + row0;
-      const int pairs = vec_ok ? rows / 2 : 0;
-      for (int base = tid; base < pairs; base += kColThreads * kColUnroll) {
-        longlong2 v[kColUnroll];
-#pragma unroll
-        for (int u = 0; u < kColUnroll; ++u) {
-          const int i = base + u * kColThreads;
-          v[u] = i < pairs ? reinterpret_cast<const longlong2*>(s)[i] : make_longlong2(0, 0);
+    const int quads = vec_ok ? rows / kColVec : 0;
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src) + row0;
+    uint32_t* d32 = dst ? reinterpret_cast<uint32_t*>(dst) + row0 : nullptr;
+    switch (op.kind) {
+      case CK_COPY64:
+      case CK_DATE:
+        miss = item_wide(op, reinterpret_cast<const int64_t*>(src) + row0, dst, row0, rows, vec_ok, tid);
+        break;
+      case CK_RANGE:
+      case CK_VALUE:
+      case CK_ONEHOT:
+        item_table(op, p.tab + op.tab, s32, dst, p.out_stride, row0, rows, quads, tid, bad, miss);
+        break;
+      case CK_COPY32:
+        if (!op.check) {
+          item_copy32(s32, d32, rows, quads, tid);
+          break;
         }
-#pragma unroll
-        for (int u = 0; u < kColUnroll; ++u) {
-          const int i = base + u * kColThreads;
-          if (i >= pairs) continue;
-          if (op.kind == CK_COPY64) {
-            reinterpret_cast<longlong2*>(reinterpret_cast<int64_t*>(dst) + row0)[i] = v[u];
-          } else {
-            const bool n0 = v[u].x == INT64_MIN, n1 = v[u].y == INT64_MIN;  // NaT
-            miss += (n0 ? 1u : 0u) + (n1 ? 1u : 0u);
-            int2 o;
-            o.x = n0 ? -1 : date_part(v[u].x, op.part);
-            o.y = n1 ? -1 : date_part(v[u].y, op.part);
-            reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(dst) + row0)[i] = o;
-          }
-        }
-      }
-      for (int i = pairs * 2 + tid; i < rows; i += kColThreads) {  // tail / unaligned
-        const int64_t v = s[i];
-        if (op.kind == CK_COPY64) {
-          reinterpret_cast<int64_t*>(dst)[row0 + i] = v;
-        } else {
-          const bool nat = v == INT64_MIN;
-          miss += nat ? 1u : 0u;
-          reinterpret_cast<int32_t*>(dst)[row0 + i] = nat ? -1 : date_part(v, op.part);
-        }
-      }
-    } else {
-      const uint32_t* s = reinterpret_cast<const uint32_t*>(src) + row0;
-      const int quads = vec_ok ? rows / kColVec : 0;
-      for (int base = tid; base < quads; base += kColThreads * kColUnroll) {
-        uint4 w[kColUnroll];
-#pragma unroll
-        for (int u = 0; u < kColUnroll; ++u) {
-          const int i = base + u * kColThreads;
-          w[u] = i < quads ? reinterpret_cast<const uint4*>(s)[i] : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < kColUnroll; ++u) {
-          const int i = base + u * kColThreads;
-          if (i >= quads) continue;
-          if (op.kind == CK_COPY32 && !op.check) {
-            reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(dst) + row0)[i] = w[u];
-            continue;
-          }
-          uint32_t in[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
-          double x[4];
-          uint32_t o[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            bool hit;
-            o[k] = col_word(op, tab, in[k], x[k], hit);
-            miss += hit ? 0u : 1u;
-            if (op.check) bad += col_check(op, x[k]);
-          }
-          if (op.kind == CK_ONEHOT) {  // OneHotEncoder._encode (steps.py:453-470): unknown -> all zeros
-            bool any[4] = {false, false, false, false};
-            for (int q = 0; q < op.n; ++q) {
-              const double c = tab[q];
-              int4 oh;
-              oh.x = x[0] == c; oh.y = x[1] == c; oh.z = x[2] == c; oh.w = x[3] == c;
-              any[0] |= oh.x; any[1] |= oh.y; any[2] |= oh.z; any[3] |= oh.w;
-              reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(dst + (int64_t)q * p.out_stride) + row0)[i] = oh;
-            }
-            miss += (any[0] ? 0u : 1u) + (any[1] ? 0u : 1u) + (any[2] ? 0u : 1u) + (any[3] ? 0u : 1u);
-          } else if (op.kind != CK_CHECK) {
-            reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(dst) + row0)[i] = make_uint4(o[0], o[1], o[2], o[3]);
-          }
-        }
-      }
-      for (int i = quads * kColVec + tid; i < rows; i += kColThreads) {  // tail / unaligned
-        double x;
-        bool hit;
-        const uint32_t o = (op.kind == CK_COPY32 && !op.check) ? s[i] : col_word(op, tab, s[i], x, hit);
-        if (op.kind == CK_COPY32 && !op.check) {
-          reinterpret_cast<uint32_t*>(dst)[row0 + i] = o;
-          continue;
-        }
-        miss += hit ? 0u : 1u;
-        if (op.check) bad += col_check(op, x);
-        if (op.kind == CK_ONEHOT) {
-          bool any = false;
-          for (int q = 0; q < op.n; ++q) {
-            const bool is = x == tab[q];
-            any |= is;
-            reinterpret_cast<int32_t*>(dst + (int64_t)q * p.out_stride)[row0 + i] = is ? 1 : 0;
-          }
-          miss += any ? 0u : 1u;
-        } else if (op.kind != CK_CHECK) {
-          reinterpret_cast<uint32_t*>(dst)[row0 + i] = o;
-        }
-      }
+        [[fallthrough]];
+      default:  // CK_F32, checked CK_COPY32, CK_CHECK
+        bad = item_plain(op, s32, d32, rows, quads, tid);
+        break;
     }
     if (counts) {
       // one shared-memory atomic per warp, one global atomic per item
