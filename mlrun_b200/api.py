@@ -12,6 +12,7 @@ from .feature_store.transforms import (  # noqa: F401
     _Step as MapClass,
 )
 from .feature_store.online import FeatureVector, get_feature_vector, register_feature_vector  # noqa: F401
+from .serving.merger import Merge  # noqa: F401
 from .serving.routing import EnrichmentModelRouter, EnrichmentVotingEnsemble  # noqa: F401
 from .serving import (  # noqa: F401
     FeatureRowModelServer,

@@ -748,6 +748,17 @@ def params_to_step(class_name, name, handler=None, graph_shape=None, function=No
 
 
 # ================================================================================= async engine
+from .merger import DROP  # noqa: E402
+
+
+def _branch_copy(event):
+    """an extra outlet gets its own deep copy of the payload (storey's fan-out contract: branches never see each other's
+    in-place edits; tests/serving/test_merger.py:107-128)"""
+    ev = copy.copy(event)
+    ev.body = copy.deepcopy(event.body)
+    return ev
+
+
 class _Node:
     __slots__ = ("name", "fullname", "call", "full_event", "input_path", "result_path", "kwargs", "outlets",
                  "recovery", "completes")
@@ -794,9 +805,13 @@ class _InlineController:
         try:
             if node.full_event:
                 out = node.call(event, **node.kwargs)
+                if out is DROP:
+                    return
                 out = event if out is None else out
             else:
                 result = node.call(select_input(node.input_path, event.body), **node.kwargs)
+                if result is DROP:
+                    return
                 out = copy.copy(event)
                 out.body = merge_result(node.result_path, event.body, result)
         except Exception as exc:
@@ -808,8 +823,9 @@ class _InlineController:
             event.origin_state = node.fullname
             self._visit(node.recovery, event, reply)
             return
-        for i, outlet in enumerate(node.outlets):
-            self._visit(outlet, out if i == 0 else copy.copy(out), reply)
+        payloads = [out] + [_branch_copy(out) for _ in node.outlets[1:]]  # copied before any branch runs
+        for outlet, ev in zip(node.outlets, payloads):
+            self._visit(outlet, ev, reply)
 
     def terminate(self):
         pass

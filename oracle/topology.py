@@ -1059,6 +1059,17 @@ class _Controller:
         return None
 
 
+from .merger import DROP  # noqa: E402
+
+
+def _branch_copy(event):
+    """what an extra outlet receives: storey hands every additional branch its own deep copy of the event, so branches
+    never see each other's in-place edits (pinned by tests/serving/test_merger.py:107-128: [10, 11], not [13, 13])"""
+    ev = _copy.copy(event)
+    ev.body = _copy.deepcopy(event.body)
+    return ev
+
+
 class _AsyncFlow:
     def __init__(self, context):
         self.context = context
@@ -1082,11 +1093,15 @@ class _AsyncFlow:
             if node.full_event:
                 kwargs = {"context": node.context} if node.pass_context else {}
                 result = node.fn(event, **kwargs)
+                if result is DROP:
+                    return
                 out = result if result is not None else event
             else:
                 kwargs = {"context": node.context} if node.pass_context else {}
                 element = _extract_input_data(node.input_path, event.body)
                 result = node.fn(element, **kwargs)
+                if result is DROP:
+                    return
                 out = _copy.copy(event)
                 out.body = _update_result_body(node.result_path, event.body, result)
         except Exception as exc:
@@ -1098,8 +1113,8 @@ class _AsyncFlow:
             event.origin_state = node.fullname
             self._run_node(node.recovery, event, awaitable)
             return
-        for i, outlet in enumerate(node.outlets):
-            ev = out if i == 0 else _copy.copy(out)
+        payloads = [out] + [_branch_copy(out) for _ in node.outlets[1:]]  # copied before any branch runs
+        for outlet, ev in zip(node.outlets, payloads):
             self._run_node(outlet, ev, awaitable)
 
 

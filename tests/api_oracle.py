@@ -25,6 +25,7 @@ DateExtractor = transforms.DateExtractor
 SetEventMetadata = transforms.SetEventMetadata
 SKLearnModelServer = model_servers.SKLearnModelServer
 NAME = "oracle"
+from oracle.merger import Merge  # noqa: E402,F401
 from oracle import enrichment as _enrichment  # noqa: E402
 
 EnrichmentModelRouter = _enrichment.EnrichmentModelRouter

@@ -66,6 +66,10 @@ def _storey_stub():
     st.MapClass = MapClass
     class Choice(MapClass): pass
     st.Choice = Choice
+    class Flow:  # base of mlrun.serving.merger.Merge: only what its join logic reads
+        def __init__(self, full_event=None, context=None, name=None, **kwargs):
+            self._full_event = full_event; self.context = context; self.name = name
+    st.Flow = Flow
     ut = types.ModuleType("storey.utils")
     ut.unpack_event_if_wrapped = lambda e: e
     ut.wrap_event_for_serialization = lambda e, d: d

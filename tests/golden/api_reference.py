@@ -39,6 +39,8 @@ DropFeatures = _steps.DropFeatures
 DateExtractor = _steps.DateExtractor
 SetEventMetadata = _steps.SetEventMetadata
 SKLearnModelServer = PickleModelServer
+from mlrun.serving.merger import Merge  # noqa: E402
+
 NAME = "reference"
 
 

@@ -171,6 +171,16 @@ def make_namespace(api):
         event.body = {"id": event.id, "key": event.key}
         return event
 
+    def double(x):  # tests/serving/test_merger.py:27-42
+        return x * 2
+
+    class Adder:
+        def __init__(self, add=1, **kwargs):
+            self.add = add
+
+        def do(self, x):
+            return x + self.add
+
     ns = dict(locals())
     ns.pop("api")
     ns.pop("V2")
@@ -995,6 +1005,96 @@ steps_pandas_engine.EXPECT = {
 }
 
 
+def merger_logic(api):
+    """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
+    `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
+    import types
+
+    log, errors = [], []
+    logger = types.SimpleNamespace(warning=lambda m, **k: log.append(("warning", str(m).split("<")[0])),
+                                   info=lambda m, **k: log.append(("info", str(m))))
+    ctx = types.SimpleNamespace(verbose=False, logger=logger,
+                                push_error=lambda event, message, source=None, **k: errors.append([event.id, message, source]))
+    out = {}
+
+    def ev(i, body):
+        return types.SimpleNamespace(id=i, body=body)
+
+    m = api.Merge(context=ctx, name="Merge", max_behind=3, expected_num_events=2)
+    m.post_init()
+    trace = []
+    for i, body in [("a", 1), ("b", 2), ("a", 3), ("c", 4), ("d", 5), ("e", 6), ("b", 7), ("c", 8), ("f", 9), ("d", 10),
+                    ("e", 11), ("f", 12), ("a", 13), ("a", 14)]:
+        res = m._merge_events(ev(i, body))
+        trace.append(None if res is None else [res.id, res.body])
+    out["by_id"] = {"trace": trace, "errors": errors, "log": [list(x) for x in log]}
+
+    log.clear()
+    m3 = api.Merge(context=ctx, name="M3", key_path="event['key']", expected_num_events=3)
+    m3.post_init()
+    trace = []
+    for body in [{"key": 7, "x": 1}, {"key": 8, "x": 2}, {"key": 7, "x": 3}, {"key": 7, "x": 4}, {"key": 8, "x": 5}, {"key": 8, "x": 6}]:
+        trace.append(m3._merge_events(body))
+    out["by_key"] = {"trace": trace, "full_event": bool(m3._full_event)}
+
+    single = api.Merge(context=ctx, name="one", expected_num_events=1)
+    single.post_init()
+    e = ev("z", 5)
+    out["single_uplink_passes"] = single._merge_events(e) is e
+    try:
+        m3._merge_events({"x": 1})
+        out["missing_key"] = None
+    except Exception as exc:  # noqa: BLE001
+        out["missing_key"] = type(exc).__name__
+    return out
+
+
+merger_logic.EXPECT = {
+    ("by_id", "trace", 2): ["a", [1, 3]],
+    ("by_id", "trace", 6): None,       # "b" was given up when "e" opened (window of 3): its second part is ignored
+    ("by_id", "trace", 7): ["c", [4, 8]],
+    ("by_key", "trace", 3): [{"key": 7, "x": 1}, {"key": 7, "x": 3}, {"key": 7, "x": 4}],
+    ("missing_key",): "KeyError",
+}
+
+
+def merge_flows(api):
+    """tests/serving/test_merger.py:87-128 -- split and merge through a served async graph (join on event.id, join on a
+    body key, a missing key surfacing as the event's error)"""
+    ns = make_namespace(api)
+    out = {}
+    fn = api.new_function("x", kind="serving")
+    graph = fn.set_topology("flow", engine="async", exist_ok=True)
+    dbl = graph.to(name="double", handler="double")
+    dbl.to(name="add3", class_name="Adder", add=3)
+    dbl.to(name="add2", class_name="Adder", add=2)
+    graph.add_step(api.Merge(name="Merge")).respond().after_step("add2", "add3")
+    server = fn.to_mock_server(namespace=ns)
+    out["simple"] = [sorted(server.test("", body=5)), sorted(server.test("", body=6))]
+    server.wait_for_completion()
+
+    fn = api.new_function("y", kind="serving")
+    graph = fn.set_topology("flow", engine="async", exist_ok=True)
+    dbl = graph.to(name="double", handler="double", input_path="x", result_path="x")
+    dbl.to(name="add3", class_name="Adder", add=3, input_path="x", result_path="x")
+    dbl.to(name="add2", class_name="Adder", add=2, input_path="x", result_path="x")
+    graph.add_step(api.Merge(name="Merge", key_path="event['key']"), after=["add2", "add3"]).respond()
+    server = fn.to_mock_server(namespace=ns)
+    try:
+        server.test("", body={"x": 4})
+        out["missing_key"] = None
+    except RuntimeError as exc:
+        out["missing_key"] = "KeyError" in str(exc)
+    resp = server.test("", body={"x": 4, "key": 77})
+    out["custom_key"] = sorted(item["x"] for item in resp)
+    server.wait_for_completion()
+    return out
+
+
+merge_flows.EXPECT = {("simple",): [[12, 13], [14, 15]], ("custom_key",): [10, 11], ("missing_key",): True}
+merge_flows.ASYNC = True  # a served async graph needs storey: the reference's own test literals pin it instead
+
+
 # =========================================================================== numeric scenarios (seeded)
 def vote_math(api):
     """serving/routers.py:708-741, 746-787 -- the vote kernels' reference arithmetic on seeded arrays"""
@@ -1058,7 +1158,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_async_basic, flow_async_misc, steps_dict_events, steps_pandas_engine, vote_math,
+    route_cap, flow_async_basic, flow_async_misc, merger_logic, merge_flows, steps_dict_events, steps_pandas_engine, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
