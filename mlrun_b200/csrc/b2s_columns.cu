@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -219,7 +220,11 @@ static int launch_cols(b2s_cols_t c, const void* d_in, int64_t in_stride, int64_
   p.tab = c->d_tab;
   p.counters = d_counters;
   const int64_t items = ((n_rows + kColChunk - 1) / kColChunk) * p.n_ops;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(c->grid, items));
+  static const int grid_mode = getenv("B2S_COL_GRID") ? atoi(getenv("B2S_COL_GRID")) : 8;  // k x (SMs x resident CTAs); -1: one CTA per item.
+  // Items differ in cost (a one-hot item writes n chunks) and a purely persistent grid with static striding leaves SMs idle
+  // at the end: 8 waves of CTAs let the hardware scheduler balance them (measured: x1 0.270 ms, x8 0.245 ms, x64 0.268 ms)
+  const int64_t want = grid_mode < 0 ? items : (int64_t)c->grid * std::max(grid_mode, 1);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, items));
   b2s_int_count_launches(1);
   columns_kernel<<<grid, kColThreads, 0, st>>>(p);
   cudaError_t e = cudaGetLastError();
