@@ -1117,10 +1117,10 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       const size_t ni = ((size_t)1 << depth[mi]) - 1, nl = (size_t)1 << depth[mi];
       max_table = std::max(max_table, align_up((size_t)nt * ni * 8, 16) + (size_t)nt * nl * 8 + (size_t)nt * 4);
     }
-    const int TR2 = 64, G2 = 8, ST2 = 1;  // one row-major landing tile + one transposed tile
+    const int TR2 = kT2TileRows, G2 = kT2Groups, ST2 = 1;  // one row-major landing tile + one transposed tile
     const int NS2 = p->NS <= 1 ? 1 : (p->NS <= 4 ? 4 : 0);
     const size_t part_bytes = (size_t)(G2 - 1) * TR2 * std::max(NS2, 1) * 8;
-    const size_t tiles_bytes = (size_t)ST2 * TR2 * pitch * 4 + (size_t)((n_in + 3) / 4 * 4) * TR2 * 4;
+    const size_t tiles_bytes = (size_t)ST2 * TR2 * pitch * 4 + (size_t)((n_in + 3) / 4 * 4) * TR2 * 4 + (size_t)TR2 * 4;
     const size_t total2 = align_up(max_table, 16) + align_up(part_bytes, 16) + tiles_bytes;
     if (ok && NS2 > 0 && total2 <= (size_t)smem_cap && M <= sms) {
       BlobBuilder tb;

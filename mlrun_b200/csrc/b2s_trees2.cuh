@@ -43,6 +43,9 @@ struct T2Params {
   int32_t sm_tables, sm_part, sm_tiles;  // byte offsets
 };
 
+constexpr int kT2TileRows = 64;  // rows per tile (threads r = 0..63 of a tree group)
+constexpr int kT2Groups = 8;     // tree groups per CTA: thread (g, r) walks trees g, g+8, ... of row r
+
 // Shared-memory layout of one model (built once per CTA from the T2Model arrays):
 //   s_foff[t][1..NI]  byte offset of the node's feature column inside the transposed tile (feature * TR * 4)
 //   s_thr [t][1..NI]  float32 threshold                      (1-based heap: children of n are 2n, 2n+1)
@@ -61,8 +64,8 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
   const int nparts = (gridDim.x - m + p.n_models - 1) / p.n_models;  // CTAs working on model m
   const T2Model tm = p.t2[m];
   const ModelDesc md = p.models[m];
-  const int TR = p.tile_rows;
-  const int G = p.groups;
+  constexpr int TR = kT2TileRows;  // compile-time: the transpose's index arithmetic is shifts and masks
+  constexpr int G = kT2Groups;
   const int NI = tm.n_internal, NL = tm.n_leaves, NT = tm.n_trees;
 
   // ---- the model's tables -> shared memory (once)
@@ -81,6 +84,8 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
   double* s_part = reinterpret_cast<double*>(smem + p.sm_part);  // [groups - 1][tile_rows][NS]
   float* s_stage = reinterpret_cast<float*>(smem + p.sm_tiles);  // row-major landing tile (cp.async)
   float* s_xt = s_stage + (size_t)TR * p.pitch;                  // transposed tile [n_in][TR]
+  int* s_bad = reinterpret_cast<int*>(s_xt + (size_t)((p.n_in + 3) / 4 * 4) * TR);  // per-row "non-finite input" flags
+  if (tid < TR) s_bad[tid] = 0;
 
   const int64_t n_tiles = (p.n_rows + TR - 1) / TR;
   const int g = tid / TR;  // tree group (warp-uniform: TR is a multiple of 32)
@@ -118,11 +123,15 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
     {                 // transpose: lanes take consecutive rows, so both the LDS and the STS are conflict-free
       const int64_t left = p.n_rows - t * TR;
       const int rows = left < TR ? (int)left : TR;
+      // every thread keeps the same row rr = tid % TR through the loop (blockDim is a multiple of TR), so it can also
+      // collect "this row holds a non-finite value" on the way; the G threads of a row merge their flags in shared memory
+      int bad = 0;
       if ((p.n_in & 3) == 0) {  // one 16-byte LDS per (row, chunk), four 4-byte STS
         for (int i = tid; i < (p.n_in >> 2) * TR; i += blockDim.x) {
           const int c = i / TR, rr = i - c * TR;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (rr < rows) v = *reinterpret_cast<const float4*>(s_stage + rr * p.pitch + c * 4);
+          bad |= (is_finite_f(v.x) && is_finite_f(v.y) && is_finite_f(v.z) && is_finite_f(v.w)) ? 0 : 1;
           float* o = s_xt + (size_t)(c * 4) * TR + rr;
           o[0] = v.x;
           o[TR] = v.y;
@@ -132,9 +141,12 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
       } else {
         for (int i = tid; i < p.n_in * TR; i += blockDim.x) {
           const int f = i / TR, rr = i - f * TR;
-          s_xt[i] = rr < rows ? s_stage[rr * p.pitch + f] : 0.0f;
+          const float v = rr < rows ? s_stage[rr * p.pitch + f] : 0.0f;
+          bad |= is_finite_f(v) ? 0 : 1;
+          s_xt[i] = v;
         }
       }
+      if (m == 0 && bad) atomicOr(&s_bad[tid % TR], 1);
     }
     __syncthreads();  // transposed tile visible; landing tile free
     {
@@ -215,10 +227,9 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
       }
       p.pred[row * p.n_models + m] = apply_link(md, sc, p.classes);
     }
-    if (m == 0 && g == 1 && live) {  // a second warp group scans the row for non-finite inputs (conflict-free)
-      int bad = 0;
-      for (int j = 0; j < p.n_in; ++j) bad |= is_finite_f(s_xt[j * TR + r]) ? 0 : 1;
-      p.row_bad[row] = bad;
+    if (m == 0 && g == 1 && live) {  // flags gathered during the transpose; reset for the next tile
+      p.row_bad[row] = s_bad[r];
+      s_bad[r] = 0;
     }
   }
   cp_async_wait<0>();
