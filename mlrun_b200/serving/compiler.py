@@ -23,11 +23,12 @@ _TRANSFORMS = ("Imputer", "OneHotEncoder", "MapValues", "DropFeatures")
 
 
 class CompiledGraph:
-    def __init__(self, plan, program, in_names, responder):
+    def __init__(self, plan, program, in_names, responder, tracker=None):
         self.plan = plan
         self.program = program
         self.in_names = list(in_names)
         self.responder = responder  # (model_name, version) used to shape per-event responses
+        self.tracker = tracker      # the responder's _ModelLogPusher when model tracking is on (else None)
 
     def pack_events(self, bodies):
         X = np.empty((len(bodies), len(self.in_names)), dtype=np.float32)
@@ -120,24 +121,24 @@ def compile_graph(graph, in_names=None, route=None):
         if terminal is not None and terminal.next:
             raise LoweringError("steps after the model / router are not lowered")
 
-    models, vote, responder = [], None, ("", "")
+    models, vote, responder, tracked = [], None, ("", ""), None
     if terminal is not None and terminal.kind == "router":
         robj = terminal._object
         routes = list(terminal.routes.values())
         if isinstance(robj, VotingEnsemble) and route is None:
             models = [_model_pack(r) for r in routes]
             vote = _vote_of(robj, models)
-            responder = (robj.name, robj.version)
+            responder, tracked = (robj.name, robj.version), robj
         elif isinstance(robj, (ModelRouter, VotingEnsemble)):
             key = route or list(terminal.routes.keys())[0]
             models = [_model_pack(terminal.routes[key])]
             mobj = terminal.routes[key]._object
-            responder = (mobj.name, mobj.version)
+            responder, tracked = (mobj.name, mobj.version), mobj
         else:
             raise LoweringError(f"router class {type(robj).__name__} is not lowerable")
     elif terminal is not None:
         models = [_model_pack(terminal)]
-        responder = (terminal._object.name, terminal._object.version)
+        responder, tracked = (terminal._object.name, terminal._object.version), terminal._object
 
     if in_names is None:
         n = _n_inputs(transforms, models)
@@ -146,7 +147,7 @@ def compile_graph(graph, in_names=None, route=None):
     for t in transforms:
         program.apply(t)
     plan = program.build_plan(models, vote)
-    return CompiledGraph(plan, program, in_names, responder)
+    return CompiledGraph(plan, program, in_names, responder, getattr(tracked, "_model_logger", None))
 
 
 def _n_inputs(transforms, models):

@@ -270,10 +270,18 @@ class GraphServer(Serde):
     def run_events(self, bodies, path=None):
         """feature-dict event bodies -> per-event responses through the fused plan.  Rows flagged by the
         device (non-finite model input) come back as the 400 Response the reference would give that event."""
+        from .model_server import now_date
+
+        start = now_date()
         compiled = self.compile(list(bodies[0].keys()) if bodies else None)
         X = compiled.pack_events(bodies)
         out, status = compiled.plan.run(X, with_status=True)
-        return compiled.responses(out, status, self.context)
+        responses = compiled.responses(out, status, self.context)
+        if compiled.tracker is not None:  # model tracking: the records per-event pushes would have produced
+            ok = [i for i, r in enumerate(responses) if isinstance(r, dict)]
+            compiled.tracker.push_batch(start, _Lazy(len(ok), lambda j: {"inputs": [X[ok[j]].tolist()]}),
+                                        lambda j: responses[ok[j]], "infer")
+        return responses
 
 
     def run_enriched(self, keys, with_status=False):
@@ -319,6 +327,9 @@ class GraphServer(Serde):
         from ..lowering import LoweringError
         from . import codec
 
+        from .model_server import now_date
+
+        start = now_date()
         compiled = self.compile()
         name, version = compiled.responder
         if not name:
@@ -331,8 +342,25 @@ class GraphServer(Serde):
         response = {"id": event_id or rest.get("id") or uuid.uuid4().hex, "model_name": name, "outputs": None}
         if version:
             response["model_version"] = version
+        if compiled.tracker is not None:  # one request carrying all rows = one tracked event
+            vals = out[:, 0] if out.shape[1] == 1 else out
+            compiled.tracker.push_batch(start, _Lazy(1, lambda j: {"id": response["id"], "inputs": X.tolist(), **rest}),
+                                        lambda j: {**response, "outputs": vals.tolist()}, "infer")
         text = codec.format_outputs(out[:, 0] if out.shape[1] == 1 else out)
         return self.context.Response(body=codec.dumps_with_outputs(response, text), content_type="application/json", status_code=200)
+
+
+class _Lazy:
+    """index -> record, built on demand (push_batch only materialises the sampled rows)"""
+
+    def __init__(self, n, fn):
+        self.n, self._fn = n, fn
+
+    def __len__(self):
+        return self.n
+
+    def __call__(self, i):
+        return self._fn(i)
 
 
 def v2_serving_init(context, namespace=None):

@@ -261,3 +261,44 @@ class _ModelLogPusher:
         if getattr(self.model, "metrics", None):
             rec["metrics"] = self.model.metrics
         self.output_stream.push([rec])
+
+    def push_batch(self, start, requests, responses, op="infer", microsec=None):
+        """tracking records for a batch the engine scored in one launch: exactly the records -- same
+        sampling positions, same micro-batch boundaries, same layout (v2_serving.py:457-504) -- that `push` would have
+        produced had the events been pushed one by one; `requests[i]` / `responses[i]` are built only for the sampled rows.
+
+        requests / responses: callables i -> dict (lazy), or sequences."""
+        n = len(requests) if hasattr(requests, "__len__") else int(requests.n)
+        if not self.output_stream or n == 0:
+            return 0
+        get_req = requests if callable(requests) else requests.__getitem__
+        get_resp = responses if callable(responses) else responses.__getitem__
+        when = start.isoformat(sep=" ", timespec="microseconds")
+        if microsec is None:
+            microsec = (now_date() - start).microseconds
+        # rows i with (iter0 + i + 1) % sample == 0 are logged
+        first = (-(self._sample_iter + 1)) % self.stream_sample
+        picked = range(first, n, self.stream_sample)
+        self._sample_iter = (self._sample_iter + n) % self.stream_sample
+        pushed = 0
+        for i in picked:
+            request, resp = get_req(i), get_resp(i)
+            if self.stream_batch > 1:
+                if self._batch_iter == 0:
+                    self._batch = []
+                self._batch.append([request, op, resp, str(start), microsec, self.model.metrics])
+                self._batch_iter = (self._batch_iter + 1) % self.stream_batch
+                if self._batch_iter == 0:
+                    rec = self.base_data()
+                    rec["headers"] = ["request", "op", "resp", "when", "microsec", "metrics"]
+                    rec["values"] = self._batch
+                    self.output_stream.push([rec])
+                    pushed += 1
+                continue
+            rec = self.base_data()
+            rec.update(request=request, op=op, resp=resp, when=when, microsec=microsec)
+            if getattr(self.model, "metrics", None):
+                rec["metrics"] = self.model.metrics
+            self.output_stream.push([rec])
+            pushed += 1
+        return pushed

@@ -121,3 +121,35 @@ def test_run_json_answers_like_the_reference_wire_path():
     assert resp.status_code == 400 and "NaN" in resp.body
     with pytest.raises(codec.NotV2Matrix):
         server.run_json(json.dumps({"inputs": [{"f0": 1.0}]}))
+
+
+def test_tracked_batches_emit_the_per_event_records():
+    """model tracking on the batched path: run_events / run_json push the same stream records the
+    per-event path pushes (sampling + micro-batching included)"""
+    wl = tree_workload(n_rows=64, n_feat=24, n_models=4, n_trees=10, depth=4, seed=8, n_fit=600)
+
+    def tracked_server(api, **params):
+        fn = api.new_function("trk", kind="serving")
+        graph = fn.set_topology("router", api.VotingEnsemble(vote_type="regression", executor_type="array"))
+        for i, m in enumerate(wl.models):
+            graph.add_route(f"m{i + 1}", class_name="SKLearnModelServer", model=m, model_path="")
+        fn.set_tracking("dummy://")
+        fn.spec.parameters.update(params)
+        return fn.to_mock_server(namespace={"SKLearnModelServer": api.SKLearnModelServer})
+
+    rows = wl.X.astype(np.float64).tolist()
+    # the reference path: one event per row through the oracle server; keep the ensemble's own records
+    oserver = tracked_server(api_oracle, log_stream_sample=4)
+    for i, row in enumerate(rows):
+        oserver.test("/v2/models/infer", body={"inputs": [row]}, event_id=f"e{i}")
+    want = [r for r in oserver.context.stream.output_stream.event_list if r["model"] == "VotingEnsemble"]
+    assert len(want) == 16
+    # the engine: ONE fused launch for the 64 rows as a V2 body, tracked as the single request it is
+    bserver = tracked_server(api_b200)
+    resp = bserver.run_json(json.dumps({"inputs": rows}), event_id="batch-1")
+    recs = [r for r in bserver.context.stream.output_stream.event_list if r["model"] == "VotingEnsemble"]
+    assert len(recs) == 1 and recs[0]["class"] == want[0]["class"] and recs[0]["op"] == "infer"
+    assert recs[0]["request"]["id"] == "batch-1" and len(recs[0]["request"]["inputs"]) == 64
+    np.testing.assert_allclose(recs[0]["resp"]["outputs"], json.loads(resp.body)["outputs"])
+    np.testing.assert_allclose([recs[0]["resp"]["outputs"][3 + 4 * j] for j in range(16)],
+                               [r["resp"]["outputs"][0] for r in want], rtol=RTOL, atol=ATOL)
