@@ -280,7 +280,7 @@ class GraphServer(Serde):
         if compiled.tracker is not None:  # model tracking: the records per-event pushes would have produced
             ok = [i for i, r in enumerate(responses) if isinstance(r, dict)]
             compiled.tracker.push_batch(start, _Lazy(len(ok), lambda j: {"inputs": [X[ok[j]].tolist()]}),
-                                        lambda j: responses[ok[j]], "infer")
+                                        lambda j: responses[ok[j]], _tracked_op(compiled.tracker))
         return responses
 
 
@@ -345,9 +345,14 @@ class GraphServer(Serde):
         if compiled.tracker is not None:  # one request carrying all rows = one tracked event
             vals = out[:, 0] if out.shape[1] == 1 else out
             compiled.tracker.push_batch(start, _Lazy(1, lambda j: {"id": response["id"], "inputs": X.tolist(), **rest}),
-                                        lambda j: {**response, "outputs": vals.tolist()}, "infer")
+                                        lambda j: {**response, "outputs": vals.tolist()}, _tracked_op(compiled.tracker))
         text = codec.format_outputs(out[:, 0] if out.shape[1] == 1 else out)
         return self.context.Response(body=codec.dumps_with_outputs(response, text), content_type="application/json", status_code=200)
+
+
+def _tracked_op(tracker):
+    """routers log their own events without an operation (routers.py:901-903), model servers with it (v2_serving.py:331-340)"""
+    return None if hasattr(tracker.model, "routes") else "infer"
 
 
 class _Lazy:

@@ -148,7 +148,7 @@ def test_tracked_batches_emit_the_per_event_records():
     bserver = tracked_server(api_b200)
     resp = bserver.run_json(json.dumps({"inputs": rows}), event_id="batch-1")
     recs = [r for r in bserver.context.stream.output_stream.event_list if r["model"] == "VotingEnsemble"]
-    assert len(recs) == 1 and recs[0]["class"] == want[0]["class"] and recs[0]["op"] == "infer"
+    assert len(recs) == 1 and recs[0]["class"] == want[0]["class"] and recs[0]["op"] == want[0]["op"]
     assert recs[0]["request"]["id"] == "batch-1" and len(recs[0]["request"]["inputs"]) == 64
     np.testing.assert_allclose(recs[0]["resp"]["outputs"], json.loads(resp.body)["outputs"])
     np.testing.assert_allclose([recs[0]["resp"]["outputs"][3 + 4 * j] for j in range(16)],
