@@ -1122,7 +1122,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
     const size_t part_bytes = (size_t)(G2 - 1) * TR2 * std::max(NS2, 1) * 8;
     const size_t tiles_bytes = (size_t)ST2 * TR2 * pitch * 4 + (size_t)((n_in + 3) / 4 * 4) * TR2 * 4 + (size_t)TR2 * 4;
     const size_t total2 = align_up(max_table, 16) + align_up(part_bytes, 16) + tiles_bytes;
-    if (ok && NS2 > 0 && total2 <= (size_t)smem_cap && M <= sms && M <= kMaxModels) {
+    if (ok && NS2 > 0 && total2 <= (size_t)smem_cap && M <= sms) {
       BlobBuilder tb;
       std::vector<T2Model> t2m(M);
       std::vector<size_t> o_nodes(M), o_leaves(M), o_slot(M), o_scale(M);
@@ -1184,7 +1184,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       t.pitch = pitch;
       t.stages = ST2;
       t.groups = G2;
-      for (int mi = 0; mi < M; ++mi) t.t2[mi] = t2m[mi];
+      t.t2 = (const T2Model*)(p->d_t2_blob + o_models2);
       t.models = k.models;
       t.classes = k.classes;
       t.bias = k.bias;

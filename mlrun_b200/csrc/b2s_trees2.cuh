@@ -36,7 +36,7 @@ struct T2Params {
   double* pred;        // [n_rows][n_models]
   int32_t* row_bad;    // [n_rows] non-finite input flags (written by the CTAs of model 0)
   int32_t n_in, n_models, tile_rows, pitch, stages, vec_ok, groups;
-  T2Model t2[kMaxModels];  // per-model tables (kernel-parameter space: sizes and bases stay in uniform registers)
+  const T2Model* t2;   // [n_models]
   const ModelDesc* models;
   const int32_t* classes;
   const double* bias;  // init scores, indexed by ModelDesc.score_off
@@ -45,58 +45,6 @@ struct T2Params {
 
 constexpr int kT2TileRows = 64;  // rows per tile (threads r = 0..63 of a tree group)
 constexpr int kT2Groups = 8;     // tree groups per CTA: thread (g, r) walks trees g, g+8, ... of row r
-
-// The walks of tree group G0 for one row.  G0 is a literal (the caller switches on the warp-uniform group), so tree
-// indices and table bases live in uniform registers.  a = base + 4n is the byte offset of node n (1-based heap) inside
-// s_foff / s_thr, base = 4 * (tree * NI - 1); the child 2n + right sits at 2a - base + 4 * right.
-template <int NS, int G0>
-__device__ __forceinline__ void t2_walk(const char* __restrict__ s_foff, const char* __restrict__ s_thr,
-                                        const double* __restrict__ s_leaf, const int32_t* __restrict__ s_slot,
-                                        const char* __restrict__ xt_r, int NT, int NI, int NL, int depth, double (&acc)[NS]) {
-  constexpr int U = 4;  // independent root->leaf walks in flight per thread (ILP over the LDS latency)
-  constexpr int G = kT2Groups;
-  auto leaf_add = [&](int tree, int a) {
-    const int n = (a - (tree * NI * 4 - 4)) >> 2;
-    const double v = s_leaf[tree * NL + n - NL];
-    if (NS == 1) {
-      acc[0] = __dadd_rn(acc[0], v);
-    } else {
-      const int slot = s_slot[tree];
-#pragma unroll
-      for (int k = 0; k < NS; ++k)
-        if (k == slot) acc[k] = __dadd_rn(acc[k], v);
-    }
-  };
-  int tr = G0;
-  for (; tr + (U - 1) * G < NT; tr += U * G) {
-    int a[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) a[u] = (tr + u * G) * NI * 4;  // base + 4: the root
-    for (int d = 0; d < depth; ++d) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int base = (tr + u * G) * NI * 4 - 4;
-        const int foff = *reinterpret_cast<const int32_t*>(s_foff + a[u]);
-        const float thr = *reinterpret_cast<const float*>(s_thr + a[u]);
-        const float x = *reinterpret_cast<const float*>(xt_r + foff);
-        a[u] = 2 * a[u] - base + ((x <= thr) ? 0 : 4);  // sklearn: left when x <= threshold
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) leaf_add(tr + u * G, a[u]);
-  }
-  for (; tr < NT; tr += G) {  // remaining trees of the group, one at a time (same order of additions)
-    const int base = tr * NI * 4 - 4;
-    int a = base + 4;
-    for (int d = 0; d < depth; ++d) {
-      const int foff = *reinterpret_cast<const int32_t*>(s_foff + a);
-      const float thr = *reinterpret_cast<const float*>(s_thr + a);
-      const float x = *reinterpret_cast<const float*>(xt_r + foff);
-      a = 2 * a - base + ((x <= thr) ? 0 : 4);
-    }
-    leaf_add(tr, a);
-  }
-}
 
 // Shared-memory layout of one model (built once per CTA from the T2Model arrays):
 //   s_foff[t][1..NI]  byte offset of the node's feature column inside the transposed tile (feature * TR * 4)
@@ -114,7 +62,7 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
   const int m = blockIdx.x % p.n_models;
   const int part = blockIdx.x / p.n_models;
   const int nparts = (gridDim.x - m + p.n_models - 1) / p.n_models;  // CTAs working on model m
-  const T2Model& tm = p.t2[m];
+  const T2Model tm = p.t2[m];
   const ModelDesc md = p.models[m];
   constexpr int TR = kT2TileRows;  // compile-time: the transpose's index arithmetic is shifts and masks
   constexpr int G = kT2Groups;
@@ -168,6 +116,7 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
   if ((int64_t)part < n_tiles) issue((int64_t)part * TR);
   cp_async_commit();
   const char* xt_r = reinterpret_cast<const char*>(s_xt + r);
+  const int leaf_bias = NL;  // n - NL is the leaf index
   for (int64_t t = part; t < n_tiles; t += nparts) {
     cp_async_wait<0>();
     __syncthreads();  // landing tile (and, first time round, the tables) visible; the previous walk is over
@@ -211,17 +160,54 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
 #pragma unroll
     for (int k = 0; k < NS; ++k) acc[k] = 0.0;
     if (live) {
-      const char* fo = reinterpret_cast<const char*>(s_foff);
-      const char* th = reinterpret_cast<const char*>(s_thr);
-      switch (g) {  // warp-uniform
-        case 0: t2_walk<NS, 0>(fo, th, s_leaf, s_slot, xt_r, NT, NI, NL, tm.depth, acc); break;
-        case 1: t2_walk<NS, 1>(fo, th, s_leaf, s_slot, xt_r, NT, NI, NL, tm.depth, acc); break;
-        case 2: t2_walk<NS, 2>(fo, th, s_leaf, s_slot, xt_r, NT, NI, NL, tm.depth, acc); break;
-        case 3: t2_walk<NS, 3>(fo, th, s_leaf, s_slot, xt_r, NT, NI, NL, tm.depth, acc); break;
-        case 4: t2_walk<NS, 4>(fo, th, s_leaf, s_slot, xt_r, NT, NI, NL, tm.depth, acc); break;
-        case 5: t2_walk<NS, 5>(fo, th, s_leaf, s_slot, xt_r, NT, NI, NL, tm.depth, acc); break;
-        case 6: t2_walk<NS, 6>(fo, th, s_leaf, s_slot, xt_r, NT, NI, NL, tm.depth, acc); break;
-        default: t2_walk<NS, 7>(fo, th, s_leaf, s_slot, xt_r, NT, NI, NL, tm.depth, acc); break;
+      constexpr int U = 4;  // independent root->leaf walks in flight per thread (ILP over the LDS latency)
+      int tr = g;
+      for (; tr + (U - 1) * G < NT; tr += U * G) {
+        int n4[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) n4[u] = 4;  // node 1 (byte index)
+        for (int d = 0; d < tm.depth; ++d) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int at = (tr + u * G) * NI * 4 - 4 + n4[u];  // 1-based
+            const int foff = *reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(s_foff) + at);
+            const float thr = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_thr) + at);
+            const float x = *reinterpret_cast<const float*>(xt_r + foff);
+            n4[u] = 2 * n4[u] + ((x <= thr) ? 0 : 4);  // sklearn: left when x <= threshold
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int tu = tr + u * G;
+          const double v = s_leaf[tu * NL + (n4[u] >> 2) - leaf_bias];
+          if (NS == 1) {
+            acc[0] = __dadd_rn(acc[0], v);
+          } else {
+            const int slot = s_slot[tu];
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+              if (k == slot) acc[k] = __dadd_rn(acc[k], v);
+          }
+        }
+      }
+      for (; tr < NT; tr += G) {  // remaining trees of the group, one at a time (same order of additions)
+        int n4 = 4;
+        for (int d = 0; d < tm.depth; ++d) {
+          const int at = tr * NI * 4 - 4 + n4;
+          const int foff = *reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(s_foff) + at);
+          const float thr = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(s_thr) + at);
+          const float x = *reinterpret_cast<const float*>(xt_r + foff);
+          n4 = 2 * n4 + ((x <= thr) ? 0 : 4);
+        }
+        const double v = s_leaf[tr * NL + (n4 >> 2) - leaf_bias];
+        if (NS == 1) {
+          acc[0] = __dadd_rn(acc[0], v);
+        } else {
+          const int slot = s_slot[tr];
+#pragma unroll
+          for (int k = 0; k < NS; ++k)
+            if (k == slot) acc[k] = __dadd_rn(acc[k], v);
+        }
       }
     }
     if (g > 0) {
