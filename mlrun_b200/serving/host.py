@@ -302,19 +302,29 @@ class GraphServer(Serde):
             raise LoweringError(f"the feature vector has {svc.table.n_feat} features, the models take {plan.n_in}")
         k = np.ascontiguousarray(svc._encode_keys(keys), dtype=np.int64)
         n = len(k)
-        d_keys = nat.DeviceBuffer(max(n, 1) * 8).upload(k)
-        d_rows = nat.DeviceBuffer(max(n, 1) * plan.n_in * 4)
-        d_found = nat.DeviceBuffer(max(n, 1) * 4)
-        d_out = nat.DeviceBuffer(max(n, 1) * plan.out_cols * 4)
-        d_status = nat.DeviceBuffer(max(n, 1) * 4)
+        bufs = getattr(self, "_enrich_bufs", None)
+        if bufs is None or bufs[0] < n or bufs[1] is not plan:  # device staging, kept and grown across calls
+            cap = max(n, 4096)
+            bufs = (cap, plan, nat.DeviceBuffer(cap * 8), nat.DeviceBuffer(cap * plan.n_in * 4), nat.DeviceBuffer(cap * 4),
+                    nat.DeviceBuffer(cap * plan.out_cols * 4), nat.DeviceBuffer(cap * 4))
+            self._enrich_bufs = bufs
+        _cap, _plan, d_keys, d_rows, d_found, d_out, d_status = bufs
+        if n:
+            nat.check(nat.load().b2s_memcpy_h2d(d_keys.ptr, k.ctypes.data, n * 8))
         svc.table.lookup_device(d_keys.ptr, n, d_rows.ptr, plan.n_in * 4, d_found.ptr)
         plan.run_device(d_rows.ptr, n, plan.n_in * 4, d_out.ptr, d_status.ptr)
         nat.load().b2s_device_sync()
-        out = d_out.download(plan.out_dtype, (n, plan.out_cols))
+        def fetch(buf, dtype, shape):
+            a = np.empty(shape, dtype=dtype)
+            if a.nbytes:
+                nat.check(nat.load().b2s_memcpy_d2h(a.ctypes.data, buf.ptr, a.nbytes))
+            return a
+
+        out = fetch(d_out, plan.out_dtype, (n, plan.out_cols))
         if not with_status:
             return out
-        status = d_status.download(np.int32, (n,))
-        found = d_found.download(np.int32, (n,))
+        status = fetch(d_status, np.int32, (n,))
+        found = fetch(d_found, np.int32, (n,))
         return out, status | np.where(found == 0, 4, 0).astype(np.int32)
 
     def run_json(self, body, event_id=None):
