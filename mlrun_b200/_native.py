@@ -235,3 +235,55 @@ def pinned_empty(shape, dtype=np.float32):
 
 
 _PINNED = {}
+
+
+class _Lease:
+    """keeps a pinned block out of the pool while any numpy array over it is alive (the arrays' base buffer holds it)"""
+
+    def __init__(self, pool, ptr, size):
+        self.pool, self.ptr, self.size = pool, ptr, size
+
+    def __del__(self):
+        try:
+            self.pool._give_back(self.ptr, self.size)
+        except Exception:
+            pass
+
+
+class PinnedPool:
+    """cudaMallocHost blocks for results that go straight into numpy / DataFrame columns: D2H copies into pinned memory run
+    at PCIe speed, and the block is reused once the arrays built over it are garbage collected.  At most `max_blocks`
+    blocks exist; beyond that `take` returns None and the caller uses pageable memory."""
+
+    def __init__(self, max_blocks=6, granule=1 << 20):
+        self.max_blocks, self.granule = max_blocks, granule
+        self._free = {}
+        self._n = 0
+        self._mu = threading.Lock()
+
+    def take(self, nbytes):
+        size = max(self.granule, (int(nbytes) + self.granule - 1) // self.granule * self.granule)
+        with self._mu:
+            ptrs = self._free.get(size)
+            ptr = ptrs.pop() if ptrs else None
+            if ptr is None:
+                if self._n >= self.max_blocks:
+                    victim = next((s for s, p in self._free.items() if p), None)  # a free block of another size makes room
+                    if victim is None:
+                        return None
+                    load().b2s_free_pinned(self._free[victim].pop())
+                    self._n -= 1
+                ptr = init().b2s_alloc_pinned(size)
+                if not ptr:
+                    return None
+                self._n += 1
+        buf = (C.c_char * size).from_address(ptr)
+        buf._lease = _Lease(self, ptr, size)
+        return buf
+
+    def _give_back(self, ptr, size):
+        with self._mu:
+            self._free.setdefault(size, []).append(ptr)
+
+
+PINNED = PinnedPool()

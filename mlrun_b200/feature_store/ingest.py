@@ -333,19 +333,28 @@ class IngestPlan:
             self._seen_key = key
         n = len(df)
         ins, _keep = self._inputs(df)
-        bufs, outs = {}, {}
+        # result columns live in one pinned block (fast D2H, no second copy); the frame built over them keeps the block
+        # alive and it returns to the pool when the frame is collected
+        specs = []
         for name, slot, how in self.out:
-            if how == "dt":
-                bufs[name] = np.empty(n, dtype=np.int64)
-            elif how == "f32" or (isinstance(how, tuple) and how[0] == "map"):
-                bufs[name] = np.empty(n, dtype=np.float32)
-            else:
-                bufs[name] = np.empty(n, dtype=np.int32)
-            outs[slot] = bufs[name]
+            dt = np.int64 if how == "dt" else (np.float32 if (how == "f32" or (isinstance(how, tuple) and how[0] == "map")) else np.int32)
+            specs.append((name, slot, np.dtype(dt)))
+        extra = [s for s in range(self.plan.n_out) if s not in {sp[1] for sp in specs} and not self._second_half(s)]
+        layout, off = [], 0
+        for dt in [sp[2] for sp in specs] + [np.dtype(np.int32)] * len(extra):
+            layout.append(off)
+            off += (n * dt.itemsize + 63) // 64 * 64
+        block = nat.PINNED.take(off) if n else None
+
+        def column(i, dt):
+            return np.frombuffer(block, dtype=dt, count=n, offset=layout[i]) if block is not None else np.empty(n, dtype=dt)
+
+        bufs, outs = {}, {}
+        for i, (name, slot, dt) in enumerate(specs):
+            bufs[name] = outs[slot] = column(i, dt)
         # slots written by the device but not part of the result (dropped one-hot members) still need a landing buffer
-        for s in range(self.plan.n_out):
-            if s not in outs and not self._second_half(s):
-                outs[s] = np.empty(n, dtype=np.int32)
+        for j, s_ in enumerate(extra):
+            outs[s_] = column(len(specs) + j, np.dtype(np.int32))
         self.counters, self.stats = self.plan.run_host(ins, n, outs, with_stats=True)
         data = {}
         for name, _slot, how in self.out:

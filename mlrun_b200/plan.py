@@ -147,9 +147,12 @@ class DevicePlan:
 
     # ---- execution ---------------------------------------------------------------------------
     def _check_rows(self, X):
-        if X.dtype != np.float32 or X.ndim != 2 or X.shape[1] != self.n_in or X.strides[1] != 4:
+        if X.dtype != np.float32 or X.ndim != 2 or X.shape[1] != self.n_in or (X.shape[0] and X.strides[1] != 4):
             raise ValueError(f"rows must be a float32 (B, {self.n_in}) array with unit inner stride")
         return X
+
+    def _stride(self, X):
+        return X.strides[0] if X.shape[0] else self.n_in * 4  # an empty array reports no usable strides
 
     def run(self, X, with_status=False, with_stats=False):
         """synchronous host call: pinned staging -> H2D -> kernels -> D2H (b2s_run_host)"""
@@ -158,7 +161,7 @@ class DevicePlan:
         out = np.empty((n, self.out_cols), dtype=self.out_dtype)
         status = np.empty(n, dtype=np.int32)
         stats = nat.Stats()
-        nat.check(self._lib.b2s_run_host(self._h, X.ctypes.data, n, X.strides[0], out.ctypes.data, out.nbytes,
+        nat.check(self._lib.b2s_run_host(self._h, X.ctypes.data, n, self._stride(X), out.ctypes.data, out.nbytes,
                                          status.ctypes.data, C.byref(stats)))
         res = (out,)
         if with_status:
@@ -170,7 +173,7 @@ class DevicePlan:
     def submit(self, X):
         X = self._check_rows(X)
         t = C.c_uint64()
-        nat.check(self._lib.b2s_submit(self._h, X.ctypes.data, X.shape[0], X.strides[0], C.byref(t)))
+        nat.check(self._lib.b2s_submit(self._h, X.ctypes.data, X.shape[0], self._stride(X), C.byref(t)))
         return (t.value, X.shape[0])
 
     def wait(self, ticket, with_status=False, with_stats=False):
