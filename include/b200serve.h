@@ -148,7 +148,9 @@ int b2s_run_host(b2s_plan_t plan, const void* rows, int64_t n_rows, int64_t row_
  * thread seals a batch when it holds max_batch rows or the oldest row waited max_wait_us, and runs
  * H2D -> kernels -> D2H on its own streams.  b2s_wait blocks until the ticket's batch completed and copies
  * that ticket's rows out.  This is the replacement of storey's SyncEmitSource.emit / await_result hand-off
- * (serving/states.py:1283-1287). */
+ * (serving/states.py:1283-1287).  A ring slot is recycled when every ticket of its batch was collected, and the ring
+ * has `ring_slots` (b2s_init cfg, default 4) batches: a producer that keeps submitting without collecting its tickets
+ * eventually blocks in b2s_submit -- emit and await per request, as the reference's callers do. */
 int b2s_submit(b2s_plan_t plan, const void* rows, int64_t n_rows, int64_t row_stride_bytes, uint64_t* ticket);
 int b2s_wait(b2s_plan_t plan, uint64_t ticket, void* out, int64_t out_bytes, int32_t* row_status, b2s_stats* stats);
 /* force the open batch out now (drain callback, serving/server.py:353-384) */

@@ -400,7 +400,8 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   }
   r.tile_rows = tr;
   const int64_t tiles = (n_rows + tr - 1) / tr;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->rt_grid, tiles));
+  static const int grid_mul = getenv("B2S_RT_GRIDMUL") ? std::max(1, atoi(getenv("B2S_RT_GRIDMUL"))) : 1;  // CTA waves (1 = persistent)
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)p->rt_grid * grid_mul, tiles));
   r.use_bulk = mode;
   {
     static const int one_sync = getenv("B2S_RT_ONESYNC") ? atoi(getenv("B2S_RT_ONESYNC")) : 0;
