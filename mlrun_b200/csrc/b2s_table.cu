@@ -52,6 +52,7 @@ struct LookupParams {
   const float* impute;      // [n_feat]; NaN: keep the stored value
   int32_t n_feat;
   int32_t any_impute;
+  int32_t lanes_per_row;    // n_feat / 4 when that is a power of two <= 32 (rows are copied by sub-warps), else 0
   const int64_t* keys;      // [n]
   int64_t n;
   float* out;               // row i at out + i * out_stride (bytes)
@@ -82,6 +83,38 @@ __global__ void __launch_bounds__(256) table_lookup_kernel(const __grid_constant
       if (p.found) p.found[q] = row >= 0 ? 1 : 0;
     }
     const int cnt = (int)((p.n - base < 32) ? (p.n - base) : 32);
+    if (vec && p.lanes_per_row) {
+      // lanes_per_row = n_feat / 4 lanes copy one row with one 16-byte access each, so a warp moves 32 / lanes_per_row rows
+      // per step (two for 64 features); kGather steps are loaded before any is stored (more rows in flight)
+      const int lpr = p.lanes_per_row, rpi = 32 / lpr;
+      const int sub = lane / lpr, c = (lane - sub * lpr) * 4;
+      const float4 f = p.any_impute ? *reinterpret_cast<const float4*>(p.impute + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      constexpr int kGather = 4;
+      for (int j0 = 0; j0 < cnt; j0 += rpi * kGather) {
+        float4 v[kGather];
+#pragma unroll
+        for (int u = 0; u < kGather; ++u) {
+          const int j = j0 + u * rpi + sub;
+          const int64_t r = __shfl_sync(0xffffffffu, row, j & 31);
+          v[u] = (j < cnt && r >= 0) ? __ldg(reinterpret_cast<const float4*>(p.values + r * p.n_feat + c))
+                                     : make_float4(NAN, NAN, NAN, NAN);
+        }
+#pragma unroll
+        for (int u = 0; u < kGather; ++u) {
+          const int j = j0 + u * rpi + sub;
+          if (j >= cnt) continue;
+          float4 w = v[u];
+          if (p.any_impute) {  // OnlineVectorService.get (:1046-1052): None / NaN / Inf -> impute value
+            w.x = (!(fabsf(w.x) <= 3.402823466e38f) && f.x == f.x) ? f.x : w.x;
+            w.y = (!(fabsf(w.y) <= 3.402823466e38f) && f.y == f.y) ? f.y : w.y;
+            w.z = (!(fabsf(w.z) <= 3.402823466e38f) && f.z == f.z) ? f.z : w.z;
+            w.w = (!(fabsf(w.w) <= 3.402823466e38f) && f.w == f.w) ? f.w : w.w;
+          }
+          *reinterpret_cast<float4*>(reinterpret_cast<char*>(p.out) + (base + j) * p.out_stride + c * 4) = w;
+        }
+      }
+      continue;
+    }
     for (int j = 0; j < cnt; ++j) {  // the warp copies query j's row together
       const int64_t r = __shfl_sync(0xffffffffu, row, j);
       float* dst = reinterpret_cast<float*>(reinterpret_cast<char*>(p.out) + (base + j) * p.out_stride);
@@ -180,6 +213,10 @@ static int launch_lookup(b2s_table_t t, const int64_t* d_keys, int64_t n, float*
   p.impute = t->d_impute;
   p.n_feat = t->n_feat;
   p.any_impute = t->any_impute;
+  {
+    const int l = t->n_feat / 4;
+    p.lanes_per_row = (t->n_feat % 4 == 0 && l >= 1 && l <= 32 && (l & (l - 1)) == 0) ? l : 0;
+  }
   p.keys = d_keys;
   p.n = n;
   p.out = d_rows;
