@@ -409,10 +409,20 @@ def main():
     # latency at the configured serving batch (4096 events): one launch per batch, CUDA-event timed
     lat = []
     small = bufs[0].data_ptr()
-    for _ in range(20):
+    for _ in range(100):
         plan.time_device([small], 4096, row_bytes, out.data_ptr(), 1)
-    for _ in range(300):
+    for _ in range(1000):
         lat.append(plan.time_device([small], 4096, row_bytes, out.data_ptr(), 1) * 1e3)
+    # end-to-end latency of one serving batch: host rows -> b2s_run_host (H2D, kernel, D2H) -> host results, wall clock
+    lat_e2e = []
+    h_small = nat.pinned_empty((4096, F), np.float32)
+    h_small[:] = base[:4096].numpy()
+    for _ in range(100):
+        plan.run(h_small, with_status=True)
+    for _ in range(1000):
+        t0 = time.perf_counter()
+        plan.run(h_small, with_status=True)
+        lat_e2e.append((time.perf_counter() - t0) * 1e6)
 
     e2e = None
     if not args.no_e2e:
@@ -478,7 +488,10 @@ def main():
                        "l2": f"{nbuf} rotating input buffers of {B * row_bytes / 1e6:.0f} MB (> 126 MB L2 between re-reads)",
                        "device": info["name"], "kernel": plan.kernel},
             "p50_step_latency_us": {"batch": 4096, "p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
-                                    "how": "CUDA events around one fused-kernel launch, 300 samples"},
+                                    "how": "CUDA events around one fused-kernel launch, 1000 samples after 100 warm-ups",
+                                    "e2e_p50": float(np.percentile(lat_e2e, 50)), "e2e_p99": float(np.percentile(lat_e2e, 99)),
+                                    "e2e_how": "wall clock of DevicePlan.run on 4096 pinned host rows (H2D + kernel + D2H + status), "
+                                               "1000 samples after 100 warm-ups"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(name, B), "kernel": plan.kernel, "algorithmic_bytes_per_event": bpe,
                          "kernel_ms_per_launch": kms, "peak_source": peak_src},
