@@ -603,7 +603,7 @@ def main_ingest(args, rank, local_rank, world):
 
     e2e = None
     if not args.no_e2e:
-        frames = [wl.df, wl.df.iloc[::-1].reset_index(drop=True)]
+        frames = [wl.df, wl.df.iloc[::-1].reset_index(drop=True).copy()]  # two materialised frames, alternated
         with contextlib.redirect_stdout(io.StringIO()):
             for j in range(2):
                 fset.ingest(frames[j % 2])
