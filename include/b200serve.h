@@ -205,6 +205,15 @@ typedef struct b2s_cols_s* b2s_cols_t;
 #define B2S_DATE_DAY_OF_WEEK 6 /* Monday = 0 */
 #define B2S_DATE_DAY_OF_YEAR 7
 #define B2S_DATE_QUARTER 8
+#define B2S_DATE_IS_LEAP_YEAR 9     /* the is_* parts give 0 / 1 */
+#define B2S_DATE_DAYS_IN_MONTH 10
+#define B2S_DATE_IS_MONTH_START 11
+#define B2S_DATE_IS_MONTH_END 12
+#define B2S_DATE_IS_QUARTER_START 13
+#define B2S_DATE_IS_QUARTER_END 14
+#define B2S_DATE_IS_YEAR_START 15
+#define B2S_DATE_IS_YEAR_END 16
+#define B2S_DATE_WEEK 17             /* ISO 8601 week (pd.Timestamp.week / weekofyear) */
 
 int b2s_cols_create(int32_t n_in_slots, b2s_cols_t* out);
 int b2s_cols_destroy(b2s_cols_t plan);

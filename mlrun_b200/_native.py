@@ -21,7 +21,10 @@ VOTE_NONE, VOTE_MEAN, VOTE_MAJORITY = 0, 1, 2
 ROW_NONFINITE_INPUT, ROW_BAD_LABEL = 1, 2
 COL_F32, COL_I32, COL_I64 = 0, 1, 2
 DATE_PARTS = {"year": 0, "month": 1, "day": 2, "hour": 3, "minute": 4, "second": 5, "day_of_week": 6, "dayofweek": 6,
-              "weekday": 6, "day_of_year": 7, "dayofyear": 7, "quarter": 8}
+              "weekday": 6, "day_of_year": 7, "dayofyear": 7, "quarter": 8, "is_leap_year": 9, "days_in_month": 10,
+              "daysinmonth": 10, "is_month_start": 11, "is_month_end": 12, "is_quarter_start": 13, "is_quarter_end": 14,
+              "is_year_start": 15, "is_year_end": 16, "week": 17, "weekofyear": 17}
+DATE_BOOL_PARTS = {9, 11, 12, 13, 14, 15, 16}
 
 
 class NativeError(RuntimeError):

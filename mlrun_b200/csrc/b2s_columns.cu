@@ -167,7 +167,7 @@ extern "C" int b2s_cols_add_onehot(b2s_cols_t c, int32_t src_slot, int32_t kind,
 
 extern "C" int b2s_cols_add_date_part(b2s_cols_t c, int32_t src_slot, int32_t part, int32_t* out_slot, int32_t* nat_counter) {
   if (int rc = check_src(c, src_slot, B2S_COL_I64)) return rc;
-  if (part < 0 || part > DP_QUARTER) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "date part %d is not computed on the device", part);
+  if (part < 0 || part > DP_LAST) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "date part %d is not computed on the device", part);
   ColOp op{};
   op.kind = CK_DATE;
   op.src = src_slot;

@@ -31,6 +31,9 @@ enum ColKind : int32_t {
 
 enum DatePart : int32_t {
   DP_YEAR = 0, DP_MONTH, DP_DAY, DP_HOUR, DP_MINUTE, DP_SECOND, DP_DAY_OF_WEEK, DP_DAY_OF_YEAR, DP_QUARTER,
+  DP_IS_LEAP_YEAR, DP_DAYS_IN_MONTH, DP_IS_MONTH_START, DP_IS_MONTH_END, DP_IS_QUARTER_START, DP_IS_QUARTER_END,
+  DP_IS_YEAR_START, DP_IS_YEAR_END, DP_WEEK,
+  DP_LAST = DP_WEEK,
 };
 
 struct ColOp {
@@ -106,13 +109,36 @@ __device__ __noinline__ int32_t date_part(int64_t ns, int part) {
   }
   int y, m, d, doy;
   civil_from_days(days, y, m, d, doy);
+  const bool leap = (y % 4 == 0 && y % 100 != 0) || y % 400 == 0;
+  const int dim = (m == 2) ? (leap ? 29 : 28) : ((m == 4 || m == 6 || m == 9 || m == 11) ? 30 : 31);
   switch (part) {
     case DP_YEAR: return y;
     case DP_MONTH: return m;
     case DP_DAY: return d;
     case DP_DAY_OF_YEAR: return doy;
-    default: return (m - 1) / 3 + 1;  // DP_QUARTER
+    case DP_QUARTER: return (m - 1) / 3 + 1;
+    case DP_IS_LEAP_YEAR: return leap ? 1 : 0;
+    case DP_DAYS_IN_MONTH: return dim;
+    case DP_IS_MONTH_START: return d == 1;
+    case DP_IS_MONTH_END: return d == dim;
+    case DP_IS_QUARTER_START: return d == 1 && (m - 1) % 3 == 0;
+    case DP_IS_QUARTER_END: return d == dim && m % 3 == 0;
+    case DP_IS_YEAR_START: return d == 1 && m == 1;
+    case DP_IS_YEAR_END: return d == 31 && m == 12;
+    default: break;
   }
+  // DP_WEEK: ISO 8601 week number (pd.Timestamp.week)
+  const int wd = (int)(((days % 7) + 7 + 3) % 7);  // Monday = 0
+  int w = (doy - wd + 9) / 7;
+  auto long_year = [](int yy) {  // 53 ISO weeks: 1 January is a Thursday, or a Wednesday in a leap year
+    const bool lp = (yy % 4 == 0 && yy % 100 != 0) || yy % 400 == 0;
+    const int64_t yp = (int64_t)yy - 1;
+    const int jan1 = (int)((yp * 365 + yp / 4 - yp / 100 + yp / 400) % 7);  // 0 = Monday (1 Jan of year 1 was a Monday)
+    return jan1 == 3 || (lp && jan1 == 2);
+  };
+  if (w < 1) w = long_year(y - 1) ? 53 : 52;
+  else if (w == 53 && !long_year(y)) w = 1;
+  return w;
 }
 
 // one 4-byte source word -> the op's outputs (shared by the vector and the tail paths)

@@ -287,7 +287,7 @@ class IngestPlan:
             else:  # date
                 slot, miss = plan.add_date_part(c.slot, c.arg)
                 self.miss.append((miss, c.name, "NaT"))
-                cnt, how = -1, ("date", miss)
+                cnt, how = -1, ("date", miss, c.arg in nat.DATE_BOOL_PARTS)
             if cnt >= 0:
                 self.checks.append((cnt, c.name, c.check[2]))
             self.out.append((c.name, slot, how))
@@ -367,6 +367,8 @@ class IngestPlan:
             elif isinstance(how, tuple) and how[0] == "date":
                 if self.counters[how[1]]:
                     a = np.where(a < 0, np.nan, a.astype(np.float64))  # NaT rows
+                elif how[2]:
+                    a = a.astype(np.bool_)  # the is_* parts are booleans
                 elif reference_dtypes:
                     a = a.astype(np.int64)
             elif how == "i32" and reference_dtypes:

@@ -91,7 +91,10 @@ def ingest_columns(steps, df):
         elif kind == "DateExtractor":  # steps.py:593-602
             ts = pd.Series(cols[step.timestamp_col])
             for part in step.parts:
-                v = getattr(ts.dt, part).to_numpy()
+                if part in ("week", "weekofyear"):  # Series.dt lost these accessors; Timestamp.week is the ISO week
+                    v = ts.dt.isocalendar().week.to_numpy().astype(np.int64)
+                else:
+                    v = getattr(ts.dt, part).to_numpy()
                 cols[f"{step.timestamp_col}_{part}"] = v
         elif kind == "DropFeatures":  # steps.py:721-729
             for f in step.features:

@@ -102,11 +102,16 @@ def test_nat_and_wide_date_range():
     secs = rng.integers(-9_000_000_000, 9_000_000_000, size=50_000)  # 1684 .. 2255
     ts = (secs * 1_000_000_000).astype("datetime64[ns]")
     df = pd.DataFrame({"timestamp": ts, "x": rng.normal(size=len(ts)).astype(np.float32)})
-    parts = ["year", "month", "day", "hour", "minute", "second", "day_of_week", "day_of_year", "quarter"]
+    parts = ["year", "month", "day", "hour", "minute", "second", "day_of_week", "day_of_year", "quarter", "is_leap_year",
+             "days_in_month", "is_month_start", "is_month_end", "is_quarter_start", "is_quarter_end", "is_year_start",
+             "is_year_end", "week", "weekofyear"]
     plan = bi.lower_steps([bs.DateExtractor(parts=parts)], df)
     got = plan.run(df)
     want, _ = oi.ingest_columns([ot.DateExtractor(parts=parts)], df)
     _same(got, want)
+    assert got["timestamp_is_leap_year"].dtype == np.bool_ and got["timestamp_week"].between(1, 53).all()
+    rows_want, _ = oi.ingest_rows([ot.DateExtractor(parts=parts)], df.iloc[:300])
+    _same(got.iloc[:300], rows_want)
     df.loc[[3, 77], "timestamp"] = pd.NaT
     got = plan.run(df)
     want, _ = oi.ingest_rows([ot.DateExtractor(parts=["hour", "year"])], df.iloc[:100])

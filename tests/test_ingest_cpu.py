@@ -77,7 +77,7 @@ def test_lowering_rejects_what_the_device_cannot_hold():
     with pytest.raises(LoweringError, match="must be an integer column"):
         bi.FrameProgram(schema).apply(bs.OneHotEncoder(mapping={"x0": [0, 1]}))
     with pytest.raises(LoweringError, match="not computed on the device"):
-        bi.FrameProgram(schema).apply(bs.DateExtractor(parts=["is_leap_year"]))
+        bi.FrameProgram(schema).apply(bs.DateExtractor(parts=["asm8"]))
     with pytest.raises(MLRunInvalidArgumentError, match="doesn't contain a feature named 'nope'"):
         bi.FrameProgram(schema).apply(bs.DropFeatures(features=["nope"]))
     with pytest.raises(MLRunInvalidArgumentError, match="ts does not exist"):
