@@ -7,8 +7,11 @@ Workload (BASELINE.json `metric`): a 3-step serving graph + 4-model ensemble at 
     Imputer(56 numeric cols) -> OneHotEncoder(8 categorical cols x 4) -> VotingEnsemble(4 linear models)
 A "step" is one pass of the fused plan over one batch of B synthetic events already resident in HBM
 (`value`), and -- for `e2e` -- the same call through the public host API with pinned HOST buffers
-(H2D + kernels + D2H inside the timed region).  Other workloads: flow3_linear (configs[1]),
-trees_ens4 (configs[2]).  See DESIGN.md "Measurement".
+(H2D + kernels + D2H inside the timed region).  Other workloads: flow3_linear (configs[1]), trees_ens4 (configs[2], plus a
+`wire` leg: V2 JSON body in, JSON out), ingest6 (configs[4]: feature-set ingest over DataFrame columns), enrich_ens4 (online
+feature table gather + ensemble); `--gpus N` under torchrun is configs[3] (event-sharded router, fused P2P ensemble-merge or
+`--merge nccl`).  Every workload prints the same JSON line (roofline of its dominant kernel, cpu_baseline, e2e) and has a
+`--impl reference` arm.  See DESIGN.md "Measurement".
 """
 
 import argparse
