@@ -258,10 +258,11 @@ class FrameProgram:
 class IngestPlan:
     """the device plan of a FrameProgram + the frame boundary (DataFrame columns <-> slots)"""
 
-    def __init__(self, prog):
+    def __init__(self, prog, finalize=True):
         self.prog = prog
         self.schema = prog.schema
         plan = ColumnsPlan(prog.n_in_slots)
+        self.ops = []  # what was handed to the C-ABI, in order: (kind, source slot, source kind, fill, argument, check)
         self.out = []  # per output column: (name, slot, how, col)
         self.checks = []  # (counter, column name, validator)
         self.miss = []    # (counter, column name, what)
@@ -269,23 +270,28 @@ class IngestPlan:
             chk = None if c.check is None else c.check[:2]
             if c.op is None:
                 slot, cnt = plan.add_copy(c.slot, c.kind, fill=c.fill, keep=True, check=chk)
+                self.ops.append(("copy", c.slot, c.kind, c.fill, None, chk))
                 how = {F32: "f32", I32: "i32", I64: "dt"}[c.kind]
             elif c.op == "range":
                 slot, miss, cnt = plan.add_range_map(c.slot, c.kind, [r[:3] for r in c.arg], fill=c.fill, check=chk)
+                self.ops.append(("range", c.slot, c.kind, c.fill, [r[:3] for r in c.arg], chk))
                 self.miss.append((miss, c.name, "matched no range"))
                 how = ("map", miss, all(isinstance(r[3], (int, np.integer)) and not isinstance(r[3], bool) for r in c.arg))
             elif c.op == "value":
                 slot, miss, cnt = plan.add_value_map(c.slot, c.kind, {k: v for k, v, _ in c.arg}, fill=c.fill, check=chk)
+                self.ops.append(("value", c.slot, c.kind, c.fill, {k: v for k, v, _ in c.arg}, chk))
                 self.miss.append((miss, c.name, "matched no key"))
                 how = ("map", miss, all(isinstance(r[2], (int, np.integer)) and not isinstance(r[2], bool) for r in c.arg))
             elif c.op == "onehot":
                 g = c.group
                 if g.first_out is None:
                     g.first_out, g.miss = plan.add_onehot(g.src.slot, g.src.kind, g.cats, fill=g.src.fill)
+                    self.ops.append(("onehot", g.src.slot, g.src.kind, g.src.fill, list(g.cats), None))
                     self.miss.append((g.miss, g.src.name, "matched no category"))
                 slot, cnt, how = g.first_out + c.arg, -1, "i32"
             else:  # date
                 slot, miss = plan.add_date_part(c.slot, c.arg)
+                self.ops.append(("date", c.slot, I64, None, c.arg, None))
                 self.miss.append((miss, c.name, "NaT"))
                 cnt, how = -1, ("date", miss, c.arg in nat.DATE_BOOL_PARTS)
             if cnt >= 0:
@@ -295,10 +301,11 @@ class IngestPlan:
             chk = c.check[:2]
             if c.op is None:
                 _, cnt = plan.add_copy(c.slot, c.kind, fill=c.fill, keep=False, check=chk)
+                self.ops.append(("check", c.slot, c.kind, c.fill, None, chk))
             else:
                 raise LoweringError(f"validated then dropped mapped column {c.name!r} is not lowered")
             self.checks.append((cnt, c.name, c.check[2]))
-        self.plan = plan.finalize()
+        self.plan = plan.finalize() if finalize else plan
         self.counters = None
         self.violations = {}
         self.unmatched = {}

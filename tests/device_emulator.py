@@ -82,3 +82,75 @@ def predict(models, E):
     for kind, packed in models:
         out.append(linear_predict(packed, E) if kind == "linear" else trees_predict(packed, E))
     return np.stack(out, axis=1)
+
+
+# ------------------------------------------------------------------------------------------ columnar ingest plan
+def run_column_ops(iplan, df):
+    """numpy emulation of columns_kernel over the ops an IngestPlan handed to the C-ABI (mlrun_b200/csrc/b2s_columns.cuh):
+    float32 / int32 words, fp64 compares against fp64 tables, outputs in slot order.  -> (frame, counters dict)"""
+    import pandas as pd
+
+    from mlrun_b200 import _native as nat
+
+    src = {}
+    for name, kind in iplan.schema:
+        a = df[name].to_numpy()
+        if kind == nat.COL_I64:
+            a = a.astype("datetime64[ns]").view(np.int64)
+        elif kind == nat.COL_I32:
+            a = a.astype(np.int32)
+        src[iplan.prog.in_slot[name]] = a
+    outs, bad, miss = [], [], []
+    for kind, slot, skind, fill, arg, check in iplan.ops:
+        a = src[slot]
+        if skind == nat.COL_F32:
+            w = a.astype(np.float32).copy()
+            if fill is not None:
+                w[np.isnan(w)] = np.float32(fill)
+        else:
+            w = a
+        x = w.astype(np.float64) if skind != nat.COL_I64 else None
+        n_miss = None
+        if kind == "copy":
+            outs.append(w)
+        elif kind == "check":
+            pass
+        elif kind in ("range", "value"):
+            val, hit = x.copy(), np.zeros(len(x), dtype=bool)
+            if kind == "range":
+                for lo, hi, v in arg:
+                    inr = (~hit) & (x >= lo) & (x < hi)
+                    val[inr] = v
+                    hit |= inr
+            else:
+                for k, v in arg.items():
+                    inr = (~hit) & (x == k)
+                    val[inr] = v
+                    hit |= inr
+            n_miss = int((~hit).sum())
+            x = val
+            outs.append(val.astype(np.float32))
+        elif kind == "onehot":
+            anyhit = np.zeros(len(x), dtype=bool)
+            for c in arg:
+                col = x == c
+                anyhit |= col
+                outs.append(col.astype(np.int32))
+            n_miss = int((~anyhit).sum())
+        elif kind == "date":
+            ts = pd.Series(a.view("datetime64[ns]"))
+            part = {v: k for k, v in nat.DATE_PARTS.items()}[arg]
+            v = ts.dt.isocalendar().week if part in ("week", "weekofyear") else getattr(ts.dt, part)
+            nat_rows = ts.isna().to_numpy()
+            outs.append(np.where(nat_rows, -1, np.nan_to_num(v.to_numpy(dtype=np.float64), nan=-1)).astype(np.int32))
+            n_miss = int(nat_rows.sum())
+        if n_miss is not None:
+            miss.append(n_miss)
+        if check and (check[0] is not None or check[1] is not None):
+            v = np.zeros(len(x), dtype=bool)
+            if check[0] is not None:
+                v |= x < check[0]
+            if check[1] is not None:
+                v |= x > check[1]
+            bad.append(int(v.sum()))
+    return outs, bad, miss

@@ -102,3 +102,33 @@ def test_feature_set_mirror_resolves_steps_and_fails_loudly_without_a_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(nat.NativeError, match="no CUDA device|CPU fallback"):
         fs.ingest(df)
+
+
+def test_lowered_ops_emulated_on_the_cpu_reproduce_the_oracle_frame():
+    """the arguments that cross the C-ABI (`IngestPlan.ops`), executed by a numpy emulation of columns_kernel
+    (tests/device_emulator.py), give the oracle's frame: the lowering is checked without a GPU"""
+    from tests.device_emulator import run_column_ops
+
+    wl = ingest_workload(n_rows=900, seed=54)
+    prog = bi.FrameProgram(bi.frame_schema(wl.df))
+    for s in wl.build_steps(bs):
+        prog.apply(s)
+    iplan = bi.IngestPlan(prog, finalize=False)
+    outs, bad, miss = run_column_ops(iplan, wl.df)
+    want, viol = oi.ingest_columns(wl.build_steps(ot), wl.df)
+    by_slot = {}
+    slot = 0
+    for kind, _s, skind, _f, arg, _c in iplan.ops:  # output slots are numbered in op order
+        n = {"copy": 2 if skind == nat.COL_I64 else 1, "check": 0, "onehot": len(arg) if kind == "onehot" else 1}.get(kind, 1)
+        for j in range(len(arg) if kind == "onehot" else (1 if kind != "check" else 0)):
+            by_slot[slot + j] = len(by_slot)
+        slot += n
+    for name, s_, how in iplan.out:
+        got = outs[by_slot[s_]]
+        ref = want[name].to_numpy()
+        if how == "dt":
+            np.testing.assert_array_equal(got.view("datetime64[ns]") if got.dtype == np.int64 else got, ref)
+        else:
+            np.testing.assert_array_equal(got.astype(np.float64), ref.astype(np.float64), err_msg=name)
+    assert sum(bad) == sum(viol.values()) > 0
+    assert sum(miss) == int(sum((wl.df[c] == 9).sum() for c in wl.onehot_cols))
