@@ -1121,7 +1121,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
     const int TR2 = kT2TileRows, G2 = kT2Groups, ST2 = 1;  // one row-major landing tile + one transposed tile
     const int NS2 = p->NS <= 1 ? 1 : (p->NS <= 4 ? 4 : 0);
     const size_t part_bytes = (size_t)(G2 - 1) * TR2 * std::max(NS2, 1) * 8;
-    const size_t tiles_bytes = (size_t)ST2 * TR2 * pitch * 4 + (size_t)((n_in + 3) / 4 * 4) * TR2 * 4 + (size_t)TR2 * 4;
+    const size_t tiles_bytes = (size_t)ST2 * TR2 * pitch * 4 + (size_t)((n_in + 3) / 4 * 4) * TR2 * 4 + (size_t)TR2 * 4 + 16 + 1024;  // + mbarrier + alignment slack
     const size_t total2 = align_up(max_table, 16) + align_up(part_bytes, 16) + tiles_bytes;
     if (ok && NS2 > 0 && total2 <= (size_t)smem_cap && M <= sms) {
       BlobBuilder tb;
@@ -1263,8 +1263,12 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
     const int M2 = p->kp.n_models;
     const int grid2 = (int)std::max<int64_t>(M2, std::min<int64_t>(p->t2_grid, tiles2 * M2));
     G.launches.fetch_add(2, std::memory_order_relaxed);
-    if (p->t2_NS == 1) trees_model_kernel<1><<<grid2, p->t2_block, p->t2_smem, st>>>(t);
-    else trees_model_kernel<4><<<grid2, p->t2_block, p->t2_smem, st>>>(t);
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    static const int t2_tma = getenv("B2S_T2_TMA") ? atoi(getenv("B2S_T2_TMA")) : 1;
+    t.use_tmap = (t2_tma && t.vec_ok && (p->n_in % 32) == 0 && encode_rows_map(&tmap, d_rows, n_rows, stride, p->n_in, t.tile_rows)) ? 1 : 0;
+    if (p->t2_NS == 1) trees_model_kernel<1><<<grid2, p->t2_block, p->t2_smem, st>>>(t, tmap);
+    else trees_model_kernel<4><<<grid2, p->t2_block, p->t2_smem, st>>>(t, tmap);
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return fail(B2S_ERR_CUDA, "tree kernel launch failed: %s", cudaGetErrorString(e2));
     const int vgrid = (int)std::max<int64_t>(1, std::min<int64_t>(4 * G.prop.multiProcessorCount, (n_rows + 255) / 256));

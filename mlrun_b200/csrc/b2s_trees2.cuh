@@ -36,6 +36,7 @@ struct T2Params {
   double* pred;        // [n_rows][n_models]
   int32_t* row_bad;    // [n_rows] non-finite input flags (written by the CTAs of model 0)
   int32_t n_in, n_models, tile_rows, pitch, stages, vec_ok, groups;
+  int32_t use_tmap;    // the landing tile is filled by TMA box copies (128-byte swizzle) instead of cp.async
   const T2Model* t2;   // [n_models]
   const ModelDesc* models;
   const int32_t* classes;
@@ -56,7 +57,7 @@ constexpr int kT2Groups = 8;     // tree groups per CTA: thread (g, r) walks tre
 // at; with row-major tiles (pitch = 4 words mod 32) the same gather is a 4-way bank conflict.  Node words of
 // one level are consecutive 4-byte words: lanes at different nodes of a level never conflict either.
 template <int NS>
-__global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant__ T2Params p) {
+__global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant__ T2Params p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x;
   const int m = blockIdx.x % p.n_models;
@@ -82,10 +83,21 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
   for (int i = tid; i < NT * NL; i += blockDim.x) s_leaf[i] = __dmul_rn(tm.scale[i / NL], tm.leaves[i]);
   for (int i = tid; i < NT; i += blockDim.x) s_slot[i] = tm.slot[i];
   double* s_part = reinterpret_cast<double*>(smem + p.sm_part);  // [groups - 1][tile_rows][NS]
-  float* s_stage = reinterpret_cast<float*>(smem + p.sm_tiles);  // row-major landing tile (cp.async)
+  float* s_stage = reinterpret_cast<float*>(smem + p.sm_tiles);  // row-major landing tile (cp.async / TMA boxes)
+  {  // 1024-byte aligned (TMA swizzle atom); the host reserved the slack
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(s_stage);
+    s_stage += ((1024u - (a & 1023u)) & 1023u) >> 2;
+  }
   float* s_xt = s_stage + (size_t)TR * p.pitch;                  // transposed tile [n_in][TR]
   int* s_bad = reinterpret_cast<int*>(s_xt + (size_t)((p.n_in + 3) / 4 * 4) * TR);  // per-row "non-finite input" flags
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bad + TR);                        // mbarrier of the TMA loads
   if (tid < TR) s_bad[tid] = 0;
+  const bool tma = p.use_tmap != 0;
+  if (tma && tid == 0) {
+    mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t tma_phase = 0;
 
   const int64_t n_tiles = (p.n_rows + TR - 1) / TR;
   const int g = tid / TR;  // tree group (warp-uniform: TR is a multiple of 32)
@@ -95,6 +107,14 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
   const int r0 = tid / cprv, c0 = tid - r0 * cprv;
   const int dr = (int)blockDim.x / cprv, dc = (int)blockDim.x - dr * cprv;
   auto issue = [&](int64_t row0) {
+    if (tma) {  // one thread: n_in / 32 box copies of (32 floats x TR rows); rows past the end arrive as zeros
+      if (tid == 0) {
+        const int boxes = p.n_in >> 5;
+        mbar_expect_tx(s_bar, (uint32_t)boxes * (uint32_t)TR * 128u);
+        for (int b = 0; b < boxes; ++b) tensor_load_2d(s_stage + b * TR * 32, &tmap, b * 32, (int)row0, s_bar);
+      }
+      return;
+    }
     int64_t left = p.n_rows - row0;
     const int rows = left < TR ? (left < 0 ? 0 : (int)left) : TR;
     const char* base = p.rows + row0 * p.row_stride;
@@ -113,12 +133,18 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
     }
   };
 
+  if (tma) __syncthreads();  // the barrier is initialised before anybody can wait on it
   if ((int64_t)part < n_tiles) issue((int64_t)part * TR);
   cp_async_commit();
   const char* xt_r = reinterpret_cast<const char*>(s_xt + r);
   const int leaf_bias = NL;  // n - NL is the leaf index
   for (int64_t t = part; t < n_tiles; t += nparts) {
-    cp_async_wait<0>();
+    if (tma) {
+      mbar_wait(s_bar, tma_phase);
+      tma_phase ^= 1u;
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();  // landing tile (and, first time round, the tables) visible; the previous walk is over
     {                 // transpose: lanes take consecutive rows, so both the LDS and the STS are conflict-free
       const int64_t left = p.n_rows - t * TR;
@@ -130,7 +156,9 @@ __global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant_
         for (int i = tid; i < (p.n_in >> 2) * TR; i += blockDim.x) {
           const int c = i / TR, rr = i - c * TR;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rr < rows) v = *reinterpret_cast<const float4*>(s_stage + rr * p.pitch + c * 4);
+          if (rr < rows)
+            v = tma ? *reinterpret_cast<const float4*>(s_stage + (c >> 3) * (TR * 32) + rr * 32 + (((c & 7) ^ (rr & 7)) << 2))
+                    : *reinterpret_cast<const float4*>(s_stage + rr * p.pitch + c * 4);
           bad |= (is_finite_f(v.x) && is_finite_f(v.y) && is_finite_f(v.z) && is_finite_f(v.w)) ? 0 : 1;
           float* o = s_xt + (size_t)(c * 4) * TR + rr;
           o[0] = v.x;
