@@ -45,7 +45,10 @@ struct T2Params {
 };
 
 constexpr int kT2TileRows = 64;  // rows per tile (threads r = 0..63 of a tree group)
-constexpr int kT2Groups = 8;     // tree groups per CTA: thread (g, r) walks trees g, g+8, ... of row r
+#ifndef B2S_T2_GROUPS
+#define B2S_T2_GROUPS 8
+#endif
+constexpr int kT2Groups = B2S_T2_GROUPS;  // tree groups per CTA: thread (g, r) walks trees g, g+G, ... of row r
 
 // Shared-memory layout of one model (built once per CTA from the T2Model arrays):
 //   s_foff[t][1..NI]  byte offset of the node's feature column inside the transposed tile (feature * TR * 4)
@@ -57,7 +60,7 @@ constexpr int kT2Groups = 8;     // tree groups per CTA: thread (g, r) walks tre
 // at; with row-major tiles (pitch = 4 words mod 32) the same gather is a 4-way bank conflict.  Node words of
 // one level are consecutive 4-byte words: lanes at different nodes of a level never conflict either.
 template <int NS>
-__global__ void __launch_bounds__(512) trees_model_kernel(const __grid_constant__ T2Params p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kT2TileRows * kT2Groups) trees_model_kernel(const __grid_constant__ T2Params p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x;
   const int m = blockIdx.x % p.n_models;
