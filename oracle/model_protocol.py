@@ -4,6 +4,11 @@ Follows (behaviour, not text) mlrun/serving/v2_serving.py:
   V2ModelServer :32-426 (do_event :228-342, validate :362-371, _inputs_to_list :391-426),
   _ModelLogPusher :429-504.
 Model-store access (`get_model`) is out of scope: models are in-memory objects or local pickles.
+
+Layout of this restatement: `do_event` resolves (operation, event id) from the path / body, then dispatches to one
+handler per operation family; the scoring families (`predict`-like, `explain`) share `_score`, everything that answers
+without scoring terminates the event.  The tracking-stream writer keeps the reference's two record layouts
+(single event, micro-batch of `values`).
 """
 
 import threading
@@ -11,43 +16,46 @@ import time
 import traceback
 from datetime import datetime, timezone
 
-from .helpers import MLRunInvalidArgumentError, logger
+from .helpers import MLRunInvalidArgumentError, logger  # noqa: F401  (logger re-exported for subclasses)
 from .step_io import StepToDict, _extract_input_data, _update_result_body
+
+_SCORING_OPS = frozenset(("predict", "infer", "infer_dict", "predict_dict"))
+_LOAD_POLLS, _LOAD_POLL_SECONDS = 50, 5
 
 
 def now_date():
     return datetime.now(timezone.utc)
 
 
+def _iso(moment):
+    return moment.isoformat(sep=" ", timespec="microseconds")
+
+
 class V2ModelServer(StepToDict):
     def __init__(self, context=None, name=None, model_path=None, model=None, protocol=None,
                  input_path=None, result_path=None, **kwargs):
-        self.name = name
-        self.version = ""
-        if name and ":" in name:
-            self.name, self.version = name.split(":", 1)
+        base, _, version = (name or "").partition(":")  # "<model>:<version>" keys come from /versions/<ver>/ URLs
+        self.name = base if name else name
+        self.version = version
         self.context = context
-        self.ready = False
-        self.error = ""
         self.protocol = protocol or "v2"
-        self.model_path = model_path
-        self.model_spec = None
-        self._input_path = input_path
-        self._result_path = result_path
-        self._kwargs = kwargs
-        self._params = kwargs
-        self._model_logger = (
-            _ModelLogPusher(self, context) if context and context.stream.enabled else None
-        )
-        self.metrics = {}
-        self.labels = {}
-        self.model = None
-        if model:
-            self.model = model
-            self.ready = True
+        self.model_path, self.model_spec = model_path, None
+        self._input_path, self._result_path = input_path, result_path
+        self._kwargs = self._params = kwargs
+        tracked = bool(context) and context.stream.enabled
+        self._model_logger = _ModelLogPusher(self, context) if tracked else None
+        self.metrics, self.labels = {}, {}
+        self.error = ""
+        self.model = model if model else None
+        self.ready = bool(model)
         self.model_endpoint_uid = None
 
-    def _load_and_update_state(self):
+    # ---- loading (v2_serving.py:124-154; endpoint records are control plane: skipped) -----------------
+    def load(self):
+        if not (self.ready or self.model):
+            raise ValueError("please specify a load method or a model object")
+
+    def _load_now(self):
         try:
             self.load()
         except Exception as exc:
@@ -58,145 +66,37 @@ class V2ModelServer(StepToDict):
         self.context.logger.info(f"model {self.name} was loaded")
 
     def post_init(self, mode="sync"):
-        """v2_serving.py:134-154 (endpoint records are control-plane: skipped)"""
-        if not self.ready:
-            if mode == "async":
-                threading.Thread(target=self._load_and_update_state, daemon=True).start()
-                self.context.logger.info(f"started async model loading for {self.name}")
-            else:
-                self._load_and_update_state()
+        if self.ready:
+            return
+        if mode != "async":
+            self._load_now()
+            return
+        threading.Thread(target=self._load_now, daemon=True).start()
+        self.context.logger.info(f"started async model loading for {self.name}")
 
+    def _await_ready(self, event):
+        """:209-219 -- HTTP callers are refused while loading, stream triggers wait"""
+        if self.ready:
+            return
+        if not event.trigger or event.trigger.kind in ("http", ""):
+            raise RuntimeError(f"model {self.name} is not ready yet")
+        self.context.logger.info(f"waiting for model {self.name} to load")
+        for _ in range(_LOAD_POLLS):
+            time.sleep(_LOAD_POLL_SECONDS)
+            if self.ready:
+                return
+        raise RuntimeError(f"model {self.name} is not ready {self.error}")
+
+    # ---- user surface ------------------------------------------------------------------------------
     def get_param(self, key, default=None):
-        if key in self._params:
-            return self._params.get(key)
-        return self.context.get_param(key, default=default)
+        return self._params[key] if key in self._params else self.context.get_param(key, default=default)
 
     def set_metric(self, name, value):
         self.metrics[name] = value
 
     def get_model(self, suffix=""):
-        """local-file stand-in for mlrun.artifacts.get_model (v2_serving.py:166-202)"""
+        """local-file stand-in for mlrun.artifacts.get_model (:166-202)"""
         return self.model_path, {}
-
-    def load(self):
-        if not self.ready and not self.model:
-            raise ValueError("please specify a load method or a model object")
-
-    def _check_readiness(self, event):
-        """v2_serving.py:209-219"""
-        if self.ready:
-            return
-        if not event.trigger or event.trigger.kind in ["http", ""]:
-            raise RuntimeError(f"model {self.name} is not ready yet")
-        self.context.logger.info(f"waiting for model {self.name} to load")
-        for _ in range(50):
-            time.sleep(5)
-            if self.ready:
-                return
-        raise RuntimeError(f"model {self.name} is not ready {self.error}")
-
-    def _pre_event_processing_actions(self, event, event_body, op):
-        self._check_readiness(event)
-        if "_dict" in op:
-            event_body = self._inputs_to_list(event_body)
-        request = self.preprocess(event_body, op)
-        return self.validate(request, op)
-
-    def do_event(self, event, *args, **kwargs):
-        """v2_serving.py:228-342"""
-        start = now_date()
-        original_body = event.body
-        event_body = _extract_input_data(self._input_path, event.body)
-        event_id = event.id
-        op = event.path.strip("/")
-        if event_body and isinstance(event_body, dict):
-            op = op or event_body.get("operation")
-            event_id = event_body.get("id", event_id)
-        if not op and event.method != "GET":
-            op = "infer"
-
-        if op in ("predict", "infer", "infer_dict", "predict_dict"):
-            request = self._pre_event_processing_actions(event, event_body, op)
-            try:
-                outputs = self.predict(request)
-            except Exception as exc:
-                request["id"] = event_id
-                if self._model_logger:
-                    self._model_logger.push(start, request, op=op, error=exc)
-                raise exc
-            response = {
-                "id": event_id,
-                "model_name": self.name,
-                "outputs": outputs,
-                "timestamp": start.isoformat(sep=" ", timespec="microseconds"),
-            }
-            if self.version:
-                response["model_version"] = self.version
-
-        elif op == "ready" and event.method == "GET":
-            setattr(event, "terminated", True)
-            if self.ready:
-                event.body = self.context.Response(
-                    status_code=200,
-                    body=bytes(f"Model {self.name} is ready (event_id = {event_id})", encoding="utf-8"),
-                )
-            else:
-                event.body = self.context.Response(status_code=408, body=b"model not ready")
-            return event
-
-        elif op == "" and event.method == "GET":
-            setattr(event, "terminated", True)
-            meta = {"name": self.name, "version": self.version, "inputs": [], "outputs": []}
-            if self.model_spec:
-                meta["inputs"] = self.model_spec.inputs.to_dict()
-                meta["outputs"] = self.model_spec.outputs.to_dict()
-            event.body = _update_result_body(self._result_path, original_body, meta)
-            return event
-
-        elif op == "explain":
-            request = self._pre_event_processing_actions(event, event_body, op)
-            try:
-                outputs = self.explain(request)
-            except Exception as exc:
-                request["id"] = event_id
-                if self._model_logger:
-                    self._model_logger.push(start, request, op=op, error=exc)
-                raise exc
-            response = {"id": event_id, "model_name": self.name, "outputs": outputs}
-            if self.version:
-                response["model_version"] = self.version
-
-        elif hasattr(self, "op_" + op):
-            response = getattr(self, "op_" + op)(event)
-            event.body = _update_result_body(self._result_path, original_body, response)
-            return event
-
-        else:
-            raise ValueError(f"illegal model operation {op}, method={event.method}")
-
-        response = self.postprocess(response)
-        if self._model_logger:
-            inputs, outputs = self.logged_results(request, response, op)
-            if inputs is None and outputs is None:
-                self._model_logger.push(start, request, response, op)
-            else:
-                track_request = {"id": event_id, "inputs": inputs or []}
-                track_response = {"outputs": outputs or []}
-                self._model_logger.push(start, track_request, track_response, op)
-        event.body = _update_result_body(self._result_path, original_body, response)
-        return event
-
-    def logged_results(self, request, response, op):
-        return None, None
-
-    def validate(self, request, operation):
-        """v2_serving.py:362-371"""
-        if self.protocol == "v2":
-            if "inputs" not in request:
-                raise Exception('Expected key "inputs" in request body')
-            if not isinstance(request["inputs"], list):
-                raise Exception('Expected "inputs" to be a list')
-        return request
 
     def preprocess(self, request, operation):
         return request
@@ -210,98 +110,158 @@ class V2ModelServer(StepToDict):
     def explain(self, request):
         raise NotImplementedError()
 
+    def logged_results(self, request, response, op):
+        return None, None
+
+    def validate(self, request, operation):
+        """:362-371"""
+        if self.protocol != "v2":
+            return request
+        if "inputs" not in request:
+            raise Exception('Expected key "inputs" in request body')
+        if not isinstance(request["inputs"], list):
+            raise Exception('Expected "inputs" to be a list')
+        return request
+
     def _inputs_to_list(self, request):
-        """v2_serving.py:391-426"""
-        if self.model_spec and self.model_spec.inputs:
-            order = [feature.name for feature in self.model_spec.inputs]
-        else:
+        """:391-426 -- `*_dict` operations: name -> value dicts become rows in model_spec order"""
+        spec = self.model_spec
+        if not (spec and spec.inputs):
             raise MLRunInvalidArgumentError(
                 "In order to use predict_dict or infer_dict operation you have to provide `model_path` "
-                "to the model server and to load it by `load()` function"
-            )
-        inputs = request.get("inputs")
-        try:
-            if isinstance(inputs, list) and all(isinstance(item, dict) for item in inputs):
-                new_inputs = [[d[key] for key in order] for d in inputs]
-            elif isinstance(inputs, dict):
-                new_inputs = [inputs[key] for key in order]
-            else:
-                raise MLRunInvalidArgumentError(
-                    "When using predict_dict or infer_dict operation the inputs must be "
-                    "of type `list[dict]` or `dict`"
-                )
-        except KeyError:
+                "to the model server and to load it by `load()` function")
+        order = [f.name for f in spec.inputs]
+        given = request.get("inputs")
+        many = isinstance(given, list) and all(isinstance(x, dict) for x in given)
+        if not many and not isinstance(given, dict):
             raise MLRunInvalidArgumentError(
-                f"Input dictionary don't contain all the necessary input keys : {order}"
-            )
-        request["inputs"] = new_inputs
+                "When using predict_dict or infer_dict operation the inputs must be of type `list[dict]` or `dict`")
+        try:
+            request["inputs"] = [[row[k] for k in order] for row in given] if many else [given[k] for k in order]
+        except KeyError:
+            raise MLRunInvalidArgumentError(f"Input dictionary don't contain all the necessary input keys : {order}")
         return request
+
+    # ---- the event handler (:228-342) ----------------------------------------------------------------
+    def do_event(self, event, *args, **kwargs):
+        started = now_date()
+        whole = event.body
+        body = _extract_input_data(self._input_path, whole)
+        op, event_id = event.path.strip("/"), event.id
+        if body and isinstance(body, dict):
+            op = op or body.get("operation")
+            event_id = body.get("id", event_id)
+        if not op and event.method != "GET":
+            op = "infer"
+        is_get = event.method == "GET"
+
+        if op in _SCORING_OPS or op == "explain":
+            response, request = self._score(event, body, op, event_id, started)
+            response = self.postprocess(response)
+            self._track(started, request, response, op, event_id)
+        elif is_get and op == "ready":
+            return self._answer_ready(event, event_id)
+        elif is_get and op == "":
+            response = self._describe(event)
+        elif hasattr(self, "op_" + op):
+            response = getattr(self, "op_" + op)(event)
+        else:
+            raise ValueError(f"illegal model operation {op}, method={event.method}")
+        event.body = _update_result_body(self._result_path, whole, response)
+        return event
+
+    def _score(self, event, body, op, event_id, started):
+        self._await_ready(event)
+        if "_dict" in op:
+            body = self._inputs_to_list(body)
+        request = self.validate(self.preprocess(body, op), op)
+        run = self.explain if op == "explain" else self.predict
+        try:
+            outputs = run(request)
+        except Exception as exc:
+            request["id"] = event_id
+            if self._model_logger:
+                self._model_logger.push(started, request, op=op, error=exc)
+            raise exc
+        response = {"id": event_id, "model_name": self.name, "outputs": outputs}
+        if op != "explain":
+            response["timestamp"] = _iso(started)
+        if self.version:
+            response["model_version"] = self.version
+        return response, request
+
+    def _track(self, started, request, response, op, event_id):
+        if not self._model_logger:
+            return
+        inputs, outputs = self.logged_results(request, response, op)
+        if inputs is None and outputs is None:
+            self._model_logger.push(started, request, response, op)
+        else:
+            self._model_logger.push(started, {"id": event_id, "inputs": inputs or []}, {"outputs": outputs or []}, op)
+
+    def _answer_ready(self, event, event_id):
+        event.terminated = True
+        if self.ready:
+            text = f"Model {self.name} is ready (event_id = {event_id})"
+            event.body = self.context.Response(status_code=200, body=bytes(text, encoding="utf-8"))
+        else:
+            event.body = self.context.Response(status_code=408, body=b"model not ready")
+        return event
+
+    def _describe(self, event):
+        event.terminated = True
+        spec = self.model_spec
+        return {"name": self.name, "version": self.version,
+                "inputs": spec.inputs.to_dict() if spec else [], "outputs": spec.outputs.to_dict() if spec else []}
 
 
 class _ModelLogPusher:
-    """v2_serving.py:429-504"""
+    """:429-504 -- sampling (`log_stream_sample`), micro-batching (`log_stream_batch`), record layout"""
+
+    _BATCH_HEADERS = ["request", "op", "resp", "when", "microsec", "metrics"]
 
     def __init__(self, model, context, output_stream=None):
         self.model = model
         self.verbose = context.verbose
-        self.hostname = context.stream.hostname
-        self.function_uri = context.stream.function_uri
-        self.stream_path = context.stream.stream_uri
+        stream = context.stream
+        self.hostname, self.function_uri, self.stream_path = stream.hostname, stream.function_uri, stream.stream_uri
         self.stream_batch = int(context.get_param("log_stream_batch", 1))
         self.stream_sample = int(context.get_param("log_stream_sample", 1))
-        self.output_stream = output_stream or context.stream.output_stream
+        self.output_stream = output_stream or stream.output_stream
         self._worker = context.worker_id
-        self._sample_iter = 0
-        self._batch_iter = 0
+        self._sample_iter = self._batch_iter = 0
         self._batch = []
 
     def base_data(self):
-        data = {
-            "class": self.model.__class__.__name__,
-            "worker": self._worker,
-            "model": self.model.name,
-            "version": self.model.version,
-            "host": self.hostname,
-            "function_uri": self.function_uri,
-        }
-        if getattr(self.model, "labels", None):
-            data["labels"] = self.model.labels
-        return data
+        m = self.model
+        record = {"class": type(m).__name__, "worker": self._worker, "model": m.name, "version": m.version,
+                  "host": self.hostname, "function_uri": self.function_uri}
+        if getattr(m, "labels", None):
+            record["labels"] = m.labels
+        return record
+
+    def _emit(self, **fields):
+        record = self.base_data()
+        record.update(fields)
+        self.output_stream.push([record])
 
     def push(self, start, request, resp=None, op=None, error=None):
-        start_str = start.isoformat(sep=" ", timespec="microseconds")
+        when = _iso(start)
         if error:
-            data = self.base_data()
-            data["request"] = request
-            data["op"] = op
-            data["when"] = start_str
-            message = str(error)
-            if self.verbose:
-                message = f"{message}\n{traceback.format_exc()}"
-            data["error"] = message
-            self.output_stream.push([data])
+            text = f"{error}\n{traceback.format_exc()}" if self.verbose else str(error)
+            self._emit(request=request, op=op, when=when, error=text)
             return
-
         self._sample_iter = (self._sample_iter + 1) % self.stream_sample
-        if self.output_stream and self._sample_iter == 0:
-            microsec = (now_date() - start).microseconds
-            if self.stream_batch > 1:
-                if self._batch_iter == 0:
-                    self._batch = []
-                self._batch.append([request, op, resp, str(start), microsec, self.model.metrics])
-                self._batch_iter = (self._batch_iter + 1) % self.stream_batch
-                if self._batch_iter == 0:
-                    data = self.base_data()
-                    data["headers"] = ["request", "op", "resp", "when", "microsec", "metrics"]
-                    data["values"] = self._batch
-                    self.output_stream.push([data])
-            else:
-                data = self.base_data()
-                data["request"] = request
-                data["op"] = op
-                data["resp"] = resp
-                data["when"] = start_str
-                data["microsec"] = microsec
-                if getattr(self.model, "metrics", None):
-                    data["metrics"] = self.model.metrics
-                self.output_stream.push([data])
+        if self._sample_iter or not self.output_stream:
+            return
+        microsec = (now_date() - start).microseconds
+        if self.stream_batch <= 1:
+            extra = {"metrics": self.model.metrics} if getattr(self.model, "metrics", None) else {}
+            self._emit(request=request, op=op, resp=resp, when=when, microsec=microsec, **extra)
+            return
+        if self._batch_iter == 0:
+            self._batch = []
+        self._batch.append([request, op, resp, str(start), microsec, self.model.metrics])
+        self._batch_iter = (self._batch_iter + 1) % self.stream_batch
+        if self._batch_iter == 0:
+            self._emit(headers=list(self._BATCH_HEADERS), values=self._batch)
