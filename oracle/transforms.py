@@ -5,11 +5,14 @@ Follows (behaviour, not text) mlrun/feature_store/steps.py:
   FeaturesetValidator :94-149 (+ MinMaxValidator.check, mlrun/features.py:292-321),
   MapValues :152-246, Imputer :377-413, OneHotEncoder :427-513, DateExtractor :516-612,
   SetEventMetadata :635-696, DropFeatures :699-753.  `_do_spark` is out of scope.
+
+Every step has the reference's two row engines: `_do_storey(event_dict)` (one event at a time) and
+`_do_pandas(frame)`; `do` picks one from the first payload it sees and keeps it.  Quirks that are part of the observable
+behaviour are kept and marked QUIRK.
 """
 
 import re
 import uuid
-from collections import OrderedDict
 
 import numpy as np
 import pandas as pd
@@ -20,28 +23,27 @@ from .topology import MapClass
 
 
 def get_engine(first_event):
-    if hasattr(first_event, "body"):
-        first_event = first_event.body
-    if isinstance(first_event, pd.DataFrame):
+    payload = getattr(first_event, "body", first_event)
+    if isinstance(payload, pd.DataFrame):
         return "pandas"
-    if hasattr(first_event, "rdd"):
-        return "spark"
-    return "storey"
+    return "spark" if hasattr(payload, "rdd") else "storey"
 
 
 class MLRunStep(MapClass):
+    """engine dispatch shared by the steps"""
+
     def __init__(self, **kwargs):
         super().__init__(**kwargs)
         self._engine_to_do_method = {"pandas": self._do_pandas, "storey": self._do_storey}
 
     def do(self, event):
         engine = get_engine(event)
-        self.do = self._engine_to_do_method.get(engine, None)
-        if self.do is None:
+        handler = self._engine_to_do_method.get(engine)
+        if handler is None:
             raise MLRunInvalidArgumentError(
-                f"Unrecognized engine: {engine}. Available engines are: pandas, spark and storey"
-            )
-        return self.do(event)
+                f"Unrecognized engine: {engine}. Available engines are: pandas, spark and storey")
+        self.do = handler  # QUIRK: the instance method is replaced; later payloads never re-select the engine
+        return handler(event)
 
     def _do_pandas(self, event):
         raise NotImplementedError
@@ -50,20 +52,20 @@ class MLRunStep(MapClass):
         raise NotImplementedError
 
 
+# ------------------------------------------------------------------------------------------ validation
 class MinMaxValidator:
     """mlrun/features.py:228-321 (check only)"""
 
     def __init__(self, check_type=None, severity=None, min=None, max=None):
-        self.check_type = check_type
-        self.severity = severity or "info"
-        self.min = min
-        self.max = max
+        self.check_type, self.severity = check_type, severity or "info"
+        self.min, self.max = min, max
 
     def check(self, value):
-        if self.min is not None and value is not None and value < self.min:
-            return False, {"message": "value is smaller than min", "min": self.min, "value": value}
-        if self.max is not None and value is not None and value > self.max:
-            return False, {"message": "value is greater than max", "max": self.max, "value": value}
+        if value is not None:
+            if self.min is not None and value < self.min:
+                return False, {"message": "value is smaller than min", "min": self.min, "value": value}
+            if self.max is not None and value > self.max:
+                return False, {"message": "value is greater than max", "max": self.max, "value": value}
         return True, {}
 
 
@@ -72,235 +74,215 @@ class FeaturesetValidator(StepToDict, MLRunStep):
     validators directly (`validators={col: MinMaxValidator}`) instead of a feature-set URI."""
 
     def __init__(self, featureset=None, columns=None, name=None, validators=None, **kwargs):
-        kwargs["full_event"] = True
-        super().__init__(**kwargs)
+        super().__init__(**dict(kwargs, full_event=True))
         self.featureset = featureset or "."
-        self.columns = columns
-        self.name = name
+        self.columns, self.name = columns, name
         self._validators = dict(validators or {})
         self.violations = 0
 
     def _do_storey(self, event):
-        body = event.body
-        for name, validator in self._validators.items():
-            if name in body:
-                ok, args = validator.check(body[name])
-                if not ok:
-                    self.violations += 1
-                    message = args.pop("message")
-                    key_text = f" key={event.key}" if event.key else ""
-                    print(f"{validator.severity}! {name} {message},{key_text} args={args}")
+        row = event.body
+        where = f" key={event.key}" if event.key else ""
+        for column, rule in self._validators.items():
+            if column not in row:
+                continue
+            passed, details = rule.check(row[column])
+            if passed:
+                continue
+            self.violations += 1
+            what = details.pop("message")
+            print(f"{rule.severity}! {column} {what},{where} args={details}")
         return event
 
     def _do_pandas(self, event):
-        body = event.body
-        for column in body:
-            validator = self._validators.get(column, None)
-            if validator:
-                violations, all_args, message = 0, [], ""
-                for i in body.index:
-                    ok, args = validator.check(body.at[i, column])
-                    if not ok:
-                        violations += 1
-                        all_args.append(args)
-                        message = args.pop("message")
-                if violations:
-                    self.violations += violations
-                    print(f"{validator.severity}! {column} {message}, column={column}, has {violations} violations args={all_args}")
+        frame = event.body
+        for column in frame:
+            rule = self._validators.get(column)
+            if not rule:
+                continue
+            failures = [d for ok, d in (rule.check(frame.at[i, column]) for i in frame.index) if not ok]
+            if not failures:
+                continue
+            what = ""
+            for d in failures:  # the report carries the LAST failure's message, and the details without it
+                what = d.pop("message")
+            self.violations += len(failures)
+            print(f"{rule.severity}! {column} {what}, column={column}, has {len(failures)} violations args={failures}")
         return event
+
+
+# ------------------------------------------------------------------------------------------ value maps
+def _bounds(pair):
+    """only these two spellings are understood: "-inf" as a lower and "inf" as an upper bound"""
+    lo, hi = pair[0], pair[1]
+    return (-np.inf if isinstance(lo, str) and lo == "-inf" else lo), (np.inf if isinstance(hi, str) and hi == "inf" else hi)
 
 
 class MapValues(StepToDict, MLRunStep):
     def __init__(self, mapping, with_original_features=False, suffix="mapped", **kwargs):
         super().__init__(**kwargs)
-        self.mapping = mapping
-        self.with_original_features = with_original_features
-        self.suffix = suffix
-
-    def _map_value(self, feature, value):
-        """ranges: first [lo, hi) hit in dict order; else dict.get(value, value) (steps.py:189-201)"""
-        feature_map = self.mapping.get(feature, {})
-        if "ranges" in feature_map:
-            for val, val_range in feature_map.get("ranges", {}).items():
-                lo = val_range[0] if val_range[0] != "-inf" else -np.inf
-                hi = val_range[1] if val_range[1] != "inf" else np.inf
-                if value >= lo and value < hi:
-                    return val
-        return feature_map.get(value, value)
+        self.mapping, self.with_original_features, self.suffix = mapping, with_original_features, suffix
 
     def _get_feature_name(self, feature):
         return f"{feature}_{self.suffix}" if self.with_original_features else feature
 
+    def _map_value(self, feature, value):
+        """ranges: first [lo, hi) hit in dict order; else dict.get(value, value) (steps.py:189-201)"""
+        rules = self.mapping.get(feature, {})
+        for label, pair in (rules.get("ranges", {}) if "ranges" in rules else {}).items():
+            lo, hi = _bounds(pair)
+            if lo <= value < hi:
+                return label
+        return rules.get(value, value)
+
     def _do_storey(self, event):
-        mapped = {
-            self._get_feature_name(f): self._map_value(f, v) for f, v in event.items() if f in self.mapping
-        }
+        out = {self._get_feature_name(k): self._map_value(k, v) for k, v in event.items() if k in self.mapping}
         if self.with_original_features:
-            mapped.update(event)
-        return mapped
+            out.update(event)
+        return out
 
     def _do_pandas(self, event):
         """closed="both" ranges; unmapped -> None (steps.py:218-246)"""
-        df = pd.DataFrame(index=event.index)
-        for feature in event.columns:
-            feature_map = self.mapping.get(feature, {})
-            if "ranges" in feature_map:
-                for val, val_range in feature_map.get("ranges", {}).items():
-                    lo = val_range[0] if val_range[0] != "-inf" else -np.inf
-                    hi = val_range[1] if val_range[1] != "inf" else np.inf
-                    feature_map["ranges"][val] = [lo, hi]
-                matchdf = pd.DataFrame.from_dict(feature_map["ranges"], "index").reset_index()
-                matchdf.index = pd.IntervalIndex.from_arrays(left=matchdf[0], right=matchdf[1], closed="both")
-                df[self._get_feature_name(feature)] = matchdf.loc[event[feature]]["index"].values
-            elif feature_map:
-                df[self._get_feature_name(feature)] = event[feature].map(lambda x: feature_map.get(x, None))
-        if self.with_original_features:
-            df = pd.concat([event, df], axis=1)
-        return df
+        mapped = pd.DataFrame(index=event.index)
+        for column in event.columns:
+            rules = self.mapping.get(column, {})
+            target = self._get_feature_name(column)
+            if "ranges" in rules:
+                for label in list(rules["ranges"]):  # QUIRK: the user's mapping is rewritten with numeric bounds
+                    rules["ranges"][label] = list(_bounds(rules["ranges"][label]))
+                table = pd.DataFrame.from_dict(rules["ranges"], "index").reset_index()
+                table.index = pd.IntervalIndex.from_arrays(left=table[0], right=table[1], closed="both")
+                mapped[target] = table.loc[event[column]]["index"].values
+            elif rules:
+                mapped[target] = event[column].map(lambda v, _r=rules: _r.get(v, None))
+        return pd.concat([event, mapped], axis=1) if self.with_original_features else mapped
 
 
+# ------------------------------------------------------------------------------------------ imputing
 class Imputer(StepToDict, MLRunStep):
     def __init__(self, method="avg", default_value=None, mapping=None, **kwargs):
         super().__init__(**kwargs)
-        self.mapping = mapping or {}
-        self.method = method
-        self.default_value = default_value
+        self.mapping, self.method, self.default_value = mapping or {}, method, default_value
 
     def _impute(self, feature, value):
-        if pd.isna(value):
-            return self.mapping.get(feature, self.default_value)
-        return value
+        return self.mapping.get(feature, self.default_value) if pd.isna(value) else value
 
     def _do_storey(self, event):
         """every feature of the dict is imputed (steps.py:397-406)"""
-        return {feature: self._impute(feature, val) for feature, val in event.items()}
+        return {k: self._impute(k, v) for k, v in event.items()}
 
     def _do_pandas(self, event):
         """columns whose fill is None are skipped (steps.py:408-413); the reference's in-place
         chained fillna is a no-op under pandas copy-on-write, so assign the filled column back"""
-        for feature in event.columns:
-            val = self.mapping.get(feature, self.default_value)
-            if val is not None:
-                event[feature] = event[feature].fillna(val)
+        fills = {c: self.mapping.get(c, self.default_value) for c in event.columns}
+        for column, fill in fills.items():
+            if fill is not None:
+                event[column] = event[column].fillna(fill)
         return event
 
 
+# ------------------------------------------------------------------------------------------ one-hot
 class OneHotEncoder(StepToDict, MLRunStep):
     def __init__(self, mapping, **kwargs):
         super().__init__(**kwargs)
         self.mapping = mapping
-        for key, values in mapping.items():
-            for val in values:
-                if not (isinstance(val, str) or isinstance(val, (int, np.integer))):
-                    raise MLRunInvalidArgumentError(
-                        "For OneHotEncoder you must provide int or string mapping list"
-                    )
-            mapping[key] = list(OrderedDict.fromkeys(values).keys())
-
-    def _encode(self, feature, value):
-        """steps.py:453-471"""
-        encoding = self.mapping.get(feature, [])
-        if encoding:
-            one_hot = {f"{feature}_{OneHotEncoder._sanitized_category(c)}": 0 for c in encoding}
-            if value in encoding:
-                one_hot[f"{feature}_{OneHotEncoder._sanitized_category(value)}"] = 1
-            elif self.logger:
-                self.logger.warn(
-                    f"OneHotEncoder does not have an encoding for value '{value}' of feature '{feature}'"
-                )
-            return one_hot
-        return {feature: value}
-
-    def _do_storey(self, event):
-        encoded = {}
-        for feature, val in event.items():
-            encoded.update(self._encode(feature, val))
-        return encoded
-
-    def _do_pandas(self, event):
-        """steps.py:480-491"""
-        for key, values in self.mapping.items():
-            event[key] = pd.Categorical(event[key], categories=list(values))
-            encoded = pd.get_dummies(event[key], prefix=key, dtype=np.int64)
-            encoded.rename(columns={n: OneHotEncoder._sanitized_category(n) for n in encoded.columns}, inplace=True)
-            event = pd.concat([event.loc[:, :key], encoded, event.loc[:, key:]], axis=1)
-        event.drop(columns=list(self.mapping.keys()), inplace=True)
-        return event
+        for feature in list(mapping):
+            categories = mapping[feature]
+            if not all(isinstance(c, (str, int, np.integer)) for c in categories):
+                raise MLRunInvalidArgumentError("For OneHotEncoder you must provide int or string mapping list")
+            mapping[feature] = list(dict.fromkeys(categories))  # de-duplicated in place, first occurrence wins
 
     @staticmethod
     def _sanitized_category(category):
-        if isinstance(category, str):
-            return re.sub("[ -]", "_", category)
-        return category
+        return re.sub("[ -]", "_", category) if isinstance(category, str) else category
+
+    def _encode(self, feature, value):
+        """steps.py:453-471"""
+        categories = self.mapping.get(feature, [])
+        if not categories:
+            return {feature: value}
+        key = lambda c: f"{feature}_{self._sanitized_category(c)}"  # noqa: E731
+        fields = dict.fromkeys(map(key, categories), 0)
+        if value in categories:
+            fields[key(value)] = 1  # QUIRK: keyed by the VALUE's spelling -- 2.0 matching category 2 adds "<f>_2.0"
+        elif self.logger:
+            self.logger.warn(f"OneHotEncoder does not have an encoding for value '{value}' of feature '{feature}'")
+        return fields
+
+    def _do_storey(self, event):
+        out = {}
+        for feature, value in event.items():
+            out.update(self._encode(feature, value))
+        return out
+
+    def _do_pandas(self, event):
+        """steps.py:480-491"""
+        for feature, categories in self.mapping.items():
+            event[feature] = pd.Categorical(event[feature], categories=list(categories))
+            dummies = pd.get_dummies(event[feature], prefix=feature, dtype=np.int64)
+            dummies = dummies.rename(columns={c: self._sanitized_category(c) for c in dummies.columns})
+            event = pd.concat([event.loc[:, :feature], dummies, event.loc[:, feature:]], axis=1)
+        return event.drop(columns=list(self.mapping))
 
 
+# ------------------------------------------------------------------------------------------ dates, metadata, drop
 class DateExtractor(StepToDict, MLRunStep):
     def __init__(self, parts, timestamp_col=None, **kwargs):
         super().__init__(**kwargs)
-        self.timestamp_col = timestamp_col if timestamp_col else "timestamp"
-        self.parts = parts
+        self.timestamp_col, self.parts = timestamp_col or "timestamp", parts
 
     def _get_key_name(self, part):
         return f"{self.timestamp_col}_{part}"
 
     def _extract_timestamp(self, event):
-        try:
-            return event[self.timestamp_col]
-        except KeyError:
+        if self.timestamp_col not in event:
             raise MLRunInvalidArgumentError(f"{self.timestamp_col} does not exist in the event")
+        return event[self.timestamp_col]
 
     def _do_storey(self, event):
-        timestamp = pd.Timestamp(self._extract_timestamp(event))
-        for part in self.parts:
-            event[self._get_key_name(part)] = getattr(timestamp, part)
+        moment = pd.Timestamp(self._extract_timestamp(event))
+        event.update({self._get_key_name(p): getattr(moment, p) for p in self.parts})
         return event
 
     def _do_pandas(self, event):
-        timestamp = self._extract_timestamp(event)
+        column = self._extract_timestamp(event)
         for part in self.parts:
-            event[self._get_key_name(part)] = timestamp.map(lambda x: getattr(pd.Timestamp(x), part))
+            event[self._get_key_name(part)] = column.map(lambda v, _p=part: getattr(pd.Timestamp(v), _p))
         return event
 
 
 class SetEventMetadata(MapClass):
+    """copies id / key from body paths onto the event, or draws a random id (steps.py:635-696)"""
+
+    _FIELDS = ("id_path", "key_path", "random_id")
+
     def __init__(self, id_path=None, key_path=None, random_id=None, **kwargs):
-        kwargs["full_event"] = True
-        super().__init__(**kwargs)
-        self.id_path = id_path
-        self.key_path = key_path
-        self.random_id = random_id
+        super().__init__(**dict(kwargs, full_event=True))
+        self.id_path, self.key_path, self.random_id = id_path, key_path, random_id
         self._tagging_funcs = []
 
     def to_dict(self, *a, **k):
-        return {
-            "class_name": f"{self.__class__.__module__}.{self.__class__.__qualname__}",
-            "name": self.name or self.__class__.__name__,
-            "class_args": {k: v for k, v in (("id_path", self.id_path), ("key_path", self.key_path),
-                                               ("random_id", self.random_id)) if v is not None},
-            "full_event": True,
-        }
+        cls = type(self)
+        args = {f: getattr(self, f) for f in self._FIELDS if getattr(self, f) is not None}
+        return {"class_name": f"{cls.__module__}.{cls.__qualname__}", "name": self.name or cls.__name__,
+                "class_args": args, "full_event": True}
 
     def post_init(self, mode="sync"):
-        def add_metadata(name, path, operator=str):
-            def _add_meta(event):
-                setattr(event, name, operator(get_in(event.body, path)))
+        def from_body(attr, path):
+            return lambda event: setattr(event, attr, str(get_in(event.body, path)))
 
-            return _add_meta
-
-        def set_random_id(event):
-            event.id = uuid.uuid4().hex
-
-        self._tagging_funcs = []
+        steps = []
         if self.id_path:
-            self._tagging_funcs.append(add_metadata("id", self.id_path))
+            steps.append(from_body("id", self.id_path))
         if self.key_path:
-            self._tagging_funcs.append(add_metadata("key", self.key_path))
+            steps.append(from_body("key", self.key_path))
         if self.random_id:
-            self._tagging_funcs.append(set_random_id)
+            steps.append(lambda event: setattr(event, "id", uuid.uuid4().hex))
+        self._tagging_funcs = steps
 
     def do(self, event):
-        for func in self._tagging_funcs:
-            func(event)
+        for tag in self._tagging_funcs:
+            tag(event)
         return event
 
 
@@ -311,12 +293,9 @@ class DropFeatures(StepToDict, MLRunStep):
 
     def _do_storey(self, event):
         for feature in self.features:
-            try:
-                del event[feature]
-            except KeyError:
-                raise MLRunInvalidArgumentError(
-                    f"The ingesting data doesn't contain a feature named '{feature}'"
-                )
+            if feature not in event:
+                raise MLRunInvalidArgumentError(f"The ingesting data doesn't contain a feature named '{feature}'")
+            del event[feature]
         return event
 
     def _do_pandas(self, event):
