@@ -6,6 +6,10 @@ Follows (behaviour, not text) mlrun/serving/routers.py:
   logic :746-787, _apply_logic :789-810, do_event :812-914, _normalize_weights :962-991).
 Process-pool execution (routers.py:378-396) is out of scope for the oracle; "process" falls back to
 the thread pool (same results, same key-order caveat).
+
+Layout of this restatement: every router's `do_event` is `_enter` (input path, preprocess hook, body parsing, health /
+prefix checks) + a class-specific middle + `_leave` (result path); URL targets are split once by `_target_segments`.
+Behavioural quirks of the reference that callers can observe are kept and marked QUIRK.
 """
 
 import concurrent.futures
@@ -25,63 +29,21 @@ from .step_io import RouterToDict, _extract_input_data, _update_result_body
 class BaseModelRouter(RouterToDict):
     def __init__(self, context=None, name=None, routes=None, protocol=None, url_prefix=None,
                  health_prefix=None, input_path=None, result_path=None, **kwargs):
-        self.name = name
-        self.context = context
-        self.routes = routes
+        self.name, self.context, self.routes = name, context, routes
         self.protocol = protocol or "v2"
-        self.url_prefix = url_prefix or f"/{self.protocol}/models"
-        self.health_prefix = health_prefix or f"/{self.protocol}/health"
-        self.inputs_key = "instances" if self.protocol == "v1" else "inputs"
-        self._input_path = input_path
-        self._result_path = result_path
+        root = f"/{self.protocol}"
+        self.url_prefix = url_prefix or f"{root}/models"
+        self.health_prefix = health_prefix or f"{root}/health"
+        self.inputs_key = "inputs" if self.protocol != "v1" else "instances"
+        self._input_path, self._result_path = input_path, result_path
         self.kwargs = kwargs
 
-    def parse_event(self, event):
-        """routers.py:86-112 (data_url download is I/O: out of scope)"""
-        parsed = {}
-        try:
-            body = event.body if isinstance(event.body, dict) else json.loads(event.body)
-            parsed = body
-        except Exception as exc:
-            content_type = getattr(event, "content_type", "") or ""
-            if content_type.startswith("image/"):
-                parsed[self.inputs_key] = [BytesIO(event.body)]
-            else:
-                raise ValueError("Unrecognized request format") from exc
-        return parsed
-
+    # ---- hooks ------------------------------------------------------------------------------------
     def post_init(self, mode="sync"):
         self.context.logger.info(f"Loaded {list(self.routes.keys())}")
 
     def get_metadata(self):
-        return {"name": self.__class__.__name__, "version": "v2", "extensions": []}
-
-    def _pre_handle_event(self, event):
-        """routers.py:122-141"""
-        method = event.method or "POST"
-        if event.body and method != "GET":
-            event.body = self.parse_event(event)
-        urlpath = getattr(event, "path", "")
-        if method == "GET" and (urlpath == "/" or urlpath.startswith(self.health_prefix)):
-            setattr(event, "terminated", True)
-            event.body = self.get_metadata()
-            return event
-        if urlpath and not urlpath.startswith(self.url_prefix) and not urlpath == "/":
-            raise ValueError(f"illegal path prefix {urlpath}, must start with {self.url_prefix}")
-        return event
-
-    def do_event(self, event, *args, **kwargs):
-        original_body = event.body
-        event.body = _extract_input_data(self._input_path, event.body)
-        event = self.preprocess(event)
-        event = self._pre_handle_event(event)
-        if not getattr(event, "terminated", None):
-            event = self.postprocess(self._handle_event(event))
-        event.body = _update_result_body(self._result_path, original_body, event.body)
-        return event
-
-    def _handle_event(self, event):
-        return event
+        return {"name": type(self).__name__, "version": "v2", "extensions": []}
 
     def preprocess(self, event):
         return event
@@ -89,43 +51,84 @@ class BaseModelRouter(RouterToDict):
     def postprocess(self, event):
         return event
 
+    def _handle_event(self, event):
+        return event
+
+    # ---- shared prologue / epilogue -------------------------------------------------------------------
+    def parse_event(self, event):
+        """routers.py:86-112 (data_url download is I/O: out of scope)"""
+        raw = event.body
+        try:
+            return raw if isinstance(raw, dict) else json.loads(raw)
+        except Exception as exc:
+            if (getattr(event, "content_type", "") or "").startswith("image/"):
+                return {self.inputs_key: [BytesIO(raw)]}
+            raise ValueError("Unrecognized request format") from exc
+
+    def _pre_handle_event(self, event):
+        """routers.py:122-141 -- body parsing, health / metadata answers, prefix check"""
+        is_get = (event.method or "POST") == "GET"
+        if event.body and not is_get:
+            event.body = self.parse_event(event)
+        path = getattr(event, "path", "")
+        if is_get and (path == "/" or path.startswith(self.health_prefix)):
+            event.terminated = True
+            event.body = self.get_metadata()
+        elif path and path != "/" and not path.startswith(self.url_prefix):
+            raise ValueError(f"illegal path prefix {path}, must start with {self.url_prefix}")
+        return event
+
+    def _enter(self, event):
+        whole = event.body
+        event.body = _extract_input_data(self._input_path, whole)
+        return whole, self._pre_handle_event(self.preprocess(event))
+
+    def _leave(self, event, whole, payload):
+        event.body = _update_result_body(self._result_path, whole, payload)
+        return event
+
+    def _target_segments(self, urlpath):
+        """path below the url prefix, split on "/" ([] when nothing follows the prefix)"""
+        rest = urlpath[len(self.url_prefix):].strip("/")
+        return rest.split("/") if rest else []
+
+    def do_event(self, event, *args, **kwargs):
+        whole, event = self._enter(event)
+        if not getattr(event, "terminated", None):
+            event = self.postprocess(self._handle_event(event))
+        return self._leave(event, whole, event.body)
+
 
 class ModelRouter(BaseModelRouter):
     def _resolve_route(self, body, urlpath):
-        """routers.py:168-197"""
-        subpath = None
-        model = ""
-        if urlpath and not urlpath == "/":
-            subpath = ""
-            urlpath = urlpath[len(self.url_prefix):].strip("/")
-            if not urlpath:
+        """routers.py:168-197 -> (model key, route step | None, operation)"""
+        model, op = "", None
+        if urlpath and urlpath != "/":
+            parts = self._target_segments(urlpath)
+            if not parts:
                 return "", None, ""
-            segments = urlpath.split("/")
-            model = segments[0]
-            if len(segments) > 2 and segments[1] == "versions":
-                model = model + ":" + segments[2]
-                segments = segments[2:]
-            if len(segments) > 1:
-                subpath = "/".join(segments[1:])
+            model = parts[0]
+            if len(parts) > 2 and parts[1] == "versions":
+                model, parts = f"{model}:{parts[2]}", parts[2:]
+            op = "/".join(parts[1:])
         if isinstance(body, dict):
             model = model or body.get("model", list(self.routes.keys())[0])
-            subpath = body.get("operation", subpath)
-        if subpath is None:
-            subpath = "infer"
+            op = body.get("operation", op)
+        if op is None:
+            op = "infer"
         if model not in self.routes:
-            models = " | ".join(self.routes.keys())
-            raise ValueError(f"model {model} doesnt exist, available models: {models}")
-        return model, self.routes[model], subpath
+            raise ValueError(f"model {model} doesnt exist, available models: {' | '.join(self.routes.keys())}")
+        return model, self.routes[model], op
 
     def _handle_event(self, event):
-        name, route, subpath = self._resolve_route(event.body, event.path)
+        _name, route, op = self._resolve_route(event.body, event.path)
         if not route:
-            setattr(event, "terminated", True)
+            event.terminated = True
             event.body = {"models": list(self.routes.keys())}
             return event
-        event.path = subpath
-        response = route.run(event)
-        event.body = response.body if response else None
+        event.path = op
+        answer = route.run(event)
+        event.body = answer.body if answer else None
         return event
 
 
@@ -160,65 +163,59 @@ class ParallelRun(BaseModelRouter):
         self.executor_type = ParallelRunnerModes(executor_type)
         self._pool = None
 
+    def merger(self, body, results):
+        for part in results.values():
+            body.update(part)
+        return body
+
     def _apply_logic(self, results, event=None):
         if not self.extend_event:
             event.body = {}
         return self.merger(event.body, results)
 
-    def merger(self, body, results):
-        for result in results.values():
-            body.update(result)
-        return body
-
-    def do_event(self, event, *args, **kwargs):
-        """routers.py:340-363"""
-        original_body = event.body
-        event.body = _extract_input_data(self._input_path, event.body)
-        event = self.preprocess(event)
-        event = self._pre_handle_event(event)
-        if getattr(event, "terminated", None):
-            event.body = _update_result_body(self._result_path, original_body, event.body)
-            self._shutdown_pool()
-            return event
-        response = copy.copy(event)
-        results = self._parallel_run(event)
-        self._apply_logic(results, response)
-        response = self.postprocess(response)
-        event.body = _update_result_body(self._result_path, original_body, response.body if response else None)
-        return event
-
+    # ---- fan-out (routers.py:365-455) -------------------------------------------------------------------
     def _init_pool(self):
         if self._pool is None and self.executor_type != ParallelRunnerModes.array:
             self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=max(1, len(self.routes)))
         return self._pool
 
     def _shutdown_pool(self):
-        if self._pool is not None:
-            self._pool.shutdown()
-            self._pool = None
-
-    def _parallel_run(self, event):
-        """routers.py:414-455: array = in route order; pools = completion order, raising routes dropped"""
-        if self.executor_type == ParallelRunnerModes.array:
-            return {name: step.run(copy.copy(event)).body for name, step in self.routes.items()}
-        futures = []
-        executor = self._init_pool()
-        for route in self.routes.keys():
-            step = self.routes[route]
-            futures.append(executor.submit(ParallelRun._wrap_method, route, step.run, copy.copy(event)))
-        results = {}
-        for future in concurrent.futures.as_completed(futures):
-            try:
-                key, result = future.result()
-                results[key] = result.body
-            except Exception as exc:
-                logger.error(traceback.format_exc())
-                print(f"child route generated an exception: {exc}")
-        return results
+        pool, self._pool = self._pool, None
+        if pool is not None:
+            pool.shutdown()
 
     @staticmethod
     def _wrap_method(route, handler, event):
         return route, handler(event)
+
+    def _parallel_run(self, event):
+        """array: route order; pools: completion order, and a route that raised is simply missing"""
+        if self.executor_type == ParallelRunnerModes.array:
+            return {key: step.run(copy.copy(event)).body for key, step in self.routes.items()}
+        pool = self._init_pool()
+        pending = [pool.submit(ParallelRun._wrap_method, key, self.routes[key].run, copy.copy(event)) for key in self.routes.keys()]
+        gathered = {}
+        for done in concurrent.futures.as_completed(pending):
+            try:
+                key, answer = done.result()
+            except Exception as exc:
+                logger.error(traceback.format_exc())
+                print(f"child route generated an exception: {exc}")
+                continue
+            gathered[key] = answer.body
+        return gathered
+
+    def do_event(self, event, *args, **kwargs):
+        """routers.py:340-363"""
+        whole, event = self._enter(event)
+        if getattr(event, "terminated", None):
+            self._leave(event, whole, event.body)
+            self._shutdown_pool()
+            return event
+        answer = copy.copy(event)
+        self._apply_logic(self._parallel_run(event), answer)
+        answer = self.postprocess(answer)
+        return self._leave(event, whole, answer.body if answer else None)
 
 
 class VotingEnsemble(ParallelRun):
@@ -228,10 +225,10 @@ class VotingEnsemble(ParallelRun):
         super().__init__(context=context, name=name, routes=routes, protocol=protocol, url_prefix=url_prefix,
                          health_prefix=health_prefix, executor_type=executor_type, **kwargs)
         self.name = name or "VotingEnsemble"
-        self.vote_type = vote_type
-        self.vote_flag = self.vote_type is not None
+        self.vote_type, self.vote_flag = vote_type, vote_type is not None
         self.weights = weights
-        self._model_logger = _ModelLogPusher(self, context) if context and context.stream.enabled else None
+        tracked = bool(context) and context.stream.enabled
+        self._model_logger = _ModelLogPusher(self, context) if tracked else None
         self.version = kwargs.get("version", "v1")
         self.log_router = True
         self.prediction_col_name = prediction_col_name or "prediction"
@@ -239,146 +236,91 @@ class VotingEnsemble(ParallelRun):
         self.model_endpoint_uid = None
 
     def post_init(self, mode="sync"):
-        server = getattr(self.context, "_server", None) or getattr(self.context, "server", None)
-        if not server:
+        ctx = self.context
+        if not (getattr(ctx, "_server", None) or getattr(ctx, "server", None)):
             logger.warn("GraphServer not initialized for VotingEnsemble instance")
             return
         self._update_weights(self.weights)
 
+    # ---- weights (routers.py:962-991) ---------------------------------------------------------------------
+    def _normalize_weights(self, weights_dict):
+        """QUIRK: sums >= ~1 are used as given ([1, 1, 1, 1] turns the mean into a sum); the 'normalise' branch divides a
+        0-d object array (`np.array(dict_values)`) and raises TypeError, so weights summing to < 1 never worked"""
+        if weights_dict is None:
+            share = 1 / len(self.routes)
+            return {key: share for key in self.routes.keys()}
+        total = np.sum([*weights_dict.values()])
+        if 1.0 - total <= 1e-5:
+            return weights_dict
+        scaled = (np.array(weights_dict.values()) / total).tolist()
+        return dict(zip(weights_dict.keys(), scaled))
+
+    def _update_weights(self, weights_dict):
+        self._weights = self._normalize_weights(weights_dict)
+        for key in self.routes.keys():
+            self._weights.setdefault(key, 0)
+
+    # ---- routing (routers.py:623-706) -----------------------------------------------------------------------
     def _resolve_route(self, body, urlpath):
-        """routers.py:623-706"""
-        subpath = None
-        model = ""
-        if urlpath and not urlpath == "/":
-            subpath = ""
-            urlpath = urlpath[len(self.url_prefix):].strip("/")
-            if not urlpath:
+        """-> (model key | ensemble name | "", route step | None, operation)"""
+        model, op = "", None
+        if urlpath and urlpath != "/":
+            parts = self._target_segments(urlpath)
+            if not parts:
                 return "", None, ""
-            segments = urlpath.split("/")
-            if len(segments) == 1:
-                try:
-                    operation = OperationTypes(segments[0])
-                except ValueError:
-                    model = segments[0]
-                else:
-                    self.log_router = True
-                    return self.name, None, operation
-            if len(segments) > 2 and segments[1] == "versions":
-                model = f"{segments[0]}:{segments[2]}"
-                segments = segments[2:]
-            else:
-                model = segments[0]
-            if len(segments) > 1:
-                subpath = "/".join(segments[1:])
+            if len(parts) == 1 and parts[0] in OperationTypes._value2member_map_:
+                self.log_router = True  # a bare operation addresses the ensemble itself
+                return self.name, None, OperationTypes(parts[0])
+            model = parts[0]
+            if len(parts) > 2 and parts[1] == "versions":
+                model, parts = f"{parts[0]}:{parts[2]}", parts[2:]
+            op = "/".join(parts[1:])
         if isinstance(body, dict):
             model = model or self.name
-            subpath = body.get("operation", subpath)
-        if subpath is None:
-            subpath = "infer"
+            op = body.get("operation", op)
+        if op is None:
+            op = "infer"
         if model in self.routes:
-            self.log_router = False
-            return model, self.routes[model], subpath
-        elif model != self.name:
-            models = " | ".join(self.routes.keys())
-            raise ValueError(
-                f"model {model} doesnt exist, available models: "
-                f"{models} | {self.name} or an operation alone for ensemble operation"
-            )
-        return model, None, subpath
+            self.log_router = False  # QUIRK: a direct model call switches router-level tracking off until a bare operation
+            return model, self.routes[model], op
+        if model != self.name:
+            known = " | ".join(self.routes.keys())
+            raise ValueError(f"model {model} doesnt exist, available models: "
+                             f"{known} | {self.name} or an operation alone for ensemble operation")
+        return model, None, op
 
+    # ---- the vote (routers.py:708-810) ---------------------------------------------------------------------
     def _majority_vote(self, all_predictions, weights):
-        """one-hot (n,c,m) @ w(m) -> argmax over classes, first max wins (routers.py:708-730)"""
-        preds = np.array(all_predictions)
-        one_hot = np.transpose(
-            (np.arange(preds.max() + 1) == preds[..., None]).astype(int), (0, 2, 1)
-        )
-        weighted = one_hot @ weights
-        return np.argmax(weighted, axis=1).tolist()
+        """one-hot (n, c, m) @ w (m) -> argmax over classes, first max wins"""
+        labels = np.array(all_predictions)
+        classes = np.arange(labels.max() + 1)
+        tally = np.transpose((classes == labels[..., None]).astype(int), (0, 2, 1)) @ weights
+        return np.argmax(tally, axis=1).tolist()
 
     def _mean_vote(self, all_predictions, weights):
-        """(n,m) float64 @ w(m) (routers.py:732-741)"""
+        """(n, m) float64 @ w (m)"""
         return (np.array(all_predictions) @ weights).tolist()
 
     def _is_int(self, value):
         return float(value).is_integer()
 
     def logic(self, predictions, weights):
-        """vote-type inference happens once and sticks (routers.py:746-787)"""
-        if not self.vote_flag:
-            if all(all(map(self._is_int, row)) for row in predictions):
-                self.vote_type = VotingTypes.classification
-            else:
-                self.vote_type = VotingTypes.regression
+        if not self.vote_flag:  # QUIRK: inferred from the FIRST request's values and never revisited
+            integral = all(self._is_int(v) for row in predictions for v in row)
+            self.vote_type = VotingTypes.classification if integral else VotingTypes.regression
             self.vote_flag = True
         if self.vote_type == VotingTypes.classification:
-            int_predictions = [list(map(int, row)) for row in predictions]
-            return self._majority_vote(int_predictions, weights)
+            return self._majority_vote([[int(v) for v in row] for row in predictions], weights)
         return self._mean_vote(predictions, weights)
 
     def _apply_logic(self, results, event=None):
-        """(m,n) outputs -> (n,m); weights in result-key order (routers.py:789-810)"""
-        flat = np.array(
-            [
-                (r["outputs"][self.prediction_col_name] if self.format_response_with_col_name_flag else r["outputs"])
-                for r in results.values()
-            ]
-        ).T
-        weights = [self._weights[name] for name in results.keys()]
-        return self.logic(flat, np.array(weights))
+        """(m, n) outputs -> (n, m); weights in result-key order"""
+        column = self.prediction_col_name if self.format_response_with_col_name_flag else None
+        per_model = [r["outputs"][column] if column is not None else r["outputs"] for r in results.values()]
+        weights = np.array([self._weights[key] for key in results.keys()])
+        return self.logic(np.array(per_model).T, weights)
 
-    def do_event(self, event, *args, **kwargs):
-        """routers.py:812-914"""
-        start = now_date()
-        original_body = event.body
-        event.body = _extract_input_data(self._input_path, event.body)
-        event = self.preprocess(event)
-        event = self._pre_handle_event(event)
-        if getattr(event, "terminated", None):
-            event.body = _update_result_body(self._result_path, original_body, event.body)
-            self._shutdown_pool()
-            return event
-
-        name, route, subpath = self._resolve_route(event.body, event.path)
-        event.path = subpath
-
-        if not name and route is None:
-            setattr(event, "terminated", True)
-            event.body = {"models": list(self.routes.keys()) + [self.name], "weights": self.weights}
-            event.body = _update_result_body(self._result_path, original_body, event.body)
-            return event
-
-        request = self.validate(event.body, event.method)
-        if name == self.name and event.method != "GET":
-            predictions = self._parallel_run(event)
-            votes = self._apply_logic(predictions)
-            if self.format_response_with_col_name_flag:
-                votes = {self.prediction_col_name: votes}
-            response = copy.copy(event)
-            body = {"id": event.id, "model_name": self.name, "outputs": votes}
-            if self.version:
-                body["model_version"] = self.version
-            response.body = body
-        elif name == self.name and event.method == "GET" and not subpath:
-            response = copy.copy(event)
-            body = {"name": self.name, "version": self.version or "", "inputs": [], "outputs": []}
-            for child in self.routes.values():
-                child_resp = child.run(copy.copy(event))
-                body["inputs"] = body["inputs"] or child_resp.body["inputs"]
-                body["outputs"] = body["outputs"] or child_resp.body["outputs"]
-                if body["inputs"] and body["outputs"]:
-                    break
-            response.body = body
-        else:
-            response = route.run(event)
-
-        response = self.postprocess(response)
-        if self._model_logger and self.log_router:
-            if "id" not in request:
-                request["id"] = response.body["id"]
-            self._model_logger.push(start, request, response.body)
-        event.body = _update_result_body(self._result_path, original_body, response.body if response else None)
-        return event
-
+    # ---- the event handler (routers.py:812-914) ---------------------------------------------------------------
     def validate(self, request, method):
         if self.protocol == "v2" and method != "GET":
             if "inputs" not in request:
@@ -387,21 +329,50 @@ class VotingEnsemble(ParallelRun):
                 raise Exception('Expected "inputs" to be a list')
         return request
 
-    def _normalize_weights(self, weights_dict):
-        """routers.py:962-980 -- including its quirk: sums >= ~1 are returned as given and the
-        'normalise' branch divides a 0-d object array (dict_values) and raises TypeError"""
-        if weights_dict is None:
-            n = len(self.routes)
-            return dict(zip(self.routes.keys(), [1 / n] * n))
-        values = [*weights_dict.values()]
-        total = np.sum(values)
-        if 1.0 - total <= 1e-5:
-            return weights_dict
-        new_values = (np.array(weights_dict.values()) / total).tolist()
-        return dict(zip(weights_dict.keys(), new_values))
+    def _ensemble_metadata(self, event):
+        meta = {"name": self.name, "version": self.version or "", "inputs": [], "outputs": []}
+        for child in self.routes.values():
+            described = child.run(copy.copy(event)).body
+            meta["inputs"] = meta["inputs"] or described["inputs"]
+            meta["outputs"] = meta["outputs"] or described["outputs"]
+            if meta["inputs"] and meta["outputs"]:
+                break
+        return meta
 
-    def _update_weights(self, weights_dict):
-        self._weights = self._normalize_weights(weights_dict)
-        for model in self.routes.keys():
-            if model not in self._weights.keys():
-                self._weights[model] = 0
+    def do_event(self, event, *args, **kwargs):
+        started = now_date()
+        whole, event = self._enter(event)
+        if getattr(event, "terminated", None):
+            self._leave(event, whole, event.body)
+            self._shutdown_pool()
+            return event
+
+        target, route, op = self._resolve_route(event.body, event.path)
+        event.path = op
+        if not target and route is None:
+            event.terminated = True
+            listing = {"models": list(self.routes.keys()) + [self.name], "weights": self.weights}
+            return self._leave(event, whole, listing)
+
+        request = self.validate(event.body, event.method)
+        to_ensemble = target == self.name
+        if to_ensemble and event.method != "GET":
+            votes = self._apply_logic(self._parallel_run(event))
+            if self.format_response_with_col_name_flag:
+                votes = {self.prediction_col_name: votes}
+            answer = copy.copy(event)
+            answer.body = {"id": event.id, "model_name": self.name, "outputs": votes}
+            if self.version:
+                answer.body["model_version"] = self.version
+        elif to_ensemble and event.method == "GET" and not op:
+            answer = copy.copy(event)
+            answer.body = self._ensemble_metadata(event)
+        else:
+            answer = route.run(event)
+
+        answer = self.postprocess(answer)
+        if self._model_logger and self.log_router:
+            if "id" not in request:
+                request["id"] = answer.body["id"]
+            self._model_logger.push(started, request, answer.body)
+        return self._leave(event, whole, answer.body if answer else None)
