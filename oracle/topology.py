@@ -43,31 +43,12 @@ class GraphError(Exception):
 
 
 class StepKinds:
-    router = "router"
-    task = "task"
-    flow = "flow"
-    queue = "queue"
-    choice = "choice"
-    root = "root"
-    error_step = "error_step"
+    router, task, flow, queue, choice, root, error_step = "router", "task", "flow", "queue", "choice", "root", "error_step"
 
 
-_task_step_fields = [
-    "kind",
-    "class_name",
-    "class_args",
-    "handler",
-    "skip_context",
-    "after",
-    "function",
-    "comment",
-    "shape",
-    "full_event",
-    "on_error",
-    "responder",
-    "input_path",
-    "result_path",
-]
+# wire fields of a task-like step, in the order the reference serialises them
+_task_step_fields = ("kind class_name class_args handler skip_context after function comment shape full_event on_error "
+                     "responder input_path result_path").split()
 
 
 class MapClass:
@@ -75,51 +56,42 @@ class MapClass:
     kwargs storey's flow base keeps (context/name/full_event/input_path/result_path)."""
 
     def __init__(self, context=None, name=None, full_event=None, input_path=None, result_path=None, **kwargs):
-        self.context = context
-        self.name = name
-        self._full_event = full_event
-        self._input_path = input_path
-        self._result_path = result_path
+        self.context, self.name = context, name
+        self._full_event, self._input_path, self._result_path = full_event, input_path, result_path
         self.logger = getattr(context, "logger", None) if context else None
         self._kwargs = kwargs
         self._outlets = []  # marks a "native" async step (states.py:1678)
 
 
 def get_current_function(context):
-    if context and hasattr(context, "current_function"):
-        return context.current_function or ""
-    return ""
+    return (getattr(context, "current_function", None) or "") if context else ""
 
 
 def get_name(name, class_name):
+    """a step is named explicitly, or after its class"""
     if name:
         return name
     if not class_name:
         raise MLRunInvalidArgumentError("name or class_name must be provided")
-    if isinstance(class_name, type):
-        return class_name.__name__
-    return class_name
+    return class_name.__name__ if isinstance(class_name, type) else class_name
 
 
 class BaseStep(ModelObj):
+    """what every node of the graph has: a name, a parent, predecessors (`after`), successors (`next`), an optional error
+    handler (states.py:102-395)"""
+
     kind = "BaseStep"
     default_shape = "ellipse"
     _dict_fields = ["kind", "comment", "after", "on_error"]
 
     def __init__(self, name=None, after=None, shape=None):
-        self.name = name
-        self._parent = None
-        self.comment = None
-        self.context = None
+        self.name, self.shape = name, shape
         self.after = after or []
-        self._next = None
-        self.shape = shape
-        self.on_error = None
-        self._on_error_handler = None
+        self._parent = self._next = None
+        self.comment = self.context = None
+        self.on_error = self._on_error_handler = None
 
-    def set_parent(self, parent):
-        self._parent = parent
-
+    # ---- wiring -----------------------------------------------------------------------------------
     @property
     def next(self):
         return self._next
@@ -128,64 +100,104 @@ class BaseStep(ModelObj):
     def parent(self):
         return self._parent
 
+    def set_parent(self, parent):
+        self._parent = parent
+
     def set_next(self, key):
-        if not self.next:
+        if not self._next:
             self._next = [key]
-        elif key not in self.next:
+        elif key not in self._next:
             self._next.append(key)
         return self
 
     def after_step(self, *after, append=True):
         if not append:
             self.after = []
-        for name in after:
-            name = name if isinstance(name, str) else name.name
-            if name not in self.after:
-                self.after.append(name)
+        for item in after:
+            key = item if isinstance(item, str) else item.name
+            if key not in self.after:
+                self.after.append(key)
         return self
 
-    def error_handler(
-        self,
-        name=None,
-        class_name=None,
-        handler=None,
-        before=None,
-        function=None,
-        full_event=None,
-        input_path=None,
-        result_path=None,
-        **class_args,
-    ):
-        """states.py:155-231"""
+    @property
+    def fullname(self):
+        own = self.name or ""
+        up = self._parent.fullname if self._parent else ""
+        return (path_splitter.join([up, own]) if up else own).replace(":", "_")
+
+    def path_to_step(self, path):
+        node = self
+        for key in (path or "").split(path_splitter):
+            if key not in node:
+                raise GraphError(f"step {key} doesnt exist in the graph under {node.fullname}")
+            node = node[key]
+        return node
+
+    def _owner(self):
+        """the flow new steps are registered in: this step when it is a flow, else its parent"""
+        if hasattr(self, "steps"):
+            return self
+        if not self._parent:
+            raise GraphError(f"step {self.name} parent is not set or it's not part of a graph")
+        return self._parent
+
+    def to(self, class_name=None, name=None, handler=None, graph_shape=None, function=None, full_event=None,
+           input_path=None, result_path=None, **class_args):
+        """append a step after this one (states.py:297-362)"""
+        owner = self._owner()
+        key, step = params_to_step(class_name, name, handler, graph_shape=graph_shape, function=function,
+                                   full_event=full_event, input_path=input_path, result_path=result_path, class_args=class_args)
+        step = owner._steps.update(key, step)
+        step.set_parent(owner)
+        if owner is not self:
+            step.after_step(self.name)
+        owner._last_added = step
+        return step
+
+    def set_flow(self, steps, force=False):
+        raise NotImplementedError("set_flow() can only be called on a FlowStep")
+
+    # ---- error routing (states.py:155-231, 263-282) ---------------------------------------------------------
+    def error_handler(self, name=None, class_name=None, handler=None, before=None, function=None, full_event=None,
+                      input_path=None, result_path=None, **class_args):
         if not (class_name or handler):
             raise MLRunInvalidArgumentError("class_name or handler must be provided")
-        if isinstance(self, RootFlowStep) and before:
+        if before and isinstance(self, RootFlowStep):
             raise MLRunInvalidArgumentError("`before` arg can't be specified for graph error handler")
-        name = get_name(name, class_name)
-        step = ErrorStep(
-            class_name,
-            class_args,
-            handler,
-            name=name,
-            function=function,
-            full_event=full_event,
-            input_path=input_path,
-            result_path=result_path,
-        )
-        self.on_error = name
-        before = [before] if isinstance(before, str) else before
-        step.before = before or []
-        step.base_step = self.name
-        if getattr(self, "_parent", None):
-            step = self._parent._steps.update(name, step)
-            step.set_parent(self._parent)
-        else:
-            step = self._steps.update(name, step)
-            step.set_parent(self)
+        key = get_name(name, class_name)
+        catcher = ErrorStep(class_name, class_args, handler, name=key, function=function, full_event=full_event,
+                            input_path=input_path, result_path=result_path)
+        catcher.before = ([before] if isinstance(before, str) else before) or []
+        catcher.base_step = self.name
+        self.on_error = key
+        flow = self._parent if getattr(self, "_parent", None) else self
+        flow._steps.update(key, catcher).set_parent(flow)
         return self
 
+    def _set_error_handler(self):
+        if self.on_error:
+            self._on_error_handler = self.context.root.path_to_step(self.on_error).run
+
+    def _log_error(self, event, err, **kwargs):
+        text, trace = err_to_str(err), traceback.format_exc()
+        log = self.context.logger
+        log.error(f"step {self.name} got error {text} when processing an event:\n {event.body}")
+        log.error(trace)
+        self.context.push_error(event, f"{text}\n{trace}", source=self.fullname, **kwargs)
+
+    def _call_error_handler(self, event, err, **kwargs):
+        """the failure is recorded on the event, which then continues at the handler step"""
+        event.error = event.error or {}
+        event.error[self.name] = err_to_str(err)
+        event.origin_state = self.fullname
+        return self._on_error_handler(event)
+
+    # ---- defaults the subclasses override ----------------------------------------------------------------
     def init_object(self, context, namespace, mode="sync", reset=False, **extra_kwargs):
         self.context = context
+
+    def _post_init(self, mode="sync"):
+        pass
 
     def _is_local_function(self, context):
         return True
@@ -196,89 +208,11 @@ class BaseStep(ModelObj):
     def __iter__(self):
         yield from []
 
-    @property
-    def fullname(self):
-        name = self.name or ""
-        if self._parent and self._parent.fullname:
-            name = path_splitter.join([self._parent.fullname, name])
-        return name.replace(":", "_")
-
-    def _post_init(self, mode="sync"):
-        pass
-
-    def _set_error_handler(self):
-        if self.on_error:
-            error_step = self.context.root.path_to_step(self.on_error)
-            self._on_error_handler = error_step.run
-
-    def _log_error(self, event, err, **kwargs):
-        message = err_to_str(err)
-        self.context.logger.error(
-            f"step {self.name} got error {message} when processing an event:\n {event.body}"
-        )
-        trace = traceback.format_exc()
-        self.context.logger.error(trace)
-        self.context.push_error(event, f"{message}\n{trace}", source=self.fullname, **kwargs)
-
-    def _call_error_handler(self, event, err, **kwargs):
-        """states.py:276-282"""
-        if not event.error:
-            event.error = {}
-        event.error[self.name] = err_to_str(err)
-        event.origin_state = self.fullname
-        return self._on_error_handler(event)
-
-    def path_to_step(self, path):
-        path = path or ""
-        level = self
-        for part in path.split(path_splitter):
-            if part not in level:
-                raise GraphError(f"step {part} doesnt exist in the graph under {level.fullname}")
-            level = level[part]
-        return level
-
-    def to(
-        self,
-        class_name=None,
-        name=None,
-        handler=None,
-        graph_shape=None,
-        function=None,
-        full_event=None,
-        input_path=None,
-        result_path=None,
-        **class_args,
-    ):
-        """append a step after this one (states.py:297-362)"""
-        if hasattr(self, "steps"):
-            parent = self
-        elif self._parent:
-            parent = self._parent
-        else:
-            raise GraphError(f"step {self.name} parent is not set or it's not part of a graph")
-        name, step = params_to_step(
-            class_name,
-            name,
-            handler,
-            graph_shape=graph_shape,
-            function=function,
-            full_event=full_event,
-            input_path=input_path,
-            result_path=result_path,
-            class_args=class_args,
-        )
-        step = parent._steps.update(name, step)
-        step.set_parent(parent)
-        if not hasattr(self, "steps"):
-            step.after_step(self.name)
-        parent._last_added = step
-        return step
-
-    def set_flow(self, steps, force=False):
-        raise NotImplementedError("set_flow() can only be called on a FlowStep")
-
     def supports_termination(self):
         return False
+
+
+_INJECTABLE = ("name", "context", "input_path", "result_path", "full_event")
 
 
 class TaskStep(BaseStep):
@@ -288,122 +222,88 @@ class TaskStep(BaseStep):
     _dict_fields = _task_step_fields
     _default_class = ""
 
-    def __init__(
-        self,
-        class_name=None,
-        class_args=None,
-        handler=None,
-        name=None,
-        after=None,
-        full_event=None,
-        function=None,
-        responder=None,
-        input_path=None,
-        result_path=None,
-    ):
+    def __init__(self, class_name=None, class_args=None, handler=None, name=None, after=None, full_event=None,
+                 function=None, responder=None, input_path=None, result_path=None):
         super().__init__(name, after)
-        self.class_name = class_name
-        self.class_args = class_args or {}
-        self.handler = handler
-        self.function = function
-        self._handler = None
-        self._object = None
-        self._async_object = None
-        self.skip_context = None
-        self.context = None
-        self._class_object = None
-        self.responder = responder
-        self.full_event = full_event
-        self.input_path = input_path
-        self.result_path = result_path
-        self.on_error = None
-        self._inject_context = False
-        self._call_with_event = False
+        self.class_name, self.class_args, self.handler = class_name, class_args or {}, handler
+        self.function, self.responder, self.full_event = function, responder, full_event
+        self.input_path, self.result_path = input_path, result_path
+        self.skip_context = self.context = self.on_error = None
+        self._handler = self._object = self._async_object = self._class_object = None
+        self._inject_context = self._call_with_event = False
 
+    # ---- resolution: class_name / handler -> the callable run() uses ------------------------------------------
     def init_object(self, context, namespace, mode="sync", reset=False, **extra_kwargs):
-        self.context = context
-        self._async_object = None
+        self.context, self._async_object = context, None
         if not self._is_local_function(context):
             return
-
         if self.handler and not self.class_name:
-            if callable(self.handler):
-                self._handler = self.handler
-                self.handler = self.handler.__name__
-            else:
-                self._handler = get_function(self.handler, namespace)
-            try:
-                params = signature(self._handler).parameters
-            except (TypeError, ValueError):
-                params = {}
-            if params and "context" in list(params.keys()):
-                self._inject_context = True
+            self._bind_function(namespace)
             self._set_error_handler()
             return
-
         self._class_object, self.class_name = self.get_step_class_object(namespace)
-        if not self._object or reset:
-            ctor_args = self.get_full_class_args(namespace, self._class_object, **extra_kwargs)
-            try:
-                self._object = self._class_object(**ctor_args)
-            except TypeError as exc:
-                raise TypeError(f"failed to init step {self.name}\n args={self.class_args}") from exc
-
-            handler = self.handler
-            if handler:
-                if not hasattr(self._object, handler):
-                    raise GraphError(
-                        f"handler ({handler}) specified but doesnt exist in class {self.class_name}"
-                    )
-            elif hasattr(self._object, "do_event"):
-                handler = "do_event"
-                self._call_with_event = True
-            elif hasattr(self._object, "do"):
-                handler = "do"
-            if handler:
-                self._handler = getattr(self._object, handler, None)
-
+        if reset or not self._object:
+            self._build_object(namespace, extra_kwargs)
         self._set_error_handler()
         if mode != "skip":
             self._post_init(mode)
 
+    def _bind_function(self, namespace):
+        """a bare handler: a callable, a name to look up, or a "(expr)" lambda body (helpers.get_function)"""
+        if callable(self.handler):
+            self._handler, self.handler = self.handler, self.handler.__name__
+        else:
+            self._handler = get_function(self.handler, namespace)
+        try:
+            accepted = list(signature(self._handler).parameters)
+        except (TypeError, ValueError):
+            accepted = []
+        self._inject_context = "context" in accepted
+
+    def _build_object(self, namespace, extra_kwargs):
+        ctor_args = self.get_full_class_args(namespace, self._class_object, **extra_kwargs)
+        try:
+            self._object = self._class_object(**ctor_args)
+        except TypeError as exc:
+            raise TypeError(f"failed to init step {self.name}\n args={self.class_args}") from exc
+        method = self.handler
+        if method:
+            if not hasattr(self._object, method):
+                raise GraphError(f"handler ({method}) specified but doesnt exist in class {self.class_name}")
+        elif hasattr(self._object, "do_event"):  # model servers / routers: they take the whole event
+            method, self._call_with_event = "do_event", True
+        elif hasattr(self._object, "do"):
+            method = "do"
+        if method:
+            self._handler = getattr(self._object, method, None)
+
     def get_full_class_args(self, namespace, class_object, **extra_kwargs):
         """states.py:494-512: `_x` args resolve to callables; name/context/... only when accepted"""
         args = {}
-        for key, val in self.class_args.items():
+        for key, value in self.class_args.items():
             if key.startswith(callable_prefix):
-                args[key[1:]] = get_function(val, namespace)
-            else:
-                args[key] = val
+                key, value = key[1:], get_function(value, namespace)
+            args[key] = value
         args.update(extra_kwargs)
         spec = getfullargspec(class_object)
-        for key in ["name", "context", "input_path", "result_path", "full_event"]:
-            if spec.varkw or key in spec.args:
-                args[key] = getattr(self, key)
-        if spec.varkw or "graph_step" in spec.args:
+        takes = (lambda k: True) if spec.varkw else (lambda k: k in spec.args)
+        args.update({k: getattr(self, k) for k in _INJECTABLE if takes(k)})
+        if takes("graph_step"):
             args["graph_step"] = self
         return args
 
     def get_step_class_object(self, namespace):
-        class_name = self.class_name
-        class_object = self._class_object
-        if isinstance(class_name, type):
-            class_object = class_name
-            class_name = class_name.__name__
-        elif not class_object:
-            class_object = get_class(class_name or self._default_class, namespace)
-        return class_object, class_name
+        if isinstance(self.class_name, type):
+            return self.class_name, self.class_name.__name__
+        found = self._class_object or get_class(self.class_name or self._default_class, namespace)
+        return found, self.class_name
 
     def _is_local_function(self, context):
-        """states.py:529-540"""
-        current = get_current_function(context)
-        if current == "*":
+        """states.py:529-540 -- does this step run in the current function of a multi-function graph?"""
+        here, mine = get_current_function(context), self.function
+        if here == "*" or (not mine and not here):
             return True
-        if not self.function and not current:
-            return True
-        if (self.function and self.function == "*") or self.function == current:
-            return True
-        return False
+        return bool(mine and mine == "*") or mine == here
 
     @property
     def async_object(self):
@@ -413,83 +313,63 @@ class TaskStep(BaseStep):
         self._object = None
 
     def _post_init(self, mode="sync"):
-        if self._object and hasattr(self._object, "post_init"):
-            self._object.post_init(mode)
+        hook = getattr(self._object, "post_init", None) if self._object else None
+        if hook:
+            hook(mode)
 
     def respond(self):
         self.responder = True
         return self
 
+    # ---- per-event call convention (states.py:564-599) --------------------------------------------------------
     def run(self, event, *args, **kwargs):
-        """per-event call convention (states.py:564-599)"""
         if not self._is_local_function(self.context):
             return event
         if self._inject_context:
             kwargs["context"] = self.context
-        elif kwargs and "context" in kwargs:
-            del kwargs["context"]
-
+        elif kwargs:
+            kwargs.pop("context", None)
         try:
             if self.full_event or self._call_with_event:
-                return self._handler(event, *args, **kwargs)
+                return self._handler(event, *args, **kwargs)  # the handler's return value IS the result event
             if self._handler is None:
                 raise MLRunInvalidArgumentError(f"step {self.name} does not have a handler")
-            result = self._handler(_extract_input_data(self.input_path, event.body), *args, **kwargs)
-            event.body = _update_result_body(self.result_path, event.body, result)
+            outcome = self._handler(_extract_input_data(self.input_path, event.body), *args, **kwargs)
+            event.body = _update_result_body(self.result_path, event.body, outcome)
         except Exception as exc:
-            if self._on_error_handler:
-                self._log_error(event, exc)
-                result = self._call_error_handler(event, exc)
-                event.body = _update_result_body(self.result_path, event.body, result)
-            else:
+            if not self._on_error_handler:
                 raise exc
+            self._log_error(event, exc)
+            event.body = _update_result_body(self.result_path, event.body, self._call_error_handler(event, exc))
         return event
 
 
 class ErrorStep(TaskStep):
+    """a task that other steps name in `on_error`"""
+
     kind = "error_step"
     _dict_fields = _task_step_fields + ["before", "base_step"]
     _default_class = ""
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
-        self.before = None
-        self.base_step = None
+        self.before = self.base_step = None
 
 
 class RouterStep(TaskStep):
-    """router with child routes (states.py:671-798)"""
+    """a task whose object dispatches to child routes (states.py:671-798)"""
 
     kind = "router"
     default_shape = "doubleoctagon"
     _dict_fields = _task_step_fields + ["routes"]
     _default_class = "mlrun.serving.ModelRouter"
 
-    def __init__(
-        self,
-        class_name=None,
-        class_args=None,
-        handler=None,
-        routes=None,
-        name=None,
-        function=None,
-        input_path=None,
-        result_path=None,
-    ):
-        super().__init__(
-            class_name,
-            class_args,
-            handler,
-            name=name,
-            function=function,
-            input_path=input_path,
-            result_path=result_path,
-        )
+    def __init__(self, class_name=None, class_args=None, handler=None, routes=None, name=None, function=None,
+                 input_path=None, result_path=None):
+        super().__init__(class_name, class_args, handler, name=name, function=function, input_path=input_path,
+                         result_path=result_path)
         self._routes = None
         self.routes = routes
-
-    def get_children(self):
-        return self._routes.values()
 
     @property
     def routes(self):
@@ -499,16 +379,17 @@ class RouterStep(TaskStep):
     def routes(self, routes):
         self._routes = ObjectDict.from_dict(classes_map, routes, "task")
 
+    def get_children(self):
+        return self._routes.values()
+
     def add_route(self, key, route=None, class_name=None, handler=None, function=None, **class_args):
-        if not route and not class_name and not handler:
+        if not (route or class_name or handler):
             raise MLRunInvalidArgumentError("route or class_name must be specified")
-        if not route:
-            route = TaskStep(class_name, class_args, handler=handler)
+        route = route or TaskStep(class_name, class_args, handler=handler)
         route.function = function or route.function
-        if len(self._routes) >= MAX_ALLOWED_STEPS:
+        if len(self._routes) >= MAX_ALLOWED_STEPS:  # states.py:740-743
             raise MLRunInvalidArgumentError(
-                f"Cannot create the serving graph: the maximum number of steps is {MAX_ALLOWED_STEPS}"
-            )
+                f"Cannot create the serving graph: the maximum number of steps is {MAX_ALLOWED_STEPS}")
         route = self._routes.update(key, route)
         route.set_parent(self)
         return route
@@ -518,18 +399,19 @@ class RouterStep(TaskStep):
             del self._routes[key]
 
     def init_object(self, context, namespace, mode="sync", reset=False, **extra_kwargs):
+        """the router object first (it receives the routes), then every child, then the router's post_init"""
         if not self._is_local_function(context):
             return
         self.class_args = self.class_args or {}
         super().init_object(context, namespace, "skip", reset=reset, routes=self._routes, **extra_kwargs)
-        for route in self._routes.values():
-            if self.function and not route.function:
-                route.function = self.function
-            route.set_parent(self)
-            route.init_object(context, namespace, mode, reset=reset)
+        for child in self._routes.values():
+            child.function = child.function or self.function or child.function
+            child.set_parent(self)
+            child.init_object(context, namespace, mode, reset=reset)
         self._set_error_handler()
         self._post_init(mode)
 
+    # mapping protocol over the routes
     def __getitem__(self, name):
         return self._routes[name]
 
@@ -555,13 +437,13 @@ class QueueStep(BaseStep):
 
     def __init__(self, name=None, path=None, after=None, shards=None, retention_in_hours=None, trigger_args=None, **options):
         super().__init__(name, after)
-        self.path = path
-        self.shards = shards
-        self.retention_in_hours = retention_in_hours
-        self.options = options
-        self.trigger_args = trigger_args
-        self._stream = None
-        self._async_object = None
+        self.path, self.shards, self.retention_in_hours = path, shards, retention_in_hours
+        self.trigger_args, self.options = trigger_args, options
+        self._stream = self._async_object = None
+
+    @property
+    def async_object(self):
+        return self._async_object
 
     def init_object(self, context, namespace, mode="sync", reset=False, **extra_kwargs):
         self.context = context
@@ -571,33 +453,24 @@ class QueueStep(BaseStep):
             self._stream = get_stream_pusher(self.path, **self.options)
         self._set_error_handler()
 
-    @property
-    def async_object(self):
-        return self._async_object
-
     def to(self, class_name=None, name=None, handler=None, graph_shape=None, function=None,
            full_event=None, input_path=None, result_path=None, **class_args):
-        if not function:
-            name = get_name(name, class_name)
+        if not function:  # what follows a queue runs in another function: it has to say which (states.py:860-864)
             raise MLRunInvalidArgumentError(
-                f"step '{name}' must specify a function, because it follows a queue step"
-            )
-        return super().to(class_name, name, handler, graph_shape, function, full_event,
-                          input_path, result_path, **class_args)
+                f"step '{get_name(name, class_name)}' must specify a function, because it follows a queue step")
+        return super().to(class_name, name, handler, graph_shape, function, full_event, input_path, result_path, **class_args)
 
     def run(self, event, *args, **kwargs):
-        data = event.body
-        if not data:
-            return event
-        if self._stream:
-            self._stream.push(data)
-            event.terminated = True
-            event.body = None
+        payload = event.body
+        if payload and self._stream:
+            self._stream.push(payload)
+            event.terminated, event.body = True, None
         return event
 
 
 class FlowStep(BaseStep):
-    """workflow / DAG (states.py:892-1402)"""
+    """workflow / DAG of steps (states.py:892-1402): wiring, validation, and the two executors -- the synchronous walk
+    of a single chain and the hand-off to the async engine"""
 
     kind = "flow"
     _dict_fields = BaseStep._dict_fields + ["steps", "engine", "default_final_step"]
@@ -606,19 +479,13 @@ class FlowStep(BaseStep):
         super().__init__(name, after)
         self._steps = None
         self.steps = steps
-        self.engine = engine
+        self.engine, self.final_step = engine, final_step
         self.from_step = os.environ.get("START_FROM_STEP", None)
-        self.final_step = final_step
-        self._last_added = None
-        self._controller = None
+        self._last_added = self._controller = self._source = self._async_flow = None
         self._wait_for_result = False
-        self._source = None
         self._start_steps = []
-        self._async_flow = None
 
-    def get_children(self):
-        return self._steps.values()
-
+    # ---- container protocol -------------------------------------------------------------------------
     @property
     def steps(self):
         return self._steps
@@ -631,44 +498,23 @@ class FlowStep(BaseStep):
     def controller(self):
         return self._controller
 
-    def add_step(self, class_name=None, name=None, handler=None, after=None, before=None, graph_shape=None,
-                 function=None, full_event=None, input_path=None, result_path=None, **class_args):
-        name, step = params_to_step(
-            class_name, name, handler, graph_shape=graph_shape, function=function, full_event=full_event,
-            input_path=input_path, result_path=result_path, class_args=class_args,
-        )
-        for item in after if isinstance(after, list) else [after]:
-            self.insert_step(name, step, item, before)
-        return step
+    def get_children(self):
+        return self._steps.values()
 
-    def insert_step(self, key, step, after, before=None):
-        """states.py:1003-1036"""
-        step = self._steps.update(key, step)
-        step.set_parent(self)
-        if after == "$prev" and len(self._steps) == 1:
-            after = None
-        previous = ""
-        if after:
-            if after == "$prev" and self._last_added:
-                previous = self._last_added.name
-            else:
-                if after not in self._steps.keys():
-                    raise MLRunInvalidArgumentError(f"cant set after, there is no step named {after}")
-                previous = after
-            step.after_step(previous)
-        if before:
-            if before not in self._steps.keys():
-                raise MLRunInvalidArgumentError(f"cant set before, there is no step named {before}")
-            if before == step.name or before == previous:
-                raise GraphError(f"graph loop, step {before} is specified in before and/or after {key}")
-            self[step.name].after_step(*self[before].after, append=False)
-            self[before].after_step(step.name, append=False)
-        self._last_added = step
-        return step
+    def is_empty(self):
+        return len(self.steps) == 0
 
     def clear_children(self, steps=None):
         for key in list(steps or self._steps.keys()):
             del self._steps[key]
+
+    def list_child_functions(self):
+        seen = []
+        for child in self.get_children():
+            fn = getattr(child, "function", None)
+            if fn and fn not in seen:
+                seen.append(fn)
+        return seen
 
     def __getitem__(self, name):
         return self._steps[name]
@@ -685,6 +531,151 @@ class FlowStep(BaseStep):
     def __contains__(self, name):
         return name in self._steps
 
+    # ---- building ------------------------------------------------------------------------------------
+    def add_step(self, class_name=None, name=None, handler=None, after=None, before=None, graph_shape=None,
+                 function=None, full_event=None, input_path=None, result_path=None, **class_args):
+        key, step = params_to_step(class_name, name, handler, graph_shape=graph_shape, function=function,
+                                   full_event=full_event, input_path=input_path, result_path=result_path, class_args=class_args)
+        for predecessor in (after if isinstance(after, list) else [after]):
+            self.insert_step(key, step, predecessor, before)
+        return step
+
+    def _must_exist(self, key, what):
+        if key not in self._steps.keys():
+            raise MLRunInvalidArgumentError(f"cant set {what}, there is no step named {key}")
+
+    def insert_step(self, key, step, after, before=None):
+        """states.py:1003-1036 -- register `step`, hang it after `after` ("$prev": the last added) and before `before`"""
+        step = self._steps.update(key, step)
+        step.set_parent(self)
+        if after == previous_step and len(self._steps) == 1:
+            after = None
+        hung_after = ""
+        if after:
+            if after == previous_step and self._last_added:
+                hung_after = self._last_added.name
+            else:
+                self._must_exist(after, "after")
+                hung_after = after
+            step.after_step(hung_after)
+        if before:
+            self._must_exist(before, "before")
+            if before in (step.name, hung_after):
+                raise GraphError(f"graph loop, step {before} is specified in before and/or after {key}")
+            successor = self[before]
+            self[step.name].after_step(*successor.after, append=False)  # the new step inherits the successor's inputs
+            successor.after_step(step.name, append=False)
+        self._last_added = step
+        return step
+
+    def set_flow(self, steps, force=False):
+        if self.steps and not force:
+            raise MLRunInvalidArgumentError(
+                "set_flow() called on a step that already has downstream steps. "
+                "If you want to overwrite existing steps, set force=True.")
+        self.steps = None
+        tail = self
+        for spec in steps:
+            tail = tail.to(**spec) if isinstance(spec, dict) else tail.to(spec)
+        return tail
+
+    def _insert_all_error_handlers(self):
+        for key, step in self._steps.items():
+            if step.kind == StepKinds.error_step:
+                self._insert_error_step(key, step)
+
+    def _insert_error_step(self, name, step):
+        """states.py:1362-1378 -- an error step nothing follows answers the caller; else it precedes its `before` steps"""
+        followed = any(step.name in other.after for other in self._steps.values())
+        if not step.before and not followed:
+            step.responder = True
+            return
+        for target in step.before:
+            self._must_exist(target, "before")
+            self[target].after_step(name)
+
+    # ---- validation (states.py:1073-1184) -----------------------------------------------------------------
+    def _cycle_through(self, step, trail=()):
+        """name of a step that closes a cycle over `after` links, if any"""
+        for prev in step.after or []:
+            if prev in trail:
+                return step.name
+            found = self._cycle_through(self[prev], trail + (prev,))
+            if found:
+                return found
+        return None
+
+    def _first_owned(self, step, function):
+        """first step on the way down from `step` that runs in `function`"""
+        if getattr(step, "function", None) and step.function == function:
+            return step
+        for key in step.next or []:
+            found = self._first_owned(self[key], function)
+            if found:
+                return found
+        return None
+
+    def check_and_process_graph(self, allow_empty=False):
+        """validate the DAG and set the .next links -> (start steps, default final step, responders)"""
+        if allow_empty and self.is_empty():
+            self._start_steps = []
+            return [], None, []
+
+        starts = []
+        for step in self._steps.values():
+            step._next, step._visited = None, False
+            if not step.after:
+                starts.append(step.name)
+                continue
+            looped = self._cycle_through(step)
+            if looped:
+                raise GraphError(f"Error, loop detected in step {looped}, graph must be acyclic (DAG)")
+
+        responders = []
+        for step in self._steps.values():
+            if getattr(step, "responder", None) and step.kind != StepKinds.error_step:
+                responders.append(step.name)
+            if step.on_error and step.on_error in starts:
+                starts.remove(step.on_error)  # an error handler is entered on failure only
+            for prev in step.after or []:
+                self[prev].set_next(step.name)
+        if self.on_error and self.on_error in starts:
+            starts.remove(self.on_error)
+        if len(responders) > 1:
+            raise GraphError(f'there are more than one responder steps in the graph ({",".join(responders)})')
+
+        if self.from_step:
+            if self.from_step not in self.steps:
+                raise GraphError(f"from_step ({self.from_step}) specified and not found in graph steps")
+            starts = [self.from_step]
+        self._start_steps = [self[key] for key in starts]
+
+        here = get_current_function(self.context)
+        if here and here != "*":  # a child function of a multi-function graph starts at its own first steps
+            owned = [s for s in (self._first_owned(start, here) for start in self._start_steps) if s]
+            if not owned:
+                raise GraphError(f"did not find steps pointing to current function ({here})")
+            self._start_steps = owned
+
+        if self.engine == "sync" and len(self._start_steps) > 1:
+            raise GraphError("sync engine can only have one starting step (without .after)")
+        return self._start_steps, self._default_final(), responders
+
+    def _default_final(self):
+        if self.final_step:
+            if self.final_step not in self.steps:
+                raise GraphError(f"final_step ({self.final_step}) specified and not found in graph steps")
+            return self.final_step
+        if len(self._start_steps) != 1:
+            return None
+        node = self._start_steps[0]
+        while node:  # follow the chain while it does not branch
+            if not node.next:
+                return node.name
+            node = self[node.next[0]] if len(node.next) == 1 else None
+        return None
+
+    # ---- initialisation ---------------------------------------------------------------------------------
     def init_object(self, context, namespace, mode="sync", reset=False, **extra_kwargs):
         self.context = context
         self._insert_all_error_handlers()
@@ -698,93 +689,6 @@ class FlowStep(BaseStep):
             self._build_async_flow()
             self._run_async_flow()
 
-    def check_and_process_graph(self, allow_empty=False):
-        """validate the DAG and set the .next links (states.py:1073-1184)"""
-        if self.is_empty() and allow_empty:
-            self._start_steps = []
-            return [], None, []
-
-        def find_loop(step, seen):
-            for prev in step.after or []:
-                if prev in seen:
-                    return step.name
-                found = find_loop(self[prev], seen + [prev])
-                if found:
-                    return found
-            return None
-
-        start_steps = []
-        for step in self._steps.values():
-            step._next = None
-            step._visited = False
-            if step.after:
-                loop = find_loop(step, [])
-                if loop:
-                    raise GraphError(f"Error, loop detected in step {loop}, graph must be acyclic (DAG)")
-            else:
-                start_steps.append(step.name)
-
-        responders = []
-        for step in self._steps.values():
-            if getattr(step, "responder", None) and step.kind != "error_step":
-                responders.append(step.name)
-            if step.on_error and step.on_error in start_steps:
-                start_steps.remove(step.on_error)
-            for prev in step.after or []:
-                self[prev].set_next(step.name)
-        if self.on_error and self.on_error in start_steps:
-            start_steps.remove(self.on_error)
-
-        if len(responders) > 1:
-            raise GraphError(
-                f'there are more than one responder steps in the graph ({",".join(responders)})'
-            )
-
-        if self.from_step:
-            if self.from_step not in self.steps:
-                raise GraphError(f"from_step ({self.from_step}) specified and not found in graph steps")
-            start_steps = [self.from_step]
-
-        self._start_steps = [self[name] for name in start_steps]
-
-        def first_in_function(step, current):
-            if getattr(step, "function", None) and step.function == current:
-                return step
-            for item in step.next or []:
-                found = first_in_function(self[item], current)
-                if found:
-                    return found
-            return None
-
-        current = get_current_function(self.context)
-        if current and current != "*":
-            new_starts = []
-            for start in self._start_steps:
-                step = first_in_function(start, current)
-                if step:
-                    new_starts.append(step)
-            if not new_starts:
-                raise GraphError(f"did not find steps pointing to current function ({current})")
-            self._start_steps = new_starts
-
-        if self.engine == "sync" and len(self._start_steps) > 1:
-            raise GraphError("sync engine can only have one starting step (without .after)")
-
-        default_final_step = None
-        if self.final_step:
-            if self.final_step not in self.steps:
-                raise GraphError(f"final_step ({self.final_step}) specified and not found in graph steps")
-            default_final_step = self.final_step
-        elif len(self._start_steps) == 1:
-            cur = self._start_steps[0]
-            while cur:
-                nxt = cur.next
-                if not nxt:
-                    default_final_step = cur.name
-                    break
-                cur = self[nxt[0]] if len(nxt) == 1 else None
-        return self._start_steps, default_final_step, responders
-
     # ---- async engine (storey emulation) ------------------------------------------------------
     def set_flow_source(self, source):
         self._source = source
@@ -795,13 +699,13 @@ class FlowStep(BaseStep):
         flow = _AsyncFlow(self.context)
 
         def link(state, node):
-            if not state._is_local_function(self.context) or state._visited:
+            if state._visited or not state._is_local_function(self.context):
                 return
-            for item in state.next or []:
-                nxt = self[item]
-                if getattr(nxt, "_node", None) is not None:
-                    node.outlets.append(nxt._node)
-                    link(nxt, nxt._node)
+            for key in state.next or []:
+                follower = self[key]
+                if getattr(follower, "_node", None) is not None:
+                    node.outlets.append(follower._node)
+                    link(follower, follower._node)
             state._visited = True
 
         for start in self._start_steps:
@@ -810,164 +714,125 @@ class FlowStep(BaseStep):
                 link(start, start._node)
 
         for step in self._steps.values():
-            node = getattr(step, "_node", None)
-            if (step.on_error or self.on_error) and node is not None:
-                err_step = self._steps[step.on_error or self.on_error]
-                if step is not err_step and getattr(err_step, "_node", None) is not None:
-                    node.recovery = err_step._node
-                    for item in err_step.next or []:
-                        nxt = self[item]
-                        nnode = getattr(nxt, "_node", None)
-                        if nnode is not None and nnode not in err_step._node.outlets:
-                            err_step._node.outlets.append(nnode)
+            node, target = getattr(step, "_node", None), step.on_error or self.on_error
+            if node is None or not target:
+                continue
+            catcher = self._steps[target]
+            cnode = getattr(catcher, "_node", None)
+            if catcher is step or cnode is None:
+                continue
+            node.recovery = cnode
+            for key in catcher.next or []:
+                fnode = getattr(self[key], "_node", None)
+                if fnode is not None and fnode not in cnode.outlets:
+                    cnode.outlets.append(fnode)
         self._async_flow = flow
 
     def _run_async_flow(self):
         self._controller = self._async_flow.run()
-
-    def is_empty(self):
-        return len(self.steps) == 0
-
-    def list_child_functions(self):
-        out = []
-        for step in self.get_children():
-            fn = getattr(step, "function", None)
-            if fn and fn not in out:
-                out.append(fn)
-        return out
-
-    def run(self, event, *args, **kwargs):
-        """states.py:1279-1323"""
-        if self._controller:
-            event._awaitable_result = None
-            resp = self._controller.emit(event, return_awaitable_result=self._wait_for_result)
-            if self._wait_for_result and resp:
-                return resp.await_result()
-            event = _copy.copy(event)
-            event.body = {"id": event.id}
-            return event
-
-        if len(self._start_steps) == 0:
-            return event
-        cur = self._start_steps[0]
-        while cur:
-            try:
-                event = cur.run(event, *args, **kwargs)
-            except Exception as exc:
-                if self._on_error_handler:
-                    self._log_error(event, exc, failed_step=cur.name)
-                    event.body = self._call_error_handler(event, exc)
-                    event.terminated = True
-                    return event
-                raise exc
-            if getattr(event, "terminated", None):
-                return event
-            if isinstance(getattr(event, "error", None), dict) and cur.name in event.error:
-                cur = self._steps[cur.on_error]
-            nxt = cur.next
-            if nxt and len(nxt) > 1:
-                raise GraphError(
-                    f"synchronous flow engine doesnt support branches use async, step={cur.name}"
-                )
-            cur = self[nxt[0]] if nxt else None
-        return event
 
     def wait_for_completion(self):
         if self._controller:
             self._controller.terminate()
             return self._controller.await_termination()
 
-    def _insert_all_error_handlers(self):
-        for name, step in self._steps.items():
-            if step.kind == "error_step":
-                self._insert_error_step(name, step)
-
-    def _insert_error_step(self, name, step):
-        """states.py:1362-1378"""
-        if not step.before and not any(step.name in other.after for other in self._steps.values()):
-            step.responder = True
-            return
-        for step_name in step.before:
-            if step_name not in self._steps.keys():
-                raise MLRunInvalidArgumentError(f"cant set before, there is no step named {step_name}")
-            self[step_name].after_step(name)
-
-    def set_flow(self, steps, force=False):
-        if not force and self.steps:
-            raise MLRunInvalidArgumentError(
-                "set_flow() called on a step that already has downstream steps. "
-                "If you want to overwrite existing steps, set force=True."
-            )
-        self.steps = None
-        step = self
-        for nxt in steps:
-            step = step.to(**nxt) if isinstance(nxt, dict) else step.to(nxt)
-        return step
-
     def supports_termination(self):
         return self.engine != "sync"
 
+    # ---- execution (states.py:1279-1323) -------------------------------------------------------------------
+    def run(self, event, *args, **kwargs):
+        if self._controller:
+            return self._run_async(event)
+        if not self._start_steps:
+            return event
+        step = self._start_steps[0]
+        while step:
+            try:
+                event = step.run(event, *args, **kwargs)
+            except Exception as exc:
+                if not self._on_error_handler:
+                    raise exc
+                self._log_error(event, exc, failed_step=step.name)  # graph-level handler: answer and stop
+                event.body = self._call_error_handler(event, exc)
+                event.terminated = True
+                return event
+            if getattr(event, "terminated", None):
+                return event
+            failed_here = isinstance(getattr(event, "error", None), dict) and step.name in event.error
+            if failed_here:
+                step = self._steps[step.on_error]  # the step's own handler ran: continue after it
+            followers = step.next
+            if followers and len(followers) > 1:
+                raise GraphError(f"synchronous flow engine doesnt support branches use async, step={step.name}")
+            step = self[followers[0]] if followers else None
+        return event
+
+    def _run_async(self, event):
+        event._awaitable_result = None
+        pending = self._controller.emit(event, return_awaitable_result=self._wait_for_result)
+        if self._wait_for_result and pending:
+            return pending.await_result()
+        receipt = _copy.copy(event)
+        receipt.body = {"id": receipt.id}
+        return receipt
+
 
 class RootFlowStep(FlowStep):
+    """the flow at the top of a function's graph"""
+
     kind = "root"
     _dict_fields = ["steps", "engine", "final_step", "on_error"]
 
 
-classes_map = {
-    "task": TaskStep,
-    "router": RouterStep,
-    "flow": FlowStep,
-    "queue": QueueStep,
-    "error_step": ErrorStep,
-}
+classes_map = {StepKinds.task: TaskStep, StepKinds.router: RouterStep, StepKinds.flow: FlowStep,
+               StepKinds.queue: QueueStep, StepKinds.error_step: ErrorStep}
 
 
 def graph_root_setter(server, graph):
-    """states.py:1520-1534"""
-    if graph:
-        if isinstance(graph, dict):
-            kind = graph.get("kind")
-        elif hasattr(graph, "kind"):
-            kind = graph.kind
-        else:
-            raise MLRunInvalidArgumentError("graph must be a dict or a valid object")
-        if kind == StepKinds.router:
-            server._graph = server._verify_dict(graph, "graph", RouterStep)
-        elif not kind or kind == StepKinds.root:
-            server._graph = server._verify_dict(graph, "graph", RootFlowStep)
-        else:
-            raise GraphError(f"illegal root step {kind}")
+    """states.py:1520-1534 -- a function's graph is a router or a (root) flow, given as object or wire dict"""
+    if not graph:
+        return
+    if isinstance(graph, dict):
+        kind = graph.get("kind")
+    elif hasattr(graph, "kind"):
+        kind = graph.kind
+    else:
+        raise MLRunInvalidArgumentError("graph must be a dict or a valid object")
+    if kind not in (None, "", StepKinds.root, StepKinds.router):
+        raise GraphError(f"illegal root step {kind}")
+    server._graph = server._verify_dict(graph, "graph", RouterStep if kind == StepKinds.router else RootFlowStep)
+
+
+def _step_from_object(obj, name, function, full_event, input_path, result_path):
+    """an object with to_dict() (a step / model / router instance) travels as its wire form"""
+    wire = obj.to_dict()
+    step = classes_map.get(wire.get("kind", StepKinds.task), RootFlowStep).from_dict(wire)
+    step.function = function
+    step.full_event = full_event or step.full_event
+    step.input_path = input_path or step.input_path
+    step.result_path = result_path or step.result_path
+    return name or wire.get("name", wire.get("class_name")), step
 
 
 def params_to_step(class_name, name, handler=None, graph_shape=None, function=None, full_event=None,
                    input_path=None, result_path=None, class_args=None):
-    """states.py:1548-1619"""
+    """states.py:1548-1619 -- the `to()` / `add_step()` arguments -> (step name, step): an object, a queue marker (">>",
+    "$queue"), a "*RouterClass", or a task class / handler"""
     class_args = class_args or {}
     if class_name and hasattr(class_name, "to_dict"):
-        struct = class_name.to_dict()
-        kind = struct.get("kind", StepKinds.task)
-        name = name or struct.get("name", struct.get("class_name"))
-        cls = classes_map.get(kind, RootFlowStep)
-        step = cls.from_dict(struct)
-        step.function = function
-        step.full_event = full_event or step.full_event
-        step.input_path = input_path or step.input_path
-        step.result_path = result_path or step.result_path
+        name, step = _step_from_object(class_name, name, function, full_event, input_path, result_path)
     elif class_name and class_name in queue_class_names:
         if "path" not in class_args:
             raise MLRunInvalidArgumentError("path=<stream path or None> must be specified for queues")
         if not name:
             raise MLRunInvalidArgumentError("queue name must be specified")
-        if full_event is not None:
-            class_args = class_args.copy()
-            class_args["full_event"] = full_event
-        step = QueueStep(name, **class_args)
+        extra = {"full_event": full_event} if full_event is not None else {}
+        step = QueueStep(name, **{**class_args, **extra})
     elif class_name and isinstance(class_name, str) and class_name.startswith("*"):
-        routes = class_args.get("routes", None)
-        class_name = class_name[1:]
-        name = get_name(name, class_name or "router")
-        step = RouterStep(class_name, class_args, handler, name=name, function=function, routes=routes,
-                          input_path=input_path, result_path=result_path)
+        router_class = class_name[1:]
+        name = get_name(name, router_class or "router")
+        step = RouterStep(router_class, class_args, handler, name=name, function=function,
+                          routes=class_args.get("routes", None), input_path=input_path, result_path=result_path)
     elif class_name or handler:
         name = get_name(name, class_name)
         step = TaskStep(class_name, class_args, handler, name=name, function=function, full_event=full_event,
