@@ -44,78 +44,65 @@ class ServingFunction:
         return f"{uri}:{self.tag}" if self.tag else uri
 
     def set_topology(self, topology=None, class_name=None, engine=None, exist_ok=False, **class_args):
+        """serving.py:245-306 -- the graph root: a router (default) or a flow"""
         topology = topology or StepKinds.router
         if self.spec.graph and not exist_ok:
             raise MLRunInvalidArgumentError("graph topology is already set, cannot be overwritten")
-        if topology == StepKinds.router:
-            if class_name and hasattr(class_name, "to_dict"):
-                _, step = params_to_step(class_name, None)
-                if step.kind != StepKinds.router:
-                    raise MLRunInvalidArgumentError(
-                        "provided class is not a router step, must provide a router class in router topology"
-                    )
-            else:
-                step = RouterStep(class_name=class_name, class_args=class_args)
-            self.spec.graph = step
-        elif topology == StepKinds.flow:
-            self.spec.graph = RootFlowStep(engine=engine)
-        else:
+        if topology == StepKinds.flow:
+            root = RootFlowStep(engine=engine)
+        elif topology != StepKinds.router:
             raise MLRunInvalidArgumentError(f"unsupported topology {topology}, use 'router' or 'flow'")
-        return self.spec.graph
+        elif class_name and hasattr(class_name, "to_dict"):  # a router instance
+            root = params_to_step(class_name, None)[1]
+            if root.kind != StepKinds.router:
+                raise MLRunInvalidArgumentError(
+                    "provided class is not a router step, must provide a router class in router topology")
+        else:
+            root = RouterStep(class_name=class_name, class_args=class_args)
+        self.spec.graph = root
+        return root
 
     def set_tracking(self, stream_path=None, batch=None, sample=None, stream_args=None, **kwargs):
+        """serving.py:308-354 -- tracking is a flag plus stream parameters read by the model servers"""
         self.spec.track_models = True
-        if stream_path:
-            self.spec.parameters["log_stream"] = stream_path
-        if batch:
-            self.spec.parameters["log_stream_batch"] = batch
-        if sample:
-            self.spec.parameters["log_stream_sample"] = sample
-        if stream_args:
-            self.spec.parameters["stream_args"] = stream_args
+        given = {"log_stream": stream_path, "log_stream_batch": batch, "log_stream_sample": sample, "stream_args": stream_args}
+        self.spec.parameters.update({k: v for k, v in given.items() if v})
+
+    def _router_for(self, router_step):
+        """the router a model is added to: the root, a named step of a flow, or the flow's only router"""
+        graph = self.spec.graph or self.set_topology()
+        if graph.kind == StepKinds.router:
+            return graph
+        if router_step:
+            if router_step not in graph:
+                raise ValueError(f"router step {router_step} not present in the graph")
+            return graph[router_step]
+        routers = [step for step in graph.steps.values() if step.kind == StepKinds.router]
+        if not routers:
+            raise ValueError("graph does not contain any router, add_model can only be used when there is a router step")
+        if len(routers) > 1:
+            raise ValueError(f"found {len(routers)} routers, please specify the router_step you would like to add this model to")
+        return routers[0]
 
     def add_model(self, key, model_path=None, class_name=None, model_url=None, handler=None,
                   router_step=None, child_function=None, **class_args):
-        graph = self.spec.graph
-        if not graph:
-            graph = self.set_topology()
-        if graph.kind != StepKinds.router:
-            if router_step:
-                if router_step not in graph:
-                    raise ValueError(f"router step {router_step} not present in the graph")
-                graph = graph[router_step]
-            else:
-                routers = [s for s in graph.steps.values() if s.kind == StepKinds.router]
-                if len(routers) == 0:
-                    raise ValueError(
-                        "graph does not contain any router, add_model can only be "
-                        "used when there is a router step"
-                    )
-                if len(routers) > 1:
-                    raise ValueError(
-                        f"found {len(routers)} routers, please specify the router_step"
-                        " you would like to add this model to"
-                    )
-                graph = routers[0]
-
-        if class_name and hasattr(class_name, "to_dict"):
+        """serving.py:356-445"""
+        router = self._router_for(router_step)
+        if class_name and hasattr(class_name, "to_dict"):  # a model-server instance
             if model_path:
                 class_name.model_path = model_path
-            key, state = params_to_step(class_name, key)
-        else:
-            if not model_path and not model_url:
-                raise ValueError("model_path or model_url must be provided")
-            class_name = class_name or self.spec.default_class
-            if class_name and not isinstance(class_name, str):
-                raise ValueError("class name must be a string (name of module.submodule.name)")
-            if model_path and not class_name:
-                raise ValueError("model_path must be provided with class_name")
-            if model_path:
-                model_path = str(model_path)
-            class_args = deepcopy(class_args)
-            class_args["model_path"] = model_path
-            state = TaskStep(class_name, class_args, handler=handler, function=child_function)
-        return graph.add_route(key, state)
+            key, route = params_to_step(class_name, key)
+            return router.add_route(key, route)
+        if not (model_path or model_url):
+            raise ValueError("model_path or model_url must be provided")
+        class_name = class_name or self.spec.default_class
+        if class_name and not isinstance(class_name, str):
+            raise ValueError("class name must be a string (name of module.submodule.name)")
+        if model_path and not class_name:
+            raise ValueError("model_path must be provided with class_name")
+        args = deepcopy(class_args)
+        args["model_path"] = str(model_path) if model_path else model_path
+        return router.add_route(key, TaskStep(class_name, args, handler=handler, function=child_function))
 
     def _get_serving_spec(self):
         return json.dumps(
