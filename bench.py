@@ -354,6 +354,10 @@ def main():
             handles = [None] * world
             dist.all_gather_object(handles, nat.ipc_export(merged_buf.ptr))
             peers = [merged_buf.ptr if r == rank else nat.ipc_open(handles[r]) for r in range(world)]
+            # the epilogue stores to the targets in list order: start every rank at its right-hand neighbour, so that at any
+            # moment the ranks write to DIFFERENT destinations instead of all converging on rank 0, then rank 1, ...
+            if os.environ.get("B2S_MERGE_ROTATE", "1") != "0":
+                peers = peers[rank + 1:] + peers[:rank + 1]
             plan.set_merge_targets(peers, rank * B)
         except Exception as exc:  # noqa: BLE001 -- no peer access on this box: use the NCCL merge
             print(f"[rank {rank}] p2p merge unavailable ({exc}); using nccl", file=sys.stderr)
