@@ -56,7 +56,7 @@ def format_outputs(values, flat=None):
     if flat is None:
         flat = a.ndim == 1
     rows, cols = (a.shape[0], 1) if a.ndim == 1 else a.shape
-    cap = 4 + rows * (cols * 28 + 4)
+    cap = 64 + rows * (cols * 32 + 4)  # the printer asks for 40 free bytes before each value
     buf = C.create_string_buffer(cap)
     n = C.c_int64()
     nat.check(nat.load().b2s_json_format_outputs(a.ctypes.data, 1 if a.dtype == np.int32 else 0, rows, cols, 1 if flat else 0,

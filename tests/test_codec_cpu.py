@@ -86,3 +86,30 @@ def test_format_is_byte_identical_to_json_dumps():
     resp = {"id": "e1", "model_name": "ens", "outputs": None, "model_version": "v1"}
     text = codec.dumps_with_outputs(resp, codec.format_outputs(vals[:4]))
     assert text == json.dumps({**resp, "outputs": [float(v) for v in vals[:4]]}).encode()
+
+
+def test_codec_property_fuzz():
+    """hypothesis: any float64 matrix json.dumps can print parses to the same float32 bits, and any float32 vector
+    prints to the same text as json.dumps"""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    floats = st.floats(allow_nan=True, allow_infinity=True, width=64)
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(st.lists(floats, min_size=3, max_size=3), min_size=1, max_size=6))
+    def parse_roundtrip(rows):
+        body = json.dumps({"id": "x", "inputs": rows})
+        got, _ = codec.parse_inputs(body)
+        with np.errstate(over="ignore"):
+            want = np.asarray(json.loads(body)["inputs"], dtype=np.float32)  # what the reference's decode gives
+        np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(st.floats(width=32, allow_nan=True, allow_infinity=True), min_size=1, max_size=8))
+    def print_identical(vals):
+        a = np.array(vals, dtype=np.float32)
+        assert codec.format_outputs(a) == json.dumps([float(v) for v in a]).encode()
+
+    parse_roundtrip()
+    print_identical()
