@@ -35,6 +35,17 @@ def _sanitized(category):
     return category
 
 
+def _ceil_f32(v):
+    """smallest float32 >= v.  The device compares float32 values with float32 constants; for a float32 x,
+    `x >= lo` and `x < hi` against the reference's float64 bounds are exactly `x >= ceil32(lo)` and `x < ceil32(hi)`."""
+    if not math.isfinite(v):
+        return v
+    f = np.float32(v)
+    if float(f) < v:
+        f = np.nextafter(f, np.float32(np.inf))
+    return float(f)
+
+
 def _num(v, what):
     if isinstance(v, bool) or not isinstance(v, (int, float, np.integer, np.floating)):
         raise LoweringError(f"{what}: {v!r} is not numeric; the device path handles numeric columns only")
@@ -92,13 +103,15 @@ class ColumnProgram:
                 for val, (lo, hi) in fmap["ranges"].items():
                     lo = -math.inf if lo == "-inf" else _num(lo, f"MapValues range of {name!r}")
                     hi = math.inf if hi == "inf" else _num(hi, f"MapValues range of {name!r}")
-                    ranges.append((lo, hi, _num(val, f"MapValues range label of {name!r}")))
+                    ranges.append((_ceil_f32(lo), _ceil_f32(hi), _num(val, f"MapValues range label of {name!r}")))
                 self.maps.setdefault(src, []).append(("range", ranges))
                 others = {k: v for k, v in fmap.items() if k != "ranges"}
                 if others:
                     raise LoweringError("MapValues mixing ranges and value replacements is rejected by the reference")
             else:
                 vm = {_num(k, f"MapValues key of {name!r}"): _num(v, f"MapValues value of {name!r}") for k, v in fmap.items()}
+                # a key that is not a float32 can never equal a float32 event value (the reference compares in float64)
+                vm = {k: v for k, v in vm.items() if not math.isfinite(k) or float(np.float32(k)) == k}
                 self.maps.setdefault(src, []).append(("value", vm))
             new_cols.append((name, src, kind, arg))
         self.cols = new_cols

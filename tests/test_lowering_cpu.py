@@ -125,3 +125,28 @@ def test_map_values_and_drop_lowering():
         ColumnProgram(names).apply(api_oracle.OneHotEncoder(mapping={"a": ["x", "y"]}))
     with pytest.raises(LoweringError):
         ColumnProgram(names).apply(api_oracle.MapValues(mapping={"a": {1: "one"}}))
+
+
+def test_range_bounds_that_are_not_float32_keep_the_reference_decisions():
+    """MapValues bounds like 0.7 or 0.1 are float64 in the reference; events carry float32 values.  The lowered float32
+    constants are rounded so that every float32 value falls in the same range as in the reference's float64 compare"""
+    edges = [0.1, 0.7, 0.3, 1.0 / 3.0]
+    vals = []
+    for e in edges:
+        f = np.float32(e)
+        vals += [np.nextafter(f, np.float32(-np.inf)), f, np.nextafter(f, np.float32(np.inf))]
+    X = np.array(vals + [0.0, 0.5, 2.0], dtype=np.float32).reshape(-1, 1)
+    mapping = {"a": {"ranges": {0: ["-inf", 0.1], 1: [0.1, 0.3], 2: [0.3, 1.0 / 3.0], 3: [1.0 / 3.0, 0.7], 4: [0.7, "inf"]}}}
+    prog = ColumnProgram(["a"])
+    prog.apply(api_oracle.MapValues(mapping=mapping))
+    got = emu.transform(prog, X)[:, 0]
+    step = api_oracle.MapValues(mapping=mapping)
+    want = [step._do_storey({"a": float(v)})["a"] for v in X[:, 0]]
+    np.testing.assert_array_equal(got, np.array(want, dtype=np.float32))
+    # value maps: a key that is not a float32 never matches
+    prog = ColumnProgram(["a"])
+    prog.apply(api_oracle.MapValues(mapping={"a": {0.1: 5, 0.5: 6}}))
+    got = emu.transform(prog, np.array([[0.1], [0.5]], dtype=np.float32))[:, 0]
+    step = api_oracle.MapValues(mapping={"a": {0.1: 5, 0.5: 6}})
+    want = [step._do_storey({"a": float(np.float32(v))})["a"] for v in (0.1, 0.5)]
+    np.testing.assert_array_equal(got, np.array(want, dtype=np.float32))
