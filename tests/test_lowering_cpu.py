@@ -150,3 +150,78 @@ def test_range_bounds_that_are_not_float32_keep_the_reference_decisions():
     step = api_oracle.MapValues(mapping={"a": {0.1: 5, 0.5: 6}})
     want = [step._do_storey({"a": float(np.float32(v))})["a"] for v in (0.1, 0.5)]
     np.testing.assert_array_equal(got, np.array(want, dtype=np.float32))
+
+
+def test_serving_lowering_fuzz_against_per_event_steps():
+    """hypothesis: random chains of Imputer / MapValues / OneHotEncoder / DropFeatures over feature-dict events --
+    whatever `ColumnProgram` accepts must give, row by row, the values and field order of the per-event steps"""
+    from hypothesis import HealthCheck, assume, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=200, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.data())
+    def run(data):
+        draw = data.draw
+        rng = np.random.default_rng(draw(st.integers(0, 10_000)))
+        n = draw(st.integers(1, 10))
+        num = [f"x{i}" for i in range(draw(st.integers(1, 3)))]
+        cat = [f"c{i}" for i in range(draw(st.integers(1, 2)))]
+        names = num + cat
+        X = np.empty((n, len(names)), dtype=np.float32)
+        for j, c in enumerate(names):
+            if c in num:
+                col = (rng.integers(-6, 7, size=n) / 4).astype(np.float32) + np.float32(draw(st.sampled_from([0.0, 0.1, 0.7])))
+                col[rng.random(n) < 0.25] = np.nan
+            else:
+                col = rng.integers(0, 5, size=n).astype(np.float32)
+            X[:, j] = col
+        live, steps = list(names), []
+        for kind in draw(st.lists(st.sampled_from(["imp", "map", "onehot", "drop"]), min_size=1, max_size=4)):
+            if kind == "imp":
+                # every numeric column needs a fill: without one the reference turns NaN into None, which its own later
+                # steps cannot compare; categorical codes are never missing here
+                steps.append(("Imputer", dict(mapping={c: draw(st.sampled_from([0.5, 0.1, -1.0])) for c in num if c in live}, default_value=0)))
+            elif kind == "map":
+                cands = [c for c in live if c in names]
+                if not cands:
+                    continue
+                col = draw(st.sampled_from(cands))
+                if col in num:
+                    fmap = {"ranges": {0: ["-inf", 0.1], 1: [0.1, 0.7], 2: [0.7, "inf"]}}
+                else:
+                    fmap = {0: 3, 1: 4, 9: 1}
+                steps.append(("MapValues", dict(mapping={col: fmap})))
+                live = [col]
+            elif kind == "onehot":
+                cands = [c for c in live if c in cat]
+                if not cands:
+                    continue
+                col = draw(st.sampled_from(cands))
+                steps.append(("OneHotEncoder", dict(mapping={col: [0, 1, 2]})))
+                live = [x for c in live for x in ([f"{col}_{k}" for k in (0, 1, 2)] if c == col else [c])]
+            elif kind == "drop" and len(live) > 1:
+                col = draw(st.sampled_from(live))
+                steps.append(("DropFeatures", dict(features=[col])))
+                live = [c for c in live if c != col]
+        assume(steps)
+        try:
+            prog = ColumnProgram(names)
+            for cls, kw in steps:
+                prog.apply(getattr(api_oracle, cls)(**{k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()}))
+        except LoweringError:
+            assume(False)
+        got = emu.transform(prog, X)
+        objs = [getattr(api_oracle, cls)(**{k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()}) for cls, kw in steps]
+        for r in range(n):
+            ev = {c: (int(X[r, j]) if c in cat else float(X[r, j])) for j, c in enumerate(names)}
+            try:
+                for o in objs:
+                    ev = o._do_storey(ev)
+            except Exception:  # noqa: BLE001 -- the reference itself fails on this event
+                assume(False)
+            assert list(ev.keys()) == prog.out_names
+            want = np.array([np.nan if v is None else float(v) for v in ev.values()], dtype=np.float64)
+            np.testing.assert_allclose(got[r].astype(np.float64), want, rtol=1e-7, atol=0, equal_nan=True,
+                                       err_msg=f"row {r} steps {[s[0] for s in steps]}")
+
+    run()
