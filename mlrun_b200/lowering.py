@@ -46,6 +46,19 @@ def _ceil_f32(v):
     return float(f)
 
 
+def _fill_in_same_range(fill, exact_ranges, name):
+    """the float32 the device imputes must fall in the range the reference's exact (float64) fill falls in"""
+    def label(x):
+        return next((i for i, (lo, hi) in enumerate(exact_ranges) if lo <= x < hi), None)
+
+    want = label(fill)
+    near = np.float32(fill)
+    for cand in (near, np.nextafter(near, np.float32(np.inf)), np.nextafter(near, np.float32(-np.inf))):
+        if label(float(cand)) == want:
+            return float(cand)
+    raise LoweringError(f"Imputer fill {fill!r} of {name!r}: no float32 next to it falls in the same MapValues range")
+
+
 def _num(v, what):
     if isinstance(v, bool) or not isinstance(v, (int, float, np.integer, np.floating)):
         raise LoweringError(f"{what}: {v!r} is not numeric; the device path handles numeric columns only")
@@ -99,11 +112,14 @@ class ColumnProgram:
                 raise LoweringError(f"MapValues on derived column {name!r} is not lowered")
             fmap = mapping[name]
             if "ranges" in fmap:
-                ranges = []
+                ranges, exact = [], []
                 for val, (lo, hi) in fmap["ranges"].items():
                     lo = -math.inf if lo == "-inf" else _num(lo, f"MapValues range of {name!r}")
                     hi = math.inf if hi == "inf" else _num(hi, f"MapValues range of {name!r}")
+                    exact.append((lo, hi))
                     ranges.append((_ceil_f32(lo), _ceil_f32(hi), _num(val, f"MapValues range label of {name!r}")))
+                if src in self.fills and len(self.maps.get(src, [])) == 0:
+                    self.fills[src] = _fill_in_same_range(self.fills[src], exact, name)
                 self.maps.setdefault(src, []).append(("range", ranges))
                 others = {k: v for k, v in fmap.items() if k != "ranges"}
                 if others:
@@ -111,6 +127,13 @@ class ColumnProgram:
             else:
                 vm = {_num(k, f"MapValues key of {name!r}"): _num(v, f"MapValues value of {name!r}") for k, v in fmap.items()}
                 # a key that is not a float32 can never equal a float32 event value (the reference compares in float64)
+                fill = self.fills.get(src) if len(self.maps.get(src, [])) == 0 else None
+                if fill is not None and fill in vm and float(np.float32(fill)) != fill:
+                    # the reference maps the exact (float64) fill through this key; the device fill is a float32 and would
+                    # miss it: impute the mapped value directly (it must not be a key itself, the map runs once)
+                    if vm[fill] in vm:
+                        raise LoweringError(f"Imputer fill {fill!r} of {name!r} maps to a value that is itself a key")
+                    self.fills[src] = vm[fill]
                 vm = {k: v for k, v in vm.items() if not math.isfinite(k) or float(np.float32(k)) == k}
                 self.maps.setdefault(src, []).append(("value", vm))
             new_cols.append((name, src, kind, arg))

@@ -225,3 +225,19 @@ def test_serving_lowering_fuzz_against_per_event_steps():
                                        err_msg=f"row {r} steps {[s[0] for s in steps]}")
 
     run()
+
+
+def test_imputed_values_keep_their_range_and_key():
+    """an Imputer fill equal to a non-float32 range bound (0.7) or map key (0.1): the reference maps the exact value"""
+    X = np.array([[np.nan, np.nan], [0.25, 0.5]], dtype=np.float32)
+    steps = lambda: [api_oracle.Imputer(mapping={"a": 0.7, "b": 0.1}),  # noqa: E731
+                     api_oracle.MapValues(mapping={"a": {"ranges": {0: ["-inf", 0.7], 1: [0.7, "inf"]}}, "b": {0.1: 5, 0.5: 6}})]
+    prog = ColumnProgram(["a", "b"])
+    for s in steps():
+        prog.apply(s)
+    got = emu.transform(prog, X)
+    for r in range(2):
+        ev = {"a": float(X[r, 0]), "b": float(X[r, 1])}
+        for s in steps():
+            ev = s._do_storey(ev)
+        np.testing.assert_array_equal(got[r], np.array(list(ev.values()), dtype=np.float32))
