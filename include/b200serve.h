@@ -66,8 +66,8 @@ typedef struct b2s_plan_s* b2s_plan_t;
 typedef struct b2s_stats {
   int64_t rows;          /* rows in the batch this call rode in                                  */
   float h2d_ms;          /* CUDA-event time of the host->device copy                             */
-  float kernel_ms;       /* CUDA-event time of the plan's kernels                                */
-  float d2h_ms;          /* CUDA-event time of the device->host copy                             */
+  float kernel_ms;       /* CUDA-event time of the plan's kernels (b2s_run_host pipelines large  */
+  float d2h_ms;          /* pinned batches in chunks: kernel/d2h are then sums over the chunks)   */
   float queue_us;        /* submit -> batch sealed (coalescing wait)                             */
   int32_t kernels;       /* kernel launches in the batch                                         */
   int32_t nonfinite_rows;/* rows flagged B2S_ROW_NONFINITE_INPUT                                 */

@@ -61,6 +61,7 @@ struct Global {
   int device = 0;
   cudaDeviceProp prop{};
   cudaStream_t stream = nullptr;  // library stream for run_device/run_host/time_device
+  cudaStream_t copy_stream = nullptr;  // host->device copies of a chunked run_host (kernels + D2H stay on `stream`)
   int ring_slots = 4;
   int64_t max_batch = 65536;
   int64_t max_wait_us = 200;
@@ -157,6 +158,7 @@ struct b2s_plan_s {
   int32_t* d_stage_status = nullptr;
   int64_t stage_rows = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> chunk_ev;  // 4 per chunk of a pipelined run_host: copied-in, kernel begin, kernel end, copied-out
   std::mutex host_mu;
   // coalescing ring
   std::vector<Slot> slots;
@@ -478,6 +480,7 @@ extern "C" int b2s_init(int device_ordinal, const char* cfg) {
   CUDA_TRY(cudaSetDevice(device_ordinal));
   CUDA_TRY(cudaGetDeviceProperties(&G.prop, device_ordinal));
   CUDA_TRY(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&G.copy_stream, cudaStreamNonBlocking));
   G.device = device_ordinal;
   std::string c = cfg ? cfg : "";
   G.ring_slots = (int)cfg_get(c, "ring_slots", 4);
@@ -492,7 +495,8 @@ extern "C" int b2s_shutdown(void) {
   std::lock_guard<std::mutex> lk(G.mu);
   if (!G.inited) return B2S_OK;
   cudaStreamDestroy(G.stream);
-  G.stream = nullptr;
+  cudaStreamDestroy(G.copy_stream);
+  G.stream = G.copy_stream = nullptr;
   G.inited = false;
   return B2S_OK;
 }
@@ -1370,6 +1374,68 @@ extern "C" int b2s_run_host(b2s_plan_t p, const void* rows, int64_t n_rows, int6
     src = p->h_stage_in;
   }
   const size_t out_sz = (size_t)n_rows * p->out_cols * 4;
+  // Large pinned batches run as a pipeline of chunks: chunk c+1 crosses PCIe while chunk c is computed, copied back and
+  // post-processed on the host, so the call costs about one H2D of the batch.  (Not with merge targets: their row offset
+  // is per launch.)
+  static const int64_t pipe_rows = getenv("B2S_HOST_CHUNK") ? atoll(getenv("B2S_HOST_CHUNK")) : 65536;  // measured: 16Ki 162, 32Ki 184, 64Ki 189 M events/s (one piece: 169)
+  if (pinned && pipe_rows > 0 && n_rows >= 2 * pipe_rows && p->peers.empty()) {
+    // whole tiles per chunk keep every chunk's base 16-byte (and tensor-map) aligned
+    const int64_t chunk = (int64_t)align_up((size_t)std::max<int64_t>(pipe_rows, (n_rows + 63) / 64), 1024);
+    const int n_chunks = (int)((n_rows + chunk - 1) / chunk);
+    while ((int)p->chunk_ev.size() < 4 * n_chunks) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreate(&e));
+      p->chunk_ev.push_back(e);
+    }
+    cudaStream_t cs = G.copy_stream;
+    int32_t* h_status = (int32_t*)(p->h_stage_out + out_sz);
+    const size_t out_row = (size_t)p->out_cols * 4;
+    CUDA_TRY(cudaEventRecord(p->ev[0], cs));
+    for (int c = 0; c < n_chunks; ++c) {
+      const int64_t r0 = (int64_t)c * chunk, nr = std::min<int64_t>(chunk, n_rows - r0);
+      cudaEvent_t* ce = &p->chunk_ev[4 * c];
+      CUDA_TRY(cudaMemcpyAsync(p->d_stage_in + r0 * row_bytes, (const char*)src + r0 * row_bytes, (size_t)nr * row_bytes,
+                               cudaMemcpyHostToDevice, cs));
+      CUDA_TRY(cudaEventRecord(ce[0], cs));
+      CUDA_TRY(cudaStreamWaitEvent(st, ce[0], 0));
+      CUDA_TRY(cudaEventRecord(ce[1], st));
+      if (int rc = launch_on(p, p->d_stage_in + r0 * row_bytes, nr, row_bytes, p->d_stage_out + r0 * out_row,
+                             p->d_stage_status + r0, st)) {
+        cudaStreamSynchronize(cs);
+        cudaStreamSynchronize(st);
+        return rc;
+      }
+      CUDA_TRY(cudaEventRecord(ce[2], st));
+      CUDA_TRY(cudaMemcpyAsync(p->h_stage_out + r0 * out_row, p->d_stage_out + r0 * out_row, (size_t)nr * out_row,
+                               cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(h_status + r0, p->d_stage_status + r0, (size_t)nr * 4, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaEventRecord(ce[3], st));
+    }
+    int bad = 0;
+    for (int c = 0; c < n_chunks; ++c) {  // hand each chunk to the caller as it lands
+      const int64_t r0 = (int64_t)c * chunk, nr = std::min<int64_t>(chunk, n_rows - r0);
+      CUDA_TRY(cudaEventSynchronize(p->chunk_ev[4 * c + 3]));
+      memcpy((char*)out + r0 * out_row, p->h_stage_out + r0 * out_row, (size_t)nr * out_row);
+      for (int64_t r = r0; r < r0 + nr; ++r) bad += (h_status[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
+      if (row_status) memcpy(row_status + r0, h_status + r0, (size_t)nr * 4);
+    }
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    if (stats) {
+      memset(stats, 0, sizeof(*stats));
+      stats->rows = n_rows;
+      cudaEventElapsedTime(&stats->h2d_ms, p->ev[0], p->chunk_ev[4 * (n_chunks - 1)]);
+      for (int c = 0; c < n_chunks; ++c) {  // the phases of different chunks overlap: these are sums over chunks
+        float k = 0.f, d = 0.f;
+        cudaEventElapsedTime(&k, p->chunk_ev[4 * c + 1], p->chunk_ev[4 * c + 2]);
+        cudaEventElapsedTime(&d, p->chunk_ev[4 * c + 2], p->chunk_ev[4 * c + 3]);
+        stats->kernel_ms += k;
+        stats->d2h_ms += d;
+      }
+      stats->kernels = p->kernels_per_batch * n_chunks;
+      stats->nonfinite_rows = bad;
+    }
+    return B2S_OK;
+  }
   CUDA_TRY(cudaEventRecord(p->ev[0], st));
   CUDA_TRY(cudaMemcpyAsync(p->d_stage_in, src, (size_t)n_rows * row_bytes, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaEventRecord(p->ev[1], st));
@@ -1610,6 +1676,7 @@ extern "C" int b2s_plan_destroy(b2s_plan_t p) {
   }
   for (int i = 0; i < 4; ++i)
     if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+  for (cudaEvent_t e : p->chunk_ev) cudaEventDestroy(e);
   if (p->d_blob) cudaFree(p->d_blob);
   if (p->d_t2_blob) cudaFree(p->d_t2_blob);
   if (p->d_pred) { cudaFree(p->d_pred); cudaFree(p->d_row_bad); }
