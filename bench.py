@@ -790,9 +790,9 @@ def main_enrich(args, rank, local_rank, world):
         for j in range(n_e2e):
             res = server.run_enriched(hk[j % 2], with_status=True)
         dt = time.perf_counter() - t0
-        e2e = {"value": world * Be * n_e2e / dt, "unit": "events/s", "h2d_bytes_per_step": Be * 8, "d2h_bytes_per_step": Be * 12,
-               "batch": Be, "steps": n_e2e, "api": "GraphServer.run_enriched(keys) (public API): host int64 keys -> H2D -> gather kernel -> "
-               "fused scoring plan -> D2H votes + status + found"}
+        e2e = {"value": world * Be * n_e2e / dt, "unit": "events/s", "h2d_bytes_per_step": Be * 8, "d2h_bytes_per_step": Be * 8,
+               "batch": Be, "steps": n_e2e, "api": "GraphServer.run_enriched(keys) (public API) -> b2s_table_enrich_host: host int64 keys -> H2D -> "
+               "gather kernel -> fused scoring plan -> D2H votes + status (pinned result block)"}
         del res
     if rank == 0:
         peak, peak_src = measured_peak()

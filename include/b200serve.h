@@ -45,6 +45,8 @@ typedef enum b2s_status {
                                      ValueError there (called from pkl_model_server.py:58) */
 #define B2S_ROW_BAD_LABEL 2       /* majority vote saw a negative label (serving/routers.py:717-725
                                      assumes labels 0..max) */
+#define B2S_ROW_UNKNOWN_KEY 4     /* b2s_table_enrich_host: the entity key is not in the online table (the reference's
+                                     OnlineVectorService.get returns None for it) */
 
 typedef struct b2s_plan_s* b2s_plan_t;
 
@@ -279,6 +281,12 @@ int b2s_table_info(b2s_table_t table, int64_t* n_keys, int32_t* n_features, int6
 int b2s_table_lookup_device(b2s_table_t table, const int64_t* d_keys, int64_t n, float* d_rows, int64_t row_stride_bytes,
                             int32_t* d_found, void* stream);
 int b2s_table_lookup_host(b2s_table_t table, const int64_t* keys, int64_t n, float* rows, int32_t* found, b2s_stats* stats);
+/* Enrichment + predict for a batch of HOST keys in one call (EnrichmentVotingEnsemble.do_event over a batch: preprocess
+ * :1335-1342, then the ensemble): keys -> H2D -> gather -> the scoring plan -> D2H of the plan's outputs and status words,
+ * nothing else crosses PCIe.  row_status (may be NULL) carries the plan's B2S_ROW_* bits plus B2S_ROW_UNKNOWN_KEY.
+ * Pinned caller buffers are used directly; pageable ones are staged through the table's pinned block. */
+int b2s_table_enrich_host(b2s_table_t table, b2s_plan_t plan, const int64_t* keys, int64_t n, void* out, int64_t out_bytes,
+                          int32_t* row_status, b2s_stats* stats);
 int b2s_table_time_device(b2s_table_t table, const int64_t* const* d_keys, int32_t n_bufs, int64_t n, float* d_rows,
                           int64_t row_stride_bytes, int32_t* d_found, int32_t n_iters, float* total_ms);
 /* 64-bit FNV-1a of each string of a packed buffer (string i = bytes[offsets[i] .. offsets[i+1])): the key of a

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb200serve.so")
 OUT_COPY, OUT_ONEHOT = 0, 1
 LINK_IDENTITY, LINK_BINARY_GT, LINK_BINARY_GE, LINK_ARGMAX = 0, 1, 2, 3
 VOTE_NONE, VOTE_MEAN, VOTE_MAJORITY = 0, 1, 2
-ROW_NONFINITE_INPUT, ROW_BAD_LABEL = 1, 2
+ROW_NONFINITE_INPUT, ROW_BAD_LABEL, ROW_UNKNOWN_KEY = 1, 2, 4
 COL_F32, COL_I32, COL_I64 = 0, 1, 2
 DATE_PARTS = {"year": 0, "month": 1, "day": 2, "hour": 3, "minute": 4, "second": 5, "day_of_week": 6, "dayofweek": 6,
               "weekday": 6, "day_of_year": 7, "dayofyear": 7, "quarter": 8, "is_leap_year": 9, "days_in_month": 10,
@@ -106,6 +106,7 @@ SIGNATURES = {
     "b2s_table_info": (C.c_int, [_vp, C.POINTER(_i64), _pi32, C.POINTER(_i64)]),
     "b2s_table_lookup_device": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "b2s_table_lookup_host": (C.c_int, [_vp, C.POINTER(_i64), _i64, _pf32, _pi32, C.POINTER(Stats)]),
+    "b2s_table_enrich_host": (C.c_int, [_vp, _vp, C.POINTER(_i64), _i64, _vp, _i64, _pi32, C.POINTER(Stats)]),
     "b2s_table_time_device": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i64, _vp, _i64, _vp, _i32, _pf32]),
     "b2s_hash_strings": (C.c_int, [C.c_char_p, C.POINTER(_i64), _i64, C.POINTER(_i64)]),
     # body codec

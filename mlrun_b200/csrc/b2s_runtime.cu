@@ -174,6 +174,13 @@ struct b2s_plan_s {
   int64_t ring_cap = 0;
 };
 
+int b2s_int_plan_shape(b2s_plan_s* p, int* n_in, int* out_cols) {
+  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+  *n_in = p->n_in;
+  *out_cols = p->out_cols;
+  return B2S_OK;
+}
+
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct BlobBuilder {

@@ -145,6 +145,12 @@ __global__ void __launch_bounds__(256) table_lookup_kernel(const __grid_constant
   }
 }
 
+// status[i] |= B2S_ROW_UNKNOWN_KEY where the key was not in the table (after the scoring plan wrote status)
+__global__ void mark_unknown_kernel(const int32_t* __restrict__ found, int32_t* __restrict__ status, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (!found[i]) status[i] |= B2S_ROW_UNKNOWN_KEY;
+}
+
 }  // namespace
 
 struct b2s_table_s {
@@ -163,6 +169,12 @@ struct b2s_table_s {
   float* d_out = nullptr;
   int32_t* d_found = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // enrich_host staging: votes + status on the device, one pinned block [keys | votes | status] on the host
+  int64_t enr_rows = 0;
+  int32_t enr_out_cols = 0;
+  float* d_votes = nullptr;
+  int32_t* d_status = nullptr;
+  char* h_pin = nullptr;
 };
 
 extern "C" int b2s_table_create(const int64_t* keys, int64_t n_keys, const float* values, int32_t n_features, const float* impute,
@@ -276,6 +288,89 @@ extern "C" int b2s_table_lookup_host(b2s_table_t t, const int64_t* keys, int64_t
   return B2S_OK;
 }
 
+static bool host_pinned(const void* ptr) {
+  cudaPointerAttributes attr{};
+  const bool yes = cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  return yes;
+}
+
+extern "C" int b2s_table_enrich_host(b2s_table_t t, b2s_plan_t plan, const int64_t* keys, int64_t n, void* out, int64_t out_bytes,
+                                     int32_t* row_status, b2s_stats* stats) {
+  if (!t || !keys || !out || n < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+  int n_in = 0, out_cols = 0;
+  if (int rc = b2s_int_plan_shape(plan, &n_in, &out_cols)) return rc;
+  if (n_in != t->n_feat) return b2s_int_fail(B2S_ERR_INVALID, "the table has %d features, the plan takes %d", t->n_feat, n_in);
+  if (out_bytes < n * out_cols * 4) return b2s_int_fail(B2S_ERR_INVALID, "out buffer too small");
+  if (n == 0) return B2S_OK;
+  std::lock_guard<std::mutex> lk(t->mu);
+  TAB_TRY(cudaSetDevice(b2s_int_device()));
+  const int64_t stride = (int64_t)t->n_feat * 4;
+  if (n > t->cap_rows) {
+    if (t->d_keys) { cudaFree(t->d_keys); cudaFree(t->d_out); cudaFree(t->d_found); t->d_keys = nullptr; }
+    t->cap_rows = 0;
+    const int64_t cap = std::max<int64_t>(n, 4096);
+    TAB_TRY(cudaMalloc(&t->d_keys, cap * 8));
+    TAB_TRY(cudaMalloc(&t->d_out, (size_t)cap * stride));
+    TAB_TRY(cudaMalloc(&t->d_found, cap * 4));
+    t->cap_rows = cap;
+  }
+  if (n > t->enr_rows || out_cols > t->enr_out_cols) {
+    if (t->d_votes) { cudaFree(t->d_votes); cudaFree(t->d_status); cudaFreeHost(t->h_pin); t->d_votes = nullptr; }
+    t->enr_rows = 0;
+    const int64_t cap = std::max<int64_t>(n, 4096);
+    const int32_t oc = std::max(out_cols, t->enr_out_cols);
+    TAB_TRY(cudaMalloc(&t->d_votes, (size_t)cap * oc * 4));
+    TAB_TRY(cudaMalloc(&t->d_status, cap * 4));
+    TAB_TRY(cudaMallocHost(&t->h_pin, (size_t)cap * (8 + (size_t)oc * 4 + 4)));
+    t->enr_rows = cap;
+    t->enr_out_cols = oc;
+  }
+  cudaStream_t st = b2s_int_stream();
+  int64_t* h_keys = (int64_t*)t->h_pin;
+  char* h_votes = t->h_pin + (size_t)t->enr_rows * 8;
+  int32_t* h_status = (int32_t*)(h_votes + (size_t)t->enr_rows * t->enr_out_cols * 4);
+  const size_t votes_sz = (size_t)n * out_cols * 4;
+  // pinned caller buffers are used as they are; pageable ones go through the pinned block (one host memcpy each way)
+  const void* k_src = keys;
+  if (!host_pinned(keys)) {
+    memcpy(h_keys, keys, (size_t)n * 8);
+    k_src = h_keys;
+  }
+  void* v_dst = host_pinned(out) ? out : (void*)h_votes;
+  int32_t* s_dst = row_status ? (host_pinned(row_status) ? row_status : h_status) : nullptr;
+  TAB_TRY(cudaEventRecord(t->ev[0], st));
+  TAB_TRY(cudaMemcpyAsync(t->d_keys, k_src, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  TAB_TRY(cudaEventRecord(t->ev[1], st));
+  if (int rc = launch_lookup(t, t->d_keys, n, t->d_out, stride, t->d_found, st)) return rc;
+  if (int rc = b2s_run_device(plan, t->d_out, n, stride, t->d_votes, t->d_status, st)) return rc;
+  {
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(4 * b2s_int_sm_count(), (n + 255) / 256));
+    b2s_int_count_launches(1);
+    mark_unknown_kernel<<<grid, 256, 0, st>>>(t->d_found, t->d_status, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return b2s_int_fail(B2S_ERR_CUDA, "mark_unknown launch failed: %s", cudaGetErrorString(e));
+  }
+  TAB_TRY(cudaEventRecord(t->ev[2], st));
+  TAB_TRY(cudaMemcpyAsync(v_dst, t->d_votes, votes_sz, cudaMemcpyDeviceToHost, st));
+  if (s_dst) TAB_TRY(cudaMemcpyAsync(s_dst, t->d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  TAB_TRY(cudaEventRecord(t->ev[3], st));
+  TAB_TRY(cudaStreamSynchronize(st));
+  if (v_dst != out) memcpy(out, h_votes, votes_sz);
+  if (s_dst && s_dst != row_status) memcpy(row_status, h_status, (size_t)n * 4);
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->rows = n;
+    cudaEventElapsedTime(&stats->h2d_ms, t->ev[0], t->ev[1]);
+    cudaEventElapsedTime(&stats->kernel_ms, t->ev[1], t->ev[2]);
+    cudaEventElapsedTime(&stats->d2h_ms, t->ev[2], t->ev[3]);
+    stats->kernels = 3;  // gather + the plan's kernel(s) + mark_unknown; the plan's own count is in b2s_plan_kernel
+    if (row_status)
+      for (int64_t r = 0; r < n; ++r) stats->nonfinite_rows += (row_status[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
+  }
+  return B2S_OK;
+}
+
 extern "C" int b2s_table_time_device(b2s_table_t t, const int64_t* const* d_keys, int32_t n_bufs, int64_t n, float* d_rows,
                                      int64_t row_stride_bytes, int32_t* d_found, int32_t n_iters, float* total_ms) {
   if (!t || !d_keys || n_bufs <= 0 || n_iters <= 0 || !total_ms) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
@@ -307,6 +402,9 @@ extern "C" int b2s_table_destroy(b2s_table_t t) {
   if (t->d_keys) cudaFree(t->d_keys);
   if (t->d_out) cudaFree(t->d_out);
   if (t->d_found) cudaFree(t->d_found);
+  if (t->d_votes) cudaFree(t->d_votes);
+  if (t->d_status) cudaFree(t->d_status);
+  if (t->h_pin) cudaFreeHost(t->h_pin);
   for (auto& e : t->ev)
     if (e) cudaEventDestroy(e);
   delete t;

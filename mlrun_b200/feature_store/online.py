@@ -69,6 +69,25 @@ class DeviceTable:
                                                   nat._p(rows, C.c_float), nat._p(found, C.c_int32), C.byref(stats)))
         return (rows, found.astype(bool), stats.as_dict()) if with_stats else (rows, found.astype(bool))
 
+    def enrich(self, plan, keys, with_stats=False):
+        """keys -> gather -> `plan` (a finalized DevicePlan over this table's features) -> (outputs, status) on the host, in
+        one C call (b2s_table_enrich_host); status carries ROW_UNKNOWN_KEY for keys that are not in the table.  The two
+        arrays share one pinned block of the pool (PCIe-speed D2H, no second copy); it is reused once they are collected."""
+        keys = np.ascontiguousarray(keys, dtype=np.int64)
+        n = len(keys)
+        out_b = (n * plan.out_cols * 4 + 63) // 64 * 64
+        block = nat.PINNED.take(out_b + n * 4) if n else None
+        if block is not None:
+            out = np.frombuffer(block, dtype=plan.out_dtype, count=n * plan.out_cols).reshape(n, plan.out_cols)
+            status = np.frombuffer(block, dtype=np.int32, count=n, offset=out_b)
+        else:
+            out = np.empty((n, plan.out_cols), dtype=plan.out_dtype)
+            status = np.empty(n, dtype=np.int32)
+        stats = nat.Stats()
+        nat.check(self._lib.b2s_table_enrich_host(self._h, plan._h, keys.ctypes.data_as(C.POINTER(C.c_int64)), n, out.ctypes.data,
+                                                  out.nbytes, nat._p(status, C.c_int32), C.byref(stats)))
+        return (out, status, stats.as_dict()) if with_stats else (out, status)
+
     def lookup_device(self, d_keys, n, d_rows, row_stride, d_found=None, stream=None):
         nat.check(self._lib.b2s_table_lookup_device(self._h, d_keys, int(n), d_rows, int(row_stride), d_found, stream))
 

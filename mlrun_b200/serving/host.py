@@ -286,10 +286,9 @@ class GraphServer(Serde):
 
     def run_enriched(self, keys, with_status=False):
         """batched enrichment + predict for a graph whose root is an Enrichment router: entity keys -> outputs with the
-        online-table gather (`b2s_table_lookup_device`) feeding the fused scoring plan (`b2s_run_device`) on the device --
-        two launches, no host round trip (replaces EnrichmentVotingEnsemble.preprocess + the per-model predicts,
-        serving/routers.py:1335-1342).  Unknown keys come back with status bit 4."""
-        from .. import _native as nat
+        online-table gather feeding the fused scoring plan on the device (`b2s_table_enrich_host`: keys in, votes and status
+        words out, nothing else crosses PCIe); replaces EnrichmentVotingEnsemble.preprocess + the per-model predicts,
+        serving/routers.py:1335-1342.  Unknown keys come back with status bit 4 (ROW_UNKNOWN_KEY)."""
         from ..lowering import LoweringError
 
         compiled = self.compile()
@@ -300,32 +299,8 @@ class GraphServer(Serde):
         plan = compiled.plan
         if plan.n_in != svc.table.n_feat:
             raise LoweringError(f"the feature vector has {svc.table.n_feat} features, the models take {plan.n_in}")
-        k = np.ascontiguousarray(svc._encode_keys(keys), dtype=np.int64)
-        n = len(k)
-        bufs = getattr(self, "_enrich_bufs", None)
-        if bufs is None or bufs[0] < n or bufs[1] is not plan:  # device staging, kept and grown across calls
-            cap = max(n, 4096)
-            bufs = (cap, plan, nat.DeviceBuffer(cap * 8), nat.DeviceBuffer(cap * plan.n_in * 4), nat.DeviceBuffer(cap * 4),
-                    nat.DeviceBuffer(cap * plan.out_cols * 4), nat.DeviceBuffer(cap * 4))
-            self._enrich_bufs = bufs
-        _cap, _plan, d_keys, d_rows, d_found, d_out, d_status = bufs
-        if n:
-            nat.check(nat.load().b2s_memcpy_h2d(d_keys.ptr, k.ctypes.data, n * 8))
-        svc.table.lookup_device(d_keys.ptr, n, d_rows.ptr, plan.n_in * 4, d_found.ptr)
-        plan.run_device(d_rows.ptr, n, plan.n_in * 4, d_out.ptr, d_status.ptr)
-        nat.load().b2s_device_sync()
-        def fetch(buf, dtype, shape):
-            a = np.empty(shape, dtype=dtype)
-            if a.nbytes:
-                nat.check(nat.load().b2s_memcpy_d2h(a.ctypes.data, buf.ptr, a.nbytes))
-            return a
-
-        out = fetch(d_out, plan.out_dtype, (n, plan.out_cols))
-        if not with_status:
-            return out
-        status = fetch(d_status, np.int32, (n,))
-        found = fetch(d_found, np.int32, (n,))
-        return out, status | np.where(found == 0, 4, 0).astype(np.int32)
+        out, status = svc.table.enrich(plan, svc._encode_keys(keys))
+        return (out, status) if with_status else out
 
     def run_json(self, body, event_id=None):
         """wire-level batched entry for graphs whose root is a router / model server: a V2 body

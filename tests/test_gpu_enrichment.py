@@ -129,3 +129,36 @@ def test_enrichment_router_per_event_and_fused_batch():
     mask = np.array([k != keys[5] for k in keys])
     np.testing.assert_allclose(out[:-1, 0][mask], ref, rtol=RTOL, atol=ATOL)
     assert (status[:-1] == 0).all() and status[-1] == 4
+
+
+def test_enrich_host_equals_lookup_then_plan_for_pinned_and_pageable_keys():
+    """b2s_table_enrich_host (one call: keys -> gather -> plan -> votes + status) against the two-call form
+    (b2s_table_lookup_host, then b2s_run_host on the rows it returned); staging grows across calls; unknown keys without an
+    impute value reach the models as NaN, so they carry both status bits"""
+    bvec, _ovec, keys, vals, feat = _vectors(n_keys=5000, n_feat=16, seed=9, key_kind="int")
+    coefs = np.random.default_rng(10).normal(size=(4, 16))
+    for policy in ({"*": "$mean"}, None):
+        server = _enriched_server(api_b200, bvec, policy, 4, coefs)
+        plan = server.compile().plan
+        table = server.graph._object._feature_service.table
+        rng = np.random.default_rng(11)
+        for n in (1, 33, 4096, 70001, 5):
+            ask = np.asarray(keys, dtype=np.int64)[rng.integers(0, len(keys), size=n)]
+            ask[::13] = 7  # not an entity
+            rows, found = table.lookup(ask)
+            want, want_st = plan.run(rows, with_status=True)
+            for pinned in (False, True):
+                k = ask
+                if pinned:
+                    k = nat.pinned_empty((n,), np.int64)
+                    k[:] = ask
+                got, st, stats = table.enrich(plan, k, with_stats=True)
+                np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+                np.testing.assert_array_equal(st, want_st | np.where(found, 0, nat.ROW_UNKNOWN_KEY))
+                assert stats["rows"] == n and stats["nonfinite_rows"] == int((want_st & 1).sum())
+            assert (st[::13] & nat.ROW_UNKNOWN_KEY).all() and not (st[1::13] & nat.ROW_UNKNOWN_KEY).any()
+            if policy is None:
+                assert (st[::13] & nat.ROW_NONFINITE_INPUT).all()
+    with pytest.raises(nat.NativeError):
+        other = _enriched_server(api_b200, _vectors(n_keys=50, n_feat=12, seed=3, key_kind="int")[0], None, 1, coefs[:1, :12])
+        table.enrich(other.compile().plan, np.array([1], dtype=np.int64))
