@@ -433,7 +433,7 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        Be = min(B, 262144)
+        Be = B  # the same batch as the device-timed step
         hin = [nat.pinned_empty((Be, F), np.float32) for _ in range(2)]
         for j, h in enumerate(hin):
             h[:] = np.roll(base[:Be].numpy(), j * 131, axis=0)
@@ -781,8 +781,10 @@ def main_enrich(args, rank, local_rank, world):
         lat.append(table.time_device([d_keys[0].data_ptr()], 4096, rows.data_ptr(), n_feat * 4, 1) * 1e3)
     e2e = None
     if not args.no_e2e:
-        Be = 262144
-        hk = [keys[rng.integers(0, n_keys, size=Be)] for _ in range(2)]
+        Be = B  # the same batch as the device-timed step
+        hk = [nat.pinned_empty((Be,), np.int64) for _ in range(2)]  # the step's inputs wait in pinned host memory
+        for h in hk:
+            h[:] = keys[rng.integers(0, n_keys, size=Be)]
         for j in range(2):
             server.run_enriched(hk[j % 2])
         n_e2e = max(5, min(args.steps, 20))

@@ -83,9 +83,9 @@ class DeviceTable:
         else:
             out = np.empty((n, plan.out_cols), dtype=plan.out_dtype)
             status = np.empty(n, dtype=np.int32)
-        stats = nat.Stats()
+        stats = nat.Stats() if with_stats else None
         nat.check(self._lib.b2s_table_enrich_host(self._h, plan._h, keys.ctypes.data_as(C.POINTER(C.c_int64)), n, out.ctypes.data,
-                                                  out.nbytes, nat._p(status, C.c_int32), C.byref(stats)))
+                                                  out.nbytes, nat._p(status, C.c_int32), C.byref(stats) if with_stats else None))
         return (out, status, stats.as_dict()) if with_stats else (out, status)
 
     def lookup_device(self, d_keys, n, d_rows, row_stride, d_found=None, stream=None):
