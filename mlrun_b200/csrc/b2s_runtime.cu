@@ -147,9 +147,15 @@ struct b2s_plan_s {
   int t2_NS = 1, t2_grid = 0, t2_block = 512, t2_smem = 0;
   T2Params t2{};
   char* d_t2_blob = nullptr;
-  double* d_pred = nullptr;
-  int32_t* d_row_bad = nullptr;
-  int64_t pred_rows = 0;
+  // per-model predictions between trees_model_kernel and vote_kernel: one scratch per stream the plan is launched on
+  // (launches on one stream are ordered; the ring's stream, the library stream and caller streams may overlap)
+  struct TreeScratch {
+    double* pred = nullptr;
+    int32_t* row_bad = nullptr;
+    int64_t rows = 0;
+  };
+  std::map<cudaStream_t, TreeScratch> t2_scratch;
+  std::mutex scratch_mu;
   // host staging for run_host
   char* h_stage_in = nullptr;
   char* h_stage_out = nullptr;
@@ -196,7 +202,7 @@ struct BlobBuilder {
 
 template <int MODE, int NS>
 static cudaError_t launch_rows(const KParams& kp, int grid, int block, cudaStream_t st) {
-  static bool attr_set = false;
+  static std::atomic<bool> attr_set{false};  // the dispatcher thread and callers may both get here first
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(rows_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)G.prop.sharedMemPerBlockOptin);
@@ -361,7 +367,7 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   using P = RTParams<NCH, NS>;
   constexpr int LMT = NCH >= 8 ? 2 : 1;  // the tensor-map variants exist for rows of >= 128 bytes
   constexpr int R2 = NCH >= 8 ? 2 : 1;
-  static bool attr_set = false;
+  static std::atomic<bool> attr_set{false};  // the dispatcher thread and callers may both get here first
   if (!attr_set) {
     const int cap = (int)G.prop.sharedMemPerBlockOptin;
     cudaError_t e = cudaFuncSetAttribute(rowthread_kernel<NCH, NS, TPR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
@@ -1251,20 +1257,28 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
   k.peer_off = p->peer_off;
   for (int g = 0; g < k.n_peers; ++g) k.peers[g] = (float*)p->peers[g];
   if (p->t2_ok) {
-    if (n_rows > p->pred_rows) {
-      if (p->d_pred) { cudaFree(p->d_pred); cudaFree(p->d_row_bad); }
-      p->pred_rows = std::max<int64_t>(n_rows, 65536);
-      CUDA_TRY(cudaMalloc(&p->d_pred, (size_t)p->pred_rows * p->kp.n_models * 8));
-      CUDA_TRY(cudaMalloc(&p->d_row_bad, (size_t)p->pred_rows * 4));
+    b2s_plan_s::TreeScratch sc;
+    {
+      std::lock_guard<std::mutex> lk(p->scratch_mu);
+      b2s_plan_s::TreeScratch& mine = p->t2_scratch[st];
+      if (n_rows > mine.rows) {  // cudaFree waits for the work that still reads the old buffers
+        if (mine.pred) { cudaFree(mine.pred); cudaFree(mine.row_bad); }
+        mine = b2s_plan_s::TreeScratch{};
+        const int64_t cap = std::max<int64_t>(n_rows, 65536);
+        CUDA_TRY(cudaMalloc(&mine.pred, (size_t)cap * p->kp.n_models * 8));
+        CUDA_TRY(cudaMalloc(&mine.row_bad, (size_t)cap * 4));
+        mine.rows = cap;
+      }
+      sc = mine;
     }
     T2Params t = p->t2;
     t.rows = (const char*)d_rows;
     t.row_stride = stride;
     t.n_rows = n_rows;
-    t.pred = p->d_pred;
-    t.row_bad = p->d_row_bad;
+    t.pred = sc.pred;
+    t.row_bad = sc.row_bad;
     t.vec_ok = k.vec_ok;
-    static bool t2_attr = false;
+    static std::atomic<bool> t2_attr{false};
     if (!t2_attr) {
       CUDA_TRY(cudaFuncSetAttribute(trees_model_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.prop.sharedMemPerBlockOptin));
       CUDA_TRY(cudaFuncSetAttribute(trees_model_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.prop.sharedMemPerBlockOptin));
@@ -1283,7 +1297,7 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return fail(B2S_ERR_CUDA, "tree kernel launch failed: %s", cudaGetErrorString(e2));
     const int vgrid = (int)std::max<int64_t>(1, std::min<int64_t>(4 * G.prop.multiProcessorCount, (n_rows + 255) / 256));
-    vote_kernel<<<vgrid, 256, 0, st>>>(k, p->d_pred, p->d_row_bad);
+    vote_kernel<<<vgrid, 256, 0, st>>>(k, sc.pred, sc.row_bad);
     e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return fail(B2S_ERR_CUDA, "vote kernel launch failed: %s", cudaGetErrorString(e2));
     return B2S_OK;
@@ -1686,7 +1700,8 @@ extern "C" int b2s_plan_destroy(b2s_plan_t p) {
   for (cudaEvent_t e : p->chunk_ev) cudaEventDestroy(e);
   if (p->d_blob) cudaFree(p->d_blob);
   if (p->d_t2_blob) cudaFree(p->d_t2_blob);
-  if (p->d_pred) { cudaFree(p->d_pred); cudaFree(p->d_row_bad); }
+  for (auto& kv : p->t2_scratch)
+    if (kv.second.pred) { cudaFree(kv.second.pred); cudaFree(kv.second.row_bad); }
   delete p;
   return B2S_OK;
 }
