@@ -12,25 +12,26 @@ import pandas as pd
 from .model_protocol import V2ModelServer
 
 
+def _as_model_input(inputs):
+    """a list whose first item is a dict becomes a frame OF THAT FIRST DICT; anything else an ndarray"""
+    first_is_dict = bool(inputs) and isinstance(inputs[0], dict)
+    return pd.DataFrame(inputs[0]) if first_is_dict else np.asarray(inputs)
+
+
 class PickleModelServer(V2ModelServer):
-    def load(self):
-        from cloudpickle import load
-
-        model_file, _ = self.get_model(".pkl")
-        with open(model_file, "rb") as fp:
-            self.model = load(fp)
-
-    def predict(self, request):
-        """np.asarray(inputs) -> model.predict -> tolist (pkl_model_server.py:52-60)"""
-        inputs = request["inputs"]
-        if inputs and isinstance(inputs[0], dict):
-            x = pd.DataFrame(inputs[0])
-        else:
-            x = np.asarray(inputs)
-        return self.model.predict(x).tolist()
-
     def explain(self, request):
         return f"A model server named '{self.name}'"
+
+    def predict(self, request):
+        """pkl_model_server.py:52-60: the third-party model's own predict, then tolist"""
+        return self.model.predict(_as_model_input(request["inputs"])).tolist()
+
+    def load(self):
+        import cloudpickle
+
+        path, _extra = self.get_model(".pkl")
+        with open(path, "rb") as handle:
+            self.model = cloudpickle.load(handle)
 
 
 SKLearnModelServer = PickleModelServer

@@ -11,74 +11,68 @@ event_id_key = "MLRUN-EVENT-ID"  # serving/utils.py:22
 event_path_key = "MLRUN-EVENT-PATH"  # serving/utils.py:23
 
 
-def _extract_input_data(input_path, body):
-    """serving/utils.py:26-31"""
-    if not input_path:
-        return body
+def _needs_mapping(body, which):
     if not hasattr(body, "__getitem__"):
-        raise TypeError("input_path parameter supports only dict-like event bodies")
-    return get_in(body, input_path)
+        raise TypeError(f"{which} parameter supports only dict-like event bodies")
+
+
+def _extract_input_data(input_path, body):
+    """the part of the body a step sees (serving/utils.py:26-31)"""
+    if input_path:
+        _needs_mapping(body, "input_path")
+        return get_in(body, input_path)
+    return body
 
 
 def _update_result_body(result_path, event_body, result):
-    """merge only when result_path AND a truthy body; otherwise replace (serving/utils.py:34-43)"""
-    if result_path and event_body:
-        if not hasattr(event_body, "__getitem__"):
-            raise TypeError("result_path parameter supports only dict-like event bodies")
-        update_in(event_body, result_path, result)
-        return event_body
-    return result
+    """the result is merged into the body only when there is a result_path AND a truthy body; else it replaces the body
+    (serving/utils.py:34-43)"""
+    if not (result_path and event_body):
+        return result
+    _needs_mapping(event_body, "result_path")
+    update_in(event_body, result_path, result)
+    return event_body
+
+
+_META = ("context", "name", "input_path", "result_path", "full_event", "kwargs")
+
+
+def _class_path(cls):
+    return cls.__qualname__ if cls.__module__ in ("__main__", "builtins") else f"{cls.__module__}.{cls.__qualname__}"
 
 
 class StepToDict:
-    """auto-serialise a step object from its __init__ signature (serving/utils.py:46-97)"""
+    """a step object describes itself from its constructor signature (serving/utils.py:46-97):
+    class_args = the non-None attributes named like constructor parameters (+ the saved **kwargs), minus the meta keys"""
 
-    meta_keys = ["context", "name", "input_path", "result_path", "full_event", "kwargs"]
+    meta_keys = list(_META)
+
+    def _constructor_fields(self, fields, exclude):
+        names = fields or getattr(self, "_dict_fields", None) or list(inspect.signature(self.__init__).parameters)
+        return [n for n in names if not (exclude and n in exclude)]
 
     def to_dict(self, fields=None, exclude=None, strip=False):
-        fields = fields or getattr(self, "_dict_fields", None)
-        if not fields:
-            fields = list(inspect.signature(self.__init__).parameters.keys())
-        if exclude:
-            fields = [f for f in fields if f not in exclude]
-
-        args = {}
-        for key in fields:
-            if key in self.meta_keys:
-                continue
-            val = getattr(self, key, None)
-            if val is not None:
-                args[key] = val
-        if "kwargs" in fields and (hasattr(self, "kwargs") or hasattr(self, "_kwargs")):
-            extra = getattr(self, "kwargs", {}) or getattr(self, "_kwargs", {})
-            for key, val in extra.items():
-                if key not in self.meta_keys:
-                    args[key] = val
-
-        module = self.__class__.__module__
-        path = self.__class__.__qualname__
-        if module not in ("__main__", "builtins"):
-            path = f"{module}.{path}"
-        struct = {
-            "class_name": path,
-            "name": self.name if getattr(self, "name", None) else self.__class__.__name__,
-            "class_args": args,
-        }
+        names = self._constructor_fields(fields, exclude)
+        args = {n: getattr(self, n) for n in names if n not in _META and getattr(self, n, None) is not None}
+        if "kwargs" in names and (hasattr(self, "kwargs") or hasattr(self, "_kwargs")):
+            saved = getattr(self, "kwargs", {}) or getattr(self, "_kwargs", {})
+            args.update({k: v for k, v in saved.items() if k not in _META})
+        out = {"class_name": _class_path(type(self)), "name": getattr(self, "name", None) or type(self).__name__,
+               "class_args": args}
         if hasattr(self, "_STEP_KIND"):
-            struct["kind"] = self._STEP_KIND
-        if getattr(self, "_input_path", None) is not None:
-            struct["input_path"] = self._input_path
-        if getattr(self, "_result_path", None) is not None:
-            struct["result_path"] = self._result_path
+            out["kind"] = self._STEP_KIND
+        for key, attr in (("input_path", "_input_path"), ("result_path", "_result_path")):
+            if getattr(self, attr, None) is not None:
+                out[key] = getattr(self, attr)
         if getattr(self, "_full_event", None):
-            struct["full_event"] = self._full_event
-        return struct
+            out["full_event"] = self._full_event
+        return out
 
 
 class RouterToDict(StepToDict):
-    """serving/utils.py:105-109"""
+    """routers never serialise their routes (serving/utils.py:105-109)"""
 
     _STEP_KIND = "router"
 
     def to_dict(self, fields=None, exclude=None, strip=False):
-        return super().to_dict(exclude=["routes"], strip=strip)
+        return StepToDict.to_dict(self, exclude=["routes"], strip=strip)
