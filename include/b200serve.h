@@ -283,8 +283,14 @@ int b2s_table_lookup_device(b2s_table_t table, const int64_t* d_keys, int64_t n,
 int b2s_table_lookup_host(b2s_table_t table, const int64_t* keys, int64_t n, float* rows, int32_t* found, b2s_stats* stats);
 /* Enrichment + predict for a batch of HOST keys in one call (EnrichmentVotingEnsemble.do_event over a batch: preprocess
  * :1335-1342, then the ensemble): keys -> H2D -> gather -> the scoring plan -> D2H of the plan's outputs and status words,
- * nothing else crosses PCIe.  row_status (may be NULL) carries the plan's B2S_ROW_* bits plus B2S_ROW_UNKNOWN_KEY.
+ * nothing else crosses PCIe (one fused launch when b2s_table_enrich_device covers the plan).  row_status (may be NULL) carries the plan's B2S_ROW_* bits plus B2S_ROW_UNKNOWN_KEY.
  * Pinned caller buffers are used directly; pageable ones are staged through the table's pinned block. */
+/* The same for device-resident keys, as ONE launch: the scoring kernel's tile loader finds each key in the table and
+ * fetches the row from there (one TMA bulk copy per row), so the gathered rows never travel to HBM and back; the table's
+ * impute policy folds into the kernel's Imputer operands.  B2S_ERR_UNSUPPORTED for plans the loader does not cover (tree
+ * ensembles, MapValues, one-hot sources under an impute policy): use b2s_table_lookup_device + b2s_run_device then. */
+int b2s_table_enrich_device(b2s_table_t table, b2s_plan_t plan, const int64_t* d_keys, int64_t n, void* d_out,
+                            int32_t* d_status, void* stream);
 int b2s_table_enrich_host(b2s_table_t table, b2s_plan_t plan, const int64_t* keys, int64_t n, void* out, int64_t out_bytes,
                           int32_t* row_status, b2s_stats* stats);
 int b2s_table_time_device(b2s_table_t table, const int64_t* const* d_keys, int32_t n_bufs, int64_t n, float* d_rows,

@@ -106,6 +106,7 @@ SIGNATURES = {
     "b2s_table_info": (C.c_int, [_vp, C.POINTER(_i64), _pi32, C.POINTER(_i64)]),
     "b2s_table_lookup_device": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "b2s_table_lookup_host": (C.c_int, [_vp, C.POINTER(_i64), _i64, _pf32, _pi32, C.POINTER(Stats)]),
+    "b2s_table_enrich_device": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "b2s_table_enrich_host": (C.c_int, [_vp, _vp, C.POINTER(_i64), _i64, _vp, _i64, _pi32, C.POINTER(Stats)]),
     "b2s_table_time_device": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i64, _vp, _i64, _vp, _i32, _pf32]),
     "b2s_hash_strings": (C.c_int, [C.c_char_p, C.POINTER(_i64), _i64, C.POINTER(_i64)]),

@@ -19,6 +19,7 @@
 #include <type_traits>
 
 #include "b2s_device.cuh"
+#include "b2s_hash.cuh"
 
 namespace b2s {
 
@@ -66,6 +67,13 @@ struct RTParams {
   int32_t cat_first[kRTMaxCatCols];  // dense columns: the categories are the integers first, first+1, ...
   int32_t cat_dense[kRTMaxCatCols];
   float cat_val[kRTMaxCats];
+  // fused enrichment (per-row bulk loader only): tile rows are fetched from an online table by entity key instead of
+  // from `rows` (b2s_table.cu).  Kept at the end: the offsets of everything above are those of the plain kernels.
+  const long long* g_keys;     // [n_rows]; null = rows come from `rows`
+  const TableSlot* g_slots;
+  uint64_t g_mask;
+  const float* g_values;       // [n_keys + 1][n_in]; row n_keys is all NaN and stands for an unknown key
+  long long g_missing_row;
 };
 
 // how a thread finds the 16-byte chunks of its row inside the shared-memory tile
@@ -298,6 +306,7 @@ __global__ void __launch_bounds__(128 * TPR / RPT, RPT == 2 ? RT_R2_MINB : (TPR 
   // bulk (TMA) variant: one mbarrier per stage; row `tid` of the tile is fetched by thread `tid`
   constexpr bool bulk = LM != 0;
   const uint32_t row_bytes = (uint32_t)p.n_in * 4u;
+  uint32_t unknown_bits = 0;  // bit s: the key of this thread's row in stage s is not in the table (gather loader)
   auto issue_bulk = [&](int st, int64_t row0) {
     int64_t left = p.n_rows - row0;
     const int rows = left < TR ? (left < 0 ? 0 : (int)left) : TR;
@@ -315,8 +324,17 @@ __global__ void __launch_bounds__(128 * TPR / RPT, RPT == 2 ? RT_R2_MINB : (TPR 
       }
     } else {
       if (tid == 0) mbar_expect_tx(&s_bar[st], (uint32_t)rows * row_bytes);
-      if (tid < rows)
-        bulk_load(s_tiles + st * tile_words + tid * p.pitch, p.rows + (row0 + tid) * p.row_stride, row_bytes, &s_bar[st]);
+      if (tid < rows) {
+        const char* src;
+        if (p.g_keys) {  // thread tid is also the q = 0 thread of tile row tid: it keeps the "unknown key" flag for the epilogue
+          const long long hit = table_find(p.g_slots, p.g_mask, p.g_keys[row0 + tid]);
+          unknown_bits = (unknown_bits & ~(1u << st)) | ((hit < 0 ? 1u : 0u) << st);
+          src = reinterpret_cast<const char*>(p.g_values + (hit < 0 ? p.g_missing_row : hit) * p.n_in);
+        } else {
+          src = p.rows + (row0 + tid) * p.row_stride;
+        }
+        bulk_load(s_tiles + st * tile_words + tid * p.pitch, src, row_bytes, &s_bar[st]);
+      }
     }
   };
   if (bulk) {
@@ -431,6 +449,7 @@ __global__ void __launch_bounds__(128 * TPR / RPT, RPT == 2 ? RT_R2_MINB : (TPR 
           acc[i][k] += p.bias[k];
           st |= (fabs(acc[i][k]) <= 1.7976931348623157e308) ? 0u : 1u;
         }
+        if (LM == 1) st |= ((unknown_bits >> stage) & 1u) << 2;  // B2S_ROW_UNKNOWN_KEY
         if (p.fast_epilogue) {
           if (p.vote_kind == 1) {  // VotingEnsemble._mean_vote: sum_m w[m] * pred[m], model order
             double s = 0.0;

@@ -137,6 +137,7 @@ struct b2s_plan_s {
   RWParams rw{};
   // row-thread kernel (constant-bank operands)
   bool rt_ok = false;
+  int rt_cat_cols = 0;  // one-hot source columns of the row-thread plan
   int rt_NCH = 0, rt_NS = 0, rt_TPR = 1, rt_grid = 0, rt_smem = 0, rt_tile_rows = 128, rt_pitch = 0, rt_stages = 2, rt_RPT = 1;
   std::vector<char> rt_blob;  // an RTParams<NCH, NS>
   // fused ensemble-merge targets (P2P)
@@ -363,7 +364,7 @@ static int rt_load_mode() {  // B2S_TMA: 0 cp.async (LDGSTS), 1 one TMA bulk cop
 
 template <int NCH, int NS, int TPR>
 static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
-                                int vec_ok, cudaStream_t st, bool query, int* occ) {
+                                int vec_ok, cudaStream_t st, bool query, int* occ, const B2SGather* gather) {
   using P = RTParams<NCH, NS>;
   constexpr int LMT = NCH >= 8 ? 2 : 1;  // the tensor-map variants exist for rows of >= 128 bytes
   constexpr int R2 = NCH >= 8 ? 2 : 1;
@@ -404,6 +405,24 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   r.stages = p->rt_stages;
   int mode = vec_ok ? rt_load_mode() : 0;
   if (mode == 2 && !tmap_ok) mode = 1;
+  if (gather) {  // rows come from the online table: one bulk copy per row, source found by key inside the kernel
+    mode = 1;
+    r.g_keys = gather->d_keys;
+    r.g_slots = reinterpret_cast<const TableSlot*>(gather->d_slots);
+    r.g_mask = gather->mask;
+    r.g_values = gather->d_values;
+    r.g_missing_row = gather->missing_row;
+    // the table's impute policy (None / NaN / Inf -> value, feature_vector.py:1046-1052) runs before the plan's own
+    // Imputer; on a column the plan reads as a number both fold into the kernel's one compare/select
+    if (gather->any_impute)
+      for (int c = 0; c < p->n_in; ++c) {
+        const float f = gather->h_impute[c];
+        if (f == f && r.lim[c] == std::numeric_limits<float>::infinity()) {
+          r.lim[c] = std::numeric_limits<float>::max();
+          r.fill[c] = f;
+        }
+      }
+  }
   int rpt = (mode == 2) ? p->rt_RPT : 1;
   int tr = p->rt_tile_rows;
   while (tr > 32 * rpt && (n_rows + tr - 1) / tr < (int64_t)G.prop.multiProcessorCount) tr /= 2;
@@ -440,10 +459,12 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
 
 template <int NCH, int NS>
 static cudaError_t rt_launch_t(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
-                               int vec_ok, cudaStream_t st, bool query, int* occ) {
-  if (p->rt_TPR == 1) return rt_launch_tt<NCH, NS, 1>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ);
-  if (NCH >= 8 && p->rt_TPR == 2) return rt_launch_tt<NCH, NS, (NCH >= 8 ? 2 : 1)>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ);
-  if (NCH >= 16 && p->rt_TPR == 4) return rt_launch_tt<NCH, NS, (NCH >= 16 ? 4 : 1)>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ);
+                               int vec_ok, cudaStream_t st, bool query, int* occ, const B2SGather* gather) {
+  if (p->rt_TPR == 1) return rt_launch_tt<NCH, NS, 1>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ, gather);
+  if (NCH >= 8 && p->rt_TPR == 2)
+    return rt_launch_tt<NCH, NS, (NCH >= 8 ? 2 : 1)>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ, gather);
+  if (NCH >= 16 && p->rt_TPR == 4)
+    return rt_launch_tt<NCH, NS, (NCH >= 16 ? 4 : 1)>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ, gather);
   return cudaErrorInvalidValue;
 }
 
@@ -469,8 +490,8 @@ static cudaError_t rt_launch_t(b2s_plan_s* p, const void* rows, int64_t stride, 
   } while (0)
 
 static cudaError_t rt_launch(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
-                             int vec_ok, cudaStream_t st, bool query = false, int* occ = nullptr) {
-  RT_DISPATCH(rt_launch_t, p, rows, stride, n_rows, out, status, vec_ok, st, query, occ);
+                             int vec_ok, cudaStream_t st, bool query = false, int* occ = nullptr, const B2SGather* gather = nullptr) {
+  RT_DISPATCH(rt_launch_t, p, rows, stride, n_rows, out, status, vec_ok, st, query, occ, gather);
   return cudaErrorInvalidValue;
 }
 static void rt_build_any(b2s_plan_s* p, const RTTables& t) {
@@ -1074,6 +1095,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       const int nch = (n_in + 3) / 4;
       p->rt_NCH = nch <= 4 ? 4 : (nch <= 8 ? 8 : (nch <= 16 ? 16 : 32));
       p->rt_NS = NS;
+      p->rt_cat_cols = n_cat_cols;
       bool simple = true;
       for (auto& m : p->models) simple = simple && m.link == B2S_LINK_IDENTITY && m.n_scores == 1;
       RTTables t{n_in, p->out_cols, M, p->vote_kind, p->out_is_int, (simple && p->vote_kind != B2S_VOTE_MAJORITY) ? 1 : 0, NS,
@@ -1344,6 +1366,21 @@ extern "C" int b2s_run_device(b2s_plan_t p, const void* d_rows, int64_t n_rows, 
   if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
   if (n_rows < 0 || row_stride_bytes < (int64_t)p->n_in * 4) return fail(B2S_ERR_INVALID, "bad n_rows/stride");
   return launch_on(p, d_rows, n_rows, row_stride_bytes, d_out, d_status, stream ? (cudaStream_t)stream : G.stream);
+}
+
+int b2s_int_launch_gathered(b2s_plan_s* p, const B2SGather& g, long long n, void* d_out, int* d_status, cudaStream_t st) {
+  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+  if (g.n_feat != p->n_in) return fail(B2S_ERR_INVALID, "the table has %d features, the plan takes %d", g.n_feat, p->n_in);
+  static const int fused = getenv("B2S_ENRICH_FUSED") ? atoi(getenv("B2S_ENRICH_FUSED")) : 1;
+  // the gather loader lives in the row-thread kernel (linear models, rows of whole 16-byte chunks); with a table impute
+  // policy, one-hot sources would need the policy applied before the category search: those plans gather first
+  if (!fused || !p->rt_ok || p->t2_ok || (p->n_in % 4) != 0) return fail(B2S_ERR_UNSUPPORTED, "plan is not fusable with the gather");
+  if (g.any_impute && p->rt_cat_cols > 0) return fail(B2S_ERR_UNSUPPORTED, "one-hot columns under a table impute policy gather first");
+  if (n <= 0) return B2S_OK;
+  G.launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = rt_launch(p, nullptr, (int64_t)p->n_in * 4, n, d_out, d_status, 1, st, false, nullptr, &g);
+  if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "row-thread (gather) kernel launch failed: %s", cudaGetErrorString(e));
+  return B2S_OK;
 }
 
 static int ensure_stage(b2s_plan_t p, int64_t n_rows) {

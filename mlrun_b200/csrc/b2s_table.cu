@@ -21,6 +21,7 @@
 
 #include "../../include/b200serve.h"
 #include "b2s_internal.h"
+#include "b2s_hash.cuh"
 
 #define TAB_TRY(expr)                                                                                       \
   do {                                                                                                      \
@@ -31,19 +32,8 @@
 
 namespace {
 
-struct Slot {
-  int64_t key;
-  int64_t row;  // -1: empty
-};
-
-__host__ __device__ inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
-  x ^= x >> 30;
-  x *= 0xbf58476d1ce4e5b9ULL;
-  x ^= x >> 27;
-  x *= 0x94d049bb133111ebULL;
-  x ^= x >> 31;
-  return x;
-}
+using Slot = b2s::TableSlot;
+using b2s::mix64;
 
 struct LookupParams {
   const Slot* slots;
@@ -69,17 +59,7 @@ __global__ void __launch_bounds__(256) table_lookup_kernel(const __grid_constant
     const int64_t q = base + lane;
     int64_t row = -1;
     if (q < p.n) {  // every lane probes for its own key
-      const int64_t key = p.keys[q];
-      uint64_t h = mix64((uint64_t)key) & p.mask;
-      for (;;) {
-        const Slot s = p.slots[h];
-        if (s.row < 0) break;
-        if (s.key == key) {
-          row = s.row;
-          break;
-        }
-        h = (h + 1) & p.mask;
-      }
+      row = b2s::table_find(p.slots, p.mask, p.keys[q]);
       if (p.found) p.found[q] = row >= 0 ? 1 : 0;
     }
     const int cnt = (int)((p.n - base < 32) ? (p.n - base) : 32);
@@ -161,6 +141,7 @@ struct b2s_table_s {
   Slot* d_slots = nullptr;
   float* d_values = nullptr;
   float* d_impute = nullptr;
+  std::vector<float> h_impute;  // host copy: the fused gather folds the policy into the scoring kernel's operands
   int grid = 0;
   // host-call staging
   std::mutex mu;
@@ -199,14 +180,20 @@ extern "C" int b2s_table_create(const int64_t* keys, int64_t n_keys, const float
   TAB_TRY(cudaSetDevice(b2s_int_device()));
   TAB_TRY(cudaMalloc(&t->d_slots, cap * sizeof(Slot)));
   TAB_TRY(cudaMemcpy(t->d_slots, slots.data(), cap * sizeof(Slot), cudaMemcpyHostToDevice));
-  TAB_TRY(cudaMalloc(&t->d_values, (size_t)n_keys * n_features * 4));
+  // one more row than keys: row n_keys is all NaN, what the fused gather copies for an unknown key
+  TAB_TRY(cudaMalloc(&t->d_values, ((size_t)n_keys + 1) * n_features * 4));
   TAB_TRY(cudaMemcpy(t->d_values, values, (size_t)n_keys * n_features * 4, cudaMemcpyHostToDevice));
+  {
+    const std::vector<float> nan_row((size_t)n_features, NAN);
+    TAB_TRY(cudaMemcpy(t->d_values + (size_t)n_keys * n_features, nan_row.data(), (size_t)n_features * 4, cudaMemcpyHostToDevice));
+  }
   std::vector<float> imp(((size_t)n_features + 3) / 4 * 4, NAN);
   if (impute)
     for (int c = 0; c < n_features; ++c) {
       imp[c] = impute[c];
       if (impute[c] == impute[c]) t->any_impute = 1;
     }
+  t->h_impute = imp;
   TAB_TRY(cudaMalloc(&t->d_impute, imp.size() * 4));
   TAB_TRY(cudaMemcpy(t->d_impute, imp.data(), imp.size() * 4, cudaMemcpyHostToDevice));
   int occ = 0;
@@ -288,6 +275,27 @@ extern "C" int b2s_table_lookup_host(b2s_table_t t, const int64_t* keys, int64_t
   return B2S_OK;
 }
 
+static int launch_fused(b2s_table_t t, b2s_plan_t plan, const int64_t* d_keys, int64_t n, void* d_out, int32_t* d_status, cudaStream_t st) {
+  B2SGather g{};
+  g.d_keys = reinterpret_cast<const long long*>(d_keys);
+  g.d_slots = t->d_slots;
+  g.mask = t->cap - 1;
+  g.d_values = t->d_values;
+  g.missing_row = t->n_keys;
+  g.h_impute = t->h_impute.data();
+  g.any_impute = t->any_impute;
+  g.n_feat = t->n_feat;
+  return b2s_int_launch_gathered(plan, g, n, d_out, d_status, st);
+}
+
+extern "C" int b2s_table_enrich_device(b2s_table_t t, b2s_plan_t plan, const int64_t* d_keys, int64_t n, void* d_out,
+                                       int32_t* d_status, void* stream) {
+  if (!t || !plan || !d_keys || !d_out || n < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+  if (n == 0) return B2S_OK;
+  TAB_TRY(cudaSetDevice(b2s_int_device()));
+  return launch_fused(t, plan, d_keys, n, d_out, d_status, stream ? (cudaStream_t)stream : b2s_int_stream());
+}
+
 static bool host_pinned(const void* ptr) {
   cudaPointerAttributes attr{};
   const bool yes = cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost;
@@ -342,14 +350,19 @@ extern "C" int b2s_table_enrich_host(b2s_table_t t, b2s_plan_t plan, const int64
   TAB_TRY(cudaEventRecord(t->ev[0], st));
   TAB_TRY(cudaMemcpyAsync(t->d_keys, k_src, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   TAB_TRY(cudaEventRecord(t->ev[1], st));
-  if (int rc = launch_lookup(t, t->d_keys, n, t->d_out, stride, t->d_found, st)) return rc;
-  if (int rc = b2s_run_device(plan, t->d_out, n, stride, t->d_votes, t->d_status, st)) return rc;
-  {
+  int n_kernels = 1;
+  int rc = launch_fused(t, plan, t->d_keys, n, t->d_votes, t->d_status, st);  // gather inside the scoring kernel
+  if (rc == B2S_ERR_UNSUPPORTED) {  // plans the gather loader does not cover: gather, score, fold the flags (3 launches)
+    n_kernels = 3;
+    if ((rc = launch_lookup(t, t->d_keys, n, t->d_out, stride, t->d_found, st))) return rc;
+    if ((rc = b2s_run_device(plan, t->d_out, n, stride, t->d_votes, t->d_status, st))) return rc;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(4 * b2s_int_sm_count(), (n + 255) / 256));
     b2s_int_count_launches(1);
     mark_unknown_kernel<<<grid, 256, 0, st>>>(t->d_found, t->d_status, n);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return b2s_int_fail(B2S_ERR_CUDA, "mark_unknown launch failed: %s", cudaGetErrorString(e));
+  } else if (rc) {
+    return rc;
   }
   TAB_TRY(cudaEventRecord(t->ev[2], st));
   TAB_TRY(cudaMemcpyAsync(v_dst, t->d_votes, votes_sz, cudaMemcpyDeviceToHost, st));
@@ -364,7 +377,7 @@ extern "C" int b2s_table_enrich_host(b2s_table_t t, b2s_plan_t plan, const int64
     cudaEventElapsedTime(&stats->h2d_ms, t->ev[0], t->ev[1]);
     cudaEventElapsedTime(&stats->kernel_ms, t->ev[1], t->ev[2]);
     cudaEventElapsedTime(&stats->d2h_ms, t->ev[2], t->ev[3]);
-    stats->kernels = 3;  // gather + the plan's kernel(s) + mark_unknown; the plan's own count is in b2s_plan_kernel
+    stats->kernels = n_kernels;  // 1: gather fused into the scoring kernel; 3: gather + the plan + mark_unknown
     if (row_status)
       for (int64_t r = 0; r < n; ++r) stats->nonfinite_rows += (row_status[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
   }

@@ -88,6 +88,16 @@ class DeviceTable:
                                                   out.nbytes, nat._p(status, C.c_int32), C.byref(stats) if with_stats else None))
         return (out, status, stats.as_dict()) if with_stats else (out, status)
 
+    def enrich_device(self, plan, d_keys, n, d_out, d_status=None, stream=None):
+        """device keys -> outputs (+ status) in ONE launch: the scoring kernel gathers its rows from the table
+        (b2s_table_enrich_device).  Returns False when the plan is not covered by the gather loader (nothing was launched:
+        use lookup_device + plan.run_device)."""
+        rc = self._lib.b2s_table_enrich_device(self._h, plan._h, d_keys, int(n), d_out, d_status, stream)
+        if rc == -6:  # B2S_ERR_UNSUPPORTED
+            return False
+        nat.check(rc)
+        return True
+
     def lookup_device(self, d_keys, n, d_rows, row_stride, d_found=None, stream=None):
         nat.check(self._lib.b2s_table_lookup_device(self._h, d_keys, int(n), d_rows, int(row_stride), d_found, stream))
 

@@ -156,9 +156,59 @@ def test_enrich_host_equals_lookup_then_plan_for_pinned_and_pageable_keys():
                 np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
                 np.testing.assert_array_equal(st, want_st | np.where(found, 0, nat.ROW_UNKNOWN_KEY))
                 assert stats["rows"] == n and stats["nonfinite_rows"] == int((want_st & 1).sum())
+                assert stats["kernels"] == 1  # the scoring kernel gathered its own rows (b2s_table_enrich_device)
             assert (st[::13] & nat.ROW_UNKNOWN_KEY).all() and not (st[1::13] & nat.ROW_UNKNOWN_KEY).any()
             if policy is None:
                 assert (st[::13] & nat.ROW_NONFINITE_INPUT).all()
     with pytest.raises(nat.NativeError):
         other = _enriched_server(api_b200, _vectors(n_keys=50, n_feat=12, seed=3, key_kind="int")[0], None, 1, coefs[:1, :12])
         table.enrich(other.compile().plan, np.array([1], dtype=np.int64))
+
+
+def test_enrich_device_one_launch_and_the_plans_it_does_not_cover():
+    """b2s_table_enrich_device on device-resident keys: one launch, same bits as gather-then-score; a tree ensemble is
+    not covered by the gather loader (B2S_ERR_UNSUPPORTED -> enrich_host gathers first, three launches)"""
+    from sklearn.ensemble import GradientBoostingRegressor
+
+    bvec, _ovec, keys, vals, feat = _vectors(n_keys=4000, n_feat=16, seed=12, key_kind="int")
+    coefs = np.random.default_rng(13).normal(size=(4, 16))
+    server = _enriched_server(api_b200, bvec, {"*": "$mean", "f3": 1.5}, 4, coefs)
+    plan = server.compile().plan
+    table = server.graph._object._feature_service.table
+    n = 10000
+    ask = np.asarray(keys, dtype=np.int64)[np.random.default_rng(14).integers(0, len(keys), size=n)]
+    ask[::17] = -3
+    rows, found = table.lookup(ask)
+    want, want_st = plan.run(rows, with_status=True)
+    d_keys, d_out, d_st = nat.DeviceBuffer(n * 8), nat.DeviceBuffer(n * plan.out_cols * 4), nat.DeviceBuffer(n * 4)
+    nat.check(nat.load().b2s_memcpy_h2d(d_keys.ptr, ask.ctypes.data, n * 8))
+    before = nat.launch_count()
+    assert table.enrich_device(plan, d_keys.ptr, n, d_out.ptr, d_st.ptr) is True
+    assert nat.launch_count() - before == 1
+    nat.load().b2s_device_sync()
+    got, st = np.empty_like(want), np.empty(n, dtype=np.int32)
+    nat.check(nat.load().b2s_memcpy_d2h(got.ctypes.data, d_out.ptr, got.nbytes))
+    nat.check(nat.load().b2s_memcpy_d2h(st.ctypes.data, d_st.ptr, st.nbytes))
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    np.testing.assert_array_equal(st, want_st | np.where(found, 0, nat.ROW_UNKNOWN_KEY))
+
+    # a tree ensemble behind the same router: not fusable, same results through the three-launch path
+    api_b200.register_feature_vector("store://vec", bvec)
+    fn = api_b200.new_function("enrich-trees", kind="serving")
+    graph = fn.set_topology("router", api_b200.EnrichmentVotingEnsemble(feature_vector_uri="store://vec", impute_policy={"*": 0.0},
+                                                                        vote_type="regression", executor_type="array"))
+    rng = np.random.default_rng(15)
+    Xf = rng.normal(size=(400, 16)).astype(np.float32)
+    for i in range(2):
+        m = GradientBoostingRegressor(n_estimators=8, max_depth=3, random_state=i).fit(Xf, Xf[:, i] * 2 + Xf[:, 5])
+        graph.add_route(f"t{i}", class_name="SKLearnModelServer", model=m, model_path="")
+    tserver = fn.to_mock_server(namespace={"SKLearnModelServer": api_b200.SKLearnModelServer})
+    tplan = tserver.compile().plan
+    ttable = tserver.graph._object._feature_service.table
+    assert ttable.enrich_device(tplan, d_keys.ptr, n, d_out.ptr, d_st.ptr) is False
+    rows, found = ttable.lookup(ask)
+    want, want_st = tplan.run(rows, with_status=True)
+    got, st, stats = ttable.enrich(tplan, ask, with_stats=True)
+    assert stats["kernels"] == 3
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    np.testing.assert_array_equal(st, want_st | np.where(found, 0, nat.ROW_UNKNOWN_KEY))
