@@ -15,6 +15,9 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <sched.h>
+#include <thread>
+#include <vector>
 
 #include "../../include/b200serve.h"
 #include "b2s_internal.h"
@@ -147,11 +150,28 @@ bool parse_number(Cur& c, float* out) {
   const char* from = s;
   auto r = std::from_chars(from, q, d);
   if (r.ec == std::errc::result_out_of_range) {
-    d = (*s == '-') ? -HUGE_VAL : HUGE_VAL;  // json.loads gives +-inf for 1e999 (and 0.0 for 1e-999)
-    bool tiny = false;
-    for (const char* t = s; t < q; ++t)
-      if ((*t == 'e' || *t == 'E') && t + 1 < q && t[1] == '-') tiny = true;
-    if (tiny) d = (*s == '-') ? -0.0 : 0.0;
+    if (integral) return false;  // an int too large for a double: np.asarray raises OverflowError; leave it to that path
+    // json.loads gives +-inf for 1e999 and +-0.0 for 1e-999 (or 0.000...1 with 400 zeros): decided by the decimal
+    // exponent of the first non-zero digit
+    const bool neg = *s == '-';
+    const char* t = neg ? s + 1 : s;
+    const char* dot = t;
+    while (dot < q && *dot >= '0' && *dot <= '9') ++dot;  // end of the integer digits
+    const char* nz = t;
+    while (nz < q && (*nz == '0' || *nz == '.')) ++nz;
+    long lead = nz < dot ? (long)(dot - nz - 1) : -(long)(nz - dot);
+    const char* ep = dot;
+    while (ep < q && *ep != 'e' && *ep != 'E') ++ep;
+    if (ep < q) {
+      long ex = 0;
+      const char* u = ep + 1;
+      const bool eneg = u < q && *u == '-';
+      if (u < q && (*u == '+' || *u == '-')) ++u;
+      for (; u < q; ++u)
+        if (ex < 100000000L) ex = ex * 10 + (*u - '0');
+      lead += eneg ? -ex : ex;
+    }
+    d = lead < 0 ? (neg ? -0.0 : 0.0) : (neg ? -HUGE_VAL : HUGE_VAL);
   } else if (r.ec != std::errc() || r.ptr != q) {
     return false;
   }
@@ -209,6 +229,108 @@ int repr_double(double v, char* buf) {
   return (int)(o - buf);
 }
 
+int codec_threads() {
+  static const int n = [] {
+    if (const char* e = getenv("B2S_CODEC_THREADS")) return atoi(e) < 1 ? 1 : atoi(e);
+    cpu_set_t set;
+    int cpus = 1;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
+    return cpus > 8 ? 8 : (cpus < 1 ? 1 : cpus);
+  }();
+  return n;
+}
+
+// Optimistic parallel parse of a large numeric matrix.  `first` points at the '[' of row 0.  Inside a numeric matrix every
+// ']' closes a row (or the matrix), so one memchr pass finds the rows; worker threads then parse disjoint row ranges with
+// the same parse_number as the sequential path.  Anything unexpected -- a string, a nested list, a ragged row, a row that
+// does not end where the scan said -- makes this return false WITHOUT a verdict: the caller re-parses sequentially, which
+// also produces the right error.  On success: rows / cols / n are set and `end` is just past the matrix's closing ']'.
+bool parse_matrix_parallel(const char* first, const char* limit, float* out, int64_t out_cap, int64_t* rows_out, int64_t* cols_out,
+                           const char** end) {
+  const int threads = codec_threads();
+  if (threads < 2 || limit - first < (1 << 18)) return false;
+  auto ws = [&](const char* p) {
+    while (p < limit && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+    return p;
+  };
+  std::vector<const char*> begin, stop;  // row r is the text (begin[r], stop[r]): after its '[' up to its ']'
+  const char* p = first;
+  for (;;) {
+    if (p >= limit || *p != '[') return false;
+    const char* close = static_cast<const char*>(memchr(p + 1, ']', (size_t)(limit - p - 1)));
+    if (!close) return false;
+    begin.push_back(p + 1);
+    stop.push_back(close);
+    p = ws(close + 1);
+    if (p >= limit) return false;
+    if (*p == ',') {
+      p = ws(p + 1);
+      continue;
+    }
+    if (*p != ']') return false;
+    ++p;  // the matrix's own ']'
+    break;
+  }
+  const int64_t rows = (int64_t)begin.size();
+  if (rows < 2 * threads) return false;
+  // row 0 fixes the width
+  int64_t cols = 0;
+  {
+    Cur c{begin[0], stop[0]};
+    c.ws();
+    if (c.p < c.end) {
+      float scratch;
+      for (;;) {
+        if (!parse_number(c, &scratch)) return false;
+        ++cols;
+        if (c.eat(',')) continue;
+        break;
+      }
+      c.ws();
+      if (c.p != c.end) return false;
+    }
+  }
+  if (rows * cols > out_cap) return false;  // the sequential path reports it
+  std::vector<char> ok((size_t)threads, 1);
+  auto work = [&](int t) {
+    const int64_t r0 = rows * t / threads, r1 = rows * (t + 1) / threads;
+    for (int64_t r = r0; r < r1; ++r) {
+      Cur c{begin[(size_t)r], stop[(size_t)r]};
+      float* dst = out + r * cols;
+      int64_t w = 0;
+      c.ws();
+      if (c.p < c.end) {
+        for (;;) {
+          float v;
+          if (!parse_number(c, &v)) {
+            ok[(size_t)t] = 0;
+            return;
+          }
+          if (w < cols) dst[w] = v;
+          ++w;
+          if (c.eat(',')) continue;
+          break;
+        }
+        c.ws();
+      }
+      if (c.p != c.end || w != cols) {
+        ok[(size_t)t] = 0;
+        return;
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+  for (char good : ok)
+    if (!good) return false;
+  *rows_out = rows;
+  *cols_out = cols;
+  *end = p;
+  return true;
+}
+
 }  // namespace
 
 extern "C" int b2s_json_parse_inputs(const char* body, int64_t len, float* out, int64_t out_cap, int64_t* n_rows, int64_t* n_cols,
@@ -236,6 +358,18 @@ extern "C" int b2s_json_parse_inputs(const char* body, int64_t len, float* out, 
       } else {
         c.ws();
         const bool nested = c.p < c.end && *c.p == '[';
+        if (nested) {  // large matrices: rows parsed by several threads (same values; falls through when unsure)
+          const char* after = nullptr;
+          if (parse_matrix_parallel(c.p, c.end, out, out_cap, &rows, &cols, &after)) {
+            *n_rows = rows;
+            *n_cols = cols;
+            if (value_begin) *value_begin = v0 - body;
+            if (value_end) *value_end = after - body;
+            return B2S_OK;
+          }
+          rows = 0;
+          cols = -1;
+        }
         for (;;) {
           if (nested) {
             if (!c.eat('[')) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "\"inputs\" mixes rows and scalars");

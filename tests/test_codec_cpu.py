@@ -34,6 +34,19 @@ def test_number_grammar_and_rounding():
     with np.errstate(over="ignore"):
         want = _ref(body)
     np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))  # bit-exact, including -0.0
+    # out-of-range floats written without an exponent, or with one that does not decide alone
+    texts = ["0." + "0" * 400 + "1", "-0." + "0" * 400 + "1", "1" + "0" * 400 + ".5", "-1" + "0" * 400 + ".0", "1e-400", "-1e-400",
+             "1e400", "0." + "0" * 10 + "1e-390", "1" + "0" * 20 + ".0e290", "0.001e-999", "123.456e-330", "0.0e999"]
+    body = '{"inputs": [[' + ", ".join(texts) + "]]}"
+    got, _ = codec.parse_inputs(body)
+    with np.errstate(over="ignore"):
+        want = _ref(body)
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    # an integer literal beyond the double range: np.asarray raises OverflowError, so the codec does not take the body
+    with pytest.raises(OverflowError):
+        _ref('{"inputs": [1' + "0" * 400 + "]}")
+    with pytest.raises(codec.NotV2Matrix):
+        codec.parse_inputs('{"inputs": [1' + "0" * 400 + "]}")
     body = '{"inputs": [NaN, Infinity, -Infinity, null, 2]}'
     got, _ = codec.parse_inputs(body)
     assert got.shape == (5, 1) and np.isnan(got[0, 0]) and got[1, 0] == np.inf and got[2, 0] == -np.inf and np.isnan(got[3, 0])
@@ -113,3 +126,55 @@ def test_codec_property_fuzz():
 
     parse_roundtrip()
     print_identical()
+
+
+def _big_rows(n_rows=3000, n_cols=40, seed=3):
+    rng = np.random.default_rng(seed)
+    return (rng.normal(size=(n_rows, n_cols)) * 10.0 ** rng.integers(-6, 7, size=(n_rows, n_cols))).tolist()
+
+
+def test_large_matrices_take_the_threaded_parser_with_the_same_results():
+    """bodies over 256 KB are split at the rows' closing brackets and parsed by several threads (b2s_codec.cpp
+    parse_matrix_parallel): same float32 bits and the same extents as json.loads, whatever the layout between rows"""
+    rows = _big_rows()
+    rows[17][3], rows[2999][39], rows[1500][0] = math.nan, math.inf, -math.inf
+    for sep, indent in ((", ", None), (",", None), (",\n   ", None), (", ", 1)):
+        inner = sep.join(json.dumps(r) for r in rows) if indent is None else json.dumps(rows, indent=indent)[1:-1]
+        body = '{"id": "big", "inputs": [' + inner + '], "model": "m"}'
+        assert len(body) > (1 << 18)
+        got, (b, e) = codec.parse_inputs(body)
+        want = np.asarray(json.loads(body)["inputs"], dtype=np.float32)
+        np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert body[b] == "[" and body[e - 1] == "]" and json.loads(body[:b] + "null" + body[e:]) == {"id": "big", "inputs": None, "model": "m"}
+    body = '{"inputs": [' + ", ".join(["[]"] * 80000) + "]}"  # many empty rows
+    got, _ = codec.parse_inputs(body)
+    assert got.shape == (80000, 0)
+    body = '{"inputs": [' + ", ".join(["[null, 1]"] * 40000) + "]}"
+    got, _ = codec.parse_inputs(body)
+    assert got.shape == (40000, 2) and np.isnan(got[:, 0]).all() and (got[:, 1] == 1).all()
+
+
+@pytest.mark.parametrize("spoil,error", [
+    (lambda rows: rows[2000].pop(), codec.NotV2Matrix),                       # ragged row
+    (lambda rows: rows[10].__setitem__(5, "x]y"), codec.NotV2Matrix),          # a string holding a bracket
+    (lambda rows: rows[2999].__setitem__(0, [1.0]), codec.NotV2Matrix),        # nested list
+    (lambda rows: rows[0].__setitem__(1, {"a": [1]}), codec.NotV2Matrix),      # dict in row 0
+    (lambda rows: rows.__setitem__(1234, 5.0), codec.NotV2Matrix),             # scalar between rows
+])
+def test_large_bodies_the_threaded_parser_cannot_take_are_classified_by_the_sequential_one(spoil, error):
+    rows = _big_rows()
+    spoil(rows)
+    body = json.dumps({"inputs": rows})
+    json.loads(body)
+    with pytest.raises(error):
+        codec.parse_inputs(body)
+
+
+def test_large_malformed_bodies_are_errors():
+    text = json.dumps({"inputs": _big_rows()})
+    for bad in (text[:-2], text.replace("], [", "] [", 1), text.replace("], [", "],, [", 1), text[: len(text) // 2]):
+        with pytest.raises(json.JSONDecodeError):
+            json.loads(bad)
+        with pytest.raises(Exception) as ei:
+            codec.parse_inputs(bad)
+        assert not isinstance(ei.value, AssertionError)  # NativeError, or NotV2Matrix -> json.loads raises for the caller
