@@ -4,11 +4,11 @@ Restates OnlineVectorService (mlrun/feature_store/feature_vector.py:903-1067) an
 `preprocess` (mlrun/serving/routers.py:1118-1196, 1199-1342).  The reference resolves each entity row by emitting it
 into a storey graph that reads the online (NoSQL) store; that read is storage (out of scope) and is restated here as a
 dict lookup -- **parity unpinned** for the store access itself (the reference only tests it against a live v3io /
-Redis), while everything around it (missing columns -> None, the impute policy incl. "$mean"-style statistics, index
-removal, the all-falsy-row -> None quirk, `as_list`) follows the source line by line.
+Redis).  Everything around it is PINNED: the golden scenario `online_service_logic` drives the REAL OnlineVectorService
+(initialize + get) over a stub controller that does the same dict lookup, and this class must give the same answers
+(missing columns -> None, the impute policy incl. "$mean"-style statistics, index removal, the all-falsy-row -> None
+quirk, `as_list`, the argument errors).
 """
-
-from copy import copy
 
 import numpy as np
 
@@ -57,72 +57,71 @@ class OnlineVectorService:
         self._impute_values = {}
 
     def initialize(self):
-        """feature_vector.py:935-968"""
-        if not self.impute_policy:
+        """resolve the impute policy into {feature: value} (feature_vector.py:935-968): "*" is the default for every feature
+        (the label excluded) that has no entry of its own; "$mean"-style values are looked up in the stats table"""
+        policy = dict(self.impute_policy)
+        if not policy:
             return
-        impute_policy = copy(self.impute_policy)
-        feature_stats = self.vector.get_stats_table()
-        self._impute_values = {}
-        feature_keys = list(self.vector.features)
-        if self.vector.label_column in feature_keys:
-            feature_keys.remove(self.vector.label_column)
-        if "*" in impute_policy:
-            value = impute_policy.pop("*")
-            for name in feature_keys:
-                if name not in impute_policy:
-                    if isinstance(value, str) and value.startswith("$"):
-                        self._impute_values[name] = feature_stats.loc[name, value[1:]]
-                    else:
-                        self._impute_values[name] = value
-        for name, value in impute_policy.items():
-            if name not in feature_keys:
-                raise MLRunInvalidArgumentError(f"feature {name} in impute_policy but not in feature vector")
-            if isinstance(value, str) and value.startswith("$"):
-                self._impute_values[name] = feature_stats.loc[name, value[1:]]
-            else:
-                self._impute_values[name] = value
+        stats = self.vector.get_stats_table()
+        imputable = [f for f in self.vector.features if f != self.vector.label_column]
+
+        def resolved(feature, value):
+            return stats.loc[feature, value[1:]] if isinstance(value, str) and value.startswith("$") else value
+
+        values = {}
+        if "*" in policy:
+            default = policy.pop("*")
+            values = {f: resolved(f, default) for f in imputable if f not in policy}
+        for feature, value in policy.items():
+            if feature not in imputable:
+                raise MLRunInvalidArgumentError(f"feature {feature} in impute_policy but not in feature vector")
+            values[feature] = resolved(feature, value)
+        self._impute_values = values
 
     def _read(self, row):
         """the storey QueryByKey graph: the entity row joined with what the online table holds for its key"""
-        key = tuple(row[k] for k in self._index_columns)
-        data = dict(row)
-        data.update(self.vector.table.get(key, {}))
-        return data
+        found = self.vector.table.get(tuple(row[k] for k in self._index_columns), {})
+        return {**row, **found}
+
+    def _entity_dicts(self, entity_rows):
+        """a dict is one row; rows given as lists are zipped with the index columns (feature_vector.py:997-1022)"""
+        rows = [entity_rows] if isinstance(entity_rows, dict) else entity_rows
+        if not (rows and isinstance(rows, list) and isinstance(rows[0], (list, dict))):
+            raise MLRunInvalidArgumentError(f"input data is of type {type(rows)}. must be a list of lists or list of dicts")
+        if isinstance(rows[0], dict):
+            return rows
+        names = self._index_columns
+        if not names or len(rows[0]) != len(names):
+            raise MLRunInvalidArgumentError("input list must be in the same size of the index_keys list")
+        return [{names[i]: item[i] for i in range(len(names))} for item in rows]
+
+    def _finish(self, data):
+        """one answer of the graph -> the row handed back, or None (feature_vector.py:1027-1056)"""
+        if not data:
+            return data
+        if all(column in self._index_columns for column in data):
+            return None  # only the entity columns came back: nothing is stored for this key
+        label = self.vector.label_column
+        for column in self._requested_columns:
+            if column != label:
+                data.setdefault(column, None)
+        if self._impute_values:
+            for column, v in data.items():
+                if v is None or (isinstance(v, float) and not np.isfinite(v)):
+                    data[column] = self._impute_values.get(column, v)
+        if not self.vector.with_indexes:
+            for column in self.vector.index_keys:
+                data.pop(column, None)
+        return data if any(data.values()) else None  # QUIRK: an all-falsy row (zeros) is reported as missing
 
     def get(self, entity_rows, as_list=False):
         """feature_vector.py:975-1067"""
+        label = self.vector.label_column
         results = []
-        if isinstance(entity_rows, dict):
-            entity_rows = [entity_rows]
-        if not entity_rows or not isinstance(entity_rows, list) or not isinstance(entity_rows[0], (list, dict)):
-            raise MLRunInvalidArgumentError(
-                f"input data is of type {type(entity_rows)}. must be a list of lists or list of dicts")
-        if isinstance(entity_rows[0], list):
-            if not self._index_columns or len(entity_rows[0]) != len(self._index_columns):
-                raise MLRunInvalidArgumentError("input list must be in the same size of the index_keys list")
-            entity_rows = [{self._index_columns[i]: item[i] for i in range(len(self._index_columns))} for item in entity_rows]
-        for row in entity_rows:
-            data = self._read(row)
-            if data:
-                actual_columns = data.keys()
-                if all(col in self._index_columns for col in actual_columns):
-                    results.append(None)  # didn't get any data from the graph
-                    continue
-                for column in self._requested_columns:
-                    if column not in actual_columns and column != self.vector.label_column:
-                        data[column] = None
-                if self._impute_values:
-                    for name in data.keys():
-                        v = data[name]
-                        if v is None or (isinstance(v, float) and (np.isinf(v) or np.isnan(v))):
-                            data[name] = self._impute_values.get(name, v)
-                if not self.vector.with_indexes:
-                    for name in self.vector.index_keys:
-                        data.pop(name, None)
-                if not any(data.values()):
-                    data = None
+        for row in self._entity_dicts(entity_rows):
+            data = self._finish(self._read(row))
             if as_list and data:
-                data = [data.get(key, None) for key in self._requested_columns if key != self.vector.label_column]
+                data = [data.get(column) for column in self._requested_columns if column != label]
             results.append(data)
         return results
 

@@ -61,3 +61,9 @@ def init_from_spec(spec, namespace):
     context.is_mock = True
     host.nuclio_init_hook(context, namespace, "serving_v2")
     return context
+
+
+def online_service(features, index_keys, table, stats, label_column, with_indexes, impute_policy):
+    """tests/scenarios.py online_service_logic: the oracle's OnlineVectorService over the same dict table"""
+    vec = _enrichment.FeatureVector("vec", features, index_keys, table, stats, label_column=label_column, with_indexes=with_indexes)
+    return vec.get_online_feature_service(impute_policy)

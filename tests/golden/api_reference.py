@@ -65,3 +65,28 @@ def init_from_spec(spec, namespace):
     context.is_mock = True
     nuclio_init_hook(context, namespace, "serving_v2")
     return context
+
+
+def online_service(features, index_keys, table, stats, label_column, with_indexes, impute_policy):
+    """the REAL OnlineVectorService (feature_store/feature_vector.py:903-1067) over a stub of the storey graph that reads
+    the online store: emit(row) answers with the row joined with the table's values for its key"""
+    import types
+
+    from mlrun.feature_store.feature_vector import OnlineVectorService
+
+    class _Controller:
+        def emit(self, row, return_awaitable_result=True):
+            data = dict(row)
+            data.update(table.get(tuple(row[k] for k in index_keys), {}))
+            return types.SimpleNamespace(await_result=lambda: types.SimpleNamespace(body=data))
+
+        def terminate(self):
+            pass
+
+    vector = types.SimpleNamespace(
+        status=types.SimpleNamespace(features={f: None for f in features}, label_column=label_column, index_keys=list(index_keys)),
+        spec=types.SimpleNamespace(with_indexes=with_indexes), get_stats_table=lambda: stats)
+    svc = OnlineVectorService(vector, types.SimpleNamespace(controller=_Controller()), list(index_keys), impute_policy,
+                              requested_columns=list(features))
+    svc.initialize()
+    return svc

@@ -1058,6 +1058,72 @@ merger_logic.EXPECT = {
 }
 
 
+def online_service_logic(api):
+    """feature_store/feature_vector.py:903-1067 -- OnlineVectorService.initialize / get driven directly.  The online-store
+    read (a storey QueryByKey graph over the NoSQL target) is the one thing replaced: a dict lookup that answers an entity
+    row with the row itself joined with what the table holds for its key (`api.online_service` wires it under each API)."""
+    import pandas as pd
+
+    feats = ["f0", "f1", "f2", "f3", "y"]
+    table = {
+        ("GOOG",): {"f0": 1.5, "f1": 2.0, "f2": -0.25, "f3": 8.0, "y": 1.0},
+        ("MSFT",): {"f0": float("nan"), "f1": float("inf"), "f2": None, "f3": float("-inf"), "y": 0.0},
+        ("ZERO",): {"f0": 0.0, "f1": 0.0, "f2": 0.0, "f3": 0.0, "y": 0.0},
+        ("PART",): {"f0": 4.0, "f3": 0.5},
+        ("INTS",): {"f0": 3, "f1": 0, "f2": float("nan"), "f3": 7, "y": 2},
+    }
+    stats = pd.DataFrame({"mean": [2.0, 0.75, -1.5, 3.25, 0.5], "min": [0.0, -2.0, -4.0, 0.5, 0.0], "max": [4.0, 2.0, 0.0, 8.0, 2.0],
+                          "std": [1.0, 0.5, 0.25, 2.0, 0.125], "count": [5.0, 5.0, 5.0, 5.0, 5.0]}, index=feats)
+
+    def norm(v):
+        if isinstance(v, float) and v != v:
+            return "nan"
+        if isinstance(v, float) and v in (float("inf"), float("-inf")):
+            return repr(v)
+        if isinstance(v, dict):
+            return {k: norm(x) for k, x in v.items()}
+        if isinstance(v, list):
+            return [norm(x) for x in v]
+        return v.item() if hasattr(v, "item") else v
+
+    def attempt(fn):
+        try:
+            return norm(fn())
+        except Exception as exc:  # noqa: BLE001
+            return {"raised": type(exc).__name__, "message": _first_line(str(exc))}
+
+    asks = [["GOOG"], ["MSFT"], ["nobody"], ["ZERO"], ["PART"], ["INTS"]]
+    out = {}
+    for tag, policy in (("none", None), ("mean", {"*": "$mean"}), ("mixed", {"*": 0.5, "f1": "$max", "f2": -3}),
+                        ("one", {"f3": "$min"}), ("zero", {"*": 0})):
+        svc = api.online_service(feats, ["ticker"], table, stats, "y", False, policy)
+        out[tag] = {"impute_values": norm(dict(svc._impute_values)),
+                    "lists": attempt(lambda: svc.get(asks, as_list=True)),
+                    "dicts": attempt(lambda: svc.get([{"ticker": k[0]} for k in asks])),
+                    "one_dict": attempt(lambda: svc.get({"ticker": "GOOG"})),
+                    "extra_column": attempt(lambda: svc.get([{"ticker": "nobody", "note": "x"}, {"ticker": "PART", "note": 7}]))}
+    with_idx = api.online_service(feats, ["ticker"], table, stats, "y", True, {"*": "$mean"})
+    out["with_indexes"] = {"dicts": attempt(lambda: with_idx.get([{"ticker": "MSFT"}, {"ticker": "ZERO"}, {"ticker": "nobody"}])),
+                           "lists": attempt(lambda: with_idx.get([["PART"]], as_list=True))}
+    no_label = api.online_service(feats[:4], ["ticker"], table, stats, None, False, {"*": "$max"})
+    out["no_label"] = attempt(lambda: no_label.get([["GOOG"], ["PART"]], as_list=True))
+    two = api.online_service(feats, ["a", "b"], {("x", 1): {"f0": 1.0, "f1": 2.0, "f2": 3.0, "f3": 4.0, "y": 1.0}}, stats, "y", False, None)
+    out["composite"] = {"hit_and_miss": attempt(lambda: two.get([["x", 1], ["x", 2]], as_list=True)),
+                        "short_row": attempt(lambda: two.get([["x"]]))}
+    plain = api.online_service(feats, ["ticker"], table, stats, "y", False, None)
+    out["bad_input"] = {"empty": attempt(lambda: plain.get([])), "scalars": attempt(lambda: plain.get(["GOOG"])),
+                        "string": attempt(lambda: plain.get("GOOG")), "tuple_rows": attempt(lambda: plain.get([("GOOG",)]))}
+    out["bad_policy"] = {"unknown_feature": attempt(lambda: api.online_service(feats, ["ticker"], table, stats, "y", False, {"zz": 1})),
+                         "label_in_policy": attempt(lambda: api.online_service(feats, ["ticker"], table, stats, "y", False, {"y": 1}))}
+    return out
+
+
+online_service_logic.EXPECT = {
+    ("mean", "lists", 2): None,  # unknown entity: the graph returned only the entity columns
+    ("none", "lists", 3): None,  # QUIRK: a row whose values are all falsy (0.0) is reported as missing
+}
+
+
 def merge_flows(api):
     """tests/serving/test_merger.py:87-128 -- split and merge through a served async graph (join on event.id, join on a
     body key, a missing key surfacing as the event's error)"""
@@ -1158,7 +1224,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_async_basic, flow_async_misc, merger_logic, merge_flows, steps_dict_events, steps_pandas_engine, vote_math,
+    route_cap, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, merge_flows, steps_dict_events, steps_pandas_engine, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
