@@ -67,3 +67,8 @@ def online_service(features, index_keys, table, stats, label_column, with_indexe
     """tests/scenarios.py online_service_logic: the oracle's OnlineVectorService over the same dict table"""
     vec = _enrichment.FeatureVector("vec", features, index_keys, table, stats, label_column=label_column, with_indexes=with_indexes)
     return vec.get_online_feature_service(impute_policy)
+
+
+def register_online_vector(uri, features, index_keys, table, stats, label_column, with_indexes):
+    register_feature_vector(uri, _enrichment.FeatureVector("vec", features, index_keys, table, stats, label_column=label_column,
+                                                         with_indexes=with_indexes))

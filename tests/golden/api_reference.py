@@ -90,3 +90,20 @@ def online_service(features, index_keys, table, stats, label_column, with_indexe
                               requested_columns=list(features))
     svc.initialize()
     return svc
+
+
+EnrichmentModelRouter = mlrun.serving.routers.EnrichmentModelRouter
+EnrichmentVotingEnsemble = mlrun.serving.routers.EnrichmentVotingEnsemble
+_ONLINE_VECTORS = {}
+
+
+def register_online_vector(uri, features, index_keys, table, stats, label_column, with_indexes):
+    """what `get_feature_vector(uri).get_online_feature_service(impute_policy=...)` answers for the REAL enrichment
+    routers (serving/routers.py:1180-1187): the REAL OnlineVectorService over the stub store read"""
+    import types
+
+    import mlrun.feature_store
+
+    _ONLINE_VECTORS[uri] = types.SimpleNamespace(get_online_feature_service=lambda impute_policy=None: online_service(
+        features, index_keys, table, stats, label_column, with_indexes, impute_policy))
+    mlrun.feature_store.get_feature_vector = lambda u, *a, **k: _ONLINE_VECTORS[u]

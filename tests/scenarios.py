@@ -1124,6 +1124,64 @@ online_service_logic.EXPECT = {
 }
 
 
+def enrichment_routers(api):
+    """serving/routers.py:1118-1196, 1199-1342 -- EnrichmentModelRouter / EnrichmentVotingEnsemble served: entity keys in
+    `inputs` become feature vectors (OnlineVectorService.get(as_list=True)) before the child models see them.  The
+    online-store read is the stub of `online_service_logic` (`api.register_online_vector`)."""
+    import pandas as pd
+    from sklearn.linear_model import LinearRegression
+
+    feats = ["f0", "f1", "f2", "f3"]
+    table = {("GOOG",): {"f0": 1.5, "f1": 2.0, "f2": -0.25, "f3": 8.0}, ("MSFT",): {"f0": float("nan"), "f1": 0.5, "f2": None, "f3": 1.0},
+             ("AMZN",): {"f0": 3.0, "f1": float("inf"), "f2": 2.0, "f3": -1.0}}
+    stats = pd.DataFrame({"mean": [2.0, 0.75, -1.5, 3.25], "max": [4.0, 2.0, 0.0, 8.0]}, index=feats)
+    api.register_online_vector("store://vectors/quotes", feats, ["ticker"], table, stats, None, False)
+    coefs = [[1.0, 2.0, 0.5, -1.0], [0.25, 0.0, 4.0, 1.0], [-2.0, 1.0, 1.0, 0.125]]
+    ns = {"SKLearnModelServer": api.SKLearnModelServer}
+
+    def served(router):
+        fn = api.new_function("enrich", kind="serving")
+        graph = fn.set_topology("router", router)
+        for i, c in enumerate(coefs):
+            m = LinearRegression()
+            m.coef_, m.intercept_, m.n_features_in_ = np.asarray(c, dtype=np.float64), 0.5 * i, 4
+            graph.add_route(f"m{i}", class_name="SKLearnModelServer", model=m, model_path="")
+        return fn.to_mock_server(namespace=ns)
+
+    def call(server, path, body):
+        resp = server.test(path, body=body, silent=True)
+        if hasattr(resp, "status_code"):
+            return {"status": resp.status_code, "error": _first_line(resp.body if isinstance(resp.body, str) else resp.body.decode()).split(":")[0]}
+        return _clean(resp)
+
+    out = {}
+    ens = served(api.EnrichmentVotingEnsemble(feature_vector_uri="store://vectors/quotes", impute_policy={"*": "$mean", "f1": "$max"},
+                                              vote_type="regression", executor_type="array"))
+    out["ensemble"] = {
+        "lists": call(ens, "/v2/models/infer", {"inputs": [["GOOG"], ["MSFT"], ["AMZN"]]}),
+        "dict_rows": call(ens, "/v2/models/infer", {"inputs": [{"ticker": "AMZN"}]}),
+        "text_body": call(ens, "/v2/models/infer", json.dumps({"inputs": [["GOOG"]]})),
+        "one_model": call(ens, "/v2/models/m1/infer", {"inputs": [["GOOG"], ["AMZN"]]}),
+        "unknown_entity": call(ens, "/v2/models/infer", {"inputs": [["GOOG"], ["nobody"]]}),
+    }
+    raw = served(api.EnrichmentModelRouter(feature_vector_uri="store://vectors/quotes"))
+    out["router_no_policy"] = {
+        "clean_row": call(raw, "/v2/models/m0/infer", {"inputs": [["GOOG"]]}),
+        "nan_row": call(raw, "/v2/models/m0/infer", {"inputs": [["MSFT"]]}),
+        "default_route": call(raw, "/v2/models/infer", {"inputs": [["GOOG"]]}),
+    }
+    fixed = served(api.EnrichmentModelRouter(feature_vector_uri="store://vectors/quotes", impute_policy={"*": 0.5}))
+    out["router_constant_policy"] = call(fixed, "/v2/models/m2/infer", {"inputs": [["MSFT"], ["AMZN"], ["GOOG"]]})
+    return out
+
+
+enrichment_routers.EXPECT = {
+    # GOOG = [1.5, 2.0, -0.25, 8.0]: m0 = 1.5 + 4 - 0.125 - 8 = -2.625; m1 = 0.375 - 1 + 8 + 0.5 = 7.875; m2 = -3 + 2 - 0.25 + 1 + 1 = 0.75
+    ("router_no_policy", "clean_row", "outputs"): [-2.625],
+    ("ensemble", "one_model", "outputs", 0): 7.875,
+}
+
+
 def merge_flows(api):
     """tests/serving/test_merger.py:87-128 -- split and merge through a served async graph (join on event.id, join on a
     body key, a missing key surfacing as the event's error)"""
@@ -1224,7 +1282,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, merge_flows, steps_dict_events, steps_pandas_engine, vote_math,
+    route_cap, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, merge_flows, steps_dict_events, steps_pandas_engine, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
