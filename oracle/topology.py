@@ -29,7 +29,7 @@ from .helpers import (
     get_class,
     get_function,
 )
-from .step_io import StepToDict, _extract_input_data, _update_result_body
+from .step_io import _extract_input_data, _update_result_body
 
 callable_prefix = "_"
 path_splitter = "/"
