@@ -14,7 +14,6 @@ rejected when the table is built; an unknown key matching a stored hash has prob
 """
 
 import ctypes as C
-from copy import copy
 
 import numpy as np
 
@@ -184,28 +183,31 @@ class OnlineVectorService:
 
     def initialize(self):
         """impute values (feature_vector.py:935-968), then the online rows go to the device"""
-        if self.impute_policy:
-            impute_policy = copy(self.impute_policy)
-            feature_stats = self.vector.get_stats_table()
-            feature_keys = list(self._columns)
-            if "*" in impute_policy:
-                value = impute_policy.pop("*")
-                for name in feature_keys:
-                    if name not in impute_policy:
-                        self._impute_values[name] = feature_stats.loc[name, value[1:]] if isinstance(value, str) and value.startswith("$") else value
-            for name, value in impute_policy.items():
-                if name not in feature_keys:
-                    raise MLRunInvalidArgumentError(f"feature {name} in impute_policy but not in feature vector")
-                self._impute_values[name] = feature_stats.loc[name, value[1:]] if isinstance(value, str) and value.startswith("$") else value
-            self._impute_values = {k: float(np.float32(v)) for k, v in self._impute_values.items()}
-            for k, v in self._impute_values.items():
-                if not np.isfinite(v):
-                    raise MLRunInvalidArgumentError(f"impute value of feature {k} is not finite ({v}): not held on the device")
+        self._impute_values = self._resolve_policy(dict(self.impute_policy)) if self.impute_policy else {}
         frame = self.vector.frame
         values = frame[self._columns].to_numpy(dtype=np.float32)
         keys = self._encode_keys(frame.index, build=True)
         impute = np.array([self._impute_values.get(c, np.nan) for c in self._columns], dtype=np.float32)
         self.table = DeviceTable(keys, values, impute if self._impute_values else None)
+
+    def _resolve_policy(self, policy):
+        """{feature | "*": constant | "$stat"} -> {feature: float32 value held on the device} (feature_vector.py:935-968)"""
+        stats = self.vector.get_stats_table()
+
+        def value_of(feature, spec):
+            v = stats.loc[feature, spec[1:]] if isinstance(spec, str) and spec.startswith("$") else spec
+            v = float(np.float32(v))
+            if not np.isfinite(v):
+                raise MLRunInvalidArgumentError(f"impute value of feature {feature} is not finite ({v}): not held on the device")
+            return v
+
+        default = policy.pop("*", None)
+        unknown = [f for f in policy if f not in self._columns]
+        if unknown:
+            raise MLRunInvalidArgumentError(f"feature {unknown[0]} in impute_policy but not in feature vector")
+        values = {} if default is None else {f: value_of(f, default) for f in self._columns if f not in policy}
+        values.update({f: value_of(f, spec) for f, spec in policy.items()})
+        return values
 
     def _encode_keys(self, raw, build=False):
         """entity keys -> int64: integers as they are, everything else through the 64-bit string hash"""
