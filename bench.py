@@ -260,19 +260,24 @@ def measured_peak():
 def run_reference(args, rank):
     if rank != 0:
         return
-    per_step = []
-    info = None
-    for _ in range(args.warmup):
-        pass  # the CPU path has no warm-up state worth timing; the calibration pass inside warms caches
-    budget = max(1.0, min(args.cpu_seconds, 150.0 / max(args.steps, 1)))
-    for _ in range(max(1, min(args.steps, 10))):
+    # a step = one bounded sample of the workload through the CPU path on all usable host cores; exactly K of them are
+    # timed after W untimed ones, sized so that the whole run stays within a few minutes
+    steps = max(1, args.steps)
+    budget = max(0.5, min(args.cpu_seconds, 150.0 / steps))
+    for _ in range(max(0, args.warmup)):
+        cpu_baseline(args.workload, min(budget, 1.0))
+    per_step, wall, info = [], [], None
+    for _ in range(steps):
+        t0 = time.perf_counter()
         info = cpu_baseline(args.workload, budget)
+        wall.append(time.perf_counter() - t0)
         per_step.append(info["value"])
     value = float(np.median(per_step))
     info["value"] = value
     print(json.dumps({
         "impl": "reference", "metric": "events/sec", "value": value, "unit": "events/s", "n_gpus": args.gpus,
-        "steps": len(per_step), "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+        "steps": len(per_step), "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(wall)), "higher_is_better": True,
+        "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_desc(args.workload), "engine": "sync per-event (oracle restatement of "
                    "mlrun.serving; storey/mlrun are not installable here)"},
