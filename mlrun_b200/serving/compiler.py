@@ -12,6 +12,8 @@ majority, regressors -> mean; the reference infers it from the first request's v
 scikit-learn models is the same thing).
 """
 
+import itertools
+
 import numpy as np
 
 from .. import _native as nat
@@ -31,24 +33,29 @@ class CompiledGraph:
         self.tracker = tracker      # the responder's _ModelLogPusher when model tracking is on (else None)
 
     def pack_events(self, bodies):
-        X = np.empty((len(bodies), len(self.in_names)), dtype=np.float32)
+        """feature-dict bodies -> (B, F) float32 rows; a None value is a missing value (NaN), as pd.isna treats it"""
+        names = tuple(self.in_names)
         for i, body in enumerate(bodies):
-            if list(body.keys()) != self.in_names:
+            if tuple(body) != names:
                 raise ValueError(f"event {i} does not carry the compiled schema {self.in_names[:4]}...")
-            X[i] = [np.nan if v is None else v for v in body.values()]
-        return X
+        n, width = len(bodies), len(names)
+        try:  # one pass over all values (2x the row-by-row assignment); float64 first: the same single rounding to float32
+            flat = np.fromiter(itertools.chain.from_iterable(map(dict.values, bodies)), dtype=np.float64, count=n * width)
+        except TypeError:  # a None (or a mapping that is not a dict) somewhere
+            flat = np.array([np.nan if v is None else v for body in bodies for v in body.values()], dtype=np.float64)
+        return flat.astype(np.float32).reshape(n, width)
 
     def responses(self, out, status, context):
         name, version = self.responder
+        head = {"model_name": name}
+        tail = {"model_version": version} if version else {}
+        rows, flagged = out.tolist(), status.tolist()
         res = []
-        for i in range(out.shape[0]):
-            if status[i]:
+        for row, bad in zip(rows, flagged):
+            if bad:
                 res.append(context.Response(body="ValueError: Input X contains NaN or infinity.", content_type="text/plain", status_code=400))
-                continue
-            body = {"model_name": name, "outputs": out[i].tolist()}
-            if version:
-                body["model_version"] = version
-            res.append(body)
+            else:
+                res.append({**head, "outputs": row, **tail})
         return res
 
 

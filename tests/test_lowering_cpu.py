@@ -241,3 +241,39 @@ def test_imputed_values_keep_their_range_and_key():
         for s in steps():
             ev = s._do_storey(ev)
         np.testing.assert_array_equal(got[r], np.array(list(ev.values()), dtype=np.float32))
+
+
+def test_event_packing_and_responses_of_the_batched_path():
+    """CompiledGraph.pack_events / responses (host code around the one fused launch of run_events)"""
+    import types
+
+    from mlrun_b200.serving.compiler import CompiledGraph
+
+    names = [f"f{i}" for i in range(7)]
+    cg = CompiledGraph(None, None, names, ("ens", "v1"))
+    rng = np.random.default_rng(8)
+    bodies = []
+    for i in range(50):
+        vals = [float(v) for v in rng.normal(size=7) * 10.0 ** rng.integers(-20, 20, size=7)]
+        vals[i % 7] = [None, 3, True, np.float32(0.1), np.float64(1e-50), float("nan"), 16777217][i % 7]
+        bodies.append(dict(zip(names, vals)))
+    want = np.empty((50, 7), dtype=np.float32)
+    for i, b in enumerate(bodies):  # the plain formulation: one row at a time, None -> NaN
+        want[i] = [np.nan if v is None else v for v in b.values()]
+    got = cg.pack_events(bodies)
+    assert got.dtype == np.float32 and got.flags["C_CONTIGUOUS"]
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    np.testing.assert_array_equal(cg.pack_events(bodies[1:2]).view(np.uint32), want[1:2].view(np.uint32))  # no None: the fast pass
+    with pytest.raises(ValueError, match="compiled schema"):
+        cg.pack_events([dict(reversed(list(bodies[0].items())))])
+    with pytest.raises(ValueError):
+        cg.pack_events([{**bodies[1], "f3": "text"}])
+    assert cg.pack_events([]).shape == (0, 7)
+
+    ctx = types.SimpleNamespace(Response=lambda **kw: types.SimpleNamespace(**kw))
+    out = np.array([[1.5], [2.5], [np.nan]], dtype=np.float32)
+    res = cg.responses(out, np.array([0, 0, 1], dtype=np.int32), ctx)
+    assert res[:2] == [{"model_name": "ens", "outputs": [1.5], "model_version": "v1"}, {"model_name": "ens", "outputs": [2.5], "model_version": "v1"}]
+    assert res[2].status_code == 400 and res[2].body.startswith("ValueError")
+    labels = CompiledGraph(None, None, names, ("clf", None)).responses(np.array([[2], [0]], dtype=np.int32), np.zeros(2, dtype=np.int32), ctx)
+    assert labels == [{"model_name": "clf", "outputs": [2]}, {"model_name": "clf", "outputs": [0]}] and type(labels[0]["outputs"][0]) is int
