@@ -170,6 +170,7 @@ class OnlineVectorService:
         self._impute_values = {}
         self.table = None
         self._string_keys = False
+        self._label_alive = None
 
     def __enter__(self):
         return self
@@ -187,6 +188,13 @@ class OnlineVectorService:
         frame = self.vector.frame
         values = frame[self._columns].to_numpy(dtype=np.float32)
         keys = self._encode_keys(frame.index, build=True)
+        # the label is not an online feature, but in the reference a truthy label keeps an all-zero row from being reported as
+        # missing (the `any(data.values())` quirk): remember which entities have one
+        label = self.vector.label_column
+        self._label_alive = None
+        if label and label in frame.columns:
+            col = frame[label]
+            self._label_alive = np.sort(keys[(col.notna() & col.map(bool)).to_numpy(dtype=bool)])  # a missing label is no label
         impute = np.array([self._impute_values.get(c, np.nan) for c in self._columns], dtype=np.float32)
         self.table = DeviceTable(keys, values, impute if self._impute_values else None)
 
@@ -233,6 +241,13 @@ class OnlineVectorService:
             raise MLRunInvalidArgumentError("two entity keys share a 64-bit hash (or a key is duplicated)")
         return keys
 
+    def _has_truthy_label(self, key):
+        alive = self._label_alive
+        if alive is None or not len(alive):
+            return False
+        j = int(np.searchsorted(alive, key))
+        return j < len(alive) and alive[j] == key
+
     # ---- batched engine surface --------------------------------------------------------------------
     def get_matrix(self, keys):
         """entity keys (one per row; tuples for composite keys) -> ((B, F) float32 imputed rows, found mask)"""
@@ -252,7 +267,8 @@ class OnlineVectorService:
                 raise MLRunInvalidArgumentError("input list must be in the same size of the index_keys list")
             entity_rows = [{idx[i]: item[i] for i in range(len(idx))} for item in entity_rows]
         keys = [row[idx[0]] if len(idx) == 1 else tuple(row[k] for k in idx) for row in entity_rows]
-        rows, found = self.get_matrix(keys)
+        encoded = self._encode_keys(keys)
+        rows, found = self.table.lookup(encoded)
         results = []
         for i, row in enumerate(entity_rows):
             if not found[i]:
@@ -270,9 +286,9 @@ class OnlineVectorService:
             if not self.vector.with_indexes:
                 for name in self.vector.index_keys:
                     data.pop(name, None)
-            if not any(data.values()):
+            if not any(data.values()) and not (found[i] and self._has_truthy_label(encoded[i])):
                 data = None
-            if as_list and data:
+            if as_list and data is not None:
                 data = [data.get(key, None) for key in self._requested_columns if key != self.vector.label_column]
             results.append(data)
         return results

@@ -104,3 +104,44 @@ def test_online_service_host_logic_matches_the_real_reference():
     _same(_norm(got["composite"], "y"), _norm(want["composite"], "y"), "composite")
     _same(got["bad_input"], want["bad_input"], "bad_input")
     _same(got["bad_policy"], want["bad_policy"], "bad_policy")
+
+
+def test_online_service_host_logic_fuzz_against_the_pinned_oracle():
+    """hypothesis: random online tables (None / NaN / Inf / zeros / missing columns), impute policies and asks; the
+    product's `get` (numpy stand-in for the device table) against the oracle's (pinned by the golden above)"""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from oracle import enrichment as oe
+
+    feats = ["a", "b", "c", "label"]
+    value = st.sampled_from([0.0, 1.0, -2.5, 8.0, 0.125, float("nan"), float("inf"), float("-inf"), None, 3])
+    # (a label stored as NaN / None is the same representational limit as for features: kept out of the label column here)
+    row = st.builds(lambda fv, lab: {**fv, **lab}, st.dictionaries(st.sampled_from(feats[:3]), value, min_size=1),
+                    st.dictionaries(st.just("label"), st.sampled_from([0.0, 1.0, 3, -2.5])))
+    tables = st.dictionaries(st.sampled_from(["k0", "k1", "k2", "k3", "k4"]), row, min_size=1)
+    policy_value = st.sampled_from([0, 0.5, -3, "$mean", "$max", "$min"])
+    policies = st.one_of(st.none(), st.dictionaries(st.sampled_from(["*", "a", "b", "c"]), policy_value, min_size=1))
+    stats = pd.DataFrame({"mean": [2.0, 0.75, -1.5, 0.5], "min": [0.0, -2.0, -4.0, 0.0], "max": [4.0, 2.0, 0.25, 2.0]}, index=feats)
+
+    @settings(max_examples=120, deadline=None)
+    @given(tables, policies, st.lists(st.sampled_from(["k0", "k1", "k2", "k3", "k4", "zz"]), min_size=1, max_size=6), st.booleans(),
+           st.booleans(), st.booleans())
+    def check(table, policy, asks, as_list, with_indexes, dict_rows):
+        keyed = {(k,): v for k, v in table.items()}
+        want_svc = oe.FeatureVector("v", feats, ["id"], keyed, stats, label_column="label", with_indexes=with_indexes
+                                    ).get_online_feature_service(policy)
+        got_svc = online_service(feats, ["id"], keyed, stats, "label", with_indexes, policy)
+        rows = [{"id": k} for k in asks] if dict_rows else [[k] for k in asks]
+        got = json.loads(json.dumps(got_svc.get(rows, as_list=as_list), default=str))
+        want = json.loads(json.dumps(want_svc.get([dict(r) for r in rows] if dict_rows else rows, as_list=as_list), default=str))
+        for g, w in zip(got, want):
+            if w is None and g is not None:
+                # QUIRK x representation: the reference drops a row whose values are all falsy, and a missing value is a None
+                # (falsy) there but a NaN (truthy) in a float32 table -- so a row of zeros-and-missing survives here
+                vals = g if as_list else [v for k, v in g.items() if k not in ("id", "label")]
+                assert any(_norm(v, None) == "missing" for v in vals) and all(_norm(v, None) == "missing" or not v for v in vals), (g, w)
+                continue
+            _same(_norm(g, "label"), _norm(w, "label"))
+
+    check()
