@@ -77,3 +77,43 @@ def test_enrichment_routers_served_match_the_real_reference(monkeypatch):
 
     got = json.loads(json.dumps(scenarios.enrichment_routers(Api()), default=str))
     assert_same(got, GOLDEN["enrichment_routers"], "enrichment_routers", rtol=RTOL, atol=ATOL)
+
+
+def _gpu_serving_cases():
+    from tests import test_gpu_serving as g  # its own tests are `-m gpu`; here their bodies run on the emulated plan
+
+    return [g.test_run_events_reports_bad_rows_as_400, g.test_router_of_tree_models_run_batch_and_single_route,
+            g.test_unlowerable_graph_is_a_hard_error, g.test_run_json_answers_like_the_reference_wire_path,
+            g.test_tracked_batches_emit_the_per_event_records]
+
+
+@pytest.mark.parametrize("case", _gpu_serving_cases(), ids=lambda f: f.__name__)
+def test_gpu_serving_cases_hold_on_the_emulated_plan(case):
+    """the host-side assertions of tests/test_gpu_serving.py (400s for flagged rows, single routes, the wire path through
+    the C body codec, tracked batches) do not depend on the device: they must hold with the numpy plan too"""
+    case()
+
+
+def _gpu_parity_cases():
+    from tests import test_gpu_parity as g
+
+    return [
+        (g.test_flow3_matches_oracle, dict(n_models=1, n_rows=129)), (g.test_flow3_matches_oracle, dict(n_models=4, n_rows=1000)),
+        (g.test_flow3_per_model_outputs_and_per_event_oracle, {}),
+        (g.test_flow3_matches_reference_golden, dict(name="flow3_linear_events", n_models=1)),
+        (g.test_flow3_matches_reference_golden, dict(name="flow3_ensemble_events", n_models=4)),
+        (g.test_onehot_edge_values_and_sparse_categories, {}), (g.test_nonfinite_input_sets_row_status, {}),
+        (g.test_transform_only_plan_is_exact, {}), (g.test_map_values_and_drop, {}),
+        (g.test_tree_ensemble_regression, dict(n_rows=65)), (g.test_tree_ensemble_classification_is_bit_exact, {}),
+        (g.test_tree_ensemble_matches_reference_golden, {}), (g.test_mixed_linear_and_tree_ensemble_with_onehot, {}),
+        (g.test_votes_match_reference_golden, {}), (g.test_majority_vote_random_against_numpy, {}),
+        (g.test_logistic_ensemble_majority_vote_is_exact, {}), (g.test_range_bounds_that_are_not_float32_on_the_device, {}),
+    ]
+
+
+@pytest.mark.parametrize("case,kwargs", _gpu_parity_cases(), ids=lambda v: v.__name__ if callable(v) else "-".join(map(str, v.values())))
+def test_gpu_parity_cases_hold_on_the_emulated_plan(case, kwargs):
+    """the plan-level parity assertions of tests/test_gpu_parity.py (oracle / golden equality of transforms, linear and
+    tree models, votes, status words) with the numpy plan: pins the lowering and the packing on CPU, and keeps the
+    emulation honest against the very assertions the kernels pass on the GPU"""
+    case(**kwargs)
