@@ -316,9 +316,11 @@ class IngestPlan:
         return [o[0] for o in self.out]
 
     def _inputs(self, df):
+        """the frame's columns as contiguous arrays, without copies where pandas allows it"""
+        raw = self._block_columns(df)
         ins, keep = {}, []
         for name, kind in self.schema:
-            a = df[name].to_numpy()
+            a = raw[name] if raw is not None else df[name].to_numpy()
             if kind == I64:
                 a = a.astype("datetime64[ns]", copy=False).view(np.int64)
             elif kind == I32 and a.dtype != np.int32:
@@ -327,6 +329,27 @@ class IngestPlan:
             keep.append(a)
             ins[self.prog.in_slot[name]] = a
         return ins, keep
+
+    @staticmethod
+    def _block_columns(df):
+        """{column: array} taken one dtype at a time: for a consolidated frame (one block per dtype) `to_numpy()` of the
+        same-dtype sub-frame is a view whose columns are contiguous, 4x cheaper than 255 `df[name]` look-ups.  Frames that
+        are not consolidated (or a pandas without the block counter) use the per-column path: None."""
+        nblocks = getattr(getattr(df, "_mgr", None), "nblocks", None)
+        dtypes = df.dtypes
+        kinds = set(dtypes)
+        if nblocks is None or nblocks > len(kinds) or not df.columns.is_unique:
+            return None
+        out = {}
+        for dt in kinds:
+            sub = df.select_dtypes(include=[dt]) if len(kinds) > 1 else df  # the dtype's block(s), not a copy
+            names = sub.columns
+            block = sub.to_numpy()
+            if block.ndim != 2 or not (block.flags["F_CONTIGUOUS"] or block.shape[1] == 1):
+                return None  # pandas had to assemble it: the columns would be strided copies
+            for j, name in enumerate(names):
+                out[name] = block[:, j]
+        return out
 
     def run(self, df, reference_dtypes=False):
         """transform the frame; returns a new DataFrame with the same index.  `reference_dtypes=True` widens integer

@@ -4,6 +4,8 @@ reference's storey walk), and the symbolic lowering of the product against both 
 import contextlib
 import io
 
+import warnings
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -249,3 +251,44 @@ def test_lowering_fuzz_against_the_per_row_oracle():
                 np.testing.assert_array_equal(g.astype(np.float64), w.astype(np.float64), err_msg=name)
 
     run()
+
+
+def test_frame_columns_reach_the_plan_as_contiguous_arrays_whatever_the_block_layout():
+    """IngestPlan._inputs: one dtype block at a time for consolidated frames (views, no copies), the per-column path for
+    everything else; either way the arrays handed to the C-ABI are contiguous and equal to the frame's columns"""
+    from mlrun_b200.feature_store import ingest as bi
+    from mlrun_b200.feature_store import steps as bs
+    from mlrun_b200.synthetic import ingest_workload
+
+    wl = ingest_workload(n_rows=3000, seed=9)
+    base = wl.df
+
+    def plan_for(df):
+        prog = bi.FrameProgram(bi.frame_schema(df))
+        for s in wl.build_steps(bs):
+            prog.apply(s)
+        return bi.IngestPlan(prog, finalize=False)
+
+    split = pd.DataFrame({c: base[c].to_numpy().copy() for c in base.columns}, copy=False)  # one block per column
+    grown = base.copy()
+    moved = grown.pop(grown.columns[5])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # pandas' fragmentation hint
+        grown[moved.name] = moved  # same dtype in two blocks
+    frames = {"consolidated": base, "one block per column": split, "extra block": grown[list(base.columns)],
+              "every other row": base.iloc[::2], "reversed": base.iloc[::-1], "empty": base.iloc[:0], "one row": base.iloc[7:8]}
+    for tag, df in frames.items():
+        plan = plan_for(df)
+        ins, _keep = plan._inputs(df)
+        assert sorted(ins) == sorted(plan.prog.in_slot[name] for name, _ in plan.schema), tag
+        for name, kind in plan.schema:
+            got = ins[plan.prog.in_slot[name]]
+            want = df[name].to_numpy()
+            want = want.astype("datetime64[ns]").view(np.int64) if kind == bi.I64 else want
+            assert got.flags["C_CONTIGUOUS"] and got.shape == (len(df),) and got.itemsize in (4, 8), (tag, name)
+            np.testing.assert_array_equal(got, want.astype(got.dtype), err_msg=f"{tag}/{name}")
+    # the consolidated frame is read in place
+    plan = plan_for(base)
+    ins, _ = plan._inputs(base)
+    name = plan.schema[3][0]
+    assert np.shares_memory(ins[plan.prog.in_slot[name]], base[name].to_numpy())
