@@ -87,9 +87,7 @@ def predict(models, E):
 # ------------------------------------------------------------------------------------------ columnar ingest plan
 def run_column_ops(iplan, df):
     """numpy emulation of columns_kernel over the ops an IngestPlan handed to the C-ABI (mlrun_b200/csrc/b2s_columns.cuh):
-    float32 / int32 words, fp64 compares against fp64 tables, outputs in slot order.  -> (frame, counters dict)"""
-    import pandas as pd
-
+    float32 / int32 words, fp64 compares against fp64 tables, outputs in slot order.  -> (outputs, violations, misses)"""
     from mlrun_b200 import _native as nat
 
     src = {}
@@ -100,6 +98,15 @@ def run_column_ops(iplan, df):
         elif kind == nat.COL_I32:
             a = a.astype(np.int32)
         src[iplan.prog.in_slot[name]] = a
+    return run_column_ops_on_slots(iplan, src)
+
+
+def run_column_ops_on_slots(iplan, src):
+    """the same over input slot arrays {slot: array} (what IngestPlan._inputs hands to b2s_cols_run_host)"""
+    import pandas as pd
+
+    from mlrun_b200 import _native as nat
+
     outs, bad, miss = [], [], []
     for kind, slot, skind, fill, arg, check in iplan.ops:
         a = src[slot]
@@ -154,3 +161,55 @@ def run_column_ops(iplan, df):
                 v |= x > check[1]
             bad.append(int(v.sum()))
     return outs, bad, miss
+
+
+class EmulatedColumns:
+    """stand-in for a finalized ColumnsPlan (tests only): `run_host` fills the output slot arrays from the numpy emulation
+    above, so IngestPlan.run / FeatureSet.ingest -- column extraction, result block, dtypes, violation and miss counters,
+    the DataFrame assembly -- run end to end on CPU"""
+
+    def __init__(self, iplan, real):
+        self._iplan, self._real = iplan, real
+        real._read_info()
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def run_host(self, in_slots, n_rows, out_slots, with_stats=False):
+        from mlrun_b200 import _native as nat
+
+        ip = self._iplan
+        outs, bad, miss = run_column_ops_on_slots(ip, in_slots)
+        slot, k = 0, 0
+        for kind, _s, skind, _f, arg, _c in ip.ops:  # output slots are numbered in op order
+            if kind == "check":
+                continue
+            width = len(arg) if kind == "onehot" else 1
+            for j in range(width):
+                dst = out_slots[slot + j]
+                dst[...] = outs[k].view(dst.dtype) if dst.dtype.itemsize == 8 and outs[k].dtype.itemsize == 8 else outs[k]
+                k += 1
+            slot += width + (1 if (kind == "copy" and skind == nat.COL_I64) else 0)
+        counters = np.zeros(max(self._real.n_counters, 1), dtype=np.uint64)
+        for (cnt, _name, _v), n in zip(ip.checks, bad):
+            counters[cnt] = n
+        for (cnt, _name, _what), n in zip(ip.miss, miss):
+            counters[cnt] = n
+        counters = counters[: self._real.n_counters]
+        return (counters, {"rows": int(n_rows), "kernels": 0}) if with_stats else counters
+
+
+def install_columns(monkeypatch):
+    """IngestPlans built from here on run on the emulation (and take their result blocks from pageable memory)"""
+    from mlrun_b200 import _native as nat
+    from mlrun_b200.feature_store import ingest as bi
+
+    real_init = bi.IngestPlan.__init__
+
+    def init(self, prog, finalize=True):
+        real_init(self, prog, finalize=False)
+        if finalize:
+            self.plan = EmulatedColumns(self, self.plan)
+
+    monkeypatch.setattr(bi.IngestPlan, "__init__", init)
+    monkeypatch.setattr(nat, "PINNED", type("NoPool", (), {"take": staticmethod(lambda nbytes: None)})())
