@@ -120,43 +120,28 @@ bool parse_number(Cur& c, float* out) {
     if (lit("Infinity", -std::numeric_limits<float>::infinity())) return true;
     return false;
   }
-  const char* q = s;
-  bool integral = true;  // json.loads makes an int of it: "-0" is 0, not -0.0
-  if (q < c.end && *q == '-') ++q;
-  if (q >= c.end) return false;
-  if (*q == '0') {
-    ++q;
-  } else if (*q >= '1' && *q <= '9') {
-    while (q < c.end && *q >= '0' && *q <= '9') ++q;
-  } else {
-    return false;
-  }
-  if (q < c.end && *q == '.') {
-    integral = false;
-    ++q;
-    const char* f = q;
-    while (q < c.end && *q >= '0' && *q <= '9') ++q;
-    if (q == f) return false;
-  }
-  if (q < c.end && (*q == 'e' || *q == 'E')) {
-    integral = false;
-    ++q;
-    if (q < c.end && (*q == '+' || *q == '-')) ++q;
-    const char* e = q;
-    while (q < c.end && *q >= '0' && *q <= '9') ++q;
-    if (q == e) return false;
-  }
+  // std::from_chars does the conversion and finds the end of the token; what it accepts beyond the JSON grammar (leading
+  // zeros, ".5", "5.", "inf" / "nan") is rejected by three checks on the span it consumed -- no second pass over the digits
+  const bool neg = *s == '-';
+  const char* t = neg ? s + 1 : s;
+  if (t >= c.end || *t < '0' || *t > '9') return false;
   double d = 0.0;
-  const char* from = s;
-  auto r = std::from_chars(from, q, d);
+  auto r = std::from_chars(s, c.end, d);
+  if (r.ec == std::errc::invalid_argument) return false;
+  const char* q = r.ptr;
+  if (*t == '0' && t + 1 < q && t[1] >= '0' && t[1] <= '9') return false;  // 007
+  const char* dot = t;
+  while (dot < q && *dot >= '0' && *dot <= '9') ++dot;  // end of the integer digits
+  if (dot < q && *dot == '.' && !(dot + 1 < q && dot[1] >= '0' && dot[1] <= '9')) return false;  // "5." / "5.e3"
+  auto is_integral = [&] {  // json.loads makes an int of it: "-0" is 0, not -0.0
+    for (const char* u = t; u < q; ++u)
+      if (*u == '.' || *u == 'e' || *u == 'E') return false;
+    return true;
+  };
   if (r.ec == std::errc::result_out_of_range) {
-    if (integral) return false;  // an int too large for a double: np.asarray raises OverflowError; leave it to that path
+    if (is_integral()) return false;  // an int too large for a double: np.asarray raises OverflowError; leave it to that path
     // json.loads gives +-inf for 1e999 and +-0.0 for 1e-999 (or 0.000...1 with 400 zeros): decided by the decimal
     // exponent of the first non-zero digit
-    const bool neg = *s == '-';
-    const char* t = neg ? s + 1 : s;
-    const char* dot = t;
-    while (dot < q && *dot >= '0' && *dot <= '9') ++dot;  // end of the integer digits
     const char* nz = t;
     while (nz < q && (*nz == '0' || *nz == '.')) ++nz;
     long lead = nz < dot ? (long)(dot - nz - 1) : -(long)(nz - dot);
@@ -172,10 +157,10 @@ bool parse_number(Cur& c, float* out) {
       lead += eneg ? -ex : ex;
     }
     d = lead < 0 ? (neg ? -0.0 : 0.0) : (neg ? -HUGE_VAL : HUGE_VAL);
-  } else if (r.ec != std::errc() || r.ptr != q) {
+  } else if (r.ec != std::errc()) {
     return false;
   }
-  if (integral && d == 0.0) d = 0.0;
+  if (d == 0.0 && is_integral()) d = 0.0;  // "-0" is the int 0
   *out = (float)d;
   c.p = q;
   return true;

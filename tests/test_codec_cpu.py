@@ -178,3 +178,34 @@ def test_large_malformed_bodies_are_errors():
         with pytest.raises(Exception) as ei:
             codec.parse_inputs(bad)
         assert not isinstance(ei.value, AssertionError)  # NativeError, or NotV2Matrix -> json.loads raises for the caller
+
+
+def test_number_grammar_fuzz_against_json_loads():
+    """hypothesis: tokens over the number alphabet -- accepted exactly when json.loads accepts them, with the same value"""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=600, deadline=None)
+    @given(st.text(alphabet="0123456789.eE+-", min_size=1, max_size=12))
+    def check(tok):
+        body = '{"inputs": [[' + tok + ", 1]]}"
+        try:
+            want = json.loads(body)["inputs"][0][0]
+        except json.JSONDecodeError:
+            want = None
+        if want is None:
+            with pytest.raises(Exception) as ei:
+                codec.parse_inputs(body)
+            assert not isinstance(ei.value, AssertionError)
+            return
+        try:
+            with np.errstate(over="ignore"):
+                ref = np.asarray([want], dtype=np.float32)
+        except OverflowError:  # an int beyond the double range
+            with pytest.raises(codec.NotV2Matrix):
+                codec.parse_inputs(body)
+            return
+        got, _ = codec.parse_inputs(body)
+        np.testing.assert_array_equal(got[0, :1].view(np.uint32), ref.view(np.uint32))
+
+    check()
