@@ -356,11 +356,10 @@ class IngestPlan:
         results to int64 (what a frame re-assembled from Python ints has) at the price of a host-side copy."""
         import pandas as pd
 
-        key = (tuple(df.columns), tuple(df.dtypes))
-        if key != getattr(self, "_seen_key", None):  # same labels and dtypes as a frame already checked: skip the walk
+        if not _same_labels_and_dtypes(df, getattr(self, "_seen", None)):  # a frame like one already checked skips the walk
             if frame_schema(df) != self.schema:
                 raise ValueError("the frame does not carry the schema this plan was lowered for")
-            self._seen_key = key
+            self._seen = (df.columns, list(df.dtypes))
         n = len(df)
         ins, _keep = self._inputs(df)
         # result columns live in one pinned block (fast D2H, no second copy); the frame built over them keeps the block
@@ -416,6 +415,12 @@ class IngestPlan:
 
     def _second_half(self, s):
         return any(how == "dt" and slot + 1 == s for _n, slot, how in self.out)
+
+
+def _same_labels_and_dtypes(df, seen):
+    """seen = (columns Index, [dtypes]) of an earlier frame; Index.equals is vectorised (50 us for 255 columns where
+    building a tuple key of labels and dtypes costs 1 ms)"""
+    return seen is not None and df.columns.equals(seen[0]) and list(df.dtypes) == seen[1]
 
 
 def lower_steps(steps, df_or_schema):
@@ -516,10 +521,9 @@ class FeatureSet:
         keys = [e.name for e in self.entities]
         if keys and all(k in df.columns for k in keys):
             df = df.set_index(keys)
-        key = tuple((str(c), str(t)) for c, t in zip(df.columns, df.dtypes))
-        if self._plan is None or self._plan_key != key:
+        if self._plan is None or not _same_labels_and_dtypes(df, self._plan_key):
             self._plan = lower_steps(self._step_objects(namespace), df)
-            self._plan_key = key
+            self._plan_key = (df.columns, list(df.dtypes))
         out = self._plan.run(df, reference_dtypes=reference_dtypes)
         return out if return_df else None
 
