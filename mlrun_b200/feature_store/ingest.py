@@ -411,7 +411,46 @@ class IngestPlan:
         for step in self.prog.validators:
             step.violations = getattr(step, "violations", 0) + sum(
                 int(self.counters[cnt]) for cnt, name, v in self.checks if v in step._validators.values())
-        return pd.DataFrame(data, index=df.index, copy=False)
+        return self._assemble(data, bufs, block, layout, n, df.index)
+
+    def _assemble(self, data, bufs, block, layout, n, index):
+        """the result frame.  Columns that stayed in their landing buffers and sit next to each other in the result block
+        with one dtype become ONE 2-D pandas block (a strided view of the block, no copy): the frame has a handful of blocks
+        instead of one per column -- cheaper to build and consolidated for whatever the caller does next."""
+        import pandas as pd
+
+        names = list(data)
+        if block is None or len(names) < 2:
+            return pd.DataFrame(data, index=index, copy=False)
+        pieces, loose, i = [], {}, 0
+
+        def flush_loose():
+            if loose:
+                pieces.append(pd.DataFrame(dict(loose), index=index, copy=False))
+                loose.clear()
+
+        while i < len(names):
+            a = data[names[i]]
+            stride = (n * a.dtype.itemsize + 63) // 64 * 64
+            j = i
+            if a is bufs[names[i]]:  # untouched landing view: extend the run while dtype and spacing hold
+                while (j + 1 < len(names) and data[names[j + 1]] is bufs[names[j + 1]] and data[names[j + 1]].dtype == a.dtype
+                       and layout[j + 1] - layout[j] == stride):
+                    j += 1
+            if j > i:
+                flush_loose()
+                k, words = j - i + 1, stride // a.dtype.itemsize
+                rows = np.frombuffer(block, dtype=a.dtype, count=(k - 1) * words + n, offset=layout[i])
+                run = np.lib.stride_tricks.as_strided(rows, shape=(n, k), strides=(a.dtype.itemsize, stride), writeable=True)
+                pieces.append(pd.DataFrame(run, columns=names[i:j + 1], index=index, copy=False))
+            else:
+                loose[names[i]] = a
+            i = j + 1
+        flush_loose()
+        if len(pieces) == 1:
+            return pieces[0]
+        concat_kw = {} if int(pd.__version__.split(".")[0]) >= 3 else {"copy": False}  # pandas 3: lazy copies by default
+        return pd.concat(pieces, axis=1, **concat_kw)
 
     def _second_half(self, s):
         return any(how == "dt" and slot + 1 == s for _n, slot, how in self.out)

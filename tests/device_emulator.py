@@ -200,7 +200,7 @@ class EmulatedColumns:
 
 
 def install_columns(monkeypatch):
-    """IngestPlans built from here on run on the emulation (and take their result blocks from pageable memory)"""
+    """IngestPlans built from here on run on the emulation (and take their result blocks from ordinary memory)"""
     from mlrun_b200 import _native as nat
     from mlrun_b200.feature_store import ingest as bi
 
@@ -212,4 +212,11 @@ def install_columns(monkeypatch):
             self.plan = EmulatedColumns(self, self.plan)
 
     monkeypatch.setattr(bi.IngestPlan, "__init__", init)
-    monkeypatch.setattr(nat, "PINNED", type("NoPool", (), {"take": staticmethod(lambda nbytes: None)})())
+    import ctypes
+
+    class PageablePool:  # result blocks like the pinned pool's, from ordinary memory
+        @staticmethod
+        def take(nbytes):
+            return (ctypes.c_char * max(int(nbytes), 1))()
+
+    monkeypatch.setattr(nat, "PINNED", PageablePool())
