@@ -364,11 +364,7 @@ class IngestPlan:
         ins, _keep = self._inputs(df)
         # result columns live in one pinned block (fast D2H, no second copy); the frame built over them keeps the block
         # alive and it returns to the pool when the frame is collected
-        specs = []
-        for name, slot, how in self.out:
-            dt = np.int64 if how == "dt" else (np.float32 if (how == "f32" or (isinstance(how, tuple) and how[0] == "map")) else np.int32)
-            specs.append((name, slot, np.dtype(dt)))
-        extra = [s for s in range(self.plan.n_out) if s not in {sp[1] for sp in specs} and not self._second_half(s)]
+        specs, extra = self._landing()
         layout, off = [], 0
         for dt in [sp[2] for sp in specs] + [np.dtype(np.int32)] * len(extra):
             layout.append(off)
@@ -452,8 +448,19 @@ class IngestPlan:
         concat_kw = {} if int(pd.__version__.split(".")[0]) >= 3 else {"copy": False}  # pandas 3: lazy copies by default
         return pd.concat(pieces, axis=1, **concat_kw)
 
-    def _second_half(self, s):
-        return any(how == "dt" and slot + 1 == s for _n, slot, how in self.out)
+    def _landing(self):
+        """(name, slot, dtype) of every result column + the slots the device writes that are not part of the result (dropped
+        one-hot members): they still need a landing buffer.  Depends on the plan only: computed once."""
+        cached = getattr(self, "_landing_cache", None)
+        if cached is None:
+            specs = []
+            for name, slot, how in self.out:
+                dt = np.int64 if how == "dt" else (np.float32 if (how == "f32" or (isinstance(how, tuple) and how[0] == "map")) else np.int32)
+                specs.append((name, slot, np.dtype(dt)))
+            taken = {sp[1] for sp in specs} | {slot + 1 for _n, slot, how in self.out if how == "dt"}  # + second halves
+            extra = [s for s in range(self.plan.n_out) if s not in taken]
+            cached = self._landing_cache = (specs, extra)
+        return cached
 
 
 def _same_labels_and_dtypes(df, seen):
