@@ -158,8 +158,7 @@ class DevicePlan:
         """synchronous host call: pinned staging -> H2D -> kernels -> D2H (b2s_run_host)"""
         X = self._check_rows(X)
         n = X.shape[0]
-        out = np.empty((n, self.out_cols), dtype=self.out_dtype)
-        status = np.empty(n, dtype=np.int32)
+        out, status = self._result_arrays(n)
         stats = nat.Stats()
         nat.check(self._lib.b2s_run_host(self._h, X.ctypes.data, n, self._stride(X), out.ctypes.data, out.nbytes,
                                          status.ctypes.data, C.byref(stats)))
@@ -169,6 +168,17 @@ class DevicePlan:
         if with_stats:
             res += (stats.as_dict(),)
         return res if len(res) > 1 else out
+
+    def _result_arrays(self, n):
+        """(outputs, status) for n rows.  Large results live in one block of the pinned pool: it is resident (a fresh
+        np.empty of 8 MB costs ~2 000 first-touch page faults per call) and goes back to the pool when both arrays are
+        collected; small ones are plain arrays (the pool's bookkeeping would cost more than it saves)."""
+        out_bytes = (n * self.out_cols * 4 + 63) // 64 * 64
+        block = nat.PINNED.take(out_bytes + n * 4) if out_bytes + n * 4 >= (1 << 20) else None
+        if block is None:
+            return np.empty((n, self.out_cols), dtype=self.out_dtype), np.empty(n, dtype=np.int32)
+        out = np.frombuffer(block, dtype=self.out_dtype, count=n * self.out_cols).reshape(n, self.out_cols)
+        return out, np.frombuffer(block, dtype=np.int32, count=n, offset=out_bytes)
 
     def submit(self, X):
         X = self._check_rows(X)

@@ -122,3 +122,38 @@ def test_event_sharding_all_gather_gloo_world2(tmp_path):
         capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_large_results_come_from_the_pinned_pool_and_small_ones_do_not(monkeypatch):
+    """DevicePlan._result_arrays: layout of the (outputs, status) pair over one pool block; plain arrays below 1 MiB or when
+    the pool is exhausted (host logic; the pool itself needs a GPU, so a stand-in hands out ordinary memory here)"""
+    import ctypes
+
+    import numpy as np
+
+    from mlrun_b200 import _native as nat
+    from mlrun_b200.plan import DevicePlan
+
+    taken = []
+
+    class Pool:
+        def take(self, nbytes):
+            taken.append(nbytes)
+            return None if nbytes > (64 << 20) else (ctypes.c_char * nbytes)()
+
+    monkeypatch.setattr(nat, "PINNED", Pool())
+    plan = DevicePlan.__new__(DevicePlan)
+    plan.out_cols, plan.out_is_int = 3, False
+    out, st = plan._result_arrays(1000)
+    assert not taken and out.shape == (1000, 3) and out.dtype == np.float32 and st.shape == (1000,) and st.dtype == np.int32
+    out, st = plan._result_arrays(100_001)
+    assert taken == [(100_001 * 12 + 63) // 64 * 64 + 100_001 * 4]
+    assert out.shape == (100_001, 3) and out.flags["C_CONTIGUOUS"] and st.shape == (100_001,)
+    out[:] = 1.5
+    st[:] = 7
+    assert (out == 1.5).all() and (st == 7).all()  # the two arrays do not overlap
+    plan.out_is_int = True
+    labels, _ = plan._result_arrays(400_000)
+    assert labels.dtype == np.int32
+    big_out, big_st = plan._result_arrays(10_000_000)  # the pool says no: ordinary arrays
+    assert big_out.shape == (10_000_000, 3) and big_out.base is None
