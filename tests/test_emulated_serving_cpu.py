@@ -117,3 +117,80 @@ def test_gpu_parity_cases_hold_on_the_emulated_plan(case, kwargs):
     tree models, votes, status words) with the numpy plan: pins the lowering and the packing on CPU, and keeps the
     emulation honest against the very assertions the kernels pass on the GPU"""
     case(**kwargs)
+
+
+def test_served_flow_fuzz_product_on_the_emulated_plan_against_the_oracle_server():
+    """hypothesis: random flows (feature steps -> one model | voting ensemble; linear regressors, logistic classifiers, small
+    tree ensembles; explicit or inferred vote type) built with the same calls on both APIs.  Per event `server.test` and the
+    batched `run_events` of the product must answer what the oracle's per-event server answers (labels exactly, scores
+    rtol 1e-5), 400s included."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+    from sklearn.ensemble import GradientBoostingClassifier, GradientBoostingRegressor
+    from sklearn.linear_model import LinearRegression, LogisticRegression
+
+    from tests import api_oracle
+
+    rng0 = np.random.default_rng(5)
+    Xfit = rng0.normal(size=(300, 6)).astype(np.float32)
+    yreg = Xfit[:, 0] * 2 - Xfit[:, 3] + 0.1 * rng0.normal(size=300)
+    ycls = (Xfit[:, 1] + Xfit[:, 2] > 0).astype(int) + (Xfit[:, 4] > 1).astype(int)
+    fitted = {  # fitted once; the flows feed 6 columns to every model (4 numeric, one 3-way one-hot minus ... see below)
+        "linreg": [LinearRegression().fit(Xfit * (1 + i), yreg) for i in range(3)],
+        "logit": [LogisticRegression(max_iter=200).fit(Xfit + i, ycls) for i in range(3)],
+        "gbr": [GradientBoostingRegressor(n_estimators=5, max_depth=2, random_state=i).fit(Xfit, yreg) for i in range(3)],
+        "gbc": [GradientBoostingClassifier(n_estimators=4, max_depth=2, random_state=i).fit(Xfit, ycls) for i in range(3)],
+    }
+    names = ["x0", "x1", "x2", "c0"]  # -> Imputer -> OneHot(c0: 0,1,2) -> 6 model inputs
+
+    def build(api, family, n_models, vote_type, with_imputer, engine):
+        fn = api.new_function("fuzz", kind="serving")
+        graph = fn.set_topology("flow", engine=engine)
+        step = graph
+        if with_imputer:
+            step = step.to(api.Imputer(mapping={"x0": 0.5, "x1": -1.0, "x2": 0.25}, default_value=0), name="imputer")
+        step = step.to(api.OneHotEncoder(mapping={"c0": [0, 1, 2]}), name="onehot")
+        models = fitted[family][:n_models]
+        if n_models == 1:
+            step = step.to(api.FeatureRowModelServer(name="solo", model=models[0]), name="solo")
+        else:
+            kw = {"vote_type": vote_type} if vote_type else {}
+            step = step.to("*FeatureRowVotingEnsemble", name="ens", executor_type="array", **kw)
+            for i, m in enumerate(models):
+                step.add_route(f"m{i}", class_name="FeatureRowModelServer", model=m, model_path="")
+        if engine != "sync":
+            step.respond()
+        ns = {"FeatureRowVotingEnsemble": api.FeatureRowVotingEnsemble, "FeatureRowModelServer": api.FeatureRowModelServer}
+        return fn.to_mock_server(namespace=ns)
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.sampled_from(sorted(fitted)), st.integers(1, 3), st.sampled_from([None, "explicit"]), st.booleans(),
+           st.sampled_from(["sync", "async"]), st.integers(0, 10_000))
+    def run(family, n_models, vote, with_imputer, engine, seed):
+        vote_type = None if vote is None else ("classification" if family in ("logit", "gbc") else "regression")
+        rng = np.random.default_rng(seed)
+        n = 12
+        X = rng.normal(size=(n, 3)).astype(np.float32)
+        X[rng.random((n, 3)) < 0.2] = np.nan
+        codes = rng.integers(0, 4, size=n)  # 3 = out of vocabulary
+        rows = [{"x0": float(X[i, 0]), "x1": float(X[i, 1]), "x2": float(X[i, 2]), "c0": int(codes[i])} for i in range(n)]
+        prod = build(api_b200, family, n_models, vote_type, with_imputer, engine)
+        orac = build(api_oracle, family, n_models, vote_type, with_imputer, "sync")
+        path = "/" if n_models == 1 else "/v2/models/infer"
+        want = [orac.test(path=path, body=dict(r), silent=True) for r in rows]
+        got_events = prod.run_events([dict(r) for r in rows])
+        got_single = [prod.test(path=path, body=dict(r), silent=True) for r in rows[:4]]
+        for i, w in enumerate(want):
+            for g in [got_events[i]] + ([got_single[i]] if i < 4 else []):
+                if hasattr(w, "status_code"):  # the reference fails this event (NaN reaches scikit-learn): so must we
+                    assert getattr(g, "status_code", 200) == w.status_code == 400, (i, g, w.body)
+                    continue
+                assert not hasattr(g, "status_code"), (i, getattr(g, "body", g))
+                assert g["model_name"] == w["model_name"] and g.get("model_version") == w.get("model_version")
+                gv, wv = g["outputs"], w["outputs"]
+                if family in ("logit", "gbc"):
+                    assert [int(v) for v in gv] == [int(v) for v in wv], (family, n_models, vote, i)
+                else:
+                    np.testing.assert_allclose(gv, wv, rtol=RTOL, atol=ATOL)
+
+    run()
