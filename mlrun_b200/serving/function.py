@@ -24,6 +24,7 @@ class ServingSpec:
         self.secret_sources = None
         self.default_content_type = None
         self.default_class = None
+        self.command = ""  # path of the function's own code file: its classes / handlers are step candidates
 
 
 class ServingFunction:
@@ -114,6 +115,9 @@ class ServingFunction:
         namespace = namespace or []
         if not isinstance(namespace, list):
             namespace = [namespace]
+        module = _code_module(self.spec.command, workdir)  # the function's own code (mlrun.run.function_to_module, silent)
+        if module is not None:
+            namespace.append(module)
         namespace.append(caller_globals())
         server = create_graph_server(
             parameters=self.spec.parameters, load_mode=self.spec.load_mode, graph=self.spec.graph, verbose=self.verbose,
@@ -130,7 +134,25 @@ class ServingFunction:
         return self._mock.test(path, body, method or ("POST" if body else "GET"), headers)
 
 
-def new_function(name="", project="", tag="", kind="", **kwargs):
+def _code_module(command, workdir=None):
+    """the function's code file as a module (mlrun/run.py:77-127 with silent=True: nothing to load -> None)"""
+    import importlib.util
+    import os
+
+    if not command:
+        return None
+    path = os.path.join(workdir or "", command)
+    spec = importlib.util.spec_from_file_location(os.path.splitext(os.path.basename(path))[0], path)
+    if spec is None:
+        raise OSError(f"cannot import from {path!r}")
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)
+    return module
+
+
+def new_function(name="", project="", tag="", kind="", command="", **kwargs):
     if kind != "serving":
         raise MLRunInvalidArgumentError("mlrun_b200 implements kind='serving' functions only")
-    return ServingFunction(name=name, project=project, tag=tag)
+    fn = ServingFunction(name=name, project=project, tag=tag)
+    fn.spec.command = command or ""
+    return fn

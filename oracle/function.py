@@ -125,6 +125,9 @@ class ServingFunction:
         namespace = namespace or []
         if not isinstance(namespace, list):
             namespace = [namespace]
+        code = self._own_code(workdir)
+        if code is not None:
+            namespace.append(code)
         namespace.append(get_caller_globals())
         server = create_graph_server(
             parameters=self.spec.parameters,
@@ -144,6 +147,24 @@ class ServingFunction:
         server.init_object(namespace)
         return server
 
+    def _own_code(self, workdir):
+        """mlrun.run.function_to_module(self, silent=True) (run.py:77-127): the function's code file, loaded as a module
+        whose classes and functions are step candidates; no code -> None"""
+        import importlib.util as loader
+        import os
+        from pathlib import Path
+
+        command = getattr(self.spec, "command", "")
+        if not command:
+            return None
+        location = os.path.join(workdir or "", command)
+        found = loader.spec_from_file_location(Path(location).stem, location)
+        if found is None:
+            raise OSError(f"cannot import from {location!r}")
+        module = loader.module_from_spec(found)
+        found.loader.exec_module(module)
+        return module
+
     def invoke(self, path, body=None, method=None, headers=None, **kwargs):
         """mock invoke only (function.py:925-936)"""
         if self._mock_server is None:
@@ -153,8 +174,10 @@ class ServingFunction:
         return self._mock_server.test(path, body, method, headers)
 
 
-def new_function(name="", project="", tag="", kind="", **kwargs):
-    """mlrun.run.new_function (run.py:425) for kind="serving" only"""
+def new_function(name="", project="", tag="", kind="", command="", **kwargs):
+    """mlrun.run.new_function (run.py:425) for kind="serving" only; `command` = the function's code file"""
     if kind != "serving":
         raise MLRunInvalidArgumentError("the oracle only restates kind='serving' functions")
-    return ServingFunction(name=name, project=project, tag=tag)
+    fn = ServingFunction(name=name, project=project, tag=tag)
+    fn.spec.command = command or ""
+    return fn

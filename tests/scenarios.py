@@ -1182,6 +1182,80 @@ enrichment_routers.EXPECT = {
 }
 
 
+def flow_add_model(api):
+    """tests/serving/test_flow.py:189-213 -- fn.add_model inside a flow: needs a router; the only router is found by itself,
+    one of several is named with router_step"""
+    make_namespace(api)
+    out = {}
+
+    def attempt(fn, **kw):
+        try:
+            fn.add_model("m1", class_name="ModelTestingClass", model_path=".", **kw)
+            return None
+        except Exception as exc:  # noqa: BLE001
+            return type(exc).__name__
+
+    fn = api.new_function("tests", kind="serving")
+    fn.set_topology("flow", engine="sync").to("Echo", "e1").to("Echo", "e2")
+    out["no_router"] = attempt(fn)
+    fn = api.new_function("tests", kind="serving")
+    graph = fn.set_topology("flow", engine="sync")
+    graph.to("Echo", "e1").to("*", "router").to("Echo", "e2")
+    out["one_router"] = [attempt(fn), sorted(graph["router"].routes)]
+    fn = api.new_function("tests", kind="serving")
+    graph = fn.set_topology("flow", engine="sync")
+    graph.to("Echo", "e1").to("*", "r1").to("Echo", "e2").to("*", "r2")
+    out["named_router"] = [attempt(fn, router_step="r2"), sorted(graph["r1"].routes), sorted(graph["r2"].routes)]
+    out["two_routers_unnamed"] = attempt(fn)
+    out["unknown_router"] = attempt(fn, router_step="r9")
+    return out
+
+
+flow_add_model.EXPECT = {("one_router",): [None, ["m1"]], ("named_router",): [None, [], ["m1"]]}
+
+
+def module_load(api):
+    """tests/serving/test_flow.py:330-350 -- classes and handlers of the function's own code file (`command=`) are found
+    without a namespace; the handler gets the graph context"""
+    import os
+    import tempfile
+
+    code = (
+        "class MyCls:\n"
+        "    def __init__(self, context=None, name=None, **kwargs):\n"
+        "        self.context, self.name = context, name\n"
+        "    def do(self, event):\n"
+        "        return event * 2\n"
+        "\n"
+        "def myhand(x, context=None):\n"
+        "    assert context is not None and hasattr(context, 'logger'), 'did not get a context'\n"
+        "    return x * 2\n"
+    )
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "graft_myfunc.py")
+        with open(path, "w") as fp:
+            fp.write(code)
+        fn = api.new_function("test2", command=path, kind="serving")
+        graph = fn.set_topology("flow", engine="sync")
+        graph.to(name="s1", class_name="MyCls").to(name="s2", handler="myhand")
+        out["from_command"] = fn.to_mock_server().test(body=5)
+        rel = api.new_function("test3", command="graft_myfunc.py", kind="serving")
+        rel.set_topology("flow", engine="sync").to(name="s1", class_name="MyCls").to(name="s2", handler="myhand")
+        out["relative_to_workdir"] = rel.to_mock_server(workdir=tmp).test(body=7)
+    plain = api.new_function("test4", kind="serving")
+    plain.set_topology("flow", engine="sync").to(name="s1", class_name="MyCls")
+    try:
+        plain.to_mock_server()
+        out["without_code"] = None
+    except Exception as exc:  # noqa: BLE001
+        out["without_code"] = type(exc).__name__
+    return out
+
+
+module_load.EXPECT = {("from_command",): 20, ("relative_to_workdir",): 28}
+
+
 def merge_flows(api):
     """tests/serving/test_merger.py:87-128 -- split and merge through a served async graph (join on event.id, join on a
     body key, a missing key surfacing as the event's error)"""
@@ -1282,7 +1356,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, merge_flows, steps_dict_events, steps_pandas_engine, vote_math,
+    route_cap, flow_add_model, module_load, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, merge_flows, steps_dict_events, steps_pandas_engine, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
