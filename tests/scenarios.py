@@ -1256,6 +1256,54 @@ def module_load(api):
 module_load.EXPECT = {("from_command",): 20, ("relative_to_workdir",): 28}
 
 
+def infer_dict_ops(api):
+    """tests/serving/test_serving.py:543-563 + serving/v2_serving.py:391-426 -- the *_dict operations reorder dict inputs by
+    the model artifact's input schema.  The artifact store is out of scope: `load()` sets `model_spec` directly."""
+    import types
+
+    fields = ["sepal_length_cm", "sepal_width_cm", "petal_length_cm", "petal_width_cm"]
+
+    class SpecModel(api.V2ModelServer):
+        def load(self):
+            if self.get_param("with_spec", True):
+                self.model_spec = types.SimpleNamespace(inputs=[types.SimpleNamespace(name=f) for f in fields])
+
+        def predict(self, request):
+            return [sum(w * v for w, v in zip((1, 10, 100, 1000), row)) for row in request["inputs"]]
+
+    rows = [[5.1, 3.5, 1.4, 0.2], [7.7, 3.8, 6.7, 2.2]]
+    shuffled = [{"petal_width_cm": r[3], "sepal_length_cm": r[0], "petal_length_cm": r[2], "sepal_width_cm": r[1]} for r in rows]
+    fn = api.new_function("tst", kind="serving")
+    fn.set_topology("router")
+    fn.add_model("m1", ".", class_name="SpecModel")
+    fn.add_model("bare", ".", class_name="SpecModel", with_spec=False)
+    server = fn.to_mock_server(namespace={"SpecModel": SpecModel})
+
+    def call(path, body):
+        resp = server.test(path, body, silent=True)
+        if hasattr(resp, "status_code"):
+            text = resp.body if isinstance(resp.body, str) else resp.body.decode()
+            return {"status": resp.status_code, "error": _first_line(text)}
+        return _clean(resp)
+
+    return {
+        "infer": call("/v2/models/m1/infer", {"inputs": rows}),
+        "predict": call("/v2/models/m1/predict", {"inputs": rows}),
+        "infer_dict": call("/v2/models/m1/infer_dict", {"inputs": shuffled}),
+        "predict_dict": call("/v2/models/m1/predict_dict", {"inputs": shuffled}),
+        "one_dict": call("/v2/models/m1/infer_dict", {"inputs": {k: [d[k] for d in shuffled] for k in fields}}),
+        "lists_to_dict_op": call("/v2/models/m1/infer_dict", {"inputs": rows}),
+        "missing_key": call("/v2/models/m1/infer_dict", {"inputs": [{k: 1.0 for k in fields[:3]}]}),
+        "no_spec": call("/v2/models/bare/infer_dict", {"inputs": shuffled}),
+        "no_spec_plain_infer": call("/v2/models/bare/infer", {"inputs": rows}),
+    }
+
+
+infer_dict_ops.EXPECT = {
+    ("infer", "outputs"): [5.1 + 35.0 + 140.0 + 200.0, 7.7 + 38.0 + 670.0 + 2200.0],
+}
+
+
 def merge_flows(api):
     """tests/serving/test_merger.py:87-128 -- split and merge through a served async graph (join on event.id, join on a
     body key, a missing key surfacing as the event's error)"""
@@ -1356,7 +1404,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, merge_flows, steps_dict_events, steps_pandas_engine, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, merge_flows, steps_dict_events, steps_pandas_engine, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
