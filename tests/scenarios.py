@@ -1304,6 +1304,44 @@ infer_dict_ops.EXPECT = {
 }
 
 
+def no_merger(api):
+    """tests/serving/test_merger.py:51-84 -- split into two branches that meet again WITHOUT a Merge step: the common step
+    sees every event once per branch (directly, and behind a queue)"""
+    ns = dict(make_namespace(api))
+
+    class Gather:
+        def __init__(self, context):
+            self.context = context
+            context.mylist = []
+
+        def do(self, event):
+            self.context.mylist.append(event)
+            return event
+
+    ns["Gather"] = Gather
+    out = {}
+    for with_queue in (False, True):
+        fn = api.new_function("x", kind="serving")
+        graph = fn.set_topology("flow", exist_ok=True)
+        dbl = graph.to(name="double", handler="double")
+        dbl.to(name="add3", class_name="Adder", add=3)
+        dbl.to(name="add2", class_name="Adder", add=2)
+        if with_queue:
+            graph.add_step("$queue", "q1", path="").after_step("add2", "add3").to("Gather", function="some_function")
+        else:
+            graph.add_step("Gather").after_step("add2", "add3")
+        server = fn.to_mock_server(namespace=ns)
+        for data in [5, 10, 15]:
+            server.test("", body=data)
+        server.wait_for_completion()
+        out["queue" if with_queue else "direct"] = sorted(server.context.mylist)
+    return out
+
+
+no_merger.EXPECT = {("direct",): [12, 13, 22, 23, 32, 33], ("queue",): [12, 13, 22, 23, 32, 33]}
+no_merger.ASYNC = True
+
+
 def merge_flows(api):
     """tests/serving/test_merger.py:87-128 -- split and merge through a served async graph (join on event.id, join on a
     body key, a missing key surfacing as the event's error)"""
@@ -1404,7 +1442,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, merge_flows, steps_dict_events, steps_pandas_engine, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
