@@ -539,6 +539,32 @@ class FeatureSet:
             last = self._graph[names[-1]]
         return last.to(*args, **kwargs)
 
+    @property
+    def spec(self):
+        """what the steps' `validate_args` read of a feature set (feature_set.py FeatureSetSpec)"""
+        import types
+
+        return types.SimpleNamespace(entities={e.name: e for e in self.entities}, label_column=self.label_column,
+                                     timestamp_key=self.timestamp_key, graph=self._graph)
+
+    def validate_steps(self, namespace=None):
+        """ingest-time argument checks of the graph's steps (feature_set.py:508-534): every step class that has a
+        `validate_args` classmethod sees the feature set and its own constructor arguments"""
+        from . import transforms
+
+        known = {k: getattr(transforms, k) for k in dir(transforms) if not k.startswith("_")}
+        known.update(namespace or {})
+        for step in self._graph.steps.values():
+            obj = getattr(step, "_object", None)
+            cls = type(obj) if obj is not None else known.get(str(step.class_name or "").rsplit(".", 1)[-1])
+            check = getattr(cls, "validate_args", None)
+            if check is None:
+                continue
+            args = dict(step.class_args or {})
+            if obj is not None:  # a step added as an object: its arguments are its attributes
+                args = {k: getattr(obj, k) for k in ("mapping", "features") if hasattr(obj, k)}
+            check(self, **args)
+
     def _step_objects(self, namespace):
         from ..serving.compiler import _chain, _transform_object
         from ..serving.host import create_graph_server
@@ -568,6 +594,7 @@ class FeatureSet:
         if keys and all(k in df.columns for k in keys):
             df = df.set_index(keys)
         if self._plan is None or not _same_labels_and_dtypes(df, self._plan_key):
+            self.validate_steps(namespace)
             self._plan = lower_steps(self._step_objects(namespace), df)
             self._plan_key = (df.columns, list(df.dtypes))
         out = self._plan.run(df, reference_dtypes=reference_dtypes)

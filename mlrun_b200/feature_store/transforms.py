@@ -14,6 +14,8 @@ import math
 import re
 import uuid
 
+import numpy as np
+
 from ..serving.resolve import MLRunInvalidArgumentError
 from ..serving.step_meta import StepMeta
 
@@ -111,6 +113,23 @@ class MapValues(_Step):
         self.with_original_features = with_original_features
         self.suffix = suffix
 
+    @classmethod
+    def validate_args(cls, feature_set, **kwargs):
+        """ingest-time check of the constructor arguments (steps.py:331-370): one value type per column (NaN aside), and
+        ranges never next to single replacements"""
+        for column, rules in kwargs.get("mapping", []).items():  # QUIRK: no mapping at all is an AttributeError ([] has no items)
+            if "ranges" in rules:
+                if len(rules) > 1:
+                    raise MLRunInvalidArgumentError("MapValues - mapping values of the same column can not combine ranges and "
+                                                    f"single replacement, which is the case for column '{column}'")
+                values = [v for pair in rules["ranges"].values() for v in pair if v != "-inf" and v != "inf"]
+            else:
+                values = list(rules.values())
+            kinds = {type(v) for v in values if not (isinstance(v, (float, np.floating)) and math.isnan(v))}
+            if len(kinds) > 1:
+                raise MLRunInvalidArgumentError("MapValues - mapping values of the same column must be in the same type, which "
+                                                f"was not the case for Column '{column}'")
+
     def _map_value(self, feature, value):
         fmap = self.mapping.get(feature, {})
         for label, bounds in fmap.get("ranges", {}).items() if "ranges" in fmap else ():
@@ -134,6 +153,18 @@ class DropFeatures(_Step):
     def __init__(self, features, **kwargs):
         super().__init__(**kwargs)
         self.features = features
+
+    @classmethod
+    def validate_args(cls, feature_set, **kwargs):
+        """entities, the label column and the timestamp key are not features (steps.py:737-753)"""
+        features = kwargs.get("features", [])
+        spec = feature_set.spec
+        entities = set(features) & set(spec.entities.keys())
+        if entities:
+            raise MLRunInvalidArgumentError(f"DropFeatures can only drop features, not entities: {entities}")
+        for what, name in (("label_column", spec.label_column), ("timestamp_key", spec.timestamp_key)):
+            if name in features:
+                raise MLRunInvalidArgumentError(f"DropFeatures can not drop {what}: {name}")
 
     def _do_event(self, event):
         for f in self.features:

@@ -126,6 +126,29 @@ class MapValues(StepToDict, MLRunStep):
     def _get_feature_name(self, feature):
         return f"{feature}_{self.suffix}" if self.with_original_features else feature
 
+    @classmethod
+    def validate_args(cls, feature_set, **kwargs):
+        """steps.py:331-370, run by FeatureSet.validate_steps at ingest: a column's replacement values share one type
+        (NaN does not count; neither do the "-inf" / "inf" spellings of range bounds) and a column has ranges or single
+        replacements, not both"""
+        def counted(v):
+            return not (isinstance(v, (float, np.float64, np.float32, np.float16)) and np.isnan(v))
+
+        for column, rules in kwargs.get("mapping", []).items():
+            if "ranges" not in rules:
+                seen = {type(v) for v in rules.values() if counted(v)}
+            elif len(rules) > 1:
+                raise MLRunInvalidArgumentError(
+                    f"MapValues - mapping values of the same column can not combine ranges and "
+                    f"single replacement, which is the case for column '{column}'")
+            else:
+                seen = {type(v) for bounds in rules["ranges"].values() for v in bounds
+                        if v != "-inf" and v != "inf" and counted(v)}
+            if len(seen) > 1:
+                raise MLRunInvalidArgumentError(
+                    f"MapValues - mapping values of the same column must be in the"
+                    f" same type, which was not the case for Column '{column}'")
+
     def _map_value(self, feature, value):
         """ranges: first [lo, hi) hit in dict order; else dict.get(value, value) (steps.py:189-201)"""
         rules = self.mapping.get(feature, {})
@@ -290,6 +313,19 @@ class DropFeatures(StepToDict, MLRunStep):
     def __init__(self, features, **kwargs):
         super().__init__(**kwargs)
         self.features = features
+
+    @classmethod
+    def validate_args(cls, feature_set, **kwargs):
+        """only features can be dropped: not an entity, not the label column, not the timestamp key (steps.py:737-753)"""
+        doomed = kwargs.get("features", [])
+        spec = feature_set.spec
+        entities = set(doomed).intersection(spec.entities.keys())
+        if entities:
+            raise MLRunInvalidArgumentError(f"DropFeatures can only drop features, not entities: {entities}")
+        protected = {"label_column": spec.label_column, "timestamp_key": spec.timestamp_key}
+        for role, column in protected.items():
+            if column in doomed:
+                raise MLRunInvalidArgumentError(f"DropFeatures can not drop {role}: {column}")
 
     def _do_storey(self, event):
         for feature in self.features:

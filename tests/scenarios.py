@@ -1005,6 +1005,50 @@ steps_pandas_engine.EXPECT = {
 }
 
 
+def steps_validate_args(api):
+    """feature_store/steps.py:331-370, 737-753 + tests/feature-store/test_steps.py:466-547 -- the ingest-time argument checks
+    of MapValues and DropFeatures (`validate_args`, called by FeatureSet.validate_steps), driven directly"""
+    import types
+
+    fset = types.SimpleNamespace(spec=types.SimpleNamespace(entities={"id": None, "name": None}, label_column="y",
+                                                            timestamp_key="when"))
+
+    def attempt(cls, **kw):
+        try:
+            cls.validate_args(fset, **kw)
+            return None
+        except Exception as exc:  # noqa: BLE001
+            return f"{type(exc).__name__}: {_first_line(exc)}"
+
+    nan = float("nan")
+    return {
+        "map_ranges_mixed": attempt(api.MapValues, mapping={"age": {"ranges": {"one": [0, 30], "two": ["a", "inf"]}}}),
+        "map_values_mixed": attempt(api.MapValues, mapping={"names": {"A": 1, "B": False}}),
+        "map_combined": attempt(api.MapValues, mapping={"age": {"ranges": {"one": [0, 30], "two": ["a", "inf"]}, 4: "kid"}}),
+        "map_ok_ranges": attempt(api.MapValues, mapping={"age": {"ranges": {"child": [0, 18], "adult": [18, "inf"]}}}),
+        "map_ok_inf_spellings": attempt(api.MapValues, mapping={"x": {"ranges": {0: ["-inf", 0], 1: [0, "inf"]}}}),
+        "map_int_and_float_bounds": attempt(api.MapValues, mapping={"x": {"ranges": {0: [0, 0.5], 1: [0.5, 1]}}}),
+        "map_nan_value_is_ignored": attempt(api.MapValues, mapping={"x": {1: nan, 2: 5}}),
+        "map_ok_strings": attempt(api.MapValues, mapping={"dep": {"IT": "tech", "RD": "tech"}}),
+        "map_second_column_bad": attempt(api.MapValues, mapping={"a": {1: 2}, "b": {1: "x", 2: 3}}),
+        "map_no_mapping": attempt(api.MapValues),
+        "drop_entity": attempt(api.DropFeatures, features=["age", "id"]),
+        "drop_label": attempt(api.DropFeatures, features=["y"]),
+        "drop_timestamp": attempt(api.DropFeatures, features=["age", "when"]),
+        "drop_ok": attempt(api.DropFeatures, features=["age", "dep"]),
+        "drop_nothing": attempt(api.DropFeatures),
+    }
+
+
+steps_validate_args.EXPECT = {
+    ("map_ranges_mixed",): "MLRunInvalidArgumentError: MapValues - mapping values of the same column must be in the same type, "
+                           "which was not the case for Column 'age'",
+    ("map_combined",): "MLRunInvalidArgumentError: MapValues - mapping values of the same column can not combine ranges and single "
+                       "replacement, which is the case for column 'age'",
+    ("map_ok_ranges",): None,
+}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -1442,7 +1486,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 

@@ -27,3 +27,40 @@ def _cases():
 @pytest.mark.parametrize("case,kwargs", _cases(), ids=lambda v: v.__name__ if callable(v) else "-".join(map(str, v.values())))
 def test_gpu_ingest_cases_hold_on_the_emulated_columns_plan(case, kwargs):
     case(**kwargs)
+
+
+def test_ingest_runs_the_steps_argument_checks_first():
+    """FeatureSet.validate_steps (feature_set.py:508-534; tests/feature-store/test_steps.py:466-547): bad MapValues mappings
+    and DropFeatures of an entity / the timestamp key are refused before anything is lowered; steps given as objects or by
+    class name alike"""
+    import numpy as np
+    import pandas as pd
+
+    from mlrun_b200.feature_store import ingest as bi
+    from mlrun_b200.feature_store import steps as bs
+    from mlrun_b200.serving.resolve import MLRunInvalidArgumentError
+
+    df = pd.DataFrame({"id": np.arange(6, dtype=np.int32), "age": np.array([1, 20, 40, 5, 70, 33], dtype=np.float32),
+                       "dep": np.array([0, 1, 2, 1, 0, 2], dtype=np.int32),
+                       "when": pd.date_range("2024-01-01", periods=6, freq="h").astype("datetime64[ns]")})
+
+    def fset(*steps):
+        fs = bi.FeatureSet("t", entities=[bi.Entity("id")], timestamp_key="when")
+        cur = fs.graph
+        for s in steps:
+            cur = cur.to(*s[0], **s[1]) if isinstance(s, tuple) else cur.to(s)
+        return fs
+
+    with pytest.raises(MLRunInvalidArgumentError, match="can not combine ranges and single replacement.*'age'"):
+        fset(bs.MapValues(mapping={"age": {"ranges": {0: [0, 30], 1: [30, "inf"]}, 4: 9}})).ingest(df)
+    with pytest.raises(MLRunInvalidArgumentError, match="must be in the same type.*'dep'"):
+        fset((("MapValues",), {"mapping": {"dep": {0: 1, 1: "x"}}})).ingest(df)
+    with pytest.raises(MLRunInvalidArgumentError, match="not entities"):
+        fset(bs.DropFeatures(features=["id"])).ingest(df)
+    with pytest.raises(MLRunInvalidArgumentError, match="can not drop timestamp_key: when"):
+        fset((("DropFeatures",), {"features": ["when"]})).ingest(df)
+    good = fset(bs.MapValues(mapping={"age": {"ranges": {0: [0, 30], 1: [30, "inf"]}}}, with_original_features=True),
+                bs.DropFeatures(features=["dep"]))
+    out = good.ingest(df)
+    assert list(out.columns) == ["age_mapped", "age", "when"] and out.index.name == "id"  # mapped first (steps.py:206-211)
+    assert out["age_mapped"].tolist() == [0, 0, 1, 0, 1, 1]
