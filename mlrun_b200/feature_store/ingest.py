@@ -24,6 +24,12 @@ from ..serving.resolve import MLRunInvalidArgumentError
 _INT_DTYPES = ("int8", "int16", "int32", "uint8", "uint16", "bool")
 
 
+def _short(value):
+    """reports carry at most 40 characters of a violating value (mlrun/features.py:24-35)"""
+    text = str(value)
+    return text if len(text) <= 40 else text[:40] + "..."
+
+
 class MinMaxValidator:
     """mlrun/features.py:265-321 -- range check whose only effect is a report (check_type is metadata here)"""
 
@@ -38,9 +44,9 @@ class MinMaxValidator:
     def check(self, value):
         try:
             if self.min is not None and value < self.min:
-                return False, {"message": "value is smaller than min", "min": self.min, "value": str(value)}
+                return False, {"message": "value is smaller than min", "min": self.min, "value": _short(value)}
             if self.max is not None and value > self.max:
-                return False, {"message": "value is greater than max", "max": self.max, "value": str(value)}
+                return False, {"message": "value is greater than max", "max": self.max, "value": _short(value)}
         except Exception as err:  # noqa: BLE001 -- the reference reports comparison errors as violations
             return False, {"message": str(err), "type": self.kind}
         return True, {}

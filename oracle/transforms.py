@@ -53,19 +53,31 @@ class MLRunStep(MapClass):
 
 
 # ------------------------------------------------------------------------------------------ validation
+def _shown(value, limit=40):
+    """how a violating value is reported: its str, cut at 40 characters (mlrun/features.py:24-35)"""
+    text = str(value)
+    return text if len(text) <= limit else text[:limit] + "..."
+
+
 class MinMaxValidator:
-    """mlrun/features.py:228-321 (check only)"""
+    """mlrun/features.py:265-321 (check only; `check_type` needs the feature's value type and is not restated)"""
+
+    kind = "minmax"
 
     def __init__(self, check_type=None, severity=None, min=None, max=None):
-        self.check_type, self.severity = check_type, severity or "info"
+        self.check_type, self.severity = check_type, severity  # QUIRK: no default severity -- reports start with "None!"
         self.min, self.max = min, max
 
     def check(self, value):
-        if value is not None:
+        """(ok, details).  A comparison that raises (None, a string against a number) is a violation whose message is the
+        exception's text"""
+        try:
             if self.min is not None and value < self.min:
-                return False, {"message": "value is smaller than min", "min": self.min, "value": value}
+                return False, {"message": "value is smaller than min", "min": self.min, "value": _shown(value)}
             if self.max is not None and value > self.max:
-                return False, {"message": "value is greater than max", "max": self.max, "value": value}
+                return False, {"message": "value is greater than max", "max": self.max, "value": _shown(value)}
+        except Exception as err:  # noqa: BLE001
+            return False, {"message": str(err), "type": self.kind}
         return True, {}
 
 

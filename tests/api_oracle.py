@@ -72,3 +72,10 @@ def online_service(features, index_keys, table, stats, label_column, with_indexe
 def register_online_vector(uri, features, index_keys, table, stats, label_column, with_indexes):
     register_feature_vector(uri, _enrichment.FeatureVector("vec", features, index_keys, table, stats, label_column=label_column,
                                                          with_indexes=with_indexes))
+
+
+def validator_step(rules, columns):
+    from oracle import transforms as _t
+
+    return _t.FeaturesetValidator(columns=columns, validators={c: _t.MinMaxValidator(**kw) for c, kw in rules.items()
+                                                                 if not columns or c in columns})

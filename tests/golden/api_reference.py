@@ -107,3 +107,16 @@ def register_online_vector(uri, features, index_keys, table, stats, label_column
     _ONLINE_VECTORS[uri] = types.SimpleNamespace(get_online_feature_service=lambda impute_policy=None: online_service(
         features, index_keys, table, stats, label_column, with_indexes, impute_policy))
     mlrun.feature_store.get_feature_vector = lambda u, *a, **k: _ONLINE_VECTORS[u]
+
+
+def validator_step(rules, columns):
+    """the REAL FeaturesetValidator (feature_store/steps.py:94-149) over the REAL MinMaxValidator / Feature (mlrun/features.py);
+    the feature set it reads its validators from is a stub of the store resource"""
+    import types
+
+    from mlrun.features import Feature, MinMaxValidator
+
+    feats = {col: Feature(validator=MinMaxValidator(**kw)) for col, kw in rules.items()}
+    ctx = types.SimpleNamespace(get_store_resource=lambda uri: types.SimpleNamespace(spec=types.SimpleNamespace(features=feats)),
+                                logger=None)
+    return _steps.FeaturesetValidator(featureset=".", columns=columns, context=ctx)

@@ -1049,6 +1049,62 @@ steps_validate_args.EXPECT = {
 }
 
 
+def _captured(fn):
+    import contextlib
+    import io
+
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        res = fn()
+    return res, buf.getvalue().splitlines()
+
+
+_VALIDATOR_RULES = {"age": dict(min=30, severity="info"), "bid": dict(min=1.5, max=9.0, severity="warn"),
+                    "qty": dict(max=100), "name": dict(min=3, severity="info")}
+
+
+def validator_events(api):
+    """feature_store/steps.py:94-128 + mlrun/features.py:265-321 -- FeaturesetValidator on storey events: events pass through
+    unchanged, violations are printed (message, key, arguments); a comparison that raises is a violation too"""
+    import types
+
+    step = api.validator_step(_VALIDATOR_RULES, None)
+    only_age = api.validator_step(_VALIDATOR_RULES, ["age"])
+    out = {}
+    events = [("k1", {"age": 25, "bid": 2.0, "qty": 5, "name": 7}), (None, {"age": 31, "bid": 0.5, "qty": 500, "other": 1}),
+              ("k3", {"age": 30, "bid": 9.0}), ("k4", {"age": float("nan"), "bid": 9.5, "qty": None, "name": "bob"}),
+              ("k5", {"bid": "x" * 300}), ("k6", {"qty": 10**50})]  # the reported value is cut at 40 characters
+    for i, (key, body) in enumerate(events):
+        ev = types.SimpleNamespace(body=dict(body), key=key)
+        res, lines = _captured(lambda: step.do(ev))
+        out[f"e{i}"] = {"same_event": res is ev, "body_unchanged": _clean(ev.body) == _clean(body), "printed": lines}
+    ev = types.SimpleNamespace(body={"age": 1, "bid": 0.1}, key="k")
+    _res, lines = _captured(lambda: only_age.do(ev))
+    out["columns_filter"] = lines
+    return out
+
+
+validator_events.EXPECT = {
+    ("e0", "printed"): ["info! age value is smaller than min, key=k1 args={'min': 30, 'value': '25'}"],
+    ("e2", "printed"): [],
+}
+
+
+def validator_pandas(api):
+    """feature_store/steps.py:130-149 + tests/feature-store/test_steps.py:550-627 -- the pandas engine of FeaturesetValidator:
+    one report per violating column, the frame passes through unchanged"""
+    import types
+
+    import pandas as pd
+
+    step = api.validator_step(_VALIDATOR_RULES, None)
+    frame = pd.DataFrame({"age": [25, 31, 29, 40], "bid": [2.0, 0.5, 9.5, 3.0], "qty": [5, 500, 7, 101], "other": [1, 2, 3, 4]},
+                         index=pd.Index([10, 11, 12, 13], name="id"))
+    ev = types.SimpleNamespace(body=frame.copy(), key=None)
+    res, lines = _captured(lambda: step.do(ev))
+    return {"same_event": res is ev, "frame_unchanged": bool(ev.body.equals(frame)), "printed": lines}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -1486,7 +1542,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
