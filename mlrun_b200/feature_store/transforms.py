@@ -203,6 +203,9 @@ class SetEventMetadata(_Step):
         self.key_path = key_path
         self.random_id = random_id
 
+    def post_init(self, mode="sync"):
+        """part of the step protocol (the reference builds its tagging closures here); the paths are read in `do`"""
+
     def do(self, event):
         from ..serving.paths import get_in
 

@@ -1105,6 +1105,37 @@ def validator_pandas(api):
     return {"same_event": res is ev, "frame_unchanged": bool(ev.body.equals(frame)), "printed": lines}
 
 
+def set_event_metadata_logic(api):
+    """feature_store/steps.py:635-696 + tests/feature-store/test_steps.py:47-76 -- SetEventMetadata driven directly:
+    post_init builds the taggers, do() copies id / key from (nested) body paths as strings, random_id draws a hex id"""
+    import types
+
+    def run(step, body):
+        step.post_init()
+        ev = types.SimpleNamespace(body=body, id="orig-id", key="orig-key")
+        res = step.do(ev)
+        return {"same_event": res is ev, "id": ev.id, "key": ev.key}
+
+    out = {
+        "both": run(api.SetEventMetadata(id_path="myid", key_path="mykey"), {"myid": "34", "mykey": "123"}),
+        "nested_and_numeric": run(api.SetEventMetadata(id_path="meta.id", key_path="k"), {"meta": {"id": 7}, "k": 2.5}),
+        "key_only": run(api.SetEventMetadata(key_path="mykey"), {"mykey": ["a", 1]}),
+        "missing_path": run(api.SetEventMetadata(id_path="nope.deeper"), {"x": 1}),
+        "nothing": run(api.SetEventMetadata(), {"x": 1}),
+    }
+    rnd = run(api.SetEventMetadata(random_id=True, key_path="k"), {"k": "kk"})
+    out["random"] = {"key": rnd["key"], "id_is_hex32": len(rnd["id"]) == 32 and all(c in "0123456789abcdef" for c in rnd["id"])}
+    rnd_wins = run(api.SetEventMetadata(id_path="myid", random_id=True), {"myid": "34"})
+    out["random_after_path"] = rnd_wins["id"] != "34" and len(rnd_wins["id"]) == 32
+    step = api.SetEventMetadata(id_path="a", key_path="b")
+    out["full_event"] = bool(getattr(step, "_full_event", None))
+    return out
+
+
+set_event_metadata_logic.EXPECT = {("both",): {"same_event": True, "id": "34", "key": "123"},
+                                   ("random", "id_is_hex32"): True}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -1542,7 +1573,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
