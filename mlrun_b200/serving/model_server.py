@@ -71,8 +71,19 @@ class V2ModelServer(StepMeta):
             raise ValueError("please specify a load method or a model object")
 
     def get_model(self, suffix=""):
-        """model store access is control plane (out of scope): the path is used as a local file"""
-        return self.model_path, {}
+        """(local model file, extra data) -- the local-filesystem slice of mlrun.artifacts.get_model (artifacts/model.py:
+        412-483): the path itself when it carries the suffix, else the first entry of the directory that does.  Store URIs,
+        model-spec yaml files and extra data items are the artifact store (out of scope)."""
+        import os
+
+        suffix = suffix or ".pkl"
+        path = str(self.model_path)
+        if path.endswith(suffix):
+            return path, {}
+        found = next((os.path.join(path, f) for f in (os.listdir(path) if os.path.isdir(path) else ()) if f.endswith(suffix)), "")
+        if not found:
+            raise ValueError(f"cant resolve model file for {path} suffix{suffix}")
+        return found, {}
 
     def get_param(self, key, default=None):
         if key in self._params:

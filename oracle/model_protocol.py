@@ -95,8 +95,20 @@ class V2ModelServer(StepToDict):
         self.metrics[name] = value
 
     def get_model(self, suffix=""):
-        """local-file stand-in for mlrun.artifacts.get_model (:166-202)"""
-        return self.model_path, {}
+        """v2_serving.py:166-202 over the local slice of mlrun.artifacts.get_model (artifacts/model.py:434-475): a path that
+        ends with the suffix (default ".pkl") is the model file; any other path is listed as a directory and the first
+        entry with the suffix is taken; nothing found is a ValueError.  (Store URIs / model-spec yaml: the artifact store.)"""
+        from pathlib import Path
+
+        wanted = suffix or ".pkl"
+        location = str(self.model_path)
+        if location.endswith(wanted):
+            return location, {}
+        folder = Path(location)
+        for entry in (folder.iterdir() if folder.is_dir() else []):
+            if entry.name.endswith(wanted):
+                return str(entry), {}
+        raise ValueError(f"cant resolve model file for {location} suffix{wanted}")
 
     def preprocess(self, request, operation):
         return request

@@ -1136,6 +1136,49 @@ set_event_metadata_logic.EXPECT = {("both",): {"same_event": True, "id": "34", "
                                    ("random", "id_is_hex32"): True}
 
 
+def pickle_model_from_path(api):
+    """frameworks/_ml_common/pkl_model_server.py:40-50 + serving/v2_serving.py:166-202 + artifacts/model.py:412-483 (local
+    slice) -- a pickled scikit-learn model served from `model_path`: the file itself, or a directory searched for the suffix"""
+    import os
+    import tempfile
+
+    import cloudpickle
+    from sklearn.linear_model import LinearRegression
+
+    model = LinearRegression()
+    model.coef_, model.intercept_, model.n_features_in_ = np.array([0.5, -2.0, 4.0]), 1.25, 3
+    ns = {"SKLearnModelServer": api.SKLearnModelServer}
+    out = {}
+
+    def serve(path):
+        fn = api.new_function("t", kind="serving")
+        fn.set_topology("router")
+        fn.add_model("m1", model_path=path, class_name="SKLearnModelServer")
+        try:
+            server = fn.to_mock_server(namespace=ns)
+        except Exception as exc:  # noqa: BLE001
+            return {"load_failed": type(exc).__name__}
+        return _clean(server.test("/v2/models/m1/infer", {"inputs": [[1.0, 2.0, 3.0], [0.0, 0.0, 0.0]]}))
+
+    with tempfile.TemporaryDirectory() as tmp:
+        full = os.path.join(tmp, "with_model")
+        os.mkdir(full)
+        with open(os.path.join(full, "model.pkl"), "wb") as fp:
+            cloudpickle.dump(model, fp)
+        with open(os.path.join(full, "notes.txt"), "w") as fp:
+            fp.write("not a model")
+        empty = os.path.join(tmp, "without_model")
+        os.mkdir(empty)
+        out["file"] = serve(os.path.join(full, "model.pkl"))
+        out["directory"] = serve(full)
+        out["directory_without_model"] = serve(empty)
+        out["missing_file"] = serve(os.path.join(tmp, "nope.pkl"))
+    return out
+
+
+pickle_model_from_path.EXPECT = {("file", "outputs"): [0.5 - 4.0 + 12.0 + 1.25, 1.25], ("directory", "outputs"): [9.75, 1.25]}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -1573,7 +1616,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 

@@ -22,7 +22,7 @@ def _emulated(monkeypatch):
     emulated_plan.install(monkeypatch)
 
 
-@pytest.mark.parametrize("name", ["flow3_linear_events", "flow3_ensemble_events", "tree_ensemble_batch"])
+@pytest.mark.parametrize("name", ["flow3_linear_events", "flow3_ensemble_events", "tree_ensemble_batch", "pickle_model_from_path"])
 def test_device_scenarios_on_the_emulated_plan_match_reference_golden(name):
     got = json.loads(json.dumps(getattr(scenarios, name)(api_b200), default=str))
     assert_same(got, GOLDEN[name], name, rtol=RTOL, atol=ATOL)

@@ -20,7 +20,7 @@ GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "scena
 RTOL, ATOL = 1e-5, 1e-5
 
 
-@pytest.mark.parametrize("name", ["flow3_linear_events", "flow3_ensemble_events", "tree_ensemble_batch"])
+@pytest.mark.parametrize("name", ["flow3_linear_events", "flow3_ensemble_events", "tree_ensemble_batch", "pickle_model_from_path"])
 def test_device_scenarios_match_reference_golden(name):
     """same scenario code as the oracle / reference runs, through mlrun_b200's API: every predict is a CUDA plan"""
     got = json.loads(json.dumps(getattr(scenarios, name)(api_b200), default=str))

@@ -13,7 +13,7 @@ from tests.compare import assert_same
 
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "scenarios.json")))
 DEVICE = {"flow3_linear_events", "flow3_ensemble_events", "tree_ensemble_batch", "online_service_logic",
-          "enrichment_routers"}  # need the GPU
+          "enrichment_routers", "pickle_model_from_path"}  # need the GPU
 PANDAS = {"steps_pandas_engine", "validator_pandas"}  # DataFrame bodies are not a host path of the engine (see transforms.py)
 HOST = [s for s in scenarios.SCENARIOS if s.__name__ not in DEVICE | PANDAS]
 
