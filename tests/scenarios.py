@@ -1179,6 +1179,48 @@ def pickle_model_from_path(api):
 pickle_model_from_path.EXPECT = {("file", "outputs"): [0.5 - 4.0 + 12.0 + 1.25, 1.25], ("directory", "outputs"): [9.75, 1.25]}
 
 
+def model_async_load(api):
+    """tests/serving/test_serving.py:471-501 -- load_mode="async": the model loads in a thread; until it is done `ready` is 408
+    and an HTTP infer fails, afterwards requests (here a stream-triggered one) are served"""
+    import threading
+    import time
+
+    gate = threading.Event()
+
+    class SlowModel(api.V2ModelServer):
+        def load(self):
+            gate.wait(20)
+
+        def predict(self, request):
+            return request["inputs"][0]
+
+    router = api.RouterStep()
+    router.routes = {"m5": api.TaskStep("SlowModel", class_args={"model_path": ""})}
+    ctx = api.init_from_spec(_spec(router.to_dict(), mode="async"), {"SlowModel": SlowModel})
+    out = {}
+
+    def text(resp):
+        return _first_line(resp.body if isinstance(resp.body, str) else resp.body.decode())
+
+    resp = ctx.mlrun_handler(ctx, api.MockEvent("", path="/v2/models/m5/ready", method="GET"))
+    out["ready_before"] = resp.status_code
+    resp = ctx.mlrun_handler(ctx, api.MockEvent(TESTDATA, path="/v2/models/m5/infer"))
+    out["infer_before"] = [resp.status_code, text(resp)]
+    gate.set()
+    for _ in range(500):
+        resp = ctx.mlrun_handler(ctx, api.MockEvent("", path="/v2/models/m5/ready", method="GET"))
+        if resp.status_code == 200:
+            break
+        time.sleep(0.02)
+    out["ready_after"] = resp.status_code
+    resp = ctx.mlrun_handler(ctx, api.MockEvent('{"model": "m5", "inputs": [5]}', trigger=api.MockTrigger(kind="stream")))
+    out["stream_after"] = _resp(resp)
+    return out
+
+
+model_async_load.EXPECT = {("ready_before",): 408, ("ready_after",): 200, ("stream_after", "body", "outputs"): 5}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -1616,7 +1658,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
