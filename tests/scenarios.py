@@ -1221,6 +1221,78 @@ def model_async_load(api):
 model_async_load.EXPECT = {("ready_before",): 408, ("ready_after",): 200, ("stream_after", "body", "outputs"): 5}
 
 
+def class_args_protocol(api):
+    """serving/states.py:437-512 (init_object / get_full_class_args) -- what a step class's constructor receives: `_x` class
+    args arrive as callables under `x`; name / context / input_path / result_path / full_event / graph_step only when the
+    signature names them or takes **kwargs"""
+
+    def triple(x):
+        return x * 3
+
+    class TakesNothing:
+        def __init__(self):
+            self.got = sorted(vars(self))
+
+        def do(self, x):
+            return [x, "nothing"]
+
+    class TakesSome:
+        def __init__(self, name=None, fn=None, factor=1):
+            self.name, self.fn, self.factor = name, fn, factor
+
+        def do(self, x):
+            return {"name": self.name, "value": self.fn(x) * self.factor}
+
+    class TakesKwargs:
+        def __init__(self, **kwargs):
+            self.kw = kwargs
+
+        def do(self, x):
+            step = self.kw.get("graph_step")
+            return {"keys": sorted(self.kw), "step_name": getattr(step, "name", None), "ctx": self.kw.get("context") is not None,
+                    "fn": self.kw["fn"](x), "full_event": self.kw.get("full_event"), "input_path": self.kw.get("input_path")}
+
+    class PrefersDoEvent:
+        def do(self, x):
+            return "do"
+
+        def do_event(self, event):
+            event.body = ["do_event", event.body]
+            return event
+
+    ns = {"TakesNothing": TakesNothing, "TakesSome": TakesSome, "TakesKwargs": TakesKwargs, "PrefersDoEvent": PrefersDoEvent,
+          "triple": triple}
+    out = {}
+
+    def serve(*args, **kw):
+        fn = api.new_function("t", kind="serving")
+        graph = fn.set_topology("flow", engine="sync")
+        graph.to(*args, **kw).respond()
+        return fn.to_mock_server(namespace=ns)
+
+    out["nothing"] = serve("TakesNothing", "s").test(body=5)
+    out["some_named_fn"] = serve("TakesSome", "s", _fn="triple", factor=2).test(body=5)
+    out["some_lambda_fn"] = serve("TakesSome", "lam", _fn="(event + 1)").test(body=5)
+    out["kwargs"] = serve("TakesKwargs", "kw", _fn="triple", extra=1).test(body=5)
+    out["kwargs_paths"] = serve("TakesKwargs", "kw2", _fn="triple", input_path="a").test(body={"a": 2})
+    out["do_event_wins"] = serve("PrefersDoEvent", "p").test(body=1)
+    try:
+        serve("TakesNothing", "s", unexpected=1)
+        out["unexpected_arg"] = None
+    except Exception as exc:  # noqa: BLE001
+        out["unexpected_arg"] = type(exc).__name__
+    try:
+        serve("TakesSome", "s", _fn="no_such_function")
+        out["unknown_callable"] = None
+    except Exception as exc:  # noqa: BLE001
+        out["unknown_callable"] = type(exc).__name__
+    return out
+
+
+class_args_protocol.EXPECT = {("some_named_fn",): {"name": "s", "value": 30}, ("some_lambda_fn",): {"name": "lam", "value": 6},
+                              ("do_event_wins",): ["do_event", 1]}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -1658,7 +1730,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
