@@ -1293,6 +1293,60 @@ class_args_protocol.EXPECT = {("some_named_fn",): {"name": "s", "value": 30}, ("
                               ("do_event_wins",): ["do_event", 1]}
 
 
+def model_hooks(api):
+    """serving/v2_serving.py:228-342, 344-383 -- the model-class hooks around predict: preprocess / validate / postprocess,
+    `logged_results` deciding what the tracking stream records, get_param falling back to the server's parameters,
+    set_metric"""
+
+    class Hooked(api.V2ModelServer):
+        def load(self):
+            self.set_metric("loaded", 1)
+
+        def preprocess(self, request, operation):
+            request["inputs"] = [v + self.get_param("shift", 0) for v in request["inputs"]]
+            request["seen_op"] = operation
+            return request
+
+        def validate(self, request, operation):
+            request = super().validate(request, operation)
+            if any(v < 0 for v in request["inputs"]):
+                raise ValueError("negative input")
+            return request
+
+        def predict(self, request):
+            return [v * self.get_param("multiplier") for v in request["inputs"]]
+
+        def postprocess(self, response):
+            response["rounded"] = [round(v) for v in response["outputs"]]
+            return response
+
+        def logged_results(self, request, response, op):
+            if self.get_param("filter_logs", False):
+                return [request["inputs"][0]], [response["outputs"][0]]
+            return None, None
+
+    out = {}
+    for tag, filter_logs in (("full_records", False), ("filtered_records", True)):
+        fn = api.new_function("hooks", kind="serving")
+        fn.set_topology("router")
+        fn.add_model("m", ".", class_name="Hooked", multiplier=2.5, filter_logs=filter_logs)
+        fn.set_tracking("dummy://")
+        fn.spec.parameters["shift"] = 1  # a server parameter: reached through get_param's fallback
+        server = fn.to_mock_server(namespace={"Hooked": Hooked})
+        resp = server.test("/v2/models/m/infer", {"inputs": [1, 2, 3]}, event_id="e1")
+        bad = server.test("/v2/models/m/infer", {"inputs": [-5]}, silent=True)
+        records = [{k: r[k] for k in ("model", "op", "request", "resp")} for r in server.context.stream.output_stream.event_list]
+        model = server.graph.routes["m"]._object
+        out[tag] = {"response": _clean(resp), "bad_status": bad.status_code,
+                    "bad_text": _first_line(bad.body if isinstance(bad.body, str) else bad.body.decode()),
+                    "records": _clean(records), "metrics": dict(model.metrics)}
+    return out
+
+
+model_hooks.EXPECT = {("full_records", "response", "outputs"): [5.0, 7.5, 10.0], ("full_records", "response", "rounded"): [5, 8, 10],
+                      ("filtered_records", "bad_status"): 400}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -1730,7 +1784,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
