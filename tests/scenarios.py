@@ -1347,6 +1347,52 @@ model_hooks.EXPECT = {("full_records", "response", "outputs"): [5.0, 7.5, 10.0],
                       ("filtered_records", "bad_status"): 400}
 
 
+def custom_router(api):
+    """serving/routers.py:46-211 -- the router class protocol: a ModelRouter subclass with its own url / health prefixes and
+    pre / post hooks, served from a router topology built with the class object"""
+    ns = make_namespace(api)
+
+    class TaggingRouter(api.ModelRouter):
+        def preprocess(self, event):
+            if isinstance(event.body, dict) and "inputs" in event.body:
+                event.body["inputs"] = [v + 1 for v in event.body["inputs"]]
+            return event
+
+        def postprocess(self, event):
+            if isinstance(event.body, dict):
+                event.body["via"] = self.name
+            return event
+
+    ns["TaggingRouter"] = TaggingRouter
+    fn = api.new_function("r", kind="serving")
+    graph = fn.set_topology("router", "TaggingRouter", url_prefix="/api/models", health_prefix="/api/health", name="tagger")
+    graph.add_route("a", class_name="ModelTestingClass", model_path=".", multiplier=10)
+    graph.add_route("b:v2", class_name="ModelTestingClass", model_path=".", multiplier=100)
+    server = fn.to_mock_server(namespace=ns)
+
+    def call(path, body=None, method=None):
+        resp = server.test(path, body, method=method or ("POST" if body is not None else "GET"), silent=True)
+        if hasattr(resp, "status_code"):
+            text = resp.body if isinstance(resp.body, str) else (resp.body or b"").decode()
+            return {"status": resp.status_code, "text": _first_line(text)}
+        return _clean(resp)
+
+    return {
+        "infer_a": call("/api/models/a/infer", {"inputs": [5]}),
+        "infer_b_version": call("/api/models/b/versions/v2/infer", {"inputs": [5]}),
+        "default_prefix_is_gone": call("/v2/models/a/infer", {"inputs": [5]}),
+        "list": call("/api/models/"),
+        "health": call("/api/health"),
+        "old_health": call("/v2/health"),
+        "unknown_model": call("/api/models/zz/infer", {"inputs": [5]}),
+        "body_model": call("/api/models", {"model": "b:v2", "inputs": [1]}),
+        "to_dict": {k: v for k, v in graph.to_dict().items() if k in ("kind", "class_name", "class_args", "name")},
+    }
+
+
+custom_router.EXPECT = {("infer_a", "outputs"): 60}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -1784,7 +1830,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
