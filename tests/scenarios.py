@@ -1393,6 +1393,40 @@ def custom_router(api):
 custom_router.EXPECT = {("infer_a", "outputs"): 60}
 
 
+def server_run_details(api):
+    """serving/server.py:196-308 + serving/utils.py:22-23 -- GraphServer.run / test around the graph: the MLRUN-EVENT-ID and
+    MLRUN-EVENT-PATH header overrides, bytes bodies, get_body, non-JSON content types, the JSON encoding of the response"""
+    ns = make_namespace(api)
+    fn = api.new_function("t", kind="serving")
+    graph = fn.set_topology("flow", engine="sync")
+    graph.to(name="meta", handler="extract_meta", full_event=True).respond()
+    server = fn.to_mock_server(namespace=ns)
+    out = {
+        "event_id_arg": server.test(body={"x": 1}, event_id="abc"),
+        "id_header_wins": server.test(body={"x": 1}, event_id="abc", headers={"MLRUN-EVENT-ID": "from-header"}),
+        "path_header": _resp(server.run(api.MockEvent(body={"x": 1}, path="/a", headers={"MLRUN-EVENT-PATH": "/b"}))),
+    }
+    fn = api.new_function("t2", kind="serving")
+    graph = fn.set_topology("flow", engine="sync")
+    graph.to(name="ret", handler="return_type").respond()
+    server = fn.to_mock_server(namespace=ns)
+    out["bytes_json"] = server.test(body=b'{"a": [1, 2]}')
+    out["bytes_text"] = server.test(body=b"plain", content_type="text/plain")
+    out["str_not_json"] = server.test(body="{not json", content_type="text/plain")
+    out["bad_json_default_type"] = _resp(server.test(body="{not json", silent=True))
+    out["number_body"] = server.test(body=5)
+    fn = api.new_function("t3", kind="serving")
+    graph = fn.set_topology("flow", engine="sync")
+    graph.to("Echo", "e").respond()
+    server = fn.to_mock_server(namespace=ns)
+    resp = server.run(api.MockEvent(body={"k": [1, 2.5, None, "s"]}))
+    out["response_is_json_text"] = [type(resp).__name__, resp if isinstance(resp, str) else None]
+    out["get_body_keeps_object"] = server.run(api.MockEvent(body={"k": 1}), get_body=True)
+    out["test_returns_object"] = server.test(body={"k": [1, 2]})
+    out["str_body_passthrough"] = server.test(body="hello", content_type="text/plain")
+    return out
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -1830,7 +1864,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
