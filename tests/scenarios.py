@@ -1427,6 +1427,47 @@ def server_run_details(api):
     return out
 
 
+def tracking_sampling_batching(api):
+    """serving/v2_serving.py:429-504 -- _ModelLogPusher: `log_stream_sample` keeps every n-th request, `log_stream_batch`
+    groups the kept ones into one stream record (lists of requests / responses / timings); errors are pushed at once"""
+    ns = make_namespace(api)
+
+    def serve(**params):
+        fn = api.new_function("trk", kind="serving")
+        fn.set_topology("router")
+        fn.add_model("my", ".", class_name=ns["ModelTestingClass"](multiplier=10))
+        fn.set_tracking("dummy://")
+        fn.spec.parameters.update(params)
+        return fn.to_mock_server(namespace=ns)
+
+    def shape(rec):
+        keep = {k: rec[k] for k in ("model", "op", "class", "function_uri") if k in rec}
+        for key in ("request", "resp", "requests", "error"):
+            if key in rec:
+                keep[key] = _clean(rec[key])
+        if "values" in rec:  # one entry per batched request: [request, op, resp, when, microsec, metrics]
+            keep["values"] = [[_clean(v[0]), v[1], _clean(v[2]), type(v[3]).__name__, type(v[4]).__name__, v[5]] for v in rec["values"]]
+        for key in ("when", "microsec", "metrics"):
+            if key in rec:
+                keep[f"{key}_kind"] = type(rec[key]).__name__
+        if isinstance(rec.get("microsec"), list):
+            keep["n_timings"] = len(rec["microsec"])
+        return keep
+
+    out = {}
+    for tag, params in (("sample3", {"log_stream_sample": 3}), ("batch2", {"log_stream_batch": 2}),
+                        ("sample2_batch2", {"log_stream_sample": 2, "log_stream_batch": 2})):
+        server = serve(**params)
+        for i in range(7):
+            server.test("/v2/models/my/infer", {"inputs": [i]}, event_id=f"e{i}")
+        out[tag] = [shape(r) for r in server.context.stream.output_stream.event_list]
+    server = serve(log_stream_batch=3)
+    server.test("/v2/models/my/infer", {"inputs": [1]}, event_id="ok")
+    server.test("/v2/models/my/infer", {"inputs": "not-a-list"}, event_id="bad", silent=True)
+    out["error_in_a_batch"] = [shape(r) for r in server.context.stream.output_stream.event_list]
+    return out
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -1864,7 +1905,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
