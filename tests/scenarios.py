@@ -1468,6 +1468,73 @@ def tracking_sampling_batching(api):
     return out
 
 
+def graph_validation_errors(api):
+    """serving/states.py:1073-1184 (check_and_process_graph) -- what a flow refuses at server start: loops, several
+    responders, a sync flow with two entry points, unknown from_step / final_step, a child function nobody points at"""
+    ns = make_namespace(api)
+
+    def attempt(build, **server_kw):
+        fn = api.new_function("g", kind="serving")
+        try:
+            build(fn)
+            fn.to_mock_server(namespace=ns, **server_kw)
+            return None
+        except Exception as exc:  # noqa: BLE001
+            return f"{type(exc).__name__}: {_first_line(exc)}"
+
+    def loop(fn):
+        g = fn.set_topology("flow", engine="sync")
+        g.add_step("Echo", "a", after="c")
+        g.add_step("Echo", "b", after="a")
+        g.add_step("Echo", "c", after="b")
+
+    def real_loop(fn):
+        g = fn.set_topology("flow", engine="sync")
+        g.add_step("Echo", "start")
+        g.add_step("Echo", "a", after="start")
+        g.add_step("Echo", "b", after="a")
+        g["a"].after_step("b")
+
+    def two_responders(fn):
+        g = fn.set_topology("flow", engine="async")
+        s = g.to("Echo", "a")
+        s.to("Echo", "b").respond()
+        s.to("Echo", "c").respond()
+
+    def two_starts_sync(fn):
+        g = fn.set_topology("flow", engine="sync")
+        g.add_step("Echo", "a")
+        g.add_step("Echo", "b")
+
+    def unknown_after(fn):
+        g = fn.set_topology("flow", engine="sync")
+        g.add_step("Echo", "a")
+        g.add_step("Echo", "b", after="nope")
+
+    def bad_from_step(fn):
+        g = fn.set_topology("flow", engine="sync")
+        g.to("Echo", "a").to("Echo", "b")
+        g.from_step = "zz"
+
+    def bad_final_step(fn):
+        g = fn.set_topology("flow", engine="sync")
+        g.to("Echo", "a").to("Echo", "b")
+        g.final_step = "zz"
+
+    def ok_chain(fn):
+        fn.set_topology("flow", engine="sync").to("Echo", "a").to("Echo", "b")
+
+    def child_function_steps(fn):
+        g = fn.set_topology("flow", engine="async")
+        g.to("Echo", "a").to("$queue", "q", path="").to("Echo", "b", function="child")
+
+    return {"loop": attempt(loop), "real_loop": attempt(real_loop), "two_responders": attempt(two_responders), "two_starts_sync": attempt(two_starts_sync),
+            "unknown_after": attempt(unknown_after), "bad_from_step": attempt(bad_from_step),
+            "bad_final_step": attempt(bad_final_step), "ok_chain": attempt(ok_chain),
+            "no_step_for_function": attempt(ok_chain, current_function="other"),
+            "child_function_found": attempt(child_function_steps, current_function="child")}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -1905,7 +1972,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
