@@ -1535,6 +1535,34 @@ def graph_validation_errors(api):
             "child_function_found": attempt(child_function_steps, current_function="child")}
 
 
+def event_envelope(api):
+    """serving/server.py:437-490 -- MockEvent / MockTrigger / Response: defaults and what the constructor keeps"""
+    def fields(ev):
+        d = {k: v for k, v in vars(ev).items() if not k.startswith("_")}
+        if "id" in d:
+            d["id"] = "uuid32" if isinstance(d["id"], str) and len(d["id"]) == 32 else d["id"]
+        if d.get("trigger") is not None:
+            d["trigger"] = {k: v for k, v in vars(d["trigger"]).items()}
+        for k, v in list(d.items()):
+            if not isinstance(v, (str, int, float, bool, type(None), dict, list)):
+                d[k] = type(v).__name__
+        return d
+
+    ctx = api.GraphContext()
+    resp = ctx.Response(body={"a": 1})
+    return {
+        "bare": fields(api.MockEvent()),
+        "full": fields(api.MockEvent(body={"x": 1}, content_type="application/json", headers={"H": "1"}, method="PUT", path="/p",
+                                     event_id="my-id", trigger=api.MockTrigger(kind="stream", name="t1"), offset=7, time="now")),
+        "path_default_method": fields(api.MockEvent(body="b", path="/x"))["method"],
+        "str": str(api.MockEvent(body=[1], event_id="e")),
+        "trigger_default": {k: v for k, v in vars(api.MockTrigger()).items()},
+        "response_defaults": {k: v for k, v in vars(resp).items()},
+        "response_full": {k: v for k, v in vars(ctx.Response(headers={"h": 1}, body="x", content_type="text/plain", status_code=404)).items()},
+        "response_repr": repr(resp),
+    }
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -1972,7 +2000,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
