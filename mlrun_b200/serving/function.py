@@ -61,8 +61,9 @@ class ServingFunction:
             raise MLRunInvalidArgumentError(f"unsupported topology {topology}, use 'router' or 'flow'")
         return self.spec.graph
 
-    def set_tracking(self, stream_path=None, batch=None, sample=None, stream_args=None, **kwargs):
-        self.spec.track_models = True
+    def set_tracking(self, stream_path=None, batch=None, sample=None, stream_args=None, tracking_policy=None,
+                     enable_tracking=True):
+        self.spec.track_models = enable_tracking  # `tracking_policy`: deprecated upstream, no effect
         for key, val in (("log_stream", stream_path), ("log_stream_batch", batch), ("log_stream_sample", sample),
                          ("stream_args", stream_args)):
             if val:

@@ -62,9 +62,11 @@ class ServingFunction:
         self.spec.graph = root
         return root
 
-    def set_tracking(self, stream_path=None, batch=None, sample=None, stream_args=None, **kwargs):
-        """serving.py:308-354 -- tracking is a flag plus stream parameters read by the model servers"""
-        self.spec.track_models = True
+    def set_tracking(self, stream_path=None, batch=None, sample=None, stream_args=None, tracking_policy=None,
+                     enable_tracking=True):
+        """serving.py:308-354 -- tracking is a flag plus stream parameters read by the model servers (`tracking_policy` is
+        deprecated upstream and has no effect)"""
+        self.spec.track_models = enable_tracking
         given = {"log_stream": stream_path, "log_stream_batch": batch, "log_stream_sample": sample, "stream_args": stream_args}
         self.spec.parameters.update({k: v for k, v in given.items() if v})
 

@@ -1563,6 +1563,34 @@ def event_envelope(api):
     }
 
 
+def set_tracking_params(api):
+    """runtimes/nuclio/serving.py:308-354 -- what set_tracking leaves in the function spec, and that a model server only
+    pushes records while tracking is enabled"""
+    ns = make_namespace(api)
+    out = {}
+
+    def spec_of(**kw):
+        fn = api.new_function("t", kind="serving")
+        fn.set_topology("router")
+        fn.set_tracking(**kw)
+        return {"track_models": fn.spec.track_models, "parameters": dict(fn.spec.parameters)}
+
+    out["defaults"] = spec_of()
+    out["all"] = spec_of(stream_path="dummy://x", batch=4, sample=2, stream_args={"mock": True})
+    out["disabled"] = spec_of(stream_path="dummy://x", enable_tracking=False)
+    out["zero_batch_is_not_set"] = spec_of(batch=0, sample=0)
+    for tag, enable in (("records_when_enabled", True), ("records_when_disabled", False)):
+        fn = api.new_function("t", kind="serving")
+        fn.set_topology("router")
+        fn.add_model("my", ".", class_name=ns["ModelTestingClass"](multiplier=100))
+        fn.set_tracking("dummy://", enable_tracking=enable)
+        server = fn.to_mock_server(namespace=ns)
+        server.test("/v2/models/my/infer", TESTDATA)
+        stream = getattr(getattr(server.context, "stream", None), "output_stream", None)
+        out[tag] = len(stream.event_list) if stream is not None else None
+    return out
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -2000,7 +2028,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
