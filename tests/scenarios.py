@@ -1591,6 +1591,36 @@ def set_tracking_params(api):
     return out
 
 
+def add_model_args(api):
+    """runtimes/nuclio/serving.py:356-445 -- add_model's argument rules in a router topology: what is required, the default
+    class of the function spec, a model object carrying its own arguments, the route's serialised form"""
+    ns = make_namespace(api)
+
+    def attempt(**kw):
+        fn = api.new_function("t", kind="serving")
+        fn.set_topology("router")
+        default = kw.pop("default_class", None)
+        if default:
+            fn.spec.default_class = default
+        try:
+            route = fn.add_model("m1", **kw)
+            d = route.to_dict()
+            return {k: d.get(k) for k in ("class_name", "class_args", "handler", "function") if d.get(k) is not None}
+        except Exception as exc:  # noqa: BLE001
+            return f"{type(exc).__name__}: {_first_line(exc)}"
+
+    return {
+        "no_path": attempt(class_name="ModelTestingClass"),
+        "path_without_class": attempt(model_path="."),
+        "default_class": attempt(model_path=".", default_class="ModelTestingClass", multiplier=3),
+        "class_not_a_string": attempt(model_path=".", class_name=5),
+        "handler_and_child": attempt(model_path=".", class_name="ModelTestingClass", handler="explain", child_function="child"),
+        "pathlike": attempt(model_path=__import__("pathlib").PurePosixPath("/models/m"), class_name="ModelTestingClass"),
+        "object_with_path": attempt(model_path="/x/y", class_name=ns["ModelTestingClass"](multiplier=7)),
+        "object_without_path": attempt(class_name=ns["ModelTestingClass"](multiplier=7, model_path="own")),
+    }
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -2028,7 +2058,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
