@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <limits>
 #include <sched.h>
 #include <thread>
@@ -305,8 +306,16 @@ bool parse_matrix_parallel(const char* first, const char* limit, float* out, int
     }
   };
   std::vector<std::thread> pool;
-  for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+  int started = 1;  // range 0 runs on this thread
+  try {
+    for (int t = 1; t < threads; ++t) {
+      pool.emplace_back(work, t);
+      ++started;
+    }
+  } catch (const std::exception&) {  // no more threads to be had: the ranges that got none are parsed here
+  }
   work(0);
+  for (int t = started; t < threads; ++t) work(t);
   for (auto& th : pool) th.join();
   for (char good : ok)
     if (!good) return false;
