@@ -327,8 +327,8 @@ bool parse_matrix_parallel(const char* first, const char* limit, float* out, int
 
 }  // namespace
 
-extern "C" int b2s_json_parse_inputs(const char* body, int64_t len, float* out, int64_t out_cap, int64_t* n_rows, int64_t* n_cols,
-                                     int64_t* value_begin, int64_t* value_end) {
+static int parse_inputs_impl(const char* body, int64_t len, float* out, int64_t out_cap, int64_t* n_rows, int64_t* n_cols,
+                             int64_t* value_begin, int64_t* value_end) {
   if (!body || len <= 0 || !out || !n_rows || !n_cols) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
   Cur c{body, body + len};
   if (!c.eat('{')) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "body is not a JSON object");
@@ -404,6 +404,15 @@ extern "C" int b2s_json_parse_inputs(const char* body, int64_t len, float* out, 
     if (c.eat(',')) continue;
     if (c.eat('}')) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "no \"inputs\" member");
     return b2s_int_fail(B2S_ERR_INVALID, "malformed JSON at offset %lld", (long long)(c.p - body));
+  }
+}
+
+extern "C" int b2s_json_parse_inputs(const char* body, int64_t len, float* out, int64_t out_cap, int64_t* n_rows, int64_t* n_cols,
+                                     int64_t* value_begin, int64_t* value_end) {
+  try {  // no C++ exception (an allocation failure on a huge body) crosses the C boundary
+    return parse_inputs_impl(body, len, out, out_cap, n_rows, n_cols, value_begin, value_end);
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "body parser failed: %s", e.what());
   }
 }
 
