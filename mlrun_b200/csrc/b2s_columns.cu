@@ -1,6 +1,8 @@
 // b2s_columns.cu -- C-ABI of the columnar feature-set transform plan (see include/b200serve.h, "columnar ingest").
 #include <cuda_runtime.h>
 
+#include <exception>
+
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
@@ -68,39 +70,47 @@ static void set_check(b2s_cols_t c, ColOp& op, int32_t check, double cmin, doubl
 }
 
 extern "C" int b2s_cols_create(int32_t n_in_slots, b2s_cols_t* out) {
-  if (!out || n_in_slots <= 0 || n_in_slots > 65536) return b2s_int_fail(B2S_ERR_INVALID, "bad n_in_slots");
-  auto* c = new b2s_cols_s();
-  c->n_in = n_in_slots;
-  c->in_used.assign(n_in_slots, 0);
-  *out = c;
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!out || n_in_slots <= 0 || n_in_slots > 65536) return b2s_int_fail(B2S_ERR_INVALID, "bad n_in_slots");
+    auto* c = new b2s_cols_s();
+    c->n_in = n_in_slots;
+    c->in_used.assign(n_in_slots, 0);
+    *out = c;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_cols_add_copy(b2s_cols_t c, int32_t src_slot, int32_t kind, int32_t has_fill, float fill, int32_t keep,
                                  int32_t check, double cmin, double cmax, int32_t* out_slot, int32_t* check_counter) {
-  if (int rc = check_src(c, src_slot, kind)) return rc;
-  if (kind == B2S_COL_I64 && (check || has_fill)) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "8-byte columns are copied verbatim");
-  if (!keep && !(check & 3)) return b2s_int_fail(B2S_ERR_INVALID, "a dropped column without a check is no op at all");
-  ColOp op{};
-  op.src = src_slot;
-  op.src_int = kind == B2S_COL_I32;
-  op.has_fill = (kind == B2S_COL_F32 && has_fill) ? 1 : 0;
-  op.fill = fill;
-  op.miss = -1;
-  set_check(c, op, check, cmin, cmax, check_counter);
-  if (!keep) {
-    op.kind = CK_CHECK;
-    op.dst = -1;
-  } else if (kind == B2S_COL_I64) {
-    op.kind = CK_COPY64;
-    op.dst = new_out(c, 2);
-  } else {
-    op.kind = (kind == B2S_COL_F32 && (op.has_fill || op.check)) ? CK_F32 : CK_COPY32;
-    op.dst = new_out(c, 1);
+  try {  // no C++ exception crosses the C boundary
+    if (int rc = check_src(c, src_slot, kind)) return rc;
+    if (kind == B2S_COL_I64 && (check || has_fill)) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "8-byte columns are copied verbatim");
+    if (!keep && !(check & 3)) return b2s_int_fail(B2S_ERR_INVALID, "a dropped column without a check is no op at all");
+    ColOp op{};
+    op.src = src_slot;
+    op.src_int = kind == B2S_COL_I32;
+    op.has_fill = (kind == B2S_COL_F32 && has_fill) ? 1 : 0;
+    op.fill = fill;
+    op.miss = -1;
+    set_check(c, op, check, cmin, cmax, check_counter);
+    if (!keep) {
+      op.kind = CK_CHECK;
+      op.dst = -1;
+    } else if (kind == B2S_COL_I64) {
+      op.kind = CK_COPY64;
+      op.dst = new_out(c, 2);
+    } else {
+      op.kind = (kind == B2S_COL_F32 && (op.has_fill || op.check)) ? CK_F32 : CK_COPY32;
+      op.dst = new_out(c, 1);
+    }
+    if (out_slot) *out_slot = op.dst;
+    c->ops.push_back(op);
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  if (out_slot) *out_slot = op.dst;
-  c->ops.push_back(op);
-  return B2S_OK;
 }
 
 static int add_map(b2s_cols_t c, int kind_op, int32_t src_slot, int32_t kind, int32_t has_fill, float fill, const double* a,
@@ -132,79 +142,103 @@ static int add_map(b2s_cols_t c, int kind_op, int32_t src_slot, int32_t kind, in
 extern "C" int b2s_cols_add_range_map(b2s_cols_t c, int32_t src_slot, int32_t kind, int32_t has_fill, float fill, const double* lo,
                                       const double* hi, const double* vals, int32_t n, int32_t check, double cmin, double cmax,
                                       int32_t* out_slot, int32_t* miss_counter, int32_t* check_counter) {
-  return add_map(c, CK_RANGE, src_slot, kind, has_fill, fill, lo, hi, vals, n, check, cmin, cmax, out_slot, miss_counter, check_counter);
+  try {  // no C++ exception crosses the C boundary
+    return add_map(c, CK_RANGE, src_slot, kind, has_fill, fill, lo, hi, vals, n, check, cmin, cmax, out_slot, miss_counter, check_counter);
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_cols_add_value_map(b2s_cols_t c, int32_t src_slot, int32_t kind, int32_t has_fill, float fill, const double* keys,
                                       const double* vals, int32_t n, int32_t check, double cmin, double cmax, int32_t* out_slot,
                                       int32_t* miss_counter, int32_t* check_counter) {
-  return add_map(c, CK_VALUE, src_slot, kind, has_fill, fill, keys, nullptr, vals, n, check, cmin, cmax, out_slot, miss_counter, check_counter);
+  try {  // no C++ exception crosses the C boundary
+    return add_map(c, CK_VALUE, src_slot, kind, has_fill, fill, keys, nullptr, vals, n, check, cmin, cmax, out_slot, miss_counter, check_counter);
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_cols_add_onehot(b2s_cols_t c, int32_t src_slot, int32_t kind, int32_t has_fill, float fill, const double* cats,
                                    int32_t n, int32_t* first_out_slot, int32_t* miss_counter) {
-  if (int rc = check_src(c, src_slot, kind)) return rc;
-  if (kind == B2S_COL_I64) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "one-hot takes 4-byte columns");
-  if (n <= 0 || n > 4096 || !cats) return b2s_int_fail(B2S_ERR_INVALID, "bad category list");
-  ColOp op{};
-  op.kind = CK_ONEHOT;
-  op.src = src_slot;
-  op.src_int = kind == B2S_COL_I32;
-  op.has_fill = (kind == B2S_COL_F32 && has_fill) ? 1 : 0;
-  op.fill = fill;
-  op.n = n;
-  op.tab = (int32_t)c->tab.size();
-  c->tab.insert(c->tab.end(), cats, cats + n);
-  op.miss = c->n_counters++;
-  op.counter = -1;
-  if (miss_counter) *miss_counter = op.miss;
-  op.dst = new_out(c, 1);
-  for (int q = 1; q < n; ++q) new_out(c, 1);
-  if (first_out_slot) *first_out_slot = op.dst;
-  c->ops.push_back(op);
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (int rc = check_src(c, src_slot, kind)) return rc;
+    if (kind == B2S_COL_I64) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "one-hot takes 4-byte columns");
+    if (n <= 0 || n > 4096 || !cats) return b2s_int_fail(B2S_ERR_INVALID, "bad category list");
+    ColOp op{};
+    op.kind = CK_ONEHOT;
+    op.src = src_slot;
+    op.src_int = kind == B2S_COL_I32;
+    op.has_fill = (kind == B2S_COL_F32 && has_fill) ? 1 : 0;
+    op.fill = fill;
+    op.n = n;
+    op.tab = (int32_t)c->tab.size();
+    c->tab.insert(c->tab.end(), cats, cats + n);
+    op.miss = c->n_counters++;
+    op.counter = -1;
+    if (miss_counter) *miss_counter = op.miss;
+    op.dst = new_out(c, 1);
+    for (int q = 1; q < n; ++q) new_out(c, 1);
+    if (first_out_slot) *first_out_slot = op.dst;
+    c->ops.push_back(op);
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_cols_add_date_part(b2s_cols_t c, int32_t src_slot, int32_t part, int32_t* out_slot, int32_t* nat_counter) {
-  if (int rc = check_src(c, src_slot, B2S_COL_I64)) return rc;
-  if (part < 0 || part > DP_LAST) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "date part %d is not computed on the device", part);
-  ColOp op{};
-  op.kind = CK_DATE;
-  op.src = src_slot;
-  op.part = part;
-  op.miss = c->n_counters++;
-  op.counter = -1;
-  if (nat_counter) *nat_counter = op.miss;
-  op.dst = new_out(c, 1);
-  if (out_slot) *out_slot = op.dst;
-  c->ops.push_back(op);
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (int rc = check_src(c, src_slot, B2S_COL_I64)) return rc;
+    if (part < 0 || part > DP_LAST) return b2s_int_fail(B2S_ERR_UNSUPPORTED, "date part %d is not computed on the device", part);
+    ColOp op{};
+    op.kind = CK_DATE;
+    op.src = src_slot;
+    op.part = part;
+    op.miss = c->n_counters++;
+    op.counter = -1;
+    if (nat_counter) *nat_counter = op.miss;
+    op.dst = new_out(c, 1);
+    if (out_slot) *out_slot = op.dst;
+    c->ops.push_back(op);
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_cols_finalize(b2s_cols_t c) {
-  if (!c) return b2s_int_fail(B2S_ERR_INVALID, "null plan");
-  if (c->finalized) return B2S_OK;
-  if (c->ops.empty()) return b2s_int_fail(B2S_ERR_INVALID, "plan has no column ops");
-  if (!b2s_int_inited()) return b2s_int_fail(B2S_ERR_STATE, "b2s_init was not called (no CUDA device: there is no CPU fallback)");
-  COL_TRY(cudaSetDevice(b2s_int_device()));
-  COL_TRY(cudaMalloc(&c->d_ops, c->ops.size() * sizeof(ColOp)));
-  COL_TRY(cudaMemcpy(c->d_ops, c->ops.data(), c->ops.size() * sizeof(ColOp), cudaMemcpyHostToDevice));
-  COL_TRY(cudaMalloc(&c->d_tab, std::max<size_t>(c->tab.size(), 1) * sizeof(double)));
-  if (!c->tab.empty()) COL_TRY(cudaMemcpy(c->d_tab, c->tab.data(), c->tab.size() * sizeof(double), cudaMemcpyHostToDevice));
-  COL_TRY(cudaMalloc(&c->d_cnt, std::max(c->n_counters, 1) * sizeof(unsigned long long)));
-  int occ = 0;
-  COL_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, columns_kernel, kColThreads, 0));
-  c->grid = b2s_int_sm_count() * std::max(occ, 1);
-  for (int i = 0; i < 4; ++i) COL_TRY(cudaEventCreate(&c->ev[i]));
-  c->finalized = true;
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!c) return b2s_int_fail(B2S_ERR_INVALID, "null plan");
+    if (c->finalized) return B2S_OK;
+    if (c->ops.empty()) return b2s_int_fail(B2S_ERR_INVALID, "plan has no column ops");
+    if (!b2s_int_inited()) return b2s_int_fail(B2S_ERR_STATE, "b2s_init was not called (no CUDA device: there is no CPU fallback)");
+    COL_TRY(cudaSetDevice(b2s_int_device()));
+    COL_TRY(cudaMalloc(&c->d_ops, c->ops.size() * sizeof(ColOp)));
+    COL_TRY(cudaMemcpy(c->d_ops, c->ops.data(), c->ops.size() * sizeof(ColOp), cudaMemcpyHostToDevice));
+    COL_TRY(cudaMalloc(&c->d_tab, std::max<size_t>(c->tab.size(), 1) * sizeof(double)));
+    if (!c->tab.empty()) COL_TRY(cudaMemcpy(c->d_tab, c->tab.data(), c->tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    COL_TRY(cudaMalloc(&c->d_cnt, std::max(c->n_counters, 1) * sizeof(unsigned long long)));
+    int occ = 0;
+    COL_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, columns_kernel, kColThreads, 0));
+    c->grid = b2s_int_sm_count() * std::max(occ, 1);
+    for (int i = 0; i < 4; ++i) COL_TRY(cudaEventCreate(&c->ev[i]));
+    c->finalized = true;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_cols_info(b2s_cols_t c, int32_t* n_out_slots, int32_t* n_counters) {
-  if (!c) return b2s_int_fail(B2S_ERR_INVALID, "null plan");
-  if (n_out_slots) *n_out_slots = (int32_t)c->out_words.size();
-  if (n_counters) *n_counters = c->n_counters;
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!c) return b2s_int_fail(B2S_ERR_INVALID, "null plan");
+    if (n_out_slots) *n_out_slots = (int32_t)c->out_words.size();
+    if (n_counters) *n_counters = c->n_counters;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 static int launch_cols(b2s_cols_t c, const void* d_in, int64_t in_stride, int64_t n_rows, void* d_out, int64_t out_stride,
@@ -234,89 +268,105 @@ static int launch_cols(b2s_cols_t c, const void* d_in, int64_t in_stride, int64_
 
 extern "C" int b2s_cols_run_device(b2s_cols_t c, const void* d_in, int64_t in_slot_stride, int64_t n_rows, void* d_out,
                                    int64_t out_slot_stride, uint64_t* d_counters, void* stream) {
-  if (!c || !c->finalized) return b2s_int_fail(B2S_ERR_STATE, "plan not finalized");
-  if (n_rows < 0 || in_slot_stride < n_rows * 4 || out_slot_stride < n_rows * 4 || (in_slot_stride & 7) || (out_slot_stride & 7))
-    return b2s_int_fail(B2S_ERR_INVALID, "slot strides must hold n_rows words and be multiples of 8 bytes");
-  if (n_rows == 0) return B2S_OK;
-  if (c->n_counters && !d_counters) return b2s_int_fail(B2S_ERR_INVALID, "the plan has %d counters: pass a device array", c->n_counters);
-  COL_TRY(cudaSetDevice(b2s_int_device()));
-  return launch_cols(c, d_in, in_slot_stride, n_rows, d_out, out_slot_stride, (unsigned long long*)d_counters,
-                     stream ? (cudaStream_t)stream : b2s_int_stream());
+  try {  // no C++ exception crosses the C boundary
+    if (!c || !c->finalized) return b2s_int_fail(B2S_ERR_STATE, "plan not finalized");
+    if (n_rows < 0 || in_slot_stride < n_rows * 4 || out_slot_stride < n_rows * 4 || (in_slot_stride & 7) || (out_slot_stride & 7))
+      return b2s_int_fail(B2S_ERR_INVALID, "slot strides must hold n_rows words and be multiples of 8 bytes");
+    if (n_rows == 0) return B2S_OK;
+    if (c->n_counters && !d_counters) return b2s_int_fail(B2S_ERR_INVALID, "the plan has %d counters: pass a device array", c->n_counters);
+    COL_TRY(cudaSetDevice(b2s_int_device()));
+    return launch_cols(c, d_in, in_slot_stride, n_rows, d_out, out_slot_stride, (unsigned long long*)d_counters,
+                       stream ? (cudaStream_t)stream : b2s_int_stream());
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_cols_time_device(b2s_cols_t c, const void* const* d_in, int32_t n_bufs, int64_t in_slot_stride, int64_t n_rows,
                                     void* d_out, int64_t out_slot_stride, uint64_t* d_counters, int32_t n_iters, float* total_ms) {
-  if (!c || !c->finalized) return b2s_int_fail(B2S_ERR_STATE, "plan not finalized");
-  if (!d_in || n_bufs <= 0 || n_iters <= 0 || !total_ms) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
-  COL_TRY(cudaSetDevice(b2s_int_device()));
-  cudaStream_t st = b2s_int_stream();
-  std::lock_guard<std::mutex> lk(c->mu);
-  COL_TRY(cudaEventRecord(c->ev[0], st));
-  for (int i = 0; i < n_iters; ++i)
-    if (int rc = launch_cols(c, d_in[i % n_bufs], in_slot_stride, n_rows, d_out, out_slot_stride, (unsigned long long*)d_counters, st)) return rc;
-  COL_TRY(cudaEventRecord(c->ev[1], st));
-  COL_TRY(cudaStreamSynchronize(st));
-  COL_TRY(cudaEventElapsedTime(total_ms, c->ev[0], c->ev[1]));
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!c || !c->finalized) return b2s_int_fail(B2S_ERR_STATE, "plan not finalized");
+    if (!d_in || n_bufs <= 0 || n_iters <= 0 || !total_ms) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+    COL_TRY(cudaSetDevice(b2s_int_device()));
+    cudaStream_t st = b2s_int_stream();
+    std::lock_guard<std::mutex> lk(c->mu);
+    COL_TRY(cudaEventRecord(c->ev[0], st));
+    for (int i = 0; i < n_iters; ++i)
+      if (int rc = launch_cols(c, d_in[i % n_bufs], in_slot_stride, n_rows, d_out, out_slot_stride, (unsigned long long*)d_counters, st)) return rc;
+    COL_TRY(cudaEventRecord(c->ev[1], st));
+    COL_TRY(cudaStreamSynchronize(st));
+    COL_TRY(cudaEventElapsedTime(total_ms, c->ev[0], c->ev[1]));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_cols_run_host(b2s_cols_t c, const void* const* h_in_slots, int64_t n_rows, void* const* h_out_slots,
                                  uint64_t* counters, b2s_stats* stats) {
-  if (!c || !c->finalized) return b2s_int_fail(B2S_ERR_STATE, "plan not finalized");
-  if (n_rows < 0 || !h_in_slots || !h_out_slots) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
-  if (c->n_counters && !counters) return b2s_int_fail(B2S_ERR_INVALID, "the plan has %d counters: pass an array", c->n_counters);
-  for (int i = 0; i < c->n_counters; ++i) counters[i] = 0;
-  if (n_rows == 0) return B2S_OK;
-  std::lock_guard<std::mutex> lk(c->mu);
-  COL_TRY(cudaSetDevice(b2s_int_device()));
-  const int64_t stride = ((n_rows * 4 + 255) / 256) * 256;
-  const size_t n_out = c->out_words.size();
-  if (n_rows > c->cap_rows) {
-    if (c->d_in) { cudaFree(c->d_in); cudaFree(c->d_out); c->d_in = c->d_out = nullptr; }
-    c->cap_rows = 0;
-    COL_TRY(cudaMalloc(&c->d_in, (size_t)stride * c->n_in));
-    COL_TRY(cudaMalloc(&c->d_out, (size_t)stride * n_out));
-    c->cap_rows = n_rows;
+  try {  // no C++ exception crosses the C boundary
+    if (!c || !c->finalized) return b2s_int_fail(B2S_ERR_STATE, "plan not finalized");
+    if (n_rows < 0 || !h_in_slots || !h_out_slots) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+    if (c->n_counters && !counters) return b2s_int_fail(B2S_ERR_INVALID, "the plan has %d counters: pass an array", c->n_counters);
+    for (int i = 0; i < c->n_counters; ++i) counters[i] = 0;
+    if (n_rows == 0) return B2S_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    COL_TRY(cudaSetDevice(b2s_int_device()));
+    const int64_t stride = ((n_rows * 4 + 255) / 256) * 256;
+    const size_t n_out = c->out_words.size();
+    if (n_rows > c->cap_rows) {
+      if (c->d_in) { cudaFree(c->d_in); cudaFree(c->d_out); c->d_in = c->d_out = nullptr; }
+      c->cap_rows = 0;
+      COL_TRY(cudaMalloc(&c->d_in, (size_t)stride * c->n_in));
+      COL_TRY(cudaMalloc(&c->d_out, (size_t)stride * n_out));
+      c->cap_rows = n_rows;
+    }
+    cudaStream_t st = b2s_int_stream();
+    COL_TRY(cudaEventRecord(c->ev[0], st));
+    for (int s = 0; s < c->n_in; ++s) {
+      if (!c->in_used[s]) continue;
+      if (!h_in_slots[s]) return b2s_int_fail(B2S_ERR_INVALID, "input slot %d is read by the plan but its pointer is NULL", s);
+      COL_TRY(cudaMemcpyAsync(c->d_in + (size_t)s * stride, h_in_slots[s], (size_t)n_rows * 4 * c->in_used[s], cudaMemcpyHostToDevice, st));
+    }
+    if (c->n_counters) COL_TRY(cudaMemsetAsync(c->d_cnt, 0, c->n_counters * sizeof(unsigned long long), st));
+    COL_TRY(cudaEventRecord(c->ev[1], st));
+    if (int rc = launch_cols(c, c->d_in, stride, n_rows, c->d_out, stride, c->d_cnt, st)) return rc;
+    COL_TRY(cudaEventRecord(c->ev[2], st));
+    for (size_t s = 0; s < n_out; ++s) {
+      if (!c->out_words[s]) continue;  // second half of an 8-byte column
+      if (!h_out_slots[s]) return b2s_int_fail(B2S_ERR_INVALID, "output slot %zu has no destination", s);
+      COL_TRY(cudaMemcpyAsync(h_out_slots[s], c->d_out + s * (size_t)stride, (size_t)n_rows * 4 * c->out_words[s], cudaMemcpyDeviceToHost, st));
+    }
+    if (c->n_counters) COL_TRY(cudaMemcpyAsync(counters, c->d_cnt, c->n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    COL_TRY(cudaEventRecord(c->ev[3], st));
+    COL_TRY(cudaStreamSynchronize(st));
+    if (stats) {
+      memset(stats, 0, sizeof(*stats));
+      stats->rows = n_rows;
+      cudaEventElapsedTime(&stats->h2d_ms, c->ev[0], c->ev[1]);
+      cudaEventElapsedTime(&stats->kernel_ms, c->ev[1], c->ev[2]);
+      cudaEventElapsedTime(&stats->d2h_ms, c->ev[2], c->ev[3]);
+      stats->kernels = 1;
+    }
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  cudaStream_t st = b2s_int_stream();
-  COL_TRY(cudaEventRecord(c->ev[0], st));
-  for (int s = 0; s < c->n_in; ++s) {
-    if (!c->in_used[s]) continue;
-    if (!h_in_slots[s]) return b2s_int_fail(B2S_ERR_INVALID, "input slot %d is read by the plan but its pointer is NULL", s);
-    COL_TRY(cudaMemcpyAsync(c->d_in + (size_t)s * stride, h_in_slots[s], (size_t)n_rows * 4 * c->in_used[s], cudaMemcpyHostToDevice, st));
-  }
-  if (c->n_counters) COL_TRY(cudaMemsetAsync(c->d_cnt, 0, c->n_counters * sizeof(unsigned long long), st));
-  COL_TRY(cudaEventRecord(c->ev[1], st));
-  if (int rc = launch_cols(c, c->d_in, stride, n_rows, c->d_out, stride, c->d_cnt, st)) return rc;
-  COL_TRY(cudaEventRecord(c->ev[2], st));
-  for (size_t s = 0; s < n_out; ++s) {
-    if (!c->out_words[s]) continue;  // second half of an 8-byte column
-    if (!h_out_slots[s]) return b2s_int_fail(B2S_ERR_INVALID, "output slot %zu has no destination", s);
-    COL_TRY(cudaMemcpyAsync(h_out_slots[s], c->d_out + s * (size_t)stride, (size_t)n_rows * 4 * c->out_words[s], cudaMemcpyDeviceToHost, st));
-  }
-  if (c->n_counters) COL_TRY(cudaMemcpyAsync(counters, c->d_cnt, c->n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  COL_TRY(cudaEventRecord(c->ev[3], st));
-  COL_TRY(cudaStreamSynchronize(st));
-  if (stats) {
-    memset(stats, 0, sizeof(*stats));
-    stats->rows = n_rows;
-    cudaEventElapsedTime(&stats->h2d_ms, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&stats->kernel_ms, c->ev[1], c->ev[2]);
-    cudaEventElapsedTime(&stats->d2h_ms, c->ev[2], c->ev[3]);
-    stats->kernels = 1;
-  }
-  return B2S_OK;
 }
 
 extern "C" int b2s_cols_destroy(b2s_cols_t c) {
-  if (!c) return B2S_OK;
-  if (c->d_ops) cudaFree(c->d_ops);
-  if (c->d_tab) cudaFree(c->d_tab);
-  if (c->d_cnt) cudaFree(c->d_cnt);
-  if (c->d_in) cudaFree(c->d_in);
-  if (c->d_out) cudaFree(c->d_out);
-  for (auto& e : c->ev)
-    if (e) cudaEventDestroy(e);
-  delete c;
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!c) return B2S_OK;
+    if (c->d_ops) cudaFree(c->d_ops);
+    if (c->d_tab) cudaFree(c->d_tab);
+    if (c->d_cnt) cudaFree(c->d_cnt);
+    if (c->d_in) cudaFree(c->d_in);
+    if (c->d_out) cudaFree(c->d_out);
+    for (auto& e : c->ev)
+      if (e) cudaEventDestroy(e);
+    delete c;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }

@@ -2,6 +2,8 @@
 // configuration, pinned ring + dispatcher thread (event coalescing), CUDA-event timing.
 #include <cuda_runtime.h>
 
+#include <exception>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -503,64 +505,80 @@ extern "C" int b2s_version(void) { return B2S_VERSION; }
 extern "C" const char* b2s_last_error(void) { return g_err.c_str(); }
 
 extern "C" int b2s_init(int device_ordinal, const char* cfg) {
-  std::lock_guard<std::mutex> lk(G.mu);
-  if (G.inited) return B2S_OK;
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n == 0)
-    return fail(B2S_ERR_NO_DEVICE, "no CUDA device (%s); this engine has no CPU fallback",
-                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-  if (device_ordinal < 0 || device_ordinal >= n) return fail(B2S_ERR_INVALID, "device ordinal %d out of range", device_ordinal);
-  CUDA_TRY(cudaSetDevice(device_ordinal));
-  CUDA_TRY(cudaGetDeviceProperties(&G.prop, device_ordinal));
-  CUDA_TRY(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaStreamCreateWithFlags(&G.copy_stream, cudaStreamNonBlocking));
-  G.device = device_ordinal;
-  std::string c = cfg ? cfg : "";
-  G.ring_slots = (int)cfg_get(c, "ring_slots", 4);
-  G.max_batch = cfg_get(c, "max_batch", 65536);
-  G.max_wait_us = cfg_get(c, "max_wait_us", 200);
-  if (G.ring_slots < 2) G.ring_slots = 2;
-  G.inited = true;
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (G.inited) return B2S_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      return fail(B2S_ERR_NO_DEVICE, "no CUDA device (%s); this engine has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device_ordinal < 0 || device_ordinal >= n) return fail(B2S_ERR_INVALID, "device ordinal %d out of range", device_ordinal);
+    CUDA_TRY(cudaSetDevice(device_ordinal));
+    CUDA_TRY(cudaGetDeviceProperties(&G.prop, device_ordinal));
+    CUDA_TRY(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&G.copy_stream, cudaStreamNonBlocking));
+    G.device = device_ordinal;
+    std::string c = cfg ? cfg : "";
+    G.ring_slots = (int)cfg_get(c, "ring_slots", 4);
+    G.max_batch = cfg_get(c, "max_batch", 65536);
+    G.max_wait_us = cfg_get(c, "max_wait_us", 200);
+    if (G.ring_slots < 2) G.ring_slots = 2;
+    G.inited = true;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_shutdown(void) {
-  std::lock_guard<std::mutex> lk(G.mu);
-  if (!G.inited) return B2S_OK;
-  cudaStreamDestroy(G.stream);
-  cudaStreamDestroy(G.copy_stream);
-  G.stream = G.copy_stream = nullptr;
-  G.inited = false;
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!G.inited) return B2S_OK;
+    cudaStreamDestroy(G.stream);
+    cudaStreamDestroy(G.copy_stream);
+    G.stream = G.copy_stream = nullptr;
+    G.inited = false;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_device_info(b2s_devinfo* out) {
-  if (!G.inited) return fail(B2S_ERR_STATE, "b2s_init was not called");
-  if (!out) return fail(B2S_ERR_INVALID, "null out");
-  memset(out, 0, sizeof(*out));
-  out->ordinal = G.device;
-  out->sm_count = G.prop.multiProcessorCount;
-  out->cc_major = G.prop.major;
-  out->cc_minor = G.prop.minor;
-  out->total_mem = (int64_t)G.prop.totalGlobalMem;
-  out->l2_bytes = G.prop.l2CacheSize;
-  out->smem_per_block_optin = (int64_t)G.prop.sharedMemPerBlockOptin;
-  strncpy(out->name, G.prop.name, sizeof(out->name) - 1);
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!G.inited) return fail(B2S_ERR_STATE, "b2s_init was not called");
+    if (!out) return fail(B2S_ERR_INVALID, "null out");
+    memset(out, 0, sizeof(*out));
+    out->ordinal = G.device;
+    out->sm_count = G.prop.multiProcessorCount;
+    out->cc_major = G.prop.major;
+    out->cc_minor = G.prop.minor;
+    out->total_mem = (int64_t)G.prop.totalGlobalMem;
+    out->l2_bytes = G.prop.l2CacheSize;
+    out->smem_per_block_optin = (int64_t)G.prop.sharedMemPerBlockOptin;
+    strncpy(out->name, G.prop.name, sizeof(out->name) - 1);
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int64_t b2s_launch_count(void) { return G.launches.load(); }
 
 // ------------------------------------------------------------------------------------------ C-ABI: plan building
 extern "C" int b2s_plan_create(int32_t n_in_cols, b2s_plan_t* out) {
-  if (!out || n_in_cols <= 0 || n_in_cols > 65536) return fail(B2S_ERR_INVALID, "bad n_in_cols %d", n_in_cols);
-  auto* p = new b2s_plan_s();
-  p->n_in = n_in_cols;
-  p->fill.assign(n_in_cols, std::numeric_limits<float>::quiet_NaN());
-  p->maps.resize(n_in_cols);
-  *out = p;
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!out || n_in_cols <= 0 || n_in_cols > 65536) return fail(B2S_ERR_INVALID, "bad n_in_cols %d", n_in_cols);
+    auto* p = new b2s_plan_s();
+    p->n_in = n_in_cols;
+    p->fill.assign(n_in_cols, std::numeric_limits<float>::quiet_NaN());
+    p->maps.resize(n_in_cols);
+    *out = p;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 static int check_build(b2s_plan_t p) {
@@ -570,40 +588,56 @@ static int check_build(b2s_plan_t p) {
 }
 
 extern "C" int b2s_plan_set_impute(b2s_plan_t p, const int32_t* cols, const float* fills, int32_t n) {
-  if (int rc = check_build(p)) return rc;
-  for (int i = 0; i < n; ++i) {
-    if (cols[i] < 0 || cols[i] >= p->n_in) return fail(B2S_ERR_INVALID, "impute column %d out of range", cols[i]);
-    p->fill[cols[i]] = fills[i];
+  try {  // no C++ exception crosses the C boundary
+    if (int rc = check_build(p)) return rc;
+    for (int i = 0; i < n; ++i) {
+      if (cols[i] < 0 || cols[i] >= p->n_in) return fail(B2S_ERR_INVALID, "impute column %d out of range", cols[i]);
+      p->fill[cols[i]] = fills[i];
+    }
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  return B2S_OK;
 }
 
 extern "C" int b2s_plan_add_value_map(b2s_plan_t p, int32_t col, const float* keys, const float* vals, int32_t n) {
-  if (int rc = check_build(p)) return rc;
-  if (col < 0 || col >= p->n_in) return fail(B2S_ERR_INVALID, "map column %d out of range", col);
-  for (int i = 0; i < n; ++i) p->maps[col].push_back(MapEntry{keys[i], 0.f, vals[i], (i == 0 ? 256 : 0) | 0});
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (int rc = check_build(p)) return rc;
+    if (col < 0 || col >= p->n_in) return fail(B2S_ERR_INVALID, "map column %d out of range", col);
+    for (int i = 0; i < n; ++i) p->maps[col].push_back(MapEntry{keys[i], 0.f, vals[i], (i == 0 ? 256 : 0) | 0});
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_plan_add_range_map(b2s_plan_t p, int32_t col, const float* lo, const float* hi, const float* vals, int32_t n) {
-  if (int rc = check_build(p)) return rc;
-  if (col < 0 || col >= p->n_in) return fail(B2S_ERR_INVALID, "map column %d out of range", col);
-  for (int i = 0; i < n; ++i) p->maps[col].push_back(MapEntry{lo[i], hi[i], vals[i], (i == 0 ? 256 : 0) | 1});
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (int rc = check_build(p)) return rc;
+    if (col < 0 || col >= p->n_in) return fail(B2S_ERR_INVALID, "map column %d out of range", col);
+    for (int i = 0; i < n; ++i) p->maps[col].push_back(MapEntry{lo[i], hi[i], vals[i], (i == 0 ? 256 : 0) | 1});
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_plan_set_output_schema(b2s_plan_t p, const int32_t* src_col, const int32_t* kind, const float* arg, int32_t n_out) {
-  if (int rc = check_build(p)) return rc;
-  if (n_out <= 0) return fail(B2S_ERR_INVALID, "empty output schema");
-  if (!p->models.empty()) return fail(B2S_ERR_STATE, "set the output schema before adding models");
-  p->out_src.assign(src_col, src_col + n_out);
-  p->out_kind.assign(kind, kind + n_out);
-  p->out_arg.assign(arg, arg + n_out);
-  for (int j = 0; j < n_out; ++j) {
-    if (src_col[j] < 0 || src_col[j] >= p->n_in) return fail(B2S_ERR_INVALID, "schema source column %d out of range", src_col[j]);
-    if (kind[j] != B2S_OUT_COPY && kind[j] != B2S_OUT_ONEHOT) return fail(B2S_ERR_INVALID, "schema kind %d unknown", kind[j]);
+  try {  // no C++ exception crosses the C boundary
+    if (int rc = check_build(p)) return rc;
+    if (n_out <= 0) return fail(B2S_ERR_INVALID, "empty output schema");
+    if (!p->models.empty()) return fail(B2S_ERR_STATE, "set the output schema before adding models");
+    p->out_src.assign(src_col, src_col + n_out);
+    p->out_kind.assign(kind, kind + n_out);
+    p->out_arg.assign(arg, arg + n_out);
+    for (int j = 0; j < n_out; ++j) {
+      if (src_col[j] < 0 || src_col[j] >= p->n_in) return fail(B2S_ERR_INVALID, "schema source column %d out of range", src_col[j]);
+      if (kind[j] != B2S_OUT_COPY && kind[j] != B2S_OUT_ONEHOT) return fail(B2S_ERR_INVALID, "schema kind %d unknown", kind[j]);
+    }
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  return B2S_OK;
 }
 
 static int n_out_of(b2s_plan_t p) { return p->out_src.empty() ? p->n_in : (int)p->out_src.size(); }
@@ -619,19 +653,23 @@ static int check_link(int link, int n_scores, int n_classes) {
 
 extern "C" int b2s_plan_add_linear_model(b2s_plan_t p, const double* W, const double* b, int32_t n_scores, int32_t link,
                                          const int32_t* classes, int32_t n_classes) {
-  if (int rc = check_build(p)) return rc;
-  if (int rc = check_link(link, n_scores, classes ? n_classes : 0)) return rc;
-  if ((int)p->models.size() >= kMaxModels) return fail(B2S_ERR_UNSUPPORTED, "more than %d models in one plan", kMaxModels);
-  HostModel m;
-  m.kind = MK_LINEAR;
-  m.n_scores = n_scores;
-  m.link = link;
-  const int no = n_out_of(p);
-  m.W.assign(W, W + (size_t)n_scores * no);
-  m.b.assign(b, b + n_scores);
-  if (classes) m.classes.assign(classes, classes + n_classes);
-  p->models.push_back(std::move(m));
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (int rc = check_build(p)) return rc;
+    if (int rc = check_link(link, n_scores, classes ? n_classes : 0)) return rc;
+    if ((int)p->models.size() >= kMaxModels) return fail(B2S_ERR_UNSUPPORTED, "more than %d models in one plan", kMaxModels);
+    HostModel m;
+    m.kind = MK_LINEAR;
+    m.n_scores = n_scores;
+    m.link = link;
+    const int no = n_out_of(p);
+    m.W.assign(W, W + (size_t)n_scores * no);
+    m.b.assign(b, b + n_scores);
+    if (classes) m.classes.assign(classes, classes + n_classes);
+    p->models.push_back(std::move(m));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_plan_add_tree_model(b2s_plan_t p, int32_t n_trees, const int32_t* tree_offset, const int32_t* feature,
@@ -639,50 +677,58 @@ extern "C" int b2s_plan_add_tree_model(b2s_plan_t p, int32_t n_trees, const int3
                                        const double* leaf_value, const int32_t* tree_slot, const double* tree_scale,
                                        const double* init, int32_t n_scores, int32_t link, const int32_t* classes,
                                        int32_t n_classes) {
-  if (int rc = check_build(p)) return rc;
-  if (int rc = check_link(link, n_scores, classes ? n_classes : 0)) return rc;
-  if (n_scores > 16) return fail(B2S_ERR_UNSUPPORTED, "tree models support at most 16 scores");
-  if ((int)p->models.size() >= kMaxModels) return fail(B2S_ERR_UNSUPPORTED, "more than %d models in one plan", kMaxModels);
-  if (n_trees < 1) return fail(B2S_ERR_INVALID, "n_trees < 1");
-  HostModel m;
-  m.kind = MK_TREES;
-  m.n_scores = n_scores;
-  m.link = link;
-  const int nn = tree_offset[n_trees];
-  const int no = n_out_of(p);
-  m.tree_offset.assign(tree_offset, tree_offset + n_trees + 1);
-  m.feature.assign(feature, feature + nn);
-  m.threshold.assign(threshold, threshold + nn);
-  m.left.assign(left, left + nn);
-  m.right.assign(right, right + nn);
-  m.leaf_value.assign(leaf_value, leaf_value + nn);
-  m.tree_slot.assign(tree_slot, tree_slot + n_trees);
-  m.tree_scale.assign(tree_scale, tree_scale + n_trees);
-  m.init.assign(init, init + n_scores);
-  if (classes) m.classes.assign(classes, classes + n_classes);
-  for (int t = 0; t < n_trees; ++t) {
-    if (tree_slot[t] < 0 || tree_slot[t] >= n_scores) return fail(B2S_ERR_INVALID, "tree %d slot out of range", t);
-    const int lo = tree_offset[t], hi = tree_offset[t + 1];
-    if (hi <= lo) return fail(B2S_ERR_INVALID, "tree %d is empty", t);
-    for (int i = lo; i < hi; ++i) {
-      if (feature[i] >= no) return fail(B2S_ERR_INVALID, "tree %d node %d feature %d >= n_out %d", t, i - lo, feature[i], no);
-      if (feature[i] >= 0) {
-        // children are tree-relative and must point forward (no cycles => the walk terminates)
-        if (left[i] <= i - lo || right[i] <= i - lo || left[i] >= hi - lo || right[i] >= hi - lo)
-          return fail(B2S_ERR_INVALID, "tree %d node %d has bad children", t, i - lo);
+  try {  // no C++ exception crosses the C boundary
+    if (int rc = check_build(p)) return rc;
+    if (int rc = check_link(link, n_scores, classes ? n_classes : 0)) return rc;
+    if (n_scores > 16) return fail(B2S_ERR_UNSUPPORTED, "tree models support at most 16 scores");
+    if ((int)p->models.size() >= kMaxModels) return fail(B2S_ERR_UNSUPPORTED, "more than %d models in one plan", kMaxModels);
+    if (n_trees < 1) return fail(B2S_ERR_INVALID, "n_trees < 1");
+    HostModel m;
+    m.kind = MK_TREES;
+    m.n_scores = n_scores;
+    m.link = link;
+    const int nn = tree_offset[n_trees];
+    const int no = n_out_of(p);
+    m.tree_offset.assign(tree_offset, tree_offset + n_trees + 1);
+    m.feature.assign(feature, feature + nn);
+    m.threshold.assign(threshold, threshold + nn);
+    m.left.assign(left, left + nn);
+    m.right.assign(right, right + nn);
+    m.leaf_value.assign(leaf_value, leaf_value + nn);
+    m.tree_slot.assign(tree_slot, tree_slot + n_trees);
+    m.tree_scale.assign(tree_scale, tree_scale + n_trees);
+    m.init.assign(init, init + n_scores);
+    if (classes) m.classes.assign(classes, classes + n_classes);
+    for (int t = 0; t < n_trees; ++t) {
+      if (tree_slot[t] < 0 || tree_slot[t] >= n_scores) return fail(B2S_ERR_INVALID, "tree %d slot out of range", t);
+      const int lo = tree_offset[t], hi = tree_offset[t + 1];
+      if (hi <= lo) return fail(B2S_ERR_INVALID, "tree %d is empty", t);
+      for (int i = lo; i < hi; ++i) {
+        if (feature[i] >= no) return fail(B2S_ERR_INVALID, "tree %d node %d feature %d >= n_out %d", t, i - lo, feature[i], no);
+        if (feature[i] >= 0) {
+          // children are tree-relative and must point forward (no cycles => the walk terminates)
+          if (left[i] <= i - lo || right[i] <= i - lo || left[i] >= hi - lo || right[i] >= hi - lo)
+            return fail(B2S_ERR_INVALID, "tree %d node %d has bad children", t, i - lo);
+        }
       }
     }
+    p->models.push_back(std::move(m));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  p->models.push_back(std::move(m));
-  return B2S_OK;
 }
 
 extern "C" int b2s_plan_set_vote(b2s_plan_t p, int32_t vote_kind, const double* weights, int32_t n_weights) {
-  if (int rc = check_build(p)) return rc;
-  if (vote_kind < 0 || vote_kind > 2) return fail(B2S_ERR_INVALID, "unknown vote kind %d", vote_kind);
-  p->vote_kind = vote_kind;
-  p->vote_w.assign(weights, weights + (weights ? n_weights : 0));
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (int rc = check_build(p)) return rc;
+    if (vote_kind < 0 || vote_kind > 2) return fail(B2S_ERR_INVALID, "unknown vote kind %d", vote_kind);
+    p->vote_kind = vote_kind;
+    p->vote_w.assign(weights, weights + (weights ? n_weights : 0));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 // ------------------------------------------------------------------------------------------ finalize
@@ -693,555 +739,559 @@ static int pow2_at_least(int x) {
 }
 
 extern "C" int b2s_plan_finalize(b2s_plan_t p) {
-  if (int rc = check_build(p)) return rc;
-  if (!G.inited) return fail(B2S_ERR_STATE, "b2s_init was not called");
-  const int n_in = p->n_in;
-  const bool identity_schema = p->out_src.empty();
-  if (identity_schema) {
-    p->out_src.resize(n_in);
-    p->out_kind.assign(n_in, B2S_OUT_COPY);
-    p->out_arg.assign(n_in, 0.f);
-    for (int j = 0; j < n_in; ++j) p->out_src[j] = j;
-  }
-  const int n_out = (int)p->out_src.size();
-  const int M = (int)p->models.size();
-  if (p->vote_kind != B2S_VOTE_NONE) {
-    if (M == 0) return fail(B2S_ERR_INVALID, "vote without models");
-    if ((int)p->vote_w.size() != M) return fail(B2S_ERR_INVALID, "vote weights (%d) != models (%d)", (int)p->vote_w.size(), M);
-  }
-  bool any_tree = false, any_class = false, any_reg = false;
-  int total_scores = 0, max_scores = 1;
-  for (auto& m : p->models) {
-    any_tree |= (m.kind == MK_TREES);
-    (m.link == B2S_LINK_IDENTITY ? any_reg : any_class) = true;
-    total_scores += m.n_scores;
-    max_scores = std::max(max_scores, m.n_scores);
-  }
-  if (any_class && any_reg) return fail(B2S_ERR_UNSUPPORTED, "classifiers and regressors cannot share one plan output");
-  if (p->vote_kind == B2S_VOTE_MAJORITY && !any_class && M) {
-    // regression outputs voted as labels: allowed (VotingEnsemble casts to int, routers.py:778-780)
-  }
-  p->mode = M == 0 ? MODE_STORE : (any_tree ? MODE_TREES : MODE_LINEAR);
-  p->out_is_int = (M > 0 && (any_class || p->vote_kind == B2S_VOTE_MAJORITY)) ? 1 : 0;
-  if (p->vote_kind == B2S_VOTE_MEAN) p->out_is_int = 0;
-  p->out_cols = M == 0 ? n_out : (p->vote_kind == B2S_VOTE_NONE ? M : 1);
+  try {  // no C++ exception crosses the C boundary
+    if (int rc = check_build(p)) return rc;
+    if (!G.inited) return fail(B2S_ERR_STATE, "b2s_init was not called");
+    const int n_in = p->n_in;
+    const bool identity_schema = p->out_src.empty();
+    if (identity_schema) {
+      p->out_src.resize(n_in);
+      p->out_kind.assign(n_in, B2S_OUT_COPY);
+      p->out_arg.assign(n_in, 0.f);
+      for (int j = 0; j < n_in; ++j) p->out_src[j] = j;
+    }
+    const int n_out = (int)p->out_src.size();
+    const int M = (int)p->models.size();
+    if (p->vote_kind != B2S_VOTE_NONE) {
+      if (M == 0) return fail(B2S_ERR_INVALID, "vote without models");
+      if ((int)p->vote_w.size() != M) return fail(B2S_ERR_INVALID, "vote weights (%d) != models (%d)", (int)p->vote_w.size(), M);
+    }
+    bool any_tree = false, any_class = false, any_reg = false;
+    int total_scores = 0, max_scores = 1;
+    for (auto& m : p->models) {
+      any_tree |= (m.kind == MK_TREES);
+      (m.link == B2S_LINK_IDENTITY ? any_reg : any_class) = true;
+      total_scores += m.n_scores;
+      max_scores = std::max(max_scores, m.n_scores);
+    }
+    if (any_class && any_reg) return fail(B2S_ERR_UNSUPPORTED, "classifiers and regressors cannot share one plan output");
+    if (p->vote_kind == B2S_VOTE_MAJORITY && !any_class && M) {
+      // regression outputs voted as labels: allowed (VotingEnsemble casts to int, routers.py:778-780)
+    }
+    p->mode = M == 0 ? MODE_STORE : (any_tree ? MODE_TREES : MODE_LINEAR);
+    p->out_is_int = (M > 0 && (any_class || p->vote_kind == B2S_VOTE_MAJORITY)) ? 1 : 0;
+    if (p->vote_kind == B2S_VOTE_MEAN) p->out_is_int = 0;
+    p->out_cols = M == 0 ? n_out : (p->vote_kind == B2S_VOTE_NONE ? M : 1);
 
-  bool any_fill = false, any_map = false;
-  for (int c = 0; c < n_in; ++c) {
-    any_fill |= !std::isnan(p->fill[c]);
-    any_map |= !p->maps[c].empty();
-  }
-  const bool need_expand = !identity_schema || any_fill || any_map;
-
-  // ---- tables
-  std::vector<uint32_t> flags(n_in, 0);
-  std::vector<int32_t> map_off(n_in + 1, 0);
-  std::vector<MapEntry> maps;
-  for (int c = 0; c < n_in; ++c) {
-    map_off[c] = (int)maps.size();
-    for (auto& e : p->maps[c]) maps.push_back(e);
-    if (!p->maps[c].empty()) flags[c] |= COL_HAS_MAP;
-  }
-  map_off[n_in] = (int)maps.size();
-  for (int j = 0; j < n_out; ++j)
-    if (p->out_kind[j] == B2S_OUT_COPY) flags[p->out_src[j]] |= COL_COPIED;
-
-  int NS = 1;
-  std::vector<int32_t> cat_off(n_in + 1, 0);
-  std::vector<float> cat_val;
-  std::vector<double> wnum, wcat, bias, wgen, leaf, tree_scale;
-  std::vector<ModelDesc> descs(std::max(M, 1));
-  std::vector<int32_t> classes, tree_root, tree_slot;
-  std::vector<TreeNode> nodes;
-
-  if (p->mode == MODE_LINEAR) {
-    NS = pow2_at_least(total_scores);
-    if (NS > kMaxScores) return fail(B2S_ERR_UNSUPPORTED, "total scores %d > %d", total_scores, kMaxScores);
-    // categories per input column, in schema order
-    std::vector<std::vector<int>> col_cats(n_in);
-    for (int j = 0; j < n_out; ++j)
-      if (p->out_kind[j] == B2S_OUT_ONEHOT) col_cats[p->out_src[j]].push_back(j);
+    bool any_fill = false, any_map = false;
     for (int c = 0; c < n_in; ++c) {
-      cat_off[c] = (int)cat_val.size();
-      for (int j : col_cats[c]) cat_val.push_back(p->out_arg[j]);
-      if (!col_cats[c].empty()) flags[c] |= COL_HAS_CAT;
+      any_fill |= !std::isnan(p->fill[c]);
+      any_map |= !p->maps[c].empty();
     }
-    cat_off[n_in] = (int)cat_val.size();
-    wnum.assign((size_t)n_in * NS, 0.0);
-    wcat.assign(std::max<size_t>(cat_val.size(), 1) * NS, 0.0);
-    bias.assign(NS, 0.0);
-    int so = 0;
-    for (int mi = 0; mi < M; ++mi) {
-      auto& m = p->models[mi];
-      for (int k = 0; k < m.n_scores; ++k) {
-        bias[so + k] = m.b[k];
-        std::vector<int> seen(n_in, 0);
-        for (int j = 0; j < n_out; ++j) {
-          const int c = p->out_src[j];
-          const double w = m.W[(size_t)k * n_out + j];
-          if (p->out_kind[j] == B2S_OUT_COPY) {
-            wnum[(size_t)c * NS + so + k] += w;
-          } else {
-            const int idx = cat_off[c] + seen[c]++;
-            wcat[(size_t)idx * NS + so + k] = w;
-          }
-        }
-      }
-      so += m.n_scores;
-    }
-  } else if (p->mode == MODE_TREES) {
-    NS = max_scores <= 1 ? 1 : (max_scores <= 4 ? 4 : (max_scores <= 8 ? 8 : 16));
-    bias.assign(std::max(total_scores, 1), 0.0);
-  }
-  {
-    int so = 0, co = 0;
-    for (int mi = 0; mi < M; ++mi) {
-      auto& m = p->models[mi];
-      ModelDesc d{};
-      d.kind = m.kind;
-      d.score_off = so;
-      d.n_scores = m.n_scores;
-      d.link = m.link;
-      d.class_off = co;
-      d.n_classes = (int)m.classes.size();
-      for (int32_t c : m.classes) classes.push_back(c);
-      co += (int)m.classes.size();
-      if (p->mode == MODE_TREES) {
-        if (m.kind == MK_TREES) {
-          d.tree_begin = (int)tree_root.size();
-          const int nt = (int)m.tree_slot.size();
-          for (int t = 0; t < nt; ++t) {
-            const int base = (int)nodes.size();
-            tree_root.push_back(base);
-            tree_slot.push_back(m.tree_slot[t]);
-            tree_scale.push_back(m.tree_scale[t]);
-            for (int i = m.tree_offset[t]; i < m.tree_offset[t + 1]; ++i) {
-              TreeNode nd;
-              nd.feature = m.feature[i];
-              nd.threshold = m.threshold[i];
-              nd.left = nd.feature >= 0 ? base + m.left[i] : 0;
-              nd.right = nd.feature >= 0 ? base + m.right[i] : 0;
-              nodes.push_back(nd);
-              leaf.push_back(m.leaf_value[i]);
-            }
-          }
-          d.tree_end = (int)tree_root.size();
-          for (int k = 0; k < m.n_scores; ++k) bias[so + k] = m.init[k];
-        } else {
-          d.w_off = (int)wgen.size();
-          for (double w : m.W) wgen.push_back(w);
-          for (int k = 0; k < m.n_scores; ++k) bias[so + k] = m.b[k];
-        }
-      }
-      descs[mi] = d;
-      so += m.n_scores;
-    }
-  }
-  if (bias.empty()) bias.assign(1, 0.0);
+    const bool need_expand = !identity_schema || any_fill || any_map;
 
-  std::vector<uint8_t> chunk_kind((n_in + 3) / 4, 1);
-  for (int ch = 0; ch < (int)chunk_kind.size(); ++ch) {
-    bool fast = (ch * 4 + 3 < n_in);
-    for (int u = 0; fast && u < 4; ++u) fast = (flags[ch * 4 + u] == COL_COPIED);
-    chunk_kind[ch] = fast ? 0 : 1;
-  }
-  // ---- row-warp kernel tables (linear plans over <= 128 columns without MapValues)
-  std::vector<float> rw_fill;
-  std::vector<uint32_t> rw_copied;
-  std::vector<double> rw_w;
-  std::vector<int32_t> rw_csrc, rw_ccomp, rw_cbase, rw_cn;
-  uint32_t rw_cat_pos_mask = 0;
-  {
-    const int nch = (n_in + 3) / 4;
-    int L, CPL;
-    if (NS <= 4) {
-      L = nch <= 16 ? 8 : 16;
-      CPL = nch <= 8 ? 1 : 2;
-    } else {
-      L = nch <= 8 ? 8 : (nch <= 16 ? 16 : 32);
-      CPL = 1;
+    // ---- tables
+    std::vector<uint32_t> flags(n_in, 0);
+    std::vector<int32_t> map_off(n_in + 1, 0);
+    std::vector<MapEntry> maps;
+    for (int c = 0; c < n_in; ++c) {
+      map_off[c] = (int)maps.size();
+      for (auto& e : p->maps[c]) maps.push_back(e);
+      if (!p->maps[c].empty()) flags[c] |= COL_HAS_MAP;
     }
-    std::vector<int> cat_cols;
-    int max_cats = 0;
-    if (p->mode == MODE_LINEAR)
-      for (int c = 0; c < n_in; ++c)
-        if (cat_off[c + 1] > cat_off[c]) {
-          cat_cols.push_back(c);
-          max_cats = std::max(max_cats, cat_off[c + 1] - cat_off[c]);
-        }
-    const int CS = (int)((cat_cols.size() + L - 1) / L);
-    const bool env_off = getenv("B2S_NO_ROWWARP") != nullptr;
-    if (!env_off && p->mode == MODE_LINEAR && !any_map && (n_in % 4) == 0 && nch <= L * CPL && NS <= 8 && CS <= 2 && max_cats <= 64) {
-      p->rw_ok = true;
-      p->rw_L = L;
-      p->rw_CPL = CPL;
-      p->rw_NS = NS;
-      p->rw_CS = CS;
-      p->rw_U = rw_u(L, CPL, NS);
-      const int npos = L * CPL;
-      rw_fill.assign((size_t)npos * 4, std::numeric_limits<float>::quiet_NaN());
-      rw_copied.assign(npos, 0);
-      rw_w.assign((size_t)npos * 4 * NS, 0.0);
-      auto pos_of = [&](int c) { const int ch = c / 4; return (ch / L) * L + (ch % L); };
-      for (int c = 0; c < n_in; ++c) {
-        const int pos = pos_of(c), u = c % 4;
-        rw_fill[(size_t)pos * 4 + u] = p->fill[c];
-        if (flags[c] & COL_COPIED) rw_copied[pos] |= (1u << u);
-        for (int kk = 0; kk < NS; ++kk) rw_w[((size_t)pos * 4 + u) * NS + kk] = wnum[(size_t)c * NS + kk];
-      }
-      const int slots = std::max(CS, 1);
-      rw_csrc.assign((size_t)slots * L, -1);
-      rw_ccomp.assign((size_t)slots * L, 0);
-      rw_cbase.assign((size_t)slots * L, 0);
-      rw_cn.assign((size_t)slots * L, 0);
-      for (size_t i = 0; i < cat_cols.size(); ++i) {
-        const int c = cat_cols[i];
-        const size_t at = (i / L) * L + (i % L);
-        rw_csrc[at] = pos_of(c);
-        rw_cat_pos_mask |= 1u << ((pos_of(c) / L) * 4 + (c % 4));
-        rw_ccomp[at] = c % 4;
-        rw_cbase[at] = cat_off[c];
-        rw_cn[at] = cat_off[c + 1] - cat_off[c];
-      }
-    }
-  }
-  // ---- upload one blob
-  BlobBuilder bb;
-  const size_t o_fill = bb.add(p->fill), o_flags = bb.add(flags), o_mapoff = bb.add(map_off), o_maps = bb.add(maps),
-               o_osrc = bb.add(p->out_src), o_okind = bb.add(p->out_kind), o_oarg = bb.add(p->out_arg),
-               o_catoff = bb.add(cat_off), o_catval = bb.add(cat_val), o_wnum = bb.add(wnum), o_wcat = bb.add(wcat),
-               o_bias = bb.add(bias), o_models = bb.add(descs), o_classes = bb.add(classes),
-               o_votew = bb.add(p->vote_w), o_wgen = bb.add(wgen), o_nodes = bb.add(nodes), o_leaf = bb.add(leaf),
-               o_troot = bb.add(tree_root), o_tslot = bb.add(tree_slot), o_tscale = bb.add(tree_scale),
-               o_chunk = bb.add(chunk_kind), o_rwfill = bb.add(rw_fill), o_rwcop = bb.add(rw_copied),
-               o_rww = bb.add(rw_w), o_rwcs = bb.add(rw_csrc), o_rwcc = bb.add(rw_ccomp), o_rwcb = bb.add(rw_cbase),
-               o_rwcn = bb.add(rw_cn);
-  CUDA_TRY(cudaSetDevice(G.device));
-  CUDA_TRY(cudaMalloc(&p->d_blob, bb.data.size()));
-  CUDA_TRY(cudaMemcpy(p->d_blob, bb.data.data(), bb.data.size(), cudaMemcpyHostToDevice));
-  p->blob_bytes = bb.data.size();
-  char* B = p->d_blob;
+    map_off[n_in] = (int)maps.size();
+    for (int j = 0; j < n_out; ++j)
+      if (p->out_kind[j] == B2S_OUT_COPY) flags[p->out_src[j]] |= COL_COPIED;
 
-  KParams& k = p->kp;
-  memset(&k, 0, sizeof(k));
-  k.n_in = n_in;
-  k.n_out = n_out;
-  k.out_cols = p->out_cols;
-  k.n_models = M;
-  k.n_scores = total_scores;
-  k.vote_kind = p->vote_kind;
-  k.out_is_int = p->out_is_int;
-  k.need_expand = need_expand ? 1 : 0;
-  k.models_pow2 = pow2_at_least(std::max(M, 1));
-  k.n_cat = (int)cat_val.size();
-  k.n_maps = (int)maps.size();
-  k.fill = (const float*)(B + o_fill);
-  k.col_flags = (const uint32_t*)(B + o_flags);
-  k.map_off = (const int32_t*)(B + o_mapoff);
-  k.maps = (const MapEntry*)(B + o_maps);
-  k.out_src = (const int32_t*)(B + o_osrc);
-  k.out_kind = (const int32_t*)(B + o_okind);
-  k.out_arg = (const float*)(B + o_oarg);
-  k.cat_off = (const int32_t*)(B + o_catoff);
-  k.cat_val = (const float*)(B + o_catval);
-  k.wnum = (const double*)(B + o_wnum);
-  k.wcat = (const double*)(B + o_wcat);
-  k.bias = (const double*)(B + o_bias);
-  k.models = (const ModelDesc*)(B + o_models);
-  k.classes = (const int32_t*)(B + o_classes);
-  k.vote_w = (const double*)(B + o_votew);
-  k.wgen = (const double*)(B + o_wgen);
-  k.nodes = (const TreeNode*)(B + o_nodes);
-  k.leaf = (const double*)(B + o_leaf);
-  k.tree_root = (const int32_t*)(B + o_troot);
-  k.tree_slot = (const int32_t*)(B + o_tslot);
-  k.tree_scale = (const double*)(B + o_tscale);
-  k.chunk_kind = (const uint8_t*)(B + o_chunk);
+    int NS = 1;
+    std::vector<int32_t> cat_off(n_in + 1, 0);
+    std::vector<float> cat_val;
+    std::vector<double> wnum, wcat, bias, wgen, leaf, tree_scale;
+    std::vector<ModelDesc> descs(std::max(M, 1));
+    std::vector<int32_t> classes, tree_root, tree_slot;
+    std::vector<TreeNode> nodes;
 
-  // ---- launch geometry + shared-memory carve-up
-  // pitch (words): rows 16B aligned and (pitch/4) odd -> conflict-free LDS.128 for one-thread-per-row
-  const int n_in4 = (int)align_up(n_in, 4);
-  int pitch = n_in4 + 4;
-  if (((pitch / 4) & 1) == 0) pitch += 4;
-  int exp_pitch = n_out | 1;
-  const int smem_cap = (int)G.prop.sharedMemPerBlockOptin;
-  const int sms = G.prop.multiProcessorCount;
-  int block, tile_rows, stages, blocks_per_sm;
-  int tpr = 1;
-  if (p->mode == MODE_LINEAR) {
-    tpr = NS <= 8 ? 4 : (NS == 16 ? 2 : 1);
-    const int nch = (n_in + 3) / 4;
-    while (tpr > 1 && nch < tpr * 2) tpr /= 2;
-    tile_rows = 128;
-    block = tile_rows * tpr;
-    stages = 3;
-    blocks_per_sm = 2;
-  } else if (p->mode == MODE_TREES) {
-    block = 256;
-    tile_rows = block / k.models_pow2;
-    stages = 2;
-    blocks_per_sm = 2;
-  } else {
-    block = 256;
-    tile_rows = 128;
-    stages = 2;
-    blocks_per_sm = 2;
-  }
-  auto carve = [&](int tr, int st) {
-    size_t off = 0;
-    auto take = [&](size_t bytes) {
-      size_t o = align_up(off, 16);
-      off = o + bytes;
-      return (int32_t)o;
-    };
-    k.sm_fill = take((size_t)n_in * 4);
-    k.sm_flags = take((size_t)n_in * 4);
-    k.sm_mapoff = take((size_t)(n_in + 1) * 4);
-    k.sm_catoff = take((size_t)(n_in + 1) * 4);
-    k.sm_catval = take(std::max<size_t>(cat_val.size(), 1) * 4);
-    k.sm_wnum = take(p->mode == MODE_LINEAR ? (size_t)n_in * NS * 8 : 16);
-    k.sm_wcat = take(p->mode == MODE_LINEAR ? std::max<size_t>(cat_val.size(), 1) * NS * 8 : 16);
-    k.sm_outsrc = take((size_t)n_out * 4);
-    k.sm_outkind = take((size_t)n_out * 4);
-    k.sm_outarg = take((size_t)n_out * 4);
-    k.sm_pred = take(p->mode == MODE_TREES ? (size_t)tr * k.models_pow2 * 8 : 16);
-    k.sm_chunk = take((size_t)(n_in + 3) / 4 + 16);
-    k.sm_part = take((p->mode == MODE_LINEAR && tpr > 1) ? (size_t)tr * tpr * NS * 8 : 16);
-    k.sm_pst = take((p->mode == MODE_LINEAR && tpr > 1) ? (size_t)tr * tpr * 4 : 16);
-    k.sm_exp = take((p->mode != MODE_LINEAR && need_expand) ? (size_t)tr * exp_pitch * 4 : 16);
-    k.sm_tiles = take((size_t)st * tr * pitch * 4);
-    return (int)align_up(off, 16);
-  };
-  int total = carve(tile_rows, stages);
-  // shrink until `blocks_per_sm` blocks fit (then until one fits)
-  while (total * blocks_per_sm > smem_cap * 1 && (stages > 2 || blocks_per_sm > 1)) {
-    if (stages > 2) --stages; else --blocks_per_sm;
-    total = carve(tile_rows, stages);
-  }
-  while (total > smem_cap && stages > 1) total = carve(tile_rows, --stages);
-  while (total > smem_cap && tile_rows > 8 && p->mode != MODE_LINEAR) {
-    tile_rows /= 2;
-    total = carve(tile_rows, stages);
-  }
-  if (total > smem_cap) {
     if (p->mode == MODE_LINEAR) {
-      // wide rows: fewer rows per tile (threads beyond tile_rows idle in the compute phase)
-      while (total > smem_cap && tile_rows > 8) {
-        tile_rows /= 2;
-        total = carve(tile_rows, stages);
+      NS = pow2_at_least(total_scores);
+      if (NS > kMaxScores) return fail(B2S_ERR_UNSUPPORTED, "total scores %d > %d", total_scores, kMaxScores);
+      // categories per input column, in schema order
+      std::vector<std::vector<int>> col_cats(n_in);
+      for (int j = 0; j < n_out; ++j)
+        if (p->out_kind[j] == B2S_OUT_ONEHOT) col_cats[p->out_src[j]].push_back(j);
+      for (int c = 0; c < n_in; ++c) {
+        cat_off[c] = (int)cat_val.size();
+        for (int j : col_cats[c]) cat_val.push_back(p->out_arg[j]);
+        if (!col_cats[c].empty()) flags[c] |= COL_HAS_CAT;
       }
-    }
-    if (total > smem_cap) return fail(B2S_ERR_UNSUPPORTED, "plan needs %d B shared memory > %d B", total, smem_cap);
-  }
-  if (p->mode == MODE_TREES) block = std::max(32, tile_rows * k.models_pow2);
-  if (p->mode == MODE_LINEAR) block = tile_rows * tpr;
-  k.tpr = tpr;
-  k.sm_total = total;
-  k.tile_rows = tile_rows;
-  k.pitch = pitch;
-  k.exp_pitch = exp_pitch;
-  k.stages = stages;
-  p->NS = NS;
-  p->block = block;
-  int occ = std::max(1, std::min(blocks_per_sm, smem_cap / std::max(total, 1)));
-  p->grid = sms * occ;
-
-  if (p->rw_ok) {
-    RWParams& r = p->rw;
-    memset(&r, 0, sizeof(r));
-    r.n_in = n_in;
-    r.nch = (n_in + 3) / 4;
-    r.out_cols = p->out_cols;
-    r.n_models = M;
-    r.vote_kind = p->vote_kind;
-    r.out_is_int = p->out_is_int;
-    r.n_cat_slots = p->rw_CS;
-    r.n_cat = (int)cat_val.size();
-    bool simple = true;
-    for (auto& m : p->models) simple = simple && m.link == B2S_LINK_IDENTITY && m.n_scores == 1;
-    r.fast_epilogue = (simple && p->vote_kind != B2S_VOTE_MAJORITY) ? 1 : 0;
-    r.fill = (const float*)(B + o_rwfill);
-    r.copied = (const uint32_t*)(B + o_rwcop);
-    r.w = (const double*)(B + o_rww);
-    r.cat_src = (const int32_t*)(B + o_rwcs);
-    r.cat_comp = (const int32_t*)(B + o_rwcc);
-    r.cat_base = (const int32_t*)(B + o_rwcb);
-    r.cat_n = (const int32_t*)(B + o_rwcn);
-    r.cat_val = k.cat_val;
-    r.wcat = k.wcat;
-    r.bias = k.bias;
-    r.vote_w = k.vote_w;
-    r.models = k.models;
-    r.classes = k.classes;
-    p->rw_smem = (int)(align_up((size_t)r.n_cat * 4, 16) + (size_t)(r.n_cat + 1) * NS * 8 + 16);
-    r.cat_pos_mask = rw_cat_pos_mask;
-    int occ = 0;
-    cudaError_t e = launch_rw(p->rw_L, p->rw_CPL, p->rw_NS, p->rw_CS, r, 0, p->rw_smem, nullptr, true, &occ);
-    if (e != cudaSuccess || occ < 1) {
-      cudaGetLastError();
-      p->rw_ok = false;
-    } else {
-      p->rw_grid = sms * occ;
-    }
-  }
-  {
-    const char* pick = getenv("B2S_LINEAR_KERNEL");  // rowthread (default) | rowwarp | generic  (A/B runs)
-    const std::string want = pick ? pick : "rowthread";
-    int n_cat_cols = 0;
-    for (int c = 0; c < n_in; ++c) n_cat_cols += (cat_off[c + 1] > cat_off[c]) ? 1 : 0;
-    if (want != "rowwarp") p->rw_ok = p->rw_ok && (want == "rowwarp");
-    if (want == "rowthread" && p->mode == MODE_LINEAR && !any_map && n_in <= 128 && NS <= 8 &&
-        n_cat_cols <= kRTMaxCatCols && (int)cat_val.size() <= kRTMaxCats) {
-      const int nch = (n_in + 3) / 4;
-      p->rt_NCH = nch <= 4 ? 4 : (nch <= 8 ? 8 : (nch <= 16 ? 16 : 32));
-      p->rt_NS = NS;
-      p->rt_cat_cols = n_cat_cols;
-      bool simple = true;
-      for (auto& m : p->models) simple = simple && m.link == B2S_LINK_IDENTITY && m.n_scores == 1;
-      RTTables t{n_in, p->out_cols, M, p->vote_kind, p->out_is_int, (simple && p->vote_kind != B2S_VOTE_MAJORITY) ? 1 : 0, NS,
-                 &p->fill, &flags, &wnum, &bias, &p->vote_w, &cat_off, &cat_val, k.wcat, k.vote_w, k.models, k.classes};
-      rt_build_any(p, t);
-      int rpitch = p->rt_NCH * 4 + 4;
-      if (((rpitch / 4) & 1) == 0) rpitch += 4;
-      p->rt_pitch = rpitch;
-      const char* stg = getenv("B2S_RT_STAGES");
-      p->rt_stages = stg ? std::max(2, std::min(4, atoi(stg))) : 2;
-      const char* tile_env = getenv("B2S_RT_TILE");  // rows per tile: 64 | 128
-      p->rt_tile_rows = tile_env && atoi(tile_env) == 64 ? 64 : 128;
-      const char* rpt_env = getenv("B2S_RT_RPT");  // rows per thread: 1 | 2 (2: tensor-map loads only)
-      p->rt_RPT = rpt_env && atoi(rpt_env) == 2 && p->rt_NCH >= 8 ? 2 : 1;
-      const char* tprs = getenv("B2S_RT_TPR");
-      p->rt_TPR = tprs ? atoi(tprs) : rt_tpr(p->rt_NCH);
-      if (p->rt_TPR != 1 && p->rt_TPR != 2 && p->rt_TPR != 4) p->rt_TPR = 1;
-      while (p->rt_TPR > 1 && (p->rt_NCH < 4 * p->rt_TPR)) p->rt_TPR /= 2;
-      {
-        const size_t fixed = 1024 + 64 + align_up((size_t)(cat_val.size() + 1) * NS * 8, 16);
-        const size_t part = (size_t)(p->rt_TPR - 1) * 128 * NS * 8;
-        // padded tiles + one partial-sum buffer (LDGSTS / per-row bulk), or swizzled tiles + two (tensor map)
-        const size_t padded = fixed + part + (size_t)p->rt_stages * p->rt_tile_rows * rpitch * 4;
-        const size_t swizzled = fixed + 2 * part + (size_t)p->rt_stages * p->rt_tile_rows * p->rt_NCH * 16;
-        p->rt_smem = (int)std::max(padded, swizzled);
-      }
-      int occ = 0;
-      if (p->rt_smem <= smem_cap && rt_launch(p, nullptr, 0, 0, nullptr, nullptr, 0, nullptr, true, &occ) == cudaSuccess && occ >= 1) {
-        p->rt_ok = true;
-        p->rt_grid = sms * occ;
-      } else {
-        cudaGetLastError();
-      }
-    }
-  }
-  if (p->mode == MODE_TREES && !need_expand && getenv("B2S_NO_TREES2") == nullptr) {
-    // re-pack every model as complete heap-ordered trees; one model must fit one CTA's shared memory
-    bool ok = true;
-    std::vector<int> depth(M, 0);
-    size_t max_table = 0;
-    for (int mi = 0; mi < M && ok; ++mi) {
-      auto& m = p->models[mi];
-      if (m.kind != MK_TREES) { ok = false; break; }
-      const int nt = (int)m.tree_slot.size();
-      for (int t = 0; t < nt; ++t) {
-        const int base = m.tree_offset[t];
-        std::vector<std::pair<int, int>> stack{{0, 0}};
-        while (!stack.empty()) {
-          auto [node, d] = stack.back();
-          stack.pop_back();
-          depth[mi] = std::max(depth[mi], d);
-          if (m.feature[base + node] >= 0) {
-            stack.push_back({m.left[base + node], d + 1});
-            stack.push_back({m.right[base + node], d + 1});
-          }
-        }
-      }
-      if (depth[mi] > 8) ok = false;
-      const size_t ni = ((size_t)1 << depth[mi]) - 1, nl = (size_t)1 << depth[mi];
-      max_table = std::max(max_table, align_up((size_t)nt * ni * 8, 16) + (size_t)nt * nl * 8 + (size_t)nt * 4);
-    }
-    const int TR2 = kT2TileRows, G2 = kT2Groups, ST2 = 1;  // one row-major landing tile + one transposed tile
-    const int NS2 = p->NS <= 1 ? 1 : (p->NS <= 4 ? 4 : 0);
-    const size_t part_bytes = (size_t)(G2 - 1) * TR2 * std::max(NS2, 1) * 8;
-    const size_t tiles_bytes = (size_t)ST2 * TR2 * pitch * 4 + (size_t)((n_in + 3) / 4 * 4) * TR2 * 4 + (size_t)TR2 * 4 + 16 + 1024;  // + mbarrier + alignment slack
-    const size_t total2 = align_up(max_table, 16) + align_up(part_bytes, 16) + tiles_bytes;
-    if (ok && NS2 > 0 && total2 <= (size_t)smem_cap && M <= sms) {
-      BlobBuilder tb;
-      std::vector<T2Model> t2m(M);
-      std::vector<size_t> o_nodes(M), o_leaves(M), o_slot(M), o_scale(M);
+      cat_off[n_in] = (int)cat_val.size();
+      wnum.assign((size_t)n_in * NS, 0.0);
+      wcat.assign(std::max<size_t>(cat_val.size(), 1) * NS, 0.0);
+      bias.assign(NS, 0.0);
+      int so = 0;
       for (int mi = 0; mi < M; ++mi) {
         auto& m = p->models[mi];
-        const int nt = (int)m.tree_slot.size();
-        const int D = depth[mi];
-        const int ni = (1 << D) - 1, nl = 1 << D;
-        std::vector<HeapNode> hn((size_t)nt * std::max(ni, 1), HeapNode{0, std::numeric_limits<float>::infinity()});
-        std::vector<double> hl((size_t)nt * nl, 0.0);
-        for (int t = 0; t < nt; ++t) {
-          const int base = m.tree_offset[t];
-          struct It { int heap, d, src; };
-          std::vector<It> stack{{0, 0, 0}};
-          while (!stack.empty()) {
-            It it = stack.back();
-            stack.pop_back();
-            const bool leaf = m.feature[base + it.src] < 0;
-            if (it.d == D) {
-              hl[(size_t)t * nl + (it.heap - ni)] = m.leaf_value[base + it.src];
-              continue;
-            }
-            if (leaf) {  // pad: a threshold of +inf sends every finite value left; both sides carry the leaf
-              hn[(size_t)t * ni + it.heap] = HeapNode{0, std::numeric_limits<float>::infinity()};
-              stack.push_back({2 * it.heap + 1, it.d + 1, it.src});
-              stack.push_back({2 * it.heap + 2, it.d + 1, it.src});
+        for (int k = 0; k < m.n_scores; ++k) {
+          bias[so + k] = m.b[k];
+          std::vector<int> seen(n_in, 0);
+          for (int j = 0; j < n_out; ++j) {
+            const int c = p->out_src[j];
+            const double w = m.W[(size_t)k * n_out + j];
+            if (p->out_kind[j] == B2S_OUT_COPY) {
+              wnum[(size_t)c * NS + so + k] += w;
             } else {
-              hn[(size_t)t * ni + it.heap] = HeapNode{m.feature[base + it.src], m.threshold[base + it.src]};
-              stack.push_back({2 * it.heap + 1, it.d + 1, m.left[base + it.src]});
-              stack.push_back({2 * it.heap + 2, it.d + 1, m.right[base + it.src]});
+              const int idx = cat_off[c] + seen[c]++;
+              wcat[(size_t)idx * NS + so + k] = w;
             }
           }
         }
-        o_nodes[mi] = tb.add(hn);
-        o_leaves[mi] = tb.add(hl);
-        o_slot[mi] = tb.add(m.tree_slot);
-        o_scale[mi] = tb.add(m.tree_scale);
-        t2m[mi].n_trees = nt;
-        t2m[mi].depth = D;
-        t2m[mi].n_internal = ni;
-        t2m[mi].n_leaves = nl;
+        so += m.n_scores;
       }
-      const size_t o_models2 = align_up(tb.data.size(), 16);
-      tb.data.resize(o_models2 + sizeof(T2Model) * M);
-      CUDA_TRY(cudaMalloc(&p->d_t2_blob, tb.data.size()));
-      for (int mi = 0; mi < M; ++mi) {
-        t2m[mi].nodes = (const HeapNode*)(p->d_t2_blob + o_nodes[mi]);
-        t2m[mi].leaves = (const double*)(p->d_t2_blob + o_leaves[mi]);
-        t2m[mi].slot = (const int32_t*)(p->d_t2_blob + o_slot[mi]);
-        t2m[mi].scale = (const double*)(p->d_t2_blob + o_scale[mi]);
-      }
-      memcpy(tb.data.data() + o_models2, t2m.data(), sizeof(T2Model) * M);
-      CUDA_TRY(cudaMemcpy(p->d_t2_blob, tb.data.data(), tb.data.size(), cudaMemcpyHostToDevice));
-      T2Params& t = p->t2;
-      memset(&t, 0, sizeof(t));
-      t.n_in = n_in;
-      t.n_models = M;
-      t.tile_rows = TR2;
-      t.pitch = pitch;
-      t.stages = ST2;
-      t.groups = G2;
-      t.t2 = (const T2Model*)(p->d_t2_blob + o_models2);
-      t.models = k.models;
-      t.classes = k.classes;
-      t.bias = k.bias;
-      t.sm_tables = 0;
-      t.sm_part = (int)align_up(max_table, 16);
-      t.sm_tiles = (int)(align_up(max_table, 16) + align_up(part_bytes, 16));
-      p->t2_smem = (int)total2;
-      p->t2_NS = NS2;
-      p->t2_block = TR2 * G2;
-      p->t2_grid = std::max(M, (sms / M) * M);
-      p->t2_ok = true;
-      p->kernels_per_batch = 2;
+    } else if (p->mode == MODE_TREES) {
+      NS = max_scores <= 1 ? 1 : (max_scores <= 4 ? 4 : (max_scores <= 8 ? 8 : 16));
+      bias.assign(std::max(total_scores, 1), 0.0);
     }
+    {
+      int so = 0, co = 0;
+      for (int mi = 0; mi < M; ++mi) {
+        auto& m = p->models[mi];
+        ModelDesc d{};
+        d.kind = m.kind;
+        d.score_off = so;
+        d.n_scores = m.n_scores;
+        d.link = m.link;
+        d.class_off = co;
+        d.n_classes = (int)m.classes.size();
+        for (int32_t c : m.classes) classes.push_back(c);
+        co += (int)m.classes.size();
+        if (p->mode == MODE_TREES) {
+          if (m.kind == MK_TREES) {
+            d.tree_begin = (int)tree_root.size();
+            const int nt = (int)m.tree_slot.size();
+            for (int t = 0; t < nt; ++t) {
+              const int base = (int)nodes.size();
+              tree_root.push_back(base);
+              tree_slot.push_back(m.tree_slot[t]);
+              tree_scale.push_back(m.tree_scale[t]);
+              for (int i = m.tree_offset[t]; i < m.tree_offset[t + 1]; ++i) {
+                TreeNode nd;
+                nd.feature = m.feature[i];
+                nd.threshold = m.threshold[i];
+                nd.left = nd.feature >= 0 ? base + m.left[i] : 0;
+                nd.right = nd.feature >= 0 ? base + m.right[i] : 0;
+                nodes.push_back(nd);
+                leaf.push_back(m.leaf_value[i]);
+              }
+            }
+            d.tree_end = (int)tree_root.size();
+            for (int k = 0; k < m.n_scores; ++k) bias[so + k] = m.init[k];
+          } else {
+            d.w_off = (int)wgen.size();
+            for (double w : m.W) wgen.push_back(w);
+            for (int k = 0; k < m.n_scores; ++k) bias[so + k] = m.b[k];
+          }
+        }
+        descs[mi] = d;
+        so += m.n_scores;
+      }
+    }
+    if (bias.empty()) bias.assign(1, 0.0);
+
+    std::vector<uint8_t> chunk_kind((n_in + 3) / 4, 1);
+    for (int ch = 0; ch < (int)chunk_kind.size(); ++ch) {
+      bool fast = (ch * 4 + 3 < n_in);
+      for (int u = 0; fast && u < 4; ++u) fast = (flags[ch * 4 + u] == COL_COPIED);
+      chunk_kind[ch] = fast ? 0 : 1;
+    }
+    // ---- row-warp kernel tables (linear plans over <= 128 columns without MapValues)
+    std::vector<float> rw_fill;
+    std::vector<uint32_t> rw_copied;
+    std::vector<double> rw_w;
+    std::vector<int32_t> rw_csrc, rw_ccomp, rw_cbase, rw_cn;
+    uint32_t rw_cat_pos_mask = 0;
+    {
+      const int nch = (n_in + 3) / 4;
+      int L, CPL;
+      if (NS <= 4) {
+        L = nch <= 16 ? 8 : 16;
+        CPL = nch <= 8 ? 1 : 2;
+      } else {
+        L = nch <= 8 ? 8 : (nch <= 16 ? 16 : 32);
+        CPL = 1;
+      }
+      std::vector<int> cat_cols;
+      int max_cats = 0;
+      if (p->mode == MODE_LINEAR)
+        for (int c = 0; c < n_in; ++c)
+          if (cat_off[c + 1] > cat_off[c]) {
+            cat_cols.push_back(c);
+            max_cats = std::max(max_cats, cat_off[c + 1] - cat_off[c]);
+          }
+      const int CS = (int)((cat_cols.size() + L - 1) / L);
+      const bool env_off = getenv("B2S_NO_ROWWARP") != nullptr;
+      if (!env_off && p->mode == MODE_LINEAR && !any_map && (n_in % 4) == 0 && nch <= L * CPL && NS <= 8 && CS <= 2 && max_cats <= 64) {
+        p->rw_ok = true;
+        p->rw_L = L;
+        p->rw_CPL = CPL;
+        p->rw_NS = NS;
+        p->rw_CS = CS;
+        p->rw_U = rw_u(L, CPL, NS);
+        const int npos = L * CPL;
+        rw_fill.assign((size_t)npos * 4, std::numeric_limits<float>::quiet_NaN());
+        rw_copied.assign(npos, 0);
+        rw_w.assign((size_t)npos * 4 * NS, 0.0);
+        auto pos_of = [&](int c) { const int ch = c / 4; return (ch / L) * L + (ch % L); };
+        for (int c = 0; c < n_in; ++c) {
+          const int pos = pos_of(c), u = c % 4;
+          rw_fill[(size_t)pos * 4 + u] = p->fill[c];
+          if (flags[c] & COL_COPIED) rw_copied[pos] |= (1u << u);
+          for (int kk = 0; kk < NS; ++kk) rw_w[((size_t)pos * 4 + u) * NS + kk] = wnum[(size_t)c * NS + kk];
+        }
+        const int slots = std::max(CS, 1);
+        rw_csrc.assign((size_t)slots * L, -1);
+        rw_ccomp.assign((size_t)slots * L, 0);
+        rw_cbase.assign((size_t)slots * L, 0);
+        rw_cn.assign((size_t)slots * L, 0);
+        for (size_t i = 0; i < cat_cols.size(); ++i) {
+          const int c = cat_cols[i];
+          const size_t at = (i / L) * L + (i % L);
+          rw_csrc[at] = pos_of(c);
+          rw_cat_pos_mask |= 1u << ((pos_of(c) / L) * 4 + (c % 4));
+          rw_ccomp[at] = c % 4;
+          rw_cbase[at] = cat_off[c];
+          rw_cn[at] = cat_off[c + 1] - cat_off[c];
+        }
+      }
+    }
+    // ---- upload one blob
+    BlobBuilder bb;
+    const size_t o_fill = bb.add(p->fill), o_flags = bb.add(flags), o_mapoff = bb.add(map_off), o_maps = bb.add(maps),
+                 o_osrc = bb.add(p->out_src), o_okind = bb.add(p->out_kind), o_oarg = bb.add(p->out_arg),
+                 o_catoff = bb.add(cat_off), o_catval = bb.add(cat_val), o_wnum = bb.add(wnum), o_wcat = bb.add(wcat),
+                 o_bias = bb.add(bias), o_models = bb.add(descs), o_classes = bb.add(classes),
+                 o_votew = bb.add(p->vote_w), o_wgen = bb.add(wgen), o_nodes = bb.add(nodes), o_leaf = bb.add(leaf),
+                 o_troot = bb.add(tree_root), o_tslot = bb.add(tree_slot), o_tscale = bb.add(tree_scale),
+                 o_chunk = bb.add(chunk_kind), o_rwfill = bb.add(rw_fill), o_rwcop = bb.add(rw_copied),
+                 o_rww = bb.add(rw_w), o_rwcs = bb.add(rw_csrc), o_rwcc = bb.add(rw_ccomp), o_rwcb = bb.add(rw_cbase),
+                 o_rwcn = bb.add(rw_cn);
+    CUDA_TRY(cudaSetDevice(G.device));
+    CUDA_TRY(cudaMalloc(&p->d_blob, bb.data.size()));
+    CUDA_TRY(cudaMemcpy(p->d_blob, bb.data.data(), bb.data.size(), cudaMemcpyHostToDevice));
+    p->blob_bytes = bb.data.size();
+    char* B = p->d_blob;
+
+    KParams& k = p->kp;
+    memset(&k, 0, sizeof(k));
+    k.n_in = n_in;
+    k.n_out = n_out;
+    k.out_cols = p->out_cols;
+    k.n_models = M;
+    k.n_scores = total_scores;
+    k.vote_kind = p->vote_kind;
+    k.out_is_int = p->out_is_int;
+    k.need_expand = need_expand ? 1 : 0;
+    k.models_pow2 = pow2_at_least(std::max(M, 1));
+    k.n_cat = (int)cat_val.size();
+    k.n_maps = (int)maps.size();
+    k.fill = (const float*)(B + o_fill);
+    k.col_flags = (const uint32_t*)(B + o_flags);
+    k.map_off = (const int32_t*)(B + o_mapoff);
+    k.maps = (const MapEntry*)(B + o_maps);
+    k.out_src = (const int32_t*)(B + o_osrc);
+    k.out_kind = (const int32_t*)(B + o_okind);
+    k.out_arg = (const float*)(B + o_oarg);
+    k.cat_off = (const int32_t*)(B + o_catoff);
+    k.cat_val = (const float*)(B + o_catval);
+    k.wnum = (const double*)(B + o_wnum);
+    k.wcat = (const double*)(B + o_wcat);
+    k.bias = (const double*)(B + o_bias);
+    k.models = (const ModelDesc*)(B + o_models);
+    k.classes = (const int32_t*)(B + o_classes);
+    k.vote_w = (const double*)(B + o_votew);
+    k.wgen = (const double*)(B + o_wgen);
+    k.nodes = (const TreeNode*)(B + o_nodes);
+    k.leaf = (const double*)(B + o_leaf);
+    k.tree_root = (const int32_t*)(B + o_troot);
+    k.tree_slot = (const int32_t*)(B + o_tslot);
+    k.tree_scale = (const double*)(B + o_tscale);
+    k.chunk_kind = (const uint8_t*)(B + o_chunk);
+
+    // ---- launch geometry + shared-memory carve-up
+    // pitch (words): rows 16B aligned and (pitch/4) odd -> conflict-free LDS.128 for one-thread-per-row
+    const int n_in4 = (int)align_up(n_in, 4);
+    int pitch = n_in4 + 4;
+    if (((pitch / 4) & 1) == 0) pitch += 4;
+    int exp_pitch = n_out | 1;
+    const int smem_cap = (int)G.prop.sharedMemPerBlockOptin;
+    const int sms = G.prop.multiProcessorCount;
+    int block, tile_rows, stages, blocks_per_sm;
+    int tpr = 1;
+    if (p->mode == MODE_LINEAR) {
+      tpr = NS <= 8 ? 4 : (NS == 16 ? 2 : 1);
+      const int nch = (n_in + 3) / 4;
+      while (tpr > 1 && nch < tpr * 2) tpr /= 2;
+      tile_rows = 128;
+      block = tile_rows * tpr;
+      stages = 3;
+      blocks_per_sm = 2;
+    } else if (p->mode == MODE_TREES) {
+      block = 256;
+      tile_rows = block / k.models_pow2;
+      stages = 2;
+      blocks_per_sm = 2;
+    } else {
+      block = 256;
+      tile_rows = 128;
+      stages = 2;
+      blocks_per_sm = 2;
+    }
+    auto carve = [&](int tr, int st) {
+      size_t off = 0;
+      auto take = [&](size_t bytes) {
+        size_t o = align_up(off, 16);
+        off = o + bytes;
+        return (int32_t)o;
+      };
+      k.sm_fill = take((size_t)n_in * 4);
+      k.sm_flags = take((size_t)n_in * 4);
+      k.sm_mapoff = take((size_t)(n_in + 1) * 4);
+      k.sm_catoff = take((size_t)(n_in + 1) * 4);
+      k.sm_catval = take(std::max<size_t>(cat_val.size(), 1) * 4);
+      k.sm_wnum = take(p->mode == MODE_LINEAR ? (size_t)n_in * NS * 8 : 16);
+      k.sm_wcat = take(p->mode == MODE_LINEAR ? std::max<size_t>(cat_val.size(), 1) * NS * 8 : 16);
+      k.sm_outsrc = take((size_t)n_out * 4);
+      k.sm_outkind = take((size_t)n_out * 4);
+      k.sm_outarg = take((size_t)n_out * 4);
+      k.sm_pred = take(p->mode == MODE_TREES ? (size_t)tr * k.models_pow2 * 8 : 16);
+      k.sm_chunk = take((size_t)(n_in + 3) / 4 + 16);
+      k.sm_part = take((p->mode == MODE_LINEAR && tpr > 1) ? (size_t)tr * tpr * NS * 8 : 16);
+      k.sm_pst = take((p->mode == MODE_LINEAR && tpr > 1) ? (size_t)tr * tpr * 4 : 16);
+      k.sm_exp = take((p->mode != MODE_LINEAR && need_expand) ? (size_t)tr * exp_pitch * 4 : 16);
+      k.sm_tiles = take((size_t)st * tr * pitch * 4);
+      return (int)align_up(off, 16);
+    };
+    int total = carve(tile_rows, stages);
+    // shrink until `blocks_per_sm` blocks fit (then until one fits)
+    while (total * blocks_per_sm > smem_cap * 1 && (stages > 2 || blocks_per_sm > 1)) {
+      if (stages > 2) --stages; else --blocks_per_sm;
+      total = carve(tile_rows, stages);
+    }
+    while (total > smem_cap && stages > 1) total = carve(tile_rows, --stages);
+    while (total > smem_cap && tile_rows > 8 && p->mode != MODE_LINEAR) {
+      tile_rows /= 2;
+      total = carve(tile_rows, stages);
+    }
+    if (total > smem_cap) {
+      if (p->mode == MODE_LINEAR) {
+        // wide rows: fewer rows per tile (threads beyond tile_rows idle in the compute phase)
+        while (total > smem_cap && tile_rows > 8) {
+          tile_rows /= 2;
+          total = carve(tile_rows, stages);
+        }
+      }
+      if (total > smem_cap) return fail(B2S_ERR_UNSUPPORTED, "plan needs %d B shared memory > %d B", total, smem_cap);
+    }
+    if (p->mode == MODE_TREES) block = std::max(32, tile_rows * k.models_pow2);
+    if (p->mode == MODE_LINEAR) block = tile_rows * tpr;
+    k.tpr = tpr;
+    k.sm_total = total;
+    k.tile_rows = tile_rows;
+    k.pitch = pitch;
+    k.exp_pitch = exp_pitch;
+    k.stages = stages;
+    p->NS = NS;
+    p->block = block;
+    int occ = std::max(1, std::min(blocks_per_sm, smem_cap / std::max(total, 1)));
+    p->grid = sms * occ;
+
+    if (p->rw_ok) {
+      RWParams& r = p->rw;
+      memset(&r, 0, sizeof(r));
+      r.n_in = n_in;
+      r.nch = (n_in + 3) / 4;
+      r.out_cols = p->out_cols;
+      r.n_models = M;
+      r.vote_kind = p->vote_kind;
+      r.out_is_int = p->out_is_int;
+      r.n_cat_slots = p->rw_CS;
+      r.n_cat = (int)cat_val.size();
+      bool simple = true;
+      for (auto& m : p->models) simple = simple && m.link == B2S_LINK_IDENTITY && m.n_scores == 1;
+      r.fast_epilogue = (simple && p->vote_kind != B2S_VOTE_MAJORITY) ? 1 : 0;
+      r.fill = (const float*)(B + o_rwfill);
+      r.copied = (const uint32_t*)(B + o_rwcop);
+      r.w = (const double*)(B + o_rww);
+      r.cat_src = (const int32_t*)(B + o_rwcs);
+      r.cat_comp = (const int32_t*)(B + o_rwcc);
+      r.cat_base = (const int32_t*)(B + o_rwcb);
+      r.cat_n = (const int32_t*)(B + o_rwcn);
+      r.cat_val = k.cat_val;
+      r.wcat = k.wcat;
+      r.bias = k.bias;
+      r.vote_w = k.vote_w;
+      r.models = k.models;
+      r.classes = k.classes;
+      p->rw_smem = (int)(align_up((size_t)r.n_cat * 4, 16) + (size_t)(r.n_cat + 1) * NS * 8 + 16);
+      r.cat_pos_mask = rw_cat_pos_mask;
+      int occ = 0;
+      cudaError_t e = launch_rw(p->rw_L, p->rw_CPL, p->rw_NS, p->rw_CS, r, 0, p->rw_smem, nullptr, true, &occ);
+      if (e != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        p->rw_ok = false;
+      } else {
+        p->rw_grid = sms * occ;
+      }
+    }
+    {
+      const char* pick = getenv("B2S_LINEAR_KERNEL");  // rowthread (default) | rowwarp | generic  (A/B runs)
+      const std::string want = pick ? pick : "rowthread";
+      int n_cat_cols = 0;
+      for (int c = 0; c < n_in; ++c) n_cat_cols += (cat_off[c + 1] > cat_off[c]) ? 1 : 0;
+      if (want != "rowwarp") p->rw_ok = p->rw_ok && (want == "rowwarp");
+      if (want == "rowthread" && p->mode == MODE_LINEAR && !any_map && n_in <= 128 && NS <= 8 &&
+          n_cat_cols <= kRTMaxCatCols && (int)cat_val.size() <= kRTMaxCats) {
+        const int nch = (n_in + 3) / 4;
+        p->rt_NCH = nch <= 4 ? 4 : (nch <= 8 ? 8 : (nch <= 16 ? 16 : 32));
+        p->rt_NS = NS;
+        p->rt_cat_cols = n_cat_cols;
+        bool simple = true;
+        for (auto& m : p->models) simple = simple && m.link == B2S_LINK_IDENTITY && m.n_scores == 1;
+        RTTables t{n_in, p->out_cols, M, p->vote_kind, p->out_is_int, (simple && p->vote_kind != B2S_VOTE_MAJORITY) ? 1 : 0, NS,
+                   &p->fill, &flags, &wnum, &bias, &p->vote_w, &cat_off, &cat_val, k.wcat, k.vote_w, k.models, k.classes};
+        rt_build_any(p, t);
+        int rpitch = p->rt_NCH * 4 + 4;
+        if (((rpitch / 4) & 1) == 0) rpitch += 4;
+        p->rt_pitch = rpitch;
+        const char* stg = getenv("B2S_RT_STAGES");
+        p->rt_stages = stg ? std::max(2, std::min(4, atoi(stg))) : 2;
+        const char* tile_env = getenv("B2S_RT_TILE");  // rows per tile: 64 | 128
+        p->rt_tile_rows = tile_env && atoi(tile_env) == 64 ? 64 : 128;
+        const char* rpt_env = getenv("B2S_RT_RPT");  // rows per thread: 1 | 2 (2: tensor-map loads only)
+        p->rt_RPT = rpt_env && atoi(rpt_env) == 2 && p->rt_NCH >= 8 ? 2 : 1;
+        const char* tprs = getenv("B2S_RT_TPR");
+        p->rt_TPR = tprs ? atoi(tprs) : rt_tpr(p->rt_NCH);
+        if (p->rt_TPR != 1 && p->rt_TPR != 2 && p->rt_TPR != 4) p->rt_TPR = 1;
+        while (p->rt_TPR > 1 && (p->rt_NCH < 4 * p->rt_TPR)) p->rt_TPR /= 2;
+        {
+          const size_t fixed = 1024 + 64 + align_up((size_t)(cat_val.size() + 1) * NS * 8, 16);
+          const size_t part = (size_t)(p->rt_TPR - 1) * 128 * NS * 8;
+          // padded tiles + one partial-sum buffer (LDGSTS / per-row bulk), or swizzled tiles + two (tensor map)
+          const size_t padded = fixed + part + (size_t)p->rt_stages * p->rt_tile_rows * rpitch * 4;
+          const size_t swizzled = fixed + 2 * part + (size_t)p->rt_stages * p->rt_tile_rows * p->rt_NCH * 16;
+          p->rt_smem = (int)std::max(padded, swizzled);
+        }
+        int occ = 0;
+        if (p->rt_smem <= smem_cap && rt_launch(p, nullptr, 0, 0, nullptr, nullptr, 0, nullptr, true, &occ) == cudaSuccess && occ >= 1) {
+          p->rt_ok = true;
+          p->rt_grid = sms * occ;
+        } else {
+          cudaGetLastError();
+        }
+      }
+    }
+    if (p->mode == MODE_TREES && !need_expand && getenv("B2S_NO_TREES2") == nullptr) {
+      // re-pack every model as complete heap-ordered trees; one model must fit one CTA's shared memory
+      bool ok = true;
+      std::vector<int> depth(M, 0);
+      size_t max_table = 0;
+      for (int mi = 0; mi < M && ok; ++mi) {
+        auto& m = p->models[mi];
+        if (m.kind != MK_TREES) { ok = false; break; }
+        const int nt = (int)m.tree_slot.size();
+        for (int t = 0; t < nt; ++t) {
+          const int base = m.tree_offset[t];
+          std::vector<std::pair<int, int>> stack{{0, 0}};
+          while (!stack.empty()) {
+            auto [node, d] = stack.back();
+            stack.pop_back();
+            depth[mi] = std::max(depth[mi], d);
+            if (m.feature[base + node] >= 0) {
+              stack.push_back({m.left[base + node], d + 1});
+              stack.push_back({m.right[base + node], d + 1});
+            }
+          }
+        }
+        if (depth[mi] > 8) ok = false;
+        const size_t ni = ((size_t)1 << depth[mi]) - 1, nl = (size_t)1 << depth[mi];
+        max_table = std::max(max_table, align_up((size_t)nt * ni * 8, 16) + (size_t)nt * nl * 8 + (size_t)nt * 4);
+      }
+      const int TR2 = kT2TileRows, G2 = kT2Groups, ST2 = 1;  // one row-major landing tile + one transposed tile
+      const int NS2 = p->NS <= 1 ? 1 : (p->NS <= 4 ? 4 : 0);
+      const size_t part_bytes = (size_t)(G2 - 1) * TR2 * std::max(NS2, 1) * 8;
+      const size_t tiles_bytes = (size_t)ST2 * TR2 * pitch * 4 + (size_t)((n_in + 3) / 4 * 4) * TR2 * 4 + (size_t)TR2 * 4 + 16 + 1024;  // + mbarrier + alignment slack
+      const size_t total2 = align_up(max_table, 16) + align_up(part_bytes, 16) + tiles_bytes;
+      if (ok && NS2 > 0 && total2 <= (size_t)smem_cap && M <= sms) {
+        BlobBuilder tb;
+        std::vector<T2Model> t2m(M);
+        std::vector<size_t> o_nodes(M), o_leaves(M), o_slot(M), o_scale(M);
+        for (int mi = 0; mi < M; ++mi) {
+          auto& m = p->models[mi];
+          const int nt = (int)m.tree_slot.size();
+          const int D = depth[mi];
+          const int ni = (1 << D) - 1, nl = 1 << D;
+          std::vector<HeapNode> hn((size_t)nt * std::max(ni, 1), HeapNode{0, std::numeric_limits<float>::infinity()});
+          std::vector<double> hl((size_t)nt * nl, 0.0);
+          for (int t = 0; t < nt; ++t) {
+            const int base = m.tree_offset[t];
+            struct It { int heap, d, src; };
+            std::vector<It> stack{{0, 0, 0}};
+            while (!stack.empty()) {
+              It it = stack.back();
+              stack.pop_back();
+              const bool leaf = m.feature[base + it.src] < 0;
+              if (it.d == D) {
+                hl[(size_t)t * nl + (it.heap - ni)] = m.leaf_value[base + it.src];
+                continue;
+              }
+              if (leaf) {  // pad: a threshold of +inf sends every finite value left; both sides carry the leaf
+                hn[(size_t)t * ni + it.heap] = HeapNode{0, std::numeric_limits<float>::infinity()};
+                stack.push_back({2 * it.heap + 1, it.d + 1, it.src});
+                stack.push_back({2 * it.heap + 2, it.d + 1, it.src});
+              } else {
+                hn[(size_t)t * ni + it.heap] = HeapNode{m.feature[base + it.src], m.threshold[base + it.src]};
+                stack.push_back({2 * it.heap + 1, it.d + 1, m.left[base + it.src]});
+                stack.push_back({2 * it.heap + 2, it.d + 1, m.right[base + it.src]});
+              }
+            }
+          }
+          o_nodes[mi] = tb.add(hn);
+          o_leaves[mi] = tb.add(hl);
+          o_slot[mi] = tb.add(m.tree_slot);
+          o_scale[mi] = tb.add(m.tree_scale);
+          t2m[mi].n_trees = nt;
+          t2m[mi].depth = D;
+          t2m[mi].n_internal = ni;
+          t2m[mi].n_leaves = nl;
+        }
+        const size_t o_models2 = align_up(tb.data.size(), 16);
+        tb.data.resize(o_models2 + sizeof(T2Model) * M);
+        CUDA_TRY(cudaMalloc(&p->d_t2_blob, tb.data.size()));
+        for (int mi = 0; mi < M; ++mi) {
+          t2m[mi].nodes = (const HeapNode*)(p->d_t2_blob + o_nodes[mi]);
+          t2m[mi].leaves = (const double*)(p->d_t2_blob + o_leaves[mi]);
+          t2m[mi].slot = (const int32_t*)(p->d_t2_blob + o_slot[mi]);
+          t2m[mi].scale = (const double*)(p->d_t2_blob + o_scale[mi]);
+        }
+        memcpy(tb.data.data() + o_models2, t2m.data(), sizeof(T2Model) * M);
+        CUDA_TRY(cudaMemcpy(p->d_t2_blob, tb.data.data(), tb.data.size(), cudaMemcpyHostToDevice));
+        T2Params& t = p->t2;
+        memset(&t, 0, sizeof(t));
+        t.n_in = n_in;
+        t.n_models = M;
+        t.tile_rows = TR2;
+        t.pitch = pitch;
+        t.stages = ST2;
+        t.groups = G2;
+        t.t2 = (const T2Model*)(p->d_t2_blob + o_models2);
+        t.models = k.models;
+        t.classes = k.classes;
+        t.bias = k.bias;
+        t.sm_tables = 0;
+        t.sm_part = (int)align_up(max_table, 16);
+        t.sm_tiles = (int)(align_up(max_table, 16) + align_up(part_bytes, 16));
+        p->t2_smem = (int)total2;
+        p->t2_NS = NS2;
+        p->t2_block = TR2 * G2;
+        p->t2_grid = std::max(M, (sms / M) * M);
+        p->t2_ok = true;
+        p->kernels_per_batch = 2;
+      }
+    }
+    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&p->ev[i]));
+    p->finalized = true;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&p->ev[i]));
-  p->finalized = true;
-  return B2S_OK;
 }
 
 // which kernel family a finalized plan launches (so that a silent fallback cannot hide in a benchmark)
@@ -1258,10 +1308,14 @@ extern "C" const char* b2s_plan_kernel(b2s_plan_t p) {
 }
 
 extern "C" int b2s_plan_out_info(b2s_plan_t p, int32_t* out_cols, int32_t* out_is_int) {
-  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
-  if (out_cols) *out_cols = p->out_cols;
-  if (out_is_int) *out_is_int = p->out_is_int;
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+    if (out_cols) *out_cols = p->out_cols;
+    if (out_is_int) *out_is_int = p->out_is_int;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 // ------------------------------------------------------------------------------------------ execution
@@ -1363,9 +1417,13 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
 
 extern "C" int b2s_run_device(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t row_stride_bytes, void* d_out,
                               int32_t* d_status, void* stream) {
-  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
-  if (n_rows < 0 || row_stride_bytes < (int64_t)p->n_in * 4) return fail(B2S_ERR_INVALID, "bad n_rows/stride");
-  return launch_on(p, d_rows, n_rows, row_stride_bytes, d_out, d_status, stream ? (cudaStream_t)stream : G.stream);
+  try {  // no C++ exception crosses the C boundary
+    if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+    if (n_rows < 0 || row_stride_bytes < (int64_t)p->n_in * 4) return fail(B2S_ERR_INVALID, "bad n_rows/stride");
+    return launch_on(p, d_rows, n_rows, row_stride_bytes, d_out, d_status, stream ? (cudaStream_t)stream : G.stream);
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 int b2s_int_launch_gathered(b2s_plan_s* p, const B2SGather& g, long long n, void* d_out, int* d_status, cudaStream_t st) {
@@ -1413,126 +1471,134 @@ static void pack_rows(char* dst, const void* rows, int64_t n_rows, int64_t strid
 
 extern "C" int b2s_run_host(b2s_plan_t p, const void* rows, int64_t n_rows, int64_t row_stride_bytes, void* out,
                             int64_t out_bytes, int32_t* row_status, b2s_stats* stats) {
-  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
-  const int64_t row_bytes = (int64_t)p->n_in * 4;
-  if (n_rows < 0 || row_stride_bytes < row_bytes) return fail(B2S_ERR_INVALID, "bad n_rows/stride");
-  if (out_bytes < n_rows * p->out_cols * 4) return fail(B2S_ERR_INVALID, "out buffer too small");
-  if (n_rows == 0) return B2S_OK;
-  std::lock_guard<std::mutex> lk(p->host_mu);
-  CUDA_TRY(cudaSetDevice(G.device));
-  if (int rc = ensure_stage(p, n_rows)) return rc;
-  cudaStream_t st = G.stream;
-  cudaPointerAttributes attr{};
-  const bool pinned = cudaPointerGetAttributes(&attr, rows) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
-                      row_stride_bytes == row_bytes;
-  cudaGetLastError();
-  const void* src = rows;
-  if (!pinned) {
-    pack_rows(p->h_stage_in, rows, n_rows, row_stride_bytes, row_bytes);
-    src = p->h_stage_in;
-  }
-  const size_t out_sz = (size_t)n_rows * p->out_cols * 4;
-  // Large pinned batches run as a pipeline of chunks: chunk c+1 crosses PCIe while chunk c is computed, copied back and
-  // post-processed on the host, so the call costs about one H2D of the batch.  (Not with merge targets: their row offset
-  // is per launch.)
-  static const int64_t pipe_rows = getenv("B2S_HOST_CHUNK") ? atoll(getenv("B2S_HOST_CHUNK")) : 65536;  // measured: 16Ki 162, 32Ki 184, 64Ki 189 M events/s (one piece: 169)
-  if (pinned && pipe_rows > 0 && n_rows >= 2 * pipe_rows && p->peers.empty()) {
-    // whole tiles per chunk keep every chunk's base 16-byte (and tensor-map) aligned
-    const int64_t chunk = (int64_t)align_up((size_t)std::max<int64_t>(pipe_rows, (n_rows + 63) / 64), 1024);
-    const int n_chunks = (int)((n_rows + chunk - 1) / chunk);
-    while ((int)p->chunk_ev.size() < 4 * n_chunks) {
-      cudaEvent_t e;
-      CUDA_TRY(cudaEventCreate(&e));
-      p->chunk_ev.push_back(e);
+  try {  // no C++ exception crosses the C boundary
+    if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+    const int64_t row_bytes = (int64_t)p->n_in * 4;
+    if (n_rows < 0 || row_stride_bytes < row_bytes) return fail(B2S_ERR_INVALID, "bad n_rows/stride");
+    if (out_bytes < n_rows * p->out_cols * 4) return fail(B2S_ERR_INVALID, "out buffer too small");
+    if (n_rows == 0) return B2S_OK;
+    std::lock_guard<std::mutex> lk(p->host_mu);
+    CUDA_TRY(cudaSetDevice(G.device));
+    if (int rc = ensure_stage(p, n_rows)) return rc;
+    cudaStream_t st = G.stream;
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, rows) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+                        row_stride_bytes == row_bytes;
+    cudaGetLastError();
+    const void* src = rows;
+    if (!pinned) {
+      pack_rows(p->h_stage_in, rows, n_rows, row_stride_bytes, row_bytes);
+      src = p->h_stage_in;
     }
-    cudaStream_t cs = G.copy_stream;
-    int32_t* h_status = (int32_t*)(p->h_stage_out + out_sz);
-    const size_t out_row = (size_t)p->out_cols * 4;
-    CUDA_TRY(cudaEventRecord(p->ev[0], cs));
-    for (int c = 0; c < n_chunks; ++c) {
-      const int64_t r0 = (int64_t)c * chunk, nr = std::min<int64_t>(chunk, n_rows - r0);
-      cudaEvent_t* ce = &p->chunk_ev[4 * c];
-      CUDA_TRY(cudaMemcpyAsync(p->d_stage_in + r0 * row_bytes, (const char*)src + r0 * row_bytes, (size_t)nr * row_bytes,
-                               cudaMemcpyHostToDevice, cs));
-      CUDA_TRY(cudaEventRecord(ce[0], cs));
-      CUDA_TRY(cudaStreamWaitEvent(st, ce[0], 0));
-      CUDA_TRY(cudaEventRecord(ce[1], st));
-      if (int rc = launch_on(p, p->d_stage_in + r0 * row_bytes, nr, row_bytes, p->d_stage_out + r0 * out_row,
-                             p->d_stage_status + r0, st)) {
-        cudaStreamSynchronize(cs);
-        cudaStreamSynchronize(st);
-        return rc;
+    const size_t out_sz = (size_t)n_rows * p->out_cols * 4;
+    // Large pinned batches run as a pipeline of chunks: chunk c+1 crosses PCIe while chunk c is computed, copied back and
+    // post-processed on the host, so the call costs about one H2D of the batch.  (Not with merge targets: their row offset
+    // is per launch.)
+    static const int64_t pipe_rows = getenv("B2S_HOST_CHUNK") ? atoll(getenv("B2S_HOST_CHUNK")) : 65536;  // measured: 16Ki 162, 32Ki 184, 64Ki 189 M events/s (one piece: 169)
+    if (pinned && pipe_rows > 0 && n_rows >= 2 * pipe_rows && p->peers.empty()) {
+      // whole tiles per chunk keep every chunk's base 16-byte (and tensor-map) aligned
+      const int64_t chunk = (int64_t)align_up((size_t)std::max<int64_t>(pipe_rows, (n_rows + 63) / 64), 1024);
+      const int n_chunks = (int)((n_rows + chunk - 1) / chunk);
+      while ((int)p->chunk_ev.size() < 4 * n_chunks) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        p->chunk_ev.push_back(e);
       }
-      CUDA_TRY(cudaEventRecord(ce[2], st));
-      CUDA_TRY(cudaMemcpyAsync(p->h_stage_out + r0 * out_row, p->d_stage_out + r0 * out_row, (size_t)nr * out_row,
-                               cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaMemcpyAsync(h_status + r0, p->d_stage_status + r0, (size_t)nr * 4, cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaEventRecord(ce[3], st));
+      cudaStream_t cs = G.copy_stream;
+      int32_t* h_status = (int32_t*)(p->h_stage_out + out_sz);
+      const size_t out_row = (size_t)p->out_cols * 4;
+      CUDA_TRY(cudaEventRecord(p->ev[0], cs));
+      for (int c = 0; c < n_chunks; ++c) {
+        const int64_t r0 = (int64_t)c * chunk, nr = std::min<int64_t>(chunk, n_rows - r0);
+        cudaEvent_t* ce = &p->chunk_ev[4 * c];
+        CUDA_TRY(cudaMemcpyAsync(p->d_stage_in + r0 * row_bytes, (const char*)src + r0 * row_bytes, (size_t)nr * row_bytes,
+                                 cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaEventRecord(ce[0], cs));
+        CUDA_TRY(cudaStreamWaitEvent(st, ce[0], 0));
+        CUDA_TRY(cudaEventRecord(ce[1], st));
+        if (int rc = launch_on(p, p->d_stage_in + r0 * row_bytes, nr, row_bytes, p->d_stage_out + r0 * out_row,
+                               p->d_stage_status + r0, st)) {
+          cudaStreamSynchronize(cs);
+          cudaStreamSynchronize(st);
+          return rc;
+        }
+        CUDA_TRY(cudaEventRecord(ce[2], st));
+        CUDA_TRY(cudaMemcpyAsync(p->h_stage_out + r0 * out_row, p->d_stage_out + r0 * out_row, (size_t)nr * out_row,
+                                 cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_status + r0, p->d_stage_status + r0, (size_t)nr * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(ce[3], st));
+      }
+      int bad = 0;
+      for (int c = 0; c < n_chunks; ++c) {  // hand each chunk to the caller as it lands
+        const int64_t r0 = (int64_t)c * chunk, nr = std::min<int64_t>(chunk, n_rows - r0);
+        CUDA_TRY(cudaEventSynchronize(p->chunk_ev[4 * c + 3]));
+        memcpy((char*)out + r0 * out_row, p->h_stage_out + r0 * out_row, (size_t)nr * out_row);
+        for (int64_t r = r0; r < r0 + nr; ++r) bad += (h_status[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
+        if (row_status) memcpy(row_status + r0, h_status + r0, (size_t)nr * 4);
+      }
+      CUDA_TRY(cudaStreamSynchronize(cs));
+      if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->rows = n_rows;
+        cudaEventElapsedTime(&stats->h2d_ms, p->ev[0], p->chunk_ev[4 * (n_chunks - 1)]);
+        for (int c = 0; c < n_chunks; ++c) {  // the phases of different chunks overlap: these are sums over chunks
+          float k = 0.f, d = 0.f;
+          cudaEventElapsedTime(&k, p->chunk_ev[4 * c + 1], p->chunk_ev[4 * c + 2]);
+          cudaEventElapsedTime(&d, p->chunk_ev[4 * c + 2], p->chunk_ev[4 * c + 3]);
+          stats->kernel_ms += k;
+          stats->d2h_ms += d;
+        }
+        stats->kernels = p->kernels_per_batch * n_chunks;
+        stats->nonfinite_rows = bad;
+      }
+      return B2S_OK;
     }
+    CUDA_TRY(cudaEventRecord(p->ev[0], st));
+    CUDA_TRY(cudaMemcpyAsync(p->d_stage_in, src, (size_t)n_rows * row_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(p->ev[1], st));
+    if (int rc = launch_on(p, p->d_stage_in, n_rows, row_bytes, p->d_stage_out, p->d_stage_status, st)) return rc;
+    CUDA_TRY(cudaEventRecord(p->ev[2], st));
+    CUDA_TRY(cudaMemcpyAsync(p->h_stage_out, p->d_stage_out, out_sz, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(p->h_stage_out + out_sz, p->d_stage_status, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(p->ev[3], st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(out, p->h_stage_out, out_sz);
+    const int32_t* hs = (const int32_t*)(p->h_stage_out + out_sz);
     int bad = 0;
-    for (int c = 0; c < n_chunks; ++c) {  // hand each chunk to the caller as it lands
-      const int64_t r0 = (int64_t)c * chunk, nr = std::min<int64_t>(chunk, n_rows - r0);
-      CUDA_TRY(cudaEventSynchronize(p->chunk_ev[4 * c + 3]));
-      memcpy((char*)out + r0 * out_row, p->h_stage_out + r0 * out_row, (size_t)nr * out_row);
-      for (int64_t r = r0; r < r0 + nr; ++r) bad += (h_status[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
-      if (row_status) memcpy(row_status + r0, h_status + r0, (size_t)nr * 4);
-    }
-    CUDA_TRY(cudaStreamSynchronize(cs));
+    for (int64_t r = 0; r < n_rows; ++r) bad += (hs[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
+    if (row_status) memcpy(row_status, hs, (size_t)n_rows * 4);
     if (stats) {
       memset(stats, 0, sizeof(*stats));
       stats->rows = n_rows;
-      cudaEventElapsedTime(&stats->h2d_ms, p->ev[0], p->chunk_ev[4 * (n_chunks - 1)]);
-      for (int c = 0; c < n_chunks; ++c) {  // the phases of different chunks overlap: these are sums over chunks
-        float k = 0.f, d = 0.f;
-        cudaEventElapsedTime(&k, p->chunk_ev[4 * c + 1], p->chunk_ev[4 * c + 2]);
-        cudaEventElapsedTime(&d, p->chunk_ev[4 * c + 2], p->chunk_ev[4 * c + 3]);
-        stats->kernel_ms += k;
-        stats->d2h_ms += d;
-      }
-      stats->kernels = p->kernels_per_batch * n_chunks;
+      cudaEventElapsedTime(&stats->h2d_ms, p->ev[0], p->ev[1]);
+      cudaEventElapsedTime(&stats->kernel_ms, p->ev[1], p->ev[2]);
+      cudaEventElapsedTime(&stats->d2h_ms, p->ev[2], p->ev[3]);
+      stats->kernels = p->kernels_per_batch;
       stats->nonfinite_rows = bad;
     }
     return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  CUDA_TRY(cudaEventRecord(p->ev[0], st));
-  CUDA_TRY(cudaMemcpyAsync(p->d_stage_in, src, (size_t)n_rows * row_bytes, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaEventRecord(p->ev[1], st));
-  if (int rc = launch_on(p, p->d_stage_in, n_rows, row_bytes, p->d_stage_out, p->d_stage_status, st)) return rc;
-  CUDA_TRY(cudaEventRecord(p->ev[2], st));
-  CUDA_TRY(cudaMemcpyAsync(p->h_stage_out, p->d_stage_out, out_sz, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(p->h_stage_out + out_sz, p->d_stage_status, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaEventRecord(p->ev[3], st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  memcpy(out, p->h_stage_out, out_sz);
-  const int32_t* hs = (const int32_t*)(p->h_stage_out + out_sz);
-  int bad = 0;
-  for (int64_t r = 0; r < n_rows; ++r) bad += (hs[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
-  if (row_status) memcpy(row_status, hs, (size_t)n_rows * 4);
-  if (stats) {
-    memset(stats, 0, sizeof(*stats));
-    stats->rows = n_rows;
-    cudaEventElapsedTime(&stats->h2d_ms, p->ev[0], p->ev[1]);
-    cudaEventElapsedTime(&stats->kernel_ms, p->ev[1], p->ev[2]);
-    cudaEventElapsedTime(&stats->d2h_ms, p->ev[2], p->ev[3]);
-    stats->kernels = p->kernels_per_batch;
-    stats->nonfinite_rows = bad;
-  }
-  return B2S_OK;
 }
 
 extern "C" int b2s_time_device(b2s_plan_t p, const void* const* d_rows, int32_t n_bufs, int64_t n_rows,
                                int64_t row_stride_bytes, void* d_out, int32_t n_iters, float* total_ms) {
-  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
-  if (n_bufs < 1 || n_iters < 1 || !total_ms) return fail(B2S_ERR_INVALID, "bad arguments");
-  cudaStream_t st = G.stream;
-  CUDA_TRY(cudaStreamSynchronize(st));
-  CUDA_TRY(cudaEventRecord(p->ev[0], st));
-  for (int i = 0; i < n_iters; ++i)
-    if (int rc = launch_on(p, d_rows[i % n_bufs], n_rows, row_stride_bytes, d_out, nullptr, st)) return rc;
-  CUDA_TRY(cudaEventRecord(p->ev[1], st));
-  CUDA_TRY(cudaEventSynchronize(p->ev[1]));
-  CUDA_TRY(cudaEventElapsedTime(total_ms, p->ev[0], p->ev[1]));
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+    if (n_bufs < 1 || n_iters < 1 || !total_ms) return fail(B2S_ERR_INVALID, "bad arguments");
+    cudaStream_t st = G.stream;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventRecord(p->ev[0], st));
+    for (int i = 0; i < n_iters; ++i)
+      if (int rc = launch_on(p, d_rows[i % n_bufs], n_rows, row_stride_bytes, d_out, nullptr, st)) return rc;
+    CUDA_TRY(cudaEventRecord(p->ev[1], st));
+    CUDA_TRY(cudaEventSynchronize(p->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(total_ms, p->ev[0], p->ev[1]));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 // ------------------------------------------------------------------------------------------ coalescing ring
@@ -1617,155 +1683,187 @@ static int ring_start(b2s_plan_s* p) {
 
 // ticket = batch_id << 24 | row offset inside the batch (max_batch <= 2^24 rows)
 extern "C" int b2s_submit(b2s_plan_t p, const void* rows, int64_t n_rows, int64_t row_stride_bytes, uint64_t* ticket) {
-  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
-  const int64_t row_bytes = (int64_t)p->n_in * 4;
-  if (n_rows <= 0 || row_stride_bytes < row_bytes || !ticket) return fail(B2S_ERR_INVALID, "bad submit arguments");
-  std::unique_lock<std::mutex> lk(p->mu);
-  if (int rc = ring_start(p)) return rc;
-  if (n_rows > p->ring_cap || p->ring_cap > (1 << 24)) return fail(B2S_ERR_INVALID, "submit of %lld rows exceeds max_batch %lld", (long long)n_rows, (long long)p->ring_cap);
-  for (;;) {
-    if (p->open_slot >= 0 && p->slots[p->open_slot].rows + n_rows > p->ring_cap) {
+  try {  // no C++ exception crosses the C boundary
+    if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+    const int64_t row_bytes = (int64_t)p->n_in * 4;
+    if (n_rows <= 0 || row_stride_bytes < row_bytes || !ticket) return fail(B2S_ERR_INVALID, "bad submit arguments");
+    std::unique_lock<std::mutex> lk(p->mu);
+    if (int rc = ring_start(p)) return rc;
+    if (n_rows > p->ring_cap || p->ring_cap > (1 << 24)) return fail(B2S_ERR_INVALID, "submit of %lld rows exceeds max_batch %lld", (long long)n_rows, (long long)p->ring_cap);
+    for (;;) {
+      if (p->open_slot >= 0 && p->slots[p->open_slot].rows + n_rows > p->ring_cap) {
+        p->slots[p->open_slot].state = 1;
+        p->sealed.push_back(p->open_slot);
+        p->open_slot = -1;
+        p->cv_work.notify_one();
+      }
+      if (p->open_slot < 0) {
+        for (int i = 0; i < (int)p->slots.size(); ++i)
+          if (p->slots[i].state == 0 && p->slots[i].rows == 0 && p->slots[i].waiters == 0) {
+            p->open_slot = i;
+            p->slots[i].batch_id = p->next_batch++;
+            p->batch_slot[p->slots[i].batch_id] = i;
+            break;
+          }
+        if (p->open_slot < 0) {
+          p->cv_free.wait(lk);  // every slot is in flight or waiting to be collected
+          continue;
+        }
+      }
+      break;
+    }
+    Slot& s = p->slots[p->open_slot];
+    if (s.rows == 0) s.first_submit = std::chrono::steady_clock::now();
+    const int64_t off = s.rows;
+    pack_rows(s.h_in + off * row_bytes, rows, n_rows, row_stride_bytes, row_bytes);
+    s.rows += n_rows;
+    s.waiters += 1;
+    *ticket = (s.batch_id << 24) | (uint64_t)off;
+    if (s.rows >= p->ring_cap) {
+      s.state = 1;
+      p->sealed.push_back(p->open_slot);
+      p->open_slot = -1;
+    }
+    p->cv_work.notify_one();
+    // remember how many rows this ticket covers (low 24 bits hold the offset; the count travels in a side map)
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
+}
+
+extern "C" int b2s_flush(b2s_plan_t p) {
+  try {  // no C++ exception crosses the C boundary
+    if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+    std::unique_lock<std::mutex> lk(p->mu);
+    if (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0) {
       p->slots[p->open_slot].state = 1;
       p->sealed.push_back(p->open_slot);
       p->open_slot = -1;
       p->cv_work.notify_one();
     }
-    if (p->open_slot < 0) {
-      for (int i = 0; i < (int)p->slots.size(); ++i)
-        if (p->slots[i].state == 0 && p->slots[i].rows == 0 && p->slots[i].waiters == 0) {
-          p->open_slot = i;
-          p->slots[i].batch_id = p->next_batch++;
-          p->batch_slot[p->slots[i].batch_id] = i;
-          break;
-        }
-      if (p->open_slot < 0) {
-        p->cv_free.wait(lk);  // every slot is in flight or waiting to be collected
-        continue;
-      }
-    }
-    break;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  Slot& s = p->slots[p->open_slot];
-  if (s.rows == 0) s.first_submit = std::chrono::steady_clock::now();
-  const int64_t off = s.rows;
-  pack_rows(s.h_in + off * row_bytes, rows, n_rows, row_stride_bytes, row_bytes);
-  s.rows += n_rows;
-  s.waiters += 1;
-  *ticket = (s.batch_id << 24) | (uint64_t)off;
-  if (s.rows >= p->ring_cap) {
-    s.state = 1;
-    p->sealed.push_back(p->open_slot);
-    p->open_slot = -1;
-  }
-  p->cv_work.notify_one();
-  // remember how many rows this ticket covers (low 24 bits hold the offset; the count travels in a side map)
-  return B2S_OK;
-}
-
-extern "C" int b2s_flush(b2s_plan_t p) {
-  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
-  std::unique_lock<std::mutex> lk(p->mu);
-  if (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0) {
-    p->slots[p->open_slot].state = 1;
-    p->sealed.push_back(p->open_slot);
-    p->open_slot = -1;
-    p->cv_work.notify_one();
-  }
-  return B2S_OK;
 }
 
 extern "C" int b2s_wait(b2s_plan_t p, uint64_t ticket, void* out, int64_t out_bytes, int32_t* row_status, b2s_stats* stats) {
-  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
-  const uint64_t batch = ticket >> 24;
-  const int64_t off = (int64_t)(ticket & ((1u << 24) - 1));
-  const int64_t n_rows = out_bytes / ((int64_t)p->out_cols * 4);
-  std::unique_lock<std::mutex> lk(p->mu);
-  auto it = p->batch_slot.find(batch);
-  if (it == p->batch_slot.end()) return fail(B2S_ERR_INVALID, "unknown ticket");
-  Slot& s = p->slots[it->second];
-  p->cv_done.wait(lk, [&] { return s.state == 3 && s.batch_id == batch; });
-  if (off + n_rows > s.rows) return fail(B2S_ERR_INVALID, "ticket range exceeds its batch");
-  memcpy(out, s.h_out + (size_t)off * p->out_cols * 4, (size_t)n_rows * p->out_cols * 4);
-  const int32_t* hs = (const int32_t*)(s.h_out + (size_t)p->ring_cap * p->out_cols * 4) + off;
-  if (row_status) memcpy(row_status, hs, (size_t)n_rows * 4);
-  if (stats) {
-    *stats = s.stats;
-    int bad = 0;
-    for (int64_t r = 0; r < n_rows; ++r) bad += (hs[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
-    stats->nonfinite_rows = bad;
+  try {  // no C++ exception crosses the C boundary
+    if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+    const uint64_t batch = ticket >> 24;
+    const int64_t off = (int64_t)(ticket & ((1u << 24) - 1));
+    const int64_t n_rows = out_bytes / ((int64_t)p->out_cols * 4);
+    std::unique_lock<std::mutex> lk(p->mu);
+    auto it = p->batch_slot.find(batch);
+    if (it == p->batch_slot.end()) return fail(B2S_ERR_INVALID, "unknown ticket");
+    Slot& s = p->slots[it->second];
+    p->cv_done.wait(lk, [&] { return s.state == 3 && s.batch_id == batch; });
+    if (off + n_rows > s.rows) return fail(B2S_ERR_INVALID, "ticket range exceeds its batch");
+    memcpy(out, s.h_out + (size_t)off * p->out_cols * 4, (size_t)n_rows * p->out_cols * 4);
+    const int32_t* hs = (const int32_t*)(s.h_out + (size_t)p->ring_cap * p->out_cols * 4) + off;
+    if (row_status) memcpy(row_status, hs, (size_t)n_rows * 4);
+    if (stats) {
+      *stats = s.stats;
+      int bad = 0;
+      for (int64_t r = 0; r < n_rows; ++r) bad += (hs[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
+      stats->nonfinite_rows = bad;
+    }
+    if (--s.waiters == 0) {  // last collector frees the slot
+      p->batch_slot.erase(it);
+      s.rows = 0;
+      s.state = 0;
+      p->cv_free.notify_all();
+    }
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  if (--s.waiters == 0) {  // last collector frees the slot
-    p->batch_slot.erase(it);
-    s.rows = 0;
-    s.state = 0;
-    p->cv_free.notify_all();
-  }
-  return B2S_OK;
 }
 
 extern "C" int b2s_plan_destroy(b2s_plan_t p) {
-  if (!p) return B2S_OK;
-  if (p->dispatcher.joinable()) {
-    {
-      std::lock_guard<std::mutex> lk(p->mu);
-      p->stop = true;
-      p->cv_work.notify_all();
+  try {  // no C++ exception crosses the C boundary
+    if (!p) return B2S_OK;
+    if (p->dispatcher.joinable()) {
+      {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->stop = true;
+        p->cv_work.notify_all();
+      }
+      p->dispatcher.join();
     }
-    p->dispatcher.join();
+    for (auto& s : p->slots) {
+      cudaFreeHost(s.h_in);
+      cudaFreeHost(s.h_out);
+      cudaFree(s.d_in);
+      cudaFree(s.d_out);
+      cudaFree(s.d_status);
+      cudaEventDestroy(s.e0);
+      cudaEventDestroy(s.e1);
+      cudaEventDestroy(s.e2);
+      cudaEventDestroy(s.e3);
+    }
+    if (p->ring_stream) cudaStreamDestroy(p->ring_stream);
+    if (p->h_stage_in) {
+      cudaFreeHost(p->h_stage_in);
+      cudaFreeHost(p->h_stage_out);
+      cudaFree(p->d_stage_in);
+      cudaFree(p->d_stage_out);
+      cudaFree(p->d_stage_status);
+    }
+    for (int i = 0; i < 4; ++i)
+      if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    for (cudaEvent_t e : p->chunk_ev) cudaEventDestroy(e);
+    if (p->d_blob) cudaFree(p->d_blob);
+    if (p->d_t2_blob) cudaFree(p->d_t2_blob);
+    for (auto& kv : p->t2_scratch)
+      if (kv.second.pred) { cudaFree(kv.second.pred); cudaFree(kv.second.row_bad); }
+    delete p;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  for (auto& s : p->slots) {
-    cudaFreeHost(s.h_in);
-    cudaFreeHost(s.h_out);
-    cudaFree(s.d_in);
-    cudaFree(s.d_out);
-    cudaFree(s.d_status);
-    cudaEventDestroy(s.e0);
-    cudaEventDestroy(s.e1);
-    cudaEventDestroy(s.e2);
-    cudaEventDestroy(s.e3);
-  }
-  if (p->ring_stream) cudaStreamDestroy(p->ring_stream);
-  if (p->h_stage_in) {
-    cudaFreeHost(p->h_stage_in);
-    cudaFreeHost(p->h_stage_out);
-    cudaFree(p->d_stage_in);
-    cudaFree(p->d_stage_out);
-    cudaFree(p->d_stage_status);
-  }
-  for (int i = 0; i < 4; ++i)
-    if (p->ev[i]) cudaEventDestroy(p->ev[i]);
-  for (cudaEvent_t e : p->chunk_ev) cudaEventDestroy(e);
-  if (p->d_blob) cudaFree(p->d_blob);
-  if (p->d_t2_blob) cudaFree(p->d_t2_blob);
-  for (auto& kv : p->t2_scratch)
-    if (kv.second.pred) { cudaFree(kv.second.pred); cudaFree(kv.second.row_bad); }
-  delete p;
-  return B2S_OK;
 }
 
 // ------------------------------------------------------------------------------------------ multi-GPU merge
 extern "C" int b2s_plan_set_merge_targets(b2s_plan_t p, void* const* peer_out, int32_t n_peers, int64_t row_offset) {
-  if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
-  if (n_peers < 0 || n_peers > 8 || row_offset < 0) return fail(B2S_ERR_INVALID, "bad merge targets");
-  if (p->mode == MODE_STORE && n_peers > 0) return fail(B2S_ERR_UNSUPPORTED, "transform-only plans have no vote to merge");
-  p->peers.assign(peer_out, peer_out + n_peers);
-  p->peer_off = row_offset;
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+    if (n_peers < 0 || n_peers > 8 || row_offset < 0) return fail(B2S_ERR_INVALID, "bad merge targets");
+    if (p->mode == MODE_STORE && n_peers > 0) return fail(B2S_ERR_UNSUPPORTED, "transform-only plans have no vote to merge");
+    p->peers.assign(peer_out, peer_out + n_peers);
+    p->peer_off = row_offset;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 extern "C" int b2s_ipc_export(void* dptr, void* handle64) {
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), dptr));
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), dptr));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 extern "C" int b2s_ipc_open(const void* handle64, void** dptr_out) {
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle64, sizeof(h));
-  CUDA_TRY(cudaIpcOpenMemHandle(dptr_out, h, cudaIpcMemLazyEnablePeerAccess));
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    CUDA_TRY(cudaIpcOpenMemHandle(dptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 extern "C" int b2s_ipc_close(void* dptr) {
-  CUDA_TRY(cudaIpcCloseMemHandle(dptr));
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    CUDA_TRY(cudaIpcCloseMemHandle(dptr));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 // ------------------------------------------------------------------------------------------ memory helpers
@@ -1778,8 +1876,12 @@ extern "C" void* b2s_alloc_pinned(size_t bytes) {
   return p;
 }
 extern "C" int b2s_free_pinned(void* p) {
-  CUDA_TRY(cudaFreeHost(p));
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    CUDA_TRY(cudaFreeHost(p));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 extern "C" void* b2s_device_alloc(size_t bytes) {
   void* p = nullptr;
@@ -1790,18 +1892,34 @@ extern "C" void* b2s_device_alloc(size_t bytes) {
   return p;
 }
 extern "C" int b2s_device_free(void* p) {
-  CUDA_TRY(cudaFree(p));
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    CUDA_TRY(cudaFree(p));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 extern "C" int b2s_memcpy_h2d(void* d, const void* h, size_t bytes) {
-  CUDA_TRY(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    CUDA_TRY(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 extern "C" int b2s_memcpy_d2h(void* h, const void* d, size_t bytes) {
-  CUDA_TRY(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    CUDA_TRY(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 extern "C" int b2s_device_sync(void) {
-  CUDA_TRY(cudaDeviceSynchronize());
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    CUDA_TRY(cudaDeviceSynchronize());
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }

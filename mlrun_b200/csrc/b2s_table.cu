@@ -12,6 +12,8 @@
 // query.
 #include <cuda_runtime.h>
 
+#include <exception>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -160,48 +162,52 @@ struct b2s_table_s {
 
 extern "C" int b2s_table_create(const int64_t* keys, int64_t n_keys, const float* values, int32_t n_features, const float* impute,
                                 b2s_table_t* out) {
-  if (!keys || !values || !out || n_keys <= 0 || n_features <= 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
-  if (!b2s_int_inited()) return b2s_int_fail(B2S_ERR_STATE, "b2s_init was not called (no CUDA device: there is no CPU fallback)");
-  uint64_t cap = 16;
-  while (cap < (uint64_t)n_keys * 2) cap <<= 1;
-  std::vector<Slot> slots(cap, Slot{0, -1});
-  for (int64_t i = 0; i < n_keys; ++i) {
-    uint64_t h = mix64((uint64_t)keys[i]) & (cap - 1);
-    while (slots[h].row >= 0) {
-      if (slots[h].key == keys[i]) return b2s_int_fail(B2S_ERR_INVALID, "duplicate entity key %lld (rows %lld and %lld)", (long long)keys[i], (long long)slots[h].row, (long long)i);
-      h = (h + 1) & (cap - 1);
+  try {  // no C++ exception crosses the C boundary
+    if (!keys || !values || !out || n_keys <= 0 || n_features <= 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+    if (!b2s_int_inited()) return b2s_int_fail(B2S_ERR_STATE, "b2s_init was not called (no CUDA device: there is no CPU fallback)");
+    uint64_t cap = 16;
+    while (cap < (uint64_t)n_keys * 2) cap <<= 1;
+    std::vector<Slot> slots(cap, Slot{0, -1});
+    for (int64_t i = 0; i < n_keys; ++i) {
+      uint64_t h = mix64((uint64_t)keys[i]) & (cap - 1);
+      while (slots[h].row >= 0) {
+        if (slots[h].key == keys[i]) return b2s_int_fail(B2S_ERR_INVALID, "duplicate entity key %lld (rows %lld and %lld)", (long long)keys[i], (long long)slots[h].row, (long long)i);
+        h = (h + 1) & (cap - 1);
+      }
+      slots[h] = Slot{keys[i], i};
     }
-    slots[h] = Slot{keys[i], i};
-  }
-  auto* t = new b2s_table_s();
-  t->n_keys = n_keys;
-  t->n_feat = n_features;
-  t->cap = cap;
-  TAB_TRY(cudaSetDevice(b2s_int_device()));
-  TAB_TRY(cudaMalloc(&t->d_slots, cap * sizeof(Slot)));
-  TAB_TRY(cudaMemcpy(t->d_slots, slots.data(), cap * sizeof(Slot), cudaMemcpyHostToDevice));
-  // one more row than keys: row n_keys is all NaN, what the fused gather copies for an unknown key
-  TAB_TRY(cudaMalloc(&t->d_values, ((size_t)n_keys + 1) * n_features * 4));
-  TAB_TRY(cudaMemcpy(t->d_values, values, (size_t)n_keys * n_features * 4, cudaMemcpyHostToDevice));
-  {
-    const std::vector<float> nan_row((size_t)n_features, NAN);
-    TAB_TRY(cudaMemcpy(t->d_values + (size_t)n_keys * n_features, nan_row.data(), (size_t)n_features * 4, cudaMemcpyHostToDevice));
-  }
-  std::vector<float> imp(((size_t)n_features + 3) / 4 * 4, NAN);
-  if (impute)
-    for (int c = 0; c < n_features; ++c) {
-      imp[c] = impute[c];
-      if (impute[c] == impute[c]) t->any_impute = 1;
+    auto* t = new b2s_table_s();
+    t->n_keys = n_keys;
+    t->n_feat = n_features;
+    t->cap = cap;
+    TAB_TRY(cudaSetDevice(b2s_int_device()));
+    TAB_TRY(cudaMalloc(&t->d_slots, cap * sizeof(Slot)));
+    TAB_TRY(cudaMemcpy(t->d_slots, slots.data(), cap * sizeof(Slot), cudaMemcpyHostToDevice));
+    // one more row than keys: row n_keys is all NaN, what the fused gather copies for an unknown key
+    TAB_TRY(cudaMalloc(&t->d_values, ((size_t)n_keys + 1) * n_features * 4));
+    TAB_TRY(cudaMemcpy(t->d_values, values, (size_t)n_keys * n_features * 4, cudaMemcpyHostToDevice));
+    {
+      const std::vector<float> nan_row((size_t)n_features, NAN);
+      TAB_TRY(cudaMemcpy(t->d_values + (size_t)n_keys * n_features, nan_row.data(), (size_t)n_features * 4, cudaMemcpyHostToDevice));
     }
-  t->h_impute = imp;
-  TAB_TRY(cudaMalloc(&t->d_impute, imp.size() * 4));
-  TAB_TRY(cudaMemcpy(t->d_impute, imp.data(), imp.size() * 4, cudaMemcpyHostToDevice));
-  int occ = 0;
-  TAB_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, table_lookup_kernel, 256, 0));
-  t->grid = b2s_int_sm_count() * std::max(occ, 1);
-  for (int i = 0; i < 4; ++i) TAB_TRY(cudaEventCreate(&t->ev[i]));
-  *out = t;
-  return B2S_OK;
+    std::vector<float> imp(((size_t)n_features + 3) / 4 * 4, NAN);
+    if (impute)
+      for (int c = 0; c < n_features; ++c) {
+        imp[c] = impute[c];
+        if (impute[c] == impute[c]) t->any_impute = 1;
+      }
+    t->h_impute = imp;
+    TAB_TRY(cudaMalloc(&t->d_impute, imp.size() * 4));
+    TAB_TRY(cudaMemcpy(t->d_impute, imp.data(), imp.size() * 4, cudaMemcpyHostToDevice));
+    int occ = 0;
+    TAB_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, table_lookup_kernel, 256, 0));
+    t->grid = b2s_int_sm_count() * std::max(occ, 1);
+    for (int i = 0; i < 4; ++i) TAB_TRY(cudaEventCreate(&t->ev[i]));
+    *out = t;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 static int launch_lookup(b2s_table_t t, const int64_t* d_keys, int64_t n, float* d_rows, int64_t row_stride, int32_t* d_found, cudaStream_t st) {
@@ -232,47 +238,55 @@ static int launch_lookup(b2s_table_t t, const int64_t* d_keys, int64_t n, float*
 
 extern "C" int b2s_table_lookup_device(b2s_table_t t, const int64_t* d_keys, int64_t n, float* d_rows, int64_t row_stride_bytes,
                                        int32_t* d_found, void* stream) {
-  if (!t) return b2s_int_fail(B2S_ERR_INVALID, "null table");
-  if (n < 0 || row_stride_bytes < (int64_t)t->n_feat * 4 || (row_stride_bytes & 3)) return b2s_int_fail(B2S_ERR_INVALID, "bad n / row stride");
-  if (n == 0) return B2S_OK;
-  TAB_TRY(cudaSetDevice(b2s_int_device()));
-  return launch_lookup(t, d_keys, n, d_rows, row_stride_bytes, d_found, stream ? (cudaStream_t)stream : b2s_int_stream());
+  try {  // no C++ exception crosses the C boundary
+    if (!t) return b2s_int_fail(B2S_ERR_INVALID, "null table");
+    if (n < 0 || row_stride_bytes < (int64_t)t->n_feat * 4 || (row_stride_bytes & 3)) return b2s_int_fail(B2S_ERR_INVALID, "bad n / row stride");
+    if (n == 0) return B2S_OK;
+    TAB_TRY(cudaSetDevice(b2s_int_device()));
+    return launch_lookup(t, d_keys, n, d_rows, row_stride_bytes, d_found, stream ? (cudaStream_t)stream : b2s_int_stream());
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_table_lookup_host(b2s_table_t t, const int64_t* keys, int64_t n, float* rows, int32_t* found, b2s_stats* stats) {
-  if (!t || !keys || !rows || n < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
-  if (n == 0) return B2S_OK;
-  std::lock_guard<std::mutex> lk(t->mu);
-  TAB_TRY(cudaSetDevice(b2s_int_device()));
-  if (n > t->cap_rows) {
-    if (t->d_keys) { cudaFree(t->d_keys); cudaFree(t->d_out); cudaFree(t->d_found); t->d_keys = nullptr; }
-    t->cap_rows = 0;
-    const int64_t cap = std::max<int64_t>(n, 4096);
-    TAB_TRY(cudaMalloc(&t->d_keys, cap * 8));
-    TAB_TRY(cudaMalloc(&t->d_out, (size_t)cap * t->n_feat * 4));
-    TAB_TRY(cudaMalloc(&t->d_found, cap * 4));
-    t->cap_rows = cap;
+  try {  // no C++ exception crosses the C boundary
+    if (!t || !keys || !rows || n < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+    if (n == 0) return B2S_OK;
+    std::lock_guard<std::mutex> lk(t->mu);
+    TAB_TRY(cudaSetDevice(b2s_int_device()));
+    if (n > t->cap_rows) {
+      if (t->d_keys) { cudaFree(t->d_keys); cudaFree(t->d_out); cudaFree(t->d_found); t->d_keys = nullptr; }
+      t->cap_rows = 0;
+      const int64_t cap = std::max<int64_t>(n, 4096);
+      TAB_TRY(cudaMalloc(&t->d_keys, cap * 8));
+      TAB_TRY(cudaMalloc(&t->d_out, (size_t)cap * t->n_feat * 4));
+      TAB_TRY(cudaMalloc(&t->d_found, cap * 4));
+      t->cap_rows = cap;
+    }
+    cudaStream_t st = b2s_int_stream();
+    const int64_t stride = (int64_t)t->n_feat * 4;
+    TAB_TRY(cudaEventRecord(t->ev[0], st));
+    TAB_TRY(cudaMemcpyAsync(t->d_keys, keys, n * 8, cudaMemcpyHostToDevice, st));
+    TAB_TRY(cudaEventRecord(t->ev[1], st));
+    if (int rc = launch_lookup(t, t->d_keys, n, t->d_out, stride, t->d_found, st)) return rc;
+    TAB_TRY(cudaEventRecord(t->ev[2], st));
+    TAB_TRY(cudaMemcpyAsync(rows, t->d_out, (size_t)n * stride, cudaMemcpyDeviceToHost, st));
+    if (found) TAB_TRY(cudaMemcpyAsync(found, t->d_found, n * 4, cudaMemcpyDeviceToHost, st));
+    TAB_TRY(cudaEventRecord(t->ev[3], st));
+    TAB_TRY(cudaStreamSynchronize(st));
+    if (stats) {
+      memset(stats, 0, sizeof(*stats));
+      stats->rows = n;
+      cudaEventElapsedTime(&stats->h2d_ms, t->ev[0], t->ev[1]);
+      cudaEventElapsedTime(&stats->kernel_ms, t->ev[1], t->ev[2]);
+      cudaEventElapsedTime(&stats->d2h_ms, t->ev[2], t->ev[3]);
+      stats->kernels = 1;
+    }
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  cudaStream_t st = b2s_int_stream();
-  const int64_t stride = (int64_t)t->n_feat * 4;
-  TAB_TRY(cudaEventRecord(t->ev[0], st));
-  TAB_TRY(cudaMemcpyAsync(t->d_keys, keys, n * 8, cudaMemcpyHostToDevice, st));
-  TAB_TRY(cudaEventRecord(t->ev[1], st));
-  if (int rc = launch_lookup(t, t->d_keys, n, t->d_out, stride, t->d_found, st)) return rc;
-  TAB_TRY(cudaEventRecord(t->ev[2], st));
-  TAB_TRY(cudaMemcpyAsync(rows, t->d_out, (size_t)n * stride, cudaMemcpyDeviceToHost, st));
-  if (found) TAB_TRY(cudaMemcpyAsync(found, t->d_found, n * 4, cudaMemcpyDeviceToHost, st));
-  TAB_TRY(cudaEventRecord(t->ev[3], st));
-  TAB_TRY(cudaStreamSynchronize(st));
-  if (stats) {
-    memset(stats, 0, sizeof(*stats));
-    stats->rows = n;
-    cudaEventElapsedTime(&stats->h2d_ms, t->ev[0], t->ev[1]);
-    cudaEventElapsedTime(&stats->kernel_ms, t->ev[1], t->ev[2]);
-    cudaEventElapsedTime(&stats->d2h_ms, t->ev[2], t->ev[3]);
-    stats->kernels = 1;
-  }
-  return B2S_OK;
 }
 
 static int launch_fused(b2s_table_t t, b2s_plan_t plan, const int64_t* d_keys, int64_t n, void* d_out, int32_t* d_status, cudaStream_t st) {
@@ -290,10 +304,14 @@ static int launch_fused(b2s_table_t t, b2s_plan_t plan, const int64_t* d_keys, i
 
 extern "C" int b2s_table_enrich_device(b2s_table_t t, b2s_plan_t plan, const int64_t* d_keys, int64_t n, void* d_out,
                                        int32_t* d_status, void* stream) {
-  if (!t || !plan || !d_keys || !d_out || n < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
-  if (n == 0) return B2S_OK;
-  TAB_TRY(cudaSetDevice(b2s_int_device()));
-  return launch_fused(t, plan, d_keys, n, d_out, d_status, stream ? (cudaStream_t)stream : b2s_int_stream());
+  try {  // no C++ exception crosses the C boundary
+    if (!t || !plan || !d_keys || !d_out || n < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+    if (n == 0) return B2S_OK;
+    TAB_TRY(cudaSetDevice(b2s_int_device()));
+    return launch_fused(t, plan, d_keys, n, d_out, d_status, stream ? (cudaStream_t)stream : b2s_int_stream());
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 static bool host_pinned(const void* ptr) {
@@ -305,135 +323,155 @@ static bool host_pinned(const void* ptr) {
 
 extern "C" int b2s_table_enrich_host(b2s_table_t t, b2s_plan_t plan, const int64_t* keys, int64_t n, void* out, int64_t out_bytes,
                                      int32_t* row_status, b2s_stats* stats) {
-  if (!t || !keys || !out || n < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
-  int n_in = 0, out_cols = 0;
-  if (int rc = b2s_int_plan_shape(plan, &n_in, &out_cols)) return rc;
-  if (n_in != t->n_feat) return b2s_int_fail(B2S_ERR_INVALID, "the table has %d features, the plan takes %d", t->n_feat, n_in);
-  if (out_bytes < n * out_cols * 4) return b2s_int_fail(B2S_ERR_INVALID, "out buffer too small");
-  if (n == 0) return B2S_OK;
-  std::lock_guard<std::mutex> lk(t->mu);
-  TAB_TRY(cudaSetDevice(b2s_int_device()));
-  const int64_t stride = (int64_t)t->n_feat * 4;
-  if (n > t->cap_rows) {
-    if (t->d_keys) { cudaFree(t->d_keys); cudaFree(t->d_out); cudaFree(t->d_found); t->d_keys = nullptr; }
-    t->cap_rows = 0;
-    const int64_t cap = std::max<int64_t>(n, 4096);
-    TAB_TRY(cudaMalloc(&t->d_keys, cap * 8));
-    TAB_TRY(cudaMalloc(&t->d_out, (size_t)cap * stride));
-    TAB_TRY(cudaMalloc(&t->d_found, cap * 4));
-    t->cap_rows = cap;
+  try {  // no C++ exception crosses the C boundary
+    if (!t || !keys || !out || n < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+    int n_in = 0, out_cols = 0;
+    if (int rc = b2s_int_plan_shape(plan, &n_in, &out_cols)) return rc;
+    if (n_in != t->n_feat) return b2s_int_fail(B2S_ERR_INVALID, "the table has %d features, the plan takes %d", t->n_feat, n_in);
+    if (out_bytes < n * out_cols * 4) return b2s_int_fail(B2S_ERR_INVALID, "out buffer too small");
+    if (n == 0) return B2S_OK;
+    std::lock_guard<std::mutex> lk(t->mu);
+    TAB_TRY(cudaSetDevice(b2s_int_device()));
+    const int64_t stride = (int64_t)t->n_feat * 4;
+    if (n > t->cap_rows) {
+      if (t->d_keys) { cudaFree(t->d_keys); cudaFree(t->d_out); cudaFree(t->d_found); t->d_keys = nullptr; }
+      t->cap_rows = 0;
+      const int64_t cap = std::max<int64_t>(n, 4096);
+      TAB_TRY(cudaMalloc(&t->d_keys, cap * 8));
+      TAB_TRY(cudaMalloc(&t->d_out, (size_t)cap * stride));
+      TAB_TRY(cudaMalloc(&t->d_found, cap * 4));
+      t->cap_rows = cap;
+    }
+    if (n > t->enr_rows || out_cols > t->enr_out_cols) {
+      if (t->d_votes) { cudaFree(t->d_votes); cudaFree(t->d_status); cudaFreeHost(t->h_pin); t->d_votes = nullptr; }
+      t->enr_rows = 0;
+      const int64_t cap = std::max<int64_t>(n, 4096);
+      const int32_t oc = std::max(out_cols, t->enr_out_cols);
+      TAB_TRY(cudaMalloc(&t->d_votes, (size_t)cap * oc * 4));
+      TAB_TRY(cudaMalloc(&t->d_status, cap * 4));
+      TAB_TRY(cudaMallocHost(&t->h_pin, (size_t)cap * (8 + (size_t)oc * 4 + 4)));
+      t->enr_rows = cap;
+      t->enr_out_cols = oc;
+    }
+    cudaStream_t st = b2s_int_stream();
+    int64_t* h_keys = (int64_t*)t->h_pin;
+    char* h_votes = t->h_pin + (size_t)t->enr_rows * 8;
+    int32_t* h_status = (int32_t*)(h_votes + (size_t)t->enr_rows * t->enr_out_cols * 4);
+    const size_t votes_sz = (size_t)n * out_cols * 4;
+    // pinned caller buffers are used as they are; pageable ones go through the pinned block (one host memcpy each way)
+    const void* k_src = keys;
+    if (!host_pinned(keys)) {
+      memcpy(h_keys, keys, (size_t)n * 8);
+      k_src = h_keys;
+    }
+    void* v_dst = host_pinned(out) ? out : (void*)h_votes;
+    int32_t* s_dst = row_status ? (host_pinned(row_status) ? row_status : h_status) : nullptr;
+    TAB_TRY(cudaEventRecord(t->ev[0], st));
+    TAB_TRY(cudaMemcpyAsync(t->d_keys, k_src, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    TAB_TRY(cudaEventRecord(t->ev[1], st));
+    int n_kernels = 1;
+    int rc = launch_fused(t, plan, t->d_keys, n, t->d_votes, t->d_status, st);  // gather inside the scoring kernel
+    if (rc == B2S_ERR_UNSUPPORTED) {  // plans the gather loader does not cover: gather, score, fold the flags (3 launches)
+      n_kernels = 3;
+      if ((rc = launch_lookup(t, t->d_keys, n, t->d_out, stride, t->d_found, st))) return rc;
+      if ((rc = b2s_run_device(plan, t->d_out, n, stride, t->d_votes, t->d_status, st))) return rc;
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(4 * b2s_int_sm_count(), (n + 255) / 256));
+      b2s_int_count_launches(1);
+      mark_unknown_kernel<<<grid, 256, 0, st>>>(t->d_found, t->d_status, n);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return b2s_int_fail(B2S_ERR_CUDA, "mark_unknown launch failed: %s", cudaGetErrorString(e));
+    } else if (rc) {
+      return rc;
+    }
+    TAB_TRY(cudaEventRecord(t->ev[2], st));
+    TAB_TRY(cudaMemcpyAsync(v_dst, t->d_votes, votes_sz, cudaMemcpyDeviceToHost, st));
+    if (s_dst) TAB_TRY(cudaMemcpyAsync(s_dst, t->d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    TAB_TRY(cudaEventRecord(t->ev[3], st));
+    TAB_TRY(cudaStreamSynchronize(st));
+    if (v_dst != out) memcpy(out, h_votes, votes_sz);
+    if (s_dst && s_dst != row_status) memcpy(row_status, h_status, (size_t)n * 4);
+    if (stats) {
+      memset(stats, 0, sizeof(*stats));
+      stats->rows = n;
+      cudaEventElapsedTime(&stats->h2d_ms, t->ev[0], t->ev[1]);
+      cudaEventElapsedTime(&stats->kernel_ms, t->ev[1], t->ev[2]);
+      cudaEventElapsedTime(&stats->d2h_ms, t->ev[2], t->ev[3]);
+      stats->kernels = n_kernels;  // 1: gather fused into the scoring kernel; 3: gather + the plan + mark_unknown
+      if (row_status)
+        for (int64_t r = 0; r < n; ++r) stats->nonfinite_rows += (row_status[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
+    }
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  if (n > t->enr_rows || out_cols > t->enr_out_cols) {
-    if (t->d_votes) { cudaFree(t->d_votes); cudaFree(t->d_status); cudaFreeHost(t->h_pin); t->d_votes = nullptr; }
-    t->enr_rows = 0;
-    const int64_t cap = std::max<int64_t>(n, 4096);
-    const int32_t oc = std::max(out_cols, t->enr_out_cols);
-    TAB_TRY(cudaMalloc(&t->d_votes, (size_t)cap * oc * 4));
-    TAB_TRY(cudaMalloc(&t->d_status, cap * 4));
-    TAB_TRY(cudaMallocHost(&t->h_pin, (size_t)cap * (8 + (size_t)oc * 4 + 4)));
-    t->enr_rows = cap;
-    t->enr_out_cols = oc;
-  }
-  cudaStream_t st = b2s_int_stream();
-  int64_t* h_keys = (int64_t*)t->h_pin;
-  char* h_votes = t->h_pin + (size_t)t->enr_rows * 8;
-  int32_t* h_status = (int32_t*)(h_votes + (size_t)t->enr_rows * t->enr_out_cols * 4);
-  const size_t votes_sz = (size_t)n * out_cols * 4;
-  // pinned caller buffers are used as they are; pageable ones go through the pinned block (one host memcpy each way)
-  const void* k_src = keys;
-  if (!host_pinned(keys)) {
-    memcpy(h_keys, keys, (size_t)n * 8);
-    k_src = h_keys;
-  }
-  void* v_dst = host_pinned(out) ? out : (void*)h_votes;
-  int32_t* s_dst = row_status ? (host_pinned(row_status) ? row_status : h_status) : nullptr;
-  TAB_TRY(cudaEventRecord(t->ev[0], st));
-  TAB_TRY(cudaMemcpyAsync(t->d_keys, k_src, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  TAB_TRY(cudaEventRecord(t->ev[1], st));
-  int n_kernels = 1;
-  int rc = launch_fused(t, plan, t->d_keys, n, t->d_votes, t->d_status, st);  // gather inside the scoring kernel
-  if (rc == B2S_ERR_UNSUPPORTED) {  // plans the gather loader does not cover: gather, score, fold the flags (3 launches)
-    n_kernels = 3;
-    if ((rc = launch_lookup(t, t->d_keys, n, t->d_out, stride, t->d_found, st))) return rc;
-    if ((rc = b2s_run_device(plan, t->d_out, n, stride, t->d_votes, t->d_status, st))) return rc;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(4 * b2s_int_sm_count(), (n + 255) / 256));
-    b2s_int_count_launches(1);
-    mark_unknown_kernel<<<grid, 256, 0, st>>>(t->d_found, t->d_status, n);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return b2s_int_fail(B2S_ERR_CUDA, "mark_unknown launch failed: %s", cudaGetErrorString(e));
-  } else if (rc) {
-    return rc;
-  }
-  TAB_TRY(cudaEventRecord(t->ev[2], st));
-  TAB_TRY(cudaMemcpyAsync(v_dst, t->d_votes, votes_sz, cudaMemcpyDeviceToHost, st));
-  if (s_dst) TAB_TRY(cudaMemcpyAsync(s_dst, t->d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  TAB_TRY(cudaEventRecord(t->ev[3], st));
-  TAB_TRY(cudaStreamSynchronize(st));
-  if (v_dst != out) memcpy(out, h_votes, votes_sz);
-  if (s_dst && s_dst != row_status) memcpy(row_status, h_status, (size_t)n * 4);
-  if (stats) {
-    memset(stats, 0, sizeof(*stats));
-    stats->rows = n;
-    cudaEventElapsedTime(&stats->h2d_ms, t->ev[0], t->ev[1]);
-    cudaEventElapsedTime(&stats->kernel_ms, t->ev[1], t->ev[2]);
-    cudaEventElapsedTime(&stats->d2h_ms, t->ev[2], t->ev[3]);
-    stats->kernels = n_kernels;  // 1: gather fused into the scoring kernel; 3: gather + the plan + mark_unknown
-    if (row_status)
-      for (int64_t r = 0; r < n; ++r) stats->nonfinite_rows += (row_status[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
-  }
-  return B2S_OK;
 }
 
 extern "C" int b2s_table_time_device(b2s_table_t t, const int64_t* const* d_keys, int32_t n_bufs, int64_t n, float* d_rows,
                                      int64_t row_stride_bytes, int32_t* d_found, int32_t n_iters, float* total_ms) {
-  if (!t || !d_keys || n_bufs <= 0 || n_iters <= 0 || !total_ms) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
-  TAB_TRY(cudaSetDevice(b2s_int_device()));
-  cudaStream_t st = b2s_int_stream();
-  std::lock_guard<std::mutex> lk(t->mu);
-  TAB_TRY(cudaEventRecord(t->ev[0], st));
-  for (int i = 0; i < n_iters; ++i)
-    if (int rc = launch_lookup(t, d_keys[i % n_bufs], n, d_rows, row_stride_bytes, d_found, st)) return rc;
-  TAB_TRY(cudaEventRecord(t->ev[1], st));
-  TAB_TRY(cudaStreamSynchronize(st));
-  TAB_TRY(cudaEventElapsedTime(total_ms, t->ev[0], t->ev[1]));
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!t || !d_keys || n_bufs <= 0 || n_iters <= 0 || !total_ms) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+    TAB_TRY(cudaSetDevice(b2s_int_device()));
+    cudaStream_t st = b2s_int_stream();
+    std::lock_guard<std::mutex> lk(t->mu);
+    TAB_TRY(cudaEventRecord(t->ev[0], st));
+    for (int i = 0; i < n_iters; ++i)
+      if (int rc = launch_lookup(t, d_keys[i % n_bufs], n, d_rows, row_stride_bytes, d_found, st)) return rc;
+    TAB_TRY(cudaEventRecord(t->ev[1], st));
+    TAB_TRY(cudaStreamSynchronize(st));
+    TAB_TRY(cudaEventElapsedTime(total_ms, t->ev[0], t->ev[1]));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_table_info(b2s_table_t t, int64_t* n_keys, int32_t* n_features, int64_t* capacity) {
-  if (!t) return b2s_int_fail(B2S_ERR_INVALID, "null table");
-  if (n_keys) *n_keys = t->n_keys;
-  if (n_features) *n_features = t->n_feat;
-  if (capacity) *capacity = (int64_t)t->cap;
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!t) return b2s_int_fail(B2S_ERR_INVALID, "null table");
+    if (n_keys) *n_keys = t->n_keys;
+    if (n_features) *n_features = t->n_feat;
+    if (capacity) *capacity = (int64_t)t->cap;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 extern "C" int b2s_table_destroy(b2s_table_t t) {
-  if (!t) return B2S_OK;
-  if (t->d_slots) cudaFree(t->d_slots);
-  if (t->d_values) cudaFree(t->d_values);
-  if (t->d_impute) cudaFree(t->d_impute);
-  if (t->d_keys) cudaFree(t->d_keys);
-  if (t->d_out) cudaFree(t->d_out);
-  if (t->d_found) cudaFree(t->d_found);
-  if (t->d_votes) cudaFree(t->d_votes);
-  if (t->d_status) cudaFree(t->d_status);
-  if (t->h_pin) cudaFreeHost(t->h_pin);
-  for (auto& e : t->ev)
-    if (e) cudaEventDestroy(e);
-  delete t;
-  return B2S_OK;
+  try {  // no C++ exception crosses the C boundary
+    if (!t) return B2S_OK;
+    if (t->d_slots) cudaFree(t->d_slots);
+    if (t->d_values) cudaFree(t->d_values);
+    if (t->d_impute) cudaFree(t->d_impute);
+    if (t->d_keys) cudaFree(t->d_keys);
+    if (t->d_out) cudaFree(t->d_out);
+    if (t->d_found) cudaFree(t->d_found);
+    if (t->d_votes) cudaFree(t->d_votes);
+    if (t->d_status) cudaFree(t->d_status);
+    if (t->h_pin) cudaFreeHost(t->h_pin);
+    for (auto& e : t->ev)
+      if (e) cudaEventDestroy(e);
+    delete t;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
 }
 
 // FNV-1a over each string of a packed buffer: the 64-bit entity key of a string-valued entity (host code)
 extern "C" int b2s_hash_strings(const char* bytes, const int64_t* offsets, int64_t n, int64_t* keys_out) {
-  if (!bytes || !offsets || !keys_out || n < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
-  for (int64_t i = 0; i < n; ++i) {
-    uint64_t h = 1469598103934665603ULL;
-    for (int64_t j = offsets[i]; j < offsets[i + 1]; ++j) {
-      h ^= (unsigned char)bytes[j];
-      h *= 1099511628211ULL;
+  try {  // no C++ exception crosses the C boundary
+    if (!bytes || !offsets || !keys_out || n < 0) return b2s_int_fail(B2S_ERR_INVALID, "bad arguments");
+    for (int64_t i = 0; i < n; ++i) {
+      uint64_t h = 1469598103934665603ULL;
+      for (int64_t j = offsets[i]; j < offsets[i + 1]; ++j) {
+        h ^= (unsigned char)bytes[j];
+        h *= 1099511628211ULL;
+      }
+      keys_out[i] = (int64_t)h;
     }
-    keys_out[i] = (int64_t)h;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return b2s_int_fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
-  return B2S_OK;
 }
