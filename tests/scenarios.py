@@ -1621,6 +1621,43 @@ def add_model_args(api):
     }
 
 
+def parallel_run_details(api):
+    """serving/routers.py:214-455 -- ParallelRun beyond the reference's own test: extend_event off (only the routes' results),
+    later routes overwriting earlier keys, a failing route under the array and the thread executors, input / result paths"""
+    ns = make_namespace(api)
+    ns["Echo"] = ns["ParEcho"]
+
+    def boom(event):
+        raise ValueError("route failed")
+
+    ns["boom"] = boom
+    out = {}
+
+    def call(server, body):
+        resp = server.test(body=body, silent=True)
+        if hasattr(resp, "status_code"):
+            text = resp.body if isinstance(resp.body, str) else (resp.body or b"").decode()
+            return {"status": resp.status_code, "text": _first_line(text)}
+        return _clean(resp)
+
+    for executor in ("array", "thread"):
+        fn = api.new_function("t", kind="serving")
+        graph = fn.set_topology("router", api.ParallelRun(executor_type=executor))
+        graph.add_route("c1", class_name="Echo", data={"a": 1, "k": "first"})
+        graph.add_route("c2", class_name="Echo", data={"c": 7, "k": "second"})
+        out[f"{executor}_plain"] = call(fn.to_mock_server(namespace=ns), {"x": 8})
+        fn = api.new_function("t", kind="serving")
+        graph = fn.set_topology("router", api.ParallelRun(executor_type=executor, extend_event=True))
+        graph.add_route("ok", class_name="Echo", data={"a": 1})
+        graph.add_route("bad", handler="boom")
+        out[f"{executor}_failing_route"] = call(fn.to_mock_server(namespace=ns), {"x": 1})
+    fn = api.new_function("t", kind="serving")
+    graph = fn.set_topology("router", api.ParallelRun(executor_type="array", extend_event=True, input_path="req", result_path="res"))
+    graph.add_route("c1", class_name="Echo", data={"a": 1})
+    out["paths"] = call(fn.to_mock_server(namespace=ns), {"req": {"x": 2}, "other": 3})
+    return out
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -2058,7 +2095,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
