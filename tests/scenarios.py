@@ -1658,6 +1658,46 @@ def parallel_run_details(api):
     return out
 
 
+def ensemble_odd_requests(api):
+    """serving/routers.py:457-991 + serving/v2_serving.py:228-371 -- a voting ensemble asked odd things: weights naming an
+    unknown model, an invalid vote type, bodies without a usable `inputs`, operations that do not exist, metadata / ready /
+    metrics paths of a child model"""
+    ns = make_namespace(api)
+    out = {}
+
+    def call(server, path, body, **kw):
+        resp = server.test(path, body, silent=True, **kw)
+        if hasattr(resp, "status_code"):
+            text = resp.body if isinstance(resp.body, str) else (resp.body or b"").decode()
+            return [resp.status_code, _first_line(text).split(" (event_id")[0]]
+        return _clean(resp)
+
+    def ensemble(**kw):
+        fn = api.new_function("e", kind="serving")
+        graph = fn.set_topology("router", api.VotingEnsemble(**kw))
+        graph.add_route("m1", class_name="ModelTestingClass", model_path=".", multiplier=1)
+        graph.add_route("m2", class_name="ModelTestingClass", model_path=".", multiplier=3)
+        return fn.to_mock_server(namespace=ns)
+
+    for tag, kw in (("weights_unknown_name", dict(vote_type="regression", weights={"m1": 0.7, "zz": 0.3})),
+                    ("bad_vote_type", dict(vote_type="banana"))):
+        try:
+            server = ensemble(**kw)
+            out[tag] = [call(server, "/v2/models/infer", {"inputs": [5]}), call(server, "/v2/models/", None, method="GET")]
+        except Exception as exc:  # noqa: BLE001
+            out[tag] = f"{type(exc).__name__}: {_first_line(exc)}"
+    server = ensemble(vote_type="regression")
+    out["no_inputs"] = call(server, "/v2/models/infer", {"x": 1})
+    out["inputs_not_list"] = call(server, "/v2/models/infer", {"inputs": 5})
+    out["empty_inputs"] = call(server, "/v2/models/infer", {"inputs": []})
+    out["explain_on_ensemble"] = call(server, "/v2/models/explain", {"inputs": [5]})
+    out["unknown_op"] = call(server, "/v2/models/m1/zzz", {"inputs": [5]})
+    out["get_on_model"] = call(server, "/v2/models/m1", None, method="GET")
+    out["ready"] = call(server, "/v2/models/m1/ready", None, method="GET")
+    out["metrics_path"] = call(server, "/v2/models/m1/metrics", None, method="GET")
+    return out
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -2095,7 +2135,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
