@@ -1698,6 +1698,71 @@ def ensemble_odd_requests(api):
     return out
 
 
+def flow_odd_cases(api):
+    """serving/states.py:564-599, 1292-1323 -- a sync flow in odd situations: a step returning None, a step terminating the
+    event, graph-level and step-level error handlers, nested input / result paths (present, missing, on a scalar body), a
+    responder in the middle, an empty flow"""
+    ns = dict(make_namespace(api))
+
+    def ret_none(x):
+        return None
+
+    def terminate(event):
+        event.terminated = True
+        event.body = {"stopped": event.body}
+        return event
+
+    def add_one(x):
+        return x + 1
+
+    def fail(x):
+        raise KeyError("bad key")
+
+    def catch(event):
+        return {"caught": str(event.error), "origin": event.origin_state, "body": event.body}
+
+    ns.update(ret_none=ret_none, terminate=terminate, add_one=add_one, fail=fail, catch=catch)
+
+    def run(build, body):
+        fn = api.new_function("f", kind="serving")
+        try:
+            build(fn.set_topology("flow", engine="sync"))
+            resp = fn.to_mock_server(namespace=ns).test(body=body, silent=True)
+        except Exception as exc:  # noqa: BLE001
+            return f"{type(exc).__name__}: {_first_line(exc)}"
+        if hasattr(resp, "status_code"):
+            text = resp.body if isinstance(resp.body, str) else (resp.body or b"").decode()
+            return [resp.status_code, _first_line(text)]
+        return _clean(resp)
+
+    def graph_handler(g):
+        g.to(name="a", handler="add_one").to(name="f", handler="fail").to(name="b", handler="add_one")
+        g.error_handler(name="catcher", handler="catch", full_event=True)
+
+    def step_handler(g):
+        g.to(name="a", handler="add_one").to(name="f", handler="fail").error_handler(
+            name="catcher", handler="catch", full_event=True).to(name="after", handler="(event)")
+
+    def paths(g):
+        g.to(name="a", handler="add_one", input_path="x.y", result_path="z.w")
+
+    return {
+        "none_result": run(lambda g: g.to(name="a", handler="add_one").to(name="n", handler="ret_none").to(name="b", handler="add_one"), 1),
+        "terminated": run(lambda g: g.to(name="a", handler="add_one").to(name="t", handler="terminate", full_event=True).to(
+            name="b", handler="add_one"), 1),
+        "graph_error_handler": run(graph_handler, 1),
+        "step_error_handler": run(step_handler, 1),
+        "nested_paths": run(paths, {"x": {"y": 4}}),
+        "nested_paths_missing": run(paths, {"x": {}}),
+        "result_path_on_scalar_body": run(lambda g: g.to(name="a", handler="add_one", result_path="r"), 5),
+        "respond_midway_sync": run(lambda g: g.to(name="a", handler="add_one").respond().to(name="b", handler="add_one"), 1),
+        "empty_flow": run(lambda g: None, 1),
+    }
+
+
+flow_odd_cases.EXPECT = {("terminated",): {"stopped": 2}, ("nested_paths",): {"x": {"y": 4}, "z": {"w": 5}}}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -2135,7 +2200,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
