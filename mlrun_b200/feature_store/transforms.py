@@ -79,7 +79,7 @@ class OneHotEncoder(_Step):
         super().__init__(**kwargs)
         for key, values in mapping.items():
             for val in values:
-                if isinstance(val, bool) or not (isinstance(val, (str, int)) or type(val).__module__ == "numpy" and "int" in type(val).__name__):
+                if not isinstance(val, (str, int, np.integer)):  # a bool is an int here too, as in the reference
                     raise MLRunInvalidArgumentError("For OneHotEncoder you must provide int or string mapping list")
             mapping[key] = list(dict.fromkeys(values))
         self.mapping = mapping
@@ -135,7 +135,7 @@ class MapValues(_Step):
         for label, bounds in fmap.get("ranges", {}).items() if "ranges" in fmap else ():
             lo = -math.inf if bounds[0] == "-inf" else bounds[0]
             hi = math.inf if bounds[1] == "inf" else bounds[1]
-            if lo <= value < hi:
+            if value >= lo and value < hi:  # operand order as upstream (same TypeError text for non-numbers)
                 return label
         return fmap.get(value, value)
 

@@ -166,7 +166,7 @@ class MapValues(StepToDict, MLRunStep):
         rules = self.mapping.get(feature, {})
         for label, pair in (rules.get("ranges", {}) if "ranges" in rules else {}).items():
             lo, hi = _bounds(pair)
-            if lo <= value < hi:
+            if value >= lo and value < hi:  # operand order as upstream: a non-number raises with the same text
                 return label
         return rules.get(value, value)
 

@@ -1763,6 +1763,43 @@ def flow_odd_cases(api):
 flow_odd_cases.EXPECT = {("terminated",): {"stopped": 2}, ("nested_paths",): {"x": {"y": 4}, "z": {"w": 5}}}
 
 
+def steps_odd_values(api):
+    """feature_store/steps.py:152-216, 377-513, 516-602, 699-735 on dict events with odd values: what counts as missing for
+    Imputer, bool / None / float values against OneHotEncoder categories, MapValues on None / strings / NaN, DateExtractor on
+    bad input, DropFeatures listing a feature twice"""
+    import pandas as pd
+
+    def run(make, ev):
+        try:
+            res = make().do(dict(ev))
+            return _clean({k: (None if v is pd.NaT else v) for k, v in res.items()})
+        except Exception as exc:  # noqa: BLE001
+            return f"{type(exc).__name__}: {_first_line(exc)}"
+
+    nan = float("nan")
+    return {
+        "imputer_kinds": run(lambda: api.Imputer(mapping={"a": 1, "b": 2, "c": 3, "d": 4, "e": 5}, default_value=9),
+                             {"a": None, "b": nan, "c": pd.NaT, "d": "nan", "e": np.float32("nan"), "f": np.nan, "g": 0, "h": ""}),
+        "imputer_none_default": run(lambda: api.Imputer(), {"a": None, "b": nan, "c": 1}),
+        "onehot_kinds": run(lambda: api.OneHotEncoder(mapping={"c": [0, 1, "x y-z", True]}), {"c": True, "k": 1}),
+        "onehot_none": run(lambda: api.OneHotEncoder(mapping={"c": [0, 1]}), {"c": None}),
+        "onehot_float_value": run(lambda: api.OneHotEncoder(mapping={"c": [0, 1, 2]}), {"c": 2.0}),
+        "onehot_missing_feature": run(lambda: api.OneHotEncoder(mapping={"zz": [0, 1]}), {"c": 1}),
+        "onehot_float_cats": run(lambda: api.OneHotEncoder(mapping={"c": [0.5, 1]}), {"c": 1}),
+        "map_missing_feature": run(lambda: api.MapValues(mapping={"zz": {1: 2}}), {"a": 1}),
+        "map_none_value": run(lambda: api.MapValues(mapping={"a": {None: 5, 1: 2}}), {"a": None}),
+        "map_range_on_string": run(lambda: api.MapValues(mapping={"a": {"ranges": {0: [0, 5]}}}), {"a": "text"}),
+        "map_range_nan": run(lambda: api.MapValues(mapping={"a": {"ranges": {0: ["-inf", "inf"]}}}), {"a": nan}),
+        "map_suffix": run(lambda: api.MapValues(mapping={"a": {1: 2}}, with_original_features=True, suffix="m"), {"a": 1, "b": 3}),
+        "date_bad": run(lambda: api.DateExtractor(parts=["hour"]), {"timestamp": "not a date"}),
+        "date_missing_col": run(lambda: api.DateExtractor(parts=["hour"], timestamp_col="when"), {"timestamp": "2021-01-01"}),
+        "date_parts": run(lambda: api.DateExtractor(parts=["year", "quarter", "is_leap_year", "day_of_year", "minute"]),
+                          {"timestamp": "2024-02-29 13:45:10"}),
+        "date_unknown_part": run(lambda: api.DateExtractor(parts=["fortnight"]), {"timestamp": "2024-02-29"}),
+        "drop_twice": run(lambda: api.DropFeatures(features=["a", "a"]), {"a": 1, "b": 2}),
+    }
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -2200,7 +2237,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, steps_odd_values, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
