@@ -242,7 +242,8 @@ class GraphServer(Serde):
         if get_body or isinstance(body, context.Response):
             return body
         if body and not isinstance(body, (str, bytes)):
-            return context.Response(body=json.dumps(body, default=_json_default), content_type="application/json", status_code=200)
+            # strict, as upstream (server.py:303-304): a numpy value in a response is a TypeError for the caller
+            return context.Response(body=json.dumps(body), content_type="application/json", status_code=200)
         return body
 
     def wait_for_completion(self):

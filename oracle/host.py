@@ -319,7 +319,7 @@ class GraphServer(ModelObj):
         if isinstance(body, context.Response) or get_body:
             return body
         if body and not isinstance(body, (str, bytes)):
-            body = json.dumps(body, default=_json_default)
+            body = json.dumps(body)  # strict, as upstream: a numpy value in the response is a TypeError for the caller
             return context.Response(body=body, content_type="application/json", status_code=200)
         return body
 

@@ -1800,6 +1800,59 @@ def steps_odd_values(api):
     }
 
 
+def model_numpy_outputs(api):
+    """serving/server.py:298-308 + serving/v2_serving.py:228-342 -- a model returning numpy values: fine for `server.test`
+    (the body object comes back), a TypeError on the wire (`GraphServer.run` json-encodes strictly); plus odd requests to a
+    model: GET on infer, a custom `op_` handler, an unknown version, a trailing slash, a body naming another model"""
+
+    class NpModel(api.V2ModelServer):
+        def load(self):
+            pass
+
+        def predict(self, request):
+            x = np.asarray(request["inputs"], dtype=np.float64)
+            return {"array": x * 2, "scalar": np.float32(x.sum()), "list_np": [np.int64(1), np.float64(2.5)],
+                    "nested": (x * 2).tolist(), "tuple": (1, 2)}[self.get_param("kind")]
+
+        def op_echo_headers(self, event):
+            return {"method": event.method, "path": event.path, "ct": event.content_type}
+
+    kinds = ("array", "scalar", "list_np", "nested", "tuple")
+    fn = api.new_function("m", kind="serving")
+    fn.set_topology("router")
+    for kind in kinds:
+        fn.add_model(kind, ".", class_name="NpModel", kind=kind)
+    server = fn.to_mock_server(namespace={"NpModel": NpModel})
+    out = {}
+
+    def call(path, body=None, **kw):
+        resp = server.test(path, body, silent=True, **kw)
+        if hasattr(resp, "status_code"):
+            text = resp.body if isinstance(resp.body, str) else (resp.body or b"").decode()
+            return [resp.status_code, _first_line(text)]
+        return _clean(resp)
+
+    for kind in kinds:
+        out[f"object_{kind}"] = call(f"/v2/models/{kind}/infer", {"inputs": [[1, 2], [3, 4]]})
+        try:
+            resp = server.run(api.MockEvent(body=json.dumps({"inputs": [[1, 2]]}), path=f"/v2/models/{kind}/infer"))
+            out[f"wire_{kind}"] = [resp.status_code, _clean(json.loads(resp.body))]
+        except Exception as exc:  # noqa: BLE001
+            out[f"wire_{kind}"] = f"raised {type(exc).__name__}: {_first_line(exc)}"
+    out["id_passthrough"] = server.test("/v2/models/nested/infer", {"id": "req-7", "inputs": [[1]]})["id"]
+    out["get_infer"] = call("/v2/models/nested/infer", None, method="GET")
+    out["custom_op"] = call("/v2/models/nested/echo_headers", {"x": 1}, content_type="application/json")
+    out["custom_op_get"] = call("/v2/models/nested/echo_headers", None, method="GET")
+    out["version_in_url_unknown"] = call("/v2/models/nested/versions/v9/infer", {"inputs": [[1]]})
+    out["trailing_slash"] = call("/v2/models/nested/infer/", {"inputs": [[1]]})
+    out["model_in_body_wrong_url"] = call("/v2/models/array/infer", {"model": "nested", "inputs": [[1]]})
+    return out
+
+
+model_numpy_outputs.EXPECT = {("wire_array",): "raised TypeError: Object of type ndarray is not JSON serializable",
+                              ("object_scalar", "outputs"): 10.0}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -2237,7 +2290,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, steps_odd_values, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, steps_odd_values, model_numpy_outputs, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
