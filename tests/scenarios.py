@@ -1853,6 +1853,55 @@ model_numpy_outputs.EXPECT = {("wire_array",): "raised TypeError: Object of type
                               ("object_scalar", "outputs"): 10.0}
 
 
+def vote_odd_predictions(api):
+    """serving/routers.py:708-810 -- the vote on odd child predictions: ties, float / negative / string / large labels, custom
+    and non-normalised weights, None and ragged predictions, vote-type inference from the first request's values"""
+
+    class Fixed(api.V2ModelServer):
+        def load(self):
+            pass
+
+        def predict(self, request):
+            return list(self.get_param("preds"))
+
+    def ens(preds_list, **kw):
+        fn = api.new_function("e", kind="serving")
+        graph = fn.set_topology("router", api.VotingEnsemble(**kw))
+        for i, preds in enumerate(preds_list):
+            graph.add_route(f"m{i}", class_name="Fixed", model_path=".", preds=preds)
+        try:
+            server = fn.to_mock_server(namespace={"Fixed": Fixed})
+            resp = server.test("/v2/models/infer", {"inputs": [[0]] * len(preds_list[0])}, silent=True)
+        except Exception as exc:  # noqa: BLE001
+            return f"raised {type(exc).__name__}: {_first_line(exc)}"
+        if hasattr(resp, "status_code"):
+            text = resp.body if isinstance(resp.body, str) else (resp.body or b"").decode()
+            return [resp.status_code, _first_line(text)]
+        return _clean(resp)["outputs"]
+
+    return {
+        "cls_basic": ens([[1, 2, 0], [1, 0, 0], [2, 2, 1]], vote_type="classification"),
+        "cls_tie_lowest": ens([[0, 3], [1, 2]], vote_type="classification"),
+        "cls_float_labels": ens([[1.0, 2.0], [1.0, 0.0], [0.0, 2.0]], vote_type="classification"),
+        "cls_negative": ens([[-1, 2], [1, 2]], vote_type="classification"),
+        "cls_weighted": ens([[0, 0], [1, 1], [1, 0]], vote_type="classification", weights={"m0": 0.6, "m1": 0.2, "m2": 0.2}),
+        "cls_strings": ens([["a", "b"], ["a", "a"]], vote_type="classification"),
+        "cls_big_labels": ens([[1000, 2], [1000, 3]], vote_type="classification"),
+        "reg_basic": ens([[1.0, 2.0], [3.0, 5.0]], vote_type="regression"),
+        "reg_ints": ens([[1, 2], [3, 5]], vote_type="regression"),
+        "reg_weights_not_one": ens([[1.0, 2.0], [3.0, 5.0]], vote_type="regression", weights={"m0": 2, "m1": 2}),
+        "reg_none": ens([[1.0, None], [3.0, 5.0]], vote_type="regression"),
+        "reg_single_model": ens([[4, 5]], vote_type="regression"),
+        "reg_ragged": ens([[1, 2], [1]], vote_type="regression"),
+        "inferred_from_ints": ens([[1, 2], [1, 0]]),
+        "inferred_from_floats": ens([[1.5, 2.0], [1.0, 0.0]]),
+        "inferred_from_integer_floats": ens([[1.0, 2.0], [1.0, 0.0]]),
+    }
+
+
+vote_odd_predictions.EXPECT = {("cls_tie_lowest",): [0, 2], ("reg_weights_not_one",): [8.0, 14.0], ("inferred_from_integer_floats",): [1, 0]}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -2290,7 +2339,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, steps_odd_values, model_numpy_outputs, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, steps_odd_values, model_numpy_outputs, vote_odd_predictions, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
