@@ -1902,6 +1902,31 @@ def vote_odd_predictions(api):
 vote_odd_predictions.EXPECT = {("cls_tie_lowest",): [0, 2], ("reg_weights_not_one",): [8.0, 14.0], ("inferred_from_integer_floats",): [1, 0]}
 
 
+def graph_serialisation(api):
+    """serving/states.py:89-154, 297-362, 940-1001 + runtimes/nuclio/serving.py:645-666 -- `to_dict` of a flow with paths,
+    a queue, a router inside the flow, an error handler and an `after` step; of a router topology; the keys of the serving
+    spec the function hands to the server"""
+    fn = api.new_function("f", kind="serving")
+    g = fn.set_topology("flow", engine="async")
+    s1 = g.to("Echo", "s1", input_path="a", result_path="b", full_event=True, custom=1)
+    queue = s1.to("$queue", "q1", path="v3io:///x", shards=2)
+    router = queue.to("*", "router", function="child")
+    router.add_route("m1", class_name="ModelTestingClass", model_path=".", multiplier=2)
+    router.add_route("m2:v3", handler="my_hnd")
+    router.to(name="post", handler="json.dumps").respond()
+    s1.error_handler(name="eh", class_name="EchoError", full_event=True)
+    g.add_step(name="side", handler="(event)", after="s1")
+    out = {"flow": g.to_dict(), "step_order": list(g.steps.keys())}
+    fn2 = api.new_function("r", kind="serving")
+    rt = fn2.set_topology("router", "mlrun.serving.ModelRouter", url_prefix="/x")
+    rt.add_route("a", class_name="ModelTestingClass", model_path=".", multiplier=1)
+    out["router"] = rt.to_dict()
+    spec = json.loads(fn._get_serving_spec())
+    out["serving_spec_keys"] = sorted(spec.keys())
+    out["serving_spec_graph_is_to_dict"] = spec["graph"] == json.loads(json.dumps(out["flow"], default=str))
+    return json.loads(json.dumps(out, default=str))
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -2339,7 +2364,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, steps_odd_values, model_numpy_outputs, vote_odd_predictions, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, steps_odd_values, model_numpy_outputs, vote_odd_predictions, graph_serialisation, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
