@@ -194,3 +194,33 @@ def test_served_flow_fuzz_product_on_the_emulated_plan_against_the_oracle_server
                     np.testing.assert_allclose(gv, wv, rtol=RTOL, atol=ATOL)
 
     run()
+
+
+def test_wire_responses_of_device_servers_are_plain_json():
+    """GraphServer.run json-encodes strictly (serving/server.py:303-304): what the device model servers and the routers put
+    in a response must be plain Python numbers -- and equal the oracle's wire response but for id / timestamp"""
+    from tests import api_oracle
+
+    def wire(server, api, body, path):
+        resp = server.run(api.MockEvent(body=body, path=path))
+        assert resp.status_code == 200 and resp.content_type == "application/json"
+        data = json.loads(resp.body)
+        return {k: v for k, v in data.items() if k not in ("id", "timestamp")}
+
+    for n_models in (1, 4):
+        wl = flow3_workload(n_rows=8, n_num=56, n_cat=8, seed=9, n_models=n_models)
+        path = "/" if n_models == 1 else "/v2/models/infer"
+        body = json.dumps(wl.rows_as_dicts(limit=1)[0])
+        got, want = wire(wl.build_server(api_b200), api_b200, body, path), wire(wl.build_server(api_oracle), api_oracle, body, path)
+        assert list(got) == list(want) and got["model_name"] == want["model_name"]
+        np.testing.assert_allclose(got["outputs"], want["outputs"], rtol=RTOL, atol=ATOL)
+    for kind in ("regression", "classification"):
+        tw = tree_workload(n_rows=8, n_feat=24, n_models=4, n_trees=5, depth=3, seed=6, n_fit=300, kind=kind)
+        body = json.dumps({"inputs": tw.X[:3].astype(np.float64).tolist()})
+        for path in ("/v2/models/infer", "/v2/models/m2/infer"):
+            got, want = wire(tw.build_server(api_b200), api_b200, body, path), wire(tw.build_server(api_oracle), api_oracle, body, path)
+            assert list(got) == list(want)
+            if kind == "classification":
+                assert got["outputs"] == want["outputs"]
+            else:
+                np.testing.assert_allclose(got["outputs"], want["outputs"], rtol=RTOL, atol=ATOL)
