@@ -1927,6 +1927,49 @@ def graph_serialisation(api):
     return json.loads(json.dumps(out, default=str))
 
 
+def router_and_model_paths(api):
+    """serving/routers.py:86-211 + serving/v2_serving.py:228-342 + serving/states.py:564-599 -- input / result paths on a
+    router and on a model route, and a router in the middle of a sync flow addressed through the flow (model urls, the
+    default route, the model list, a foreign prefix)"""
+    ns = make_namespace(api)
+
+    def call(server, path, body, **kw):
+        resp = server.test(path, body, silent=True, **kw)
+        if hasattr(resp, "status_code"):
+            text = resp.body if isinstance(resp.body, str) else (resp.body or b"").decode()
+            return [resp.status_code, _first_line(text)]
+        return _clean(resp)
+
+    out = {}
+    fn = api.new_function("r", kind="serving")
+    graph = fn.set_topology("router", api.ModelRouter(input_path="req", result_path="res"))
+    graph.add_route("m1", class_name="ModelTestingClass", model_path=".", multiplier=2)
+    server = fn.to_mock_server(namespace=ns)
+    out["router_paths"] = call(server, "/v2/models/m1/infer", {"req": {"inputs": [5]}, "keep": 1})
+    out["router_paths_missing"] = call(server, "/v2/models/m1/infer", {"inputs": [5]})
+    fn = api.new_function("r", kind="serving")
+    graph = fn.set_topology("router")
+    graph.add_route("m1", class_name="ModelTestingClass", model_path=".", multiplier=2, input_path="a.b", result_path="out")
+    server = fn.to_mock_server(namespace=ns)
+    out["model_paths"] = call(server, "/v2/models/m1/infer", {"a": {"b": {"inputs": [4]}}, "z": 0})
+    out["model_meta"] = call(server, "/v2/models/m1", None, method="GET")
+    fn = api.new_function("f", kind="serving")
+    flow = fn.set_topology("flow", engine="sync")
+    router = flow.to("Echo", "pre").to("*", "router")
+    router.add_route("m1", class_name="ModelTestingClass", model_path=".", multiplier=3)
+    router.add_route("m2", class_name="ModelTestingClass", model_path=".", multiplier=5)
+    router.to("Echo", "post").respond()
+    server = fn.to_mock_server(namespace=ns)
+    out["flow_router_m2"] = call(server, "/v2/models/m2/infer", {"inputs": [2]})
+    out["flow_router_default"] = call(server, "/", {"inputs": [2]})
+    out["flow_router_list"] = call(server, "/v2/models/", None, method="GET")
+    out["flow_router_bad_prefix"] = call(server, "/other/m1/infer", {"inputs": [2]})
+    return out
+
+
+router_and_model_paths.EXPECT = {("router_paths", "res", "outputs"): 10, ("flow_router_default", "outputs"): 6}
+
+
 def merger_logic(api):
     """serving/merger.py:36-156 -- the join itself, driven directly: post_init, then a sequence of arrivals through
     `_merge_events` (full events joined on event.id with a window of 3 keys; bodies joined on a key expression)"""
@@ -2364,7 +2407,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, steps_odd_values, model_numpy_outputs, vote_odd_predictions, graph_serialisation, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, steps_odd_values, model_numpy_outputs, vote_odd_predictions, graph_serialisation, router_and_model_paths, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
