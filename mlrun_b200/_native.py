@@ -6,8 +6,10 @@ that every symbol of the header is exported).
 """
 
 import ctypes as C
+import collections
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -235,11 +237,17 @@ def pinned_empty(shape, dtype=np.float32):
         raise NativeError("pinned alloc failed")
     buf = (C.c_char * max(nbytes, 1)).from_address(ptr)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    _PINNED[id(buf)] = (buf, ptr)
+    # the block goes back to the driver when the last array over it is collected (arrays keep `buf` alive as their base)
+    weakref.finalize(buf, _free_pinned, ptr)
     return arr
 
 
-_PINNED = {}
+def _free_pinned(ptr):
+    try:
+        if _lib is not None:
+            _lib.b2s_free_pinned(ptr)
+    except Exception:
+        pass
 
 
 class _Lease:
@@ -249,8 +257,10 @@ class _Lease:
         self.pool, self.ptr, self.size = pool, ptr, size
 
     def __del__(self):
+        # may run inside a garbage-collection pass triggered while take() holds the pool lock on this very thread:
+        # only append to a deque here (atomic, lock free); take() drains it
         try:
-            self.pool._give_back(self.ptr, self.size)
+            self.pool._returned.append((self.ptr, self.size))
         except Exception:
             pass
 
@@ -264,11 +274,13 @@ class PinnedPool:
         self.max_blocks, self.granule = max_blocks, granule
         self._free = {}
         self._n = 0
-        self._mu = threading.Lock()
+        self._mu = threading.RLock()
+        self._returned = collections.deque()  # blocks whose arrays died (filled by _Lease.__del__ without the lock)
 
     def take(self, nbytes):
         size = max(self.granule, (int(nbytes) + self.granule - 1) // self.granule * self.granule)
         with self._mu:
+            self._drain()
             ptrs = self._free.get(size)
             ptr = ptrs.pop() if ptrs else None
             if ptr is None:
@@ -286,9 +298,16 @@ class PinnedPool:
         buf._lease = _Lease(self, ptr, size)
         return buf
 
-    def _give_back(self, ptr, size):
-        with self._mu:
+    def _drain(self):
+        while True:
+            try:
+                ptr, size = self._returned.popleft()
+            except IndexError:
+                return
             self._free.setdefault(size, []).append(ptr)
+
+    def _give_back(self, ptr, size):
+        self._returned.append((ptr, size))
 
 
 PINNED = PinnedPool()

@@ -110,6 +110,8 @@ struct Slot {  // one in-flight batch of the coalescing ring
   std::chrono::steady_clock::time_point first_submit;
   b2s_stats stats{};
   int waiters = 0;      // tickets issued on this batch not yet collected
+  int err = 0;          // b2s_status of the batch (a failed copy / launch): every ticket of the batch gets it
+  std::string err_msg;
 };
 
 struct b2s_plan_s {
@@ -1443,13 +1445,19 @@ int b2s_int_launch_gathered(b2s_plan_s* p, const B2SGather& g, long long n, void
 
 static int ensure_stage(b2s_plan_t p, int64_t n_rows) {
   if (n_rows <= p->stage_rows) return B2S_OK;
-  if (p->h_stage_in) {
-    cudaFreeHost(p->h_stage_in);
-    cudaFreeHost(p->h_stage_out);
-    cudaFree(p->d_stage_in);
-    cudaFree(p->d_stage_out);
-    cudaFree(p->d_stage_status);
-  }
+  // free first, and forget the old buffers before anything can fail: a failed allocation below must leave the plan
+  // with no staging area (stage_rows = 0) rather than with dangling pointers a later call would copy into / free twice
+  if (p->h_stage_in) cudaFreeHost(p->h_stage_in);
+  if (p->h_stage_out) cudaFreeHost(p->h_stage_out);
+  if (p->d_stage_in) cudaFree(p->d_stage_in);
+  if (p->d_stage_out) cudaFree(p->d_stage_out);
+  if (p->d_stage_status) cudaFree(p->d_stage_status);
+  p->h_stage_in = nullptr;
+  p->h_stage_out = nullptr;
+  p->d_stage_in = nullptr;
+  p->d_stage_out = nullptr;
+  p->d_stage_status = nullptr;
+  p->stage_rows = 0;
   const int64_t cap = std::max<int64_t>(n_rows, 4096);
   CUDA_TRY(cudaMallocHost(&p->h_stage_in, (size_t)cap * p->n_in * 4));
   CUDA_TRY(cudaMallocHost(&p->h_stage_out, (size_t)cap * (p->out_cols + 1) * 4));
@@ -1635,49 +1643,101 @@ static void dispatcher_main(b2s_plan_s* p) {
     cudaStream_t st = p->ring_stream;
     const int64_t row_bytes = (int64_t)p->n_in * 4;
     const size_t out_sz = (size_t)rows * p->out_cols * 4;
-    cudaEventRecord(s.e0, st);
-    cudaMemcpyAsync(s.d_in, s.h_in, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st);
-    cudaEventRecord(s.e1, st);
-    launch_on(p, s.d_in, rows, row_bytes, s.d_out, s.d_status, st);
-    cudaEventRecord(s.e2, st);
-    cudaMemcpyAsync(s.h_out, s.d_out, out_sz, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(s.h_out + (size_t)p->ring_cap * p->out_cols * 4, s.d_status, (size_t)rows * 4, cudaMemcpyDeviceToHost, st);
-    cudaEventRecord(s.e3, st);
-    cudaEventSynchronize(s.e3);
+    // every step is checked: a batch whose copy or launch failed is reported to all of its tickets (b2s_wait returns
+    // the error and copies nothing) instead of handing out whatever an earlier batch left in the pinned slot
+    int err = 0;
+    std::string err_msg;
+    auto step = [&](cudaError_t e, const char* what) {
+      if (e != cudaSuccess && !err) {
+        err = B2S_ERR_CUDA;
+        err_msg = std::string("coalesced batch: ") + what + ": " + cudaGetErrorString(e);
+      }
+    };
+    step(cudaEventRecord(s.e0, st), "event record");
+    step(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st), "H2D copy");
+    step(cudaEventRecord(s.e1, st), "event record");
+    if (!err) {
+      const int rc = launch_on(p, s.d_in, rows, row_bytes, s.d_out, s.d_status, st);
+      if (rc) {
+        err = rc;
+        err_msg = std::string("coalesced batch: ") + g_err;
+      }
+    }
+    step(cudaEventRecord(s.e2, st), "event record");
+    if (!err) {
+      step(cudaMemcpyAsync(s.h_out, s.d_out, out_sz, cudaMemcpyDeviceToHost, st), "D2H copy");
+      step(cudaMemcpyAsync(s.h_out + (size_t)p->ring_cap * p->out_cols * 4, s.d_status, (size_t)rows * 4, cudaMemcpyDeviceToHost, st), "D2H copy");
+    }
+    step(cudaEventRecord(s.e3, st), "event record");
+    step(cudaEventSynchronize(s.e3), "execution");
     b2s_stats stt{};
     stt.rows = rows;
-    cudaEventElapsedTime(&stt.h2d_ms, s.e0, s.e1);
-    cudaEventElapsedTime(&stt.kernel_ms, s.e1, s.e2);
-    cudaEventElapsedTime(&stt.d2h_ms, s.e2, s.e3);
+    if (!err) {
+      cudaEventElapsedTime(&stt.h2d_ms, s.e0, s.e1);
+      cudaEventElapsedTime(&stt.kernel_ms, s.e1, s.e2);
+      cudaEventElapsedTime(&stt.d2h_ms, s.e2, s.e3);
+    } else {
+      cudaGetLastError();  // the error is reported through the tickets
+    }
     stt.queue_us = queue_us;
     stt.kernels = p->kernels_per_batch;
     lk.lock();
     s.stats = stt;
+    s.err = err;
+    s.err_msg = err_msg;
     s.state = 3;
     p->cv_done.notify_all();
   }
 }
 
+static void ring_free_slot(Slot& s) {
+  if (s.h_in) cudaFreeHost(s.h_in);
+  if (s.h_out) cudaFreeHost(s.h_out);
+  if (s.d_in) cudaFree(s.d_in);
+  if (s.d_out) cudaFree(s.d_out);
+  if (s.d_status) cudaFree(s.d_status);
+  for (cudaEvent_t e : {s.e0, s.e1, s.e2, s.e3})
+    if (e) cudaEventDestroy(e);
+  s = Slot{};
+}
+
 static int ring_start(b2s_plan_s* p) {
   if (!p->slots.empty()) return B2S_OK;
   CUDA_TRY(cudaSetDevice(G.device));
-  p->ring_cap = G.max_batch;
-  p->slots.resize(G.ring_slots);
+  // built aside and committed only when everything (buffers, events, stream, dispatcher) exists: a failure leaves the
+  // plan without a ring, so the next submit retries instead of queueing rows nobody will ever dispatch
+  const int64_t cap = G.max_batch;
+  std::vector<Slot> slots(G.ring_slots);
+  cudaStream_t stream = nullptr;
   const int64_t row_bytes = (int64_t)p->n_in * 4;
-  for (auto& s : p->slots) {
-    CUDA_TRY(cudaMallocHost(&s.h_in, (size_t)p->ring_cap * row_bytes));
-    CUDA_TRY(cudaMallocHost(&s.h_out, (size_t)p->ring_cap * (p->out_cols + 1) * 4));
-    CUDA_TRY(cudaMalloc(&s.d_in, (size_t)p->ring_cap * row_bytes));
-    CUDA_TRY(cudaMalloc(&s.d_out, (size_t)p->ring_cap * p->out_cols * 4));
-    CUDA_TRY(cudaMalloc(&s.d_status, (size_t)p->ring_cap * 4));
-    CUDA_TRY(cudaEventCreate(&s.e0));
-    CUDA_TRY(cudaEventCreate(&s.e1));
-    CUDA_TRY(cudaEventCreate(&s.e2));
-    CUDA_TRY(cudaEventCreate(&s.e3));
+  cudaError_t e = cudaSuccess;
+  auto ok = [&](cudaError_t r) { return e == cudaSuccess && (e = r) == cudaSuccess; };
+  for (auto& s : slots) {
+    if (!(ok(cudaMallocHost(&s.h_in, (size_t)cap * row_bytes)) && ok(cudaMallocHost(&s.h_out, (size_t)cap * (p->out_cols + 1) * 4)) &&
+          ok(cudaMalloc(&s.d_in, (size_t)cap * row_bytes)) && ok(cudaMalloc(&s.d_out, (size_t)cap * p->out_cols * 4)) &&
+          ok(cudaMalloc(&s.d_status, (size_t)cap * 4)) && ok(cudaEventCreate(&s.e0)) && ok(cudaEventCreate(&s.e1)) &&
+          ok(cudaEventCreate(&s.e2)) && ok(cudaEventCreate(&s.e3))))
+      break;
   }
-  CUDA_TRY(cudaStreamCreateWithFlags(&p->ring_stream, cudaStreamNonBlocking));
+  if (e == cudaSuccess) ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  if (e != cudaSuccess) {
+    for (auto& s : slots) ring_free_slot(s);
+    cudaGetLastError();
+    return fail(B2S_ERR_CUDA, "coalescing ring of %d x %lld rows: %s", G.ring_slots, (long long)cap, cudaGetErrorString(e));
+  }
+  p->ring_cap = cap;
+  p->slots = std::move(slots);
+  p->ring_stream = stream;
   p->stop = false;
-  p->dispatcher = std::thread(dispatcher_main, p);
+  try {
+    p->dispatcher = std::thread(dispatcher_main, p);
+  } catch (const std::exception& ex) {
+    for (auto& s : p->slots) ring_free_slot(s);
+    p->slots.clear();
+    cudaStreamDestroy(p->ring_stream);
+    p->ring_stream = nullptr;
+    return fail(B2S_ERR_STATE, "coalescing ring: cannot start the dispatcher thread: %s", ex.what());
+  }
   return B2S_OK;
 }
 
@@ -1759,23 +1819,32 @@ extern "C" int b2s_wait(b2s_plan_t p, uint64_t ticket, void* out, int64_t out_by
     if (it == p->batch_slot.end()) return fail(B2S_ERR_INVALID, "unknown ticket");
     Slot& s = p->slots[it->second];
     p->cv_done.wait(lk, [&] { return s.state == 3 && s.batch_id == batch; });
-    if (off + n_rows > s.rows) return fail(B2S_ERR_INVALID, "ticket range exceeds its batch");
-    memcpy(out, s.h_out + (size_t)off * p->out_cols * 4, (size_t)n_rows * p->out_cols * 4);
-    const int32_t* hs = (const int32_t*)(s.h_out + (size_t)p->ring_cap * p->out_cols * 4) + off;
-    if (row_status) memcpy(row_status, hs, (size_t)n_rows * 4);
-    if (stats) {
-      *stats = s.stats;
-      int bad = 0;
-      for (int64_t r = 0; r < n_rows; ++r) bad += (hs[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
-      stats->nonfinite_rows = bad;
+    // the batch is done: whatever this call returns, the ticket is spent and the last one recycles the slot
+    int rc = B2S_OK;
+    if (s.err) {
+      rc = fail(s.err, "%s", s.err_msg.c_str());
+    } else if (off + n_rows > s.rows) {
+      rc = fail(B2S_ERR_INVALID, "ticket range exceeds its batch");
+    } else {
+      memcpy(out, s.h_out + (size_t)off * p->out_cols * 4, (size_t)n_rows * p->out_cols * 4);
+      const int32_t* hs = (const int32_t*)(s.h_out + (size_t)p->ring_cap * p->out_cols * 4) + off;
+      if (row_status) memcpy(row_status, hs, (size_t)n_rows * 4);
+      if (stats) {
+        *stats = s.stats;
+        int bad = 0;
+        for (int64_t r = 0; r < n_rows; ++r) bad += (hs[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
+        stats->nonfinite_rows = bad;
+      }
     }
     if (--s.waiters == 0) {  // last collector frees the slot
       p->batch_slot.erase(it);
       s.rows = 0;
       s.state = 0;
+      s.err = 0;
+      s.err_msg.clear();
       p->cv_free.notify_all();
     }
-    return B2S_OK;
+    return rc;
   } catch (const std::exception& e) {
     return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
@@ -1792,25 +1861,13 @@ extern "C" int b2s_plan_destroy(b2s_plan_t p) {
       }
       p->dispatcher.join();
     }
-    for (auto& s : p->slots) {
-      cudaFreeHost(s.h_in);
-      cudaFreeHost(s.h_out);
-      cudaFree(s.d_in);
-      cudaFree(s.d_out);
-      cudaFree(s.d_status);
-      cudaEventDestroy(s.e0);
-      cudaEventDestroy(s.e1);
-      cudaEventDestroy(s.e2);
-      cudaEventDestroy(s.e3);
-    }
+    for (auto& s : p->slots) ring_free_slot(s);
     if (p->ring_stream) cudaStreamDestroy(p->ring_stream);
-    if (p->h_stage_in) {
-      cudaFreeHost(p->h_stage_in);
-      cudaFreeHost(p->h_stage_out);
-      cudaFree(p->d_stage_in);
-      cudaFree(p->d_stage_out);
-      cudaFree(p->d_stage_status);
-    }
+    if (p->h_stage_in) cudaFreeHost(p->h_stage_in);
+    if (p->h_stage_out) cudaFreeHost(p->h_stage_out);
+    if (p->d_stage_in) cudaFree(p->d_stage_in);
+    if (p->d_stage_out) cudaFree(p->d_stage_out);
+    if (p->d_stage_status) cudaFree(p->d_stage_status);
     for (int i = 0; i < 4; ++i)
       if (p->ev[i]) cudaEventDestroy(p->ev[i]);
     for (cudaEvent_t e : p->chunk_ev) cudaEventDestroy(e);

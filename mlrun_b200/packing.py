@@ -46,14 +46,34 @@ def _int_classes(classes):
     return classes.astype(np.int32)
 
 
+# Estimators whose predict() is exactly  X @ coef_.T + intercept_  followed by identity / "> 0" / argmax.  Anything
+# else that happens to carry coef_ (GLMs with a log link, SVC(kernel="linear") with its one-vs-one rows, PLS with its
+# centring ...) would be exported with the wrong arithmetic, so the export goes by class name, as pack_trees does.
+LINEAR_REGRESSORS = frozenset({
+    "LinearRegression", "Ridge", "RidgeCV", "Lasso", "LassoCV", "ElasticNet", "ElasticNetCV", "Lars", "LarsCV",
+    "LassoLars", "LassoLarsCV", "LassoLarsIC", "OrthogonalMatchingPursuit", "OrthogonalMatchingPursuitCV",
+    "BayesianRidge", "ARDRegression", "SGDRegressor", "HuberRegressor", "TheilSenRegressor",
+    "PassiveAggressiveRegressor", "LinearSVR", "QuantileRegressor",
+})
+LINEAR_CLASSIFIERS = frozenset({
+    "LogisticRegression", "LogisticRegressionCV", "SGDClassifier", "Perceptron", "PassiveAggressiveClassifier",
+    "RidgeClassifier", "RidgeClassifierCV", "LinearSVC", "LinearDiscriminantAnalysis",
+})
+
+
 def pack_linear(model):
     """-> dict(W (K,F) f64, b (K,), link, classes)"""
     name = type(model).__name__
+    if name not in LINEAR_REGRESSORS and name not in LINEAR_CLASSIFIERS:
+        raise UnsupportedModel(
+            f"{name} is not a plain linear estimator (predict != X @ coef_.T + intercept_ with identity / >0 / argmax)")
     if not hasattr(model, "coef_"):
         raise UnsupportedModel(f"{name} has no coef_")
+    if name in LINEAR_CLASSIFIERS and not hasattr(model, "classes_"):
+        raise UnsupportedModel(f"{name} has no classes_")
     coef = np.asarray(model.coef_, dtype=np.float64)
     intercept = np.atleast_1d(np.asarray(model.intercept_, dtype=np.float64))
-    if hasattr(model, "classes_"):  # linear classifier
+    if name in LINEAR_CLASSIFIERS:
         classes = _int_classes(model.classes_)
         W = np.atleast_2d(coef)
         if W.shape[0] == 1:
@@ -159,8 +179,11 @@ def pack_trees(model):
 
 def pack_model(model):
     """-> ("linear", dict) | ("trees", PackedTrees)"""
-    if hasattr(model, "coef_"):
-        return "linear", pack_linear(model)
+    name = type(model).__name__
+    if name in LINEAR_REGRESSORS or name in LINEAR_CLASSIFIERS:
+        packed = pack_linear(model)
+        packed["n_features"] = int(packed["W"].shape[1])
+        return "linear", packed
     if hasattr(model, "estimators_") or hasattr(model, "tree_"):
         packed = pack_trees(model)
         packed.n_features = int(getattr(model, "n_features_in_", 0)) or None  # the width predict() checks its input against

@@ -63,6 +63,12 @@ class PickleModelServer(V2ModelServer):
         return self._packed
 
     def _own_plan(self, n_features):
+        kind, packed = self.packed
+        want = packed.get("n_features") if kind == "linear" else getattr(packed, "n_features", None)
+        if want and int(want) != int(n_features):
+            # scikit-learn's predict -> validate_data raises this for a width mismatch (extra columns included)
+            raise ValueError(f"X has {n_features} features, but {type(self.model).__name__} is expecting {want} "
+                             "features as input.")
         if self._plan is None or self._plan.n_in != n_features:
             self._plan = ColumnProgram([f"f{i}" for i in range(n_features)]).build_plan([self.packed])
         return self._plan

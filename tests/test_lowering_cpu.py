@@ -277,3 +277,49 @@ def test_event_packing_and_responses_of_the_batched_path():
     assert res[2].status_code == 400 and res[2].body.startswith("ValueError")
     labels = CompiledGraph(None, None, names, ("clf", None)).responses(np.array([[2], [0]], dtype=np.int32), np.zeros(2, dtype=np.int32), ctx)
     assert labels == [{"model_name": "clf", "outputs": [2]}, {"model_name": "clf", "outputs": [0]}] and type(labels[0]["outputs"][0]) is int
+
+
+def test_only_plain_linear_estimators_are_exported_as_linear():
+    """An estimator that merely carries coef_ is not X @ coef_.T + b: GLMs apply exp, SVC(kernel='linear') keeps
+    one-vs-one rows, PLS centres.  They must be refused (UnsupportedModel), never exported with the wrong arithmetic."""
+    from sklearn.cross_decomposition import PLSRegression
+    from sklearn.linear_model import LogisticRegression, PoissonRegressor, Ridge, SGDClassifier
+    from sklearn.svm import SVC, LinearSVC
+
+    rng = np.random.default_rng(5)
+    X = rng.normal(size=(200, 6))
+    y_cnt = rng.poisson(np.exp(0.3 * X[:, 0]) + 0.5)
+    y3 = (X[:, 0] > 0.4).astype(int) + (X[:, 1] > 0.2).astype(int)
+    for bad in (PoissonRegressor().fit(X, y_cnt), SVC(kernel="linear").fit(X, y3), PLSRegression(n_components=2).fit(X, X[:, 0])):
+        with pytest.raises(packing.UnsupportedModel):
+            packing.pack_model(bad)
+    for good in (Ridge().fit(X, X[:, 0] * 2), LogisticRegression().fit(X, y3), LinearSVC().fit(X, y3),
+                 SGDClassifier(random_state=0).fit(X, y3 > 0)):
+        kind, packed = packing.pack_model(good)
+        assert kind == "linear" and packed["n_features"] == 6
+        scores = X @ packed["W"].T + packed["b"]
+        if packed["link"] == packing.nat.LINK_IDENTITY:
+            got = scores[:, 0]
+        elif packed["link"] == packing.nat.LINK_BINARY_GT:
+            got = packed["classes"][(scores[:, 0] > 0).astype(int)]
+        else:
+            got = packed["classes"][scores.argmax(axis=1)]
+        np.testing.assert_allclose(got, good.predict(X), rtol=1e-9)
+
+
+def test_model_server_refuses_a_request_of_the_wrong_width():
+    """sklearn's predict raises for a width mismatch (extra columns included); so does the device server, before any
+    device call (this runs without a GPU)."""
+    from sklearn.linear_model import Ridge
+    from sklearn.tree import DecisionTreeRegressor
+
+    from mlrun_b200.serving.device_models import PickleModelServer
+
+    rng = np.random.default_rng(6)
+    X = rng.normal(size=(64, 5))
+    for model in (Ridge().fit(X, X[:, 0]), DecisionTreeRegressor(max_depth=2).fit(X, X[:, 0])):
+        server = PickleModelServer(name="m", model=model)
+        with pytest.raises(ValueError, match="expecting 5 features"):
+            server.predict({"inputs": rng.normal(size=(3, 7)).tolist()})
+        with pytest.raises(ValueError):
+            model.predict(rng.normal(size=(3, 7)))
