@@ -126,6 +126,25 @@ int b2s_plan_add_tree_model(b2s_plan_t plan, int32_t n_trees, const int32_t* tre
                             const int32_t* right, const double* leaf_value, const int32_t* tree_slot,
                             const double* tree_scale, const double* init, int32_t n_scores, int32_t link,
                             const int32_t* classes, int32_t n_classes);
+/* The same with the tree semantics of the other libraries behind the reference's model servers (XGBoostModelServer is
+ * PickleModelServer, frameworks/xgboost/__init__.py:30; LGBMModelServer.predict, frameworks/lgbm/model_server.py:142-159):
+ *   cmp_mode       B2S_CMP_LE: left when x <= threshold (scikit-learn, LightGBM);  B2S_CMP_LT: left when x < threshold (xgboost);
+ *   default_left   per node (may be NULL = all 0): where a missing value (NaN) goes -- xgboost's "missing" child,
+ *                  LightGBM's default_left, scikit-learn's tree_.missing_go_to_left;
+ *   nan_mode       B2S_NAN_ERROR: a NaN input flags the row B2S_ROW_NONFINITE_INPUT (estimators whose predict refuses NaN);
+ *                  B2S_NAN_DEFAULT_CHILD: NaN follows default_left.  It is honoured when every model of the plan routes
+ *                  missing values and the plan runs on the shared-memory tree kernel (b2s_plan_kernel says so); in any
+ *                  other plan a NaN row is still flagged -- an error, never a silently different answer.
+ * Inf is flagged in both modes (what check_array / DMatrix refuse). */
+#define B2S_CMP_LE 0
+#define B2S_CMP_LT 1
+#define B2S_NAN_ERROR 0
+#define B2S_NAN_DEFAULT_CHILD 1
+int b2s_plan_add_tree_model_ex(b2s_plan_t plan, int32_t n_trees, const int32_t* tree_offset /* n_trees+1 */,
+                               const int32_t* feature, const float* threshold, const int32_t* left, const int32_t* right,
+                               const double* leaf_value, const int32_t* tree_slot, const double* tree_scale,
+                               const double* init, int32_t n_scores, int32_t link, const int32_t* classes, int32_t n_classes,
+                               int32_t cmp_mode, const uint8_t* default_left, int32_t nan_mode);
 /* VotingEnsemble reduce over the plan's models (weights in model order; fp64). */
 int b2s_plan_set_vote(b2s_plan_t plan, int32_t vote_kind, const double* weights, int32_t n_weights);
 /* Upload tables to HBM, pick kernels, size staging buffers.  After this the plan is immutable. */
@@ -157,6 +176,15 @@ int b2s_submit(b2s_plan_t plan, const void* rows, int64_t n_rows, int64_t row_st
 int b2s_wait(b2s_plan_t plan, uint64_t ticket, void* out, int64_t out_bytes, int32_t* row_status, b2s_stats* stats);
 /* force the open batch out now (drain callback, serving/server.py:353-384) */
 int b2s_flush(b2s_plan_t plan);
+/* Per-plan ring configuration, before the plan's first b2s_submit: batches in flight, rows per batch and how long the
+ * oldest row may wait for company (0 / 0 / negative keep the b2s_init defaults).  This is where a serving function's
+ * `spec.parameters["b200"] = {"max_batch": .., "max_wait_us": .., "ring_slots": ..}` lands (runtimes/nuclio/serving.py:
+ * 668-724 hands spec.parameters to the GraphServer). */
+int b2s_plan_set_ring(b2s_plan_t plan, int32_t ring_slots, int64_t max_batch, int32_t max_wait_us);
+/* The ring measured by itself: n_threads native producers, each emitting rows_per_submit rows of `rows` and awaiting them
+ * (emit / await_result of one request), for `seconds`.  events = rows served; p50 / p99 of the submit -> wait round trip. */
+int b2s_ring_bench(b2s_plan_t plan, const void* rows, int64_t n_src_rows, int64_t row_stride_bytes, int32_t n_threads,
+                   int32_t rows_per_submit, double seconds, int64_t* events, double* p50_us, double* p99_us);
 
 /* ---- multi-GPU: fused ensemble-merge ----------------------------------------------------------------
  * One process per GPU, events sharded by rows (they are independent: VotingEnsemble reduces across models,

@@ -21,6 +21,8 @@ OUT_COPY, OUT_ONEHOT = 0, 1
 LINK_IDENTITY, LINK_BINARY_GT, LINK_BINARY_GE, LINK_ARGMAX = 0, 1, 2, 3
 VOTE_NONE, VOTE_MEAN, VOTE_MAJORITY = 0, 1, 2
 ROW_NONFINITE_INPUT, ROW_BAD_LABEL, ROW_UNKNOWN_KEY = 1, 2, 4
+CMP_LE, CMP_LT = 0, 1          # left when x <= threshold (scikit-learn, LightGBM) | x < threshold (xgboost)
+NAN_ERROR, NAN_DEFAULT_CHILD = 0, 1
 COL_F32, COL_I32, COL_I64 = 0, 1, 2
 DATE_PARTS = {"year": 0, "month": 1, "day": 2, "hour": 3, "minute": 4, "second": 5, "day_of_week": 6, "dayofweek": 6,
               "weekday": 6, "day_of_year": 7, "dayofyear": 7, "quarter": 8, "is_leap_year": 9, "days_in_month": 10,
@@ -67,6 +69,8 @@ SIGNATURES = {
     "b2s_plan_add_linear_model": (C.c_int, [_vp, _pf64, _pf64, _i32, _i32, _pi32, _i32]),
     "b2s_plan_add_tree_model": (C.c_int, [_vp, _i32, _pi32, _pi32, _pf32, _pi32, _pi32, _pf64, _pi32, _pf64, _pf64,
                                           _i32, _i32, _pi32, _i32]),
+    "b2s_plan_add_tree_model_ex": (C.c_int, [_vp, _i32, _pi32, _pi32, _pf32, _pi32, _pi32, _pf64, _pi32, _pf64, _pf64,
+                                             _i32, _i32, _pi32, _i32, _i32, C.POINTER(C.c_uint8), _i32]),
     "b2s_plan_set_vote": (C.c_int, [_vp, _i32, _pf64, _i32]),
     "b2s_plan_finalize": (C.c_int, [_vp]),
     "b2s_plan_out_info": (C.c_int, [_vp, _pi32, _pi32]),
@@ -76,6 +80,9 @@ SIGNATURES = {
     "b2s_submit": (C.c_int, [_vp, _vp, _i64, _i64, C.POINTER(_u64)]),
     "b2s_wait": (C.c_int, [_vp, _u64, _vp, _i64, _vp, C.POINTER(Stats)]),
     "b2s_flush": (C.c_int, [_vp]),
+    "b2s_plan_set_ring": (C.c_int, [_vp, _i32, _i64, _i32]),
+    "b2s_ring_bench": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, C.c_double, C.POINTER(_i64), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double)]),
     "b2s_plan_set_merge_targets": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i64]),
     "b2s_ipc_export": (C.c_int, [_vp, _vp]),
     "b2s_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),

@@ -19,6 +19,7 @@ from .serving import (  # noqa: F401
     FeatureRowVotingEnsemble,
     GraphContext,
     GraphServer,
+    LGBMModelServer,
     MockEvent,
     MockTrigger,
     ModelRouter,
@@ -28,6 +29,7 @@ from .serving import (  # noqa: F401
     TaskStep,
     V2ModelServer,
     VotingEnsemble,
+    XGBoostModelServer,
     create_graph_server,
     new_function,
 )

@@ -27,6 +27,7 @@
 #include "b2s_rowwarp.cuh"
 #include "b2s_rowthread.cuh"
 #include "b2s_trees2.cuh"
+#include "b2s_trees3.cuh"
 
 using namespace b2s;
 
@@ -95,6 +96,8 @@ struct HostModel {
   std::vector<int32_t> tree_offset, feature, left, right, tree_slot;
   std::vector<float> threshold;
   std::vector<double> leaf_value, tree_scale, init;
+  std::vector<uint8_t> default_left;  // per node: a missing value (NaN) goes to the left child (empty: always right)
+  bool nan_ok = false;                // the estimator routes NaN through its trees instead of refusing it
 };
 
 struct Slot {  // one in-flight batch of the coalescing ring
@@ -161,6 +164,12 @@ struct b2s_plan_s {
   };
   std::map<cudaStream_t, TreeScratch> t2_scratch;
   std::mutex scratch_mu;
+  // round-2 tree kernel: parts resident in shared memory (b2s_trees3.cuh); scratch = partial sums, column-major
+  bool t3_ok = false, t3_miss = false;
+  int t3_D = 0, t3_grid = 0, t3_block = 0, t3_smem = 0, t3_cols = 0, t3_parts = 0;
+  T3Params t3{};
+  char* d_t3_blob = nullptr;
+  const int32_t* d_t3_col_score = nullptr;
   // host staging for run_host
   char* h_stage_in = nullptr;
   char* h_stage_out = nullptr;
@@ -183,6 +192,11 @@ struct b2s_plan_s {
   bool stop = false;
   cudaStream_t ring_stream = nullptr;
   int64_t ring_cap = 0;
+  // per-plan ring configuration (b2s_plan_set_ring; 0 / negative: the library defaults of b2s_init)
+  int ring_cfg_slots = 0;
+  int64_t ring_cfg_max_batch = 0;
+  int ring_cfg_wait_us = -1;
+  int wait_us() const { return ring_cfg_wait_us >= 0 ? ring_cfg_wait_us : G.max_wait_us; }
 };
 
 int b2s_int_plan_shape(b2s_plan_s* p, int* n_in, int* out_cols) {
@@ -674,12 +688,22 @@ extern "C" int b2s_plan_add_linear_model(b2s_plan_t p, const double* W, const do
   }
 }
 
-extern "C" int b2s_plan_add_tree_model(b2s_plan_t p, int32_t n_trees, const int32_t* tree_offset, const int32_t* feature,
-                                       const float* threshold, const int32_t* left, const int32_t* right,
-                                       const double* leaf_value, const int32_t* tree_slot, const double* tree_scale,
-                                       const double* init, int32_t n_scores, int32_t link, const int32_t* classes,
-                                       int32_t n_classes) {
-  try {  // no C++ exception crosses the C boundary
+// float32 t' with  x < t  <=>  x <= t'  for every float32 x: the next float below t (nothing is below -inf: a NaN
+// threshold sends every value right, which is what "x < -inf" does)
+static float threshold_for_less_than(float t) {
+  if (std::isnan(t)) return t;
+  if (t == -std::numeric_limits<float>::infinity()) return std::numeric_limits<float>::quiet_NaN();
+  return std::nextafterf(t, -std::numeric_limits<float>::infinity());
+}
+
+extern "C" int b2s_plan_add_tree_model_ex(b2s_plan_t p, int32_t n_trees, const int32_t* tree_offset, const int32_t* feature,
+                                          const float* threshold, const int32_t* left, const int32_t* right,
+                                          const double* leaf_value, const int32_t* tree_slot, const double* tree_scale,
+                                          const double* init, int32_t n_scores, int32_t link, const int32_t* classes,
+                                          int32_t n_classes, int32_t cmp_mode, const uint8_t* default_left, int32_t nan_mode) {
+  try {
+    if (cmp_mode != B2S_CMP_LE && cmp_mode != B2S_CMP_LT) return fail(B2S_ERR_INVALID, "unknown cmp_mode %d", cmp_mode);
+    if (nan_mode != B2S_NAN_ERROR && nan_mode != B2S_NAN_DEFAULT_CHILD) return fail(B2S_ERR_INVALID, "unknown nan_mode %d", nan_mode);  // no C++ exception crosses the C boundary
     if (int rc = check_build(p)) return rc;
     if (int rc = check_link(link, n_scores, classes ? n_classes : 0)) return rc;
     if (n_scores > 16) return fail(B2S_ERR_UNSUPPORTED, "tree models support at most 16 scores");
@@ -694,6 +718,11 @@ extern "C" int b2s_plan_add_tree_model(b2s_plan_t p, int32_t n_trees, const int3
     m.tree_offset.assign(tree_offset, tree_offset + n_trees + 1);
     m.feature.assign(feature, feature + nn);
     m.threshold.assign(threshold, threshold + nn);
+    if (cmp_mode == B2S_CMP_LT)  // xgboost: left when x < t.  Stored as the equivalent "x <= t'" (every kernel tests <=)
+      for (int i = 0; i < nn; ++i)
+        if (feature[i] >= 0) m.threshold[i] = threshold_for_less_than(m.threshold[i]);
+    if (default_left) m.default_left.assign(default_left, default_left + nn);
+    m.nan_ok = nan_mode == B2S_NAN_DEFAULT_CHILD;
     m.left.assign(left, left + nn);
     m.right.assign(right, right + nn);
     m.leaf_value.assign(leaf_value, leaf_value + nn);
@@ -721,6 +750,15 @@ extern "C" int b2s_plan_add_tree_model(b2s_plan_t p, int32_t n_trees, const int3
   }
 }
 
+extern "C" int b2s_plan_add_tree_model(b2s_plan_t p, int32_t n_trees, const int32_t* tree_offset, const int32_t* feature,
+                                       const float* threshold, const int32_t* left, const int32_t* right,
+                                       const double* leaf_value, const int32_t* tree_slot, const double* tree_scale,
+                                       const double* init, int32_t n_scores, int32_t link, const int32_t* classes,
+                                       int32_t n_classes) {
+  return b2s_plan_add_tree_model_ex(p, n_trees, tree_offset, feature, threshold, left, right, leaf_value, tree_slot, tree_scale,
+                                    init, n_scores, link, classes, n_classes, B2S_CMP_LE, nullptr, B2S_NAN_ERROR);
+}
+
 extern "C" int b2s_plan_set_vote(b2s_plan_t p, int32_t vote_kind, const double* weights, int32_t n_weights) {
   try {  // no C++ exception crosses the C boundary
     if (int rc = check_build(p)) return rc;
@@ -731,6 +769,283 @@ extern "C" int b2s_plan_set_vote(b2s_plan_t p, int32_t vote_kind, const double* 
   } catch (const std::exception& e) {
     return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
+}
+
+// ------------------------------------------------------------------------------------------ trees3 plan
+// order-preserving int32 key of a float32 (see t3_key in b2s_trees3.cuh): thresholds in the NaN-routing layout
+static int32_t host_key(float x) {
+  if (x == 0.0f) x = 0.0f;  // -0 -> +0
+  int32_t b;
+  memcpy(&b, &x, 4);
+  return b ^ ((b >> 31) & 0x7fffffff);
+}
+
+// Lower a MODE_TREES plan to parts (b2s_trees3.cuh).  Leaves p->t3_ok false when the plan does not qualify (the caller
+// then falls back to the round-1 kernels); returns an error only for CUDA failures.
+static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
+  const int n_in = p->n_in, M = (int)p->models.size();
+  const int sms = G.prop.multiProcessorCount;
+  const int smem_cap = (int)G.prop.sharedMemPerBlockOptin;
+  constexpr int TR = kT3TR;
+  // ---- depth, NaN mode, linear columns
+  int D = 2, n_lin_cols = 0;
+  bool all_nan_ok = true, any_trees = false;
+  for (auto& m : p->models) {
+    if (m.kind != MK_TREES) {
+      n_lin_cols += m.n_scores;
+      all_nan_ok = false;
+      continue;
+    }
+    any_trees = true;
+    all_nan_ok = all_nan_ok && m.nan_ok;
+    const int nt = (int)m.tree_slot.size();
+    for (int t = 0; t < nt; ++t) {
+      const int base = m.tree_offset[t];
+      std::vector<std::pair<int, int>> stack{{0, 0}};
+      while (!stack.empty()) {
+        auto [node, d] = stack.back();
+        stack.pop_back();
+        D = std::max(D, d);
+        if (D > kT3MaxDepth) return B2S_OK;
+        if (m.feature[base + node] >= 0) {
+          stack.push_back({m.left[base + node], d + 1});
+          stack.push_back({m.right[base + node], d + 1});
+        }
+      }
+    }
+  }
+  if (!any_trees || n_lin_cols > kT3MaxLin) return B2S_OK;
+  const bool miss = all_nan_ok;
+  const int NN = 1 << D;
+  const int n_in4 = (int)align_up(n_in, 4);
+  const int xt_words = n_in4 * TR;
+  // ---- shared-memory budget: tables | fill | partial sums | transposed tile(s) | landing tile | flags | barrier
+  int pitch = n_in4 + 4;
+  if (((pitch / 4) & 1) == 0) pitch += 4;
+  const size_t land_bytes = std::max((size_t)TR * pitch * 4, (size_t)TR * n_in4 * 4);
+  const size_t fixed = align_up((size_t)n_in4 * 4, 16) + (size_t)32 * TR * 8 + (size_t)xt_words * 4 * (miss ? 2 : 1) + land_bytes +
+                       1024 /* landing alignment */ + (size_t)TR * 4 + 16 + 64;
+  const size_t lin_bytes = (size_t)n_lin_cols * n_in * 8;
+  if (fixed + lin_bytes + 2 * (size_t)NN * 16 > (size_t)smem_cap) return B2S_OK;
+  const int cap_trees = (int)(((size_t)smem_cap - fixed) / ((size_t)NN * 16));
+  // ---- parts: per (tree model, score slot) the trees of that slot, split evenly when they exceed a CTA's capacity
+  struct HostPart {
+    int model, slot, n_trees = 0, n_cols = 1, col0 = 0;
+    std::vector<uint2> nodes;
+    std::vector<double> leaves;
+    double cost = 0.0;
+  };
+  std::vector<HostPart> parts;
+  std::vector<int32_t> col_score;
+  {
+    int so = 0;
+    for (int mi = 0; mi < M; ++mi) {
+      auto& m = p->models[mi];
+      if (m.kind == MK_TREES) {
+        const int nt = (int)m.tree_slot.size();
+        for (int slot = 0; slot < m.n_scores; ++slot) {
+          std::vector<int> mine;
+          for (int t = 0; t < nt; ++t)
+            if (m.tree_slot[t] == slot) mine.push_back(t);
+          if (mine.empty()) continue;
+          const int n_chunks = ((int)mine.size() + cap_trees - 1) / cap_trees;
+          const int per = ((int)mine.size() + n_chunks - 1) / n_chunks;
+          for (int c0 = 0; c0 < (int)mine.size(); c0 += per) {
+            HostPart hp;
+            hp.model = mi;
+            hp.slot = slot;
+            hp.n_trees = std::min(per, (int)mine.size() - c0);
+            hp.nodes.assign((size_t)hp.n_trees * NN, make_uint2(0u, 0u));
+            hp.leaves.assign((size_t)hp.n_trees * NN, 0.0);
+            for (int q = 0; q < hp.n_trees; ++q) {
+              const int t = mine[c0 + q];
+              const int base = m.tree_offset[t];
+              struct It { int heap, d, src; };  // heap: 1-based index in the complete tree
+              std::vector<It> stack{{1, 0, 0}};
+              while (!stack.empty()) {
+                const It it = stack.back();
+                stack.pop_back();
+                const bool leaf = m.feature[base + it.src] < 0;
+                if (it.d == D) {
+                  hp.leaves[(size_t)q * NN + (it.heap - NN)] = m.tree_scale[t] * m.leaf_value[base + it.src];
+                  continue;
+                }
+                uint2 nd;
+                if (leaf) {  // pad: every value goes left, and both children carry the leaf anyway
+                  const float inf = std::numeric_limits<float>::infinity();
+                  nd.x = 0;
+                  if (miss) nd.y = (uint32_t)0x7fffffff; else memcpy(&nd.y, &inf, 4);
+                  stack.push_back({2 * it.heap, it.d + 1, it.src});
+                  stack.push_back({2 * it.heap + 1, it.d + 1, it.src});
+                } else {
+                  const float thr = m.threshold[base + it.src];
+                  const bool dl = !m.default_left.empty() && m.default_left[base + it.src] != 0;
+                  nd.x = (uint32_t)(m.feature[base + it.src] * TR * 4 + ((miss && dl) ? xt_words * 4 : 0));
+                  if (miss) {
+                    // NaN threshold ("x < -inf" of an xgboost model): nothing goes left but a missing value that defaults left
+                    nd.y = std::isnan(thr) ? 0x80000000u : (uint32_t)host_key(thr);
+                  } else {
+                    memcpy(&nd.y, &thr, 4);
+                  }
+                  stack.push_back({2 * it.heap, it.d + 1, m.left[base + it.src]});
+                  stack.push_back({2 * it.heap + 1, it.d + 1, m.right[base + it.src]});
+                }
+                hp.nodes[(size_t)q * NN + it.heap] = nd;
+              }
+            }
+            hp.cost = 8.0 + hp.n_trees * (2.0 + 3.0 * D) / 32.0 * 2.0;  // wavefronts per row: transpose + walks
+            hp.col0 = (int)col_score.size();
+            col_score.push_back(so + slot);
+            parts.push_back(std::move(hp));
+          }
+        }
+      }
+      so += m.n_scores;
+    }
+    if (n_lin_cols > 0) {  // one part for all the linear scorers: weights [col][n_in] (identity schema: n_out == n_in)
+      HostPart hp;
+      hp.model = -1;
+      hp.slot = 0;
+      hp.n_trees = 0;
+      hp.n_cols = n_lin_cols;
+      hp.col0 = (int)col_score.size();
+      int so2 = 0;
+      for (int mi = 0; mi < M; ++mi) {
+        auto& m = p->models[mi];
+        if (m.kind == MK_LINEAR)
+          for (int kk = 0; kk < m.n_scores; ++kk) {
+            for (int j = 0; j < n_in; ++j) hp.leaves.push_back(m.W[(size_t)kk * n_in + j]);
+            col_score.push_back(so2 + kk);
+          }
+        so2 += m.n_scores;
+      }
+      hp.cost = 8.0 + 2.0 + n_in * n_lin_cols / 32.0 * 0.25;
+      parts.push_back(std::move(hp));
+    }
+  }
+  const int P = (int)parts.size();
+  if (P == 0 || P > sms) return B2S_OK;
+  // ---- CTAs per part, proportional to cost (largest-remainder rounding, at least one each)
+  std::vector<int> n_ctas(P, 1);
+  {
+    double total = 0.0;
+    for (auto& hp : parts) total += hp.cost;
+    int left = sms - P;
+    std::vector<double> want(P);
+    for (int i = 0; i < P; ++i) want[i] = std::max(0.0, parts[i].cost / total * sms - 1.0);
+    for (int i = 0; i < P; ++i) {
+      const int take = std::min(left, (int)want[i]);
+      n_ctas[i] += take;
+      left -= take;
+      want[i] -= (int)want[i];
+    }
+    while (left > 0) {
+      int best = 0;
+      for (int i = 1; i < P; ++i)
+        if (want[i] > want[best]) best = i;
+      ++n_ctas[best];
+      want[best] = -1.0;
+      --left;
+      bool any = false;
+      for (int i = 0; i < P; ++i) any |= want[i] >= 0.0;
+      if (!any)
+        for (int i = 0; i < P; ++i) want[i] = parts[i].cost;
+    }
+  }
+  // ---- warps per CTA: whole iterations of U trees per warp, as little padding as possible
+  int W = 25;
+  {
+    const char* wenv = getenv("B2S_T3_WARPS");
+    if (wenv) {
+      W = std::max(4, std::min(32, atoi(wenv)));
+    } else {
+      double best = 1e30;
+      for (int w = 16; w <= 28; ++w) {
+        double waste = 0.0;
+        for (auto& hp : parts) {
+          if (hp.n_trees == 0) continue;
+          const int tpw = (hp.n_trees + w - 1) / w;
+          const int iters = (tpw + kT3U - 1) / kT3U;
+          waste += (double)iters * kT3U * w / hp.n_trees * hp.cost;
+        }
+        if (waste < best - 1e-9 || (std::fabs(waste - best) <= 1e-9 && w > W)) {
+          best = waste;
+          W = w;
+        }
+      }
+    }
+  }
+  // ---- one blob: nodes / leaves of every part, the part table, the column -> score map
+  BlobBuilder tb;
+  std::vector<size_t> o_nodes(P), o_leaves(P);
+  for (int i = 0; i < P; ++i) {
+    o_nodes[i] = tb.add(parts[i].nodes);
+    o_leaves[i] = tb.add(parts[i].leaves);
+  }
+  const size_t o_cols = tb.add(col_score);
+  const size_t o_parts = align_up(tb.data.size(), 16);
+  tb.data.resize(o_parts + sizeof(T3Part) * P);
+  CUDA_TRY(cudaMalloc(&p->d_t3_blob, tb.data.size()));
+  std::vector<T3Part> dev(P);
+  int cta0 = 0;
+  for (int i = 0; i < P; ++i) {
+    T3Part& d = dev[i];
+    d.nodes = parts[i].n_trees ? (const uint2*)(p->d_t3_blob + o_nodes[i]) : nullptr;
+    d.leaves = (const double*)(p->d_t3_blob + o_leaves[i]);
+    d.n_trees = parts[i].n_trees;
+    d.n_cols = parts[i].n_cols;
+    d.col0 = parts[i].col0;
+    d.cta0 = cta0;
+    d.n_ctas = n_ctas[i];
+    d.flags_rows = i == 0 ? 1 : 0;
+    cta0 += n_ctas[i];
+  }
+  memcpy(tb.data.data() + o_parts, dev.data(), sizeof(T3Part) * P);
+  CUDA_TRY(cudaMemcpy(p->d_t3_blob, tb.data.data(), tb.data.size(), cudaMemcpyHostToDevice));
+  p->d_t3_col_score = (const int32_t*)(p->d_t3_blob + o_cols);
+
+  T3Params& t = p->t3;
+  memset(&t, 0, sizeof(t));
+  t.parts = (const T3Part*)(p->d_t3_blob + o_parts);
+  t.fill = k.fill;
+  t.n_in = n_in;
+  t.n_parts = P;
+  t.warps = W;
+  t.pitch = pitch;
+  t.any_fill = any_fill ? 1 : 0;
+  t.xt_words = xt_words;
+  size_t off = 0;
+  auto take = [&](size_t bytes, size_t al) {
+    off = align_up(off, al);
+    const size_t o = off;
+    off += bytes;
+    return (int32_t)o;
+  };
+  int max_trees = 0;
+  for (auto& hp : parts) max_trees = std::max(max_trees, hp.n_trees);
+  take(std::max((size_t)max_trees * NN * 8, lin_bytes), 16);  // nodes (or the linear weights) at offset 0
+  t.sm_leaf = take((size_t)max_trees * NN * 8, 16);
+  t.sm_fill = take((size_t)n_in4 * 4, 16);
+  t.sm_part = take((size_t)std::max(W, kT3MaxLin) * TR * 8, 16);
+  t.sm_xt = take((size_t)xt_words * 4 * (miss ? 2 : 1), 128);
+  t.sm_land = take(land_bytes, 1024);
+  t.sm_bad = take((size_t)TR * 4, 16);
+  t.sm_bar = take(16, 16);
+  if (off > (size_t)smem_cap) {  // cannot happen with the budget above; stay on the safe side
+    cudaFree(p->d_t3_blob);
+    p->d_t3_blob = nullptr;
+    return B2S_OK;
+  }
+  p->t3_smem = (int)align_up(off, 16);
+  p->t3_D = D;
+  p->t3_miss = miss;
+  p->t3_block = W * 32;
+  p->t3_grid = cta0;
+  p->t3_cols = (int)col_score.size();
+  p->t3_parts = P;
+  p->t3_ok = true;
+  p->kernels_per_batch = 2;
+  return B2S_OK;
 }
 
 // ------------------------------------------------------------------------------------------ finalize
@@ -745,14 +1060,15 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
     if (int rc = check_build(p)) return rc;
     if (!G.inited) return fail(B2S_ERR_STATE, "b2s_init was not called");
     const int n_in = p->n_in;
-    const bool identity_schema = p->out_src.empty();
-    if (identity_schema) {
+    if (p->out_src.empty()) {
       p->out_src.resize(n_in);
       p->out_kind.assign(n_in, B2S_OUT_COPY);
       p->out_arg.assign(n_in, 0.f);
       for (int j = 0; j < n_in; ++j) p->out_src[j] = j;
     }
     const int n_out = (int)p->out_src.size();
+    bool identity_schema = n_out == n_in;  // no schema given, or one that copies every column in place
+    for (int j = 0; identity_schema && j < n_out; ++j) identity_schema = p->out_kind[j] == B2S_OUT_COPY && p->out_src[j] == j;
     const int M = (int)p->models.size();
     if (p->vote_kind != B2S_VOTE_NONE) {
       if (M == 0) return fail(B2S_ERR_INVALID, "vote without models");
@@ -1180,6 +1496,14 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
         }
       }
     }
+    // ---- round-2 tree path: parts resident in shared memory (b2s_trees3.cuh).  Covers tree ensembles (any number of
+    // score slots per model), ensembles mixing tree and linear scorers, an Imputer in front, and NaN routing.
+    const char* trees_pick = getenv("B2S_TREES");  // 3 (default) | 2 (round-1 kernel) | 0 (generic rows_kernel)  -- A/B runs
+    const int trees_want = trees_pick ? atoi(trees_pick) : 3;
+    if (p->mode == MODE_TREES && identity_schema && !any_map && trees_want == 3) {
+      if (int rc = t3_build(p, k, any_fill)) return rc;
+    }
+    if (!p->t3_ok && trees_want >= 2)
     if (p->mode == MODE_TREES && !need_expand && getenv("B2S_NO_TREES2") == nullptr) {
       // re-pack every model as complete heap-ordered trees; one model must fit one CTA's shared memory
       bool ok = true;
@@ -1299,10 +1623,11 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
 // which kernel family a finalized plan launches (so that a silent fallback cannot hide in a benchmark)
 extern "C" const char* b2s_plan_kernel(b2s_plan_t p) {
   if (!p || !p->finalized) return "";
-  static thread_local char buf[160];
+  static thread_local char buf[200];
   int lm = rt_load_mode();
   if (lm == 2 && !(p->rt_NCH >= 8 && p->n_in == p->rt_NCH * 4 && tensor_map_encoder())) lm = 1;
-  if (p->t2_ok) snprintf(buf, sizeof(buf), "trees_model_kernel<%d> + vote_kernel (models resident in shared memory)", p->t2_NS);
+  if (p->t3_ok) snprintf(buf, sizeof(buf), "trees3_kernel<D=%d,%s> + t3_vote_kernel (%d parts resident in shared memory, %d warps)", p->t3_D, p->t3_miss ? "NaN routing" : "floats", p->t3_parts, p->t3_block / 32);
+  else if (p->t2_ok) snprintf(buf, sizeof(buf), "trees_model_kernel<%d> + vote_kernel (models resident in shared memory)", p->t2_NS);
   else if (p->rt_ok) snprintf(buf, sizeof(buf), "rowthread_kernel<NCH=%d,NS=%d,TPR=%d,RPT=%d,%s>", p->rt_NCH, p->rt_NS, p->rt_TPR, lm == 2 ? p->rt_RPT : 1, lm == 2 ? "TMA tensor-map loads" : (lm == 1 ? "TMA bulk loads" : "cp.async loads"));
   else if (p->rw_ok) snprintf(buf, sizeof(buf), "rowwarp_kernel<L=%d,CPL=%d,NS=%d,U=%d,CS=%d>", p->rw_L, p->rw_CPL, p->rw_NS, p->rw_U, p->rw_CS);
   else snprintf(buf, sizeof(buf), "rows_kernel<%s,NS=%d>", p->mode == MODE_LINEAR ? "LINEAR" : (p->mode == MODE_TREES ? "TREES" : "STORE"), p->NS);
@@ -1334,6 +1659,58 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
   k.n_peers = (int)p->peers.size();
   k.peer_off = p->peer_off;
   for (int g = 0; g < k.n_peers; ++g) k.peers[g] = (float*)p->peers[g];
+  if (p->t3_ok) {
+    const int C = p->t3_cols;
+    b2s_plan_s::TreeScratch sc;
+    {
+      std::lock_guard<std::mutex> lk(p->scratch_mu);
+      b2s_plan_s::TreeScratch& mine = p->t2_scratch[st];
+      if (n_rows > mine.rows) {  // cudaFree waits for the work that still reads the old buffers
+        if (mine.pred) cudaFree(mine.pred);
+        if (mine.row_bad) cudaFree(mine.row_bad);
+        mine = b2s_plan_s::TreeScratch{};
+        const int64_t cap = std::max<int64_t>(align_up((size_t)n_rows, 64), 65536);
+        CUDA_TRY(cudaMalloc(&mine.pred, (size_t)cap * C * 8));
+        CUDA_TRY(cudaMalloc(&mine.row_bad, (size_t)cap * 4));
+        mine.rows = cap;
+      }
+      sc = mine;
+    }
+    T3Params t = p->t3;
+    t.rows = (const char*)d_rows;
+    t.row_stride = stride;
+    t.n_rows = n_rows;
+    t.partial = sc.pred;
+    t.col_stride = sc.rows;
+    t.row_bad = sc.row_bad;
+    t.vec_ok = k.vec_ok;
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    static const int t3_tma = getenv("B2S_T3_TMA") ? atoi(getenv("B2S_T3_TMA")) : 1;
+    t.use_tmap = (t3_tma && t.vec_ok && (p->n_in % 32) == 0 && encode_rows_map(&tmap, d_rows, n_rows, stride, p->n_in, kT3TR)) ? 1 : 0;
+    G.launches.fetch_add(2, std::memory_order_relaxed);
+    cudaError_t e3 = cudaErrorInvalidValue;
+#define B2S_T3_CASE(DD)                                                                                                   \
+  if (p->t3_D == DD) {                                                                                                      \
+    static std::atomic<bool> attr{false};                                                                                   \
+    if (!attr) {                                                                                                            \
+      CUDA_TRY(cudaFuncSetAttribute(trees3_kernel<DD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.prop.sharedMemPerBlockOptin)); \
+      CUDA_TRY(cudaFuncSetAttribute(trees3_kernel<DD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.prop.sharedMemPerBlockOptin));  \
+      attr = true;                                                                                                          \
+    }                                                                                                                       \
+    if (p->t3_miss) trees3_kernel<DD, true><<<p->t3_grid, p->t3_block, p->t3_smem, st>>>(t, tmap);                          \
+    else trees3_kernel<DD, false><<<p->t3_grid, p->t3_block, p->t3_smem, st>>>(t, tmap);                                    \
+    e3 = cudaGetLastError();                                                                                                \
+  }
+    B2S_T3_CASE(2) B2S_T3_CASE(3) B2S_T3_CASE(4) B2S_T3_CASE(5) B2S_T3_CASE(6) B2S_T3_CASE(7) B2S_T3_CASE(8)
+#undef B2S_T3_CASE
+    if (e3 != cudaSuccess) return fail(B2S_ERR_CUDA, "tree kernel launch failed: %s", cudaGetErrorString(e3));
+    const int vgrid = (int)std::max<int64_t>(1, std::min<int64_t>(4 * G.prop.multiProcessorCount, (n_rows + 255) / 256));
+    t3_vote_kernel<<<vgrid, 256, 0, st>>>(k, sc.pred, sc.rows, p->d_t3_col_score, C, sc.row_bad);
+    e3 = cudaGetLastError();
+    if (e3 != cudaSuccess) return fail(B2S_ERR_CUDA, "vote kernel launch failed: %s", cudaGetErrorString(e3));
+    return B2S_OK;
+  }
   if (p->t2_ok) {
     b2s_plan_s::TreeScratch sc;
     {
@@ -1434,7 +1811,7 @@ int b2s_int_launch_gathered(b2s_plan_s* p, const B2SGather& g, long long n, void
   static const int fused = getenv("B2S_ENRICH_FUSED") ? atoi(getenv("B2S_ENRICH_FUSED")) : 1;
   // the gather loader lives in the row-thread kernel (linear models, rows of whole 16-byte chunks); with a table impute
   // policy, one-hot sources would need the policy applied before the category search: those plans gather first
-  if (!fused || !p->rt_ok || p->t2_ok || (p->n_in % 4) != 0) return fail(B2S_ERR_UNSUPPORTED, "plan is not fusable with the gather");
+  if (!fused || !p->rt_ok || p->t2_ok || p->t3_ok || (p->n_in % 4) != 0) return fail(B2S_ERR_UNSUPPORTED, "plan is not fusable with the gather");
   if (g.any_impute && p->rt_cat_cols > 0) return fail(B2S_ERR_UNSUPPORTED, "one-hot columns under a table impute policy gather first");
   if (n <= 0) return B2S_OK;
   G.launches.fetch_add(1, std::memory_order_relaxed);
@@ -1618,10 +1995,10 @@ static void dispatcher_main(b2s_plan_s* p) {
     if (p->sealed.empty()) {
       if (p->stop) return;
       if (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0) {
-        auto deadline = p->slots[p->open_slot].first_submit + std::chrono::microseconds(G.max_wait_us);
+        auto deadline = p->slots[p->open_slot].first_submit + std::chrono::microseconds(p->wait_us());
         if (p->cv_work.wait_until(lk, deadline) == std::cv_status::timeout) {
           if (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0 &&
-              std::chrono::steady_clock::now() >= p->slots[p->open_slot].first_submit + std::chrono::microseconds(G.max_wait_us)) {
+              std::chrono::steady_clock::now() >= p->slots[p->open_slot].first_submit + std::chrono::microseconds(p->wait_us())) {
             p->slots[p->open_slot].state = 1;
             p->sealed.push_back(p->open_slot);
             p->open_slot = -1;
@@ -1706,8 +2083,9 @@ static int ring_start(b2s_plan_s* p) {
   CUDA_TRY(cudaSetDevice(G.device));
   // built aside and committed only when everything (buffers, events, stream, dispatcher) exists: a failure leaves the
   // plan without a ring, so the next submit retries instead of queueing rows nobody will ever dispatch
-  const int64_t cap = G.max_batch;
-  std::vector<Slot> slots(G.ring_slots);
+  const int64_t cap = p->ring_cfg_max_batch > 0 ? p->ring_cfg_max_batch : G.max_batch;
+  const int n_slots = p->ring_cfg_slots > 0 ? p->ring_cfg_slots : G.ring_slots;
+  std::vector<Slot> slots(n_slots);
   cudaStream_t stream = nullptr;
   const int64_t row_bytes = (int64_t)p->n_in * 4;
   cudaError_t e = cudaSuccess;
@@ -1723,7 +2101,7 @@ static int ring_start(b2s_plan_s* p) {
   if (e != cudaSuccess) {
     for (auto& s : slots) ring_free_slot(s);
     cudaGetLastError();
-    return fail(B2S_ERR_CUDA, "coalescing ring of %d x %lld rows: %s", G.ring_slots, (long long)cap, cudaGetErrorString(e));
+    return fail(B2S_ERR_CUDA, "coalescing ring of %d x %lld rows: %s", n_slots, (long long)cap, cudaGetErrorString(e));
   }
   p->ring_cap = cap;
   p->slots = std::move(slots);
@@ -1808,6 +2186,22 @@ extern "C" int b2s_flush(b2s_plan_t p) {
   }
 }
 
+extern "C" int b2s_plan_set_ring(b2s_plan_t p, int32_t ring_slots, int64_t max_batch, int32_t max_wait_us) {
+  try {  // no C++ exception crosses the C boundary
+    if (!p) return fail(B2S_ERR_INVALID, "null plan");
+    std::unique_lock<std::mutex> lk(p->mu);
+    if (!p->slots.empty()) return fail(B2S_ERR_STATE, "the coalescing ring of this plan is already running");
+    if (ring_slots < 0 || ring_slots > 64 || max_batch < 0 || max_batch > (1 << 24) || max_wait_us > 10000000)
+      return fail(B2S_ERR_INVALID, "ring configuration out of range");
+    p->ring_cfg_slots = ring_slots;
+    p->ring_cfg_max_batch = max_batch;
+    p->ring_cfg_wait_us = max_wait_us;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
+}
+
 extern "C" int b2s_wait(b2s_plan_t p, uint64_t ticket, void* out, int64_t out_bytes, int32_t* row_status, b2s_stats* stats) {
   try {  // no C++ exception crosses the C boundary
     if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
@@ -1850,6 +2244,64 @@ extern "C" int b2s_wait(b2s_plan_t p, uint64_t ticket, void* out, int64_t out_by
   }
 }
 
+// Throughput / latency of the coalescing ring itself, driven by native producer threads (no Python in the loop): every
+// thread emits `rows_per_submit` rows and awaits them, like a request thread of the reference emits one event and blocks
+// in await_result (serving/states.py:1283-1287), for `seconds`.
+extern "C" int b2s_ring_bench(b2s_plan_t p, const void* rows, int64_t n_src_rows, int64_t row_stride_bytes, int32_t n_threads,
+                              int32_t rows_per_submit, double seconds, int64_t* events, double* p50_us, double* p99_us) {
+  try {  // no C++ exception crosses the C boundary
+    if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+    if (n_threads < 1 || n_threads > 1024 || rows_per_submit < 1 || rows_per_submit > n_src_rows || seconds <= 0 || !events)
+      return fail(B2S_ERR_INVALID, "bad ring bench arguments");
+    std::vector<std::thread> threads;
+    std::vector<int64_t> done(n_threads, 0);
+    std::vector<std::vector<float>> lat(n_threads);
+    std::vector<int> rcs(n_threads, 0);
+    std::vector<std::string> msgs(n_threads);
+    const auto t_end = std::chrono::steady_clock::now() + std::chrono::duration_cast<std::chrono::steady_clock::duration>(
+                                                               std::chrono::duration<double>(seconds));
+    const size_t out_bytes = (size_t)rows_per_submit * p->out_cols * 4;
+    for (int t = 0; t < n_threads; ++t) {
+      threads.emplace_back([&, t] {
+        std::vector<char> out(out_bytes);
+        std::vector<int32_t> status(rows_per_submit);
+        int64_t off = ((int64_t)t * 7919) % (n_src_rows - rows_per_submit + 1);
+        while (std::chrono::steady_clock::now() < t_end) {
+          const auto t0 = std::chrono::steady_clock::now();
+          uint64_t ticket = 0;
+          int rc = b2s_submit(p, (const char*)rows + off * row_stride_bytes, rows_per_submit, row_stride_bytes, &ticket);
+          if (!rc) rc = b2s_wait(p, ticket, out.data(), (int64_t)out_bytes, status.data(), nullptr);
+          if (rc) {
+            rcs[t] = rc;
+            msgs[t] = g_err;
+            return;
+          }
+          if (lat[t].size() < (1u << 20))
+            lat[t].push_back(std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count());
+          done[t] += rows_per_submit;
+          off = (off + rows_per_submit * 13) % (n_src_rows - rows_per_submit + 1);
+        }
+      });
+    }
+    for (auto& th : threads) th.join();
+    for (int t = 0; t < n_threads; ++t)
+      if (rcs[t]) return fail(rcs[t], "ring bench producer %d: %s", t, msgs[t].c_str());
+    int64_t total = 0;
+    std::vector<float> all;
+    for (int t = 0; t < n_threads; ++t) {
+      total += done[t];
+      all.insert(all.end(), lat[t].begin(), lat[t].end());
+    }
+    *events = total;
+    std::sort(all.begin(), all.end());
+    if (p50_us) *p50_us = all.empty() ? 0.0 : all[all.size() / 2];
+    if (p99_us) *p99_us = all.empty() ? 0.0 : all[(size_t)((all.size() - 1) * 0.99)];
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
+}
+
 extern "C" int b2s_plan_destroy(b2s_plan_t p) {
   try {  // no C++ exception crosses the C boundary
     if (!p) return B2S_OK;
@@ -1873,6 +2325,7 @@ extern "C" int b2s_plan_destroy(b2s_plan_t p) {
     for (cudaEvent_t e : p->chunk_ev) cudaEventDestroy(e);
     if (p->d_blob) cudaFree(p->d_blob);
     if (p->d_t2_blob) cudaFree(p->d_t2_blob);
+    if (p->d_t3_blob) cudaFree(p->d_t3_blob);
     for (auto& kv : p->t2_scratch)
       if (kv.second.pred) { cudaFree(kv.second.pred); cudaFree(kv.second.row_bad); }
     delete p;

@@ -97,14 +97,39 @@ def _append_tree(tree, value_of, acc):
     acc["right"].append(np.where(feat >= 0, t.children_right, 0).astype(np.int32))
     acc["leaf"].append(np.asarray(value_of(t.value), dtype=np.float64))
     acc["offset"].append(acc["offset"][-1] + n)
+    # where a missing value goes (scikit-learn >= 1.3: Tree.missing_go_to_left; only meaningful for estimators whose
+    # predict accepts NaN -- see NAN_ROUTING below)
+    mgl = getattr(t, "missing_go_to_left", None)
+    acc["default_left"].append(np.zeros(n, dtype=np.uint8) if mgl is None else np.asarray(mgl, dtype=np.uint8))
 
 
 def _new_acc():
-    return {"feature": [], "threshold": [], "left": [], "right": [], "leaf": [], "offset": [0], "slot": [], "scale": []}
+    return {"feature": [], "threshold": [], "left": [], "right": [], "leaf": [], "offset": [0], "slot": [], "scale": [],
+            "default_left": []}
 
 
-def _finish(acc, init, link, classes):
+# estimators whose predict() lets NaN through and routes it by Tree.missing_go_to_left (scikit-learn >= 1.3 for single
+# trees, >= 1.4 for forests; GradientBoosting* refuses NaN): for the others a NaN row stays an error, as in predict()
+NAN_ROUTING = frozenset({"DecisionTreeRegressor", "DecisionTreeClassifier", "RandomForestRegressor", "RandomForestClassifier",
+                         "ExtraTreesRegressor", "ExtraTreesClassifier"})
+
+
+def _routes_nan(model):
+    if type(model).__name__ not in NAN_ROUTING:
+        return False
+    tree = model.tree_ if hasattr(model, "tree_") else model.estimators_[0].tree_
+    if not hasattr(tree, "missing_go_to_left"):
+        return False
+    try:  # the installed scikit-learn decides (the estimator tag its predict() consults)
+        return bool(model.__sklearn_tags__().input_tags.allow_nan)
+    except Exception:
+        return False
+
+
+def _finish(acc, init, link, classes, nan_ok=False):
     return PackedTrees(
+        default_left=np.concatenate(acc["default_left"]) if nan_ok else None,
+        nan_ok=nan_ok,
         tree_offset=np.asarray(acc["offset"], dtype=np.int32),
         feature=np.concatenate(acc["feature"]),
         threshold=np.concatenate(acc["threshold"]),
@@ -144,7 +169,7 @@ def pack_trees(model):
             _append_tree(est.tree_, lambda v: v[:, 0, 0], acc)
             acc["slot"].append(0)
             acc["scale"].append(1.0 / n)
-        return _finish(acc, [0.0], nat.LINK_IDENTITY, None)
+        return _finish(acc, [0.0], nat.LINK_IDENTITY, None, nan_ok=_routes_nan(model))
     if name in ("RandomForestClassifier", "ExtraTreesClassifier"):
         classes = _int_classes(model.classes_)
         n = len(model.estimators_)
@@ -157,12 +182,12 @@ def pack_trees(model):
                 _append_tree(est.tree_, proba_k, acc)
                 acc["slot"].append(k)
                 acc["scale"].append(1.0 / n)
-        return _finish(acc, np.zeros(K), nat.LINK_ARGMAX, classes)
+        return _finish(acc, np.zeros(K), nat.LINK_ARGMAX, classes, nan_ok=_routes_nan(model))
     if name == "DecisionTreeRegressor":
         _append_tree(model.tree_, lambda v: v[:, 0, 0], acc)
         acc["slot"].append(0)
         acc["scale"].append(1.0)
-        return _finish(acc, [0.0], nat.LINK_IDENTITY, None)
+        return _finish(acc, [0.0], nat.LINK_IDENTITY, None, nan_ok=_routes_nan(model))
     if name == "DecisionTreeClassifier":
         classes = _int_classes(model.classes_)
         K = len(classes)
@@ -173,12 +198,21 @@ def pack_trees(model):
             _append_tree(model.tree_, proba_k, acc)
             acc["slot"].append(k)
             acc["scale"].append(1.0)
-        return _finish(acc, np.zeros(K), nat.LINK_ARGMAX, classes)
+        return _finish(acc, np.zeros(K), nat.LINK_ARGMAX, classes, nan_ok=_routes_nan(model))
     raise UnsupportedModel(f"{name} is not a supported tree ensemble")
 
 
 def pack_model(model):
     """-> ("linear", dict) | ("trees", PackedTrees)"""
+    from . import tree_formats  # (imports this module)
+
+    if isinstance(model, PackedTrees):  # already exported, e.g. tree_formats.pack_xgboost_json(open("model.json").read())
+        return "trees", model
+    if isinstance(model, dict) and ("learner" in model or "tree_info" in model):  # a parsed xgboost / LightGBM document
+        return "trees", tree_formats.pack_serialised(model)
+    packed = tree_formats.pack_library_model(model)  # live xgboost / LightGBM objects
+    if packed is not None:
+        return "trees", packed
     name = type(model).__name__
     if name in LINEAR_REGRESSORS or name in LINEAR_CLASSIFIERS:
         packed = pack_linear(model)

@@ -28,7 +28,7 @@ class PackedTrees:
     """SoA tree ensemble in the layout b2s_plan_add_tree_model takes (children are tree-relative)"""
 
     def __init__(self, tree_offset, feature, threshold, left, right, leaf_value, tree_slot, tree_scale, init,
-                 link=nat.LINK_IDENTITY, classes=None):
+                 link=nat.LINK_IDENTITY, classes=None, cmp_mode=nat.CMP_LE, default_left=None, nan_ok=False):
         self.tree_offset = _i32(tree_offset)
         self.feature = _i32(feature)
         self.threshold = _f32(threshold)
@@ -40,6 +40,10 @@ class PackedTrees:
         self.init = _f64(init)
         self.link = int(link)
         self.classes = None if classes is None else _i32(classes)
+        # tree semantics of the library the model comes from (include/b200serve.h, b2s_plan_add_tree_model_ex)
+        self.cmp_mode = int(cmp_mode)  # nat.CMP_LE (scikit-learn, LightGBM) | nat.CMP_LT (xgboost)
+        self.default_left = None if default_left is None else np.ascontiguousarray(default_left, dtype=np.uint8)
+        self.nan_ok = bool(nan_ok)     # predict() routes NaN to the default child instead of refusing it
 
     @property
     def n_trees(self):
@@ -114,11 +118,13 @@ class DevicePlan:
 
     def add_trees(self, t: PackedTrees):
         cls = t.classes
-        nat.check(self._lib.b2s_plan_add_tree_model(
+        nat.check(self._lib.b2s_plan_add_tree_model_ex(
             self._h, t.n_trees, nat._p(t.tree_offset, C.c_int32), nat._p(t.feature, C.c_int32),
             nat._p(t.threshold, C.c_float), nat._p(t.left, C.c_int32), nat._p(t.right, C.c_int32),
             nat._p(t.leaf_value, C.c_double), nat._p(t.tree_slot, C.c_int32), nat._p(t.tree_scale, C.c_double),
-            nat._p(t.init, C.c_double), t.n_scores, t.link, nat._p(cls, C.c_int32), 0 if cls is None else len(cls)))
+            nat._p(t.init, C.c_double), t.n_scores, t.link, nat._p(cls, C.c_int32), 0 if cls is None else len(cls),
+            getattr(t, "cmp_mode", nat.CMP_LE), nat._p(getattr(t, "default_left", None), C.c_uint8),
+            nat.NAN_DEFAULT_CHILD if getattr(t, "nan_ok", False) else nat.NAN_ERROR))
         self.n_models += 1
         return self
 
@@ -201,6 +207,20 @@ class DevicePlan:
 
     def flush(self):
         nat.check(self._lib.b2s_flush(self._h))
+
+    def set_ring(self, ring_slots=0, max_batch=0, max_wait_us=-1):
+        """ring configuration of this plan (before its first submit); zeros / -1 keep the library defaults"""
+        nat.check(self._lib.b2s_plan_set_ring(self._h, int(ring_slots), int(max_batch), int(max_wait_us)))
+        return self
+
+    def ring_bench(self, X, n_threads, rows_per_submit, seconds):
+        """events/s and round-trip latency of submit -> wait from native producer threads (b2s_ring_bench)"""
+        X = self._check_rows(X)
+        ev, p50, p99 = C.c_int64(), C.c_double(), C.c_double()
+        nat.check(self._lib.b2s_ring_bench(self._h, X.ctypes.data, X.shape[0], self._stride(X), int(n_threads),
+                                           int(rows_per_submit), float(seconds), C.byref(ev), C.byref(p50), C.byref(p99)))
+        return {"events_per_s": ev.value / float(seconds), "p50_us": p50.value, "p99_us": p99.value,
+                "producers": int(n_threads), "rows_per_submit": int(rows_per_submit)}
 
     def run_device(self, d_rows, n_rows, row_stride, d_out, d_status=None, stream=None):
         nat.check(self._lib.b2s_run_device(self._h, d_rows, n_rows, row_stride, d_out, d_status, stream))

@@ -2,6 +2,7 @@
 from .device_models import (  # noqa: F401
     FeatureRowModelServer,
     FeatureRowVotingEnsemble,
+    LGBMModelServer,
     PickleModelServer,
     SKLearnModelServer,
     XGBoostModelServer,

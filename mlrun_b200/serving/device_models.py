@@ -47,6 +47,14 @@ class PickleModelServer(V2ModelServer):
 
     def load(self):
         if self.model is None:
+            if str(self.model_path or "").endswith(".json"):
+                # an xgboost `save_model("m.json")` / LightGBM `dump_model()` document: the libraries' own portable format
+                import json
+
+                model_file, _ = self.get_model(".json")
+                with open(model_file) as fp:
+                    self.model = json.load(fp)
+                return
             from cloudpickle import load
 
             model_file, _ = self.get_model(".pkl")
@@ -67,11 +75,14 @@ class PickleModelServer(V2ModelServer):
         want = packed.get("n_features") if kind == "linear" else getattr(packed, "n_features", None)
         if want and int(want) != int(n_features):
             # scikit-learn's predict -> validate_data raises this for a width mismatch (extra columns included)
-            raise ValueError(f"X has {n_features} features, but {type(self.model).__name__} is expecting {want} "
+            raise ValueError(f"X has {n_features} features, but {self._model_kind()} is expecting {want} "
                              "features as input.")
         if self._plan is None or self._plan.n_in != n_features:
             self._plan = ColumnProgram([f"f{i}" for i in range(n_features)]).build_plan([self.packed])
         return self._plan
+
+    def _model_kind(self):
+        return "the tree ensemble" if isinstance(self.model, dict) else type(self.model).__name__
 
     def preprocess(self, request, operation):
         if self.feature_rows and isinstance(request, dict) and "inputs" not in request:
@@ -94,7 +105,12 @@ class PickleModelServer(V2ModelServer):
 
 
 SKLearnModelServer = PickleModelServer
-XGBoostModelServer = PickleModelServer
+XGBoostModelServer = PickleModelServer  # mlrun/frameworks/xgboost/__init__.py:30; models: live objects or save_model JSON
+
+
+class LGBMModelServer(PickleModelServer):
+    """mlrun/frameworks/lgbm/model_server.py:142-159 (`self.model.predict(x)`): a live LightGBM object, or the document
+    `Booster.dump_model()` writes (model_path="model.json")"""
 
 
 class FeatureRowModelServer(PickleModelServer):

@@ -256,7 +256,29 @@ class GraphServer(Serde):
 
         if self._compiled is None or (in_names is not None and list(in_names) != self._compiled.in_names):
             self._compiled = compile_graph(self.graph, in_names)
+            # the function's engine parameters (fn.spec.parameters["b200"], handed over like every other parameter:
+            # runtimes/nuclio/serving.py:668-724): the coalescing ring of this graph's plan
+            ring = (self.parameters or {}).get("b200") or {}
+            if ring and hasattr(self._compiled.plan, "set_ring"):
+                unknown = set(ring) - {"max_batch", "max_wait_us", "ring_slots"}
+                if unknown:
+                    raise ValueError(f'parameters["b200"]: unknown keys {sorted(unknown)}')
+                self._compiled.plan.set_ring(ring_slots=ring.get("ring_slots", 0), max_batch=ring.get("max_batch", 0),
+                                             max_wait_us=ring.get("max_wait_us", -1))
         return self._compiled
+
+    def emit(self, body):
+        """one event body (a feature dict of the compiled schema) -> ticket.  The rows of concurrent callers are coalesced
+        into one device batch by the plan's ring (`b2s_submit`): the replacement of storey's SyncEmitSource.emit
+        (serving/states.py:1283-1287).  Collect the response with `await_result(ticket)`."""
+        compiled = self.compile(list(body.keys()))
+        return compiled.plan.submit(compiled.pack_events([body]))
+
+    def await_result(self, ticket):
+        """blocks until the ticket's batch ran; -> the response dict `run_events` gives that event (or its 400 Response)"""
+        compiled = self.compile()
+        out, status = compiled.plan.wait(ticket, with_status=True)
+        return compiled.responses(out, status, self.context)[0]
 
     @property
     def device_plan(self):

@@ -72,6 +72,7 @@ _REF_PATHS = {
     "mlrun.serving.v2_serving.V2ModelServer": "mlrun_b200.serving.model_server.V2ModelServer",
     "mlrun.frameworks.sklearn.SKLearnModelServer": "mlrun_b200.serving.device_models.SKLearnModelServer",
     "mlrun.frameworks.xgboost.XGBoostModelServer": "mlrun_b200.serving.device_models.XGBoostModelServer",
+    "mlrun.frameworks.lgbm.LGBMModelServer": "mlrun_b200.serving.device_models.LGBMModelServer",
 }
 for _n in ("Imputer", "OneHotEncoder", "MapValues", "DropFeatures", "DateExtractor", "SetEventMetadata", "FeaturesetValidator"):
     _REF_PATHS[f"mlrun.feature_store.steps.{_n}"] = f"mlrun_b200.feature_store.transforms.{_n}"

@@ -58,18 +58,34 @@ def linear_predict(packed, E):
     return link(scores, packed["link"], packed["classes"])
 
 
+def device_thresholds(t):
+    """what b2s_plan_add_tree_model_ex stores: `x < t` (xgboost, CMP_LT) becomes `x <= prev_float32(t)`"""
+    thr = np.asarray(t.threshold, dtype=np.float32).copy()
+    if getattr(t, "cmp_mode", nat.CMP_LE) == nat.CMP_LT:
+        split = t.feature >= 0
+        low = thr == -np.inf
+        thr[split] = np.nextafter(thr[split], np.float32(-np.inf))
+        thr[split & low] = np.nan  # nothing is below -inf: every value goes right
+    return thr
+
+
 def trees_predict(t, E):
     B = E.shape[0]
     scores = np.tile(t.init, (B, 1)).astype(np.float64)
+    thr_all = device_thresholds(t)
+    dleft = getattr(t, "default_left", None)
     for ti in range(t.n_trees):
         base = t.tree_offset[ti]
         node = np.zeros(B, dtype=np.int64)
         active = t.feature[base + node] >= 0
         while active.any():
             f = t.feature[base + node]
-            thr = t.threshold[base + node]
+            thr = thr_all[base + node]
             x = E[np.arange(B), np.where(f >= 0, f, 0)]
-            go_left = x <= thr
+            with np.errstate(invalid="ignore"):
+                go_left = x <= thr
+            if dleft is not None:  # a missing value follows the node's default child (kernel: the NaN-routing tile copies)
+                go_left = np.where(np.isnan(x), dleft[base + node] != 0, go_left)
             nxt = np.where(go_left, t.left[base + node], t.right[base + node])
             node = np.where(active, nxt, node)
             active = t.feature[base + node] >= 0

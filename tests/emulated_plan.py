@@ -35,9 +35,15 @@ class EmulatedPlan:
         if not self.models:
             out = E
         else:
-            status |= (~np.isfinite(E)).any(axis=1).astype(np.int32) * nat.ROW_NONFINITE_INPUT
+            # NaN routing (b2s_trees3.cuh): when every model is a tree ensemble that routes missing values, the plan has
+            # no feature steps but an Imputer, and no linear scorer, a NaN is data and only Inf flags the row
+            nan_ok = (all(kind == "trees" and getattr(m, "nan_ok", False) for kind, m in self.models)
+                      and not self.prog.maps and all(k == nat.OUT_COPY for _n, _s, k, _a in self.prog.cols)
+                      and [s for _n, s, _k, _a in self.prog.cols] == list(range(self.n_in)))
+            bad = np.isinf(E) if nan_ok else ~np.isfinite(E)
+            status |= bad.any(axis=1).astype(np.int32) * nat.ROW_NONFINITE_INPUT
             with np.errstate(all="ignore"):
-                per = emu.predict(self.models, np.where(np.isfinite(E), E, 0.0).astype(np.float32)) if len(X) else np.zeros((0, self.n_models))
+                per = emu.predict(self.models, np.where(bad, 0.0, E).astype(np.float32)) if len(X) else np.zeros((0, self.n_models))
             kind = self.vote[0] if self.vote is not None else nat.VOTE_NONE
             if kind == nat.VOTE_NONE:
                 out = per
