@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-BYTES_PER_EVENT = {"flow3_ens4": 260, "flow3_linear": 260, "trees_ens4": 516, "ingest6": 2280, "enrich_ens4": 536}
+BYTES_PER_EVENT = {"flow3_ens4": 260, "flow3_linear": 260, "trees_ens4": 516, "router8": 260, "ingest6": 2280, "enrich_ens4": 536}
 
 
 def parse():
@@ -42,6 +42,13 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="wall budget of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--launches-per-step", type=int, default=0,
+                    help="a step = this many back-to-back launches over rotating batches (default: as many as fill ~10 ms, so "
+                         "that the K timed steps hold >= 200 ms of kernels)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config table of the default run")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = --batch events per GPU; strong = --batch events in total, split over the GPUs "
+                         "(BASELINE configs[3]: --workload router8 --scaling strong --batch 65536)")
     ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 ensemble-merge: p2p = votes stored into every rank's buffer from the kernel epilogue over "
                          "NVLink peer memory (fused); nccl = a separate all_gather per step")
@@ -59,7 +66,43 @@ def make_workload(name, n_rows, seed=2):
         return flow3_workload(n_rows=n_rows, n_num=56, n_cat=8, seed=seed, n_models=4)
     if name == "flow3_linear":
         return flow3_workload(n_rows=n_rows, n_num=56, n_cat=8, seed=seed, n_models=1)
+    if name == "router8":
+        return router8_workload(n_rows, seed=4)
     return tree_cfg3_workload(n_rows, seed=3)
+
+
+class Router8Workload:
+    """BASELINE configs[3]: X (n, 64) float32 ~ N(0,1), seed 4; a VotingEnsemble router of 8 scorers over
+    the 64 raw features -- 4 linear (random float64 weights, like configs[1]'s) and 4 GradientBoostingRegressor(100 trees,
+    depth 6) fit on 20 000 rows (the committed fixtures tests/golden/trees_cfg4_reg.pkl.xz)"""
+
+    def __init__(self, X, models):
+        self.X, self.models, self.kind = X, models, "regression"
+
+    def build_server(self, api, executor="array", **kw):
+        fn = api.new_function("router8", kind="serving")
+        graph = fn.set_topology("router", api.VotingEnsemble(vote_type="regression", executor_type=executor))
+        for i, m in enumerate(self.models):
+            graph.add_route(f"m{i + 1}", class_name="SKLearnModelServer", model=m, model_path="")
+        return fn.to_mock_server(namespace={"SKLearnModelServer": api.SKLearnModelServer}, **kw)
+
+
+def router8_workload(n_rows, seed=4):
+    import lzma
+
+    import cloudpickle
+    from sklearn.linear_model import LinearRegression
+
+    with lzma.open(os.path.join(ROOT, "tests", "golden", "trees_cfg4_reg.pkl.xz"), "rb") as fp:
+        trees = cloudpickle.load(fp)
+    wr = np.random.default_rng(seed + 20)
+    models = []
+    for i in range(4):
+        lin = LinearRegression()
+        lin.coef_, lin.intercept_, lin.n_features_in_ = wr.normal(size=64), float(wr.normal()), 64
+        models += [lin, trees[i]]  # alternating: linear, tree, linear, tree ...
+    X = np.random.default_rng(seed).normal(size=(n_rows, 64)).astype(np.float32)
+    return Router8Workload(X, models)
 
 
 def tree_cfg3_workload(n_rows, seed=3, kind="reg"):
@@ -306,6 +349,8 @@ def workload_desc(name):
     return {
         "flow3_ens4": "3-step flow Imputer->OneHotEncoder->VotingEnsemble(4 linear models), 64-feat f32 (56 num + 8 cat x4 -> 88)",
         "flow3_linear": "3-step flow Imputer->OneHotEncoder->linear predict, 64-feat f32 (BASELINE configs[1])",
+        "router8": "router of 8 scorers (4 linear + 4 GradientBoostingRegressor(100 trees, depth 6)), 64-feat f32, sharded by events "
+                   "with the fused ensemble-merge (BASELINE configs[3], SURVEY 8(d) config 4)",
         "trees_ens4": "VotingEnsemble of 4 GradientBoostingRegressor(100 trees, depth 6, fit on 20 000 rows, all features), "
                       "128-feat f32 (BASELINE configs[2], SURVEY 8(d) config 3)",
         "enrich_ens4": "real-time enrichment: entity keys -> online feature table (4 Mi keys x 64 f32, 1 GiB in HBM) -> $mean imputing "
@@ -315,6 +360,97 @@ def workload_desc(name):
                    "(BASELINE configs[4])",
     }[name]
 
+
+
+# ------------------------------------------------------------------------------------------ per-config table
+def serving_config_bench(nat, torch, name, B, min_ms=60.0, e2e_ms=250.0, seed=2):
+    """one row of the `configs` table: the fused plan of workload `name` at `B` events per launch -- CUDA-event time of
+    back-to-back launches over rotating batches (> L2 between re-reads), and the same batch through the public API from pinned
+    host memory (H2D + kernel + D2H per call)"""
+    wl = make_workload(name, min(B, 65536), seed)
+    server, plan, names = build_server(name, wl)
+    F = wl.X.shape[1]
+    row_bytes = F * 4
+    nbuf = max(2, int(np.ceil(2 * 126e6 / (B * row_bytes))) + 1)
+    reps = int(np.ceil(nbuf * B / wl.X.shape[0]))
+    big = torch.from_numpy(np.tile(wl.X, (reps, 1))[: nbuf * B]).cuda()
+    ptrs = [big.data_ptr() + i * B * row_bytes for i in range(nbuf)]
+    out = torch.empty(B * plan.out_cols, dtype=torch.float32, device="cuda")
+    plan.time_device(ptrs, B, row_bytes, out.data_ptr(), 5)
+    probe = plan.time_device(ptrs, B, row_bytes, out.data_ptr(), 10) / 10
+    iters = int(min(20000, max(20, min_ms / max(probe, 1e-4))))
+    l0 = nat.launch_count()
+    ms = plan.time_device(ptrs, B, row_bytes, out.data_ptr(), iters) / iters
+    launches = nat.launch_count() - l0
+    peak, _src = measured_peak()
+    bpe = BYTES_PER_EVENT[name]
+    row = {"workload": name, "batch": B, "kernel": plan.kernel, "ms_per_launch": ms, "events_per_s": B / (ms * 1e-3),
+           "algorithmic_bytes_per_event": bpe, "roofline_frac": bpe * B / (ms * 1e-3) / 1e9 / peak, "launches_timed": int(launches),
+           "timed_ms": ms * iters, "input_rotation": f"{nbuf} batches, {nbuf * B * row_bytes / 1e6:.0f} MB"}
+    hin = [nat.pinned_empty((B, F), np.float32) for _ in range(2)]
+    src = np.tile(wl.X, (int(np.ceil(B / wl.X.shape[0])), 1))[:B]
+    for j, h in enumerate(hin):
+        h[:] = np.roll(src, j * 131, axis=0)
+    for j in range(3):
+        server.run_batch(hin[j % 2], names=names, with_status=True)
+    t0 = time.perf_counter()
+    server.run_batch(hin[0], names=names, with_status=True)
+    one = time.perf_counter() - t0
+    n = int(min(3000, max(5, e2e_ms * 1e-3 / max(one, 1e-6))))
+    t0 = time.perf_counter()
+    for j in range(n):
+        server.run_batch(hin[j % 2], names=names, with_status=True)
+    dt = time.perf_counter() - t0
+    row["e2e_events_per_s"] = B * n / dt
+    row["e2e_ms_per_call"] = 1e3 * dt / n
+    row["e2e_calls_timed"] = n
+    del big, out, hin
+    return row
+
+
+def ring_bench(nat, name="flow3_ens4", seconds=0.5):
+    """the coalescing ring (b2s_submit / b2s_wait: the replacement of storey's emit / await_result) by itself: native
+    producer threads, each emitting a few rows and awaiting them; and `GraphServer.run_events` / `emit` + `await_result`
+    (the per-event Python callers of the same ring)"""
+    wl = make_workload(name, 8192, 5)
+    server, plan, names = build_server(name, wl)
+    X = np.ascontiguousarray(wl.X)
+    rows = []
+    for producers, per in ((1, 1), (8, 1), (32, 1), (128, 1), (8, 16), (32, 16), (128, 16)):
+        plan.ring_bench(X, producers, per, 0.1)
+        rows.append(plan.ring_bench(X, producers, per, seconds))
+    bodies = wl.rows_as_dicts(limit=4096)
+    server.run_events(bodies[:64])
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < seconds:
+        server.run_events(bodies)
+        reps += 1
+    run_events = {"events_per_s": reps * len(bodies) / (time.perf_counter() - t0), "batch": len(bodies),
+                  "api": "GraphServer.run_events(list of feature dicts): pack -> one fused launch -> per-event responses"}
+    lat = []
+    for body in bodies[:300]:
+        t0 = time.perf_counter()
+        server.await_result(server.emit(body))
+        lat.append((time.perf_counter() - t0) * 1e6)
+    return {"how": "b2s_ring_bench: N native threads, each b2s_submit(rows) + b2s_wait(ticket) in a loop (default ring: "
+                   "4 slots x 65536 rows, max_wait_us 200); events/s = rows served / wall",
+            "native": rows, "run_events": run_events,
+            "emit_await_one_caller_us": {"p50": float(np.percentile(lat[20:], 50)), "p99": float(np.percentile(lat[20:], 99)),
+                                         "how": "GraphServer.emit(body) + await_result(ticket), one Python caller (pays max_wait_us)"}}
+
+
+def compact_line(line):
+    """a full bench line of another workload -> one row of the `configs` table"""
+    r = line["roofline"]
+    row = {"workload": line["config"]["workload"].split(",")[0][:60], "batch": line["config"]["batch_per_gpu"], "kernel": r["kernel"],
+           "ms_per_launch": r["kernel_ms_per_launch"], "events_per_s": line["value"],
+           "algorithmic_bytes_per_event": r["algorithmic_bytes_per_event"], "roofline_frac": r["frac"],
+           "launches_timed": line["gpu_launches"], "p50_launch_us_at_4096": line["p50_step_latency_us"]["p50"]}
+    if "e2e" in line:
+        row["e2e_events_per_s"] = line["e2e"]["value"]
+        row["e2e_api"] = line["e2e"]["api"][:80]
+    return row
 
 # ------------------------------------------------------------------------------------------ main (b200 arm)
 def main():
@@ -331,7 +467,10 @@ def main():
         return main_ingest(args, rank, local_rank, world)
     if name == "enrich_ens4":
         return main_enrich(args, rank, local_rank, world)
-    B = args.batch or (262144 if name == "trees_ens4" else 1048576)
+    B = args.batch or (262144 if name == "trees_ens4" else (65536 if name == "router8" else 1048576))
+    if args.scaling == "strong":
+        B = max(64, B // world)  # the global batch is fixed; every GPU takes its share
+    default_run = name == "flow3_ens4" and world == 1 and not args.batch and not args.no_configs
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -367,39 +506,59 @@ def main():
     stream = torch.cuda.Stream()  # a real (non-NULL) stream: kernels, NCCL and the timing events all ride on it
     torch.cuda.set_stream(stream)
     merge = args.merge if world > 1 else "none"
-    merged_buf = None
+    comm = None
     if merge == "p2p":
-        # every rank owns a (world*B, out_cols) response buffer; the kernels of ALL ranks store their shard's votes
-        # into ALL of them over NVLink peer mappings (CUDA IPC), so no collective runs in the step
+        # the product's communicator (mlrun_b200.sharding.MergeComm / b2s_comm_*): every rank owns the merged response rows,
+        # double buffered, plus completion flags; the kernels of ALL ranks store their shard's votes into ALL of them over
+        # NVLink peer mappings (CUDA IPC) and publish a flag; no collective and no host barrier run in the step
+        from mlrun_b200.sharding import MergeComm, torch_exchange
+
         try:
-            merged_buf = nat.DeviceBuffer(world * B * plan.out_cols * 4)
-            handles = [None] * world
-            dist.all_gather_object(handles, nat.ipc_export(merged_buf.ptr))
-            peers = [merged_buf.ptr if r == rank else nat.ipc_open(handles[r]) for r in range(world)]
-            # the epilogue stores to the targets in list order: start every rank at its right-hand neighbour, so that at any
-            # moment the ranks write to DIFFERENT destinations instead of all converging on rank 0, then rank 1, ...
-            if os.environ.get("B2S_MERGE_ROTATE", "1") != "0":
-                peers = peers[rank + 1:] + peers[:rank + 1]
-            plan.set_merge_targets(peers, rank * B)
+            comm = MergeComm(rank, world, B, plan.out_cols, torch_exchange(dist))
+            comm.attach(plan)
         except Exception as exc:  # noqa: BLE001 -- no peer access on this box: use the NCCL merge
             print(f"[rank {rank}] p2p merge unavailable ({exc}); using nccl", file=sys.stderr)
             merge = "nccl"
         flags = torch.tensor([1 if merge == "p2p" else 0], device="cuda")
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         if int(flags.item()) == 0 and merge == "p2p":
-            plan.set_merge_targets([], 0)
+            comm.detach(plan)
+            comm = None
             merge = "nccl"
+    last_merged = [None]
 
-    def step(i):
+    def launch(i):
         plan.run_device(bufs[i % nbuf].data_ptr(), B, row_bytes, out.data_ptr(), None, stream.cuda_stream)
         if merge == "nccl":  # ensemble-merge: every rank ends up with every shard's votes (4 B/event)
             dist.all_gather_into_tensor(gathered, out)
+        elif merge == "p2p":  # the step is over when this rank has seen the completion flags of all shards
+            last_merged[0] = comm.wait(stream.cuda_stream)[0]
+
+    inner = args.launches_per_step
+
+    def step(i):  # one step = `inner` launches, each over the next of the rotating batches
+        for j in range(inner):
+            launch(i * inner + j)
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    if inner <= 0:  # size a step to ~10 ms of launches (the same on every rank: the probe's maximum)
+        for i in range(5):
+            launch(i)
+        sync()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for i in range(10):
+            launch(i)
+        p1.record(stream)
+        sync()
+        probe = torch.tensor([p0.elapsed_time(p1) / 10], device="cuda")
+        if world > 1:
+            dist.all_reduce(probe, op=dist.ReduceOp.MAX)
+        inner = int(max(1, min(1000, round(10.0 / max(float(probe.item()), 1e-3)))))
     for i in range(max(args.warmup, 3)):
         step(i)
     sync()
@@ -423,17 +582,27 @@ def main():
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     merge_check = None
     if merge == "p2p":
-        # every rank must now hold every shard: compare a checksum of each rank's own shard with what landed here
-        full = merged_buf.download(np.float32, (world * B, plan.out_cols))
-        mine = torch.tensor(full[rank * B:(rank + 1) * B].astype(np.float64).sum(axis=0)[:1], device="cuda")
-        sums = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(sums, mine)
-        got = [float(full[r * B:(r + 1) * B].astype(np.float64).sum(axis=0)[0]) for r in range(world)]
-        merge_check = all(abs(got[r] - float(sums[r].item())) <= 1e-6 * max(1.0, abs(got[r])) for r in range(world))
-        plan.set_merge_targets([], 0)  # the single-GPU measurements below write locally again
+        # every rank must now hold every shard: the last step's merged rows against the same launch scored locally
+        comm.check()
+        full = np.empty((world * comm.max_rows, plan.out_cols), dtype=np.float32)
+        nat.check(nat.load().b2s_memcpy_d2h(full.ctypes.data, last_merged[0], full.nbytes))
+        comm.detach(plan)  # the single-GPU measurements below write locally again
+        last = inner * args.steps - 1 if inner > 0 else args.steps - 1
+        plan.run_device(bufs[last % nbuf].data_ptr(), B, row_bytes, out.data_ptr(), None, stream.cuda_stream)
+        torch.cuda.synchronize()
+        mine = out.cpu().numpy().reshape(B, plan.out_cols)
+        ok_mine = bool(np.array_equal(full[rank * comm.max_rows: rank * comm.max_rows + B], mine))
+        sums = [None] * world
+        dist.all_gather_object(sums, float(mine.astype(np.float64).sum()))
+        got = [float(full[r * comm.max_rows: r * comm.max_rows + B].astype(np.float64).sum()) for r in range(world)]
+        merge_check = ok_mine and all(abs(got[r] - sums[r]) <= 1e-9 * max(1.0, abs(got[r])) for r in range(world))
+        oks = [None] * world
+        dist.all_gather_object(oks, merge_check)
+        merge_check = all(oks)
 
     # kernel-only time of the dominant kernel (no collective), for the roofline
-    kms = plan.time_device([b.data_ptr() for b in bufs], B, row_bytes, out.data_ptr(), max(args.steps, 10)) / max(args.steps, 10)
+    n_k = max(args.steps * inner, 10)
+    kms = plan.time_device([b.data_ptr() for b in bufs], B, row_bytes, out.data_ptr(), n_k) / n_k
 
     # latency at the configured serving batch (4096 events): one launch per batch, CUDA-event timed
     lat = []
@@ -504,15 +673,16 @@ def main():
         peak, peak_src = measured_peak()
         bpe = BYTES_PER_EVENT[name]
         achieved = bpe * B / (kms * 1e-3) / 1e9
-        value = world * B * args.steps / (ms * 1e-3)
+        value = world * B * inner * args.steps / (ms * 1e-3)
         line = {
             "metric": "events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32 in / f64 accumulate", "data": "synthetic",
             "config": {"workload": workload_desc(name), "batch_per_gpu": B, "global_batch": B * world,
+                       "launches_per_step": inner, "events_per_step_per_gpu": B * inner, "timed_region_ms": ms,
                        "parallelism": f"event-sharded x{world}" + {"none": "", "nccl": " + NCCL all-gather of votes per step",
-                                                                    "p2p": " + fused P2P ensemble-merge (votes stored to every "
-                                                                           "rank over NVLink from the kernel epilogue)"}[merge],
+                                                                    "p2p": " + fused P2P ensemble-merge (votes stored to every rank over NVLink "
+                                                                           "from the kernel epilogue, completion flags awaited on the device each step)"}[merge],
                        "merge_verified": merge_check,
                        "l2": f"{nbuf} rotating input buffers of {B * row_bytes / 1e6:.0f} MB (> 126 MB L2 between re-reads)",
                        "device": info["name"], "kernel": plan.kernel},
@@ -522,7 +692,9 @@ def main():
                                     "e2e_how": "wall clock of DevicePlan.run on 4096 pinned host rows (H2D + kernel + D2H + status), "
                                                "1000 samples after 100 warm-ups"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(name, B), "kernel": plan.kernel, "algorithmic_bytes_per_event": bpe,
+                         "traffic": measured_traffic(name, B), "traffic_source": "from_profile: ncu --set full capture of this "
+                         "kernel (profiles/traffic.json), scaled to this launch; not measured in this run",
+                         "kernel": plan.kernel, "algorithmic_bytes_per_event": bpe,
                          "kernel_ms_per_launch": kms, "peak_source": peak_src},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -533,12 +705,42 @@ def main():
             line["wire"] = wire
         if cpu:
             line["cpu_baseline"] = cpu
+        if default_run:
+            # every config of BASELINE.json (and the SURVEY 8(f) callers) under the same clocks, one row each
+            torch.cuda.synchronize()
+            del bufs, base
+            torch.cuda.empty_cache()
+            rows = []
+            for nm, bb in (("flow3_ens4", 4096), ("flow3_ens4", 65536), ("flow3_ens4", 1048576), ("flow3_linear", 4096),
+                           ("flow3_linear", 1048576), ("trees_ens4", 16384), ("trees_ens4", 262144)):
+                try:
+                    rows.append(serving_config_bench(nat, torch, nm, bb))
+                except Exception as exc:  # noqa: BLE001 -- a failing row must not hide the others
+                    rows.append({"workload": nm, "batch": bb, "error": f"{type(exc).__name__}: {exc}"})
+                torch.cuda.empty_cache()
+            import copy
+
+            sub = copy.copy(args)
+            sub.no_cpu_baseline, sub.steps, sub.warmup, sub.batch = True, 200, 3, 0
+            for nm, fn in (("ingest6", main_ingest), ("enrich_ens4", main_enrich)):
+                try:
+                    row = compact_line(fn(sub, 0, local_rank, 1, emit=False))
+                    row["workload"] = nm
+                    rows.append(row)
+                except Exception as exc:  # noqa: BLE001
+                    rows.append({"workload": nm, "error": f"{type(exc).__name__}: {exc}"})
+                torch.cuda.empty_cache()
+            line["configs"] = rows
+            try:
+                line["ring"] = ring_bench(nat)
+            except Exception as exc:  # noqa: BLE001
+                line["ring"] = {"error": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def main_ingest(args, rank, local_rank, world):
+def main_ingest(args, rank, local_rank, world, emit=True):
     """config 5: the columnar feature-set plan.  Rows shard over ranks with no exchange at all (every rank ingests its
     own partition, as the reference's N workers write their own target partitions)."""
     name = "ingest6"
@@ -674,9 +876,11 @@ def main_ingest(args, rank, local_rank, world):
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        if emit:
+            print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 def _enrich_setup(api, n_keys, n_feat, seed):
@@ -721,7 +925,7 @@ def _enrich_cpu_worker(args):
     return n_events, time.perf_counter() - t0
 
 
-def main_enrich(args, rank, local_rank, world):
+def main_enrich(args, rank, local_rank, world, emit=True):
     """SURVEY 8(f) #3: keys -> device hash table gather (+ imputing) -> fused scoring plan; two launches per step"""
     name = "enrich_ens4"
     B = args.batch or 1048576
@@ -866,9 +1070,11 @@ def main_enrich(args, rank, local_rank, world):
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        if emit:
+            print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 if __name__ == "__main__":

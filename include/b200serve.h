@@ -85,7 +85,8 @@ typedef struct b2s_devinfo {
 int b2s_version(void);
 const char* b2s_last_error(void);
 /* Replaces: nothing in the reference (device bring-up).  cfg is "key=value;..." or NULL:
- *   ring_slots (4), max_batch (65536 rows), max_wait_us (200).  Idempotent per process. */
+ *   ring_slots (4), max_batch (65536 rows), max_wait_us (0: a coalesced batch leaves as soon as the dispatcher is free, so
+ *   batches form while the previous one runs; > 0: the oldest row may wait that long for company).  Idempotent per process. */
 int b2s_init(int device_ordinal, const char* cfg);
 int b2s_shutdown(void);
 int b2s_device_info(b2s_devinfo* out);
@@ -162,12 +163,15 @@ int b2s_plan_out_info(b2s_plan_t plan, int32_t* out_cols, int32_t* out_is_int);
  * d_status may be NULL. */
 int b2s_run_device(b2s_plan_t plan, const void* d_rows, int64_t n_rows, int64_t row_stride_bytes, void* d_out,
                    int32_t* d_status, void* stream);
-/* Synchronous host call: pinned staging -> H2D -> kernels -> D2H -> out.  row_status / stats may be NULL. */
+/* Synchronous host call: pinned staging -> H2D -> kernels -> D2H -> out.  row_status / stats may be NULL.
+ * Batches of at most B2S_ZEROCOPY_ROWS (8192) rows skip both copies: the kernels read the rows from (and write the votes
+ * to) pinned host memory over PCIe themselves -- one launch and one synchronisation, the latency path of a serving batch;
+ * pinned batches of 128 Ki rows and more are pipelined in chunks (copy of chunk c + 1 under the kernels of chunk c). */
 int b2s_run_host(b2s_plan_t plan, const void* rows, int64_t n_rows, int64_t row_stride_bytes, void* out,
                  int64_t out_bytes, int32_t* row_status, b2s_stats* stats);
 /* Coalescing path (thread-safe, many producers): rows are copied into a pinned ring slot; a dispatcher
- * thread seals a batch when it holds max_batch rows or the oldest row waited max_wait_us, and runs
- * H2D -> kernels -> D2H on its own streams.  b2s_wait blocks until the ticket's batch completed and copies
+ * thread seals a batch when it holds max_batch rows or the oldest row waited max_wait_us (0: as soon as the dispatcher is
+ * free -- batches form while the previous one runs), and runs it on its own stream (small batches zero-copy, like b2s_run_host).  b2s_wait blocks until the ticket's batch completed and copies
  * that ticket's rows out.  This is the replacement of storey's SyncEmitSource.emit / await_result hand-off
  * (serving/states.py:1283-1287).  A ring slot is recycled when every ticket of its batch was collected, and the ring
  * has `ring_slots` (b2s_init cfg, default 4) batches: a producer that keeps submitting without collecting its tickets
@@ -196,6 +200,29 @@ int b2s_plan_set_merge_targets(b2s_plan_t plan, void* const* peer_out, int32_t n
 int b2s_ipc_export(void* dptr, void* handle64 /* 64 bytes out */);
 int b2s_ipc_open(const void* handle64, void** dptr_out);
 int b2s_ipc_close(void* dptr);
+
+/* The same exchange as a product object: a communicator owns, per rank, ONE device allocation -- completion flags and the
+ * merged response rows, double buffered -- that every peer maps over CUDA IPC.  Bootstrap needs any out-of-band channel
+ * that can all-gather 64 bytes per rank (torch.distributed, MPI, a file, a socket ...):
+ *     b2s_comm_create(rank, world, max_rows_per_rank, out_cols, &c);  b2s_comm_handle(c, mine);
+ *     <all-gather the 64-byte handles>;  b2s_comm_connect(c, all);  b2s_plan_attach_comm(plan, c);
+ * Every b2s_run_device / b2s_run_host / ring batch of an attached plan is then one STEP (epoch e = 1, 2, ...) of the
+ * ensemble-merge (serving/routers.py:414-455 fans the event out to the routes, :789-810 reduces them; here the rows are
+ * sharded and the votes merged): the kernels store this rank's votes into parity e & 1 of EVERY rank's merged rows at row
+ * block `rank`, and the launch's last CTA publishes e in every rank's flag array (st.release.sys).  b2s_comm_wait enqueues
+ * a kernel that acquires all `world` flags of THIS rank at the current epoch, so work enqueued behind it (a D2H copy, the
+ * next kernel) reads a complete response; *d_merged is that response, (world x max_rows_per_rank x out_cols) words, rank
+ * r's rows at r * max_rows_per_rank.  Ranks must wait on every step before launching the next one: seeing all flags of
+ * step e proves that every peer has consumed step e - 1, which is what makes two buffers enough.  A peer that never
+ * signals makes the wait give up after 2 s (b2s_comm_check reports B2S_ERR_TIMEOUT) instead of hanging the GPU. */
+typedef struct b2s_comm_s* b2s_comm_t;
+int b2s_comm_create(int32_t rank, int32_t world, int64_t max_rows_per_rank, int32_t out_cols, b2s_comm_t* out);
+int b2s_comm_handle(b2s_comm_t comm, void* handle64 /* 64 bytes out */);
+int b2s_comm_connect(b2s_comm_t comm, const void* all_handles /* world x 64 bytes, in rank order */);
+int b2s_plan_attach_comm(b2s_plan_t plan, b2s_comm_t comm /* NULL detaches */);
+int b2s_comm_wait(b2s_comm_t comm, void* stream, const void** d_merged, uint32_t* epoch);
+int b2s_comm_check(b2s_comm_t comm);
+int b2s_comm_destroy(b2s_comm_t comm);
 
 /* pinned host memory for zero-extra-copy submits and for bench.py's e2e leg */
 void* b2s_alloc_pinned(size_t bytes);

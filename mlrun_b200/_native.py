@@ -84,6 +84,13 @@ SIGNATURES = {
     "b2s_ring_bench": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, C.c_double, C.POINTER(_i64), C.POINTER(C.c_double),
                                  C.POINTER(C.c_double)]),
     "b2s_plan_set_merge_targets": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i64]),
+    "b2s_comm_create": (C.c_int, [_i32, _i32, _i64, _i32, C.POINTER(_vp)]),
+    "b2s_comm_handle": (C.c_int, [_vp, _vp]),
+    "b2s_comm_connect": (C.c_int, [_vp, _vp]),
+    "b2s_plan_attach_comm": (C.c_int, [_vp, _vp]),
+    "b2s_comm_wait": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.POINTER(C.c_uint32)]),
+    "b2s_comm_check": (C.c_int, [_vp]),
+    "b2s_comm_destroy": (C.c_int, [_vp]),
     "b2s_ipc_export": (C.c_int, [_vp, _vp]),
     "b2s_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
     "b2s_ipc_close": (C.c_int, [_vp]),

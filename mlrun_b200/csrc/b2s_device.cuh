@@ -52,6 +52,33 @@ struct ModelDesc {
   int32_t pad;
 };
 
+// Completion signal of the fused ensemble-merge (b2s_comm_*): when every CTA of the launch that stores the votes has
+// finished, the last one publishes `epoch` in slot `rank` of EVERY target's flag array with a system-scope release store;
+// a reader that acquires all n flags of its own array at `epoch` therefore sees every shard's rows of that step.
+struct MergeSig {
+  uint32_t* flags[8];  // the flag array of every target (own GPU included), in peer memory (NVLink)
+  uint32_t* counter;   // CTAs of this launch that are done (this GPU's memory; the last one resets it)
+  int32_t n;           // 0: no signal
+  int32_t rank;
+  uint32_t epoch;
+  int32_t pad;
+};
+
+__device__ __forceinline__ void merge_signal(const MergeSig& m) {
+  if (m.n <= 0) return;
+  __threadfence_system();  // this thread's remote stores are performed before what follows
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(m.counter, 1u);
+    if (prev == gridDim.x - 1) {  // every other CTA has fenced its stores and counted itself
+      *m.counter = 0;             // launches of a plan are stream ordered: the next one finds a clean counter
+      __threadfence_system();
+      for (int g = 0; g < m.n; ++g)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(m.flags[g] + m.rank), "r"(m.epoch) : "memory");
+    }
+  }
+}
+
 struct KParams {
   // ---- batch
   const char* rows;
@@ -97,6 +124,7 @@ struct KParams {
   int32_t tpr;                // LINEAR: threads per row (slices of the row's 16-byte chunks)
   int32_t sm_part, sm_pst, sm_chunk;
   const uint8_t* chunk_kind;  // [ceil(n_in/4)] 0 = four plain numeric columns (fast path), 1 = generic
+  MergeSig sig;               // completion signal of the ensemble-merge (kernels that store the votes)
 };
 
 // ------------------------------------------------------------------------------------------ helpers
@@ -539,6 +567,7 @@ __global__ void __launch_bounds__(512) rows_kernel(const __grid_constant__ KPara
     if (stage == S) stage = 0;
   }
   cp_async_wait<0>();
+  if (MODE != MODE_STORE) merge_signal(p.sig);
 }
 
 }  // namespace b2s

@@ -44,6 +44,7 @@ struct RTParams {
   float* peers[8];   // ensemble-merge targets (see KParams)
   int64_t peer_off;
   int32_t n_peers;
+  MergeSig sig;      // completion signal of the merge (b2s_device.cuh)
   const double* wcat;       // [n_cat][NS] (global; copied to shared memory, plus a zero row)
   const double* vote_w_g;   // generic epilogue
   const ModelDesc* models;
@@ -475,6 +476,7 @@ __global__ void __launch_bounds__(128 * TPR / RPT, RPT == 2 ? RT_R2_MINB : (TPR 
     if (stage == S) stage = 0;
   }
   cp_async_wait<0>();
+  merge_signal(p.sig);
 }
 
 }  // namespace b2s

@@ -67,7 +67,7 @@ struct Global {
   cudaStream_t copy_stream = nullptr;  // host->device copies of a chunked run_host (kernels + D2H stay on `stream`)
   int ring_slots = 4;
   int64_t max_batch = 65536;
-  int64_t max_wait_us = 200;
+  int64_t max_wait_us = 0;  // 0: a batch leaves as soon as the dispatcher is free (batches form while the previous one runs)
   std::atomic<int64_t> launches{0};
   std::mutex mu;
 };
@@ -117,6 +117,23 @@ struct Slot {  // one in-flight batch of the coalescing ring
   std::string err_msg;
 };
 
+// Ensemble-merge communicator: ONE device allocation per rank, exported over CUDA IPC and mapped by every peer:
+//   [flags: 64 x uint32][CTA counter][pad to 256 B][merged rows, parity 0][merged rows, parity 1]
+// merged rows = world x max_rows x out_cols 4-byte words; step e (epoch, 1-based) lands in parity e & 1.
+struct b2s_comm_s {
+  int rank = 0, world = 1, out_cols = 1;
+  int64_t max_rows = 0;
+  char* base = nullptr;            // this rank's allocation
+  std::vector<char*> peer_base;    // [world] every rank's allocation as mapped here (peer_base[rank] == base)
+  uint32_t epoch = 0;              // launches signalled so far
+  size_t bytes = 0;
+  bool connected = false;
+  size_t buf_bytes() const { return (size_t)world * max_rows * out_cols * 4; }
+  char* buf(int r, uint32_t e) const { return peer_base[r] + 256 + (size_t)(e & 1u) * buf_bytes(); }
+  uint32_t* flags(int r) const { return reinterpret_cast<uint32_t*>(peer_base[r]); }
+  uint32_t* counter() const { return reinterpret_cast<uint32_t*>(base) + 64; }
+};
+
 struct b2s_plan_s {
   int32_t n_in = 0;
   bool finalized = false;
@@ -150,6 +167,7 @@ struct b2s_plan_s {
   // fused ensemble-merge targets (P2P)
   std::vector<void*> peers;
   int64_t peer_off = 0;
+  struct b2s_comm_s* comm = nullptr;  // attached merge communicator (double-buffered targets + completion flags)
   // shared-memory-resident tree kernel
   bool t2_ok = false;
   int t2_NS = 1, t2_grid = 0, t2_block = 512, t2_smem = 0;
@@ -160,6 +178,7 @@ struct b2s_plan_s {
   struct TreeScratch {
     double* pred = nullptr;
     int32_t* row_bad = nullptr;
+    uint32_t* xt = nullptr;  // trees3: the batch transposed into tiles (t3_prep_kernel)
     int64_t rows = 0;
   };
   std::map<cudaStream_t, TreeScratch> t2_scratch;
@@ -168,6 +187,8 @@ struct b2s_plan_s {
   bool t3_ok = false, t3_miss = false;
   int t3_D = 0, t3_grid = 0, t3_block = 0, t3_smem = 0, t3_cols = 0, t3_parts = 0;
   T3Params t3{};
+  T3Prep t3_prep{};
+  int t3_prep_smem = 0;
   char* d_t3_blob = nullptr;
   const int32_t* d_t3_col_score = nullptr;
   // host staging for run_host
@@ -380,9 +401,14 @@ static int rt_load_mode() {  // B2S_TMA: 0 cp.async (LDGSTS), 1 one TMA bulk cop
   return mode;
 }
 
+struct LaunchCtx {             // per-launch context (launches of one plan may be issued from several threads at once)
+  const KParams* k = nullptr;  // merge targets / completion signal of this launch
+  bool host_rows = false;      // the rows live in mapped host memory (zero-copy small batches): plain cp.async loads
+};
+
 template <int NCH, int NS, int TPR>
 static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
-                                int vec_ok, cudaStream_t st, bool query, int* occ, const B2SGather* gather) {
+                                int vec_ok, cudaStream_t st, bool query, int* occ, const B2SGather* gather, const LaunchCtx* lc) {
   using P = RTParams<NCH, NS>;
   constexpr int LMT = NCH >= 8 ? 2 : 1;  // the tensor-map variants exist for rows of >= 128 bytes
   constexpr int R2 = NCH >= 8 ? 2 : 1;
@@ -416,12 +442,15 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   r.out = (float*)out;
   r.status = status;
   r.vec_ok = vec_ok;
-  r.n_peers = (int)p->peers.size();
-  r.peer_off = p->peer_off;
-  for (int g = 0; g < r.n_peers; ++g) r.peers[g] = (float*)p->peers[g];
+  const KParams* lk = lc ? lc->k : nullptr;
+  r.n_peers = lk ? lk->n_peers : (int)p->peers.size();
+  r.peer_off = lk ? lk->peer_off : p->peer_off;
+  for (int g = 0; g < r.n_peers; ++g) r.peers[g] = lk ? lk->peers[g] : (float*)p->peers[g];
+  r.sig = lk ? lk->sig : MergeSig{};
   r.pitch = p->rt_pitch;
   r.stages = p->rt_stages;
   int mode = vec_ok ? rt_load_mode() : 0;
+  if (lc && lc->host_rows) mode = 0;
   if (mode == 2 && !tmap_ok) mode = 1;
   if (gather) {  // rows come from the online table: one bulk copy per row, source found by key inside the kernel
     mode = 1;
@@ -477,12 +506,12 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
 
 template <int NCH, int NS>
 static cudaError_t rt_launch_t(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
-                               int vec_ok, cudaStream_t st, bool query, int* occ, const B2SGather* gather) {
-  if (p->rt_TPR == 1) return rt_launch_tt<NCH, NS, 1>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ, gather);
+                               int vec_ok, cudaStream_t st, bool query, int* occ, const B2SGather* gather, const LaunchCtx* lc) {
+  if (p->rt_TPR == 1) return rt_launch_tt<NCH, NS, 1>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ, gather, lc);
   if (NCH >= 8 && p->rt_TPR == 2)
-    return rt_launch_tt<NCH, NS, (NCH >= 8 ? 2 : 1)>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ, gather);
+    return rt_launch_tt<NCH, NS, (NCH >= 8 ? 2 : 1)>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ, gather, lc);
   if (NCH >= 16 && p->rt_TPR == 4)
-    return rt_launch_tt<NCH, NS, (NCH >= 16 ? 4 : 1)>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ, gather);
+    return rt_launch_tt<NCH, NS, (NCH >= 16 ? 4 : 1)>(p, rows, stride, n_rows, out, status, vec_ok, st, query, occ, gather, lc);
   return cudaErrorInvalidValue;
 }
 
@@ -508,8 +537,9 @@ static cudaError_t rt_launch_t(b2s_plan_s* p, const void* rows, int64_t stride, 
   } while (0)
 
 static cudaError_t rt_launch(b2s_plan_s* p, const void* rows, int64_t stride, int64_t n_rows, void* out, int32_t* status,
-                             int vec_ok, cudaStream_t st, bool query = false, int* occ = nullptr, const B2SGather* gather = nullptr) {
-  RT_DISPATCH(rt_launch_t, p, rows, stride, n_rows, out, status, vec_ok, st, query, occ, gather);
+                             int vec_ok, cudaStream_t st, bool query = false, int* occ = nullptr, const B2SGather* gather = nullptr,
+                             const LaunchCtx* lc = nullptr) {
+  RT_DISPATCH(rt_launch_t, p, rows, stride, n_rows, out, status, vec_ok, st, query, occ, gather, lc);
   return cudaErrorInvalidValue;
 }
 static void rt_build_any(b2s_plan_s* p, const RTTables& t) {
@@ -538,7 +568,7 @@ extern "C" int b2s_init(int device_ordinal, const char* cfg) {
     std::string c = cfg ? cfg : "";
     G.ring_slots = (int)cfg_get(c, "ring_slots", 4);
     G.max_batch = cfg_get(c, "max_batch", 65536);
-    G.max_wait_us = cfg_get(c, "max_wait_us", 200);
+    G.max_wait_us = cfg_get(c, "max_wait_us", 0);
     if (G.ring_slots < 2) G.ring_slots = 2;
     G.inited = true;
     return B2S_OK;
@@ -823,11 +853,55 @@ static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
   int pitch = n_in4 + 4;
   if (((pitch / 4) & 1) == 0) pitch += 4;
   const size_t land_bytes = std::max((size_t)TR * pitch * 4, (size_t)TR * n_in4 * 4);
-  const size_t fixed = align_up((size_t)n_in4 * 4, 16) + (size_t)32 * TR * 8 + (size_t)xt_words * 4 * (miss ? 2 : 1) + land_bytes +
-                       1024 /* landing alignment */ + (size_t)TR * 4 + 16 + 64;
+  const int kMaxW = kT3MaxWalk;  // walking warps: (kMaxW + kT3Service) * 32 <= 1024 threads
   const size_t lin_bytes = (size_t)n_lin_cols * n_in * 8;
-  if (fixed + lin_bytes + 2 * (size_t)NN * 16 > (size_t)smem_cap) return B2S_OK;
-  const int cap_trees = (int)(((size_t)smem_cap - fixed) / ((size_t)NN * 16));
+  // walking kernel: tables | two partial-sum buffers | two tiles (filled by TMA bulk copies) | four mbarriers
+  auto fixed_bytes = [&](int w) {
+    return 2 * (size_t)std::max(w, kT3MaxLin) * TR * 8 + 2 * (size_t)xt_words * 4 + 128 /* tile alignment */ + 64;
+  };
+  auto capacity = [&](int w) {  // trees one CTA can hold with w walking warps (0: the plan does not fit at all)
+    const size_t fixed = fixed_bytes(w);
+    if (fixed + std::max(lin_bytes, 2 * (size_t)NN * 16) > (size_t)smem_cap) return 0;
+    return (int)(((size_t)smem_cap - fixed) / ((size_t)NN * 16));
+  };
+  // ---- walking warps per CTA: the partial-sum buffers grow with them, so they decide how many trees a CTA holds and with
+  // that the number of parts; cost = shared-memory wavefronts per row: 8 per part for the transpose, (2 + 3 D) per tree
+  // walk of 32 rows, whole iterations of U trees per warp
+  std::vector<int> group_sizes;
+  for (auto& m : p->models)
+    if (m.kind == MK_TREES)
+      for (int slot = 0; slot < m.n_scores; ++slot) {
+        int n = 0;
+        for (int32_t sl : m.tree_slot) n += sl == slot ? 1 : 0;
+        if (n) group_sizes.push_back(n);
+      }
+  int W = 0;
+  {
+    const char* wenv = getenv("B2S_T3_WARPS");
+    const int w_lo = wenv ? std::max(4, std::min(kMaxW, atoi(wenv))) : 16, w_hi = wenv ? w_lo : kMaxW;
+    double best = 1e300;
+    for (int w = w_lo; w <= w_hi; ++w) {
+      const int cap = capacity(w);
+      if (cap < 1) continue;
+      double cost = n_lin_cols > 0 ? 2.0 : 0.0;
+      int n_parts = n_lin_cols > 0 ? 1 : 0;
+      for (int n : group_sizes) {
+        const int n_chunks = (n + cap - 1) / cap, per = (n + n_chunks - 1) / n_chunks;
+        for (int c0 = 0; c0 < n; c0 += per) {
+          const int nt = std::min(per, n - c0), tpw = (nt + w - 1) / w, iters = (tpw + kT3U - 1) / kT3U;
+          cost += 0.5 + (double)iters * kT3U * w * (2.0 + 3.0 * D) / 32.0;
+          ++n_parts;
+        }
+      }
+      if (n_parts > sms) continue;
+      if (cost < best - 1e-9 || (std::fabs(cost - best) <= 1e-9 && w > W)) {
+        best = cost;
+        W = w;
+      }
+    }
+  }
+  if (W == 0) return B2S_OK;
+  const int cap_trees = capacity(W);
   // ---- parts: per (tree model, score slot) the trees of that slot, split evenly when they exceed a CTA's capacity
   struct HostPart {
     int model, slot, n_trees = 0, n_cols = 1, col0 = 0;
@@ -874,16 +948,18 @@ static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
                 if (leaf) {  // pad: every value goes left, and both children carry the leaf anyway
                   const float inf = std::numeric_limits<float>::infinity();
                   nd.x = 0;
-                  if (miss) nd.y = (uint32_t)0x7fffffff; else memcpy(&nd.y, &inf, 4);
+                  if (miss) nd.y = (uint32_t)0x7fffffff; else memcpy(&nd.y, &inf, 4);  // key(x) + 0 > INT_MAX never holds
                   stack.push_back({2 * it.heap, it.d + 1, it.src});
                   stack.push_back({2 * it.heap + 1, it.d + 1, it.src});
                 } else {
                   const float thr = m.threshold[base + it.src];
                   const bool dl = !m.default_left.empty() && m.default_left[base + it.src] != 0;
-                  nd.x = (uint32_t)(m.feature[base + it.src] * TR * 4 + ((miss && dl) ? xt_words * 4 : 0));
+                  nd.x = (uint32_t)(m.feature[base + it.src] * TR * 4) | ((miss && dl) ? 0x80000000u : 0u);
                   if (miss) {
-                    // NaN threshold ("x < -inf" of an xgboost model): nothing goes left but a missing value that defaults left
-                    nd.y = std::isnan(thr) ? 0x80000000u : (uint32_t)host_key(thr);
+                    // the walk tests key(x) + d > key(t) + d with d = 1 for "missing goes left": NaN's key INT_MAX wraps
+                    // to INT_MIN.  NaN threshold ("x < -inf" of an xgboost model): every value goes right
+                    const uint32_t d = dl ? 1u : 0u;
+                    nd.y = (std::isnan(thr) ? 0x80000000u : (uint32_t)host_key(thr)) + d;
                   } else {
                     memcpy(&nd.y, &thr, 4);
                   }
@@ -893,7 +969,7 @@ static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
                 hp.nodes[(size_t)q * NN + it.heap] = nd;
               }
             }
-            hp.cost = 8.0 + hp.n_trees * (2.0 + 3.0 * D) / 32.0 * 2.0;  // wavefronts per row: transpose + walks
+            hp.cost = 0.5 + hp.n_trees * (2.0 + 3.0 * D) / 32.0 * 2.0;  // shared-memory wavefronts per row (the walks)
             hp.col0 = (int)col_score.size();
             col_score.push_back(so + slot);
             parts.push_back(std::move(hp));
@@ -919,7 +995,7 @@ static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
           }
         so2 += m.n_scores;
       }
-      hp.cost = 8.0 + 2.0 + n_in * n_lin_cols / 32.0 * 0.25;
+      hp.cost = 2.0 + n_in * n_lin_cols / 32.0;
       parts.push_back(std::move(hp));
     }
   }
@@ -952,29 +1028,6 @@ static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
         for (int i = 0; i < P; ++i) want[i] = parts[i].cost;
     }
   }
-  // ---- warps per CTA: whole iterations of U trees per warp, as little padding as possible
-  int W = 25;
-  {
-    const char* wenv = getenv("B2S_T3_WARPS");
-    if (wenv) {
-      W = std::max(4, std::min(32, atoi(wenv)));
-    } else {
-      double best = 1e30;
-      for (int w = 16; w <= 28; ++w) {
-        double waste = 0.0;
-        for (auto& hp : parts) {
-          if (hp.n_trees == 0) continue;
-          const int tpw = (hp.n_trees + w - 1) / w;
-          const int iters = (tpw + kT3U - 1) / kT3U;
-          waste += (double)iters * kT3U * w / hp.n_trees * hp.cost;
-        }
-        if (waste < best - 1e-9 || (std::fabs(waste - best) <= 1e-9 && w > W)) {
-          best = waste;
-          W = w;
-        }
-      }
-    }
-  }
   // ---- one blob: nodes / leaves of every part, the part table, the column -> score map
   BlobBuilder tb;
   std::vector<size_t> o_nodes(P), o_leaves(P);
@@ -997,7 +1050,7 @@ static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
     d.col0 = parts[i].col0;
     d.cta0 = cta0;
     d.n_ctas = n_ctas[i];
-    d.flags_rows = i == 0 ? 1 : 0;
+    d.pad = 0;
     cta0 += n_ctas[i];
   }
   memcpy(tb.data.data() + o_parts, dev.data(), sizeof(T3Part) * P);
@@ -1007,12 +1060,10 @@ static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
   T3Params& t = p->t3;
   memset(&t, 0, sizeof(t));
   t.parts = (const T3Part*)(p->d_t3_blob + o_parts);
-  t.fill = k.fill;
   t.n_in = n_in;
   t.n_parts = P;
   t.warps = W;
-  t.pitch = pitch;
-  t.any_fill = any_fill ? 1 : 0;
+  t.unroll = getenv("B2S_T3_UNROLL") ? atoi(getenv("B2S_T3_UNROLL")) : kT3U;
   t.xt_words = xt_words;
   size_t off = 0;
   auto take = [&](size_t bytes, size_t al) {
@@ -1025,26 +1076,52 @@ static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
   for (auto& hp : parts) max_trees = std::max(max_trees, hp.n_trees);
   take(std::max((size_t)max_trees * NN * 8, lin_bytes), 16);  // nodes (or the linear weights) at offset 0
   t.sm_leaf = take((size_t)max_trees * NN * 8, 16);
-  t.sm_fill = take((size_t)n_in4 * 4, 16);
-  t.sm_part = take((size_t)std::max(W, kT3MaxLin) * TR * 8, 16);
-  t.sm_xt = take((size_t)xt_words * 4 * (miss ? 2 : 1), 128);
-  t.sm_land = take(land_bytes, 1024);
-  t.sm_bad = take((size_t)TR * 4, 16);
-  t.sm_bar = take(16, 16);
+  t.part_words = std::max(W, kT3MaxLin) * TR;
+  t.sm_part = take(2 * (size_t)t.part_words * 8, 16);
+  t.sm_xt = take(2 * (size_t)xt_words * 4, 128);
+  t.sm_bar = take(64, 16);
   if (off > (size_t)smem_cap) {  // cannot happen with the budget above; stay on the safe side
     cudaFree(p->d_t3_blob);
     p->d_t3_blob = nullptr;
     return B2S_OK;
   }
+  // ---- the prepare kernel: transposed tile | landing tile (TMA boxes or padded rows) | fill | flags | mbarrier
+  T3Prep& pr = p->t3_prep;
+  memset(&pr, 0, sizeof(pr));
+  pr.fill = k.fill;
+  pr.n_in = n_in;
+  pr.n_in4 = n_in4;
+  pr.pitch = pitch;
+  pr.any_fill = any_fill ? 1 : 0;
+  {
+    size_t po = 0;
+    auto ptake = [&](size_t bytes, size_t al) {
+      po = align_up(po, al);
+      const size_t o = po;
+      po += bytes;
+      return (int32_t)o;
+    };
+    pr.sm_xt = ptake((size_t)xt_words * 4, 16);
+    pr.sm_land = ptake(land_bytes, 1024);
+    pr.sm_fill = ptake((size_t)n_in4 * 4, 16);
+    pr.sm_bad = ptake((size_t)TR * 4, 16);
+    pr.sm_bar = ptake(16, 16);
+    p->t3_prep_smem = (int)align_up(po, 16);
+    if (p->t3_prep_smem > smem_cap) {
+      cudaFree(p->d_t3_blob);
+      p->d_t3_blob = nullptr;
+      return B2S_OK;
+    }
+  }
   p->t3_smem = (int)align_up(off, 16);
   p->t3_D = D;
   p->t3_miss = miss;
-  p->t3_block = W * 32;
+  p->t3_block = (W + kT3Service) * 32;
   p->t3_grid = cta0;
   p->t3_cols = (int)col_score.size();
   p->t3_parts = P;
   p->t3_ok = true;
-  p->kernels_per_batch = 2;
+  p->kernels_per_batch = 3;
   return B2S_OK;
 }
 
@@ -1626,7 +1703,7 @@ extern "C" const char* b2s_plan_kernel(b2s_plan_t p) {
   static thread_local char buf[200];
   int lm = rt_load_mode();
   if (lm == 2 && !(p->rt_NCH >= 8 && p->n_in == p->rt_NCH * 4 && tensor_map_encoder())) lm = 1;
-  if (p->t3_ok) snprintf(buf, sizeof(buf), "trees3_kernel<D=%d,%s> + t3_vote_kernel (%d parts resident in shared memory, %d warps)", p->t3_D, p->t3_miss ? "NaN routing" : "floats", p->t3_parts, p->t3_block / 32);
+  if (p->t3_ok) snprintf(buf, sizeof(buf), "t3_prep_kernel + trees3_kernel<D=%d,%s> + t3_vote_kernel (%d parts resident in shared memory, %d walking warps)", p->t3_D, p->t3_miss ? "NaN routing" : "floats", p->t3_parts, p->t3.warps);
   else if (p->t2_ok) snprintf(buf, sizeof(buf), "trees_model_kernel<%d> + vote_kernel (models resident in shared memory)", p->t2_NS);
   else if (p->rt_ok) snprintf(buf, sizeof(buf), "rowthread_kernel<NCH=%d,NS=%d,TPR=%d,RPT=%d,%s>", p->rt_NCH, p->rt_NS, p->rt_TPR, lm == 2 ? p->rt_RPT : 1, lm == 2 ? "TMA tensor-map loads" : (lm == 1 ? "TMA bulk loads" : "cp.async loads"));
   else if (p->rw_ok) snprintf(buf, sizeof(buf), "rowwarp_kernel<L=%d,CPL=%d,NS=%d,U=%d,CS=%d>", p->rw_L, p->rw_CPL, p->rw_NS, p->rw_U, p->rw_CS);
@@ -1647,7 +1724,7 @@ extern "C" int b2s_plan_out_info(b2s_plan_t p, int32_t* out_cols, int32_t* out_i
 
 // ------------------------------------------------------------------------------------------ execution
 static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t stride, void* d_out, int32_t* d_status,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool host_rows = false) {
   if (n_rows == 0) return B2S_OK;
   KParams k = p->kp;
   k.rows = (const char*)d_rows;
@@ -1659,8 +1736,29 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
   k.n_peers = (int)p->peers.size();
   k.peer_off = p->peer_off;
   for (int g = 0; g < k.n_peers; ++g) k.peers[g] = (float*)p->peers[g];
+  k.sig = MergeSig{};
+  if (p->comm) {
+    // one more step of the attached communicator: this launch's votes go to parity (epoch & 1) of every rank's merged
+    // rows, at this rank's row block; the launch's last CTA then publishes the epoch in every rank's flag array
+    b2s_comm_s* c = p->comm;
+    if (n_rows > c->max_rows) return fail(B2S_ERR_INVALID, "shard of %lld rows exceeds the communicator's %lld", (long long)n_rows, (long long)c->max_rows);
+    if (p->mode == MODE_STORE) return fail(B2S_ERR_UNSUPPORTED, "transform-only plans have no vote to merge");
+    const uint32_t e = ++c->epoch;
+    k.n_peers = c->world;
+    k.peer_off = (int64_t)c->rank * c->max_rows;
+    k.sig.n = c->world;
+    k.sig.rank = c->rank;
+    k.sig.epoch = e;
+    k.sig.counter = c->counter();
+    for (int g = 0; g < c->world; ++g) {
+      const int r = (c->rank + 1 + g) % c->world;  // start at the right-hand neighbour: the ranks write to different targets
+      k.peers[g] = (float*)c->buf(r, e);
+      k.sig.flags[g] = c->flags(r);
+    }
+  }
   if (p->t3_ok) {
     const int C = p->t3_cols;
+    const int64_t n_tiles = (n_rows + kT3TR - 1) / kT3TR;
     b2s_plan_s::TreeScratch sc;
     {
       std::lock_guard<std::mutex> lk(p->scratch_mu);
@@ -1668,46 +1766,41 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
       if (n_rows > mine.rows) {  // cudaFree waits for the work that still reads the old buffers
         if (mine.pred) cudaFree(mine.pred);
         if (mine.row_bad) cudaFree(mine.row_bad);
+        if (mine.xt) cudaFree(mine.xt);
         mine = b2s_plan_s::TreeScratch{};
         const int64_t cap = std::max<int64_t>(align_up((size_t)n_rows, 64), 65536);
         CUDA_TRY(cudaMalloc(&mine.pred, (size_t)cap * C * 8));
         CUDA_TRY(cudaMalloc(&mine.row_bad, (size_t)cap * 4));
+        CUDA_TRY(cudaMalloc(&mine.xt, (size_t)(cap / kT3TR) * p->t3.xt_words * 4));
         mine.rows = cap;
       }
       sc = mine;
     }
-    T3Params t = p->t3;
-    t.rows = (const char*)d_rows;
-    t.row_stride = stride;
-    t.n_rows = n_rows;
-    t.partial = sc.pred;
-    t.col_stride = sc.rows;
-    t.row_bad = sc.row_bad;
-    t.vec_ok = k.vec_ok;
+    T3Prep pr = p->t3_prep;
+    pr.rows = (const char*)d_rows;
+    pr.row_stride = stride;
+    pr.n_rows = n_rows;
+    pr.xt = sc.xt;
+    pr.row_bad = sc.row_bad;
+    pr.vec_ok = k.vec_ok;
     alignas(64) CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     static const int t3_tma = getenv("B2S_T3_TMA") ? atoi(getenv("B2S_T3_TMA")) : 1;
-    t.use_tmap = (t3_tma && t.vec_ok && (p->n_in % 32) == 0 && encode_rows_map(&tmap, d_rows, n_rows, stride, p->n_in, kT3TR)) ? 1 : 0;
-    G.launches.fetch_add(2, std::memory_order_relaxed);
-    cudaError_t e3 = cudaErrorInvalidValue;
-#define B2S_T3_CASE(DD)                                                                                                   \
-  if (p->t3_D == DD) {                                                                                                      \
-    static std::atomic<bool> attr{false};                                                                                   \
-    if (!attr) {                                                                                                            \
-      CUDA_TRY(cudaFuncSetAttribute(trees3_kernel<DD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.prop.sharedMemPerBlockOptin)); \
-      CUDA_TRY(cudaFuncSetAttribute(trees3_kernel<DD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.prop.sharedMemPerBlockOptin));  \
-      attr = true;                                                                                                          \
-    }                                                                                                                       \
-    if (p->t3_miss) trees3_kernel<DD, true><<<p->t3_grid, p->t3_block, p->t3_smem, st>>>(t, tmap);                          \
-    else trees3_kernel<DD, false><<<p->t3_grid, p->t3_block, p->t3_smem, st>>>(t, tmap);                                    \
-    e3 = cudaGetLastError();                                                                                                \
-  }
-    B2S_T3_CASE(2) B2S_T3_CASE(3) B2S_T3_CASE(4) B2S_T3_CASE(5) B2S_T3_CASE(6) B2S_T3_CASE(7) B2S_T3_CASE(8)
-#undef B2S_T3_CASE
+    pr.use_tmap = (t3_tma && !host_rows && pr.vec_ok && (p->n_in % 32) == 0 && encode_rows_map(&tmap, d_rows, n_rows, stride, p->n_in, kT3TR)) ? 1 : 0;
+    const int resident = std::max(1, (int)G.prop.sharedMemPerMultiprocessor / std::max(p->t3_prep_smem + 1024, 1));
+    const int pgrid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)G.prop.multiProcessorCount * std::min(resident, 4)));
+    G.launches.fetch_add(3, std::memory_order_relaxed);
+    cudaError_t e3 = t3_launch_prep(pr, tmap, p->t3_miss, pgrid, p->t3_prep_smem, (int)G.prop.sharedMemPerBlockOptin, st);
+    if (e3 != cudaSuccess) return fail(B2S_ERR_CUDA, "tree prepare kernel launch failed: %s", cudaGetErrorString(e3));
+    T3Params t = p->t3;
+    t.xt = sc.xt;
+    t.n_rows = n_rows;
+    t.partial = sc.pred;
+    t.col_stride = sc.rows;
+    e3 = t3_launch_walk(t, p->t3_D, p->t3_miss, p->t3_grid, p->t3_block, p->t3_smem, (int)G.prop.sharedMemPerBlockOptin, st);
     if (e3 != cudaSuccess) return fail(B2S_ERR_CUDA, "tree kernel launch failed: %s", cudaGetErrorString(e3));
     const int vgrid = (int)std::max<int64_t>(1, std::min<int64_t>(4 * G.prop.multiProcessorCount, (n_rows + 255) / 256));
-    t3_vote_kernel<<<vgrid, 256, 0, st>>>(k, sc.pred, sc.rows, p->d_t3_col_score, C, sc.row_bad);
-    e3 = cudaGetLastError();
+    e3 = t3_launch_vote(k, sc.pred, sc.rows, p->d_t3_col_score, C, sc.row_bad, vgrid, st);
     if (e3 != cudaSuccess) return fail(B2S_ERR_CUDA, "vote kernel launch failed: %s", cudaGetErrorString(e3));
     return B2S_OK;
   }
@@ -1746,7 +1839,7 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
     alignas(64) CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     static const int t2_tma = getenv("B2S_T2_TMA") ? atoi(getenv("B2S_T2_TMA")) : 1;
-    t.use_tmap = (t2_tma && t.vec_ok && (p->n_in % 32) == 0 && encode_rows_map(&tmap, d_rows, n_rows, stride, p->n_in, t.tile_rows)) ? 1 : 0;
+    t.use_tmap = (t2_tma && !host_rows && t.vec_ok && (p->n_in % 32) == 0 && encode_rows_map(&tmap, d_rows, n_rows, stride, p->n_in, t.tile_rows)) ? 1 : 0;
     if (p->t2_NS == 1) trees_model_kernel<1><<<grid2, p->t2_block, p->t2_smem, st>>>(t, tmap);
     else trees_model_kernel<4><<<grid2, p->t2_block, p->t2_smem, st>>>(t, tmap);
     cudaError_t e2 = cudaGetLastError();
@@ -1759,11 +1852,14 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
   }
   if (p->rt_ok) {
     G.launches.fetch_add(1, std::memory_order_relaxed);
-    cudaError_t e = rt_launch(p, d_rows, stride, n_rows, d_out, d_status, k.vec_ok, st);
+    LaunchCtx lc;
+    lc.k = &k;
+    lc.host_rows = host_rows;
+    cudaError_t e = rt_launch(p, d_rows, stride, n_rows, d_out, d_status, k.vec_ok, st, false, nullptr, nullptr, &lc);
     if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "row-thread kernel launch failed: %s", cudaGetErrorString(e));
     return B2S_OK;
   }
-  if (p->rw_ok && k.vec_ok && k.n_peers == 0) {
+  if (p->rw_ok && k.vec_ok && k.n_peers == 0 && !p->comm && !host_rows) {
     RWParams r = p->rw;
     r.rows = (const char*)d_rows;
     r.row_stride = stride;
@@ -1938,6 +2034,30 @@ extern "C" int b2s_run_host(b2s_plan_t p, const void* rows, int64_t n_rows, int6
       }
       return B2S_OK;
     }
+    // Small batches skip both copies: the kernels read the rows from pinned host memory and write votes and status words
+    // back into pinned host memory over PCIe themselves (one launch, one synchronisation: the latency path of a serving
+    // batch).  Larger ones take the copy engines, which is where the bandwidth is.
+    static const int64_t zc_rows = getenv("B2S_ZEROCOPY_ROWS") ? atoll(getenv("B2S_ZEROCOPY_ROWS")) : 8192;
+    if (n_rows <= zc_rows && p->peers.empty() && !p->comm) {
+      const void* d_src = pinned ? attr.devicePointer : (const void*)p->h_stage_in;
+      if (stats) CUDA_TRY(cudaEventRecord(p->ev[1], st));
+      if (int rc = launch_on(p, d_src, n_rows, row_bytes, p->h_stage_out, (int32_t*)(p->h_stage_out + out_sz), st, true)) return rc;
+      if (stats) CUDA_TRY(cudaEventRecord(p->ev[2], st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      memcpy(out, p->h_stage_out, out_sz);
+      const int32_t* hs = (const int32_t*)(p->h_stage_out + out_sz);
+      int bad = 0;
+      for (int64_t r = 0; r < n_rows; ++r) bad += (hs[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
+      if (row_status) memcpy(row_status, hs, (size_t)n_rows * 4);
+      if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->rows = n_rows;
+        cudaEventElapsedTime(&stats->kernel_ms, p->ev[1], p->ev[2]);  // includes the PCIe traffic of the rows
+        stats->kernels = p->kernels_per_batch;
+        stats->nonfinite_rows = bad;
+      }
+      return B2S_OK;
+    }
     CUDA_TRY(cudaEventRecord(p->ev[0], st));
     CUDA_TRY(cudaMemcpyAsync(p->d_stage_in, src, (size_t)n_rows * row_bytes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaEventRecord(p->ev[1], st));
@@ -2030,20 +2150,35 @@ static void dispatcher_main(b2s_plan_s* p) {
         err_msg = std::string("coalesced batch: ") + what + ": " + cudaGetErrorString(e);
       }
     };
+    static const int64_t zc_rows = getenv("B2S_ZEROCOPY_ROWS") ? atoll(getenv("B2S_ZEROCOPY_ROWS")) : 8192;
+    const bool zero_copy = rows <= zc_rows && p->peers.empty() && !p->comm;
     step(cudaEventRecord(s.e0, st), "event record");
-    step(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st), "H2D copy");
-    step(cudaEventRecord(s.e1, st), "event record");
-    if (!err) {
-      const int rc = launch_on(p, s.d_in, rows, row_bytes, s.d_out, s.d_status, st);
-      if (rc) {
-        err = rc;
-        err_msg = std::string("coalesced batch: ") + g_err;
+    if (zero_copy) {
+      // a small batch: the kernels read the slot's pinned rows and write its pinned result area over PCIe themselves
+      step(cudaEventRecord(s.e1, st), "event record");
+      if (!err) {
+        const int rc = launch_on(p, s.h_in, rows, row_bytes, s.h_out, (int32_t*)(s.h_out + (size_t)p->ring_cap * p->out_cols * 4), st, true);
+        if (rc) {
+          err = rc;
+          err_msg = std::string("coalesced batch: ") + g_err;
+        }
       }
-    }
-    step(cudaEventRecord(s.e2, st), "event record");
-    if (!err) {
-      step(cudaMemcpyAsync(s.h_out, s.d_out, out_sz, cudaMemcpyDeviceToHost, st), "D2H copy");
-      step(cudaMemcpyAsync(s.h_out + (size_t)p->ring_cap * p->out_cols * 4, s.d_status, (size_t)rows * 4, cudaMemcpyDeviceToHost, st), "D2H copy");
+      step(cudaEventRecord(s.e2, st), "event record");
+    } else {
+      step(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st), "H2D copy");
+      step(cudaEventRecord(s.e1, st), "event record");
+      if (!err) {
+        const int rc = launch_on(p, s.d_in, rows, row_bytes, s.d_out, s.d_status, st);
+        if (rc) {
+          err = rc;
+          err_msg = std::string("coalesced batch: ") + g_err;
+        }
+      }
+      step(cudaEventRecord(s.e2, st), "event record");
+      if (!err) {
+        step(cudaMemcpyAsync(s.h_out, s.d_out, out_sz, cudaMemcpyDeviceToHost, st), "D2H copy");
+        step(cudaMemcpyAsync(s.h_out + (size_t)p->ring_cap * p->out_cols * 4, s.d_status, (size_t)rows * 4, cudaMemcpyDeviceToHost, st), "D2H copy");
+      }
     }
     step(cudaEventRecord(s.e3, st), "event record");
     step(cudaEventSynchronize(s.e3), "execution");
@@ -2327,7 +2462,7 @@ extern "C" int b2s_plan_destroy(b2s_plan_t p) {
     if (p->d_t2_blob) cudaFree(p->d_t2_blob);
     if (p->d_t3_blob) cudaFree(p->d_t3_blob);
     for (auto& kv : p->t2_scratch)
-      if (kv.second.pred) { cudaFree(kv.second.pred); cudaFree(kv.second.row_bad); }
+      if (kv.second.pred) { cudaFree(kv.second.pred); cudaFree(kv.second.row_bad); if (kv.second.xt) cudaFree(kv.second.xt); }
     delete p;
     return B2S_OK;
   } catch (const std::exception& e) {
@@ -2370,6 +2505,139 @@ extern "C" int b2s_ipc_open(const void* handle64, void** dptr_out) {
 extern "C" int b2s_ipc_close(void* dptr) {
   try {  // no C++ exception crosses the C boundary
     CUDA_TRY(cudaIpcCloseMemHandle(dptr));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
+}
+
+// ------------------------------------------------------------------------------------------ ensemble-merge communicator
+__global__ void merge_wait_kernel(const uint32_t* flags, int n, uint32_t epoch, uint32_t* timeout_flag, long long max_ns) {
+  // one lane per source rank: acquire its flag until it shows `epoch` (or later)
+  if ((int)threadIdx.x < n) {
+    long long t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+      if ((int32_t)(v - epoch) >= 0) break;
+      long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > max_ns) {  // a peer died: give up instead of hanging the GPU; the host reports it
+        atomicExch(timeout_flag, 1u + threadIdx.x);
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+}
+
+extern "C" int b2s_comm_create(int32_t rank, int32_t world, int64_t max_rows_per_rank, int32_t out_cols, b2s_comm_t* out) {
+  try {  // no C++ exception crosses the C boundary
+    if (!G.inited) return fail(B2S_ERR_STATE, "b2s_init was not called");
+    if (!out || world < 1 || world > 8 || rank < 0 || rank >= world || max_rows_per_rank < 1 || out_cols < 1)
+      return fail(B2S_ERR_INVALID, "bad communicator arguments (at most 8 ranks)");
+    std::unique_ptr<b2s_comm_s> c(new b2s_comm_s);
+    c->rank = rank;
+    c->world = world;
+    c->out_cols = out_cols;
+    c->max_rows = (max_rows_per_rank + 3) / 4 * 4;  // row blocks start 16-byte aligned
+    c->bytes = 256 + 2 * c->buf_bytes();
+    CUDA_TRY(cudaSetDevice(G.device));
+    CUDA_TRY(cudaMalloc(&c->base, c->bytes));
+    CUDA_TRY(cudaMemset(c->base, 0, 512 < c->bytes ? 512 : c->bytes));
+    c->peer_base.assign(world, nullptr);
+    c->peer_base[rank] = c->base;
+    if (world == 1) c->connected = true;
+    *out = c.release();
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
+}
+
+extern "C" int b2s_comm_handle(b2s_comm_t c, void* handle64) {
+  try {
+    if (!c || !handle64) return fail(B2S_ERR_INVALID, "null communicator");
+    CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), c->base));
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
+}
+
+extern "C" int b2s_comm_connect(b2s_comm_t c, const void* all_handles) {
+  try {
+    if (!c || !all_handles) return fail(B2S_ERR_INVALID, "null communicator");
+    if (c->connected) return B2S_OK;
+    for (int r = 0; r < c->world; ++r) {
+      if (r == c->rank) continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char*)all_handles + (size_t)r * 64, 64);
+      void* ptr = nullptr;
+      CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      c->peer_base[r] = (char*)ptr;
+    }
+    c->connected = true;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
+}
+
+extern "C" int b2s_plan_attach_comm(b2s_plan_t p, b2s_comm_t c) {
+  try {
+    if (!p || !p->finalized) return fail(B2S_ERR_STATE, "plan not finalized");
+    if (c) {
+      if (!c->connected) return fail(B2S_ERR_STATE, "communicator is not connected");
+      if (c->out_cols != p->out_cols) return fail(B2S_ERR_INVALID, "communicator rows have %d words, the plan writes %d", c->out_cols, p->out_cols);
+      if (p->mode == MODE_STORE) return fail(B2S_ERR_UNSUPPORTED, "transform-only plans have no vote to merge");
+    }
+    p->comm = c;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
+}
+
+extern "C" int b2s_comm_wait(b2s_comm_t c, void* stream, const void** d_merged, uint32_t* epoch_out) {
+  try {
+    if (!c || !c->connected) return fail(B2S_ERR_STATE, "communicator is not connected");
+    cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
+    const uint32_t e = c->epoch;
+    if (e == 0) return fail(B2S_ERR_STATE, "no step has been launched on this communicator");
+    uint32_t* timeout_flag = reinterpret_cast<uint32_t*>(c->base) + 65;
+    merge_wait_kernel<<<1, 32, 0, st>>>(c->flags(c->rank), c->world, e, timeout_flag, 2000000000ll);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(B2S_ERR_CUDA, "merge wait launch failed: %s", cudaGetErrorString(err));
+    G.launches.fetch_add(1, std::memory_order_relaxed);
+    if (d_merged) *d_merged = c->buf(c->rank, e);
+    if (epoch_out) *epoch_out = e;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
+}
+
+extern "C" int b2s_comm_check(b2s_comm_t c) {
+  try {  // after a stream synchronisation: did a wait give up on a peer?
+    if (!c) return fail(B2S_ERR_INVALID, "null communicator");
+    uint32_t v = 0;
+    CUDA_TRY(cudaMemcpy(&v, reinterpret_cast<uint32_t*>(c->base) + 65, 4, cudaMemcpyDeviceToHost));
+    if (v) return fail(B2S_ERR_TIMEOUT, "ensemble-merge: rank %u did not signal its shard within 2 s", v - 1);
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
+}
+
+extern "C" int b2s_comm_destroy(b2s_comm_t c) {
+  try {
+    if (!c) return B2S_OK;
+    for (int r = 0; r < c->world; ++r)
+      if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+    if (c->base) cudaFree(c->base);
+    delete c;
     return B2S_OK;
   } catch (const std::exception& e) {
     return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());

@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(256) vote_kernel(KParams kp, const double* __r
     for (int m = 0; m < kp.n_models; ++m) pred[m] = pred_buf[row * kp.n_models + m];
     vote_and_store(kp, pred, row, row_bad[row] ? 1u : 0u);
   }
+  merge_signal(kp.sig);
 }
 
 }  // namespace b2s

@@ -32,3 +32,125 @@ def gather_votes(dist, local, n_rows, world):
         lo, hi = shard_bounds(n_rows, r, world)
         parts.append(full[r * max_rows: r * max_rows + (hi - lo)])
     return torch.cat(parts, dim=0)
+
+
+class MergeComm:
+    """The ensemble-merge communicator of the C-ABI (include/b200serve.h, b2s_comm_*): one device allocation per rank --
+    completion flags + the merged response rows, double buffered -- mapped by every peer over CUDA IPC.
+
+    `exchange(blob) -> [blob of rank 0, ..., blob of rank world-1]` is the only thing the bootstrap needs from the outside
+    (64 bytes per rank): `torch.distributed.all_gather_object`, MPI, a shared file ...; `torch_exchange(dist)` wraps the
+    first."""
+
+    def __init__(self, rank, world, max_rows_per_rank, out_cols, exchange):
+        import ctypes as C
+
+        from . import _native as nat
+
+        self._nat, self._lib = nat, nat.init()
+        self.rank, self.world, self.out_cols = int(rank), int(world), int(out_cols)
+        self.max_rows = (int(max_rows_per_rank) + 3) // 4 * 4
+        self._h = C.c_void_p()
+        nat.check(self._lib.b2s_comm_create(self.rank, self.world, int(max_rows_per_rank), self.out_cols, C.byref(self._h)))
+        if self.world > 1:
+            mine = C.create_string_buffer(64)
+            nat.check(self._lib.b2s_comm_handle(self._h, mine))
+            blobs = exchange(bytes(mine.raw))
+            if len(blobs) != self.world or any(len(b) != 64 for b in blobs):
+                raise ValueError("exchange() must return one 64-byte handle per rank, in rank order")
+            nat.check(self._lib.b2s_comm_connect(self._h, C.create_string_buffer(b"".join(blobs), 64 * self.world)))
+
+    def attach(self, plan):
+        self._nat.check(self._lib.b2s_plan_attach_comm(plan._h, self._h))
+        return plan
+
+    def detach(self, plan):
+        self._nat.check(self._lib.b2s_plan_attach_comm(plan._h, None))
+
+    def wait(self, stream=None):
+        """enqueue the completion wait of the step just launched -> (device pointer of the merged rows, epoch)"""
+        import ctypes as C
+
+        ptr, epoch = C.c_void_p(), C.c_uint32()
+        self._nat.check(self._lib.b2s_comm_wait(self._h, stream, C.byref(ptr), C.byref(epoch)))
+        return ptr.value, epoch.value
+
+    def check(self):
+        self._nat.check(self._lib.b2s_comm_check(self._h))
+
+    def close(self):
+        if self._h:
+            self._lib.b2s_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def torch_exchange(dist, group=None):
+    """exchange() over torch.distributed (NCCL on GPUs, gloo in the CPU tests)"""
+
+    def exchange(blob):
+        out = [None] * dist.get_world_size(group)
+        dist.all_gather_object(out, blob, group=group)
+        return out
+
+    return exchange
+
+
+class ShardedGraphServer:
+    """A GraphServer whose batches are event-sharded over `world` GPUs (one process per GPU): BASELINE configs[3], the
+    8-replica router with the ensemble-merge.  Every rank holds the same graph (same models, replicated tables), scores its
+    own shard with the fused plan, and the plan's kernels store the shard's votes into EVERY rank's response buffer over
+    NVLink peer mappings; `run_batch` returns the merged response of all shards once the completion flags of all ranks
+    have been observed on the device (no host barrier, no collective).  Replaces the per-event fan-out / reduce of
+    ParallelRun._parallel_run and VotingEnsemble._apply_logic (mlrun/serving/routers.py:414-455, 789-810) across replicas.
+
+        server = fn.to_mock_server(...)
+        sharded = ShardedGraphServer(server, rank, world, max_rows_per_rank, torch_exchange(dist), names=feature_names)
+        merged = sharded.run_batch(X[lo:hi])        # (world * max_rows_per_rank, out_cols); rank r's rows at r * max_rows
+
+    Every rank must call run_batch the same number of times (a step is collective in the sense that its flags are awaited)."""
+
+    def __init__(self, server, rank, world, max_rows_per_rank, exchange, names=None):
+        from . import _native as nat
+
+        self.server, self.rank, self.world = server, int(rank), int(world)
+        self.plan = server.compile(names).plan
+        self.comm = MergeComm(rank, world, max_rows_per_rank, self.plan.out_cols, exchange)
+        self.max_rows = self.comm.max_rows
+        self.comm.attach(self.plan)
+        self._nat = nat
+        self._d_in = nat.DeviceBuffer(self.max_rows * self.plan.n_in * 4)
+
+    def rows_of(self, merged, rank, n_rows):
+        """rank's shard inside a merged response"""
+        return merged[rank * self.max_rows: rank * self.max_rows + n_rows]
+
+    def run_device(self, d_rows, n_rows, row_stride=None, stream=None):
+        """device-resident shard -> (device pointer of the merged rows of this step, epoch); asynchronous on `stream`"""
+        self.plan.run_device(d_rows, n_rows, row_stride or self.plan.n_in * 4, None, None, stream)
+        return self.comm.wait(stream)
+
+    def run_batch(self, X):
+        """this rank's shard (B_r, F) float32 -> the merged (world * max_rows, out_cols) response of all ranks' shards"""
+        import numpy as np
+
+        nat = self._nat
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        if X.ndim != 2 or X.shape[1] != self.plan.n_in or len(X) > self.max_rows:
+            raise ValueError(f"a shard is a float32 (<= {self.max_rows}, {self.plan.n_in}) array")
+        self._d_in.upload(X)
+        ptr, _epoch = self.run_device(self._d_in.ptr, len(X))
+        out = np.empty((self.world * self.max_rows, self.plan.out_cols), dtype=self.plan.out_dtype)
+        nat.check(nat.load().b2s_device_sync())  # the wait kernel has seen every rank's flag
+        self.comm.check()
+        nat.check(nat.load().b2s_memcpy_d2h(out.ctypes.data, ptr, out.nbytes))
+        return out
+
+    def close(self):
+        self.comm.detach(self.plan)
+        self.comm.close()

@@ -1,6 +1,7 @@
 """Fit the tree ensembles of BASELINE configs[2] ONCE and commit them as fixtures.
 
-    python -m tests.golden.gen_trees_cfg3          # ~15 min on 8 cores; writes tests/golden/trees_cfg3_{reg,cls}.pkl.xz
+    python -m tests.golden.gen_trees_cfg3          # ~6 min on 8 cores; writes tests/golden/trees_cfg3_{reg,cls}.pkl.xz
+                                                   # and trees_cfg4_reg.pkl.xz (the 64-feature tree scorers of configs[3])
 
 4 x GradientBoostingRegressor(n_estimators=100, max_depth=6, random_state=30+i) and 4 x GradientBoostingClassifier (3
 classes: terciles of y) fit on 20 000 synthetic rows of 128 float32 features, all features considered at every split,
@@ -18,11 +19,12 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 N_FIT, N_FEAT, N_TREES, DEPTH, N_MODELS = 20000, 128, 100, 6, 4
+N_FEAT_CFG4 = 64  # BASELINE configs[3]: "8 linear+tree models (as cfg 2/3, depth 6, 100 trees, 64 feat)"
 
 
-def fit_data():
-    frng = np.random.default_rng(103)
-    Xf = frng.normal(size=(N_FIT, N_FEAT)).astype(np.float32)
+def fit_data(n_feat=N_FEAT):
+    frng = np.random.default_rng(103 if n_feat == N_FEAT else 104)
+    Xf = frng.normal(size=(N_FIT, n_feat)).astype(np.float32)
     y = 2 * Xf[:, 0] + np.sin(Xf[:, 1]) + Xf[:, 2] * Xf[:, 3] + 0.1 * frng.normal(size=N_FIT)
     return Xf, y
 
@@ -40,8 +42,8 @@ def _slim(tree):
 def fit_one(kind, i):
     from sklearn.ensemble import GradientBoostingClassifier, GradientBoostingRegressor
 
-    Xf, y = fit_data()
-    if kind == "reg":
+    Xf, y = fit_data(N_FEAT_CFG4 if kind == "cfg4" else N_FEAT)
+    if kind in ("reg", "cfg4"):
         m = GradientBoostingRegressor(n_estimators=N_TREES, max_depth=DEPTH, random_state=30 + i, subsample=0.8).fit(Xf, y)
     else:
         labels = np.digitize(y, np.quantile(y, [1 / 3, 2 / 3]))
@@ -60,11 +62,14 @@ def main():
     from joblib import Parallel, delayed
 
     t0 = time.time()
-    jobs = [("reg", i) for i in range(N_MODELS)] + [("cls", i) for i in range(N_MODELS)]
+    only = sys.argv[1:]  # e.g. `python -m tests.golden.gen_trees_cfg3 cfg4` regenerates one set
+    jobs = [(k, i) for k in ("reg", "cls", "cfg4") if not only or k in only for i in range(N_MODELS)]
     models = Parallel(n_jobs=min(8, os.cpu_count() or 1))(delayed(fit_one)(k, i) for k, i in jobs)
-    for kind in ("reg", "cls"):
+    for kind in ("reg", "cls", "cfg4"):
         mine = [m for (k, _i), m in zip(jobs, models) if k == kind]
-        path = os.path.join(HERE, f"trees_cfg3_{kind}.pkl.xz")
+        if not mine:
+            continue
+        path = os.path.join(HERE, f"trees_cfg3_{kind}.pkl.xz" if kind != "cfg4" else "trees_cfg4_reg.pkl.xz")
         with lzma.open(path, "wb", preset=9) as fp:
             cloudpickle.dump(mine, fp)
         print(path, os.path.getsize(path), "bytes")

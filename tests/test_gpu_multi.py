@@ -56,3 +56,71 @@ def test_fused_p2p_merge_two_gpus(tmp_path):
         capture_output=True, text=True, env=dict(os.environ, REPO_ROOT=ROOT), timeout=300)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("merge ok") == 2
+
+
+_SHARDED = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO_ROOT"])
+from mlrun_b200 import _native as nat, api
+from mlrun_b200.sharding import ShardedGraphServer, shard_bounds, torch_exchange
+from mlrun_b200.synthetic import flow3_workload
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+nat.init(rank)
+
+def check(server, names, batches, label):
+    full = [server.run_batch(X, names=names) for X in batches]          # single-GPU answers (same on every rank)
+    max_rows = max(shard_bounds(len(X), 0, world)[1] for X in batches)
+    sharded = ShardedGraphServer(server, rank, world, max_rows, torch_exchange(dist), names=names)
+    for step, X in enumerate(batches * 3):                              # several steps: both buffer parities, reused
+        lo, hi = shard_bounds(len(X), rank, world)
+        merged = sharded.run_batch(X[lo:hi])
+        for r in range(world):
+            rlo, rhi = shard_bounds(len(X), r, world)
+            got = sharded.rows_of(merged, r, rhi - rlo)
+            want = full[step % len(batches)][rlo:rhi]
+            assert np.array_equal(got, want), (label, step, rank, r, np.abs(got.astype(np.float64) - want).max())
+    sharded.close()
+    dist.barrier()
+    print("rank", rank, label, "ok")
+
+# (a) the metric workload: Imputer -> OneHotEncoder -> VotingEnsemble(4 linear) on the row-thread kernel
+wl = flow3_workload(n_rows=10001, n_num=56, n_cat=8, seed=7, n_models=4)
+server = wl.build_server(api, engine="sync")
+rng = np.random.default_rng(5)
+check(server, wl.names, [wl.X, wl.X[rng.permutation(len(wl.X))[:7777]]], "flow3")
+
+# (b) BASELINE configs[3]: a router of 8 mixed linear / tree scorers over 64 raw features (tree parts kernel + vote kernel)
+from sklearn.ensemble import GradientBoostingRegressor
+from sklearn.linear_model import Ridge
+frng = np.random.default_rng(11)
+Xf = frng.normal(size=(3000, 64)).astype(np.float32)
+y = 2 * Xf[:, 0] + np.sin(Xf[:, 1]) + Xf[:, 2] * Xf[:, 3]
+fn = api.new_function("router8", kind="serving")
+graph = fn.set_topology("router", api.VotingEnsemble(vote_type="regression"))
+for i in range(8):
+    m = (GradientBoostingRegressor(n_estimators=25, max_depth=6, random_state=i, subsample=0.5) if i % 2 == 0 else Ridge(alpha=1.0 + i)).fit(Xf, y)
+    graph.add_route(f"m{i}", class_name="SKLearnModelServer", model=m, model_path="")
+server8 = fn.to_mock_server(namespace={"SKLearnModelServer": api.SKLearnModelServer})
+X8 = frng.normal(size=(65536, 64)).astype(np.float32)
+check(server8, [f"f{i}" for i in range(64)], [X8, X8[:30011]], "router8")
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_graph_server_with_completion_flags(tmp_path):
+    """the product API of the sharded router: no barrier, no collective -- readers wait on the per-rank completion flags"""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "sharded.py"
+    script.write_text(_SHARDED)
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+         "--master-port", "29622", str(script)],
+        capture_output=True, text=True, env=dict(os.environ, REPO_ROOT=ROOT), timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("flow3 ok") == 2 and out.stdout.count("router8 ok") == 2
