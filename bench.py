@@ -848,10 +848,45 @@ def main_ingest(args, rank, local_rank, world, emit=True):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         Be = len(wl.df)
-        e2e = {"value": world * Be * n_e2e / dt, "unit": "events/s", "h2d_bytes_per_step": Be * wl.in_bytes_per_row,
-               "d2h_bytes_per_step": Be * wl.out_bytes_per_row, "batch": Be, "steps": n_e2e, "out_columns": int(res.shape[1]),
-               "api": "FeatureSet.ingest(DataFrame) (public API): frame columns -> H2D per column -> columns_kernel -> D2H per "
-                      "column -> DataFrame (pageable host memory; includes the frame (dis)assembly)"}
+        e2e_df = {"value": world * Be * n_e2e / dt, "unit": "events/s", "batch": Be, "steps": n_e2e, "out_columns": int(res.shape[1]),
+                  "api": "FeatureSet.ingest(DataFrame): frame columns -> H2D per column -> columns_kernel -> D2H per column -> "
+                         "DataFrame (pageable host memory; includes the frame (dis)assembly)"}
+        # the columnar boundary: pinned column arrays in, a ColumnBatch over a pinned block out -- no pandas
+        # object on either side, the frame pipelined in row ranges (H2D of range r + 1 under kernel + D2H of range r)
+        from mlrun_b200.feature_store import columnar
+
+        Bc = 1048576
+        reps_c = int(np.ceil(Bc / len(wl.df)))
+        cols_in = []
+        for j in range(2):
+            pc = columnar.pinned_columns({n: wl.df[n].to_numpy() for n in wl.df.columns}, Bc)
+            for n in wl.df.columns:
+                pc[n][:] = np.tile(np.roll(wl.df[n].to_numpy(), j * 977), reps_c)[:Bc]
+            cols_in.append(pc)
+        fset_c = bingest.FeatureSet("ingest6c", timestamp_key="timestamp")
+        cur = fset_c.graph
+        for st_ in wl.build_steps(bsteps):
+            cur = cur.to(st_)
+        for c_, v_ in zip(wl.checked_cols, [bsteps.MinMaxValidator(severity="info", min=-2.5, max=2.5)] * len(wl.checked_cols)):
+            fset_c[c_] = bingest.Feature(validator=v_)
+        with contextlib.redirect_stdout(io.StringIO()):
+            for j in range(2):
+                batch = fset_c.ingest(cols_in[j % 2])
+            n_c = max(3, min(args.steps, 6))
+            t0 = time.perf_counter()
+            for j in range(n_c):
+                batch = fset_c.ingest(cols_in[j % 2])
+            dtc = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dtc], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtc = float(t.item())
+        e2e = {"value": world * Bc * n_c / dtc, "unit": "events/s", "h2d_bytes_per_step": Bc * wl.in_bytes_per_row,
+               "d2h_bytes_per_step": Bc * wl.out_bytes_per_row, "batch": Bc, "steps": n_c, "out_columns": len(batch.names),
+               "api": "FeatureSet.ingest(pinned column arrays) (public API, columnar boundary): H2D per column and row range -> "
+                      "columns_kernel -> D2H per column into a pinned ColumnBatch; pipelined in 64 Ki-row ranges",
+               "dataframe_boundary": e2e_df}
+        del cols_in, batch
     if rank == 0:
         peak, peak_src = measured_peak()
         bpe = wl.in_bytes_per_row + wl.out_bytes_per_row

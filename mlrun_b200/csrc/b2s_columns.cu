@@ -41,6 +41,7 @@ struct b2s_cols_s {
   unsigned long long* d_cnt = nullptr;
   int64_t cap_rows = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> chunk_ev;  // one per row range of a pipelined host run
 };
 
 static int check_src(b2s_cols_t c, int32_t src, int32_t kind) {
@@ -242,8 +243,9 @@ extern "C" int b2s_cols_info(b2s_cols_t c, int32_t* n_out_slots, int32_t* n_coun
 }
 
 static int launch_cols(b2s_cols_t c, const void* d_in, int64_t in_stride, int64_t n_rows, void* d_out, int64_t out_stride,
-                       unsigned long long* d_counters, cudaStream_t st) {
+                       unsigned long long* d_counters, cudaStream_t st, int64_t row_begin = 0) {
   ColParams p{};
+  p.row_begin = row_begin;
   p.in = (const char*)d_in;
   p.in_stride = in_stride;
   p.out = (char*)d_out;
@@ -322,6 +324,61 @@ extern "C" int b2s_cols_run_host(b2s_cols_t c, const void* const* h_in_slots, in
       c->cap_rows = n_rows;
     }
     cudaStream_t st = b2s_int_stream();
+    // Large frames run as a pipeline of row ranges: the columns of range r + 1 cross PCIe on the copy stream while range r
+    // is transformed and its result columns travel back (the two PCIe directions overlap), so a frame costs about
+    // max(H2D, D2H) instead of their sum.  Needs pinned column buffers on both sides to overlap at all (pageable copies
+    // are staged synchronously by the driver) -- see mlrun_b200.feature_store.columnar.
+    static const int64_t pipe_rows = getenv("B2S_COLS_CHUNK") ? atoll(getenv("B2S_COLS_CHUNK")) : 65536;
+    if (pipe_rows > 0 && n_rows >= 2 * pipe_rows) {
+      const int64_t chunk = (pipe_rows + kColChunk - 1) / kColChunk * kColChunk;
+      const int n_chunks = (int)((n_rows + chunk - 1) / chunk);
+      cudaStream_t cs = b2s_int_copy_stream();
+      while ((int)c->chunk_ev.size() < n_chunks) {
+        cudaEvent_t e;
+        COL_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->chunk_ev.push_back(e);
+      }
+      for (int s = 0; s < c->n_in; ++s)
+        if (c->in_used[s] && !h_in_slots[s]) return b2s_int_fail(B2S_ERR_INVALID, "input slot %d is read by the plan but its pointer is NULL", s);
+      for (size_t s = 0; s < n_out; ++s)
+        if (c->out_words[s] && !h_out_slots[s]) return b2s_int_fail(B2S_ERR_INVALID, "output slot %zu has no destination", s);
+      if (c->n_counters) COL_TRY(cudaMemsetAsync(c->d_cnt, 0, c->n_counters * sizeof(unsigned long long), st));
+      COL_TRY(cudaEventRecord(c->ev[0], st));
+      COL_TRY(cudaStreamWaitEvent(cs, c->ev[0], 0));  // whatever ran on the library stream before is done with d_in
+      for (int k = 0; k < n_chunks; ++k) {
+        const int64_t r0 = (int64_t)k * chunk, nr = std::min<int64_t>(chunk, n_rows - r0);
+        for (int s = 0; s < c->n_in; ++s) {
+          if (!c->in_used[s]) continue;
+          const size_t w = 4u * c->in_used[s];
+          COL_TRY(cudaMemcpyAsync(c->d_in + (size_t)s * stride + (size_t)r0 * w, (const char*)h_in_slots[s] + (size_t)r0 * w, (size_t)nr * w,
+                                  cudaMemcpyHostToDevice, cs));
+        }
+        COL_TRY(cudaEventRecord(c->chunk_ev[k], cs));
+        COL_TRY(cudaStreamWaitEvent(st, c->chunk_ev[k], 0));
+        if (int rc = launch_cols(c, c->d_in, stride, nr, c->d_out, stride, c->d_cnt, st, r0)) {
+          cudaStreamSynchronize(cs);
+          cudaStreamSynchronize(st);
+          return rc;
+        }
+        for (size_t s = 0; s < n_out; ++s) {
+          if (!c->out_words[s]) continue;  // second half of an 8-byte column
+          const size_t w = 4u * c->out_words[s];
+          COL_TRY(cudaMemcpyAsync((char*)h_out_slots[s] + (size_t)r0 * w, c->d_out + s * (size_t)stride + (size_t)r0 * w, (size_t)nr * w,
+                                  cudaMemcpyDeviceToHost, st));
+        }
+      }
+      if (c->n_counters) COL_TRY(cudaMemcpyAsync(counters, c->d_cnt, c->n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      COL_TRY(cudaEventRecord(c->ev[3], st));
+      COL_TRY(cudaStreamSynchronize(st));
+      COL_TRY(cudaStreamSynchronize(cs));
+      if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->rows = n_rows;
+        cudaEventElapsedTime(&stats->kernel_ms, c->ev[0], c->ev[3]);  // the whole pipelined span
+        stats->kernels = n_chunks;
+      }
+      return B2S_OK;
+    }
     COL_TRY(cudaEventRecord(c->ev[0], st));
     for (int s = 0; s < c->n_in; ++s) {
       if (!c->in_used[s]) continue;
@@ -364,6 +421,7 @@ extern "C" int b2s_cols_destroy(b2s_cols_t c) {
     if (c->d_out) cudaFree(c->d_out);
     for (auto& e : c->ev)
       if (e) cudaEventDestroy(e);
+    for (auto& e : c->chunk_ev) cudaEventDestroy(e);
     delete c;
     return B2S_OK;
   } catch (const std::exception& e) {

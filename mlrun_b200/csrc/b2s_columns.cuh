@@ -57,11 +57,12 @@ struct ColParams {
   int64_t in_stride;
   char* out;
   int64_t out_stride;
-  int64_t n_rows;
+  int64_t n_rows;     // rows of this launch: [row_begin, row_begin + n_rows) of the slots
   const ColOp* ops;
   int32_t n_ops;
   const double* tab;
   unsigned long long* counters;
+  int64_t row_begin;  // a multiple of kColChunk (the host path pipelines a frame in row ranges)
 };
 
 #ifndef B2S_COL_THREADS
@@ -361,8 +362,9 @@ __global__ void __launch_bounds__(kColThreads) columns_kernel(const __grid_const
     const int64_t chunk = item - opi * n_chunks;
     const ColOp op = p.ops[opi];
 #endif
-    const int64_t row0 = chunk * kColChunk;
-    const int rows = (int)((p.n_rows - row0 < kColChunk) ? (p.n_rows - row0) : kColChunk);
+    const int64_t row0 = p.row_begin + chunk * kColChunk;
+    const int64_t row_end = p.row_begin + p.n_rows;
+    const int rows = (int)((row_end - row0 < kColChunk) ? (row_end - row0) : kColChunk);
     const char* src = p.in + (int64_t)op.src * p.in_stride;
     char* dst = op.dst >= 0 ? p.out + (int64_t)op.dst * p.out_stride : nullptr;
     unsigned int bad = 0, miss = 0;

@@ -9,6 +9,7 @@ B2S_HIDDEN bool b2s_int_inited();
 B2S_HIDDEN int b2s_int_device();
 B2S_HIDDEN int b2s_int_sm_count();
 B2S_HIDDEN cudaStream_t b2s_int_stream();                      // the library stream
+B2S_HIDDEN cudaStream_t b2s_int_copy_stream();                 // the library's copy stream (pipelined host runs)
 B2S_HIDDEN void b2s_int_count_launches(int n);
 struct b2s_plan_s;
 B2S_HIDDEN int b2s_int_plan_shape(b2s_plan_s* plan, int* n_in, int* out_cols);  // B2S_ERR_STATE unless finalized

@@ -28,6 +28,8 @@
 #include "b2s_rowthread.cuh"
 #include "b2s_trees2.cuh"
 #include "b2s_trees3.cuh"
+#include "b2s_dense.cuh"
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost nothing unless a profiler is attached
 
 using namespace b2s;
 
@@ -77,6 +79,7 @@ bool b2s_int_inited() { return G.inited; }
 int b2s_int_device() { return G.device; }
 int b2s_int_sm_count() { return G.prop.multiProcessorCount; }
 cudaStream_t b2s_int_stream() { return G.stream; }
+cudaStream_t b2s_int_copy_stream() { return G.copy_stream; }
 void b2s_int_count_launches(int n) { G.launches.fetch_add(n, std::memory_order_relaxed); }
 
 static int64_t cfg_get(const std::string& cfg, const char* key, int64_t dflt) {
@@ -183,6 +186,10 @@ struct b2s_plan_s {
   };
   std::map<cudaStream_t, TreeScratch> t2_scratch;
   std::mutex scratch_mu;
+  // dense linear head on the tensor cores (b2s_dense.cu): > 8 scores over <= 128 plain numeric columns
+  bool dense_ok = false;
+  DenseParams dense{};
+  int dense_smem = 0, dense_grid = 0;
   // round-2 tree kernel: parts resident in shared memory (b2s_trees3.cuh); scratch = partial sums, column-major
   bool t3_ok = false, t3_miss = false;
   int t3_D = 0, t3_grid = 0, t3_block = 0, t3_smem = 0, t3_cols = 0, t3_parts = 0;
@@ -214,6 +221,7 @@ struct b2s_plan_s {
   cudaStream_t ring_stream = nullptr;
   int64_t ring_cap = 0;
   // per-plan ring configuration (b2s_plan_set_ring; 0 / negative: the library defaults of b2s_init)
+  std::atomic<int> spinners{0};  // waiters currently polling instead of sleeping (b2s_wait)
   int ring_cfg_slots = 0;
   int64_t ring_cfg_max_batch = 0;
   int ring_cfg_wait_us = -1;
@@ -1347,8 +1355,41 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
         }
       }
     }
+    // ---- dense head (tcgen05): linear scorers with more than 8 scores in total over plain numeric columns.  Weights are
+    // split like the inputs will be: w (float32) = wh + wl with wh = tf32(w), wl = tf32(w - wh); W^T rows padded to 16 / 32
+    std::vector<float> dense_wh, dense_wl;
+    int dense_pad = 0;
+    {
+      const char* denv = getenv("B2S_DENSE");  // 1 (default) | 0: stay on the fp64 row kernels (A/B runs)
+      int n_cat_cols = 0;
+      for (int c = 0; c < n_in; ++c) n_cat_cols += (cat_off[c + 1] > cat_off[c]) ? 1 : 0;
+      bool all_copied = true;
+      for (int c = 0; c < n_in; ++c) all_copied = all_copied && (flags[c] & COL_COPIED);
+      if ((!denv || atoi(denv) != 0) && p->mode == MODE_LINEAR && total_scores > 8 && total_scores <= 32 && identity_schema &&
+          !any_map && n_cat_cols == 0 && all_copied && (n_in % 32) == 0 && n_in <= kDenseMaxIn) {
+        dense_pad = total_scores <= 16 ? 16 : 32;
+        dense_wh.assign((size_t)dense_pad * n_in, 0.0f);
+        dense_wl.assign((size_t)dense_pad * n_in, 0.0f);
+        auto tf32 = [](float x) {
+          uint32_t b;
+          memcpy(&b, &x, 4);
+          b &= 0xffffe000u;
+          float y;
+          memcpy(&y, &b, 4);
+          return y;
+        };
+        for (int kk = 0; kk < total_scores; ++kk)
+          for (int c = 0; c < n_in; ++c) {
+            const float w = (float)wnum[(size_t)c * NS + kk];
+            const float hi = tf32(w);
+            dense_wh[(size_t)kk * n_in + c] = hi;
+            dense_wl[(size_t)kk * n_in + c] = tf32(w - hi);
+          }
+      }
+    }
     // ---- upload one blob
     BlobBuilder bb;
+    const size_t o_dwh = bb.add(dense_wh), o_dwl = bb.add(dense_wl);
     const size_t o_fill = bb.add(p->fill), o_flags = bb.add(flags), o_mapoff = bb.add(map_off), o_maps = bb.add(maps),
                  o_osrc = bb.add(p->out_src), o_okind = bb.add(p->out_kind), o_oarg = bb.add(p->out_arg),
                  o_catoff = bb.add(cat_off), o_catval = bb.add(cat_val), o_wnum = bb.add(wnum), o_wcat = bb.add(wcat),
@@ -1399,6 +1440,44 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
     k.tree_slot = (const int32_t*)(B + o_tslot);
     k.tree_scale = (const double*)(B + o_tscale);
     k.chunk_kind = (const uint8_t*)(B + o_chunk);
+    if (dense_pad > 0 && tensor_map_encoder() != nullptr) {
+      DenseParams& d = p->dense;
+      memset(&d, 0, sizeof(d));
+      d.wh = (const float*)(B + o_dwh);
+      d.wl = (const float*)(B + o_dwl);
+      d.fill = k.fill;
+      d.bias = k.bias;
+      d.n_in = n_in;
+      d.n_scores = total_scores;
+      d.n_pad = dense_pad;
+      d.any_fill = any_fill ? 1 : 0;
+      for (int kk = 0; kk < 32; ++kk) {
+        d.biasf[kk] = kk < total_scores ? (float)bias[kk] : 0.0f;
+        d.votewf[kk] = 0.0f;
+        d.labels[kk] = kk;
+      }
+      {
+        bool simple = true;  // every model: one identity score
+        for (auto& m : p->models) simple = simple && m.link == B2S_LINK_IDENTITY && m.n_scores == 1;
+        d.epi = DENSE_EPI_GENERIC;
+        if (simple && p->vote_kind == B2S_VOTE_NONE) d.epi = DENSE_EPI_SCORES;
+        if (simple && p->vote_kind == B2S_VOTE_MEAN) {
+          d.epi = DENSE_EPI_MEAN;
+          for (int mi = 0; mi < M; ++mi) d.votewf[mi] = (float)p->vote_w[mi];
+        }
+        if (M == 1 && p->models[0].link == B2S_LINK_ARGMAX && p->vote_kind == B2S_VOTE_NONE) {
+          d.epi = DENSE_EPI_ARGMAX;
+          const auto& cls = p->models[0].classes;
+          for (int kk = 0; kk < total_scores && kk < 32; ++kk) d.labels[kk] = cls.empty() ? kk : cls[kk];
+        }
+      }
+      p->dense_smem = dense_smem_bytes(n_in, dense_pad);
+      if (p->dense_smem <= (int)G.prop.sharedMemPerBlockOptin) {
+        const int resident = std::max(1, std::min(4, (int)G.prop.sharedMemPerMultiprocessor / (p->dense_smem + 1024)));
+        p->dense_grid = G.prop.multiProcessorCount * resident;
+        p->dense_ok = true;
+      }
+    }
 
     // ---- launch geometry + shared-memory carve-up
     // pitch (words): rows 16B aligned and (pitch/4) odd -> conflict-free LDS.128 for one-thread-per-row
@@ -1703,7 +1782,8 @@ extern "C" const char* b2s_plan_kernel(b2s_plan_t p) {
   static thread_local char buf[200];
   int lm = rt_load_mode();
   if (lm == 2 && !(p->rt_NCH >= 8 && p->n_in == p->rt_NCH * 4 && tensor_map_encoder())) lm = 1;
-  if (p->t3_ok) snprintf(buf, sizeof(buf), "t3_prep_kernel + trees3_kernel<D=%d,%s> + t3_vote_kernel (%d parts resident in shared memory, %d walking warps)", p->t3_D, p->t3_miss ? "NaN routing" : "floats", p->t3_parts, p->t3.warps);
+  if (p->dense_ok) snprintf(buf, sizeof(buf), "dense_head_kernel<N=%d> (tcgen05.mma kind::tf32 x3, TMEM accumulator; %d scores over %d columns)", p->dense.n_pad, p->dense.n_scores, p->dense.n_in);
+  else if (p->t3_ok) snprintf(buf, sizeof(buf), "t3_prep_kernel + trees3_kernel<D=%d,%s> + t3_vote_kernel (%d parts resident in shared memory, %d walking warps)", p->t3_D, p->t3_miss ? "NaN routing" : "floats", p->t3_parts, p->t3.warps);
   else if (p->t2_ok) snprintf(buf, sizeof(buf), "trees_model_kernel<%d> + vote_kernel (models resident in shared memory)", p->t2_NS);
   else if (p->rt_ok) snprintf(buf, sizeof(buf), "rowthread_kernel<NCH=%d,NS=%d,TPR=%d,RPT=%d,%s>", p->rt_NCH, p->rt_NS, p->rt_TPR, lm == 2 ? p->rt_RPT : 1, lm == 2 ? "TMA tensor-map loads" : (lm == 1 ? "TMA bulk loads" : "cp.async loads"));
   else if (p->rw_ok) snprintf(buf, sizeof(buf), "rowwarp_kernel<L=%d,CPL=%d,NS=%d,U=%d,CS=%d>", p->rw_L, p->rw_CPL, p->rw_NS, p->rw_U, p->rw_CS);
@@ -1723,9 +1803,16 @@ extern "C" int b2s_plan_out_info(b2s_plan_t p, int32_t* out_cols, int32_t* out_i
 }
 
 // ------------------------------------------------------------------------------------------ execution
+struct NvtxRange {  // one range per plan launch, named after the kernel family (nsys / ncu --nvtx timelines)
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t stride, void* d_out, int32_t* d_status,
                      cudaStream_t st, bool host_rows = false) {
   if (n_rows == 0) return B2S_OK;
+  NvtxRange nvtx(p->dense_ok ? "b2s:dense_head" : p->t3_ok ? "b2s:trees3 (prep+walk+vote)" : p->t2_ok ? "b2s:trees2"
+                 : p->rt_ok ? "b2s:rowthread" : p->mode == MODE_STORE ? "b2s:rows_store" : "b2s:rows_kernel");
   KParams k = p->kp;
   k.rows = (const char*)d_rows;
   k.row_stride = stride;
@@ -1849,6 +1936,20 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
     e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return fail(B2S_ERR_CUDA, "vote kernel launch failed: %s", cudaGetErrorString(e2));
     return B2S_OK;
+  }
+  if (p->dense_ok && !host_rows && k.vec_ok) {
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (encode_rows_map(&tmap, d_rows, n_rows, stride, p->n_in, kDenseTileRows)) {
+      DenseParams d = p->dense;
+      d.n_rows = n_rows;
+      const int64_t tiles = (n_rows + kDenseTileRows - 1) / kDenseTileRows;
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->dense_grid, tiles));
+      G.launches.fetch_add(1, std::memory_order_relaxed);
+      cudaError_t e = dense_launch(d, k, tmap, grid, p->dense_smem, (int)G.prop.sharedMemPerBlockOptin, st);
+      if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "dense head kernel launch failed: %s", cudaGetErrorString(e));
+      return B2S_OK;
+    }
   }
   if (p->rt_ok) {
     G.launches.fetch_add(1, std::memory_order_relaxed);
@@ -2034,14 +2135,21 @@ extern "C" int b2s_run_host(b2s_plan_t p, const void* rows, int64_t n_rows, int6
       }
       return B2S_OK;
     }
-    // Small batches skip both copies: the kernels read the rows from pinned host memory and write votes and status words
-    // back into pinned host memory over PCIe themselves (one launch, one synchronisation: the latency path of a serving
-    // batch).  Larger ones take the copy engines, which is where the bandwidth is.
-    static const int64_t zc_rows = getenv("B2S_ZEROCOPY_ROWS") ? atoll(getenv("B2S_ZEROCOPY_ROWS")) : 8192;
-    if (n_rows <= zc_rows && p->peers.empty() && !p->comm) {
-      const void* d_src = pinned ? attr.devicePointer : (const void*)p->h_stage_in;
+    // Not pipelined: the kernels write votes and status words straight into pinned host memory (posted PCIe writes of a few
+    // bytes per row: no D2H copy, one synchronisation).  A tiny batch is also READ from pinned host memory by the kernels
+    // (no H2D copy: the latency path of a small serving batch); larger ones cross PCIe on the copy engine first, which is
+    // where the bandwidth is.  Not with merge targets: those kernels write to the targets.
+    static const int64_t zc_in_bytes = getenv("B2S_ZEROCOPY_IN_BYTES") ? atoll(getenv("B2S_ZEROCOPY_IN_BYTES")) : 65536;
+    static const int zc_out = getenv("B2S_ZEROCOPY_OUT") ? atoi(getenv("B2S_ZEROCOPY_OUT")) : 1;
+    const bool merging = !p->peers.empty() || p->comm;
+    if (zc_out && !merging) {
+      const bool zc_in = n_rows * row_bytes <= zc_in_bytes;
+      const void* d_src = p->d_stage_in;
+      if (stats) CUDA_TRY(cudaEventRecord(p->ev[0], st));
+      if (zc_in) d_src = pinned ? attr.devicePointer : (const void*)p->h_stage_in;
+      else CUDA_TRY(cudaMemcpyAsync(p->d_stage_in, src, (size_t)n_rows * row_bytes, cudaMemcpyHostToDevice, st));
       if (stats) CUDA_TRY(cudaEventRecord(p->ev[1], st));
-      if (int rc = launch_on(p, d_src, n_rows, row_bytes, p->h_stage_out, (int32_t*)(p->h_stage_out + out_sz), st, true)) return rc;
+      if (int rc = launch_on(p, d_src, n_rows, row_bytes, p->h_stage_out, (int32_t*)(p->h_stage_out + out_sz), st, zc_in)) return rc;
       if (stats) CUDA_TRY(cudaEventRecord(p->ev[2], st));
       CUDA_TRY(cudaStreamSynchronize(st));
       memcpy(out, p->h_stage_out, out_sz);
@@ -2052,7 +2160,8 @@ extern "C" int b2s_run_host(b2s_plan_t p, const void* rows, int64_t n_rows, int6
       if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->rows = n_rows;
-        cudaEventElapsedTime(&stats->kernel_ms, p->ev[1], p->ev[2]);  // includes the PCIe traffic of the rows
+        cudaEventElapsedTime(&stats->h2d_ms, p->ev[0], p->ev[1]);
+        cudaEventElapsedTime(&stats->kernel_ms, p->ev[1], p->ev[2]);  // includes the PCIe writes of the results
         stats->kernels = p->kernels_per_batch;
         stats->nonfinite_rows = bad;
       }
@@ -2111,13 +2220,24 @@ static void dispatcher_main(b2s_plan_s* p) {
   cudaSetDevice(G.device);
   std::unique_lock<std::mutex> lk(p->mu);
   for (;;) {
-    // wake up when a batch is sealed, when the open batch times out, or on stop
+    // wake up when a batch is sealed, when the open batch is due, or on stop
     if (p->sealed.empty()) {
       if (p->stop) return;
       if (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0) {
+        // The open batch leaves when its oldest row has waited max_wait_us (0: at once -- this thread is free, so batches
+        // form while the previous one runs) -- but only while another slot is free to take the submits that follow: the
+        // last free slot keeps collecting rows (until it is full, a waiter asks for it, or b2s_flush), so that a caller
+        // that submits many tickets before it collects any fills a batch instead of exhausting the ring.
+        int spare = 0;
+        for (int i = 0; i < (int)p->slots.size(); ++i)
+          spare += (i != p->open_slot && p->slots[i].state == 0 && p->slots[i].rows == 0 && p->slots[i].waiters == 0) ? 1 : 0;
+        if (spare == 0) {
+          p->cv_work.wait(lk);  // a slot is collected, the batch fills up, a waiter or a flush seals it
+          continue;
+        }
         auto deadline = p->slots[p->open_slot].first_submit + std::chrono::microseconds(p->wait_us());
-        if (p->cv_work.wait_until(lk, deadline) == std::cv_status::timeout) {
-          if (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0 &&
+        if (std::chrono::steady_clock::now() >= deadline || p->cv_work.wait_until(lk, deadline) == std::cv_status::timeout) {
+          if (p->sealed.empty() && p->open_slot >= 0 && p->slots[p->open_slot].rows > 0 &&
               std::chrono::steady_clock::now() >= p->slots[p->open_slot].first_submit + std::chrono::microseconds(p->wait_us())) {
             p->slots[p->open_slot].state = 1;
             p->sealed.push_back(p->open_slot);
@@ -2125,7 +2245,15 @@ static void dispatcher_main(b2s_plan_s* p) {
           }
         }
       } else {
-        p->cv_work.wait(lk);
+        // nothing to run: look again for a little while before sleeping (the next request is usually close behind)
+        bool work = false;
+        for (int spin = 0; spin < 300 && !work; ++spin) {
+          lk.unlock();
+          for (int i = 0; i < 40; ++i) __builtin_ia32_pause();
+          lk.lock();
+          work = p->stop || !p->sealed.empty() || (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0);
+        }
+        if (!work) p->cv_work.wait(lk);
       }
       continue;
     }
@@ -2150,35 +2278,26 @@ static void dispatcher_main(b2s_plan_s* p) {
         err_msg = std::string("coalesced batch: ") + what + ": " + cudaGetErrorString(e);
       }
     };
-    static const int64_t zc_rows = getenv("B2S_ZEROCOPY_ROWS") ? atoll(getenv("B2S_ZEROCOPY_ROWS")) : 8192;
-    const bool zero_copy = rows <= zc_rows && p->peers.empty() && !p->comm;
+    static const int64_t zc_in_bytes = getenv("B2S_ZEROCOPY_IN_BYTES") ? atoll(getenv("B2S_ZEROCOPY_IN_BYTES")) : 65536;
+    static const int zc_out = getenv("B2S_ZEROCOPY_OUT") ? atoi(getenv("B2S_ZEROCOPY_OUT")) : 1;
+    const bool zero_out = zc_out && p->peers.empty() && !p->comm;  // results go straight into the slot's pinned result area
+    const bool zero_in = zero_out && rows * row_bytes <= zc_in_bytes;  // a tiny batch is read from the pinned slot as well
     step(cudaEventRecord(s.e0, st), "event record");
-    if (zero_copy) {
-      // a small batch: the kernels read the slot's pinned rows and write its pinned result area over PCIe themselves
-      step(cudaEventRecord(s.e1, st), "event record");
-      if (!err) {
-        const int rc = launch_on(p, s.h_in, rows, row_bytes, s.h_out, (int32_t*)(s.h_out + (size_t)p->ring_cap * p->out_cols * 4), st, true);
-        if (rc) {
-          err = rc;
-          err_msg = std::string("coalesced batch: ") + g_err;
-        }
+    if (!zero_in) step(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st), "H2D copy");
+    step(cudaEventRecord(s.e1, st), "event record");
+    if (!err) {
+      int32_t* h_status = (int32_t*)(s.h_out + (size_t)p->ring_cap * p->out_cols * 4);
+      const int rc = zero_out ? launch_on(p, zero_in ? s.h_in : s.d_in, rows, row_bytes, s.h_out, h_status, st, zero_in)
+                              : launch_on(p, s.d_in, rows, row_bytes, s.d_out, s.d_status, st);
+      if (rc) {
+        err = rc;
+        err_msg = std::string("coalesced batch: ") + g_err;
       }
-      step(cudaEventRecord(s.e2, st), "event record");
-    } else {
-      step(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st), "H2D copy");
-      step(cudaEventRecord(s.e1, st), "event record");
-      if (!err) {
-        const int rc = launch_on(p, s.d_in, rows, row_bytes, s.d_out, s.d_status, st);
-        if (rc) {
-          err = rc;
-          err_msg = std::string("coalesced batch: ") + g_err;
-        }
-      }
-      step(cudaEventRecord(s.e2, st), "event record");
-      if (!err) {
-        step(cudaMemcpyAsync(s.h_out, s.d_out, out_sz, cudaMemcpyDeviceToHost, st), "D2H copy");
-        step(cudaMemcpyAsync(s.h_out + (size_t)p->ring_cap * p->out_cols * 4, s.d_status, (size_t)rows * 4, cudaMemcpyDeviceToHost, st), "D2H copy");
-      }
+    }
+    step(cudaEventRecord(s.e2, st), "event record");
+    if (!err && !zero_out) {
+      step(cudaMemcpyAsync(s.h_out, s.d_out, out_sz, cudaMemcpyDeviceToHost, st), "D2H copy");
+      step(cudaMemcpyAsync(s.h_out + (size_t)p->ring_cap * p->out_cols * 4, s.d_status, (size_t)rows * 4, cudaMemcpyDeviceToHost, st), "D2H copy");
     }
     step(cudaEventRecord(s.e3, st), "event record");
     step(cudaEventSynchronize(s.e3), "execution");
@@ -2347,6 +2466,23 @@ extern "C" int b2s_wait(b2s_plan_t p, uint64_t ticket, void* out, int64_t out_by
     auto it = p->batch_slot.find(batch);
     if (it == p->batch_slot.end()) return fail(B2S_ERR_INVALID, "unknown ticket");
     Slot& s = p->slots[it->second];
+    if (s.state == 0 && p->open_slot == it->second && s.rows > 0) {  // the ticket's batch is still collecting rows: send it
+      s.state = 1;
+      p->sealed.push_back(p->open_slot);
+      p->open_slot = -1;
+      p->cv_work.notify_one();
+    }
+    // a short spin before sleeping: two condition-variable hand-offs (producer -> dispatcher -> waiter) cost more than a
+    // small batch takes on the device
+    // (only a couple of waiters at a time: a crowd of spinners would fight the dispatcher for the lock and the cores)
+    if (p->spinners.fetch_add(1, std::memory_order_relaxed) < 2) {
+      for (int spin = 0; spin < 400 && !(s.state == 3 && s.batch_id == batch); ++spin) {
+        lk.unlock();
+        for (int i = 0; i < 40; ++i) __builtin_ia32_pause();
+        lk.lock();
+      }
+    }
+    p->spinners.fetch_sub(1, std::memory_order_relaxed);
     p->cv_done.wait(lk, [&] { return s.state == 3 && s.batch_id == batch; });
     // the batch is done: whatever this call returns, the ticket is spent and the last one recycles the slot
     int rc = B2S_OK;
@@ -2372,6 +2508,7 @@ extern "C" int b2s_wait(b2s_plan_t p, uint64_t ticket, void* out, int64_t out_by
       s.err = 0;
       s.err_msg.clear();
       p->cv_free.notify_all();
+      p->cv_work.notify_one();  // the dispatcher may have been holding the open batch for want of a spare slot
     }
     return rc;
   } catch (const std::exception& e) {

@@ -73,3 +73,34 @@ def dumps_with_outputs(response, outputs_text):
     body["outputs"] = _MARK
     text = json.dumps(body).encode()
     return text.replace(json.dumps(_MARK).encode(), outputs_text, 1)
+
+
+# ------------------------------------------------------------------------------------------ binary bodies
+# Content type "application/x-b2s-f32": the rows themselves instead of their decimal text.  A V2 JSON body of 4096 x 128
+# values is 10.8 MB of text for 2 MB of float32; parsing it is the first CPU cost once the kernels are fast.
+#   request / response = 16-byte header + row-major 4-byte words, little endian:
+#       magic b"B2S1" | uint32 rows | uint32 cols | uint32 flags        (flags bit 0: the words are int32 labels)
+BINARY_CONTENT_TYPE = "application/x-b2s-f32"
+_MAGIC = b"B2S1"
+
+
+def encode_rows(values):
+    """(rows, cols) float32 (or int32 labels) -> binary body"""
+    a = np.ascontiguousarray(values)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    if a.ndim != 2 or a.dtype not in (np.float32, np.int32):
+        raise TypeError("a 2-D float32 (or int32) array")
+    head = _MAGIC + np.array([a.shape[0], a.shape[1], 1 if a.dtype == np.int32 else 0], dtype="<u4").tobytes()
+    return head + a.astype(a.dtype.newbyteorder("<"), copy=False).tobytes()
+
+
+def decode_rows(body):
+    """binary body -> (rows, cols) array viewing the body's bytes (float32, or int32 when the flag says so)"""
+    mv = memoryview(body)
+    if len(mv) < 16 or bytes(mv[:4]) != _MAGIC:
+        raise ValueError("not an application/x-b2s-f32 body (bad magic)")
+    rows, cols, flags = (int(v) for v in np.frombuffer(mv[4:16], dtype="<u4"))
+    if len(mv) != 16 + rows * cols * 4:
+        raise ValueError(f"application/x-b2s-f32 body of {rows} x {cols} words must be {16 + rows * cols * 4} bytes, got {len(mv)}")
+    return np.frombuffer(mv[16:], dtype="<i4" if flags & 1 else "<f4").reshape(rows, cols)

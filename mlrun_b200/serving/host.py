@@ -18,6 +18,7 @@ import traceback
 
 import numpy as np
 
+from .codec import BINARY_CONTENT_TYPE
 from .events import MockEvent, MockTrigger, Response  # noqa: F401
 from .graph import RootFlowStep, RouterStep, graph_root_setter  # noqa: F401
 from .resolve import MLRunInvalidArgumentError, caller_globals, err_to_str, get_function, logger as _logger
@@ -217,6 +218,14 @@ class GraphServer(Serde):
         if event.headers:
             event.id = event.headers.get(EVENT_ID_HEADER, event.id)
             event.path = event.headers.get(EVENT_PATH_HEADER, event.path)
+        if event.content_type == BINARY_CONTENT_TYPE and isinstance(event.body, (bytes, bytearray, memoryview)):
+            # the engine's binary wire format: float32 rows in, 4-byte result words out, one fused launch (no JSON at all)
+            try:
+                return self.run_binary(event.body)
+            except Exception as exc:  # noqa: BLE001 -- like any other failure of this event: its 400
+                message = f"{type(exc).__name__}: {err_to_str(exc)}"
+                own.push_error(event, message, source="_handler")
+                return context.Response(body=message, content_type="text/plain", status_code=400)
         is_json = event.content_type in ("json", "application/json")
         if isinstance(event.body, (str, bytes)) and (not event.content_type or is_json):
             try:
@@ -324,6 +333,20 @@ class GraphServer(Serde):
             raise LoweringError(f"the feature vector has {svc.table.n_feat} features, the models take {plan.n_in}")
         out, status = svc.table.enrich(plan, svc._encode_keys(keys))
         return (out, status) if with_status else out
+
+    def run_binary(self, body):
+        """`application/x-b2s-f32` request (codec.encode_rows) -> Response carrying the outputs in the same format;
+        a batch with a row the device flags answers 400 as a whole, like `run_json` (one event carries all rows)"""
+        from . import codec
+
+        X = codec.decode_rows(body)
+        if X.dtype != np.float32:
+            raise ValueError("the request words must be float32 feature values")
+        out, status = self.compile().plan.run(np.ascontiguousarray(X), with_status=True)
+        if status.any():
+            return self.context.Response(body="ValueError: Input X contains NaN or infinity.", content_type="text/plain",
+                                         status_code=400)
+        return self.context.Response(body=codec.encode_rows(out), content_type=codec.BINARY_CONTENT_TYPE, status_code=200)
 
     def run_json(self, body, event_id=None):
         """wire-level batched entry for graphs whose root is a router / model server: a V2 body

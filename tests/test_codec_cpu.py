@@ -209,3 +209,45 @@ def test_number_grammar_fuzz_against_json_loads():
         np.testing.assert_array_equal(got[0, :1].view(np.uint32), ref.view(np.uint32))
 
     check()
+
+
+def test_binary_bodies_round_trip_and_reject_malformed_ones():
+    from mlrun_b200.serving import codec as bcodec
+
+    X = np.random.default_rng(3).normal(size=(37, 5)).astype(np.float32)
+    X[3, 2] = np.nan
+    body = bcodec.encode_rows(X)
+    assert len(body) == 16 + X.nbytes and body[:4] == b"B2S1"
+    back = bcodec.decode_rows(body)
+    assert back.dtype == np.float32 and np.array_equal(back.view(np.uint32), X.view(np.uint32))
+    labels = np.arange(12, dtype=np.int32)
+    got = bcodec.decode_rows(bcodec.encode_rows(labels))
+    assert got.dtype == np.int32 and got.shape == (12, 1) and np.array_equal(got[:, 0], labels)
+    for bad in (b"", b"B2S0" + body[4:], body[:-1], body + b"\0"):
+        with pytest.raises(ValueError):
+            bcodec.decode_rows(bad)
+
+
+def test_binary_content_type_through_graph_server_run(monkeypatch):
+    """GraphServer.run with content_type application/x-b2s-f32: rows in, result words out, no JSON; a flagged row is the
+    event's 400 (the same contract as run_json); runs on the emulated plan (no GPU)"""
+    from mlrun_b200 import api
+    from mlrun_b200.serving import codec as bcodec
+    from mlrun_b200.synthetic import tree_workload
+    from oracle import batch as obatch
+    from tests import emulated_plan
+
+    emulated_plan.install(monkeypatch)
+    wl = tree_workload(n_rows=64, n_feat=8, n_models=3, n_trees=5, depth=3, seed=2, n_fit=300)
+    server = wl.build_server(api)
+    event = api.MockEvent(body=bcodec.encode_rows(wl.X), path="/v2/models/infer", content_type=bcodec.BINARY_CONTENT_TYPE)
+    resp = server.run(event)
+    assert resp.status_code == 200 and resp.content_type == bcodec.BINARY_CONTENT_TYPE
+    out = bcodec.decode_rows(resp.body)
+    np.testing.assert_allclose(out[:, 0], obatch.tree_ensemble(wl)["out"], rtol=1e-5, atol=1e-5)
+    bad = wl.X.copy()
+    bad[5, 1] = np.inf
+    resp = server.run(api.MockEvent(body=bcodec.encode_rows(bad), path="/v2/models/infer", content_type=bcodec.BINARY_CONTENT_TYPE))
+    assert resp.status_code == 400 and "infinity" in resp.body
+    resp = server.run(api.MockEvent(body=b"garbage", path="/v2/models/infer", content_type=bcodec.BINARY_CONTENT_TYPE))
+    assert resp.status_code == 400 and "bad magic" in resp.body

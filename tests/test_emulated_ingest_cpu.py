@@ -64,3 +64,57 @@ def test_ingest_runs_the_steps_argument_checks_first():
     out = good.ingest(df)
     assert list(out.columns) == ["age_mapped", "age", "when"] and out.index.name == "id"  # mapped first (steps.py:206-211)
     assert out["age_mapped"].tolist() == [0, 0, 1, 0, 1, 1]
+
+
+def test_columnar_sources_give_the_frame_path_results_without_pandas():
+    """dict of arrays / Arrow table in, ColumnBatch (-> Arrow) out: the same columns, dtypes and counters as FeatureSet.ingest(df)
+    (SURVEY 8(f) #1); entity columns are carried through; int64 / float64 columns are refused like in frames"""
+    import contextlib
+    import io
+
+    import numpy as np
+    import pandas as pd
+    import pyarrow as pa
+
+    from mlrun_b200.feature_store import columnar
+    from mlrun_b200.feature_store import ingest as bi
+    from mlrun_b200.feature_store import steps as bs
+    from mlrun_b200.lowering import LoweringError
+    from mlrun_b200.synthetic import ingest_workload
+
+    iw = ingest_workload(n_rows=3000, seed=11)
+
+    def fset():
+        fs = bi.FeatureSet("cols", timestamp_key="timestamp")
+        cur = fs.graph
+        for st in iw.build_steps(bs):
+            cur = cur.to(st)
+        return fs
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        want = fset().ingest(iw.df)
+        cols = {name: iw.df[name].to_numpy() for name in iw.df.columns}
+        batch = fset().ingest(cols)
+        from_arrow = fset().ingest(pa.table(cols))
+    assert isinstance(batch, columnar.ColumnBatch) and len(batch) == 3000 and batch.names == list(want.columns)
+    for got in (batch, from_arrow):
+        for name in want.columns:
+            a, b = got[name], want[name].to_numpy()
+            assert a.dtype == b.dtype, (name, a.dtype, b.dtype)
+            assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f"), name
+    table = batch.to_arrow()
+    assert table.num_rows == 3000 and table.column_names == list(want.columns)
+    pd.testing.assert_frame_equal(batch.to_pandas(), want.reset_index(drop=True), check_exact=True)
+
+    # entities ride along, untouched
+    fs = bi.FeatureSet("e", entities=[bi.Entity("id")])
+    fs.graph.to(bs.Imputer(mapping={"x": 1.5}))
+    got = fs.ingest({"id": np.arange(5, dtype=np.int32), "x": np.array([1, np.nan, 3, np.nan, 5], dtype=np.float32)})
+    assert got.names == ["x"] and got["x"].tolist() == [1.0, 1.5, 3.0, 1.5, 5.0] and got.index["id"].tolist() == [0, 1, 2, 3, 4]
+    assert got.to_pandas().index.name == "id"
+    with pytest.raises(LoweringError, match="int64"):
+        fs.ingest({"id": np.arange(5, dtype=np.int32), "x": np.arange(5, dtype=np.int64)})
+    with pytest.raises(LoweringError, match="float64"):
+        fs.ingest({"id": np.arange(5, dtype=np.int32), "x": np.arange(5, dtype=np.float64)})
+    with pytest.raises(ValueError, match="Arrow nulls"):
+        fs.ingest(pa.table({"id": pa.array([1, 2], type=pa.int32()), "x": pa.array([1.0, None], type=pa.float32())}))
