@@ -308,6 +308,39 @@ __global__ void __launch_bounds__(128 * TPR / RPT, RPT == 2 ? RT_R2_MINB : (TPR 
   constexpr bool bulk = LM != 0;
   const uint32_t row_bytes = (uint32_t)p.n_in * 4u;
   uint32_t unknown_bits = 0;  // bit s: the key of this thread's row in stage s is not in the table (gather loader)
+  // Gather loader, software pipelined.  key -> slot -> row are three dependent DRAM reads (random over a table far larger
+  // than the TLB reach); done back to back they stall the thread -- which also computes -- for ~2 us per tile.  The loader
+  // is called for this CTA's tiles in order (T_j = blockIdx + j * grid), so every hop runs one call ahead of its consumer:
+  // call j finishes the slot probe started in call j - 1 and issues the row copy of T_j, starts the probe of T_{j+1}
+  // (its key was loaded in call j - 1) and loads the key of T_{j+2}.  Each load has a whole tile of compute to land.
+  long long gk_cur = 0, gk_nxt = 0;  // keys of T_j and T_{j+1} (thread tid: row tid of the tile)
+  longlong2 g_slot = make_longlong2(0, -1);
+  uint64_t g_hash = 0;
+  int64_t g_tile_nxt = 0;
+  auto g_key = [&](int64_t tile) -> long long {
+    const int64_t row = tile * TR + tid;
+    return row < p.n_rows ? __ldg(p.g_keys + row) : 0;
+  };
+  auto g_probe_start = [&](long long key) {
+    g_hash = mix64((uint64_t)key) & p.g_mask;
+    g_slot = __ldg(reinterpret_cast<const longlong2*>(p.g_slots) + g_hash);
+  };
+  auto g_probe_finish = [&](long long key) -> long long {  // the first slot decides for most keys (load factor <= 0.5)
+    uint64_t h = g_hash;
+    longlong2 sl = g_slot;
+    for (;;) {
+      if (sl.y < 0) return -1;
+      if (sl.x == key) return sl.y;
+      h = (h + 1) & p.g_mask;
+      sl = __ldg(reinterpret_cast<const longlong2*>(p.g_slots) + h);
+    }
+  };
+  if (LM == 1 && p.g_keys && tid < TR) {
+    gk_cur = g_key(blockIdx.x);
+    gk_nxt = g_key((int64_t)blockIdx.x + gridDim.x);
+    g_probe_start(gk_cur);
+    g_tile_nxt = (int64_t)blockIdx.x + 2 * (int64_t)gridDim.x;
+  }
   auto issue_bulk = [&](int st, int64_t row0) {
     int64_t left = p.n_rows - row0;
     const int rows = left < TR ? (left < 0 ? 0 : (int)left) : TR;
@@ -325,16 +358,21 @@ __global__ void __launch_bounds__(128 * TPR / RPT, RPT == 2 ? RT_R2_MINB : (TPR 
       }
     } else {
       if (tid == 0) mbar_expect_tx(&s_bar[st], (uint32_t)rows * row_bytes);
-      if (tid < rows) {
-        const char* src;
-        if (p.g_keys) {  // thread tid is also the q = 0 thread of tile row tid: it keeps the "unknown key" flag for the epilogue
-          const long long hit = table_find(p.g_slots, p.g_mask, p.g_keys[row0 + tid]);
-          unknown_bits = (unknown_bits & ~(1u << st)) | ((hit < 0 ? 1u : 0u) << st);
-          src = reinterpret_cast<const char*>(p.g_values + (hit < 0 ? p.g_missing_row : hit) * p.n_in);
-        } else {
-          src = p.rows + (row0 + tid) * p.row_stride;
+      if (p.g_keys) {
+        if (tid < TR) {  // thread tid is also the q = 0 thread of tile row tid: it keeps the "unknown key" flag for the epilogue
+          const long long hit = g_probe_finish(gk_cur);
+          if (tid < rows) {
+            unknown_bits = (unknown_bits & ~(1u << st)) | ((hit < 0 ? 1u : 0u) << st);
+            bulk_load(s_tiles + st * tile_words + tid * p.pitch,
+                      reinterpret_cast<const char*>(p.g_values + (hit < 0 ? p.g_missing_row : hit) * p.n_in), row_bytes, &s_bar[st]);
+          }
+          gk_cur = gk_nxt;
+          g_probe_start(gk_cur);        // consumed by the next call
+          gk_nxt = g_key(g_tile_nxt);   // consumed by the call after that
+          g_tile_nxt += gridDim.x;
         }
-        bulk_load(s_tiles + st * tile_words + tid * p.pitch, src, row_bytes, &s_bar[st]);
+      } else if (tid < rows) {
+        bulk_load(s_tiles + st * tile_words + tid * p.pitch, p.rows + (row0 + tid) * p.row_stride, row_bytes, &s_bar[st]);
       }
     }
   };

@@ -96,7 +96,7 @@ _GLOO_WORKER = r'''
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["REPO_ROOT"])
-from mlrun_b200.sharding import shard_bounds, gather_votes
+from mlrun_b200.sharding import shard_bounds, gather_votes, torch_exchange
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 n = 1001
@@ -107,6 +107,9 @@ assert full.shape == (n, 1) and torch.equal(full, votes), (rank, full.shape)
 t = torch.tensor([float(rank + 1)])
 dist.all_reduce(t, op=dist.ReduceOp.MAX)   # the bench's max-over-ranks timing reduction
 assert t.item() == world
+# the bootstrap channel of the merge communicator (MergeComm / b2s_comm_connect): 64 bytes per rank, in rank order
+blobs = torch_exchange(dist)(bytes([rank]) * 64)
+assert [b[0] for b in blobs] == list(range(world)) and all(len(b) == 64 for b in blobs)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
