@@ -16,6 +16,7 @@
 #include <deque>
 #include <limits>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -197,6 +198,7 @@ struct b2s_plan_s {
   T3Prep t3_prep{};
   int t3_prep_smem = 0;
   char* d_t3_blob = nullptr;
+  std::unique_ptr<T3Top> t3_top;  // top levels of every tree as a launch parameter (null: read from shared memory)
   const int32_t* d_t3_col_score = nullptr;
   // host staging for run_host
   char* h_stage_in = nullptr;
@@ -1048,7 +1050,7 @@ static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
   tb.data.resize(o_parts + sizeof(T3Part) * P);
   CUDA_TRY(cudaMalloc(&p->d_t3_blob, tb.data.size()));
   std::vector<T3Part> dev(P);
-  int cta0 = 0;
+  int cta0 = 0, top0 = 0;
   for (int i = 0; i < P; ++i) {
     T3Part& d = dev[i];
     d.nodes = parts[i].n_trees ? (const uint2*)(p->d_t3_blob + o_nodes[i]) : nullptr;
@@ -1058,8 +1060,23 @@ static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
     d.col0 = parts[i].col0;
     d.cta0 = cta0;
     d.n_ctas = n_ctas[i];
-    d.pad = 0;
+    d.top0 = top0;
+    top0 += parts[i].n_trees;
     cta0 += n_ctas[i];
+  }
+  // the top three levels as a launch parameter (constant bank) when every tree fits and has them
+  p->t3_top.reset();
+  {
+    const char* tenv = getenv("B2S_T3_TOPC");
+    // measured (r2h): 0.3187 vs 0.3209 ms per 256 Ki events on configs[2] -- within noise, so it stays opt-in
+    if (D >= 3 && top0 <= kT3TopTrees && tenv && atoi(tenv) == 1 && !getenv("B2S_T3_UNROLL")) {
+      p->t3_top.reset(new T3Top);
+      memset(p->t3_top.get(), 0, sizeof(T3Top));
+      int q0 = 0;
+      for (auto& hp : parts)
+        for (int q = 0; q < hp.n_trees; ++q, ++q0)
+          for (int j = 0; j < 7; ++j) p->t3_top->n[(size_t)q0 * 7 + j] = hp.nodes[(size_t)q * NN + 1 + j];
+    }
   }
   memcpy(tb.data.data() + o_parts, dev.data(), sizeof(T3Part) * P);
   CUDA_TRY(cudaMemcpy(p->d_t3_blob, tb.data.data(), tb.data.size(), cudaMemcpyHostToDevice));
@@ -1783,7 +1800,7 @@ extern "C" const char* b2s_plan_kernel(b2s_plan_t p) {
   int lm = rt_load_mode();
   if (lm == 2 && !(p->rt_NCH >= 8 && p->n_in == p->rt_NCH * 4 && tensor_map_encoder())) lm = 1;
   if (p->dense_ok) snprintf(buf, sizeof(buf), "dense_head_kernel<N=%d> (tcgen05.mma kind::tf32 x3, TMEM accumulator; %d scores over %d columns)", p->dense.n_pad, p->dense.n_scores, p->dense.n_in);
-  else if (p->t3_ok) snprintf(buf, sizeof(buf), "t3_prep_kernel + trees3_kernel<D=%d,%s> + t3_vote_kernel (%d parts resident in shared memory, %d walking warps)", p->t3_D, p->t3_miss ? "NaN routing" : "floats", p->t3_parts, p->t3.warps);
+  else if (p->t3_ok) snprintf(buf, sizeof(buf), "t3_prep_kernel + trees3_kernel<D=%d,%s> + t3_vote_kernel (%d parts resident in shared memory, %d walking warps%s)", p->t3_D, p->t3_miss ? "NaN routing" : "floats", p->t3_parts, p->t3.warps, p->t3_top ? ", top levels in the constant bank" : "");
   else if (p->t2_ok) snprintf(buf, sizeof(buf), "trees_model_kernel<%d> + vote_kernel (models resident in shared memory)", p->t2_NS);
   else if (p->rt_ok) snprintf(buf, sizeof(buf), "rowthread_kernel<NCH=%d,NS=%d,TPR=%d,RPT=%d,%s>", p->rt_NCH, p->rt_NS, p->rt_TPR, lm == 2 ? p->rt_RPT : 1, lm == 2 ? "TMA tensor-map loads" : (lm == 1 ? "TMA bulk loads" : "cp.async loads"));
   else if (p->rw_ok) snprintf(buf, sizeof(buf), "rowwarp_kernel<L=%d,CPL=%d,NS=%d,U=%d,CS=%d>", p->rw_L, p->rw_CPL, p->rw_NS, p->rw_U, p->rw_CS);
@@ -1884,7 +1901,7 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
     t.n_rows = n_rows;
     t.partial = sc.pred;
     t.col_stride = sc.rows;
-    e3 = t3_launch_walk(t, p->t3_D, p->t3_miss, p->t3_grid, p->t3_block, p->t3_smem, (int)G.prop.sharedMemPerBlockOptin, st);
+    e3 = t3_launch_walk(t, p->t3_top.get(), p->t3_D, p->t3_miss, p->t3_grid, p->t3_block, p->t3_smem, (int)G.prop.sharedMemPerBlockOptin, st);
     if (e3 != cudaSuccess) return fail(B2S_ERR_CUDA, "tree kernel launch failed: %s", cudaGetErrorString(e3));
     const int vgrid = (int)std::max<int64_t>(1, std::min<int64_t>(4 * G.prop.multiProcessorCount, (n_rows + 255) / 256));
     e3 = t3_launch_vote(k, sc.pred, sc.rows, p->d_t3_col_score, C, sc.row_bad, vgrid, st);

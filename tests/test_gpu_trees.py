@@ -95,6 +95,35 @@ def test_depths(depth, n_trees):
     np.testing.assert_allclose(plan.run(wl.X), obatch.tree_ensemble(wl)["per_model"], rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("depth,routes_nan", [(3, False), (6, False), (5, True)])
+def test_top_levels_from_the_constant_bank_equal_the_shared_memory_walk(depth, routes_nan, monkeypatch):
+    """B2S_T3_TOPC=1: the walk reads heap nodes 1..7 of every tree from the launch parameters (constant bank) instead of
+    shared memory (the default; measured equal): same comparisons, same fp64 adds in the same order -> bit-identical outputs"""
+    if routes_nan:
+        from sklearn.ensemble import RandomForestRegressor
+
+        rng = np.random.default_rng(70)
+        Xf = rng.normal(size=(3000, 16)).astype(np.float32)
+        Xf[rng.random(Xf.shape) < 0.1] = np.nan
+        yf = np.nan_to_num(Xf[:, 0]) * 2 + np.nan_to_num(Xf[:, 3]) + rng.normal(size=3000) * 0.1
+        models = [RandomForestRegressor(n_estimators=20, max_depth=depth, random_state=i).fit(Xf, yf) for i in range(2)]
+        X = rng.normal(size=(1500, 16)).astype(np.float32)
+        X[rng.random(X.shape) < 0.1] = np.nan
+    else:
+        wl = tree_workload(n_rows=1500, n_feat=16, n_models=2, n_trees=20, depth=depth, seed=60 + depth, n_fit=3000)
+        models, X = wl.models, wl.X
+    packed = [packing.pack_model(m) for m in models]
+    monkeypatch.setenv("B2S_T3_TOPC", "1")
+    plan = ColumnProgram(names(16)).build_plan(packed)
+    assert "top levels in the constant bank" in plan.kernel, plan.kernel
+    got = plan.run(X)
+    monkeypatch.delenv("B2S_T3_TOPC")
+    shared = ColumnProgram(names(16)).build_plan(packed)
+    assert "constant bank" not in shared.kernel and "trees3_kernel" in shared.kernel, shared.kernel
+    assert np.array_equal(got, shared.run(X))
+    np.testing.assert_allclose(got, np.stack([m.predict(X.astype(np.float64)) for m in models], axis=1), rtol=RTOL, atol=ATOL)
+
+
 def test_a_model_larger_than_one_cta_is_split_into_parts():
     """600 depth-6 trees do not fit one CTA's shared memory: the model becomes several parts whose partial sums are added
     in a fixed order"""
