@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-BYTES_PER_EVENT = {"flow3_ens4": 260, "flow3_linear": 260, "trees_ens4": 516, "router8": 260, "ingest6": 2280, "enrich_ens4": 536}
+BYTES_PER_EVENT = {"flow3_ens4": 260, "flow3_linear": 260, "trees_ens4": 516, "router8": 260, "dense_ens12": 260, "ingest6": 2280, "enrich_ens4": 536}
 
 
 def parse():
@@ -68,6 +68,8 @@ def make_workload(name, n_rows, seed=2):
         return flow3_workload(n_rows=n_rows, n_num=56, n_cat=8, seed=seed, n_models=1)
     if name == "router8":
         return router8_workload(n_rows, seed=4)
+    if name == "dense_ens12":
+        return dense12_workload(n_rows, seed=6)
     return tree_cfg3_workload(n_rows, seed=3)
 
 
@@ -101,6 +103,21 @@ def router8_workload(n_rows, seed=4):
         lin = LinearRegression()
         lin.coef_, lin.intercept_, lin.n_features_in_ = wr.normal(size=64), float(wr.normal()), 64
         models += [lin, trees[i]]  # alternating: linear, tree, linear, tree ...
+    X = np.random.default_rng(seed).normal(size=(n_rows, 64)).astype(np.float32)
+    return Router8Workload(X, models)
+
+
+def dense12_workload(n_rows, seed=6):
+    """the dense linear-predict path the north_star puts on the tensor cores: a VotingEnsemble of 12 linear scorers over 64 raw
+    float32 features (random float64 weights, like configs[1]'s) -- 12 scores per event, N = 16 on tcgen05 (csrc/b2s_dense.cu)"""
+    from sklearn.linear_model import LinearRegression
+
+    wr = np.random.default_rng(seed + 20)
+    models = []
+    for _ in range(12):
+        lin = LinearRegression()
+        lin.coef_, lin.intercept_, lin.n_features_in_ = wr.normal(size=64), float(wr.normal()), 64
+        models.append(lin)
     X = np.random.default_rng(seed).normal(size=(n_rows, 64)).astype(np.float32)
     return Router8Workload(X, models)
 
@@ -351,6 +368,8 @@ def workload_desc(name):
         "flow3_linear": "3-step flow Imputer->OneHotEncoder->linear predict, 64-feat f32 (BASELINE configs[1])",
         "router8": "router of 8 scorers (4 linear + 4 GradientBoostingRegressor(100 trees, depth 6)), 64-feat f32, sharded by events "
                    "with the fused ensemble-merge (BASELINE configs[3], SURVEY 8(d) config 4)",
+        "dense_ens12": "VotingEnsemble of 12 linear scorers over 64 raw f32 features: the dense linear-predict path on the tensor "
+                       "cores (tcgen05 kind::tf32, exact 3-term splits; north_star)",
         "trees_ens4": "VotingEnsemble of 4 GradientBoostingRegressor(100 trees, depth 6, fit on 20 000 rows, all features), "
                       "128-feat f32 (BASELINE configs[2], SURVEY 8(d) config 3)",
         "enrich_ens4": "real-time enrichment: entity keys -> online feature table (4 Mi keys x 64 f32, 1 GiB in HBM) -> $mean imputing "
@@ -712,7 +731,8 @@ def main():
             torch.cuda.empty_cache()
             rows = []
             for nm, bb in (("flow3_ens4", 4096), ("flow3_ens4", 65536), ("flow3_ens4", 1048576), ("flow3_linear", 4096),
-                           ("flow3_linear", 1048576), ("trees_ens4", 16384), ("trees_ens4", 262144)):
+                           ("flow3_linear", 1048576), ("trees_ens4", 16384), ("trees_ens4", 262144), ("dense_ens12", 4096),
+                           ("dense_ens12", 1048576)):
                 try:
                     rows.append(serving_config_bench(nat, torch, nm, bb))
                 except Exception as exc:  # noqa: BLE001 -- a failing row must not hide the others

@@ -214,7 +214,7 @@ int b2s_ipc_close(void* dptr);
  * next kernel) reads a complete response; *d_merged is that response, (world x max_rows_per_rank x out_cols) words, rank
  * r's rows at r * max_rows_per_rank.  Ranks must wait on every step before launching the next one: seeing all flags of
  * step e proves that every peer has consumed step e - 1, which is what makes two buffers enough.  A peer that never
- * signals makes the wait give up after 2 s (b2s_comm_check reports B2S_ERR_TIMEOUT) instead of hanging the GPU. */
+ * signals makes the wait give up after B2S_COMM_TIMEOUT_MS (default 10 s; b2s_comm_check reports B2S_ERR_TIMEOUT) instead of hanging the GPU. */
 typedef struct b2s_comm_s* b2s_comm_t;
 int b2s_comm_create(int32_t rank, int32_t world, int64_t max_rows_per_rank, int32_t out_cols, b2s_comm_t* out);
 int b2s_comm_handle(b2s_comm_t comm, void* handle64 /* 64 bytes out */);

@@ -3,21 +3,29 @@
 // north_star: "tensor cores only on the dense linear-predict path".  A linear / logistic scorer (or an ensemble of them)
 // with many scores per event -- a 16-class LogisticRegression is scores = X (B x K) . W^T (K x 16) + b, then argmax
 // (sklearn decision_function + predict behind PickleModelServer.predict, frameworks/_ml_common/pkl_model_server.py:52-60)
-// -- is a GEMM with a skinny N.  The fp64 FMA path of the row kernels does K x N DFMAs per event and turns FP64-pipe bound
-// beyond ~8 scores; here the products run on the tensor cores and the kernel goes back to being HBM bound:
+// -- is a GEMM with a skinny N.  The fp64 FMA path of the row kernels does K x N DFMAs per event; here the products run on
+// the tensor cores.  One persistent CTA per SM, four roles connected by mbarriers (no CTA-wide barrier in the loop):
 //
-//   HBM rows --TMA boxes (32 floats x 128 rows, 128-byte swizzle)--> shared memory, 2 stages
-//     split   every value x (after the Imputer) becomes xh = tf32(x) and xl = tf32(x - xh), written in place / to a second
-//             tile in the same K-major SWIZZLE_128B layout (what the TMA produced is already the UMMA operand layout)
-//     mma     ONE thread issues  D  = xh . wh ;  D += xh . wl ;  D += xl . wh   (tcgen05.mma.cta_group::1.kind::tf32, M = 128,
-//             N = 16 | 32, K = 8 per instruction; weights split on the host the same way) -- the "3xTF32" scheme: every
-//             partial product is exact in the fp32 accumulator's input, the dropped xl . wl term is < 2^-22 |x w|
-//     TMEM    the 128 x N fp32 accumulator lives in 32 TMEM columns; tcgen05.commit -> mbarrier tells the CTA it is complete
-//     epilogue  thread r reads row r with tcgen05.ld (32 lanes x 32 bit x N), adds the intercepts in fp64, applies each
-//             model's link (argmax / > 0 / identity) and the VotingEnsemble reduce, stores votes + status (to every merge
-//             target when sharded) -- the same epilogue functions as the other kernels.
-// Scores are within ~1e-6 relative of the fp64 path (tests: rtol 1e-5); labels are exact unless two class scores tie to
-// that precision.  Evidence to look for: SASS UTCHMMA / UTCQMMA-family + LDTM, ncu sm__pipe_tensor_cycles_active > 0.
+//   producer   (1 thread)   TMA boxes (32 floats x 128 rows, 128-byte swizzle: already the UMMA K-major operand layout) into
+//                           a ring of 4 raw stages
+//   split      (8 warps)    every value x (after the Imputer) becomes xh + xm + xl, three tf32 numbers that add up to x
+//                           EXACTLY (11 + 11 + 2 significant bits, by masking and exact subtraction), written to a ring of 2
+//                           operand stages; non-finite values flag their row.  Warp w owns the 16-byte chunk w of every box
+//                           row, lanes take consecutive rows: LDS.128 / STS.128 without bank conflicts, addresses constant
+//   mma        (1 thread)   per k-step of 8 columns six tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = 16 | 32):
+//                             main [box]  (+)= xh.wh                                  one accumulator per 32-column box
+//                             small       (+)= xh.wm + xm.wh + xm.wm + xh.wl + xl.wh   one accumulator per tile
+//                           weights are split on the host into wh + wm + wl (33 bits of the float64 coefficient); the dropped
+//                           products are < 2^-33 |x w|.  Every product is exact in fp32; what rounds is the accumulation
+//                           (the tensor core truncates), so large terms get one accumulator per box and the small ones
+//                           (2^-11 of the large) their own: the error is a few ulp of a 32-column partial sum, ~1e-6
+//                           absolute for unit-scale data, where a single accumulator lost 1e-5 (measured, r2h)
+//   TMEM       two sets of (boxes + 1) x N fp32 columns: the epilogue of tile t overlaps the MMAs of tile t + 1
+//   epilogue   (4 warps)    thread r reads row r of every accumulator (tcgen05.ld 32x32b), adds them and the intercepts,
+//                           applies the links and the VotingEnsemble reduce, stores votes + status (to every merge target
+//                           when sharded) -- float32 fast paths for the common shapes, the generic epilogue functions of the
+//                           other kernels (fp64) for the rest.
+// Evidence to look for: SASS UTCHMMA + LDTM + UTMALDG, ncu sm__pipe_tensor_cycles_active > 0.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -52,149 +60,165 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
 
-template <int NP>  // padded score count: 16 | 32
-__global__ void __launch_bounds__(kDM) dense_head_kernel(const __grid_constant__ DenseParams p, const __grid_constant__ KParams kp,
-                                                        const __grid_constant__ CUtensorMap tmap) {
+constexpr int kRawStages = 4;                  // TMA landing boxes of 16 KB
+constexpr int kOutStages = 2;                  // operand stages of 3 x 16 KB (xh | xm | xl)
+constexpr int kSplitWarps = 8, kEpiWarps = 4;  // + producer warp + MMA warp
+constexpr int kDenseThreads = (2 + kEpiWarps + kSplitWarps) * 32;
+constexpr uint32_t kBoxBytes = kDM * 128u;     // one box: 128 rows x 32 floats
+constexpr uint32_t kOutBytes = 3u * kBoxBytes;
+constexpr uint32_t kOffOut = kRawStages * kBoxBytes, kOffB = kOffOut + kOutStages * kOutBytes;
+constexpr int kBadDepth = 4;                   // flag buffers: the split may run this many tiles ahead of the epilogue
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+#define B2S_TMEM_LD16(r, c0, addr)                                                                                          \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+               : "=r"(r[c0 + 0]), "=r"(r[c0 + 1]), "=r"(r[c0 + 2]), "=r"(r[c0 + 3]), "=r"(r[c0 + 4]), "=r"(r[c0 + 5]),          \
+                 "=r"(r[c0 + 6]), "=r"(r[c0 + 7]), "=r"(r[c0 + 8]), "=r"(r[c0 + 9]), "=r"(r[c0 + 10]), "=r"(r[c0 + 11]),       \
+                 "=r"(r[c0 + 12]), "=r"(r[c0 + 13]), "=r"(r[c0 + 14]), "=r"(r[c0 + 15])                                        \
+               : "r"(addr))
+
+template <int NP, int BOXES, bool FILL>  // padded score count 16 | 32; input columns / 32; an Imputer is folded in
+__global__ void __launch_bounds__(kDenseThreads, 1) dense_head_kernel(const __grid_constant__ DenseParams p, const __grid_constant__ KParams kp,
+                                                                      const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) unsigned char smem_dense[];
-  unsigned char* const smem = smem_dense;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int K = p.n_in, boxes = K >> 5;
-  const uint32_t tile_bytes = (uint32_t)boxes * kDM * 128u;  // one A tile: boxes x (128 rows x 128 B)
-  // shared memory: A stage 0 | A stage 1 | A residual (xl) | B hi | B lo | bias, fill, flags, barriers, TMEM address
-  unsigned char* s_a[2] = {smem, smem + tile_bytes};
-  unsigned char* s_al = smem + 2 * tile_bytes;
-  unsigned char* s_bh = smem + 3 * tile_bytes;
-  const uint32_t b_bytes = (uint32_t)boxes * NP * 128u;
-  unsigned char* s_bl = s_bh + b_bytes;
-  unsigned char* s_misc = s_bl + b_bytes;
-  float* s_fill = reinterpret_cast<float*>(s_misc);               // [K]
-  int* s_bad = reinterpret_cast<int*>(s_misc + 4 * 128);          // [128]
-  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_misc + 1024);  // [2]
-  uint64_t* s_mma = s_full + 2;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_full + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int K = BOXES * 32;
+  constexpr uint32_t kBTerm = (uint32_t)BOXES * NP * 128u;  // one weight term: BOXES x (NP rows x 128 B)
+  constexpr uint32_t kOffMisc = kOffB + 3u * kBTerm;
+  float* s_fill = reinterpret_cast<float*>(smem_dense + kOffMisc);                       // [K]
+  int* s_bad = reinterpret_cast<int*>(smem_dense + kOffMisc + 512);                      // [kBadDepth][128]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_dense + kOffMisc + 512 + kBadDepth * 512);
+  uint64_t* raw_full = s_bar;                   // [4]  TMA transaction bytes
+  uint64_t* raw_empty = s_bar + 4;              // [4]  8 split warps
+  uint64_t* out_full = s_bar + 8;               // [2]  8 split warps
+  uint64_t* out_empty = s_bar + 10;             // [2]  tcgen05.commit
+  uint64_t* acc_full = s_bar + 12;              // [2]  tcgen05.commit
+  uint64_t* acc_empty = s_bar + 14;             // [2]  128 epilogue threads
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
+  constexpr uint32_t kAccCols = (uint32_t)(BOXES + 1) * NP;  // one accumulator set
 
   // ---- one-time setup: TMEM columns, barriers, the weights in the UMMA layout (rows = scores, K-major, 128-byte swizzle)
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(s_tmem)) : "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
-    mbar_init(s_mma, 1);
+    for (int i = 0; i < kRawStages; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_empty[i], kSplitWarps);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&out_full[i], kSplitWarps);
+      mbar_init(&out_empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], kEpiWarps * 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < NP * K; i += kDM) {
+  for (int i = tid; i < NP * K; i += kDenseThreads) {
     const int n = i / K, k = i - n * K;
     const int b = k >> 5, c = (k & 31) >> 2, e = k & 3;
-    const uint32_t off = (uint32_t)b * NP * 128u + (uint32_t)n * 128u + (uint32_t)((c ^ (n & 7)) << 4) + (uint32_t)e * 4u;
-    *reinterpret_cast<float*>(s_bh + off) = p.wh[i];
-    *reinterpret_cast<float*>(s_bl + off) = p.wl[i];
+    const uint32_t off = kOffB + (uint32_t)b * NP * 128u + (uint32_t)n * 128u + (uint32_t)((c ^ (n & 7)) << 4) + (uint32_t)e * 4u;
+    *reinterpret_cast<float*>(smem_dense + off) = p.wh[i];
+    *reinterpret_cast<float*>(smem_dense + off + kBTerm) = p.wm[i];
+    *reinterpret_cast<float*>(smem_dense + off + 2u * kBTerm) = p.wl[i];
   }
-  for (int i = tid; i < K; i += kDM) s_fill[i] = p.fill[i];
-  s_bad[tid] = 0;
+  for (int i = tid; i < K; i += kDenseThreads) s_fill[i] = p.fill[i];
+  for (int i = tid; i < kBadDepth * kDM; i += kDenseThreads) s_bad[i] = 0;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores above -> visible to the tensor core
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *s_tmem;
-  const uint32_t idesc = umma_idesc(NP);
-
   const int64_t n_tiles = (p.n_rows + kDM - 1) / kDM;
-  auto issue = [&](int64_t t, int stage) {  // one thread: the tile's boxes; rows past the end arrive as zeros
-    mbar_expect_tx(&s_full[stage], tile_bytes);
-    for (int b = 0; b < boxes; ++b)
-      tensor_load_2d(s_a[stage] + (size_t)b * kDM * 128, &tmap, b * 32, (int)(t * kDM), &s_full[stage]);
-  };
-  if (tid == 0 && (int64_t)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+  const uint32_t sbase = smem_u32(smem_dense);
 
-  int it = 0;
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-    const int stage = it & 1;
-    const int64_t row0 = t * kDM;
-    mbar_wait(&s_full[stage], (uint32_t)(it >> 1) & 1u);
-    // the other stage was this CTA's previous tile: its MMAs completed before that tile's epilogue ran, so it is free
-    if (tid == 0 && t + gridDim.x < n_tiles) issue(t + gridDim.x, stage ^ 1);
-    {  // ---- split: x -> (xh, xl), Imputer and the non-finite test on the way.  Lanes take consecutive rows: conflict free.
-      const int64_t left = p.n_rows - row0;
-      const int rows = left < kDM ? (int)left : kDM;
-      const int n_chunks = (K >> 2) * kDM;
-      for (int i0 = tid; i0 < n_chunks; i0 += kDM * 4) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * kDM;
-          const int c = i / kDM, rr = i - c * kDM;
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < n_chunks)
-            v[u] = *reinterpret_cast<const float4*>(s_a[stage] + (size_t)(c >> 3) * (kDM * 128) + rr * 128 + (((c & 7) ^ (rr & 7)) << 4));
+  if (warp == 0) {
+    // =============================================================================================== producer
+    if (lane == 0) {
+      int q = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+        for (int b = 0; b < BOXES; ++b, ++q) {
+          const int rs = q % kRawStages, use = q / kRawStages;
+          if (use > 0) mbar_wait(&raw_empty[rs], (uint32_t)(use - 1) & 1u);
+          mbar_expect_tx(&raw_full[rs], kBoxBytes);
+          tensor_load_2d(smem_dense + (size_t)rs * kBoxBytes, &tmap, b * 32, (int)(t * kDM), &raw_full[rs]);  // rows past the end: zeros
         }
+    }
+  } else if (warp == 1) {
+    // =============================================================================================== tensor-core feeder
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(NP);
+      int q = 0, i = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        const int a = i & 1;
+        if (i >= 2) mbar_wait(&acc_empty[a], (uint32_t)((i >> 1) - 1) & 1u);  // the epilogue of tile i - 2 has read this set
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_set = tmem + (uint32_t)a * kAccCols, d_small = d_set + (uint32_t)BOXES * NP;
+        for (int b = 0; b < BOXES; ++b, ++q) {
+          const int os = q % kOutStages;
+          mbar_wait(&out_full[os], (uint32_t)(q / kOutStages) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t xh = sbase + kOffOut + (uint32_t)os * kOutBytes, xm = xh + kBoxBytes, xl = xm + kBoxBytes;
+          const uint32_t wh = sbase + kOffB + (uint32_t)b * NP * 128u, wm = wh + kBTerm, wl = wm + kBTerm;
+          const uint32_t d_main = d_set + (uint32_t)b * NP;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * kDM;
-          if (i >= n_chunks) break;
-          const int c = i / kDM, rr = i - c * kDM;
-          float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-          uint32_t hi[4], lo[4];
-          bool bad = false;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = xs[e];
-            if (p.any_fill) {
-              const float f = s_fill[c * 4 + e];
-              x = (x != x) ? f : x;  // Imputer._impute (feature_store/steps.py:397-406); NaN where nothing is imputed
-            }
-            bad |= !is_finite_f(x) && rr < rows;
-            x = is_finite_f(x) ? x : 0.0f;  // a flagged row must not poison the accumulator of its neighbours' columns
-            hi[e] = tf32_hi(x);
-            lo[e] = tf32_hi(x - __uint_as_float(hi[e]));  // exact difference, then its own 11 significant bits
+          for (int kk = 0; kk < 4; ++kk) {  // 8 tf32 = 32 bytes per instruction inside the 128-byte swizzle atom
+            const uint32_t ko = (uint32_t)kk * 32u;
+            umma_tf32(d_main, umma_desc(xh + ko), umma_desc(wh + ko), idesc, kk > 0);
+            umma_tf32(d_small, umma_desc(xh + ko), umma_desc(wm + ko), idesc, (b | kk) != 0);
+            umma_tf32(d_small, umma_desc(xm + ko), umma_desc(wh + ko), idesc, true);
+            umma_tf32(d_small, umma_desc(xm + ko), umma_desc(wm + ko), idesc, true);
+            umma_tf32(d_small, umma_desc(xh + ko), umma_desc(wl + ko), idesc, true);
+            umma_tf32(d_small, umma_desc(xl + ko), umma_desc(wh + ko), idesc, true);
           }
-          const size_t off = (size_t)(c >> 3) * (kDM * 128) + rr * 128 + (((c & 7) ^ (rr & 7)) << 4);
-          *reinterpret_cast<uint4*>(s_a[stage] + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(s_al + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          if (bad) atomicOr(&s_bad[rr], 1);
+          umma_commit(&out_empty[os]);  // arrives when the MMAs above have read the stage
         }
+        umma_commit(&acc_full[a]);
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {  // ---- one thread feeds the tensor core: 3 x K / 8 instructions, then the completion arrives on s_mma
+  } else if (warp < 2 + kEpiWarps) {
+    // =============================================================================================== epilogue
+    const int quarter = warp & 3;  // TMEM lanes 32 q .. 32 q + 31 belong to the warps with (warp id % 4) == q
+    const int rr = quarter * 32 + lane;
+    int i = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const int a = i & 1;
+      mbar_wait(&acc_full[a], (uint32_t)(i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(s_a[stage]), a_lo = smem_u32(s_al), b_hi = smem_u32(s_bh), b_lo = smem_u32(s_bl);
-      bool acc = false;
-      for (int b = 0; b < boxes; ++b)
-        for (int kk = 0; kk < 4; ++kk) {  // 8 tf32 = 32 bytes per instruction inside the 128-byte swizzle atom
-          const uint32_t ao = (uint32_t)b * kDM * 128u + (uint32_t)kk * 32u, bo = (uint32_t)b * NP * 128u + (uint32_t)kk * 32u;
-          umma_tf32(tmem, umma_desc(a_hi + ao), umma_desc(b_hi + bo), idesc, acc);
-          umma_tf32(tmem, umma_desc(a_hi + ao), umma_desc(b_lo + bo), idesc, true);
-          umma_tf32(tmem, umma_desc(a_lo + ao), umma_desc(b_hi + bo), idesc, true);
-          acc = true;
-        }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(s_mma)) : "memory");
-    }
-    mbar_wait(s_mma, (uint32_t)it & 1u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {  // ---- epilogue: thread r owns row r (TMEM lane r: warp w reads lanes 32 w .. 32 w + 31)
-      uint32_t r[NP];
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+      int* flag = s_bad + (i & (kBadDepth - 1)) * kDM + rr;
+      const uint32_t st = *flag ? 1u : 0u;
+      *flag = 0;
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * kAccCols;
+      float sc[NP];
 #pragma unroll
-      for (int c0 = 0; c0 < NP; c0 += 16)
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(r[c0 + 0]), "=r"(r[c0 + 1]), "=r"(r[c0 + 2]), "=r"(r[c0 + 3]), "=r"(r[c0 + 4]), "=r"(r[c0 + 5]), "=r"(r[c0 + 6]),
-              "=r"(r[c0 + 7]), "=r"(r[c0 + 8]), "=r"(r[c0 + 9]), "=r"(r[c0 + 10]), "=r"(r[c0 + 11]), "=r"(r[c0 + 12]),
-              "=r"(r[c0 + 13]), "=r"(r[c0 + 14]), "=r"(r[c0 + 15])
-            : "r"(taddr + (uint32_t)c0));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int64_t row = row0 + tid;
-      const uint32_t st = s_bad[tid] ? 1u : 0u;
-      s_bad[tid] = 0;
+      for (int g = 0; g < NP; g += 16) {
+        uint32_t r[(BOXES + 1) * 16];
+#pragma unroll
+        for (int j = 0; j <= BOXES; ++j) B2S_TMEM_LD16(r, j * 16, taddr + (uint32_t)(j * NP + g));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          float v = __uint_as_float(r[k]);  // boxes in column order, then the small terms
+#pragma unroll
+          for (int j = 1; j <= BOXES; ++j) v += __uint_as_float(r[j * 16 + k]);
+          sc[g + k] = v;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&acc_empty[a]);  // the accumulators are in registers: the MMAs of tile i + 2 may overwrite the set
+      const int64_t row = t * kDM + rr;
       if (row < p.n_rows) {
         if (p.epi != DENSE_EPI_GENERIC && kp.n_peers == 0) {
           // ---- fast epilogues: float32 registers only (compile-time indices; the intercepts are constant-bank operands)
-          float sc[NP];
 #pragma unroll
-          for (int k = 0; k < NP; ++k) sc[k] = __uint_as_float(r[k]) + p.biasf[k];
+          for (int k = 0; k < NP; ++k) sc[k] += p.biasf[k];
           if (p.epi == DENSE_EPI_SCORES) {  // out_cols == n_scores consecutive floats per row
             float* o = kp.out + row * kp.out_cols;
             if ((kp.out_cols & 3) == 0) {
@@ -227,42 +251,107 @@ __global__ void __launch_bounds__(kDM) dense_head_kernel(const __grid_constant__
           }
           if (kp.status) kp.status[row] = (int32_t)st;
         } else {
-          double sc[NP];
+          double scd[NP];
 #pragma unroll
-          for (int k = 0; k < NP; ++k) sc[k] = k < p.n_scores ? (double)__uint_as_float(r[k]) + p.bias[k] : 0.0;
+          for (int k = 0; k < NP; ++k) scd[k] = k < p.n_scores ? (double)sc[k] + p.bias[k] : 0.0;
           double pred[kMaxModels];
           for (int m = 0; m < kp.n_models; ++m) {
             const ModelDesc md = kp.models[m];
-            pred[m] = apply_link(md, sc + md.score_off, kp.classes);
+            pred[m] = apply_link(md, scd + md.score_off, kp.classes);
           }
           vote_and_store(kp, pred, row, st);
         }
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();  // the accumulator, the residual tile and the flags are free for the next tile
+  } else {
+    // =============================================================================================== split
+    const int w = warp - 2 - kEpiWarps;  // chunk of 4 columns inside every 32-column box row
+    const uint32_t toff = (uint32_t)lane * 128u + (uint32_t)((w ^ (lane & 7)) << 4);  // rows lane + 32 j: + 4096 j
+    int q = 0, i = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i)
+      for (int b = 0; b < BOXES; ++b, ++q) {
+        const int rs = q % kRawStages, os = q % kOutStages;
+        mbar_wait(&raw_full[rs], (uint32_t)(q / kRawStages) & 1u);
+        if (q >= kOutStages) mbar_wait(&out_empty[os], (uint32_t)(q / kOutStages - 1) & 1u);
+        const unsigned char* src = smem_dense + (size_t)rs * kBoxBytes + toff;
+        unsigned char* dst = smem_dense + kOffOut + (size_t)os * kOutBytes + toff;
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(src + j * 4096);
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (FILL) f = *reinterpret_cast<const float4*>(s_fill + (b * 8 + w) * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float xs[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+          const float fs[4] = {f.x, f.y, f.z, f.w};
+          uint32_t h[4], m[4], l[4];
+          float probe = 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = xs[e];
+            if (FILL) x = (x != x) ? fs[e] : x;  // Imputer._impute (feature_store/steps.py:397-406); NaN where nothing is imputed
+            probe = fmaf(x, 0.f, probe);              // NaN as soon as one value is NaN or +-Inf
+            h[e] = tf32_hi(x);
+            const float r1 = x - __uint_as_float(h[e]);  // exact: the low 13 bits of x
+            m[e] = tf32_hi(r1);
+            l[e] = __float_as_uint(r1 - __uint_as_float(m[e]));  // exact: at most 2 significant bits are left
+          }
+          *reinterpret_cast<uint4*>(dst + j * 4096) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(dst + j * 4096 + kBoxBytes) = make_uint4(m[0], m[1], m[2], m[3]);
+          *reinterpret_cast<uint4*>(dst + j * 4096 + 2 * kBoxBytes) = make_uint4(l[0], l[1], l[2], l[3]);
+          // a non-finite value makes its own row's scores NaN (rows are independent in the product) and flags the row
+          if (probe != probe) atomicOr(s_bad + (i & (kBadDepth - 1)) * kDM + lane + 32 * j, 1);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stores above -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&out_full[os]);
+          mbar_arrive(&raw_empty[rs]);
+        }
+      }
   }
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
   merge_signal(kp.sig);
+}
+
+template <int NP, int BOXES, bool FILL>
+static cudaError_t dense_go(const DenseParams& p, const KParams& kp, const CUtensorMap& tmap, int grid, int smem, int smem_optin,
+                            cudaStream_t st) {
+  static std::atomic<bool> attr{false};
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(dense_head_kernel<NP, BOXES, FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  dense_head_kernel<NP, BOXES, FILL><<<grid, kDenseThreads, smem, st>>>(p, kp, tmap);
+  return cudaGetLastError();
 }
 
 cudaError_t dense_launch(const DenseParams& p, const KParams& kp, const CUtensorMap& tmap, int grid, int smem, int smem_optin,
                          cudaStream_t st) {
-  static std::atomic<bool> attr{false};
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(dense_head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_head_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
-  if (p.n_pad == 16) dense_head_kernel<16><<<grid, kDM, smem, st>>>(p, kp, tmap);
-  else dense_head_kernel<32><<<grid, kDM, smem, st>>>(p, kp, tmap);
-  return cudaGetLastError();
+  const int boxes = p.n_in / 32;
+#define B2S_DENSE_CASE(NPV, BX)                                                                          \
+  if (p.n_pad == NPV && boxes == BX)                                                                   \
+    return p.any_fill ? dense_go<NPV, BX, true>(p, kp, tmap, grid, smem, smem_optin, st)                \
+                      : dense_go<NPV, BX, false>(p, kp, tmap, grid, smem, smem_optin, st);
+  B2S_DENSE_CASE(16, 1) B2S_DENSE_CASE(16, 2) B2S_DENSE_CASE(16, 3) B2S_DENSE_CASE(16, 4)
+  B2S_DENSE_CASE(32, 1) B2S_DENSE_CASE(32, 2) B2S_DENSE_CASE(32, 3) B2S_DENSE_CASE(32, 4)
+#undef B2S_DENSE_CASE
+  return cudaErrorInvalidValue;
 }
 
 int dense_smem_bytes(int n_in, int n_pad) {
   const int boxes = n_in / 32;
-  return 3 * boxes * kDM * 128 + 2 * boxes * n_pad * 128 + 2048;
+  return (int)(kOffB + 3u * (uint32_t)boxes * (uint32_t)n_pad * 128u) + 512 + kBadDepth * 512 + 256 + 1024;
+}
+
+int dense_tmem_cols(int n_in, int n_pad) {  // two accumulator sets of (boxes + 1) x n_pad columns, as a power of two >= 32
+  const int need = 2 * (n_in / 32 + 1) * n_pad;
+  int cols = 32;
+  while (cols < need) cols *= 2;
+  return cols;
 }
 
 }  // namespace b2s

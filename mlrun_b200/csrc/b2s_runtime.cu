@@ -117,13 +117,16 @@ struct Slot {  // one in-flight batch of the coalescing ring
   std::chrono::steady_clock::time_point first_submit;
   b2s_stats stats{};
   int waiters = 0;      // tickets issued on this batch not yet collected
+  bool wanted = false;  // a caller is blocked in b2s_wait on this (still open) batch: it leaves as soon as the dispatcher is free
   int err = 0;          // b2s_status of the batch (a failed copy / launch): every ticket of the batch gets it
   std::string err_msg;
 };
 
 // Ensemble-merge communicator: ONE device allocation per rank, exported over CUDA IPC and mapped by every peer:
-//   [flags: 64 x uint32][CTA counter][pad to 256 B][merged rows, parity 0][merged rows, parity 1]
+//   [flags: 64 x uint32][CTA counter][timeout word][pad to kCommHeader = 512 B][merged rows, parity 0][merged rows, parity 1]
+// (round 2's first version started the rows at byte 256 = word 64: the first vote of a step overwrote the counter)
 // merged rows = world x max_rows x out_cols 4-byte words; step e (epoch, 1-based) lands in parity e & 1.
+constexpr size_t kCommHeader = 512;
 struct b2s_comm_s {
   int rank = 0, world = 1, out_cols = 1;
   int64_t max_rows = 0;
@@ -133,7 +136,7 @@ struct b2s_comm_s {
   size_t bytes = 0;
   bool connected = false;
   size_t buf_bytes() const { return (size_t)world * max_rows * out_cols * 4; }
-  char* buf(int r, uint32_t e) const { return peer_base[r] + 256 + (size_t)(e & 1u) * buf_bytes(); }
+  char* buf(int r, uint32_t e) const { return peer_base[r] + kCommHeader + (size_t)(e & 1u) * buf_bytes(); }
   uint32_t* flags(int r) const { return reinterpret_cast<uint32_t*>(peer_base[r]); }
   uint32_t* counter() const { return reinterpret_cast<uint32_t*>(base) + 64; }
 };
@@ -1372,9 +1375,9 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
         }
       }
     }
-    // ---- dense head (tcgen05): linear scorers with more than 8 scores in total over plain numeric columns.  Weights are
-    // split like the inputs will be: w (float32) = wh + wl with wh = tf32(w), wl = tf32(w - wh); W^T rows padded to 16 / 32
-    std::vector<float> dense_wh, dense_wl;
+    // ---- dense head (tcgen05): linear scorers with more than 8 scores in total over plain numeric columns.  The float64
+    // coefficients become three tf32 terms wh + wm + wl (11 significant bits each, 33 in total); W^T rows padded to 16 / 32
+    std::vector<float> dense_wh, dense_wm, dense_wl;
     int dense_pad = 0;
     {
       const char* denv = getenv("B2S_DENSE");  // 1 (default) | 0: stay on the fp64 row kernels (A/B runs)
@@ -1386,27 +1389,32 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
           !any_map && n_cat_cols == 0 && all_copied && (n_in % 32) == 0 && n_in <= kDenseMaxIn) {
         dense_pad = total_scores <= 16 ? 16 : 32;
         dense_wh.assign((size_t)dense_pad * n_in, 0.0f);
+        dense_wm.assign((size_t)dense_pad * n_in, 0.0f);
         dense_wl.assign((size_t)dense_pad * n_in, 0.0f);
-        auto tf32 = [](float x) {
+        auto tf32 = [](double x) {  // the leading 11 significant bits of the float32 nearest to x
+          float f = (float)x;
+          if (!std::isfinite(f)) return f;
           uint32_t b;
-          memcpy(&b, &x, 4);
+          memcpy(&b, &f, 4);
           b &= 0xffffe000u;
-          float y;
-          memcpy(&y, &b, 4);
-          return y;
+          memcpy(&f, &b, 4);
+          return f;
         };
         for (int kk = 0; kk < total_scores; ++kk)
           for (int c = 0; c < n_in; ++c) {
-            const float w = (float)wnum[(size_t)c * NS + kk];
+            const double w = wnum[(size_t)c * NS + kk];
             const float hi = tf32(w);
+            const double r1 = w - (double)hi;  // exact in float64
+            const float mid = tf32(r1);
             dense_wh[(size_t)kk * n_in + c] = hi;
-            dense_wl[(size_t)kk * n_in + c] = tf32(w - hi);
+            dense_wm[(size_t)kk * n_in + c] = mid;
+            dense_wl[(size_t)kk * n_in + c] = tf32(r1 - (double)mid);
           }
       }
     }
     // ---- upload one blob
     BlobBuilder bb;
-    const size_t o_dwh = bb.add(dense_wh), o_dwl = bb.add(dense_wl);
+    const size_t o_dwh = bb.add(dense_wh), o_dwm = bb.add(dense_wm), o_dwl = bb.add(dense_wl);
     const size_t o_fill = bb.add(p->fill), o_flags = bb.add(flags), o_mapoff = bb.add(map_off), o_maps = bb.add(maps),
                  o_osrc = bb.add(p->out_src), o_okind = bb.add(p->out_kind), o_oarg = bb.add(p->out_arg),
                  o_catoff = bb.add(cat_off), o_catval = bb.add(cat_val), o_wnum = bb.add(wnum), o_wcat = bb.add(wcat),
@@ -1461,12 +1469,14 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       DenseParams& d = p->dense;
       memset(&d, 0, sizeof(d));
       d.wh = (const float*)(B + o_dwh);
+      d.wm = (const float*)(B + o_dwm);
       d.wl = (const float*)(B + o_dwl);
       d.fill = k.fill;
       d.bias = k.bias;
       d.n_in = n_in;
       d.n_scores = total_scores;
       d.n_pad = dense_pad;
+      d.tmem_cols = dense_tmem_cols(n_in, dense_pad);
       d.any_fill = any_fill ? 1 : 0;
       for (int kk = 0; kk < 32; ++kk) {
         d.biasf[kk] = kk < total_scores ? (float)bias[kk] : 0.0f;
@@ -1490,8 +1500,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       }
       p->dense_smem = dense_smem_bytes(n_in, dense_pad);
       if (p->dense_smem <= (int)G.prop.sharedMemPerBlockOptin) {
-        const int resident = std::max(1, std::min(4, (int)G.prop.sharedMemPerMultiprocessor / (p->dense_smem + 1024)));
-        p->dense_grid = G.prop.multiProcessorCount * resident;
+        p->dense_grid = G.prop.multiProcessorCount;  // persistent: one CTA per SM (its shared memory and TMEM see to that)
         p->dense_ok = true;
       }
     }
@@ -1799,7 +1808,7 @@ extern "C" const char* b2s_plan_kernel(b2s_plan_t p) {
   static thread_local char buf[200];
   int lm = rt_load_mode();
   if (lm == 2 && !(p->rt_NCH >= 8 && p->n_in == p->rt_NCH * 4 && tensor_map_encoder())) lm = 1;
-  if (p->dense_ok) snprintf(buf, sizeof(buf), "dense_head_kernel<N=%d> (tcgen05.mma kind::tf32 x3, TMEM accumulator; %d scores over %d columns)", p->dense.n_pad, p->dense.n_scores, p->dense.n_in);
+  if (p->dense_ok) snprintf(buf, sizeof(buf), "dense_head_kernel<N=%d> (tcgen05.mma kind::tf32, exact 3-term splits, TMEM accumulators per 32-column box; %d scores over %d columns)", p->dense.n_pad, p->dense.n_scores, p->dense.n_in);
   else if (p->t3_ok) snprintf(buf, sizeof(buf), "t3_prep_kernel + trees3_kernel<D=%d,%s> + t3_vote_kernel (%d parts resident in shared memory, %d walking warps%s)", p->t3_D, p->t3_miss ? "NaN routing" : "floats", p->t3_parts, p->t3.warps, p->t3_top ? ", top levels in the constant bank" : "");
   else if (p->t2_ok) snprintf(buf, sizeof(buf), "trees_model_kernel<%d> + vote_kernel (models resident in shared memory)", p->t2_NS);
   else if (p->rt_ok) snprintf(buf, sizeof(buf), "rowthread_kernel<NCH=%d,NS=%d,TPR=%d,RPT=%d,%s>", p->rt_NCH, p->rt_NS, p->rt_TPR, lm == 2 ? p->rt_RPT : 1, lm == 2 ? "TMA tensor-map loads" : (lm == 1 ? "TMA bulk loads" : "cp.async loads"));
@@ -2243,9 +2252,9 @@ static void dispatcher_main(b2s_plan_s* p) {
       if (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0) {
         // The open batch leaves when its oldest row has waited max_wait_us (0: at once -- this thread is free, so batches
         // form while the previous one runs) -- but only while another slot is free to take the submits that follow: the
-        // last free slot keeps collecting rows (until it is full, a waiter asks for it, or b2s_flush), so that a caller
+        // last free slot keeps collecting rows (until it is full, a caller blocks on it, or b2s_flush), so that a caller
         // that submits many tickets before it collects any fills a batch instead of exhausting the ring.
-        int spare = 0;
+        int spare = p->slots[p->open_slot].wanted ? 1 : 0;  // a caller blocked on this batch: holding it back gains nothing
         for (int i = 0; i < (int)p->slots.size(); ++i)
           spare += (i != p->open_slot && p->slots[i].state == 0 && p->slots[i].rows == 0 && p->slots[i].waiters == 0) ? 1 : 0;
         if (spare == 0) {
@@ -2483,10 +2492,12 @@ extern "C" int b2s_wait(b2s_plan_t p, uint64_t ticket, void* out, int64_t out_by
     auto it = p->batch_slot.find(batch);
     if (it == p->batch_slot.end()) return fail(B2S_ERR_INVALID, "unknown ticket");
     Slot& s = p->slots[it->second];
-    if (s.state == 0 && p->open_slot == it->second && s.rows > 0) {  // the ticket's batch is still collecting rows: send it
-      s.state = 1;
-      p->sealed.push_back(p->open_slot);
-      p->open_slot = -1;
+    // The ticket's batch is still collecting rows: ask for it.  It is NOT sealed here -- while the dispatcher is busy with
+    // the previous batch the rows of other callers keep joining (that is what coalesces concurrent request threads; sealing
+    // at once made every caller's row a batch of its own: 28 K events/s for 8 producers, measured r2h); an idle dispatcher
+    // takes it immediately.
+    if (s.state == 0 && p->open_slot == it->second && s.rows > 0 && !s.wanted) {
+      s.wanted = true;
       p->cv_work.notify_one();
     }
     // a short spin before sleeping: two condition-variable hand-offs (producer -> dispatcher -> waiter) cost more than a
@@ -2522,6 +2533,7 @@ extern "C" int b2s_wait(b2s_plan_t p, uint64_t ticket, void* out, int64_t out_by
       p->batch_slot.erase(it);
       s.rows = 0;
       s.state = 0;
+      s.wanted = false;
       s.err = 0;
       s.err_msg.clear();
       p->cv_free.notify_all();
@@ -2696,7 +2708,7 @@ extern "C" int b2s_comm_create(int32_t rank, int32_t world, int64_t max_rows_per
     c->world = world;
     c->out_cols = out_cols;
     c->max_rows = (max_rows_per_rank + 3) / 4 * 4;  // row blocks start 16-byte aligned
-    c->bytes = 256 + 2 * c->buf_bytes();
+    c->bytes = kCommHeader + 2 * c->buf_bytes();
     CUDA_TRY(cudaSetDevice(G.device));
     CUDA_TRY(cudaMalloc(&c->base, c->bytes));
     CUDA_TRY(cudaMemset(c->base, 0, 512 < c->bytes ? 512 : c->bytes));
@@ -2761,7 +2773,9 @@ extern "C" int b2s_comm_wait(b2s_comm_t c, void* stream, const void** d_merged, 
     const uint32_t e = c->epoch;
     if (e == 0) return fail(B2S_ERR_STATE, "no step has been launched on this communicator");
     uint32_t* timeout_flag = reinterpret_cast<uint32_t*>(c->base) + 65;
-    merge_wait_kernel<<<1, 32, 0, st>>>(c->flags(c->rank), c->world, e, timeout_flag, 2000000000ll);
+    // how long a rank may lag behind before the step is declared dead (B2S_COMM_TIMEOUT_MS, default 10 s)
+    static const long long timeout_ns = (getenv("B2S_COMM_TIMEOUT_MS") ? atoll(getenv("B2S_COMM_TIMEOUT_MS")) : 10000ll) * 1000000ll;
+    merge_wait_kernel<<<1, 32, 0, st>>>(c->flags(c->rank), c->world, e, timeout_flag, timeout_ns);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(B2S_ERR_CUDA, "merge wait launch failed: %s", cudaGetErrorString(err));
     G.launches.fetch_add(1, std::memory_order_relaxed);
@@ -2778,7 +2792,7 @@ extern "C" int b2s_comm_check(b2s_comm_t c) {
     if (!c) return fail(B2S_ERR_INVALID, "null communicator");
     uint32_t v = 0;
     CUDA_TRY(cudaMemcpy(&v, reinterpret_cast<uint32_t*>(c->base) + 65, 4, cudaMemcpyDeviceToHost));
-    if (v) return fail(B2S_ERR_TIMEOUT, "ensemble-merge: rank %u did not signal its shard within 2 s", v - 1);
+    if (v) return fail(B2S_ERR_TIMEOUT, "ensemble-merge: rank %u did not signal its shard in time (B2S_COMM_TIMEOUT_MS)", v - 1);
     return B2S_OK;
   } catch (const std::exception& e) {
     return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
