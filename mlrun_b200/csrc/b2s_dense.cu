@@ -29,6 +29,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "b2s_rowthread.cuh"  // mbarrier / TMA helpers, KParams, epilogue functions
@@ -61,13 +62,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
 
 constexpr int kRawStages = 4;                  // TMA landing boxes of 16 KB
-constexpr int kOutStages = 2;                  // operand stages of 3 x 16 KB (xh | xm | xl)
+constexpr uint32_t kOutRing = 6;               // operand ring: 6 boxes of 16 KB = 3 stages of (xh | xm) or 2 of (xh | xm | xl)
 constexpr int kSplitWarps = 8, kEpiWarps = 4;  // + producer warp + MMA warp
 constexpr int kDenseThreads = (2 + kEpiWarps + kSplitWarps) * 32;
 constexpr uint32_t kBoxBytes = kDM * 128u;     // one box: 128 rows x 32 floats
-constexpr uint32_t kOutBytes = 3u * kBoxBytes;
-constexpr uint32_t kOffOut = kRawStages * kBoxBytes, kOffB = kOffOut + kOutStages * kOutBytes;
-constexpr int kBadDepth = 4;                   // flag buffers: the split may run this many tiles ahead of the epilogue
+constexpr uint32_t kOffOut = kRawStages * kBoxBytes, kOffB = kOffOut + kOutRing * kBoxBytes;
+constexpr int kBadDepth = 8;                   // flag buffers: the split of tile t + 8 cannot start before the epilogue of tile t is over
+                                               // (3 operand stages ahead of the MMAs, which are 2 accumulator sets ahead of the epilogue)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -82,25 +83,32 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  "=r"(r[c0 + 12]), "=r"(r[c0 + 13]), "=r"(r[c0 + 14]), "=r"(r[c0 + 15])                                        \
                : "r"(addr))
 
-template <int NP, int BOXES, bool FILL>  // padded score count 16 | 32; input columns / 32; an Imputer is folded in
+// NP: padded score count 16 | 32; BOXES: input columns / 32; FILL: an Imputer is folded in; XT: tf32 terms per input (3: exact,
+// 2: xh + round-to-nearest residual, |error| <= 2^-23 |x|)
+template <int NP, int BOXES, bool FILL, int XT>
 __global__ void __launch_bounds__(kDenseThreads, 1) dense_head_kernel(const __grid_constant__ DenseParams p, const __grid_constant__ KParams kp,
                                                                       const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) unsigned char smem_dense[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int K = BOXES * 32;
-  constexpr uint32_t kBTerm = (uint32_t)BOXES * NP * 128u;  // one weight term: BOXES x (NP rows x 128 B)
-  constexpr uint32_t kOffMisc = kOffB + 3u * kBTerm;
+  constexpr int kOutStages = (int)kOutRing / XT;
+  constexpr uint32_t kOutBytes = (uint32_t)XT * kBoxBytes;
+  constexpr uint32_t kBBox = 3u * NP * 128u;  // the weights of one box: rows [wh (NP) | wm (NP) | wl (NP)] x 128 B
+  constexpr uint32_t kOffMisc = kOffB + (uint32_t)BOXES * kBBox;
+  // accumulator groups: [main | small 1 | small 2] x NP columns each; one per box while two sets of them fit the 512 columns
+  constexpr int G = NP == 16 ? BOXES : (BOXES < 2 ? BOXES : 2);
+  constexpr int BPG = (BOXES + G - 1) / G;  // boxes per group
   float* s_fill = reinterpret_cast<float*>(smem_dense + kOffMisc);                       // [K]
   int* s_bad = reinterpret_cast<int*>(smem_dense + kOffMisc + 512);                      // [kBadDepth][128]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_dense + kOffMisc + 512 + kBadDepth * 512);
   uint64_t* raw_full = s_bar;                   // [4]  TMA transaction bytes
   uint64_t* raw_empty = s_bar + 4;              // [4]  8 split warps
-  uint64_t* out_full = s_bar + 8;               // [2]  8 split warps
-  uint64_t* out_empty = s_bar + 10;             // [2]  tcgen05.commit
-  uint64_t* acc_full = s_bar + 12;              // [2]  tcgen05.commit
-  uint64_t* acc_empty = s_bar + 14;             // [2]  128 epilogue threads
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
-  constexpr uint32_t kAccCols = (uint32_t)(BOXES + 1) * NP;  // one accumulator set
+  uint64_t* out_full = s_bar + 8;               // [3]  8 split warps
+  uint64_t* out_empty = s_bar + 11;             // [3]  tcgen05.commit
+  uint64_t* acc_full = s_bar + 14;              // [2]  tcgen05.commit
+  uint64_t* acc_empty = s_bar + 16;             // [2]  128 epilogue threads
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 18);
+  constexpr uint32_t kAccCols = (uint32_t)G * 3u * NP;  // one accumulator set
 
   // ---- one-time setup: TMEM columns, barriers, the weights in the UMMA layout (rows = scores, K-major, 128-byte swizzle)
   if (warp == 1) {
@@ -113,9 +121,11 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_head_kernel(const __gr
       mbar_init(&raw_full[i], 1);
       mbar_init(&raw_empty[i], kSplitWarps);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&out_full[i], kSplitWarps);
       mbar_init(&out_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], kEpiWarps * 32);
     }
@@ -124,10 +134,10 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_head_kernel(const __gr
   for (int i = tid; i < NP * K; i += kDenseThreads) {
     const int n = i / K, k = i - n * K;
     const int b = k >> 5, c = (k & 31) >> 2, e = k & 3;
-    const uint32_t off = kOffB + (uint32_t)b * NP * 128u + (uint32_t)n * 128u + (uint32_t)((c ^ (n & 7)) << 4) + (uint32_t)e * 4u;
-    *reinterpret_cast<float*>(smem_dense + off) = p.wh[i];
-    *reinterpret_cast<float*>(smem_dense + off + kBTerm) = p.wm[i];
-    *reinterpret_cast<float*>(smem_dense + off + 2u * kBTerm) = p.wl[i];
+    const uint32_t off = kOffB + (uint32_t)b * kBBox + (uint32_t)n * 128u + (uint32_t)((c ^ (n & 7)) << 4) + (uint32_t)e * 4u;
+    *reinterpret_cast<float*>(smem_dense + off) = p.wh[i];  // NP * 128 is a multiple of 1024: the swizzle phase of a row is n & 7 in every term
+    *reinterpret_cast<float*>(smem_dense + off + NP * 128u) = p.wm[i];
+    *reinterpret_cast<float*>(smem_dense + off + 2u * NP * 128u) = p.wl[i];
   }
   for (int i = tid; i < K; i += kDenseThreads) s_fill[i] = p.fill[i];
   for (int i = tid; i < kBadDepth * kDM; i += kDenseThreads) s_bad[i] = 0;
@@ -154,29 +164,27 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_head_kernel(const __gr
   } else if (warp == 1) {
     // =============================================================================================== tensor-core feeder
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(NP);
+      const uint32_t idesc3 = umma_idesc(3 * NP), idesc2 = umma_idesc(2 * NP), idesc1 = umma_idesc(NP);
       int q = 0, i = 0;
       for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
         const int a = i & 1;
         if (i >= 2) mbar_wait(&acc_empty[a], (uint32_t)((i >> 1) - 1) & 1u);  // the epilogue of tile i - 2 has read this set
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_set = tmem + (uint32_t)a * kAccCols, d_small = d_set + (uint32_t)BOXES * NP;
+        const uint32_t d_set = tmem + (uint32_t)a * kAccCols;
         for (int b = 0; b < BOXES; ++b, ++q) {
           const int os = q % kOutStages;
           mbar_wait(&out_full[os], (uint32_t)(q / kOutStages) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t xh = sbase + kOffOut + (uint32_t)os * kOutBytes, xm = xh + kBoxBytes, xl = xm + kBoxBytes;
-          const uint32_t wh = sbase + kOffB + (uint32_t)b * NP * 128u, wm = wh + kBTerm, wl = wm + kBTerm;
-          const uint32_t d_main = d_set + (uint32_t)b * NP;
+          const uint32_t wb = sbase + kOffB + (uint32_t)b * kBBox;       // rows [wh | wm | wl]
+          const uint32_t d_main = d_set + (uint32_t)(b / BPG) * 3u * NP;  // this box's group: [main | small 1 | small 2]
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {  // 8 tf32 = 32 bytes per instruction inside the 128-byte swizzle atom
             const uint32_t ko = (uint32_t)kk * 32u;
-            umma_tf32(d_main, umma_desc(xh + ko), umma_desc(wh + ko), idesc, kk > 0);
-            umma_tf32(d_small, umma_desc(xh + ko), umma_desc(wm + ko), idesc, (b | kk) != 0);
-            umma_tf32(d_small, umma_desc(xm + ko), umma_desc(wh + ko), idesc, true);
-            umma_tf32(d_small, umma_desc(xm + ko), umma_desc(wm + ko), idesc, true);
-            umma_tf32(d_small, umma_desc(xh + ko), umma_desc(wl + ko), idesc, true);
-            umma_tf32(d_small, umma_desc(xl + ko), umma_desc(wh + ko), idesc, true);
+            // one read of the A operand per input term: the weight terms are stacked along N
+            umma_tf32(d_main, umma_desc(xh + ko), umma_desc(wb + ko), idesc3, (b % BPG) != 0 || kk > 0);  // xh.wh | xh.wm | xh.wl
+            umma_tf32(d_main + NP, umma_desc(xm + ko), umma_desc(wb + ko), idesc2, true);                 //         xm.wh | xm.wm
+            if (XT == 3) umma_tf32(d_main + NP, umma_desc(xl + ko), umma_desc(wb + ko), idesc1, true);    //         xl.wh
           }
           umma_commit(&out_empty[os]);  // arrives when the MMAs above have read the stage
         }
@@ -198,18 +206,24 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_head_kernel(const __gr
       const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * kAccCols;
       float sc[NP];
 #pragma unroll
-      for (int g = 0; g < NP; g += 16) {
-        uint32_t r[(BOXES + 1) * 16];
+      for (int c0 = 0; c0 < NP; c0 += 16) {
+        float mainv[16], smallv[16];
 #pragma unroll
-        for (int j = 0; j <= BOXES; ++j) B2S_TMEM_LD16(r, j * 16, taddr + (uint32_t)(j * NP + g));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int g = 0; g < G; ++g) {
+          uint32_t r[48];
+          B2S_TMEM_LD16(r, 0, taddr + (uint32_t)(g * 3 * NP + c0));
+          B2S_TMEM_LD16(r, 16, taddr + (uint32_t)(g * 3 * NP + NP + c0));
+          B2S_TMEM_LD16(r, 32, taddr + (uint32_t)(g * 3 * NP + 2 * NP + c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          float v = __uint_as_float(r[k]);  // boxes in column order, then the small terms
-#pragma unroll
-          for (int j = 1; j <= BOXES; ++j) v += __uint_as_float(r[j * 16 + k]);
-          sc[g + k] = v;
+          for (int k = 0; k < 16; ++k) {  // groups in column order; the small terms (2^-11 of the large) on their own
+            const float sm = __uint_as_float(r[16 + k]) + __uint_as_float(r[32 + k]);
+            mainv[k] = g == 0 ? __uint_as_float(r[k]) : mainv[k] + __uint_as_float(r[k]);
+            smallv[k] = g == 0 ? sm : smallv[k] + sm;
+          }
         }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sc[c0 + k] = mainv[k] + smallv[k];
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&acc_empty[a]);  // the accumulators are in registers: the MMAs of tile i + 2 may overwrite the set
@@ -293,12 +307,17 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_head_kernel(const __gr
             probe = fmaf(x, 0.f, probe);              // NaN as soon as one value is NaN or +-Inf
             h[e] = tf32_hi(x);
             const float r1 = x - __uint_as_float(h[e]);  // exact: the low 13 bits of x
-            m[e] = tf32_hi(r1);
-            l[e] = __float_as_uint(r1 - __uint_as_float(m[e]));  // exact: at most 2 significant bits are left
+            if (XT == 3) {
+              m[e] = tf32_hi(r1);
+              l[e] = __float_as_uint(r1 - __uint_as_float(m[e]));  // exact: at most 2 significant bits are left
+            } else {
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(m[e]) : "f"(r1));  // nearest tf32: x = xh + xm up to 2^-23 |x|
+              l[e] = 0u;
+            }
           }
           *reinterpret_cast<uint4*>(dst + j * 4096) = make_uint4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<uint4*>(dst + j * 4096 + kBoxBytes) = make_uint4(m[0], m[1], m[2], m[3]);
-          *reinterpret_cast<uint4*>(dst + j * 4096 + 2 * kBoxBytes) = make_uint4(l[0], l[1], l[2], l[3]);
+          if (XT == 3) *reinterpret_cast<uint4*>(dst + j * 4096 + 2 * kBoxBytes) = make_uint4(l[0], l[1], l[2], l[3]);
           // a non-finite value makes its own row's scores NaN (rows are independent in the product) and flags the row
           if (probe != probe) atomicOr(s_bad + (i & (kBadDepth - 1)) * kDM + lane + 32 * j, 1);
         }
@@ -316,16 +335,16 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_head_kernel(const __gr
   merge_signal(kp.sig);
 }
 
-template <int NP, int BOXES, bool FILL>
+template <int NP, int BOXES, bool FILL, int XT>
 static cudaError_t dense_go(const DenseParams& p, const KParams& kp, const CUtensorMap& tmap, int grid, int smem, int smem_optin,
                             cudaStream_t st) {
   static std::atomic<bool> attr{false};
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(dense_head_kernel<NP, BOXES, FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    cudaError_t e = cudaFuncSetAttribute(dense_head_kernel<NP, BOXES, FILL, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  dense_head_kernel<NP, BOXES, FILL><<<grid, kDenseThreads, smem, st>>>(p, kp, tmap);
+  dense_head_kernel<NP, BOXES, FILL, XT><<<grid, kDenseThreads, smem, st>>>(p, kp, tmap);
   return cudaGetLastError();
 }
 
@@ -334,8 +353,10 @@ cudaError_t dense_launch(const DenseParams& p, const KParams& kp, const CUtensor
   const int boxes = p.n_in / 32;
 #define B2S_DENSE_CASE(NPV, BX)                                                                          \
   if (p.n_pad == NPV && boxes == BX)                                                                   \
-    return p.any_fill ? dense_go<NPV, BX, true>(p, kp, tmap, grid, smem, smem_optin, st)                \
-                      : dense_go<NPV, BX, false>(p, kp, tmap, grid, smem, smem_optin, st);
+    return p.exact ? (p.any_fill ? dense_go<NPV, BX, true, 3>(p, kp, tmap, grid, smem, smem_optin, st)   \
+                                 : dense_go<NPV, BX, false, 3>(p, kp, tmap, grid, smem, smem_optin, st)) \
+                   : (p.any_fill ? dense_go<NPV, BX, true, 2>(p, kp, tmap, grid, smem, smem_optin, st)   \
+                                 : dense_go<NPV, BX, false, 2>(p, kp, tmap, grid, smem, smem_optin, st));
   B2S_DENSE_CASE(16, 1) B2S_DENSE_CASE(16, 2) B2S_DENSE_CASE(16, 3) B2S_DENSE_CASE(16, 4)
   B2S_DENSE_CASE(32, 1) B2S_DENSE_CASE(32, 2) B2S_DENSE_CASE(32, 3) B2S_DENSE_CASE(32, 4)
 #undef B2S_DENSE_CASE
@@ -347,8 +368,9 @@ int dense_smem_bytes(int n_in, int n_pad) {
   return (int)(kOffB + 3u * (uint32_t)boxes * (uint32_t)n_pad * 128u) + 512 + kBadDepth * 512 + 256 + 1024;
 }
 
-int dense_tmem_cols(int n_in, int n_pad) {  // two accumulator sets of (boxes + 1) x n_pad columns, as a power of two >= 32
-  const int need = 2 * (n_in / 32 + 1) * n_pad;
+int dense_tmem_cols(int n_in, int n_pad) {  // two sets of G groups x 3 x n_pad columns, as a power of two >= 32
+  const int boxes = n_in / 32, groups = n_pad == 16 ? boxes : std::min(boxes, 2);
+  const int need = 2 * groups * 3 * n_pad;
   int cols = 32;
   while (cols < need) cols *= 2;
   return cols;

@@ -18,6 +18,7 @@ struct DenseParams {
   const double* bias;  // [n_scores] intercepts
   int32_t n_in, n_scores, n_pad, any_fill;
   int32_t tmem_cols;   // TMEM columns the CTA allocates (dense_tmem_cols)
+  int32_t exact;       // 1: inputs split into three tf32 terms (exact); 0: two terms, the second rounded to nearest (2^-23 |x|)
   // epilogue: the common shapes run in float32 registers (fp64 conversions and local-memory arrays are what the generic
   // epilogue spends its time on); everything else takes the generic link + vote functions
   int32_t epi;         // 0 generic | 1 every model one identity score, all emitted | 2 the same under a mean vote | 3 one argmax classifier

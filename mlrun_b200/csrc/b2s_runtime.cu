@@ -117,6 +117,7 @@ struct Slot {  // one in-flight batch of the coalescing ring
   std::chrono::steady_clock::time_point first_submit;
   b2s_stats stats{};
   int waiters = 0;      // tickets issued on this batch not yet collected
+  std::shared_ptr<std::condition_variable> done_cv;  // the batch's own waiters (one wake-up per batch, not a herd over all tickets)
   bool wanted = false;  // a caller is blocked in b2s_wait on this (still open) batch: it leaves as soon as the dispatcher is free
   int err = 0;          // b2s_status of the batch (a failed copy / launch): every ticket of the batch gets it
   std::string err_msg;
@@ -1008,7 +1009,9 @@ static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
           }
         so2 += m.n_scores;
       }
-      hp.cost = 2.0 + n_in * n_lin_cols / 32.0;
+      // measured (r2i, router of 4 linear + 4 tree models over 64 columns): the linear part's tiles cost about a fifth of a
+      // 100-tree part's; erring high only hands it a few CTAs more
+      hp.cost = 8.0 + n_in * (n_lin_cols + 4) / 16.0;
       parts.push_back(std::move(hp));
     }
   }
@@ -1108,6 +1111,18 @@ static int t3_build(b2s_plan_s* p, const KParams& k, bool any_fill) {
   t.sm_part = take(2 * (size_t)t.part_words * 8, 16);
   t.sm_xt = take(2 * (size_t)xt_words * 4, 128);
   t.sm_bar = take(64, 16);
+  if (n_lin_cols > 0) {
+    // feature slices of the linear part: as many walking warps as fit -- either behind the weights, in the room the tree
+    // parts use for their tables, or (small tree tables) in the per-warp partial-sum buffers
+    const size_t w_end = align_up(lin_bytes, 16);
+    const size_t per_slice = (size_t)n_lin_cols * TR * 8;
+    const int cap_a = (size_t)t.sm_part > w_end ? (int)(((size_t)t.sm_part - w_end) / (2 * per_slice)) : 0;
+    const int cap_b = std::max(W, kT3MaxLin) / n_lin_cols;
+    const bool alias = cap_a >= cap_b;
+    t.lin_slices = std::max(1, std::min({W, n_in, alias ? cap_a : cap_b}));
+    t.lin_part_words = alias ? t.lin_slices * n_lin_cols * TR : t.part_words;
+    t.sm_lin_part = alias ? (int32_t)w_end : t.sm_part;
+  }
   if (off > (size_t)smem_cap) {  // cannot happen with the budget above; stay on the safe side
     cudaFree(p->d_t3_blob);
     p->d_t3_blob = nullptr;
@@ -1477,6 +1492,7 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
       d.n_scores = total_scores;
       d.n_pad = dense_pad;
       d.tmem_cols = dense_tmem_cols(n_in, dense_pad);
+      d.exact = (getenv("B2S_DENSE_EXACT") && atoi(getenv("B2S_DENSE_EXACT")) != 0) ? 1 : 0;
       d.any_fill = any_fill ? 1 : 0;
       for (int kk = 0; kk < 32; ++kk) {
         d.biasf[kk] = kk < total_scores ? (float)bias[kk] : 0.0f;
@@ -1808,7 +1824,7 @@ extern "C" const char* b2s_plan_kernel(b2s_plan_t p) {
   static thread_local char buf[200];
   int lm = rt_load_mode();
   if (lm == 2 && !(p->rt_NCH >= 8 && p->n_in == p->rt_NCH * 4 && tensor_map_encoder())) lm = 1;
-  if (p->dense_ok) snprintf(buf, sizeof(buf), "dense_head_kernel<N=%d> (tcgen05.mma kind::tf32, exact 3-term splits, TMEM accumulators per 32-column box; %d scores over %d columns)", p->dense.n_pad, p->dense.n_scores, p->dense.n_in);
+  if (p->dense_ok) snprintf(buf, sizeof(buf), "dense_head_kernel<N=%d> (tcgen05.mma kind::tf32, %s, TMEM accumulator groups; %d scores over %d columns)", p->dense.n_pad, p->dense.exact ? "exact 3-term input split" : "2-term input split", p->dense.n_scores, p->dense.n_in);
   else if (p->t3_ok) snprintf(buf, sizeof(buf), "t3_prep_kernel + trees3_kernel<D=%d,%s> + t3_vote_kernel (%d parts resident in shared memory, %d walking warps%s)", p->t3_D, p->t3_miss ? "NaN routing" : "floats", p->t3_parts, p->t3.warps, p->t3_top ? ", top levels in the constant bank" : "");
   else if (p->t2_ok) snprintf(buf, sizeof(buf), "trees_model_kernel<%d> + vote_kernel (models resident in shared memory)", p->t2_NS);
   else if (p->rt_ok) snprintf(buf, sizeof(buf), "rowthread_kernel<NCH=%d,NS=%d,TPR=%d,RPT=%d,%s>", p->rt_NCH, p->rt_NS, p->rt_TPR, lm == 2 ? p->rt_RPT : 1, lm == 2 ? "TMA tensor-map loads" : (lm == 1 ? "TMA bulk loads" : "cp.async loads"));
@@ -2343,7 +2359,7 @@ static void dispatcher_main(b2s_plan_s* p) {
     s.err = err;
     s.err_msg = err_msg;
     s.state = 3;
-    p->cv_done.notify_all();
+    if (s.done_cv) s.done_cv->notify_all();
   }
 }
 
@@ -2371,6 +2387,7 @@ static int ring_start(b2s_plan_s* p) {
   cudaError_t e = cudaSuccess;
   auto ok = [&](cudaError_t r) { return e == cudaSuccess && (e = r) == cudaSuccess; };
   for (auto& s : slots) {
+    s.done_cv = std::make_shared<std::condition_variable>();
     if (!(ok(cudaMallocHost(&s.h_in, (size_t)cap * row_bytes)) && ok(cudaMallocHost(&s.h_out, (size_t)cap * (p->out_cols + 1) * 4)) &&
           ok(cudaMalloc(&s.d_in, (size_t)cap * row_bytes)) && ok(cudaMalloc(&s.d_out, (size_t)cap * p->out_cols * 4)) &&
           ok(cudaMalloc(&s.d_status, (size_t)cap * 4)) && ok(cudaEventCreate(&s.e0)) && ok(cudaEventCreate(&s.e1)) &&
@@ -2511,7 +2528,7 @@ extern "C" int b2s_wait(b2s_plan_t p, uint64_t ticket, void* out, int64_t out_by
       }
     }
     p->spinners.fetch_sub(1, std::memory_order_relaxed);
-    p->cv_done.wait(lk, [&] { return s.state == 3 && s.batch_id == batch; });
+    s.done_cv->wait(lk, [&] { return s.state == 3 && s.batch_id == batch; });
     // the batch is done: whatever this call returns, the ticket is spent and the last one recycles the slot
     int rc = B2S_OK;
     if (s.err) {
@@ -2519,15 +2536,20 @@ extern "C" int b2s_wait(b2s_plan_t p, uint64_t ticket, void* out, int64_t out_by
     } else if (off + n_rows > s.rows) {
       rc = fail(B2S_ERR_INVALID, "ticket range exceeds its batch");
     } else {
+      // the slot cannot be recycled while this ticket is outstanding (waiters > 0): copy without the lock, so that the
+      // tickets of a batch are collected side by side
+      const b2s_stats batch_stats = s.stats;
+      lk.unlock();
       memcpy(out, s.h_out + (size_t)off * p->out_cols * 4, (size_t)n_rows * p->out_cols * 4);
       const int32_t* hs = (const int32_t*)(s.h_out + (size_t)p->ring_cap * p->out_cols * 4) + off;
       if (row_status) memcpy(row_status, hs, (size_t)n_rows * 4);
       if (stats) {
-        *stats = s.stats;
+        *stats = batch_stats;
         int bad = 0;
         for (int64_t r = 0; r < n_rows; ++r) bad += (hs[r] & B2S_ROW_NONFINITE_INPUT) ? 1 : 0;
         stats->nonfinite_rows = bad;
       }
+      lk.lock();
     }
     if (--s.waiters == 0) {  // last collector frees the slot
       p->batch_slot.erase(it);

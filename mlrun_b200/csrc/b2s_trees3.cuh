@@ -87,6 +87,9 @@ struct T3Params {         // trees3_kernel
   int32_t xt_words;              // words of one tile (n_in rounded up to 4, times TR); two tiles are resident
   int32_t part_words;            // doubles of one partial-sum buffer; two are resident
   int32_t sm_leaf, sm_part, sm_xt, sm_bar;  // byte offsets into dynamic shared memory
+  // the linear part: walking warp s < lin_slices takes the feature slice s of every score column; its partial sums live where
+  // the tree parts keep their tables (two buffers of lin_part_words doubles at sm_lin_part)
+  int32_t lin_slices, lin_part_words, sm_lin_part, pad0;
 };
 
 // launchers (b2s_trees3.cu: the kernels are compiled in their own translation unit)
@@ -283,7 +286,8 @@ __device__ __forceinline__ void t3_walk_body(const T3Params& p, const uint2* __r
 
   unsigned char* s_nodes = smem;
   double* s_leaf = reinterpret_cast<double*>(smem + p.sm_leaf);
-  double* s_part = reinterpret_cast<double*>(smem + p.sm_part);  // [2][trees: W x TR | linear part: n_cols x TR]
+  double* s_part = reinterpret_cast<double*>(smem + p.sm_part);  // [2][W x TR] one partial sum per walking warp and row
+  double* s_lin = reinterpret_cast<double*>(smem + p.sm_lin_part);  // [2][lin_slices x n_cols x TR] (the linear part)
   uint32_t* s_xt = reinterpret_cast<uint32_t*>(smem + p.sm_xt);  // [2][n_in][TR] tiles (128-byte aligned)
   uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + p.sm_bar);  // [2] tile landed (TMA transaction bytes)
   uint64_t* s_done = s_full + 2;                                    // [2] every walking warp is through with the tile
@@ -326,13 +330,13 @@ __device__ __forceinline__ void t3_walk_body(const T3Params& p, const uint2* __r
     };
     if (sid == 0)
       for (int k = 0; k < 2 && k < K; ++k) refill(k, k);
-    const int n_sum = is_lin ? 1 : W;  // tree parts: one partial per warp; the linear part: warp s wrote column s
+    const int n_sum = is_lin ? p.lin_slices : W;  // tree parts: one partial per warp; the linear part: one per feature slice
     for (int k = 0; k < K; ++k) {
       const int buf = k & 1;
       const int64_t row0 = ((int64_t)cta + (int64_t)k * part.n_ctas) * TR;
       mbar_wait(&s_done[buf], (uint32_t)(k >> 1) & 1u);
       if (sid == 0 && k + 2 < K) refill(k + 2, buf);
-      const double* sp = s_part + (size_t)buf * p.part_words;
+      const double* sp = is_lin ? s_lin + (size_t)buf * p.lin_part_words : s_part + (size_t)buf * p.part_words;
       for (int sc = 0; sc < ncols; ++sc) {
         // eight partials are requested before their adds (the LSU queue is full of the walkers' loads); warp order is kept
         double sum = 0.0;
@@ -486,37 +490,44 @@ __device__ __forceinline__ void t3_walk_body(const T3Params& p, const uint2* __r
             if (valid[u]) acc[j] = __dadd_rn(acc[j], v);
           }
       }
-    } else if (g < ncols) {
-      // ---- the linear part: warp s computes score column s of the tile's rows, features in order (fp64 products of
-      // float32 inputs are exact; two interleaved chains per row hide the DFMA latency)
-      const double* sw = reinterpret_cast<const double*>(s_nodes) + (size_t)g * p.n_in;
-      const uint32_t* xt = s_xt + (size_t)buf * p.xt_words;
-      double a1[RPT];
-#pragma unroll
-      for (int j = 0; j < RPT; ++j) a1[j] = 0.0;
-      int f = 0;
-      for (; f + 1 < p.n_in; f += 2) {
-        const double w0 = sw[f], w1 = sw[f + 1];
-#pragma unroll
-        for (int j = 0; j < RPT; ++j) {
-          acc[j] = fma(w0, (double)__uint_as_float(xt[(size_t)f * TR + j * 32 + lane]), acc[j]);
-          a1[j] = fma(w1, (double)__uint_as_float(xt[(size_t)(f + 1) * TR + j * 32 + lane]), a1[j]);
-        }
-      }
-      if (f < p.n_in) {
-        const double w0 = sw[f];
-#pragma unroll
-        for (int j = 0; j < RPT; ++j) acc[j] = fma(w0, (double)__uint_as_float(xt[(size_t)f * TR + j * 32 + lane]), acc[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < RPT; ++j) acc[j] += a1[j];
     }
     // the partial-sum buffer of this parity is free once tile k - 2 has been combined (long ago: that is one walk back)
     if (k >= 2) mbar_wait(&s_pfree[buf], (uint32_t)((k - 2) >> 1) & 1u);
-    if (!is_lin || g < ncols) {
+    if (!is_lin) {
       double* sp = s_part + (size_t)buf * p.part_words;
 #pragma unroll
       for (int j = 0; j < RPT; ++j) sp[g * TR + j * 32 + lane] = acc[j];
+    } else if (g < p.lin_slices) {
+      // ---- the linear part: warp s adds the features of slice s into every score column for the tile's rows (fp64 products of
+      // float32 inputs are exact; each value is converted once); the service warps add the slices in order
+      const double* sw = reinterpret_cast<const double*>(s_nodes);
+      const uint32_t* xt = s_xt + (size_t)buf * p.xt_words;
+      const int fps = (p.n_in + p.lin_slices - 1) / p.lin_slices;
+      const int f0 = g * fps, f1 = min(p.n_in, f0 + fps);
+      double a[RPT][kT3MaxLin];
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+#pragma unroll
+        for (int c = 0; c < kT3MaxLin; ++c) a[j][c] = 0.0;
+      for (int f = f0; f < f1; ++f) {
+        double xv[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) xv[j] = (double)__uint_as_float(xt[(size_t)f * TR + j * 32 + lane]);
+#pragma unroll
+        for (int c = 0; c < kT3MaxLin; ++c)
+          if (c < ncols) {
+            const double wv = sw[(size_t)c * p.n_in + f];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) a[j][c] = fma(wv, xv[j], a[j][c]);
+          }
+      }
+      double* sp = s_lin + (size_t)buf * p.lin_part_words;
+#pragma unroll
+      for (int c = 0; c < kT3MaxLin; ++c)
+        if (c < ncols) {
+#pragma unroll
+          for (int j = 0; j < RPT; ++j) sp[((size_t)g * ncols + c) * TR + j * 32 + lane] = a[j][c];
+        }
     }
     __syncwarp();
     if (lane == 0) t3_mbar_arrive(&s_done[buf]);  // release: the stores above are visible to whoever completes the wait

@@ -1,7 +1,7 @@
 set -x
-OUT=${OUT:-r2h}
+export OUT=${OUT:-r2h}
 mkdir -p gpurun_out/${OUT:-r2h}
-(timeout 300 python -m pytest tests/test_gpu_dense.py -q --timeout 100 -s) > gpurun_out/${OUT:-r2h}/pytest_dense.txt 2>&1
+(timeout 300 python -m pytest tests/test_gpu_dense.py tests/test_gpu_trees.py -q --timeout 100 -s) > gpurun_out/${OUT:-r2h}/pytest_dense.txt 2>&1
 tail -15 gpurun_out/${OUT:-r2h}/pytest_dense.txt
 (timeout 900 python -m pytest tests -m gpu -q --timeout 120) > gpurun_out/${OUT:-r2h}/pytest_gpu.txt 2>&1
 tail -25 gpurun_out/${OUT:-r2h}/pytest_gpu.txt
@@ -10,7 +10,7 @@ tail -5 gpurun_out/${OUT:-r2h}/bench_default.err
 python - <<'PY'
 import json
 try:
-    d=json.loads(open('gpurun_out/${OUT:-r2h}/bench_default.json').read().strip().splitlines()[-1])
+    d=json.loads(open('gpurun_out/'+__import__('os').environ.get('OUT','r2h')+'/bench_default.json').read().strip().splitlines()[-1])
     print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['roofline']['frac'], d['e2e']['value'])
     print(d['p50_step_latency_us'])
     for r in d.get('configs',[]): print({k:(round(v,4) if isinstance(v,float) else v) for k,v in r.items() if k in ('workload','batch','ms_per_launch','roofline_frac','e2e_events_per_s','e2e_ms_per_call','error')})

@@ -1,5 +1,6 @@
-"""Dense linear head on the tensor cores (csrc/b2s_dense.cu: tcgen05.mma kind::tf32 x3, TMEM accumulator) vs scikit-learn's
-own predict().  Needs a B200: `-m gpu`.  Scores rtol 1e-5 (+ atol 1e-5); labels exact (see the tie note in the test)."""
+"""Dense linear head on the tensor cores (csrc/b2s_dense.cu: tcgen05.mma kind::tf32 over split operands, TMEM accumulator
+groups) vs scikit-learn's own predict().  Needs a B200: `-m gpu`.  Scores rtol 1e-5 (+ atol 1e-5); labels exact (see the tie
+note in the test)."""
 
 import numpy as np
 import pytest
@@ -50,6 +51,24 @@ def test_twelve_regressors_scores(n_rows):
     assert not status.any()
     voted = ColumnProgram(names(64)).build_plan([packing.pack_model(m) for m in models], vote=(nat.VOTE_MEAN, [1 / 12] * 12)).run(X)
     np.testing.assert_allclose(voted[:, 0], obatch.mean_vote(want, [1 / 12] * 12), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("exact", [0, 1])
+def test_error_against_float64_at_unit_scale(exact, monkeypatch):
+    """what the splits buy: inputs as xh + xm (second term rounded to nearest: 2^-23 |x| is dropped) or, B2S_DENSE_EXACT=1,
+    as three exact terms; weights always as three terms of the float64 coefficient; one accumulator group per 32-column box.
+    Unit-scale data, 128 columns, 16 scores of magnitude ~10: the error stays a few float32 ulp of the partial sums"""
+    monkeypatch.setenv("B2S_DENSE_EXACT", str(exact))
+    models = linear_models(16, 128, seed=21)
+    X = np.random.default_rng(22).normal(size=(40000, 128)).astype(np.float32)
+    plan = ColumnProgram(names(128)).build_plan([packing.pack_model(m) for m in models])
+    assert "dense_head_kernel<N=16>" in plan.kernel and ("exact 3-term" in plan.kernel) == bool(exact), plan.kernel
+    out = plan.run(X).astype(np.float64)
+    want = np.stack([m.predict(X.astype(np.float64)) for m in models], axis=1)
+    err = np.abs(out - want)
+    print("dense head, exact=%d: max |err| %.3e, mean %.3e (max |score| %.1f)" % (exact, err.max(), err.mean(), np.abs(want).max()))
+    np.testing.assert_allclose(out, want, rtol=RTOL, atol=ATOL)
+    assert err.max() < 8e-6 and err.mean() < 1.5e-6  # float32 output rounding alone is up to 2e-6 at |score| ~ 40
 
 
 def test_sixteen_class_logistic_regression_labels():
