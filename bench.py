@@ -453,10 +453,10 @@ def ring_bench(nat, name="flow3_ens4", seconds=0.5):
         server.await_result(server.emit(body))
         lat.append((time.perf_counter() - t0) * 1e6)
     return {"how": "b2s_ring_bench: N native threads, each b2s_submit(rows) + b2s_wait(ticket) in a loop (default ring: "
-                   "4 slots x 65536 rows, max_wait_us 200); events/s = rows served / wall",
+                   "4 slots x 65536 rows, max_wait_us 0: a blocked caller runs its batch as soon as the stream is free, rows of other callers join meanwhile); events/s = rows served / wall",
             "native": rows, "run_events": run_events,
             "emit_await_one_caller_us": {"p50": float(np.percentile(lat[20:], 50)), "p99": float(np.percentile(lat[20:], 99)),
-                                         "how": "GraphServer.emit(body) + await_result(ticket), one Python caller (pays max_wait_us)"}}
+                                         "how": "GraphServer.emit(body) + await_result(ticket), one Python caller"}}
 
 
 def compact_line(line):

@@ -224,6 +224,7 @@ struct b2s_plan_s {
   std::condition_variable cv_work, cv_done, cv_free;
   std::thread dispatcher;
   bool stop = false;
+  bool dispatch_busy = false;  // a batch is on the ring's stream (run by the dispatcher thread or by a waiting caller)
   cudaStream_t ring_stream = nullptr;
   int64_t ring_cap = 0;
   // per-plan ring configuration (b2s_plan_set_ring; 0 / negative: the library defaults of b2s_init)
@@ -2258,11 +2259,96 @@ extern "C" int b2s_time_device(b2s_plan_t p, const void* const* d_rows, int32_t 
 }
 
 // ------------------------------------------------------------------------------------------ coalescing ring
+// One coalesced batch on the ring's stream: pinned slot -> (H2D) -> kernels -> (D2H) -> pinned slot, then the host waits for it.
+// Runs WITHOUT the plan's lock, either on the dispatcher thread or on a caller blocked in b2s_wait (see there); `dispatch_busy`
+// keeps it to one batch at a time.
+struct BatchResult {
+  b2s_stats stats{};
+  int err = 0;
+  std::string err_msg;
+};
+
+constexpr int kRingGraceUs = 50;
+
+static BatchResult ring_run_batch(b2s_plan_s* p, Slot& s) {
+  BatchResult res;
+  const int64_t rows = s.rows;
+  const float queue_us =
+      std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - s.first_submit).count();
+  cudaStream_t st = p->ring_stream;
+  const int64_t row_bytes = (int64_t)p->n_in * 4;
+  const size_t out_sz = (size_t)rows * p->out_cols * 4;
+  // every step is checked: a batch whose copy or launch failed is reported to all of its tickets (b2s_wait returns
+  // the error and copies nothing) instead of handing out whatever an earlier batch left in the pinned slot
+  int& err = res.err;
+  std::string& err_msg = res.err_msg;
+  auto step = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && !err) {
+      err = B2S_ERR_CUDA;
+      err_msg = std::string("coalesced batch: ") + what + ": " + cudaGetErrorString(e);
+    }
+  };
+  static const int64_t zc_in_bytes = getenv("B2S_ZEROCOPY_IN_BYTES") ? atoll(getenv("B2S_ZEROCOPY_IN_BYTES")) : 65536;
+  static const int zc_out = getenv("B2S_ZEROCOPY_OUT") ? atoi(getenv("B2S_ZEROCOPY_OUT")) : 1;
+  const bool zero_out = zc_out && p->peers.empty() && !p->comm;  // results go straight into the slot's pinned result area
+  const bool zero_in = zero_out && rows * row_bytes <= zc_in_bytes;  // a tiny batch is read from the pinned slot as well
+  step(cudaEventRecord(s.e0, st), "event record");
+  if (!zero_in) step(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st), "H2D copy");
+  step(cudaEventRecord(s.e1, st), "event record");
+  if (!err) {
+    int32_t* h_status = (int32_t*)(s.h_out + (size_t)p->ring_cap * p->out_cols * 4);
+    const int rc = zero_out ? launch_on(p, zero_in ? s.h_in : s.d_in, rows, row_bytes, s.h_out, h_status, st, zero_in)
+                            : launch_on(p, s.d_in, rows, row_bytes, s.d_out, s.d_status, st);
+    if (rc) {
+      err = rc;
+      err_msg = std::string("coalesced batch: ") + g_err;
+    }
+  }
+  step(cudaEventRecord(s.e2, st), "event record");
+  if (!err && !zero_out) {
+    step(cudaMemcpyAsync(s.h_out, s.d_out, out_sz, cudaMemcpyDeviceToHost, st), "D2H copy");
+    step(cudaMemcpyAsync(s.h_out + (size_t)p->ring_cap * p->out_cols * 4, s.d_status, (size_t)rows * 4, cudaMemcpyDeviceToHost, st), "D2H copy");
+  }
+  step(cudaEventRecord(s.e3, st), "event record");
+  step(cudaEventSynchronize(s.e3), "execution");
+  b2s_stats& stt = res.stats;
+  stt.rows = rows;
+  if (!err) {
+    cudaEventElapsedTime(&stt.h2d_ms, s.e0, s.e1);
+    cudaEventElapsedTime(&stt.kernel_ms, s.e1, s.e2);
+    cudaEventElapsedTime(&stt.d2h_ms, s.e2, s.e3);
+  } else {
+    cudaGetLastError();  // the error is reported through the tickets
+  }
+  stt.queue_us = queue_us;
+  stt.kernels = p->kernels_per_batch;
+  return res;
+}
+
+// with the lock held: publish the batch to its tickets and pass the stream on
+static void ring_finish_batch(b2s_plan_s* p, Slot& s, const BatchResult& res) {
+  s.stats = res.stats;
+  s.err = res.err;
+  s.err_msg = res.err_msg;
+  s.state = 3;
+  p->dispatch_busy = false;
+  if (s.done_cv) s.done_cv->notify_all();
+  // the batch that collected rows meanwhile: one of the callers blocked on it runs it (b2s_wait); the dispatcher thread
+  // covers batches nobody is blocked on
+  if (p->open_slot >= 0 && p->slots[p->open_slot].wanted && p->slots[p->open_slot].done_cv) p->slots[p->open_slot].done_cv->notify_one();
+  p->cv_work.notify_one();
+}
+
 static void dispatcher_main(b2s_plan_s* p) {
   cudaSetDevice(G.device);
   std::unique_lock<std::mutex> lk(p->mu);
   for (;;) {
     // wake up when a batch is sealed, when the open batch is due, or on stop
+    if (p->dispatch_busy) {  // a caller blocked in b2s_wait is running a batch on the ring's stream
+      if (p->stop) return;
+      p->cv_work.wait(lk);
+      continue;
+    }
     if (p->sealed.empty()) {
       if (p->stop) return;
       if (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0) {
@@ -2277,25 +2363,20 @@ static void dispatcher_main(b2s_plan_s* p) {
           p->cv_work.wait(lk);  // a slot is collected, the batch fills up, a waiter or a flush seals it
           continue;
         }
-        auto deadline = p->slots[p->open_slot].first_submit + std::chrono::microseconds(p->wait_us());
+        // max_wait_us = 0: a caller that blocks on the batch runs it itself (b2s_wait); this thread takes what nobody has
+        // claimed after a short grace period (callers that submit now and collect later)
+        const auto hold = std::chrono::microseconds(p->wait_us() > 0 ? p->wait_us() : kRingGraceUs);
+        auto deadline = p->slots[p->open_slot].first_submit + hold;
         if (std::chrono::steady_clock::now() >= deadline || p->cv_work.wait_until(lk, deadline) == std::cv_status::timeout) {
-          if (p->sealed.empty() && p->open_slot >= 0 && p->slots[p->open_slot].rows > 0 &&
-              std::chrono::steady_clock::now() >= p->slots[p->open_slot].first_submit + std::chrono::microseconds(p->wait_us())) {
+          if (!p->dispatch_busy && p->sealed.empty() && p->open_slot >= 0 && p->slots[p->open_slot].rows > 0 &&
+              std::chrono::steady_clock::now() >= p->slots[p->open_slot].first_submit + hold) {
             p->slots[p->open_slot].state = 1;
             p->sealed.push_back(p->open_slot);
             p->open_slot = -1;
           }
         }
       } else {
-        // nothing to run: look again for a little while before sleeping (the next request is usually close behind)
-        bool work = false;
-        for (int spin = 0; spin < 300 && !work; ++spin) {
-          lk.unlock();
-          for (int i = 0; i < 40; ++i) __builtin_ia32_pause();
-          lk.lock();
-          work = p->stop || !p->sealed.empty() || (p->open_slot >= 0 && p->slots[p->open_slot].rows > 0);
-        }
-        if (!work) p->cv_work.wait(lk);
+        p->cv_work.wait(lk);  // nothing to run (blocked callers run their own batches: no reason to poll here)
       }
       continue;
     }
@@ -2303,63 +2384,11 @@ static void dispatcher_main(b2s_plan_s* p) {
     p->sealed.pop_front();
     Slot& s = p->slots[si];
     s.state = 2;
-    const int64_t rows = s.rows;
-    const float queue_us =
-        std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - s.first_submit).count();
+    p->dispatch_busy = true;
     lk.unlock();
-    cudaStream_t st = p->ring_stream;
-    const int64_t row_bytes = (int64_t)p->n_in * 4;
-    const size_t out_sz = (size_t)rows * p->out_cols * 4;
-    // every step is checked: a batch whose copy or launch failed is reported to all of its tickets (b2s_wait returns
-    // the error and copies nothing) instead of handing out whatever an earlier batch left in the pinned slot
-    int err = 0;
-    std::string err_msg;
-    auto step = [&](cudaError_t e, const char* what) {
-      if (e != cudaSuccess && !err) {
-        err = B2S_ERR_CUDA;
-        err_msg = std::string("coalesced batch: ") + what + ": " + cudaGetErrorString(e);
-      }
-    };
-    static const int64_t zc_in_bytes = getenv("B2S_ZEROCOPY_IN_BYTES") ? atoll(getenv("B2S_ZEROCOPY_IN_BYTES")) : 65536;
-    static const int zc_out = getenv("B2S_ZEROCOPY_OUT") ? atoi(getenv("B2S_ZEROCOPY_OUT")) : 1;
-    const bool zero_out = zc_out && p->peers.empty() && !p->comm;  // results go straight into the slot's pinned result area
-    const bool zero_in = zero_out && rows * row_bytes <= zc_in_bytes;  // a tiny batch is read from the pinned slot as well
-    step(cudaEventRecord(s.e0, st), "event record");
-    if (!zero_in) step(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st), "H2D copy");
-    step(cudaEventRecord(s.e1, st), "event record");
-    if (!err) {
-      int32_t* h_status = (int32_t*)(s.h_out + (size_t)p->ring_cap * p->out_cols * 4);
-      const int rc = zero_out ? launch_on(p, zero_in ? s.h_in : s.d_in, rows, row_bytes, s.h_out, h_status, st, zero_in)
-                              : launch_on(p, s.d_in, rows, row_bytes, s.d_out, s.d_status, st);
-      if (rc) {
-        err = rc;
-        err_msg = std::string("coalesced batch: ") + g_err;
-      }
-    }
-    step(cudaEventRecord(s.e2, st), "event record");
-    if (!err && !zero_out) {
-      step(cudaMemcpyAsync(s.h_out, s.d_out, out_sz, cudaMemcpyDeviceToHost, st), "D2H copy");
-      step(cudaMemcpyAsync(s.h_out + (size_t)p->ring_cap * p->out_cols * 4, s.d_status, (size_t)rows * 4, cudaMemcpyDeviceToHost, st), "D2H copy");
-    }
-    step(cudaEventRecord(s.e3, st), "event record");
-    step(cudaEventSynchronize(s.e3), "execution");
-    b2s_stats stt{};
-    stt.rows = rows;
-    if (!err) {
-      cudaEventElapsedTime(&stt.h2d_ms, s.e0, s.e1);
-      cudaEventElapsedTime(&stt.kernel_ms, s.e1, s.e2);
-      cudaEventElapsedTime(&stt.d2h_ms, s.e2, s.e3);
-    } else {
-      cudaGetLastError();  // the error is reported through the tickets
-    }
-    stt.queue_us = queue_us;
-    stt.kernels = p->kernels_per_batch;
+    BatchResult res = ring_run_batch(p, s);
     lk.lock();
-    s.stats = stt;
-    s.err = err;
-    s.err_msg = err_msg;
-    s.state = 3;
-    if (s.done_cv) s.done_cv->notify_all();
+    ring_finish_batch(p, s, res);
   }
 }
 
@@ -2509,26 +2538,57 @@ extern "C" int b2s_wait(b2s_plan_t p, uint64_t ticket, void* out, int64_t out_by
     auto it = p->batch_slot.find(batch);
     if (it == p->batch_slot.end()) return fail(B2S_ERR_INVALID, "unknown ticket");
     Slot& s = p->slots[it->second];
-    // The ticket's batch is still collecting rows: ask for it.  It is NOT sealed here -- while the dispatcher is busy with
-    // the previous batch the rows of other callers keep joining (that is what coalesces concurrent request threads; sealing
-    // at once made every caller's row a batch of its own: 28 K events/s for 8 producers, measured r2h); an idle dispatcher
-    // takes it immediately.
-    if (s.state == 0 && p->open_slot == it->second && s.rows > 0 && !s.wanted) {
-      s.wanted = true;
-      p->cv_work.notify_one();
-    }
-    // a short spin before sleeping: two condition-variable hand-offs (producer -> dispatcher -> waiter) cost more than a
-    // small batch takes on the device
-    // (only a couple of waiters at a time: a crowd of spinners would fight the dispatcher for the lock and the cores)
-    if (p->spinners.fetch_add(1, std::memory_order_relaxed) < 2) {
-      for (int spin = 0; spin < 400 && !(s.state == 3 && s.batch_id == batch); ++spin) {
-        lk.unlock();
-        for (int i = 0; i < 40; ++i) __builtin_ia32_pause();
-        lk.lock();
+    // Who runs the batch?  With max_wait_us = 0 the caller that blocks on it does, right here, as soon as the ring's stream is
+    // free (no hand-off to another thread and back: that costs more than a small batch takes on the device, and under many
+    // request threads the dispatcher thread would queue for a core behind them).  While a batch is in flight the rows of other
+    // callers keep joining the open one (that is what coalesces concurrent request threads); whoever finishes a batch wakes one
+    // caller of the next.  The dispatcher thread covers sealed batches and batches nobody is blocked on.
+    const int idx = it->second;
+    auto done = [&] { return s.state == 3 && s.batch_id == batch; };
+    auto claim = [&] {  // with the lock held: may this thread run the ticket's batch now?
+      if (p->dispatch_busy || p->stop) return false;
+      if (s.state == 0 && p->open_slot == idx && s.rows > 0 && p->sealed.empty() && p->wait_us() == 0) {
+        p->open_slot = -1;
+        return true;
       }
+      if (s.state == 1 && !p->sealed.empty() && p->sealed.front() == idx) {
+        p->sealed.pop_front();
+        return true;
+      }
+      return false;
+    };
+    bool spun = false;
+    while (!done()) {
+      if (claim()) {
+        s.state = 2;
+        p->dispatch_busy = true;
+        lk.unlock();
+        cudaSetDevice(G.device);
+        BatchResult res = ring_run_batch(p, s);
+        lk.lock();
+        ring_finish_batch(p, s, res);
+        continue;
+      }
+      if (s.state == 0 && p->open_slot == idx && !s.wanted) {  // a caller is blocked on this batch: it must not be held back
+        s.wanted = true;
+        p->cv_work.notify_one();
+      }
+      // a short spin before sleeping (only a couple of callers at a time: a crowd of spinners would fight for the lock)
+      if (!spun) {
+        spun = true;
+        if (p->spinners.fetch_add(1, std::memory_order_relaxed) < 2) {
+          for (int spin = 0; spin < 400 && !done(); ++spin) {
+            lk.unlock();
+            for (int i = 0; i < 40; ++i) __builtin_ia32_pause();
+            lk.lock();
+            if (!p->dispatch_busy && (s.state == 0 || s.state == 1)) break;  // the stream is free: try to claim the batch
+          }
+        }
+        p->spinners.fetch_sub(1, std::memory_order_relaxed);
+        continue;
+      }
+      s.done_cv->wait(lk);  // woken when the batch is done, or to take the stream over
     }
-    p->spinners.fetch_sub(1, std::memory_order_relaxed);
-    s.done_cv->wait(lk, [&] { return s.state == 3 && s.batch_id == batch; });
     // the batch is done: whatever this call returns, the ticket is spent and the last one recycles the slot
     int rc = B2S_OK;
     if (s.err) {

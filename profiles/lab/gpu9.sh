@@ -1,17 +1,25 @@
 # 2-GPU validation: communicator, ShardedGraphServer, weak and strong scaling legs of bench.py
 set -x
-mkdir -p gpurun_out/r2i
-nvidia-smi topo -m > gpurun_out/r2i/topo.txt 2>&1
-(timeout 600 python -m pytest tests/test_gpu_multi.py -q --timeout 300 -x) > gpurun_out/r2i/pytest_multi.txt 2>&1
-tail -30 gpurun_out/r2i/pytest_multi.txt
+export OUT=${OUT:-r2i}
+NP=${NP:-2}
+mkdir -p gpurun_out/$OUT
+nvidia-smi topo -m > gpurun_out/$OUT/topo.txt 2>&1
+# single-GPU checks of what changed since the last single-GPU batch (ring: callers run their own batches; dense test bound)
+(timeout 300 python -m pytest tests/test_gpu_serving.py tests/test_gpu_dense.py tests/test_gpu_parity.py -q --timeout 100 -x) > gpurun_out/$OUT/pytest_ring.txt 2>&1
+tail -4 gpurun_out/$OUT/pytest_ring.txt
+(cd profiles/lab/bin && TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 suppressions=../tsan.supp" LD_LIBRARY_PATH=/usr/local/cuda/lib64:. timeout 300 setarch $(uname -m) -R ./ring_tsan 3 16) > gpurun_out/$OUT/tsan_ring.txt 2>&1
+tail -2 gpurun_out/$OUT/tsan_ring.txt; grep -c "WARNING: ThreadSanitizer" gpurun_out/$OUT/tsan_ring.txt
+(timeout 120 python profiles/lab/ring_probe.py) > gpurun_out/$OUT/ring_probe.txt 2>&1; cat gpurun_out/$OUT/ring_probe.txt | tail -12
+(timeout 600 python -m pytest tests/test_gpu_multi.py -q --timeout 300 -x) > gpurun_out/$OUT/pytest_multi.txt 2>&1
+tail -30 gpurun_out/$OUT/pytest_multi.txt
 run() {  # name, extra args...
   name=$1; shift
-  (timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 3 "$@") > gpurun_out/r2i/$name.json 2> gpurun_out/r2i/$name.err
-  tail -3 gpurun_out/r2i/$name.err
+  (timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $NP --steps 20 --warmup 3 "$@") > gpurun_out/$OUT/$name.json 2> gpurun_out/$OUT/$name.err
+  tail -3 gpurun_out/$OUT/$name.err
   python - <<PY
 import json
 try:
-    d=json.loads(open('gpurun_out/r2i/$name.json').read().strip().splitlines()[-1])
+    d=json.loads(open('gpurun_out/$OUT/$name.json').read().strip().splitlines()[-1])
     print('$name', {k:d.get(k) for k in ('value','ms_per_step','n_gpus','scaling','merge','merge_verified')}, d.get('config'))
 except Exception as e: print('$name parse failed', e)
 PY
@@ -20,12 +28,17 @@ run weak2 --no-configs
 run weak2_nccl --no-configs --merge nccl
 run strong2_router8 --workload router8 --scaling strong --batch 65536 --no-configs
 run ingest2 --workload ingest6 --no-configs
-(timeout 300 python bench.py --steps 20 --warmup 3 --no-configs --no-cpu-baseline) > gpurun_out/r2i/one.json 2> gpurun_out/r2i/one.err
-(timeout 300 python bench.py --steps 20 --warmup 3 --no-configs --no-cpu-baseline --workload router8 --batch 65536) > gpurun_out/r2i/one_router8.json 2> gpurun_out/r2i/one_router8.err
+(timeout 300 python bench.py --steps 20 --warmup 3 --no-configs --no-cpu-baseline) > gpurun_out/$OUT/one.json 2> gpurun_out/$OUT/one.err
+(timeout 300 python bench.py --steps 20 --warmup 3 --no-configs --no-cpu-baseline --workload router8 --batch 65536) > gpurun_out/$OUT/one_router8.json 2> gpurun_out/$OUT/one_router8.err
 python - <<'PY'
 import json
 for n in ('one','one_router8'):
     try:
-        d=json.loads(open(f'gpurun_out/r2i/{n}.json').read().strip().splitlines()[-1]); print(n, d['value'], d['ms_per_step'])
+        d=json.loads(open('gpurun_out/'+__import__('os').environ['OUT']+'/'+n+'.json').read().strip().splitlines()[-1]); print(n, d['value'], d['ms_per_step'])
     except Exception as e: print(n,'failed',e)
 PY
+
+# NVLink counters of the scoring kernel with the fused merge stores (rank 0 under ncu, the peers only hold their buffers)
+(MASTER_ADDR=127.0.0.1 MASTER_PORT=29533 WORLD_SIZE=2 RANK=1 timeout 200 python profiles/lab/nvlink_probe.py > gpurun_out/$OUT/nvlink_rank1.log 2>&1 &)
+(MASTER_ADDR=127.0.0.1 MASTER_PORT=29533 WORLD_SIZE=2 RANK=0 timeout 200 ncu --clock-control none -k regex:rowthread -s 2 -c 3 --metrics nvltx__bytes.sum,nvlrx__bytes.sum,nvltx__bytes.sum.per_second,lts__t_sectors_srcunit_tex_aperture_peer_op_write.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv --log-file gpurun_out/$OUT/nvlink_ncu.csv python profiles/lab/nvlink_probe.py) > gpurun_out/$OUT/nvlink_rank0.log 2>&1
+tail -3 gpurun_out/$OUT/nvlink_rank0.log; tail -12 gpurun_out/$OUT/nvlink_ncu.csv | cut -c1-300
