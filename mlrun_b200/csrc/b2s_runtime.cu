@@ -27,6 +27,7 @@
 #include "b2s_device.cuh"
 #include "b2s_rowwarp.cuh"
 #include "b2s_rowthread.cuh"
+#include "b2s_rowmma.cuh"
 #include "b2s_trees2.cuh"
 #include "b2s_trees3.cuh"
 #include "b2s_dense.cuh"
@@ -171,6 +172,9 @@ struct b2s_plan_s {
   bool rt_ok = false;
   int rt_cat_cols = 0;  // one-hot source columns of the row-thread plan
   int rt_NCH = 0, rt_NS = 0, rt_TPR = 1, rt_grid = 0, rt_smem = 0, rt_tile_rows = 128, rt_pitch = 0, rt_stages = 2, rt_RPT = 1;
+  // DMMA variant of the row kernel (b2s_rowmma.cuh): tensor-map launches of plans with 32 / 64 columns
+  bool rm_ok = false;
+  int rm_warps = 8, rm_stages = 3, rm_smem = 0;
   std::vector<char> rt_blob;  // an RTParams<NCH, NS>
   // fused ensemble-merge targets (P2P)
   std::vector<void*> peers;
@@ -488,6 +492,11 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   int rpt = (mode == 2) ? p->rt_RPT : 1;
   int tr = p->rt_tile_rows;
   while (tr > 32 * rpt && (n_rows + tr - 1) / tr < (int64_t)G.prop.multiProcessorCount) tr /= 2;
+  const bool mma = mode == 2 && p->rm_ok;  // DMMA variant: warp-private rings of 32-row tiles
+  if (mma) {
+    tr = 32;
+    rpt = 1;
+  }
   alignas(64) CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (mode == 2 && !encode_rows_map(&tmap, rows, n_rows, stride, p->n_in, tr)) {
@@ -507,6 +516,13 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
     const int col = r.cat_col[cc], ch = col >> 2;
     r.cat_off[cc] = mode == 2 ? (ch >> 3) * (tr * 32) + (col & 3) : col;
     r.cat_sw[cc] = mode == 2 ? (ch & 7) << 2 : 0;
+  }
+  if (mode == 2 && mma) {
+    r.stages = p->rm_stages;
+    const int64_t per_cta = (tiles + G.prop.multiProcessorCount - 1) / G.prop.multiProcessorCount;  // tiles a CTA will see
+    const int warps = (int)std::max<int64_t>(1, std::min<int64_t>(p->rm_warps, per_cta));
+    const int mgrid = (int)std::max<int64_t>(1, std::min<int64_t>(G.prop.multiProcessorCount, tiles));
+    return rowmma_launch(NCH, NS, &r, &tmap, mgrid, warps, (size_t)p->rm_smem, st);
   }
   if (mode == 2 && rpt == 2)
     rowthread_kernel<NCH, NS, TPR, LMT, R2><<<grid, tr / 2 * TPR, p->rt_smem, st>>>(r, tmap);
@@ -1690,6 +1706,18 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
         if (p->rt_smem <= smem_cap && rt_launch(p, nullptr, 0, 0, nullptr, nullptr, 0, nullptr, true, &occ) == cudaSuccess && occ >= 1) {
           p->rt_ok = true;
           p->rt_grid = sms * occ;
+          // DMMA variant (default where it applies; B2S_RT_MMA=0 keeps the DFMA kernel): 32 or 64 float32 columns, tensor-map loads
+          const char* mma_env = getenv("B2S_RT_MMA");
+          if ((!mma_env || atoi(mma_env) != 0) && (p->rt_NCH == 8 || p->rt_NCH == 16) && n_in == p->rt_NCH * 4 && tensor_map_encoder()) {
+            const char* we = getenv("B2S_RM_WARPS");
+            const char* se = getenv("B2S_RM_STAGES");
+            p->rm_warps = we ? std::max(1, std::min(kRMMaxWarps, atoi(we))) : 8;
+            p->rm_stages = se ? std::max(2, std::min(kRMMaxStages, atoi(se))) : 3;
+            while (p->rm_warps > 1 && rowmma_smem_bytes(p->rt_NCH, NS, (int)cat_val.size(), p->rm_warps, p->rm_stages) > (size_t)smem_cap) --p->rm_warps;
+            p->rm_smem = (int)rowmma_smem_bytes(p->rt_NCH, NS, (int)cat_val.size(), p->rm_warps, p->rm_stages);
+            if (p->rm_smem <= smem_cap && rowmma_prepare(p->rt_NCH, NS, smem_cap) == cudaSuccess) p->rm_ok = true;
+            else cudaGetLastError();
+          }
         } else {
           cudaGetLastError();
         }
@@ -1828,6 +1856,7 @@ extern "C" const char* b2s_plan_kernel(b2s_plan_t p) {
   if (p->dense_ok) snprintf(buf, sizeof(buf), "dense_head_kernel<N=%d> (tcgen05.mma kind::tf32, %s, TMEM accumulator groups; %d scores over %d columns)", p->dense.n_pad, p->dense.exact ? "exact 3-term input split" : "2-term input split", p->dense.n_scores, p->dense.n_in);
   else if (p->t3_ok) snprintf(buf, sizeof(buf), "t3_prep_kernel + trees3_kernel<D=%d,%s> + t3_vote_kernel (%d parts resident in shared memory, %d walking warps%s)", p->t3_D, p->t3_miss ? "NaN routing" : "floats", p->t3_parts, p->t3.warps, p->t3_top ? ", top levels in the constant bank" : "");
   else if (p->t2_ok) snprintf(buf, sizeof(buf), "trees_model_kernel<%d> + vote_kernel (models resident in shared memory)", p->t2_NS);
+  else if (p->rt_ok && p->rm_ok && lm == 2) snprintf(buf, sizeof(buf), "rowmma_kernel<NCH=%d,NS=%d> (DMMA m8n8k4 fp64, %d warps x %d stages of 32-row TMA tiles per SM)", p->rt_NCH, p->rt_NS, p->rm_warps, p->rm_stages);
   else if (p->rt_ok) snprintf(buf, sizeof(buf), "rowthread_kernel<NCH=%d,NS=%d,TPR=%d,RPT=%d,%s>", p->rt_NCH, p->rt_NS, p->rt_TPR, lm == 2 ? p->rt_RPT : 1, lm == 2 ? "TMA tensor-map loads" : (lm == 1 ? "TMA bulk loads" : "cp.async loads"));
   else if (p->rw_ok) snprintf(buf, sizeof(buf), "rowwarp_kernel<L=%d,CPL=%d,NS=%d,U=%d,CS=%d>", p->rw_L, p->rw_CPL, p->rw_NS, p->rw_U, p->rw_CS);
   else snprintf(buf, sizeof(buf), "rows_kernel<%s,NS=%d>", p->mode == MODE_LINEAR ? "LINEAR" : (p->mode == MODE_TREES ? "TREES" : "STORE"), p->NS);
