@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = --batch events per GPU; strong = --batch events in total, split over the GPUs "
                          "(BASELINE configs[3]: --workload router8 --scaling strong --batch 65536)")
+    ap.add_argument("--merge-lag", type=int, default=1, choices=[0, 1],
+                    help="p2p merge: 0 = every launch waits for its own completion flags (lockstep); 1 = it waits for the "
+                         "previous launch's (pipelined: the merged response of a batch is complete one launch later)")
     ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 ensemble-merge: p2p = votes stored into every rank's buffer from the kernel epilogue over "
                          "NVLink peer memory (fused); nccl = a separate all_gather per step")
@@ -550,14 +553,19 @@ def main():
         plan.run_device(bufs[i % nbuf].data_ptr(), B, row_bytes, out.data_ptr(), None, stream.cuda_stream)
         if merge == "nccl":  # ensemble-merge: every rank ends up with every shard's votes (4 B/event)
             dist.all_gather_into_tensor(gathered, out)
-        elif merge == "p2p":  # the step is over when this rank has seen the completion flags of all shards
-            last_merged[0] = comm.wait(stream.cuda_stream)[0]
+        elif merge == "p2p":  # lag 0: the step is over when this rank has seen the completion flags of all shards;
+            # lag 1 (default): the wait is for the previous launch, this one's votes travel while the next is scored
+            comm.wait(stream.cuda_stream, args.merge_lag)
 
     inner = args.launches_per_step
 
     def step(i):  # one step = `inner` launches, each over the next of the rotating batches
         for j in range(inner):
             launch(i * inner + j)
+
+    def drain():  # pipelined merge: the last launch's votes have to be complete inside the timed region
+        if merge == "p2p":
+            last_merged[0] = comm.wait(stream.cuda_stream, 0)[0]
 
     def sync():
         if world > 1:
@@ -589,6 +597,7 @@ def main():
     e0.record(stream)
     for i in range(args.steps):
         step(i)
+    drain()
     e1.record(stream)
     sync()
     t_wall1 = time.perf_counter()
@@ -701,7 +710,8 @@ def main():
                        "launches_per_step": inner, "events_per_step_per_gpu": B * inner, "timed_region_ms": ms,
                        "parallelism": f"event-sharded x{world}" + {"none": "", "nccl": " + NCCL all-gather of votes per step",
                                                                     "p2p": " + fused P2P ensemble-merge (votes stored to every rank over NVLink "
-                                                                           "from the kernel epilogue, completion flags awaited on the device each step)"}[merge],
+                                                                           "from the kernel epilogue, completion flags awaited on the device "
+                                                                           + ("each launch)" if args.merge_lag == 0 else "one launch later: pipelined, lag 1)")}[merge],
                        "merge_verified": merge_check,
                        "l2": f"{nbuf} rotating input buffers of {B * row_bytes / 1e6:.0f} MB (> 126 MB L2 between re-reads)",
                        "device": info["name"], "kernel": plan.kernel},

@@ -202,18 +202,22 @@ int b2s_ipc_open(const void* handle64, void** dptr_out);
 int b2s_ipc_close(void* dptr);
 
 /* The same exchange as a product object: a communicator owns, per rank, ONE device allocation -- completion flags and the
- * merged response rows, double buffered -- that every peer maps over CUDA IPC.  Bootstrap needs any out-of-band channel
+ * merged response rows in four slots -- that every peer maps over CUDA IPC.  Bootstrap needs any out-of-band channel
  * that can all-gather 64 bytes per rank (torch.distributed, MPI, a file, a socket ...):
  *     b2s_comm_create(rank, world, max_rows_per_rank, out_cols, &c);  b2s_comm_handle(c, mine);
  *     <all-gather the 64-byte handles>;  b2s_comm_connect(c, all);  b2s_plan_attach_comm(plan, c);
  * Every b2s_run_device / b2s_run_host / ring batch of an attached plan is then one STEP (epoch e = 1, 2, ...) of the
  * ensemble-merge (serving/routers.py:414-455 fans the event out to the routes, :789-810 reduces them; here the rows are
- * sharded and the votes merged): the kernels store this rank's votes into parity e & 1 of EVERY rank's merged rows at row
+ * sharded and the votes merged): the kernels store this rank's votes into slot e & 3 of EVERY rank's merged rows at row
  * block `rank`, and the launch's last CTA publishes e in every rank's flag array (st.release.sys).  b2s_comm_wait enqueues
  * a kernel that acquires all `world` flags of THIS rank at the current epoch, so work enqueued behind it (a D2H copy, the
  * next kernel) reads a complete response; *d_merged is that response, (world x max_rows_per_rank x out_cols) words, rank
- * r's rows at r * max_rows_per_rank.  Ranks must wait on every step before launching the next one: seeing all flags of
- * step e proves that every peer has consumed step e - 1, which is what makes two buffers enough.  A peer that never
+ * r's rows at r * max_rows_per_rank.  Every launch must be followed by a wait on the same stream: b2s_comm_wait (step e,
+ * lockstep) or b2s_comm_wait_lag(.., 1, ..) (step e - 1: the votes and flags of step e cross NVLink while step e + 1 is being
+ * scored; the response of a step is then available one launch later, and a final b2s_comm_wait drains the last step).
+ * Four slots make both safe: before a rank launches step e + 4 (which overwrites slot e & 3 everywhere) it has passed its
+ * wait for step e + 2 at the latest, i.e. it has seen every peer's flag of step e + 2 -- and a peer's launch of step e + 2
+ * sits behind that peer's wait for (and use of) step e in the peer's own stream.  A peer that never
  * signals makes the wait give up after B2S_COMM_TIMEOUT_MS (default 10 s; b2s_comm_check reports B2S_ERR_TIMEOUT) instead of hanging the GPU. */
 typedef struct b2s_comm_s* b2s_comm_t;
 int b2s_comm_create(int32_t rank, int32_t world, int64_t max_rows_per_rank, int32_t out_cols, b2s_comm_t* out);
@@ -221,6 +225,8 @@ int b2s_comm_handle(b2s_comm_t comm, void* handle64 /* 64 bytes out */);
 int b2s_comm_connect(b2s_comm_t comm, const void* all_handles /* world x 64 bytes, in rank order */);
 int b2s_plan_attach_comm(b2s_plan_t plan, b2s_comm_t comm /* NULL detaches */);
 int b2s_comm_wait(b2s_comm_t comm, void* stream, const void** d_merged, uint32_t* epoch);
+/* lag 0 or 1; with fewer than lag + 1 steps launched there is nothing to wait for: *d_merged = NULL, *epoch = 0 */
+int b2s_comm_wait_lag(b2s_comm_t comm, void* stream, int32_t lag, const void** d_merged, uint32_t* epoch);
 int b2s_comm_check(b2s_comm_t comm);
 int b2s_comm_destroy(b2s_comm_t comm);
 

@@ -70,6 +70,23 @@ struct RTParams {
   float cat_val[kRTMaxCats];
   // fused enrichment (per-row bulk loader only): tile rows are fetched from an online table by entity key instead of
   // from `rows` (b2s_table.cu).  Kept at the end: the offsets of everything above are those of the plain kernels.
+  // fast one-hot path (every categorical column has consecutive integer codes): the constants of a column packed so that
+  // two 16-byte constant loads fetch them; byte offsets, so that the address of a weight row is one shift-add
+  struct CatFast {
+    int32_t off_b;    // byte offset of the column's word in a tile row (per launch, like cat_off)
+    int32_t sw_b;     // swizzle term in bytes (tensor-map tiles), 0 otherwise
+    int32_t first;    // first category code
+    int32_t cnt;      // number of categories
+    int32_t woff_b;   // byte offset of the first category's weight row in s_wcat
+    float fill;       // Imputer value of the column (NaN: not imputed)
+    int32_t pad[2];
+  };
+  CatFast catf[kRTMaxCatCols];
+  int32_t cats_fast;   // 1: catf describes every categorical column
+  int32_t zero_woff_b; // byte offset of the all-zero weight row ("no category matched")
+  int32_t dead_tail;   // trailing 16-byte chunks without a model-input column (one-hot sources at the end of the row):
+                       // the dot products run over the live chunks only (0, 2 or 4 chunks skipped; see rt_row_slices)
+  int32_t pad_fast;
   const long long* g_keys;     // [n_rows]; null = rows come from `rows`
   const TableSlot* g_slots;
   uint64_t g_mask;
@@ -82,6 +99,7 @@ struct RowPadded {  // LDGSTS / per-row bulk copies: rows `pitch` words apart (p
   const float* xr;
   __device__ __forceinline__ float4 chunk(int ch) const { return *reinterpret_cast<const float4*>(xr + ch * 4); }
   __device__ __forceinline__ float at2(int off, int) const { return xr[off]; }
+  __device__ __forceinline__ float at_b(int off_b, int) const { return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(xr) + off_b); }
 };
 struct RowSwizzled {  // 2-D TMA boxes of 32 floats x TR rows, SWIZZLE_128B: chunk j of row r sits at j ^ (r & 7)
   const float* box0;  // row r of box 0
@@ -92,6 +110,9 @@ struct RowSwizzled {  // 2-D TMA boxes of 32 floats x TR rows, SWIZZLE_128B: chu
   }
   // off = (ch >> 3) * box_words + (col & 3), sw = (ch & 7) << 2 with ch = col >> 2 (set per launch by the host)
   __device__ __forceinline__ float at2(int off, int sw) const { return box0[off + (sw ^ r7s)]; }
+  __device__ __forceinline__ float at_b(int off_b, int sw_b) const {
+    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(box0) + off_b + (sw_b ^ (r7s << 2)));
+  }
 };
 
 // dot products of the chunks [CH0, CH1) of RPT rows with all NS weight columns (the weights, fills and limits
@@ -158,6 +179,37 @@ template <int NCH, int NS, int Q0, int TPR, int RPT, typename Row>
 __device__ __forceinline__ void rt_cats(const RTParams<NCH, NS>& p, const Row (&xr)[RPT], const double* __restrict__ s_wcat,
                                         double (&acc)[RPT][NS]) {
   constexpr int ITERS = (kRTMaxCatCols - Q0 + TPR - 1) / TPR;
+  if (p.cats_fast) {  // integer codes first .. first + cnt - 1 in every column: no search, no per-column branch
+    const char* wb = reinterpret_cast<const char*>(s_wcat);
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int cc = Q0 + it * TPR;
+      if (cc >= p.n_cat_cols) break;
+      const typename RTParams<NCH, NS>::CatFast cf = p.catf[cc];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        float x = xr[i].at_b(cf.off_b, cf.sw_b);
+        x = (x != x) ? cf.fill : x;
+        const int v = __float2int_rz(x);  // saturating; NaN -> 0 and fails the equality below
+        const unsigned jj = (unsigned)(v - cf.first);
+        const bool miss = ((float)v != x) | (jj >= (unsigned)cf.cnt);
+        const int a = miss ? p.zero_woff_b : cf.woff_b + (int)jj * (NS * 8);
+        if constexpr (NS % 2 == 0) {  // weight rows are 16-byte aligned: LDS.128
+#pragma unroll
+          for (int k = 0; k < NS; k += 2) {
+            const double2 w2 = *reinterpret_cast<const double2*>(wb + a + k * 8);
+            acc[i][k] += w2.x;
+            acc[i][k + 1] += w2.y;
+          }
+        } else {
+          const double* wc = reinterpret_cast<const double*>(wb + a);
+#pragma unroll
+          for (int k = 0; k < NS; ++k) acc[i][k] += wc[k];
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int cc = Q0 + it * TPR;
@@ -178,6 +230,29 @@ __device__ __forceinline__ void rt_cats(const RTParams<NCH, NS>& p, const Row (&
 #pragma unroll
       for (int k = 0; k < NS; ++k) acc[i][k] += wc[k];
     }
+  }
+}
+
+// slice q of a row: the dot products over its share of the LIVE leading chunks + its share of the one-hot columns.
+// The slice index is warp-uniform; each case has compile-time column indices (constant operands); the row's one-hot
+// columns are dealt round-robin to its threads.
+template <int NCH, int NS, int TPR, int LIVE, int RPT, typename Row>
+__device__ __forceinline__ void rt_row_slices(const RTParams<NCH, NS>& p, int q, const Row (&xr)[RPT], const double* __restrict__ s_wcat,
+                                              double (&acc)[RPT][NS]) {
+  static_assert(LIVE % TPR == 0, "live chunks must split evenly over the row's threads");
+  constexpr int CPT = LIVE / TPR;
+  if (TPR == 1 || q == 0) {
+    rt_slice<NCH, NS, 0, CPT>(p, xr, acc);
+    rt_cats<NCH, NS, 0, TPR>(p, xr, s_wcat, acc);
+  } else if (q == 1) {
+    rt_slice<NCH, NS, (TPR > 1 ? CPT : 0), (TPR > 1 ? 2 * CPT : 0)>(p, xr, acc);
+    rt_cats<NCH, NS, (TPR > 1 ? 1 : 0), TPR>(p, xr, s_wcat, acc);
+  } else if (q == 2) {
+    rt_slice<NCH, NS, (TPR > 2 ? 2 * CPT : 0), (TPR > 2 ? 3 * CPT : 0)>(p, xr, acc);
+    rt_cats<NCH, NS, (TPR > 2 ? 2 : 0), TPR>(p, xr, s_wcat, acc);
+  } else {
+    rt_slice<NCH, NS, (TPR > 3 ? 3 * CPT : 0), (TPR > 3 ? 4 * CPT : 0)>(p, xr, acc);
+    rt_cats<NCH, NS, (TPR > 3 ? 3 : 0), TPR>(p, xr, s_wcat, acc);
   }
 }
 
@@ -439,20 +514,14 @@ __global__ void __launch_bounds__(128 * TPR / RPT, RPT == 2 ? RT_R2_MINB : (TPR 
 #pragma unroll
       for (int k = 0; k < NS; ++k) acc[i][k] = 0.0;
     if (any_live) {
-      // the slice index is warp-uniform; each case has compile-time column indices (constant operands)
-      // (the row's one-hot columns are dealt round-robin to its threads)
-      if (TPR == 1 || q == 0) {
-        rt_slice<NCH, NS, 0, CPT>(p, xr, acc);
-        rt_cats<NCH, NS, 0, TPR>(p, xr, s_wcat, acc);
-      } else if (q == 1) {
-        rt_slice<NCH, NS, (TPR > 1 ? CPT : 0), (TPR > 1 ? 2 * CPT : 0)>(p, xr, acc);
-        rt_cats<NCH, NS, (TPR > 1 ? 1 : 0), TPR>(p, xr, s_wcat, acc);
-      } else if (q == 2) {
-        rt_slice<NCH, NS, (TPR > 2 ? 2 * CPT : 0), (TPR > 2 ? 3 * CPT : 0)>(p, xr, acc);
-        rt_cats<NCH, NS, (TPR > 2 ? 2 : 0), TPR>(p, xr, s_wcat, acc);
+      // trailing chunks without a model input are not multiplied at all: the live chunks are split evenly over the row's
+      // threads (a uniform branch picks the fully unrolled version for 0, 2 or 4 skipped chunks)
+      if constexpr (LM == 2 && RPT == 1 && NCH >= 8 && (TPR == 1 || TPR == 2)) {  // (the tensor-map variants only: build time)
+        if (p.dead_tail >= 4) rt_row_slices<NCH, NS, TPR, NCH - 4>(p, q, xr, s_wcat, acc);
+        else if (p.dead_tail >= 2) rt_row_slices<NCH, NS, TPR, NCH - 2>(p, q, xr, s_wcat, acc);
+        else rt_row_slices<NCH, NS, TPR, NCH>(p, q, xr, s_wcat, acc);
       } else {
-        rt_slice<NCH, NS, (TPR > 3 ? 3 * CPT : 0), (TPR > 3 ? 4 * CPT : 0)>(p, xr, acc);
-        rt_cats<NCH, NS, (TPR > 3 ? 3 : 0), TPR>(p, xr, s_wcat, acc);
+        rt_row_slices<NCH, NS, TPR, NCH>(p, q, xr, s_wcat, acc);
       }
     }
     if (TPR > 1) {  // combine the row's slices in a fixed order (deterministic fp64 sum)

@@ -125,10 +125,12 @@ struct Slot {  // one in-flight batch of the coalescing ring
 };
 
 // Ensemble-merge communicator: ONE device allocation per rank, exported over CUDA IPC and mapped by every peer:
-//   [flags: 64 x uint32][CTA counter][timeout word][pad to kCommHeader = 512 B][merged rows, parity 0][merged rows, parity 1]
+//   [flags: 64 x uint32][CTA counter][timeout word][pad to kCommHeader = 512 B][merged rows, slot 0] .. [merged rows, slot 3]
 // (round 2's first version started the rows at byte 256 = word 64: the first vote of a step overwrote the counter)
-// merged rows = world x max_rows x out_cols 4-byte words; step e (epoch, 1-based) lands in parity e & 1.
+// merged rows = world x max_rows x out_cols 4-byte words; step e (epoch, 1-based) lands in slot e & 3.  Four slots let a
+// caller wait for step e - 1 after launching step e (b2s_comm_wait_lag): see DESIGN.md section 7 for why that is safe.
 constexpr size_t kCommHeader = 512;
+constexpr uint32_t kCommSlots = 4;
 struct b2s_comm_s {
   int rank = 0, world = 1, out_cols = 1;
   int64_t max_rows = 0;
@@ -138,7 +140,7 @@ struct b2s_comm_s {
   size_t bytes = 0;
   bool connected = false;
   size_t buf_bytes() const { return (size_t)world * max_rows * out_cols * 4; }
-  char* buf(int r, uint32_t e) const { return peer_base[r] + kCommHeader + (size_t)(e & 1u) * buf_bytes(); }
+  char* buf(int r, uint32_t e) const { return peer_base[r] + kCommHeader + (size_t)(e & (kCommSlots - 1u)) * buf_bytes(); }
   uint32_t* flags(int r) const { return reinterpret_cast<uint32_t*>(peer_base[r]); }
   uint32_t* counter() const { return reinterpret_cast<uint32_t*>(base) + 64; }
 };
@@ -412,6 +414,23 @@ static void rt_build(b2s_plan_s* p, const RTTables& t) {
     }
   r.n_cat_cols = ncc;
   r.n_cat = (int)t.cat_val->size();
+  r.cats_fast = 1;
+  for (int cc = 0; cc < ncc; ++cc) {
+    r.cats_fast = r.cats_fast && r.cat_dense[cc];
+    r.catf[cc].first = r.cat_first[cc];
+    r.catf[cc].cnt = r.cat_cnt[cc];
+    r.catf[cc].woff_b = r.cat_base[cc] * NS * 8;
+    r.catf[cc].fill = r.cat_fill[cc];
+  }
+  r.zero_woff_b = r.n_cat * NS * 8;
+  {
+    int last_live = -1;  // last chunk that holds a model-input column
+    for (int c = 0; c < t.n_in; ++c)
+      if (((*t.flags)[c] & COL_COPIED) != 0) last_live = c >> 2;
+    r.dead_tail = std::max(0, NCH - 1 - last_live);
+    if (last_live < 0 || getenv("B2S_RT_NOSKIP")) r.dead_tail = 0;  // (A/B runs)
+  }
+  if (getenv("B2S_RT_SLOWCATS")) r.cats_fast = 0;
   for (int i = 0; i < r.n_cat; ++i) r.cat_val[i] = (*t.cat_val)[i];
 }
 
@@ -516,6 +535,8 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
     const int col = r.cat_col[cc], ch = col >> 2;
     r.cat_off[cc] = mode == 2 ? (ch >> 3) * (tr * 32) + (col & 3) : col;
     r.cat_sw[cc] = mode == 2 ? (ch & 7) << 2 : 0;
+    r.catf[cc].off_b = r.cat_off[cc] * 4;
+    r.catf[cc].sw_b = r.cat_sw[cc] * 4;
   }
   if (mode == 2 && mma) {
     r.stages = p->rm_stages;
@@ -1706,13 +1727,14 @@ extern "C" int b2s_plan_finalize(b2s_plan_t p) {
         if (p->rt_smem <= smem_cap && rt_launch(p, nullptr, 0, 0, nullptr, nullptr, 0, nullptr, true, &occ) == cudaSuccess && occ >= 1) {
           p->rt_ok = true;
           p->rt_grid = sms * occ;
-          // DMMA variant (default where it applies; B2S_RT_MMA=0 keeps the DFMA kernel): 32 or 64 float32 columns, tensor-map loads
+          // DMMA variant, opt-in with B2S_RT_MMA=1 (measured slower than the DFMA kernel: profiles/r2_kernel_log.md): 32 or 64
+          // float32 columns, tensor-map loads
           const char* mma_env = getenv("B2S_RT_MMA");
-          if ((!mma_env || atoi(mma_env) != 0) && (p->rt_NCH == 8 || p->rt_NCH == 16) && n_in == p->rt_NCH * 4 && tensor_map_encoder()) {
+          if (mma_env && atoi(mma_env) != 0 && (p->rt_NCH == 8 || p->rt_NCH == 16) && n_in == p->rt_NCH * 4 && tensor_map_encoder()) {
             const char* we = getenv("B2S_RM_WARPS");
             const char* se = getenv("B2S_RM_STAGES");
-            p->rm_warps = we ? std::max(1, std::min(kRMMaxWarps, atoi(we))) : 8;
-            p->rm_stages = se ? std::max(2, std::min(kRMMaxStages, atoi(se))) : 3;
+            p->rm_warps = we ? std::max(1, std::min(kRMMaxWarps, atoi(we))) : 12;
+            p->rm_stages = se ? std::max(2, std::min(kRMMaxStages, atoi(se))) : 2;
             while (p->rm_warps > 1 && rowmma_smem_bytes(p->rt_NCH, NS, (int)cat_val.size(), p->rm_warps, p->rm_stages) > (size_t)smem_cap) --p->rm_warps;
             p->rm_smem = (int)rowmma_smem_bytes(p->rt_NCH, NS, (int)cat_val.size(), p->rm_warps, p->rm_stages);
             if (p->rm_smem <= smem_cap && rowmma_prepare(p->rt_NCH, NS, smem_cap) == cudaSuccess) p->rm_ok = true;
@@ -1897,7 +1919,7 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
   for (int g = 0; g < k.n_peers; ++g) k.peers[g] = (float*)p->peers[g];
   k.sig = MergeSig{};
   if (p->comm) {
-    // one more step of the attached communicator: this launch's votes go to parity (epoch & 1) of every rank's merged
+    // one more step of the attached communicator: this launch's votes go to slot (epoch & 3) of every rank's merged
     // rows, at this rank's row block; the launch's last CTA then publishes the epoch in every rank's flag array
     b2s_comm_s* c = p->comm;
     if (n_rows > c->max_rows) return fail(B2S_ERR_INVALID, "shard of %lld rows exceeds the communicator's %lld", (long long)n_rows, (long long)c->max_rows);
@@ -2819,7 +2841,7 @@ extern "C" int b2s_comm_create(int32_t rank, int32_t world, int64_t max_rows_per
     c->world = world;
     c->out_cols = out_cols;
     c->max_rows = (max_rows_per_rank + 3) / 4 * 4;  // row blocks start 16-byte aligned
-    c->bytes = kCommHeader + 2 * c->buf_bytes();
+    c->bytes = kCommHeader + kCommSlots * c->buf_bytes();
     CUDA_TRY(cudaSetDevice(G.device));
     CUDA_TRY(cudaMalloc(&c->base, c->bytes));
     CUDA_TRY(cudaMemset(c->base, 0, 512 < c->bytes ? 512 : c->bytes));
@@ -2877,12 +2899,39 @@ extern "C" int b2s_plan_attach_comm(b2s_plan_t p, b2s_comm_t c) {
   }
 }
 
+static int comm_wait_epoch(b2s_comm_t c, void* stream, uint32_t e, const void** d_merged, uint32_t* epoch_out);
+
 extern "C" int b2s_comm_wait(b2s_comm_t c, void* stream, const void** d_merged, uint32_t* epoch_out) {
   try {
     if (!c || !c->connected) return fail(B2S_ERR_STATE, "communicator is not connected");
+    if (c->epoch == 0) return fail(B2S_ERR_STATE, "no step has been launched on this communicator");
+    return comm_wait_epoch(c, stream, c->epoch, d_merged, epoch_out);
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
+}
+
+// Pipelined steps: wait for the step launched `lag` launches ago (lag 0 = b2s_comm_wait, lag 1 = the previous step, so that
+// the peers' stores and flags of step e travel while step e + 1 is being scored).  When fewer than lag + 1 steps have been
+// launched there is nothing to wait for: *d_merged = NULL, *epoch_out = 0.
+extern "C" int b2s_comm_wait_lag(b2s_comm_t c, void* stream, int32_t lag, const void** d_merged, uint32_t* epoch_out) {
+  try {
+    if (!c || !c->connected) return fail(B2S_ERR_STATE, "communicator is not connected");
+    if (lag < 0 || lag > 1) return fail(B2S_ERR_INVALID, "lag must be 0 or 1 (four response slots)");
+    if (c->epoch <= (uint32_t)lag) {
+      if (d_merged) *d_merged = nullptr;
+      if (epoch_out) *epoch_out = 0;
+      return B2S_OK;
+    }
+    return comm_wait_epoch(c, stream, c->epoch - (uint32_t)lag, d_merged, epoch_out);
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
+  }
+}
+
+static int comm_wait_epoch(b2s_comm_t c, void* stream, uint32_t e, const void** d_merged, uint32_t* epoch_out) {
+  {
     cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
-    const uint32_t e = c->epoch;
-    if (e == 0) return fail(B2S_ERR_STATE, "no step has been launched on this communicator");
     uint32_t* timeout_flag = reinterpret_cast<uint32_t*>(c->base) + 65;
     // how long a rank may lag behind before the step is declared dead (B2S_COMM_TIMEOUT_MS, default 10 s)
     static const long long timeout_ns = (getenv("B2S_COMM_TIMEOUT_MS") ? atoll(getenv("B2S_COMM_TIMEOUT_MS")) : 10000ll) * 1000000ll;
@@ -2893,8 +2942,6 @@ extern "C" int b2s_comm_wait(b2s_comm_t c, void* stream, const void** d_merged, 
     if (d_merged) *d_merged = c->buf(c->rank, e);
     if (epoch_out) *epoch_out = e;
     return B2S_OK;
-  } catch (const std::exception& e) {
-    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
 }
 

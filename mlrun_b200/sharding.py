@@ -36,7 +36,7 @@ def gather_votes(dist, local, n_rows, world):
 
 class MergeComm:
     """The ensemble-merge communicator of the C-ABI (include/b200serve.h, b2s_comm_*): one device allocation per rank --
-    completion flags + the merged response rows, double buffered -- mapped by every peer over CUDA IPC.
+    completion flags + the merged response rows in four slots -- mapped by every peer over CUDA IPC.
 
     `exchange(blob) -> [blob of rank 0, ..., blob of rank world-1]` is the only thing the bootstrap needs from the outside
     (64 bytes per rank): `torch.distributed.all_gather_object`, MPI, a shared file ...; `torch_exchange(dist)` wraps the
@@ -67,12 +67,14 @@ class MergeComm:
     def detach(self, plan):
         self._nat.check(self._lib.b2s_plan_attach_comm(plan._h, None))
 
-    def wait(self, stream=None):
-        """enqueue the completion wait of the step just launched -> (device pointer of the merged rows, epoch)"""
+    def wait(self, stream=None, lag=0):
+        """enqueue the completion wait of the step launched `lag` launches ago (0: the one just launched; 1: the one before,
+        so that a step's votes cross NVLink while the next step is scored) -> (device pointer of that step's merged rows,
+        epoch); (None, 0) while fewer than lag + 1 steps have been launched"""
         import ctypes as C
 
         ptr, epoch = C.c_void_p(), C.c_uint32()
-        self._nat.check(self._lib.b2s_comm_wait(self._h, stream, C.byref(ptr), C.byref(epoch)))
+        self._nat.check(self._lib.b2s_comm_wait_lag(self._h, stream, int(lag), C.byref(ptr), C.byref(epoch)))
         return ptr.value, epoch.value
 
     def check(self):
@@ -130,10 +132,16 @@ class ShardedGraphServer:
         """rank's shard inside a merged response"""
         return merged[rank * self.max_rows: rank * self.max_rows + n_rows]
 
-    def run_device(self, d_rows, n_rows, row_stride=None, stream=None):
-        """device-resident shard -> (device pointer of the merged rows of this step, epoch); asynchronous on `stream`"""
+    def run_device(self, d_rows, n_rows, row_stride=None, stream=None, lag=0):
+        """device-resident shard -> (device pointer of the merged rows, epoch); asynchronous on `stream`.
+        lag=0: the merged response of THIS step.  lag=1 (pipelined serving): the merged response of the PREVIOUS step
+        ((None, 0) on the first call) -- this step's votes travel while the next one is scored; `drain()` returns the last."""
         self.plan.run_device(d_rows, n_rows, row_stride or self.plan.n_in * 4, None, None, stream)
-        return self.comm.wait(stream)
+        return self.comm.wait(stream, lag)
+
+    def drain(self, stream=None):
+        """after lag=1 steps: the merged response of the last step launched"""
+        return self.comm.wait(stream, 0)
 
     def run_batch(self, X):
         """this rank's shard (B_r, F) float32 -> the merged (world * max_rows, out_cols) response of all ranks' shards"""

@@ -82,6 +82,34 @@ def check(server, names, batches, label):
             got = sharded.rows_of(merged, r, rhi - rlo)
             want = full[step % len(batches)][rlo:rhi]
             assert np.array_equal(got, want), (label, step, rank, r, np.abs(got.astype(np.float64) - want).max())
+    # pipelined steps (lag 1): three launches back to back, each followed by the wait for the launch BEFORE it, then the
+    # drain; nothing synchronises in between, so step e's votes and flags cross NVLink while e + 1 is scored.  The four
+    # response slots keep all three responses intact until they are read; four groups walk every slot three times.
+    d_in = [nat.DeviceBuffer(sharded.max_rows * sharded.plan.n_in * 4) for _ in range(3)]
+    seq = batches * 6
+    for g0 in range(0, len(seq), 3):
+        group = seq[g0:g0 + 3]
+        for j, X in enumerate(group):
+            lo, hi = shard_bounds(len(X), rank, world)
+            d_in[j].upload(np.ascontiguousarray(X[lo:hi]))
+        ptrs = []
+        for j, X in enumerate(group):
+            lo, hi = shard_bounds(len(X), rank, world)
+            ptr, epoch = sharded.run_device(d_in[j].ptr, hi - lo, lag=1)
+            assert (ptr is None) == (g0 == 0 and j == 0), (g0, j, ptr)
+            if j > 0:
+                ptrs.append(ptr)
+        ptrs.append(sharded.drain()[0])
+        nat.check(nat.load().b2s_device_sync())
+        sharded.comm.check()
+        for j, X in enumerate(group):
+            merged = np.empty((world * sharded.max_rows, sharded.plan.out_cols), dtype=sharded.plan.out_dtype)
+            nat.check(nat.load().b2s_memcpy_d2h(merged.ctypes.data, ptrs[j], merged.nbytes))
+            for r in range(world):
+                rlo, rhi = shard_bounds(len(X), r, world)
+                got = sharded.rows_of(merged, r, rhi - rlo)
+                want = full[(g0 + j) % len(batches)][rlo:rhi]
+                assert np.array_equal(got, want), (label, "lag1", g0 + j, rank, r)
     sharded.close()
     dist.barrier()
     print("rank", rank, label, "ok")
