@@ -494,7 +494,9 @@ __global__ void __launch_bounds__(128 * TPR / RPT, RPT == 2 ? RT_R2_MINB : (TPR 
       }
     }
     const float* tile = s_tiles + stage * tile_words;
-    const bool any_live = t * TR + r < p.n_rows;  // rows past the end were zero-filled (TMA) or are skipped
+    const int64_t row0 = t * TR;                                                       // uniform
+    const int live_rows = (int)(p.n_rows - row0 < (int64_t)TR ? p.n_rows - row0 : (int64_t)TR);  // uniform: rows of this tile
+    const bool any_live = r < live_rows;  // rows past the end were zero-filled (TMA) or are skipped
     using Row = typename std::conditional<LM == 2, RowSwizzled, RowPadded>::type;
     Row xr[RPT];
 #pragma unroll
@@ -549,8 +551,8 @@ __global__ void __launch_bounds__(128 * TPR / RPT, RPT == 2 ? RT_R2_MINB : (TPR 
     }
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
-      const int64_t row = t * TR + r + i * TRT;
-      if (q == 0 && row < p.n_rows) {
+      const int64_t row = row0 + (r + i * TRT);
+      if (q == 0 && r + i * TRT < live_rows) {
         uint32_t st = 0;
 #pragma unroll
         for (int k = 0; k < NS; ++k) {

@@ -528,7 +528,7 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)p->rt_grid * grid_mul, tiles));
   r.use_bulk = mode;
   {
-    static const int one_sync = getenv("B2S_RT_ONESYNC") ? atoi(getenv("B2S_RT_ONESYNC")) : 0;
+    static const int one_sync = getenv("B2S_RT_ONESYNC") ? atoi(getenv("B2S_RT_ONESYNC")) : 1;  // r2o: 0.0506 vs 0.0512 ms
     r.one_sync = one_sync;
   }
   for (int cc = 0; cc < r.n_cat_cols; ++cc) {  // tile-relative position of each categorical column
@@ -1936,6 +1936,14 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
       k.peers[g] = (float*)c->buf(r, e);
       k.sig.flags[g] = c->flags(r);
     }
+    // lab switches (profiles/lab/comm_lab.py): which part of a merged step costs what.  Results are NOT merged with them.
+    static const int lab_selfonly = getenv("B2S_LAB_COMM_SELFONLY") ? atoi(getenv("B2S_LAB_COMM_SELFONLY")) : 0;
+    static const int lab_nosignal = getenv("B2S_LAB_COMM_NOSIGNAL") ? atoi(getenv("B2S_LAB_COMM_NOSIGNAL")) : 0;
+    if (lab_selfonly) {
+      k.n_peers = 1;
+      k.peers[0] = (float*)c->buf(c->rank, e);
+    }
+    if (lab_nosignal) k.sig.n = 0;
   }
   if (p->t3_ok) {
     const int C = p->t3_cols;
@@ -2935,7 +2943,8 @@ static int comm_wait_epoch(b2s_comm_t c, void* stream, uint32_t e, const void** 
     uint32_t* timeout_flag = reinterpret_cast<uint32_t*>(c->base) + 65;
     // how long a rank may lag behind before the step is declared dead (B2S_COMM_TIMEOUT_MS, default 10 s)
     static const long long timeout_ns = (getenv("B2S_COMM_TIMEOUT_MS") ? atoll(getenv("B2S_COMM_TIMEOUT_MS")) : 10000ll) * 1000000ll;
-    merge_wait_kernel<<<1, 32, 0, st>>>(c->flags(c->rank), c->world, e, timeout_flag, timeout_ns);
+    static const int lab_nowait = getenv("B2S_LAB_COMM_NOWAIT") ? atoi(getenv("B2S_LAB_COMM_NOWAIT")) : 0;  // lab: no wait kernel
+    if (!lab_nowait) merge_wait_kernel<<<1, 32, 0, st>>>(c->flags(c->rank), c->world, e, timeout_flag, timeout_ns);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(B2S_ERR_CUDA, "merge wait launch failed: %s", cudaGetErrorString(err));
     G.launches.fetch_add(1, std::memory_order_relaxed);

@@ -19,8 +19,10 @@ except Exception as e: print('$name parse failed', e)
 PY
 }
 run weak2 --no-configs
+run weak2_lag0 --no-configs --merge-lag 0
 run weak2_nccl --no-configs --merge nccl
 run strong2_router8 --workload router8 --scaling strong --batch 65536 --no-configs
+run strong2_router8_lag0 --workload router8 --scaling strong --batch 65536 --no-configs --merge-lag 0
 run ingest2 --workload ingest6 --no-configs
 (timeout 300 python bench.py --steps 20 --warmup 3 --no-configs --no-cpu-baseline) > gpurun_out/$OUT/one.json 2> gpurun_out/$OUT/one.err
 (timeout 300 python bench.py --steps 20 --warmup 3 --no-configs --no-cpu-baseline --workload router8 --batch 65536) > gpurun_out/$OUT/one_router8.json 2> gpurun_out/$OUT/one_router8.err
