@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = --batch events per GPU; strong = --batch events in total, split over the GPUs "
                          "(BASELINE configs[3]: --workload router8 --scaling strong --batch 65536)")
+    ap.add_argument("--merge-wait", default="fused", choices=["fused", "kernel"],
+                    help="p2p merge: fused = the scoring launch's last CTA waits for the completion flags itself; kernel = a "
+                         "one-warp wait kernel after every launch")
     ap.add_argument("--merge-lag", type=int, default=1, choices=[0, 1],
                     help="p2p merge: 0 = every launch waits for its own completion flags (lockstep); 1 = it waits for the "
                          "previous launch's (pipelined: the merged response of a batch is complete one launch later)")
@@ -537,6 +540,7 @@ def main():
 
         try:
             comm = MergeComm(rank, world, B, plan.out_cols, torch_exchange(dist))
+            comm.set_fused_wait(args.merge_lag if args.merge_wait == "fused" else None)
             comm.attach(plan)
         except Exception as exc:  # noqa: BLE001 -- no peer access on this box: use the NCCL merge
             print(f"[rank {rank}] p2p merge unavailable ({exc}); using nccl", file=sys.stderr)
@@ -710,7 +714,7 @@ def main():
                        "launches_per_step": inner, "events_per_step_per_gpu": B * inner, "timed_region_ms": ms,
                        "parallelism": f"event-sharded x{world}" + {"none": "", "nccl": " + NCCL all-gather of votes per step",
                                                                     "p2p": " + fused P2P ensemble-merge (votes stored to every rank over NVLink "
-                                                                           "from the kernel epilogue, completion flags awaited on the device "
+                                                                           "from the kernel epilogue, completion flags awaited " + ("by the launch's last CTA " if args.merge_wait == "fused" else "by a wait kernel ")
                                                                            + ("each launch)" if args.merge_lag == 0 else "one launch later: pipelined, lag 1)")}[merge],
                        "merge_verified": merge_check,
                        "l2": f"{nbuf} rotating input buffers of {B * row_bytes / 1e6:.0f} MB (> 126 MB L2 between re-reads)",

@@ -90,6 +90,7 @@ SIGNATURES = {
     "b2s_plan_attach_comm": (C.c_int, [_vp, _vp]),
     "b2s_comm_wait": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.POINTER(C.c_uint32)]),
     "b2s_comm_wait_lag": (C.c_int, [_vp, _vp, C.c_int32, C.POINTER(_vp), C.POINTER(C.c_uint32)]),
+    "b2s_comm_set_fused_wait": (C.c_int, [_vp, C.c_int32]),
     "b2s_comm_check": (C.c_int, [_vp]),
     "b2s_comm_destroy": (C.c_int, [_vp]),
     "b2s_ipc_export": (C.c_int, [_vp, _vp]),

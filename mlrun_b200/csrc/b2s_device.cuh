@@ -61,20 +61,47 @@ struct MergeSig {
   int32_t n;           // 0: no signal
   int32_t rank;
   uint32_t epoch;
-  int32_t pad;
+  // fused wait (b2s_comm_set_fused_wait): after publishing, the launch's last CTA also acquires THIS rank's n flags until they
+  // show wait_epoch (epoch, or epoch - 1 for pipelined steps), so that what follows the kernel on its stream reads a
+  // complete response without a separate wait kernel.  0 = no fused wait.
+  uint32_t wait_epoch;
+  const uint32_t* wait_flags;
+  uint32_t* timeout_flag;
+  long long timeout_ns;
 };
 
 __device__ __forceinline__ void merge_signal(const MergeSig& m) {
   if (m.n <= 0) return;
-  __threadfence_system();  // this thread's remote stores are performed before what follows
+  // every thread's vote stores -> CTA barrier -> ONE system-scope fence by thread 0 (fences are cumulative: the stores thread 0
+  // has observed through the barrier are ordered before everything it writes after the fence).  The fence waits for the CTA's
+  // peer stores to be acknowledged: about one NVLink round trip at the tail of the launch (profiles/r2_kernel_log.md, r2p/r2r).
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned prev = atomicAdd(m.counter, 1u);
     if (prev == gridDim.x - 1) {  // every other CTA has fenced its stores and counted itself
       *m.counter = 0;             // launches of a plan are stream ordered: the next one finds a clean counter
       __threadfence_system();
       for (int g = 0; g < m.n; ++g)
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(m.flags[g] + m.rank), "r"(m.epoch) : "memory");
+      if (m.wait_epoch) {  // fused wait: every source rank's flag of step wait_epoch (or a later one)
+        long long t0 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int g = 0; g < m.n; ++g) {
+          for (;;) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(m.wait_flags + g) : "memory");
+            if ((int32_t)(v - m.wait_epoch) >= 0) break;
+            long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > m.timeout_ns) {  // a peer died: give up instead of hanging the GPU; b2s_comm_check reports it
+              atomicExch(m.timeout_flag, 1u + (uint32_t)g);
+              break;
+            }
+            __nanosleep(100);
+          }
+        }
+      }
     }
   }
 }

@@ -137,6 +137,8 @@ struct b2s_comm_s {
   char* base = nullptr;            // this rank's allocation
   std::vector<char*> peer_base;    // [world] every rank's allocation as mapped here (peer_base[rank] == base)
   uint32_t epoch = 0;              // launches signalled so far
+  int fused_lag = -1;              // b2s_comm_set_fused_wait: -1 off, 0 / 1: the launches wait in their own last CTA
+  uint32_t fused_epoch = 0;        // highest step a launched kernel already waits for (0: none)
   size_t bytes = 0;
   bool connected = false;
   size_t buf_bytes() const { return (size_t)world * max_rows * out_cols * 4; }
@@ -330,6 +332,19 @@ static EncodeTiledFn tensor_map_encoder() {
       sym = nullptr;
     }
     return reinterpret_cast<EncodeTiledFn>(sym);
+  }();
+  return fn;
+}
+typedef CUresult (*BatchMemOpFn)(CUstream, unsigned int, CUstreamBatchMemOpParams*, unsigned int);
+static BatchMemOpFn stream_batch_memop() {
+  static BatchMemOpFn fn = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamBatchMemOp", &sym, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      sym = nullptr;
+    }
+    return reinterpret_cast<BatchMemOpFn>(sym);
   }();
   return fn;
 }
@@ -1936,6 +1951,14 @@ static int launch_on(b2s_plan_t p, const void* d_rows, int64_t n_rows, int64_t s
       k.peers[g] = (float*)c->buf(r, e);
       k.sig.flags[g] = c->flags(r);
     }
+    if (c->fused_lag >= 0 && e > (uint32_t)c->fused_lag) {
+      static const long long fused_timeout_ns = (getenv("B2S_COMM_TIMEOUT_MS") ? atoll(getenv("B2S_COMM_TIMEOUT_MS")) : 10000ll) * 1000000ll;
+      k.sig.wait_epoch = e - (uint32_t)c->fused_lag;
+      k.sig.wait_flags = c->flags(c->rank);
+      k.sig.timeout_flag = reinterpret_cast<uint32_t*>(c->base) + 65;
+      k.sig.timeout_ns = fused_timeout_ns;
+      c->fused_epoch = k.sig.wait_epoch;
+    }
     // lab switches (profiles/lab/comm_lab.py): which part of a merged step costs what.  Results are NOT merged with them.
     static const int lab_selfonly = getenv("B2S_LAB_COMM_SELFONLY") ? atoi(getenv("B2S_LAB_COMM_SELFONLY")) : 0;
     static const int lab_nosignal = getenv("B2S_LAB_COMM_NOSIGNAL") ? atoi(getenv("B2S_LAB_COMM_NOSIGNAL")) : 0;
@@ -2940,17 +2963,55 @@ extern "C" int b2s_comm_wait_lag(b2s_comm_t c, void* stream, int32_t lag, const 
 static int comm_wait_epoch(b2s_comm_t c, void* stream, uint32_t e, const void** d_merged, uint32_t* epoch_out) {
   {
     cudaStream_t st = stream ? (cudaStream_t)stream : G.stream;
+    if (c->fused_epoch && (int32_t)(c->fused_epoch - e) >= 0) {  // the last launch's own last CTA waits for this step already
+      if (d_merged) *d_merged = c->buf(c->rank, e);
+      if (epoch_out) *epoch_out = e;
+      return B2S_OK;
+    }
     uint32_t* timeout_flag = reinterpret_cast<uint32_t*>(c->base) + 65;
     // how long a rank may lag behind before the step is declared dead (B2S_COMM_TIMEOUT_MS, default 10 s)
     static const long long timeout_ns = (getenv("B2S_COMM_TIMEOUT_MS") ? atoll(getenv("B2S_COMM_TIMEOUT_MS")) : 10000ll) * 1000000ll;
-    static const int lab_nowait = getenv("B2S_LAB_COMM_NOWAIT") ? atoi(getenv("B2S_LAB_COMM_NOWAIT")) : 0;  // lab: no wait kernel
-    if (!lab_nowait) merge_wait_kernel<<<1, 32, 0, st>>>(c->flags(c->rank), c->world, e, timeout_flag, timeout_ns);
+    static const int lab_nowait = getenv("B2S_LAB_COMM_NOWAIT") ? atoi(getenv("B2S_LAB_COMM_NOWAIT")) : 0;  // lab: no wait at all
+    // A one-warp polling kernel (gives up after B2S_COMM_TIMEOUT_MS).  B2S_COMM_WAIT=memop: stream memory operations instead
+    // (cuStreamBatchMemOp, one WAIT_VALUE_32 >= e per source rank; no kernel, no timeout) -- measured SLOWER than the kernel
+    // (0.0641 vs 0.0601 ms per merged step, r2r), kept for A/B runs.  The cheap form is the fused wait (b2s_comm_set_fused_wait).
+    static const bool want_memop = getenv("B2S_COMM_WAIT") && std::string(getenv("B2S_COMM_WAIT")) == "memop";
+    BatchMemOpFn memop = want_memop ? stream_batch_memop() : nullptr;
+    if (lab_nowait) {
+    } else if (memop) {
+      CUstreamBatchMemOpParams ops[8];
+      memset(ops, 0, sizeof(ops));
+      for (int g = 0; g < c->world; ++g) {
+        ops[g].waitValue.operation = CU_STREAM_MEM_OP_WAIT_VALUE_32;
+        ops[g].waitValue.address = (CUdeviceptr)(uintptr_t)(c->flags(c->rank) + g);
+        ops[g].waitValue.value = e;
+        ops[g].waitValue.flags = CU_STREAM_WAIT_VALUE_GEQ;  // (int32)(*addr - e) >= 0: wrap-safe like the kernel's test
+      }
+      const CUresult r = memop((CUstream)st, (unsigned)c->world, ops, 0);
+      if (r != CUDA_SUCCESS) return fail(B2S_ERR_CUDA, "cuStreamBatchMemOp (merge wait) failed: %d", (int)r);
+    } else {
+      merge_wait_kernel<<<1, 32, 0, st>>>(c->flags(c->rank), c->world, e, timeout_flag, timeout_ns);
+    }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(B2S_ERR_CUDA, "merge wait launch failed: %s", cudaGetErrorString(err));
     G.launches.fetch_add(1, std::memory_order_relaxed);
     if (d_merged) *d_merged = c->buf(c->rank, e);
     if (epoch_out) *epoch_out = e;
     return B2S_OK;
+  }
+}
+
+// Fused wait: lag = 0 / 1 makes every launch of an attached plan end by waiting (in its last CTA) for the flags of its own
+// step / of the previous step; b2s_comm_wait / b2s_comm_wait_lag then launch nothing for steps that are covered.  lag = -1: off.
+extern "C" int b2s_comm_set_fused_wait(b2s_comm_t c, int32_t lag) {
+  try {
+    if (!c) return fail(B2S_ERR_INVALID, "null communicator");
+    if (lag < -1 || lag > 1) return fail(B2S_ERR_INVALID, "fused wait lag must be -1 (off), 0 or 1");
+    c->fused_lag = lag;
+    c->fused_epoch = 0;
+    return B2S_OK;
+  } catch (const std::exception& e) {
+    return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
   }
 }
 
@@ -3014,7 +3075,12 @@ extern "C" int b2s_device_free(void* p) {
 }
 extern "C" int b2s_memcpy_h2d(void* d, const void* h, size_t bytes) {
   try {  // no C++ exception crosses the C boundary
-    CUDA_TRY(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
+    // on the library stream and awaited: cudaMemcpy from pageable memory may return while the DMA is still in flight, and the
+    // (non-blocking) library stream that launches the kernels is not ordered behind the legacy stream -- a kernel launched
+    // right after the call read the tail of the previous batch (found by the 2-GPU test of ShardedGraphServer, r2n)
+    cudaStream_t st = G.inited ? G.stream : (cudaStream_t)0;
+    CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return B2S_OK;
   } catch (const std::exception& e) {
     return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());
@@ -3022,7 +3088,9 @@ extern "C" int b2s_memcpy_h2d(void* d, const void* h, size_t bytes) {
 }
 extern "C" int b2s_memcpy_d2h(void* h, const void* d, size_t bytes) {
   try {  // no C++ exception crosses the C boundary
-    CUDA_TRY(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
+    cudaStream_t st = G.inited ? G.stream : (cudaStream_t)0;  // ordered behind the kernels of the library stream
+    CUDA_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return B2S_OK;
   } catch (const std::exception& e) {
     return fail(B2S_ERR_INVALID, "%s: %s", __func__, e.what());

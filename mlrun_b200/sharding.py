@@ -60,6 +60,11 @@ class MergeComm:
                 raise ValueError("exchange() must return one 64-byte handle per rank, in rank order")
             nat.check(self._lib.b2s_comm_connect(self._h, C.create_string_buffer(b"".join(blobs), 64 * self.world)))
 
+    def set_fused_wait(self, lag):
+        """lag 0 / 1: every launch ends by waiting (in its own last CTA) for its own / the previous step's flags -- `wait`
+        then enqueues nothing for a covered step; None: off (a one-warp wait kernel per `wait`)"""
+        self._nat.check(self._lib.b2s_comm_set_fused_wait(self._h, -1 if lag is None else int(lag)))
+
     def attach(self, plan):
         self._nat.check(self._lib.b2s_plan_attach_comm(plan._h, self._h))
         return plan
@@ -117,13 +122,16 @@ class ShardedGraphServer:
 
     Every rank must call run_batch the same number of times (a step is collective in the sense that its flags are awaited)."""
 
-    def __init__(self, server, rank, world, max_rows_per_rank, exchange, names=None):
+    def __init__(self, server, rank, world, max_rows_per_rank, exchange, names=None, fused_wait=0):
+        """fused_wait: 0 (default) -- every launch waits for its own step's flags in its last CTA (`run_batch` / `run_device`
+        with lag 0 then need no wait kernel); 1 -- for the previous step's (pipelined callers: `run_device(lag=1)`); None -- off"""
         from . import _native as nat
 
         self.server, self.rank, self.world = server, int(rank), int(world)
         self.plan = server.compile(names).plan
         self.comm = MergeComm(rank, world, max_rows_per_rank, self.plan.out_cols, exchange)
         self.max_rows = self.comm.max_rows
+        self.comm.set_fused_wait(fused_wait)
         self.comm.attach(self.plan)
         self._nat = nat
         self._d_in = nat.DeviceBuffer(self.max_rows * self.plan.n_in * 4)
