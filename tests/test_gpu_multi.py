@@ -39,7 +39,8 @@ got = merged.download(np.float32, (len(wl.X), plan.out_cols))
 assert np.array_equal(got, full_ref), (rank, np.abs(got - full_ref).max())
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "merge ok")
+sys.stdout.write(f"[merge ok on rank {rank}]\n")
+sys.stdout.flush()
 '''
 
 
@@ -55,7 +56,7 @@ def test_fused_p2p_merge_two_gpus(tmp_path):
          "--master-port", "29621", str(script)],
         capture_output=True, text=True, env=dict(os.environ, REPO_ROOT=ROOT), timeout=300)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("merge ok") == 2
+    assert "[merge ok on rank 0]" in out.stdout and "[merge ok on rank 1]" in out.stdout, out.stdout[-2000:]
 
 
 _SHARDED = r'''
@@ -76,7 +77,8 @@ def check(server, names, batches, label):
     for fused in (0, 1, None):      # the three ways of waiting: launch's last CTA (own step / previous step), wait kernel
         check_one(server, names, batches, label, full, max_rows, fused)
     dist.barrier()
-    print("rank", rank, label, "ok")
+    sys.stdout.write(f"[{label} ok on rank {rank}]\n")  # one write per rank: the ranks share the pipe
+    sys.stdout.flush()
 
 
 def check_one(server, names, batches, label, full, max_rows, fused):
@@ -156,4 +158,6 @@ def test_sharded_graph_server_with_completion_flags(tmp_path):
          "--master-port", "29622", str(script)],
         capture_output=True, text=True, env=dict(os.environ, REPO_ROOT=ROOT), timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("flow3 ok") == 2 and out.stdout.count("router8 ok") == 2
+    for label in ("flow3", "router8"):
+        for r in range(2):
+            assert f"[{label} ok on rank {r}]" in out.stdout, out.stdout[-2000:]
