@@ -543,8 +543,10 @@ static cudaError_t rt_launch_tt(b2s_plan_s* p, const void* rows, int64_t stride,
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)p->rt_grid * grid_mul, tiles));
   r.use_bulk = mode;
   {
-    static const int one_sync = getenv("B2S_RT_ONESYNC") ? atoi(getenv("B2S_RT_ONESYNC")) : 1;  // r2o: 0.0506 vs 0.0512 ms
-    r.one_sync = one_sync;
+    // single-barrier tile loop: measured better with 4 score columns (0.0506 vs 0.0512 ms, r2o) and worse with one
+    // (0.0481 vs 0.0454 ms, r2q / r2o): the default follows the number of score columns
+    static const int one_sync = getenv("B2S_RT_ONESYNC") ? atoi(getenv("B2S_RT_ONESYNC")) : -1;
+    r.one_sync = one_sync >= 0 ? one_sync : (NS >= 4 ? 1 : 0);
   }
   for (int cc = 0; cc < r.n_cat_cols; ++cc) {  // tile-relative position of each categorical column
     const int col = r.cat_col[cc], ch = col >> 2;
