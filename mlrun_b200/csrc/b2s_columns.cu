@@ -360,7 +360,9 @@ extern "C" int b2s_cols_run_host(b2s_cols_t c, const void* const* h_in_slots, in
           int prev = s, t = s + wd;
           while (two_d && t < n_slots && words_of(t) == wd) {
             const ptrdiff_t d = (const char*)host_of(t) - (const char*)host_of(prev);
-            if (d < (ptrdiff_t)(chunk * r.w) || (r.count > 1 && (size_t)d != r.hpitch)) break;
+            if (d < (ptrdiff_t)(chunk * r.w) || d > (ptrdiff_t)0x7fffffff || r.dpitch > (size_t)0x7fffffff ||  // (pitch limit of 2-D copies)
+                (r.count > 1 && (size_t)d != r.hpitch))
+              break;
             r.hpitch = (size_t)d;
             ++r.count;
             prev = t;
@@ -376,9 +378,12 @@ extern "C" int b2s_cols_run_host(b2s_cols_t c, const void* const* h_in_slots, in
       const std::vector<Run> out_runs = find_runs((int)n_out, [&](int s) { return (int)c->out_words[s]; }, [&](int s) { return (const void*)h_out_slots[s]; });
       for (int k = 0; k < n_chunks; ++k) {
         const int64_t r0 = (int64_t)k * chunk, nr = std::min<int64_t>(chunk, n_rows - r0);
-        for (const Run& r : in_runs)
-          COL_TRY(cudaMemcpy2DAsync(c->d_in + (size_t)r.s0 * stride + (size_t)r0 * r.w, r.dpitch, (const char*)h_in_slots[r.s0] + (size_t)r0 * r.w,
-                                    r.hpitch, (size_t)nr * r.w, (size_t)r.count, cudaMemcpyHostToDevice, cs));
+        for (const Run& r : in_runs) {
+          char* dst = c->d_in + (size_t)r.s0 * stride + (size_t)r0 * r.w;
+          const char* src = (const char*)h_in_slots[r.s0] + (size_t)r0 * r.w;
+          if (r.count == 1) COL_TRY(cudaMemcpyAsync(dst, src, (size_t)nr * r.w, cudaMemcpyHostToDevice, cs));
+          else COL_TRY(cudaMemcpy2DAsync(dst, r.dpitch, src, r.hpitch, (size_t)nr * r.w, (size_t)r.count, cudaMemcpyHostToDevice, cs));
+        }
         COL_TRY(cudaEventRecord(c->chunk_ev[k], cs));
         COL_TRY(cudaStreamWaitEvent(st, c->chunk_ev[k], 0));
         if (int rc = launch_cols(c, c->d_in, stride, nr, c->d_out, stride, c->d_cnt, st, r0)) {
@@ -386,9 +391,12 @@ extern "C" int b2s_cols_run_host(b2s_cols_t c, const void* const* h_in_slots, in
           cudaStreamSynchronize(st);
           return rc;
         }
-        for (const Run& r : out_runs)
-          COL_TRY(cudaMemcpy2DAsync((char*)h_out_slots[r.s0] + (size_t)r0 * r.w, r.hpitch, c->d_out + (size_t)r.s0 * stride + (size_t)r0 * r.w,
-                                    r.dpitch, (size_t)nr * r.w, (size_t)r.count, cudaMemcpyDeviceToHost, st));
+        for (const Run& r : out_runs) {
+          char* dst = (char*)h_out_slots[r.s0] + (size_t)r0 * r.w;
+          const char* src = c->d_out + (size_t)r.s0 * stride + (size_t)r0 * r.w;
+          if (r.count == 1) COL_TRY(cudaMemcpyAsync(dst, src, (size_t)nr * r.w, cudaMemcpyDeviceToHost, st));
+          else COL_TRY(cudaMemcpy2DAsync(dst, r.hpitch, src, r.dpitch, (size_t)nr * r.w, (size_t)r.count, cudaMemcpyDeviceToHost, st));
+        }
       }
       if (c->n_counters) COL_TRY(cudaMemcpyAsync(counters, c->d_cnt, c->n_counters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       COL_TRY(cudaEventRecord(c->ev[3], st));
