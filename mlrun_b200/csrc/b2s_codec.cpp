@@ -9,13 +9,22 @@
 //     rounded to float32 -- the same two roundings as np.asarray(json.loads(body)["inputs"], dtype=float32);
 //   * floats are printed with the shortest round-trip digits (std::to_chars) laid out by Python's repr rule
 //     (fixed notation for 1e-4 <= |x| < 1e16, else d.ddde+XX), so the text is byte-identical to json.dumps.
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
 #include <charconv>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <exception>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <limits>
+#include <mutex>
+#include <pthread.h>
 #include <sched.h>
 #include <thread>
 #include <vector>
@@ -99,9 +108,137 @@ bool skip_value(Cur& c, int depth) {
   return c.p > s;
 }
 
+// ---- fast path for ordinary decimal numbers -------------------------------------------------------------------------------
+// One pass over the token collects its digits (at most 19 after leading zeros) in a uint64 (w) and the decimal exponent (e10),
+// checking the JSON number grammar on the way; value = w * 10^e10.  For |e10| <= 27 both w (< 2^64) and 10^|e10| (5^27 < 2^63) are exact in the
+// x87 80-bit format, so ONE multiplication or division there is the correctly rounded 64-bit significand of the exact value.
+// Rounding that to double is the correctly rounded double (what json.loads / float() produce) unless the 64-bit result sits
+// exactly on a double's rounding boundary (low 11 bits == 0x400): rounding to 64 bits is monotonic and the boundary itself is
+// a 64-bit number, so the exact value can only be on the other side of a boundary the result does not touch.  Those tokens
+// (1 in 2048), longer digit strings, larger exponents, literals and everything malformed go to the general path below, which
+// also decides every error.  Integers of up to 19 digits are converted by the uint64 -> double instruction (one rounding).
+#if defined(__x86_64__) && LDBL_MANT_DIG == 64
+#define B2S_CODEC_FAST 1
+const long double kPow10[28] = {1e0L,  1e1L,  1e2L,  1e3L,  1e4L,  1e5L,  1e6L,  1e7L,  1e8L,  1e9L,  1e10L, 1e11L, 1e12L, 1e13L,
+                                1e14L, 1e15L, 1e16L, 1e17L, 1e18L, 1e19L, 1e20L, 1e21L, 1e22L, 1e23L, 1e24L, 1e25L, 1e26L, 1e27L};
+
+bool x87_is_extended() {  // the precision-control field of this thread's x87 unit (Linux default: 64-bit significands)
+  volatile long double a = 1.0L, b = 0x1p-63L;
+  volatile long double c = a + b;
+  return c != a;
+}
+
+const uint64_t kPow10u[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull,
+                             10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull, 100000000000000ull,
+                             1000000000000000ull, 10000000000000000ull, 100000000000000000ull, 1000000000000000000ull,
+                             10000000000000000000ull};
+
+// Appends the run of decimal digits at p to w (w = w * 10^n + digits), eight bytes at a time: the number of leading digit
+// bytes of a chunk comes from one SWAR test + count-trailing-zeros, the digits are shifted to the end of an eight-digit
+// field (zeros in front) and converted by three multiplications -- no per-digit branch to mispredict.  Returns the end of
+// the run, or nullptr when w would pass 19 digits.
+inline const char* append_digits(const char* p, const char* end, uint64_t& w) {
+  while (end - p >= 8) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    uint64_t x = v ^ 0x3030303030303030ull;  // digit bytes become 0..9
+    // bit 7 of a byte is set when the byte is > 9 (a carry out of such a byte can only disturb LATER bytes)
+    const uint64_t stop = ((x + 0x7676767676767676ull) | x) & 0x8080808080808080ull;
+    const int n = stop ? (__builtin_ctzll(stop) >> 3) : 8;
+    if (w >= kPow10u[19 - n]) return n ? nullptr : p;
+    const int sh = (8 - n) * 4;
+    x = (x << sh) << sh;  // first digit in the low byte: the n digits move to the last n places
+    x = (x * 10) + (x >> 8);
+    const uint64_t mask = 0x000000FF000000FFull;
+    const uint64_t val = (((x & mask) * 0x000F424000000064ull) + (((x >> 16) & mask) * 0x0000271000000001ull)) >> 32;
+    w = w * kPow10u[n] + val;
+    p += n;
+    if (n < 8) return p;
+  }
+  unsigned d;
+  while (p < end && (d = (unsigned char)*p - '0') <= 9) {  // the last bytes of the buffer (or of a row)
+    if (w >= kPow10u[18]) return nullptr;
+    w = w * 10 + d;
+    ++p;
+  }
+  return p;
+}
+
+// 1: *out set, c.p moved past the token; 0: not taken (c.p unchanged)
+inline int parse_number_fast(Cur& c, float* out) {
+  static const bool ok = x87_is_extended();
+  if (!ok) return 0;
+  const char* p = c.p;
+  const char* const end = c.end;
+  if (p >= end) return 0;
+  const uint64_t neg = *p == '-';
+  p += neg;
+  uint64_t w = 0;
+  const char* const i0 = p;
+  p = append_digits(p, end, w);
+  if (!p || p == i0) return 0;                  // too long / not a digit (literals, garbage)
+  if (*i0 == '0' && p - i0 > 1) return 0;       // leading zero
+  long e10 = 0;
+  bool integral = true;
+  if (p < end && *p == '.') {
+    integral = false;
+    const char* const f0 = ++p;
+    p = append_digits(p, end, w);
+    if (!p || p == f0) return 0;                // too long / "5."
+    e10 = -(long)(p - f0);
+  }
+  if (p < end && (*p == 'e' || *p == 'E')) {
+    integral = false;
+    ++p;
+    bool eneg = false;
+    if (p < end && (*p == '+' || *p == '-')) {
+      eneg = *p == '-';
+      ++p;
+    }
+    const char* x0 = p;
+    long ex = 0;
+    unsigned d;
+    while (p < end && (d = (unsigned char)*p - '0') <= 9) {
+      if (ex > 9999) return 0;
+      ex = ex * 10 + d;
+      ++p;
+    }
+    if (p == x0) return 0;
+    e10 += eneg ? -ex : ex;
+  }
+  double v;
+  uint64_t sign = neg << 63;
+  if (integral) {
+    v = (double)w;
+    if (w == 0) sign = 0;  // "-0" is the int 0
+  } else if (w == 0) {
+    v = 0.0;
+  } else {
+    if (e10 < -27 || e10 > 27) return 0;
+    const long double y = e10 < 0 ? (long double)w / kPow10[-e10] : (long double)w * kPow10[e10];
+    uint64_t m;
+    memcpy(&m, &y, 8);
+    if ((m & 0x7FFull) == 0x400ull) return 0;  // on a double's rounding boundary: let the exact converter decide
+    v = (double)y;
+  }
+  uint64_t bits;
+  memcpy(&bits, &v, 8);
+  bits |= sign;
+  memcpy(&v, &bits, 8);
+  *out = (float)v;
+  c.p = p;
+  return 1;
+}
+#else
+#define B2S_CODEC_FAST 0
+#endif
+
 // one JSON number (json.loads grammar, plus the NaN / Infinity / -Infinity literals it accepts, plus null -> NaN)
 bool parse_number(Cur& c, float* out) {
   c.ws();
+#if B2S_CODEC_FAST
+  if (parse_number_fast(c, out)) return true;
+#endif
   const char* s = c.p;
   if (s >= c.end) return false;
   auto lit = [&](const char* w, float v) {
@@ -184,7 +321,14 @@ int repr_double(double v, char* buf) {
     ++s;
     while (*s && *s != 'e') digits[nd++] = *s++;
   }
-  const int exp10 = atoi(s + 1);  // after 'e'
+  int exp10 = 0;  // after 'e': sign and at least two digits
+  {
+    const char* x = s + 1;
+    const bool xneg = *x == '-';
+    if (*x == '-' || *x == '+') ++x;
+    while (*x >= '0' && *x <= '9') exp10 = exp10 * 10 + (*x++ - '0');
+    if (xneg) exp10 = -exp10;
+  }
   if (exp10 >= -4 && exp10 < 16) {
     if (exp10 < 0) {
       *o++ = '0';
@@ -210,7 +354,7 @@ int repr_double(double v, char* buf) {
     *o++ = exp10 < 0 ? '-' : '+';
     const int a = exp10 < 0 ? -exp10 : exp10;
     if (a < 10) *o++ = '0';
-    o += snprintf(o, 8, "%d", a);
+    o = std::to_chars(o, o + 8, a).ptr;
   }
   return (int)(o - buf);
 }
@@ -226,6 +370,218 @@ int codec_threads() {
   return n;
 }
 
+// ---- rows of a numeric matrix, two stages (x86-64 with AVX2; anything else takes the scalar row loop) --------------------
+// A scalar parser is one long dependency chain: where token k + 1 starts is known only when token k has been scanned, about
+// 14 cycles per eight-byte step and four steps per 17-digit number.  Stage 1 breaks the chain: 32 bytes at a time are
+// classified as separator (comma / white space) or token byte, and the token boundaries fall out of the bit masks
+// (throughput bound, no conversion).  Stage 2 converts every token from its known extent: sign, position of the '.', digit
+// runs of known length converted eight at a time at fixed offsets -- independent work the core overlaps across tokens.  It
+// takes plain decimals ("-12.345", up to 8 integer and 19 total digits); exponents, literals (NaN, Infinity, null), longer
+// numbers and anything malformed go to parse_number token by token, which also rejects what is not a number.
+#if B2S_CODEC_FAST
+#define B2S_AVX2 __attribute__((target("avx2,bmi,bmi2,lzcnt,popcnt")))
+
+bool cpu_has_avx2() {
+  static const bool ok = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi") && __builtin_cpu_supports("bmi2") &&
+                         __builtin_cpu_supports("popcnt") && getenv("B2S_CODEC_SCALAR") == nullptr;
+  return ok;
+}
+
+inline uint64_t digits_value(const char* p, int n) {  // n <= 8 digit bytes at p (eight bytes are read)
+  uint64_t x;
+  memcpy(&x, p, 8);
+  x ^= 0x3030303030303030ull;
+  const int sh = (8 - n) * 4;
+  x = (x << sh) << sh;
+  x = (x * 10) + (x >> 8);
+  const uint64_t mask = 0x000000FF000000FFull;
+  return (((x & mask) * 0x000F424000000064ull) + (((x >> 16) & mask) * 0x0000271000000001ull)) >> 32;
+}
+
+// the token [s, e) as a plain decimal; false = not taken (the caller asks parse_number).  40 readable bytes from s are required.
+B2S_AVX2 inline bool convert_plain_decimal(const char* s, const char* e, float* out) {
+  const uint64_t neg = *s == '-';
+  const char* q = s + neg;
+  const int n = (int)(e - q);
+  if (n < 1 || n > 21) return false;
+  const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(q));
+  const uint32_t in_token = (uint32_t)((1ull << n) - 1);
+  const uint32_t dots = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('.'))) & in_token;
+  const __m256i t = _mm256_sub_epi8(v, _mm256_set1_epi8('0'));
+  const uint32_t digs = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_min_epu8(t, _mm256_set1_epi8(9)), t)) & in_token;
+  if ((digs | dots) != in_token || (dots & (dots - 1))) return false;  // exponent, literal, garbage, two dots
+  const int ni = dots ? (int)_tzcnt_u32(dots) : n;
+  const int nf = dots ? n - ni - 1 : 0;
+  if (ni < 1 || ni > 8 || ni + nf > 19 || (dots && nf < 1) || (*q == '0' && ni > 1)) return false;
+  uint64_t w = digits_value(q, ni);
+  double val;
+  uint64_t sign = neg << 63;
+  if (!dots) {
+    val = (double)w;
+    if (w == 0) sign = 0;  // "-0" is the int 0
+  } else {
+    const char* f = q + ni + 1;
+    const int na = nf < 8 ? nf : 8, nb = nf - na < 8 ? nf - na : 8, nc = nf - na - nb;
+    const uint64_t a = digits_value(f, na), b = digits_value(f + 8, nb), c = digits_value(f + 16, nc);
+    w = ((w * kPow10u[na] + a) * kPow10u[nb] + b) * kPow10u[nc] + c;
+    if (w == 0) {
+      val = 0.0;
+    } else {
+      const long double y = (long double)w / kPow10[nf];
+      uint64_t m;
+      memcpy(&m, &y, 8);
+      if ((m & 0x7FFull) == 0x400ull) return false;  // on a double's rounding boundary: the exact converter decides
+      val = (double)y;
+    }
+  }
+  uint64_t bits;
+  memcpy(&bits, &val, 8);
+  bits |= sign;
+  memcpy(&val, &bits, 8);
+  *out = (float)val;
+  return true;
+}
+
+// Row text (b, e) -- between '[' and ']' -- into dst[0 .. cols); `limit` is the end of the readable buffer.  false: not `cols`
+// well-formed numbers separated by single commas (the caller falls back to the sequential parser for the verdict).
+B2S_AVX2 bool parse_row_simd(const char* b, const char* e, const char* limit, float* dst, int64_t cols, std::vector<uint32_t>& marks) {
+  const size_t len = (size_t)(e - b);
+  if (len >= (1ull << 31)) return false;
+  if (marks.size() < (size_t)(2 * cols + 2 + 64)) marks.resize((size_t)(2 * cols + 2 + 64));
+  uint32_t* const mk = marks.data();  // token k: [mk[2k], mk[2k + 1])
+  const size_t cap = (size_t)(2 * cols + 2);
+  size_t nm = 0;
+  uint32_t carry = 0;  // was the previous byte a token byte?
+  const __m256i comma = _mm256_set1_epi8(','), space = _mm256_set1_epi8(' '), tab = _mm256_set1_epi8('\t'), nl = _mm256_set1_epi8('\n'),
+                cr = _mm256_set1_epi8('\r');
+  for (size_t off = 0; off < len; off += 32) {
+    __m256i v;
+    if (off + 32 <= len) {
+      v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(b + off));
+    } else {  // the row's last bytes, padded with separators
+      alignas(32) char tail[32];
+      memset(tail, ' ', 32);
+      memcpy(tail, b + off, len - off);
+      v = _mm256_load_si256(reinterpret_cast<const __m256i*>(tail));
+    }
+    const __m256i sep = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, comma), _mm256_cmpeq_epi8(v, space)),
+                                        _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, tab), _mm256_cmpeq_epi8(v, nl)), _mm256_cmpeq_epi8(v, cr)));
+    const uint32_t tok = ~(uint32_t)_mm256_movemask_epi8(sep);
+    const uint32_t prev = (tok << 1) | carry;
+    uint32_t edges = tok ^ prev;  // bit i: byte i starts a token (tok) or is the first byte after one (!tok)
+    carry = tok >> 31;
+    if (nm + (size_t)_mm_popcnt_u32(edges) > cap) return false;  // more tokens than columns
+    while (edges) {
+      mk[nm++] = (uint32_t)off + _tzcnt_u32(edges);
+      edges = _blsr_u32(edges);
+    }
+  }
+  if (carry) mk[nm++] = (uint32_t)len;  // the last token ends with the row  (the padded tail cannot carry; a full last chunk can)
+  if (nm != (size_t)(2 * cols)) return false;
+  // separators: nothing but white space in front of the first token and behind the last, exactly one comma between neighbours
+  uint32_t prev_end = 0;
+  for (int64_t k = 0; k < cols; ++k) {
+    const uint32_t s0 = mk[2 * k], e0 = mk[2 * k + 1];
+    const uint32_t gap = s0 - prev_end;
+    int commas = 0;
+    if (gap == 2) commas = (b[prev_end] == ',') + (b[prev_end + 1] == ',');
+    else if (gap == 1) commas = b[prev_end] == ',';
+    else
+      for (uint32_t i = prev_end; i < s0; ++i) commas += b[i] == ',';
+    if (commas != (k ? 1 : 0)) return false;
+    prev_end = e0;
+    const char* ts = b + s0;
+    const char* te = b + e0;
+    if (ts + 40 <= limit && convert_plain_decimal(ts, te, dst + k)) continue;
+    Cur c{ts, te};
+    if (!parse_number(c, dst + k) || c.p != te) return false;
+  }
+  for (uint32_t i = prev_end; i < (uint32_t)len; ++i)
+    if (b[i] == ',') return false;
+  return true;
+}
+#endif
+
+// ---- worker pool of the parallel parse ---------------------------------------------------------------------------------
+// Threads are created once and parked on a condition variable: a body of a few MB is parsed in about a millisecond per
+// thread, less than it takes freshly created threads to be spread over the cores.  One job at a time: a caller that finds the
+// pool taken parses its body on its own thread.  After fork() the child starts without a pool and builds its own on first use.
+struct Pool {
+  std::mutex caller;  // held for the duration of a job
+  std::mutex m;
+  std::condition_variable cv_job, cv_done;
+  uint64_t generation = 0;
+  int pending = 0;
+  void (*fn)(void*) = nullptr;
+  void* arg = nullptr;
+  int workers = 0;
+};
+std::atomic<Pool*> g_pool{nullptr};
+std::mutex g_pool_make;
+
+void pool_worker(Pool* pl) {
+  uint64_t seen = 0;
+  for (;;) {
+    void (*fn)(void*);
+    void* arg;
+    {
+      std::unique_lock<std::mutex> lk(pl->m);
+      pl->cv_job.wait(lk, [&] { return pl->generation != seen; });
+      seen = pl->generation;
+      fn = pl->fn;
+      arg = pl->arg;
+    }
+    fn(arg);
+    {
+      std::lock_guard<std::mutex> lk(pl->m);
+      if (--pl->pending == 0) pl->cv_done.notify_one();
+    }
+  }
+}
+
+Pool* get_pool(int threads) {
+  Pool* pl = g_pool.load(std::memory_order_acquire);
+  if (pl) return pl;
+  std::lock_guard<std::mutex> lk(g_pool_make);
+  pl = g_pool.load(std::memory_order_acquire);
+  if (pl) return pl;
+  static const bool hooked = [] {
+    pthread_atfork(nullptr, nullptr, [] { g_pool.store(nullptr, std::memory_order_release); });  // the child has no workers
+    return true;
+  }();
+  (void)hooked;
+  pl = new Pool;  // never destroyed: its threads are parked for the life of the process
+  try {
+    for (int t = 1; t < threads; ++t) {
+      std::thread(pool_worker, pl).detach();
+      ++pl->workers;
+    }
+  } catch (const std::exception&) {  // no more threads to be had: the job runs on those that started (and the caller)
+  }
+  g_pool.store(pl, std::memory_order_release);
+  return pl;
+}
+
+// runs `work` on the caller's thread and on every pool thread at once; false (nothing ran) when another job holds the pool
+template <class F>
+bool run_on_pool(int threads, F& work) {
+  Pool* pl = get_pool(threads);
+  std::unique_lock<std::mutex> job(pl->caller, std::try_to_lock);
+  if (!job.owns_lock()) return false;
+  {
+    std::lock_guard<std::mutex> lk(pl->m);
+    pl->fn = [](void* a) { (*static_cast<F*>(a))(); };
+    pl->arg = &work;
+    pl->pending = pl->workers;
+    ++pl->generation;
+  }
+  pl->cv_job.notify_all();
+  work();
+  std::unique_lock<std::mutex> lk(pl->m);
+  pl->cv_done.wait(lk, [&] { return pl->pending == 0; });
+  return true;
+}
+
 // Optimistic parallel parse of a large numeric matrix.  `first` points at the '[' of row 0.  Inside a numeric matrix every
 // ']' closes a row (or the matrix), so one memchr pass finds the rows; worker threads then parse disjoint row ranges with
 // the same parse_number as the sequential path.  Anything unexpected -- a string, a nested list, a ragged row, a row that
@@ -233,8 +589,14 @@ int codec_threads() {
 // also produces the right error.  On success: rows / cols / n are set and `end` is just past the matrix's closing ']'.
 bool parse_matrix_parallel(const char* first, const char* limit, float* out, int64_t out_cap, int64_t* rows_out, int64_t* cols_out,
                            const char** end) {
-  const int threads = codec_threads();
-  if (threads < 2 || limit - first < (1 << 18)) return false;
+  // several threads for bodies over 256 KB; smaller ones (and B2S_CODEC_THREADS=1) take the same row parser on this thread
+  const int threads = limit - first < (1 << 18) ? 1 : codec_threads();
+#if B2S_CODEC_FAST
+  const bool simd = cpu_has_avx2();
+#else
+  const bool simd = false;
+#endif
+  if (threads < 2 && !simd) return false;  // nothing to gain over the sequential parser
   auto ws = [&](const char* p) {
     while (p < limit && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
     return p;
@@ -258,7 +620,7 @@ bool parse_matrix_parallel(const char* first, const char* limit, float* out, int
     break;
   }
   const int64_t rows = (int64_t)begin.size();
-  if (rows < 2 * threads) return false;
+  const int use_threads = rows < 2 * (int64_t)threads ? 1 : threads;
   // row 0 fixes the width
   int64_t cols = 0;
   {
@@ -277,48 +639,52 @@ bool parse_matrix_parallel(const char* first, const char* limit, float* out, int
     }
   }
   if (rows * cols > out_cap) return false;  // the sequential path reports it
-  std::vector<char> ok((size_t)threads, 1);
-  auto work = [&](int t) {
-    const int64_t r0 = rows * t / threads, r1 = rows * (t + 1) / threads;
-    for (int64_t r = r0; r < r1; ++r) {
-      Cur c{begin[(size_t)r], stop[(size_t)r]};
-      float* dst = out + r * cols;
-      int64_t w = 0;
-      c.ws();
-      if (c.p < c.end) {
-        for (;;) {
-          float v;
-          if (!parse_number(c, &v)) {
-            ok[(size_t)t] = 0;
-            return;
-          }
-          if (w < cols) dst[w] = v;
-          ++w;
-          if (c.eat(',')) continue;
-          break;
+  // row blocks are handed out through one atomic counter: a worker that is scheduled late simply takes fewer of them
+  const int64_t block = std::max<int64_t>(16, rows / (8 * (int64_t)use_threads));
+  const int64_t n_blocks = (rows + block - 1) / block;
+  std::atomic<int64_t> next{0};
+  std::atomic<int> bad{0};
+  auto work = [&] {
+    std::vector<uint32_t> marks;  // token boundaries of one row (stage 1 of the SIMD row parser)
+    for (;;) {
+      const int64_t b = next.fetch_add(1, std::memory_order_relaxed);
+      if (b >= n_blocks || bad.load(std::memory_order_relaxed)) return;
+      const int64_t r0 = b * block, r1 = std::min(rows, r0 + block);
+      for (int64_t r = r0; r < r1; ++r) {
+        float* dst = out + r * cols;
+#if B2S_CODEC_FAST
+        if (simd) {
+          if (parse_row_simd(begin[(size_t)r], stop[(size_t)r], limit, dst, cols, marks)) continue;
+          bad.store(1, std::memory_order_relaxed);
+          return;
         }
+#endif
+        Cur c{begin[(size_t)r], stop[(size_t)r]};
+        int64_t w = 0;
         c.ws();
-      }
-      if (c.p != c.end || w != cols) {
-        ok[(size_t)t] = 0;
-        return;
+        if (c.p < c.end) {
+          for (;;) {
+            float v;
+            if (!parse_number(c, &v)) {
+              bad.store(1, std::memory_order_relaxed);
+              return;
+            }
+            if (w < cols) dst[w] = v;
+            ++w;
+            if (c.eat(',')) continue;
+            break;
+          }
+          c.ws();
+        }
+        if (c.p != c.end || w != cols) {
+          bad.store(1, std::memory_order_relaxed);
+          return;
+        }
       }
     }
   };
-  std::vector<std::thread> pool;
-  int started = 1;  // range 0 runs on this thread
-  try {
-    for (int t = 1; t < threads; ++t) {
-      pool.emplace_back(work, t);
-      ++started;
-    }
-  } catch (const std::exception&) {  // no more threads to be had: the ranges that got none are parsed here
-  }
-  work(0);
-  for (int t = started; t < threads; ++t) work(t);
-  for (auto& th : pool) th.join();
-  for (char good : ok)
-    if (!good) return false;
+  if (use_threads < 2 || !run_on_pool(threads, work)) work();  // (the pool is busy with another caller's body: this thread alone)
+  if (bad.load()) return false;
   *rows_out = rows;
   *cols_out = cols;
   *end = p;
@@ -443,7 +809,7 @@ extern "C" int b2s_json_format_outputs(const void* vals, int32_t is_int, int64_t
         *o++ = ',';
         *o++ = ' ';
       }
-      if (is_int) o += snprintf(o, 16, "%d", iv[r * n_cols + k]);
+      if (is_int) o = std::to_chars(o, o + 16, iv[r * n_cols + k]).ptr;
       else o += repr_double((double)f[r * n_cols + k], o);
     }
     if (!flat) {

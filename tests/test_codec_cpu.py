@@ -251,3 +251,117 @@ def test_binary_content_type_through_graph_server_run(monkeypatch):
     assert resp.status_code == 400 and "infinity" in resp.body
     resp = server.run(api.MockEvent(body=b"garbage", path="/v2/models/infer", content_type=bcodec.BINARY_CONTENT_TYPE))
     assert resp.status_code == 400 and "bad magic" in resp.body
+
+
+def _parse_tokens(tokens):
+    got, _ = codec.parse_inputs('{"inputs": [[' + ", ".join(tokens) + "]]}")
+    return got[0]
+
+
+def _float32_of(tokens):
+    with np.errstate(over="ignore"):
+        return np.asarray([float(t) for t in tokens], dtype=np.float64).astype(np.float32)
+
+
+def test_fast_number_path_is_correctly_rounded_on_long_digit_strings():
+    """The codec's fast path (b2s_codec.cpp parse_number_fast: <= 19 digits, |exponent| <= 27, one 80-bit multiply or divide,
+    hand-over to the exact converter on a double's rounding boundary) gives float32(float(token)) bit for bit: random
+    digit strings of every length in every notation"""
+    import random
+
+    rnd = random.Random(5)
+    tokens = []
+    for _ in range(60000):
+        nd = rnd.randint(1, 21)
+        digits = str(rnd.randint(1, 9)) + "".join(rnd.choice("0123456789") for _ in range(nd - 1))
+        form = rnd.randint(0, 4)
+        if form == 0:  # d.ddd
+            cut = rnd.randint(1, nd)
+            tok = digits[:cut] + ("." + digits[cut:] if cut < nd else "")
+        elif form == 1:  # 0.000ddd
+            tok = "0." + "0" * rnd.randint(0, 12) + digits
+        elif form == 2:  # d.ddde+-xx
+            tok = digits[0] + ("." + digits[1:] if nd > 1 else "") + rnd.choice("eE") + rnd.choice(["", "+", "-"]) + str(rnd.randint(0, 45))
+        elif form == 3:  # integer
+            tok = digits
+        else:  # ddd.ddde-xx around the fast path's exponent limit
+            cut = rnd.randint(1, nd)
+            tok = digits[:cut] + "." + (digits[cut:] or "0") + "e" + str(rnd.randint(-30, 30))
+        tokens.append(("-" if rnd.random() < 0.5 else "") + tok)
+    got = _parse_tokens(tokens)
+    want = _float32_of(tokens)
+    bad = np.flatnonzero(got.view(np.uint32) != want.view(np.uint32))
+    assert bad.size == 0, [(tokens[i], got[i], want[i]) for i in bad[:5]]
+
+
+def test_numbers_next_to_rounding_boundaries():
+    """tokens a hair above / below / on the midpoint of two neighbouring float32 values (where the float32 result depends on
+    the double being the correctly rounded one) and of two neighbouring doubles (where the 80-bit product lands on the
+    boundary pattern and the exact converter has to take over)"""
+    from decimal import Decimal, getcontext
+
+    getcontext().prec = 60
+    rng = np.random.default_rng(9)
+    tokens = []
+    a = np.abs(rng.normal(size=4000).astype(np.float32) * np.float32(10.0) ** rng.integers(-6, 7, size=4000).astype(np.float32))
+    a = a[np.isfinite(a) & (a > 0)]
+    b = np.nextafter(a, np.float32(np.inf))
+    for lo, hi in zip(a.tolist(), b.tolist()):
+        mid = (Decimal(lo) + Decimal(hi)) / 2  # exact: a float32 midpoint is a double
+        ulp_d = Decimal(float(np.nextafter(np.float64(float(mid)), np.inf))) - mid
+        # +-0.5: the midpoint of the float32 midpoint and its neighbouring double; its nearest 19-digit decimal is often closer to
+        # it than half a unit of the 80-bit format, so the product lands exactly on the boundary while the token is beside it
+        for k in (Decimal("-0.6"), Decimal("-0.5"), Decimal("-0.4"), Decimal(0), Decimal("0.4"), Decimal("0.5"), Decimal("0.6")):
+            x = mid + k * ulp_d
+            for digits in (17, 18, 19):
+                tokens.append(format(x, f".{digits - 1}e"))  # d.ddde-xx
+                tokens.append(format(x.quantize(Decimal(1).scaleb(x.adjusted() - digits + 1)), "f"))  # plain notation
+    d = np.abs(rng.normal(size=3000) * 10.0 ** rng.integers(-8, 9, size=3000))
+    for lo in d.tolist():
+        hi = float(np.nextafter(np.float64(lo), np.inf))
+        mid = (Decimal(lo) + Decimal(hi)) / 2
+        for digits in (17, 18, 19):
+            q = Decimal(1).scaleb(mid.adjusted() - digits + 1)
+            for x in (mid.quantize(q), mid.quantize(q) + q, mid.quantize(q) - q):
+                tokens.append(format(x, "f"))
+                tokens.append(format(x, f".{digits - 1}e"))
+    got = _parse_tokens(tokens)
+    want = _float32_of(tokens)
+    bad = np.flatnonzero(got.view(np.uint32) != want.view(np.uint32))
+    assert bad.size == 0, [(tokens[i], got[i], want[i]) for i in bad[:5]]
+
+
+def test_threaded_parser_serves_concurrent_callers_and_survives_fork():
+    """the worker pool takes one body at a time (other callers parse on their own thread) and a forked child builds its own"""
+    import multiprocessing as mp
+    import threading
+
+    rows = _big_rows(n_rows=4000)
+    body = json.dumps({"inputs": rows}).encode()
+    want = np.asarray(rows, dtype=np.float32)
+    results, errors = [None] * 6, []
+
+    def one(i):
+        try:
+            for _ in range(3):
+                results[i] = codec.parse_inputs(body)[0].copy()
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=one, args=(i,)) for i in range(6)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors
+    for r in results:
+        np.testing.assert_array_equal(r.view(np.uint32), want.view(np.uint32))
+    ctx = mp.get_context("fork")  # the pool's threads do not exist in the child
+    q = ctx.Queue()
+    p = ctx.Process(target=_forked_parse, args=(body, q))
+    p.start()
+    shape = q.get(timeout=60)
+    p.join(timeout=60)
+    assert shape == want.shape and p.exitcode == 0
+
+
+def _forked_parse(body, q):
+    q.put(codec.parse_inputs(body)[0].shape)
