@@ -92,34 +92,40 @@ class BaseModelRouter(_RouterMeta):
     def _handle_event(self, event):
         return event
 
-    def _url_target(self, urlpath):
-        """<prefix>/<model>[/versions/<ver>]/<op> -> (segments after the prefix)"""
-        return urlpath[len(self.url_prefix):].strip("/")
+    def _parse_url(self, urlpath):
+        """`<prefix>/<model>[/versions/<ver>][/<operation...>]` -> (model, operation) as the routers read a URL
+        (serving/routers.py:143-181): None when the event has no routing URL ("" or "/"), ("", "") for the bare prefix;
+        a version becomes part of the model key ("name:ver"); the operation is "" when the URL stops at the model."""
+        if not urlpath or urlpath == "/":
+            return None
+        pieces = [piece for piece in urlpath[len(self.url_prefix):].strip("/").split("/")]
+        if pieces == [""]:
+            return "", ""
+        model, operation = pieces[0], pieces[1:]
+        if len(pieces) > 2 and pieces[1] == "versions":
+            model, operation = f"{pieces[0]}:{pieces[2]}", pieces[3:]
+        return model, "/".join(operation)
+
+    @staticmethod
+    def _operation_of(body, from_url):
+        """the body of a stream event may name the operation (routers.py:183-190); "infer" when nobody does"""
+        op = body.get("operation", from_url) if isinstance(body, dict) else from_url
+        return "infer" if op is None else op
 
 
 class ModelRouter(BaseModelRouter):
     def _resolve_route(self, body, urlpath):
-        subpath, model = None, ""
-        if urlpath and urlpath != "/":
-            subpath = ""
-            rest = self._url_target(urlpath)
-            if not rest:
-                return "", None, ""
-            parts = rest.split("/")
-            model = parts[0]
-            if len(parts) > 2 and parts[1] == "versions":
-                model = f"{model}:{parts[2]}"
-                parts = parts[2:]
-            if len(parts) > 1:
-                subpath = "/".join(parts[1:])
-        if isinstance(body, dict):
-            model = model or body.get("model", list(self.routes.keys())[0])
-            subpath = body.get("operation", subpath)
-        if subpath is None:
-            subpath = "infer"
+        """-> (model key, route, operation); ("", None, "") for the bare prefix (the caller lists the models)"""
+        target = self._parse_url(urlpath)
+        if target == ("", ""):
+            return "", None, ""
+        model, url_op = target if target else ("", None)
+        if not model and isinstance(body, dict):  # stream events carry the route in the body; the first model is the default
+            model = body.get("model", next(iter(self.routes)))
+        operation = self._operation_of(body, url_op)
         if model not in self.routes:
             raise ValueError(f"model {model} doesnt exist, available models: {' | '.join(self.routes.keys())}")
-        return model, self.routes[model], subpath
+        return model, self.routes[model], operation
 
     def _handle_event(self, event):
         name, route, subpath = self._resolve_route(event.body, event.path)
@@ -252,41 +258,27 @@ class VotingEnsemble(ParallelRun):
 
     # ---- routing (routers.py:623-706) -----------------------------------------------------------------
     def _resolve_route(self, body, urlpath):
-        subpath, model = None, ""
-        if urlpath and urlpath != "/":
-            subpath = ""
-            rest = self._url_target(urlpath)
-            if not rest:
-                return "", None, ""
-            parts = rest.split("/")
-            if len(parts) == 1:
-                try:
-                    op = OperationTypes(parts[0])
-                except ValueError:
-                    model = parts[0]
-                else:
-                    self.log_router = True
-                    return self.name, None, op
-            if len(parts) > 2 and parts[1] == "versions":
-                model = f"{parts[0]}:{parts[2]}"
-                parts = parts[2:]
-            else:
-                model = parts[0]
-            if len(parts) > 1:
-                subpath = "/".join(parts[1:])
-        if isinstance(body, dict):
-            model = model or self.name
-            subpath = body.get("operation", subpath)
-        if subpath is None:
-            subpath = "infer"
+        """-> (name, route, operation).  route None + name == self.name: the ensemble itself answers (vote over all routes);
+        a URL that is `<prefix>/<operation>` alone addresses the ensemble too (routers.py:640-706)"""
+        target = self._parse_url(urlpath)
+        if target == ("", ""):
+            return "", None, ""
+        model, url_op = target if target else ("", None)
+        if target and "/" not in urlpath[len(self.url_prefix):].strip("/"):  # one segment: an operation of the router, or a model
+            if model in OperationTypes._value2member_map_:
+                self.log_router = True
+                return self.name, None, OperationTypes(model)
+        if not model and isinstance(body, dict):
+            model = self.name
+        operation = self._operation_of(body, url_op)
         if model in self.routes:
-            self.log_router = False
-            return model, self.routes[model], subpath
-        if model != self.name:
-            raise ValueError(
-                f"model {model} doesnt exist, available models: "
-                f"{' | '.join(self.routes.keys())} | {self.name} or an operation alone for ensemble operation")
-        return model, None, subpath
+            self.log_router = False  # plain pass-through to one model: its own server logs the event
+            return model, self.routes[model], operation
+        if model == self.name:
+            return model, None, operation
+        raise ValueError(
+            f"model {model} doesnt exist, available models: "
+            f"{' | '.join(self.routes.keys())} | {self.name} or an operation alone for ensemble operation")
 
     # ---- vote arithmetic (routers.py:708-810) -- the CPU form of what vote_and_store does on the device ---
     def _majority_vote(self, all_predictions, weights):
