@@ -195,6 +195,15 @@ def launch_count():
     return int(load().b2s_launch_count())
 
 
+def ptr(arr):
+    """address of a numpy array's first element, 3x cheaper than `arr.ctypes.data` (which builds a helper object per call:
+    1.2 us, three of them per serving call); read-only, empty and non-contiguous arrays take the ordinary route"""
+    try:
+        return C.addressof(C.c_char.from_buffer(arr))
+    except (TypeError, ValueError):
+        return arr.ctypes.data
+
+
 def _p(arr, ctype):
     return arr.ctypes.data_as(C.POINTER(ctype)) if arr is not None else None
 

@@ -166,8 +166,7 @@ class DevicePlan:
         n = X.shape[0]
         out, status = self._result_arrays(n)
         stats = nat.Stats()
-        nat.check(self._lib.b2s_run_host(self._h, X.ctypes.data, n, self._stride(X), out.ctypes.data, out.nbytes,
-                                         status.ctypes.data, C.byref(stats)))
+        nat.check(self._lib.b2s_run_host(self._h, nat.ptr(X), n, self._stride(X), nat.ptr(out), out.nbytes, nat.ptr(status), C.byref(stats)))
         res = (out,)
         if with_status:
             res += (status,)
@@ -189,7 +188,7 @@ class DevicePlan:
     def submit(self, X):
         X = self._check_rows(X)
         t = C.c_uint64()
-        nat.check(self._lib.b2s_submit(self._h, X.ctypes.data, X.shape[0], self._stride(X), C.byref(t)))
+        nat.check(self._lib.b2s_submit(self._h, nat.ptr(X), X.shape[0], self._stride(X), C.byref(t)))
         return (t.value, X.shape[0])
 
     def wait(self, ticket, with_status=False, with_stats=False):
@@ -197,7 +196,7 @@ class DevicePlan:
         out = np.empty((n, self.out_cols), dtype=self.out_dtype)
         status = np.empty(n, dtype=np.int32)
         stats = nat.Stats()
-        nat.check(self._lib.b2s_wait(self._h, t, out.ctypes.data, out.nbytes, status.ctypes.data, C.byref(stats)))
+        nat.check(self._lib.b2s_wait(self._h, t, nat.ptr(out), out.nbytes, nat.ptr(status), C.byref(stats)))
         res = (out,)
         if with_status:
             res += (status,)
