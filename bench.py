@@ -465,19 +465,21 @@ def ring_bench(nat, name="flow3_ens4", seconds=0.5):
                                          "how": "GraphServer.emit(body) + await_result(ticket), one Python caller"}}
 
 
-def config4_leg(rank, world, steps=10, timeout_s=100.0):
+def config4_leg(rank, world, steps=10, timeout_s=100.0, workload_args=("--workload", "router8", "--scaling", "strong", "--batch", "65536", "--no-e2e"),
+                port_shift=17):
     """BASELINE configs[3] as written -- the 8-model mixed router (4 linear + 4 tree scorers), GLOBAL batch 65 536 split over the
     GPUs (strong scaling), fused P2P ensemble-merge -- measured beside the headline workload so that the driver's 1 / 2 / 4 / 8
     runs carry its curve.  Every rank starts `bench.py --workload router8 --scaling strong --batch 65536` as a CHILD process
     (the invocation the 2-GPU lab runs used, profiles/lab/gpu18.sh); the children form their own process group (same RANK /
     WORLD_SIZE, MASTER_PORT + 17, torchrun's agent-store variables removed so that child rank 0 hosts the store).  A separate
     process, so a failure or a hang of this leg costs its own row after `timeout_s`, never the parent's line.
+    `workload_args` selects another stand-alone invocation the same way (the configs[4] ingest leg).
     -> summary dict on rank 0, None elsewhere."""
     env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")}
     if world > 1:
-        env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 17)
-    cmd = [sys.executable, os.path.abspath(__file__), "--workload", "router8", "--scaling", "strong", "--batch", "65536", "--gpus", str(world),
-           "--steps", str(steps), "--warmup", "3", "--no-cpu-baseline", "--no-e2e", "--no-configs"]
+        env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + port_shift)
+    cmd = [sys.executable, os.path.abspath(__file__)] + list(workload_args) + ["--gpus", str(world), "--steps", str(steps), "--warmup", "3",
+                                                                     "--no-cpu-baseline", "--no-configs"]
     if os.environ.get("B2S_BENCH_CONFIG4_CMD"):  # tests: a stand-in child (tests/test_bench_config4_cpu.py)
         cmd = [sys.executable] + json.loads(os.environ["B2S_BENCH_CONFIG4_CMD"])
     t0 = time.perf_counter()
@@ -496,6 +498,8 @@ def config4_leg(rank, world, steps=10, timeout_s=100.0):
                 "launches_timed": lps * int(d.get("steps", 0)), "parallelism": cfg.get("parallelism"), "merge_verified": cfg.get("merge_verified"),
                 "kernel": cfg.get("kernel"), "roofline_frac": (d.get("roofline") or {}).get("frac"), "clocks": d.get("clocks"),
                 "p50_step_latency_us": (d.get("p50_step_latency_us") or {}).get("p50"), "wall_s": round(time.perf_counter() - t0, 1),
+                **({"e2e": {k: d["e2e"].get(k) for k in ("value", "unit", "batch", "steps", "h2d_bytes_per_step", "d2h_bytes_per_step", "api")}}
+                   if isinstance(d.get("e2e"), dict) else {}),
                 "how": "child process per rank: " + " ".join(cmd[1:])}
     except Exception as exc:  # noqa: BLE001 -- the row reports what went wrong
         return {"error": f"{type(exc).__name__}: {exc}", "rc": done.returncode, "stderr_tail": done.stderr[-400:]}
@@ -737,11 +741,13 @@ def main():
                 "api": "GraphServer.run_json: JSON body -> b2s_json_parse_inputs -> fused plan -> b2s_json_format_outputs",
                 "python_json_codec_only_events_per_s": Bw / dt_py}
 
-    cfg4 = None
+    cfg4 = cfg5 = None
     if name == "flow3_ens4" and not args.batch and args.scaling == "weak" and not args.no_configs:
         # BASELINE configs[3] (strong scaling of the 8-model router at a global batch of 65 536) on the same GPUs, every rank's child
         # at the same point of the run; this process keeps its buffers and is idle meanwhile
         cfg4 = config4_leg(rank, world)
+        if world > 1:  # BASELINE configs[4] on all the GPUs (rows shard over the ranks, no exchange); at N = 1 it is a row of `configs`
+            cfg5 = config4_leg(rank, world, steps=10, timeout_s=120.0, workload_args=("--workload", "ingest6"), port_shift=23)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -782,6 +788,8 @@ def main():
             line["cpu_baseline"] = cpu
         if cfg4:
             line["config4"] = cfg4
+        if cfg5:
+            line["config5"] = cfg5
         if default_run:
             # every config of BASELINE.json (and the SURVEY 8(f) callers) under the same clocks, one row each
             torch.cuda.synchronize()

@@ -27,4 +27,4 @@ if rank == 0:
                       "config": {"workload": "stand-in", "global_batch": 65536, "batch_per_gpu": 65536 // world, "launches_per_step": 8,
                                  "merge_verified": total == world * (world + 1) // 2 if world > 1 else None, "kernel": "none",
                                  "parallelism": f"x{world}", "master_port": os.environ.get("MASTER_PORT")},
-                      "roofline": {"frac": 0.5}, "clocks": None, "p50_step_latency_us": {"p50": 1.0}}))
+                      "roofline": {"frac": 0.5}, "clocks": None, "e2e": {"value": 7.0, "unit": "events/s", "batch": 5, "other": 1}, "p50_step_latency_us": {"p50": 1.0}}))

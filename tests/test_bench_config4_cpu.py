@@ -30,6 +30,7 @@ def test_single_process_row_and_a_child_that_hangs(monkeypatch):
         monkeypatch.delenv(k, raising=False)
     row = bench.config4_leg(0, 1)
     assert row["n_gpus"] == 1 and row["events_per_s"] == 1000.0 and row["merge_verified"] is None
+    assert row["e2e"]["value"] == 7.0 and "other" not in row["e2e"]  # the child's end-to-end figure travels with the row
     monkeypatch.setenv("B2S_BENCH_CONFIG4_CMD", json.dumps([CHILD, "sleep"]))
     row = bench.config4_leg(0, 1, timeout_s=2.0)
     assert "error" in row and "killed" in row["error"]
