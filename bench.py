@@ -745,8 +745,11 @@ def main():
     if name == "flow3_ens4" and not args.batch and args.scaling == "weak" and not args.no_configs:
         # BASELINE configs[3] (strong scaling of the 8-model router at a global batch of 65 536) on the same GPUs, every rank's child
         # at the same point of the run; this process keeps its buffers and is idle meanwhile
+        if world > 1:
+            dist.barrier()  # the children of all ranks start together
         cfg4 = config4_leg(rank, world)
         if world > 1:  # BASELINE configs[4] on all the GPUs (rows shard over the ranks, no exchange); at N = 1 it is a row of `configs`
+            dist.barrier()  # (a leg that failed on one rank only must not stagger the next one)
             cfg5 = config4_leg(rank, world, steps=10, timeout_s=120.0, workload_args=("--workload", "ingest6"), port_shift=23)
 
     if rank == 0:
