@@ -398,6 +398,17 @@ inline uint64_t digits_value(const char* p, int n) {  // n <= 8 digit bytes at p
   return (((x & mask) * 0x000F424000000064ull) + (((x >> 16) & mask) * 0x0000271000000001ull)) >> 32;
 }
 
+// shuffle controls that move the first n bytes of a 16-byte register to its end and clear the rest (n = 0 .. 16)
+struct RightAlign16 {
+  alignas(16) uint8_t m[17][16];
+  constexpr RightAlign16() : m() {
+    for (int n = 0; n <= 16; ++n)
+      for (int i = 0; i < 16; ++i) m[n][i] = i >= 16 - n ? (uint8_t)(i - (16 - n)) : (uint8_t)0x80;
+  }
+  const uint8_t* operator[](int n) const { return m[n]; }
+};
+constexpr RightAlign16 kRightAlign16{};
+
 // the token [s, e) as a plain decimal; false = not taken (the caller asks parse_number).  40 readable bytes from s are required.
 B2S_AVX2 inline bool convert_plain_decimal(const char* s, const char* e, float* out) {
   const uint64_t neg = *s == '-';
@@ -420,10 +431,20 @@ B2S_AVX2 inline bool convert_plain_decimal(const char* s, const char* e, float* 
     val = (double)w;
     if (w == 0) sign = 0;  // "-0" is the int 0
   } else {
+    // the fraction: its first min(nf, 16) digits in ONE 128-bit step -- moved to the end of a 16-digit field (zeros in front) by a
+    // byte shuffle, then pairs -> fours -> eights by three multiply-adds; a 17th / 18th digit is appended one at a time
     const char* f = q + ni + 1;
-    const int na = nf < 8 ? nf : 8, nb = nf - na < 8 ? nf - na : 8, nc = nf - na - nb;
-    const uint64_t a = digits_value(f, na), b = digits_value(f + 8, nb), c = digits_value(f + 16, nc);
-    w = ((w * kPow10u[na] + a) * kPow10u[nb] + b) * kPow10u[nc] + c;
+    const int n16 = nf < 16 ? nf : 16;
+    __m128i d = _mm_sub_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(f)), _mm_set1_epi8('0'));
+    d = _mm_shuffle_epi8(d, _mm_load_si128(reinterpret_cast<const __m128i*>(kRightAlign16[n16])));
+    const __m128i pairs = _mm_maddubs_epi16(d, _mm_set_epi8(1, 10, 1, 10, 1, 10, 1, 10, 1, 10, 1, 10, 1, 10, 1, 10));
+    const __m128i fours = _mm_madd_epi16(pairs, _mm_set_epi16(1, 100, 1, 100, 1, 100, 1, 100));
+    const __m128i packed = _mm_packus_epi32(fours, fours);
+    const __m128i eights = _mm_madd_epi16(packed, _mm_set_epi16(1, 10000, 1, 10000, 1, 10000, 1, 10000));
+    const uint64_t two = (uint64_t)_mm_cvtsi128_si64(eights);  // low word: digits 1-8 of the field, high word: digits 9-16
+    uint64_t frac = (two & 0xFFFFFFFFull) * 100000000ull + (two >> 32);
+    for (int i = 16; i < nf; ++i) frac = frac * 10 + (uint64_t)(f[i] - '0');
+    w = w * kPow10u[nf] + frac;
     if (w == 0) {
       val = 0.0;
     } else {
