@@ -750,7 +750,7 @@ def main():
         cfg4 = config4_leg(rank, world)
         if world > 1:  # BASELINE configs[4] on all the GPUs (rows shard over the ranks, no exchange); at N = 1 it is a row of `configs`
             dist.barrier()  # (a leg that failed on one rank only must not stagger the next one)
-            cfg5 = config4_leg(rank, world, steps=10, timeout_s=120.0, workload_args=("--workload", "ingest6"), port_shift=23)
+            cfg5 = config4_leg(rank, world, steps=200, timeout_s=120.0, workload_args=("--workload", "ingest6"), port_shift=23)
 
     if rank == 0:
         peak, peak_src = measured_peak()
