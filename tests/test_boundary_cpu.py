@@ -160,3 +160,23 @@ def test_large_results_come_from_the_pinned_pool_and_small_ones_do_not(monkeypat
     assert labels.dtype == np.int32
     big_out, big_st = plan._result_arrays(10_000_000)  # the pool says no: ordinary arrays
     assert big_out.shape == (10_000_000, 3) and big_out.base is None
+
+
+def test_array_addresses_handed_to_the_library():
+    """_native.ptr (the cheap address of an array's first element that plan.run / submit / wait pass to the C-ABI) equals
+    arr.ctypes.data for every kind of array the host layer builds: fresh, sliced, pinned-style (ctypes-backed), read-only,
+    empty and strided ones (the last three through its fallback)"""
+    import ctypes as C
+
+    import numpy as np
+
+    from mlrun_b200 import _native as nat
+
+    raw = C.create_string_buffer(1 << 16)
+    backed = np.frombuffer((C.c_char * (1 << 16)).from_address(C.addressof(raw)), dtype=np.float32, count=4096).reshape(64, 64)
+    status = np.frombuffer((C.c_char * (1 << 16)).from_address(C.addressof(raw)), dtype=np.int32, count=64, offset=32768)
+    cases = [np.zeros((4096, 64), np.float32), np.zeros((10, 64), np.float32)[3:], backed, status, np.frombuffer(b"12345678", dtype=np.float32),
+             np.empty((0, 64), np.float32), np.zeros((8, 128), np.float32)[:, :64], np.zeros(7, np.int32), np.float32(1.0).reshape(1, 1)]
+    for a in cases:
+        assert nat.ptr(a) == a.ctypes.data, (a.shape, a.flags)
+    assert nat.ptr(backed) == C.addressof(raw) and nat.ptr(status) == C.addressof(raw) + 32768
