@@ -1800,6 +1800,82 @@ def steps_odd_values(api):
     }
 
 
+def steps_random_events(api):
+    """feature_store/steps.py:152-246 (MapValues), 377-413 (Imputer), 427-513 (OneHotEncoder), 699-735 (DropFeatures) on 240
+    seeded random dict events -- the per-event semantics the fused kernels restate, away from hand-picked cases: missing values
+    of every kind the reference recognises (None / nan / float32 nan) and +-inf beside ordinary floats and ints, categorical
+    values inside and outside the encoder's categories (ints, floats equal to ints, strings with sanitised characters),
+    range tables whose bounds are hit exactly, value maps over ints; every step alone and the chain Imputer -> OneHotEncoder
+    -> MapValues -> DropFeatures, one `do(event)` per event"""
+    import random
+
+    rnd = random.Random(20260922)
+    nan = float("nan")
+    num_cols = [f"n{i}" for i in range(6)]
+    cat_cols = ["c0", "c1", "c2"]
+    cats = {"c0": [0, 1, 2, 3], "c1": ["red", "dark green", "blue-ish", "x"], "c2": [10, 20, 30]}
+    bounds = [-2.0, -0.5, 0.0, 0.5, 2.0]
+
+    def number():
+        r = rnd.random()
+        if r < 0.08:
+            return None
+        if r < 0.16:
+            return nan
+        if r < 0.19:
+            return np.float32("nan")
+        if r < 0.23:
+            return rnd.choice([float("inf"), float("-inf")])
+        if r < 0.45:
+            return rnd.choice(bounds)  # exactly on a range bound
+        if r < 0.6:
+            return rnd.randint(-3, 3)
+        return round(rnd.uniform(-3, 3), 3)
+
+    def category(col):
+        r = rnd.random()
+        if r < 0.7:
+            v = rnd.choice(cats[col])
+            return float(v) if isinstance(v, int) and rnd.random() < 0.2 else v  # 2.0 == 2 for the encoder
+        if r < 0.8:
+            return None
+        return rnd.choice([99, "unknown", -1, 2.5])
+
+    events = []
+    for _ in range(240):
+        ev = {c: number() for c in num_cols}
+        ev.update({c: category(c) for c in cat_cols})
+        ev["key"] = rnd.randint(0, 5)
+        events.append(ev)
+
+    imputer = dict(mapping={"n0": 0.25, "n1": -1, "c0": 1, "c1": "x"}, default_value=7)
+    onehot = dict(mapping=cats)
+    ranges = {"lowest": ["-inf", -2.0], "low": [-2.0, -0.5], "mid": [-0.5, 0.5], "high": [0.5, 2.0], "highest": [2.0, "inf"]}
+    mapval = dict(mapping={"n2": {"ranges": {k: list(v) for k, v in ranges.items()}}, "n3": {"ranges": {0: [-1, 1], 1: [0, 3]}},
+                           "key": {0: 100, 1: 101, 2: 102}})
+
+    def run(steps, ev):
+        try:
+            body = dict(ev)
+            for step in steps:
+                body = step.do(body)
+            return _clean(body)
+        except Exception as exc:  # noqa: BLE001
+            return f"{type(exc).__name__}: {_first_line(exc)}"
+
+    def mk_chain():
+        return [api.Imputer(**imputer), api.OneHotEncoder(**onehot), api.MapValues(with_original_features=True, **mapval),
+                api.DropFeatures(features=["n5", "key"])]
+
+    singles = {"imputer": [api.Imputer(**imputer)], "imputer_no_default": [api.Imputer(mapping=imputer["mapping"])],
+               "onehot": [api.OneHotEncoder(**onehot)], "mapval": [api.MapValues(**mapval)],
+               "mapval_with_originals": [api.MapValues(with_original_features=True, **mapval)]}
+    out = {name: [run(steps, ev) for ev in events] for name, steps in singles.items()}
+    chain = mk_chain()
+    out["chain"] = [run(chain, ev) for ev in events]
+    return out
+
+
 def model_numpy_outputs(api):
     """serving/server.py:298-308 + serving/v2_serving.py:228-342 -- a model returning numpy values: fine for `server.test`
     (the body object comes back), a TypeError on the wire (`GraphServer.run` json-encodes strictly); plus odd requests to a
@@ -2407,7 +2483,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, steps_odd_values, model_numpy_outputs, vote_odd_predictions, graph_serialisation, router_and_model_paths, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, steps_odd_values, steps_random_events, model_numpy_outputs, vote_odd_predictions, graph_serialisation, router_and_model_paths, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
