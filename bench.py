@@ -203,6 +203,33 @@ def _cpu_worker(args):
     return n_events, time.perf_counter() - t0
 
 
+def _cpu_batched_worker(args):
+    """SURVEY 8(d) (ii), "reference-batched": ONE event carrying all B rows in `inputs` -- what a user of the reference does to
+    go fast on a router / model topology: every model sees (B, F) in one predict (V2ModelServer.do_event -> predict,
+    serving/v2_serving.py:228-342), the vote runs once over (B, M) (routers.py:789-810); json-free (`server.test` with a dict)"""
+    name, n_rows, seconds, seed = args
+    import logging
+
+    logging.disable(logging.CRITICAL)
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from tests import api_oracle
+
+    wl = make_workload(name, n_rows, seed)
+    server = wl.build_server(api_oracle)
+    body = {"inputs": wl.X.astype(np.float64).tolist()}
+    server.test("/v2/models/infer", body=body)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 2 or time.perf_counter() - t0 < seconds:
+        server.test("/v2/models/infer", body=body)
+        reps += 1
+    return reps * n_rows, time.perf_counter() - t0
+
+
 def usable_cores():
     """host threads this process may really use: affinity mask, capped by the cgroup CPU quota"""
     n = len(os.sched_getaffinity(0))
@@ -235,7 +262,18 @@ def cpu_baseline(name, seconds, procs=None):
     wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
     slowest = max(r[1] for r in res)
+    if name.startswith("flow3") or name in ("ingest6", "enrich_ens4"):
+        batched = ("n/a: this graph's feature steps take one dict per event (feature_store/steps.py:397-406, 453-478); only router / "
+                   "model topologies accept B rows in one event")
+    else:  # one event carrying 4 096 rows, on every core at once
+        with ctx.Pool(procs) as pool:
+            bres = pool.map(_cpu_batched_worker, [(name, 4096, max(1.0, seconds * 0.25), 2 + i) for i in range(procs)])
+        batched = {"value": sum(r[0] for r in bres) / max(r[1] for r in bres), "unit": "events/s", "cores": procs, "rows_per_event": 4096,
+                   "single_process_events_per_s": bres[0][0] / bres[0][1],
+                   "how": "one MockEvent carrying 4 096 rows in `inputs` through the oracle GraphServer: every model predicts (B, F) "
+                          "once, one vote over (B, M)"}
     return {
+        "reference_batched": batched,
         "value": total / slowest,
         "unit": "events/s",
         "cores": procs,
@@ -775,7 +813,7 @@ def main():
                                     "e2e_p50": float(np.percentile(lat_e2e, 50)), "e2e_p99": float(np.percentile(lat_e2e, 99)),
                                     "e2e_how": "wall clock of DevicePlan.run on 4096 pinned host rows (H2D + kernel + D2H + status), "
                                                "1000 samples after 100 warm-ups"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
                          "traffic": measured_traffic(name, B), "traffic_source": "from_profile: ncu --set full capture of this "
                          "kernel (profiles/traffic.json), scaled to this launch; not measured in this run",
                          "kernel": plan.kernel, "algorithmic_bytes_per_event": bpe,
@@ -991,7 +1029,7 @@ def main_ingest(args, rank, local_rank, world, emit=True):
                        "n_column_ops": len(iplan.out), "out_slots": plan.n_out},
             "p50_step_latency_us": {"batch": 4096, "p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                                     "how": "CUDA events around one columns_kernel launch, 300 samples"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
                          "traffic": measured_traffic(name, B), "kernel": "columns_kernel", "algorithmic_bytes_per_event": bpe,
                          "kernel_ms_per_launch": kms, "peak_source": peak_src},
             "gpu_launches": int(launches), "clocks": clocks,
@@ -1185,7 +1223,7 @@ def main_enrich(args, rank, local_rank, world, emit=True):
                        else f"table_lookup_kernel + {plan.kernel}"},
             "p50_step_latency_us": {"batch": 4096, "p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                                     "how": f"CUDA events around one launch ({top}), 300 samples"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
                          "traffic": None if fused else measured_traffic(name, B), "kernel": top,
                          "algorithmic_bytes_per_event": bpe, "kernel_ms_per_launch": kms, "peak_source": peak_src},
             "gpu_launches": int(launches), "clocks": clocks,
