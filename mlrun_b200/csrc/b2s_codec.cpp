@@ -567,7 +567,13 @@ Pool* get_pool(int threads) {
   pl = g_pool.load(std::memory_order_acquire);
   if (pl) return pl;
   static const bool hooked = [] {
-    pthread_atfork(nullptr, nullptr, [] { g_pool.store(nullptr, std::memory_order_release); });  // the child has no workers
+    // fork: the child has no workers, so it starts without a pool; the pool-creation lock is held across the fork so that the
+    // child never inherits it locked by a thread that does not exist there
+    pthread_atfork([] { g_pool_make.lock(); }, [] { g_pool_make.unlock(); },
+                   [] {
+                     g_pool.store(nullptr, std::memory_order_release);
+                     g_pool_make.unlock();
+                   });
     return true;
   }();
   (void)hooked;
