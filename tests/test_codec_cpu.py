@@ -365,3 +365,89 @@ def test_threaded_parser_serves_concurrent_callers_and_survives_fork():
 
 def _forked_parse(body, q):
     q.put(codec.parse_inputs(body)[0].shape)
+
+
+def test_structural_fuzz_of_whole_bodies_against_json_loads():
+    """seeded random V2 bodies -- random white space between every token, specials, exponents, 1 .. 12 000 rows -- and the same
+    bodies with one to three characters deleted / inserted / replaced anywhere: `decode_body` (the entry `run_json` uses)
+    accepts exactly the bodies json.loads accepts whose "inputs" is a numeric matrix, with the same float32 bits; everything
+    else is NotV2Matrix (valid JSON, not a matrix) or an error (invalid JSON), never a silent acceptance"""
+    import random
+
+    from mlrun_b200 import _native as nat
+
+    rnd = random.Random(77)
+    spaces = [" ", "", "", "\n", "\t", "  ", "\r\n"]
+
+    def num():
+        r = rnd.random()
+        if r < 0.3:
+            return str(rnd.randint(-1000, 1000))
+        if r < 0.8:
+            return repr(rnd.uniform(-100, 100))
+        if r < 0.85:
+            return rnd.choice(["NaN", "Infinity", "-Infinity", "null"])
+        return "%.3e" % rnd.uniform(-1e10, 1e10)
+
+    def matrix(rows, cols):
+        w = lambda: rnd.choice(spaces)  # noqa: E731
+        return "[" + w() + ("," + w()).join("[" + w() + ("," + w()).join(num() + w() for _ in range(cols)) + "]" + w() for _ in range(rows)) + "]"
+
+    def numeric(y):
+        return (isinstance(y, (int, float)) and not isinstance(y, bool)) or y is None
+
+    def is_matrix(v):
+        if not isinstance(v, list):
+            return False
+        if v and all(isinstance(x, list) for x in v):
+            return all(len(x) == len(v[0]) and all(numeric(y) for y in x) for x in v)
+        return all(numeric(y) for y in v)
+
+    counts = {"same": 0, "not_matrix": 0, "invalid": 0}
+    for it in range(1500):
+        rows, cols = rnd.choice([(1, 1), (2, 3), (5, 4), (40, 7), (7, 2)]) if it % 150 else (12000, 12)  # (the last: the pool's path)
+        body = '{"id": "x", "inputs":' + rnd.choice(spaces) + matrix(rows, cols) + ', "z": [1, {"a": "]"}]}'
+        if rnd.random() < 0.6:
+            chars = list(body)
+            for _ in range(rnd.randint(1, 3)):
+                i = rnd.randrange(len(chars))
+                op = rnd.random()
+                if op < 0.4:
+                    del chars[i]
+                elif op < 0.8:
+                    chars.insert(i, rnd.choice('[],"{}:.e-0 a'))
+                else:
+                    chars[i] = rnd.choice('[],"{}:.e-0 a')
+            body = "".join(chars)
+        try:
+            ref = json.loads(body)
+        except (json.JSONDecodeError, RecursionError):
+            ref = Ellipsis
+        try:
+            got, _rest = codec.decode_body(body.encode())
+            verdict = "ok"
+        except codec.NotV2Matrix:
+            verdict = "not_matrix"
+        except (nat.NativeError, json.JSONDecodeError):
+            verdict = "invalid"
+        if ref is Ellipsis:
+            assert verdict != "ok", body[:300]
+            counts["invalid"] += 1
+            continue
+        if body.count('"inputs"') != 1:
+            continue  # a corruption made a second member of that name: json.loads keeps the last, the codec reads the first
+        if isinstance(ref, dict) and "inputs" in ref and is_matrix(ref["inputs"]):
+            try:
+                with np.errstate(over="ignore"):
+                    want = np.asarray(ref["inputs"], dtype=np.float32)
+            except (OverflowError, ValueError):
+                continue
+            assert verdict == "ok", (verdict, body[:300])
+            want = want.reshape(-1, 1) if want.ndim == 1 else want
+            if want.size or got.size:
+                assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), body[:300]
+            counts["same"] += 1
+        else:
+            assert verdict != "ok", body[:300]
+            counts["not_matrix"] += 1
+    assert counts["same"] > 500 and counts["invalid"] > 300 and counts["not_matrix"] > 5, counts
