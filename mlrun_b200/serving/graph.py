@@ -307,7 +307,8 @@ class TaskStep(BaseStep):
             if self._error_call is None:
                 raise
             self._report(event, exc)
-            event.body = merge_result(self.result_path, event.body, self._divert(event, exc))
+            recovered = self._divert(event, exc)  # first: the handler may replace event.body, and the merge below reads it after
+            event.body = merge_result(self.result_path, event.body, recovered)
         return event
 
 

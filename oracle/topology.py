@@ -340,7 +340,8 @@ class TaskStep(BaseStep):
             if not self._on_error_handler:
                 raise exc
             self._log_error(event, exc)
-            event.body = _update_result_body(self.result_path, event.body, self._call_error_handler(event, exc))
+            outcome = self._call_error_handler(event, exc)  # states.py:592-597: the handler runs BEFORE event.body is read again
+            event.body = _update_result_body(self.result_path, event.body, outcome)
         return event
 
 

@@ -1876,6 +1876,44 @@ def steps_random_events(api):
     return out
 
 
+def flow_error_handler_paths(api):
+    """serving/states.py:592-597 -- a step that raises under a step-level error handler AND a result_path: the handler runs
+    first (it may replace event.body), the step's result_path merge then reads the body the handler left; same with an
+    input_path the body does not have, and with a handler that only mutates the body (found by tests/golden/diff_flow_graphs.py)"""
+
+    class Boom:
+        def do(self, x):
+            raise ValueError(f"boom on {type(x).__name__}")
+
+    class Replace:
+        def do_event(self, event):
+            event.body = {"handled": str(event.error), "origin": event.origin_state}
+            return event
+
+    class Mutate:
+        def do_event(self, event):
+            event.body["seen"] = sorted(event.error)
+            return event
+
+    ns = {"Boom": Boom, "Replace": Replace, "Mutate": Mutate}
+    out = {}
+    for handler in ("Replace", "Mutate"):
+        for result_path in (None, "res", "x.res"):
+            for input_path in (None, "x", "nope.deep"):
+                fn = api.new_function("f", kind="serving")
+                flow = fn.set_topology("flow", engine="sync")
+                kw = {k: v for k, v in (("result_path", result_path), ("input_path", input_path)) if v}
+                flow.to("Boom", name="s0", **kw).error_handler(name="catch", class_name=handler)
+                server = fn.to_mock_server(namespace=ns)
+                try:
+                    body = server.test(body={"x": {"y": 3}, "q": 2}, silent=True)
+                    text = json.dumps(_resp(body), sort_keys=True, default=lambda o: f"<{type(o).__name__}>")
+                    out[f"{handler}|{result_path}|{input_path}"] = text
+                except Exception as exc:  # noqa: BLE001
+                    out[f"{handler}|{result_path}|{input_path}"] = f"{type(exc).__name__}: {_first_line(exc)}"
+    return out
+
+
 def model_numpy_outputs(api):
     """serving/server.py:298-308 + serving/v2_serving.py:228-342 -- a model returning numpy values: fine for `server.test`
     (the body object comes back), a TypeError on the wire (`GraphServer.run` json-encodes strictly); plus odd requests to a
@@ -2483,7 +2521,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, steps_odd_values, steps_random_events, model_numpy_outputs, vote_odd_predictions, graph_serialisation, router_and_model_paths, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, flow_error_handler_paths, steps_odd_values, steps_random_events, model_numpy_outputs, vote_odd_predictions, graph_serialisation, router_and_model_paths, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
