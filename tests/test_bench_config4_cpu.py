@@ -9,10 +9,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = os.path.join(ROOT, "tests", "_config4_child.py")
 
 
+def _free_port_pair(shift=17):
+    """a port p with p and p + shift both free (the parents' rendezvous and the children's)"""
+    import socket
+
+    for p in range(29533, 29933, 7):
+        try:
+            for q in (p, p + shift):
+                with socket.socket() as sock:
+                    sock.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+                    sock.bind(("127.0.0.1", q))
+            return p
+        except OSError:
+            continue
+    return 29533
+
+
 def test_children_of_a_torchrun_job_form_their_own_group():
     env = dict(os.environ, B2S_BENCH_CONFIG4_CMD=json.dumps([CHILD]))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
-           "29533", os.path.join(ROOT, "tests", "_config4_parent.py")]
+           str(_free_port_pair()), os.path.join(ROOT, "tests", "_config4_parent.py")]
     done = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert done.returncode == 0, done.stderr[-2000:]
     row = json.loads([ln for ln in done.stdout.splitlines() if ln.startswith("ROW ")][-1][4:])
