@@ -22,15 +22,22 @@ class GraphError(Exception):
 
 
 def err_to_str(err):
-    if err is None:
+    """text of an exception and of its chain of causes (mlrun/errors.py:126-149): messages joined by ", caused by: ", an
+    exception without a message shown by its repr, a chain that loops back cut where it repeats, more than 32 000 characters
+    reduced to the first and last 16 000"""
+    if not err:
         return ""
     if isinstance(err, str):
         return err
-    out = []
-    while err is not None and len(out) < 10:
-        out.append(str(err))
+    chain, texts = [], []
+    while err and err not in chain:
+        chain.append(err)
+        texts.append(str(err) or repr(err))
         err = err.__cause__
-    return ", caused by: ".join(out)
+    text = ", caused by: ".join(texts)
+    if len(text) > 32_000:
+        text = text[:16_000] + "...truncated..." + text[-16_000:]
+    return text
 
 
 class _Log:

@@ -19,18 +19,22 @@ class MLRunInvalidArgumentError(ValueError):
 
 
 def err_to_str(err):
-    # mlrun/errors.py: chained causes joined by ", caused by: "
-    if err is None:
+    """text of an exception and of its chain of causes (mlrun/errors.py:126-149): messages joined by ", caused by: ", an
+    exception without a message shown by its repr, a chain that loops back cut where it repeats, more than 32 000 characters
+    reduced to the first and last 16 000"""
+    if not err:
         return ""
     if isinstance(err, str):
         return err
-    parts = []
-    seen = 0
-    while err is not None and seen < 10:
-        parts.append(str(err))
+    chain, texts = [], []
+    while err and err not in chain:
+        chain.append(err)
+        texts.append(str(err) or repr(err))
         err = err.__cause__
-        seen += 1
-    return ", caused by: ".join(parts)
+    text = ", caused by: ".join(texts)
+    if len(text) > 32_000:
+        text = text[:16_000] + "...truncated..." + text[-16_000:]
+    return text
 
 
 class _Logger:
