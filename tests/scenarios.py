@@ -1914,6 +1914,44 @@ def flow_error_handler_paths(api):
     return out
 
 
+def error_text_shapes(api):
+    """mlrun/errors.py:126-149 through serving/server.py:278-288 -- how a failing step's exception reads in the 400 response:
+    no message (the repr stands in), an empty message, a chain of causes, a cause chain that loops back, a message beyond
+    32 000 characters (cut to its two ends); found by tests/golden/diff_flow_with_routers.py"""
+
+    class Raise:
+        def __init__(self, how="bare", **kw):
+            self.how = how
+
+        def do(self, x):
+            if self.how == "bare":
+                raise NotImplementedError()
+            if self.how == "empty":
+                raise ValueError("")
+            if self.how == "chain":
+                try:
+                    try:
+                        raise KeyError("inner")
+                    except KeyError as inner:
+                        raise RuntimeError() from inner
+                except RuntimeError as middle:
+                    raise ValueError("outer") from middle
+            if self.how == "loop":
+                a, b = ValueError("a"), TypeError("b")
+                a.__cause__, b.__cause__ = b, a
+                raise a
+            raise ValueError("x" * 20000 + "MIDDLE" + "y" * 20000)
+
+    out = {}
+    for how in ("bare", "empty", "chain", "loop", "long"):
+        fn = api.new_function("f", kind="serving")
+        fn.set_topology("flow", engine="sync").to("Raise", name="s", how=how).respond()
+        resp = fn.to_mock_server(namespace={"Raise": Raise}).test(body={"a": 1}, silent=True)
+        text = resp.body if isinstance(resp.body, str) else resp.body.decode()
+        out[how] = {"status": resp.status_code, "length": len(text), "head": text[:80], "tail": text[-40:], "has_cut": "...truncated..." in text}
+    return out
+
+
 def model_numpy_outputs(api):
     """serving/server.py:298-308 + serving/v2_serving.py:228-342 -- a model returning numpy values: fine for `server.test`
     (the body object comes back), a TypeError on the wire (`GraphServer.run` json-encodes strictly); plus odd requests to a
@@ -2521,7 +2559,7 @@ SCENARIOS = [
     ensemble_metadata, ensemble_weight_sum_below_one, ensemble_vote_type_inference, router_mock_direct,
     echo_plumbing, tracking, parallel_run, flow_basic_sync, flow_handlers_sync, flow_on_error_sync,
     flow_content_type, flow_model_no_router, flow_multi_function_sync, flow_path_control_sync, step_to_dict,
-    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, flow_error_handler_paths, steps_odd_values, steps_random_events, model_numpy_outputs, vote_odd_predictions, graph_serialisation, router_and_model_paths, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
+    route_cap, flow_add_model, module_load, infer_dict_ops, pickle_model_from_path, model_async_load, class_args_protocol, model_hooks, custom_router, server_run_details, tracking_sampling_batching, graph_validation_errors, event_envelope, set_tracking_params, add_model_args, parallel_run_details, ensemble_odd_requests, flow_odd_cases, flow_error_handler_paths, error_text_shapes, steps_odd_values, steps_random_events, model_numpy_outputs, vote_odd_predictions, graph_serialisation, router_and_model_paths, flow_async_basic, flow_async_misc, merger_logic, online_service_logic, enrichment_routers, no_merger, merge_flows, steps_dict_events, steps_pandas_engine, steps_validate_args, validator_events, validator_pandas, set_event_metadata_logic, vote_math,
     flow3_linear_events, flow3_ensemble_events, tree_ensemble_batch,
 ]
 
