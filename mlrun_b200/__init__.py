@@ -15,4 +15,4 @@ loudly when `libb200serve.so` or a GPU is missing (there is no CPU fallback on t
 __version__ = "0.1.0"
 
 from . import feature_store, serving  # noqa: E402,F401
-from .serving import new_function  # noqa: E402,F401
+from .serving import ServingRuntime, new_function  # noqa: E402,F401

@@ -8,7 +8,7 @@ from .device_models import (  # noqa: F401
     XGBoostModelServer,
 )
 from .events import MockEvent, MockTrigger, Response  # noqa: F401
-from .function import ServingFunction, new_function  # noqa: F401
+from .function import ServingFunction, ServingRuntime, new_function  # noqa: F401
 from .graph import (  # noqa: F401
     ErrorStep,
     FlowStep,

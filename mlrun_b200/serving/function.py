@@ -27,7 +27,7 @@ class ServingSpec:
         self.command = ""  # path of the function's own code file: its classes / handlers are step candidates
 
 
-class ServingFunction:
+class ServingRuntime:
     kind = "serving"
 
     def __init__(self, name="", project="", tag=""):
@@ -154,6 +154,9 @@ def _code_module(command, workdir=None):
 def new_function(name="", project="", tag="", kind="", command="", **kwargs):
     if kind != "serving":
         raise MLRunInvalidArgumentError("mlrun_b200 implements kind='serving' functions only")
-    fn = ServingFunction(name=name, project=project, tag=tag)
+    fn = ServingRuntime(name=name, project=project, tag=tag)
     fn.spec.command = command or ""
     return fn
+
+
+ServingFunction = ServingRuntime  # the name this class had before it took the reference's (mlrun.runtimes.ServingRuntime)

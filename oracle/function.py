@@ -28,7 +28,7 @@ class _ServingSpec:
         self.function_refs = {}
 
 
-class ServingFunction:
+class ServingRuntime:
     kind = "serving"
 
     def __init__(self, name="", project="", tag=""):
@@ -180,6 +180,9 @@ def new_function(name="", project="", tag="", kind="", command="", **kwargs):
     """mlrun.run.new_function (run.py:425) for kind="serving" only; `command` = the function's code file"""
     if kind != "serving":
         raise MLRunInvalidArgumentError("the oracle only restates kind='serving' functions")
-    fn = ServingFunction(name=name, project=project, tag=tag)
+    fn = ServingRuntime(name=name, project=project, tag=tag)
     fn.spec.command = command or ""
     return fn
+
+
+ServingFunction = ServingRuntime  # the name this class had before it took the reference's (mlrun.runtimes.ServingRuntime)
