@@ -18,7 +18,7 @@ def main():
         name = os.path.splitext(os.path.basename(path))[0]
         t0 = time.time()
         done = subprocess.run([sys.executable, "-m", f"tests.golden.{name}"], cwd=ROOT, capture_output=True, text=True)
-        verdict = [ln for ln in done.stdout.splitlines() if ln.startswith(("identical", "DIFF", "BUILD DIFF", "the batched", "ingest_columns", "vote math", "get_in"))]
+        verdict = [ln for ln in done.stdout.splitlines() if ln.startswith(("identical", "DIFF", "BUILD DIFF", "the batched", "ingest_columns", "vote math", "get_in", "FeatureSet.ingest"))]
         print(f"{name:28s} rc={done.returncode} {time.time() - t0:5.1f}s  {' | '.join(verdict)[:200]}")
         if done.returncode != 0:
             failed.append(name)
