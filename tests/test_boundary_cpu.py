@@ -180,3 +180,18 @@ def test_array_addresses_handed_to_the_library():
     for a in cases:
         assert nat.ptr(a) == a.ctypes.data, (a.shape, a.flags)
     assert nat.ptr(backed) == C.addressof(raw) and nat.ptr(status) == C.addressof(raw) + 32768
+
+
+def test_reference_import_paths_resolve():
+    """existing code imports the serving classes by the reference's module paths; they resolve to this package's classes"""
+    import mlrun_b200 as mlrun
+    from mlrun_b200.serving.routers import ModelRouter, ParallelRun, VotingEnsemble
+    from mlrun_b200.serving.server import GraphContext, GraphServer, MockEvent, create_graph_server
+    from mlrun_b200.serving.states import ErrorStep, FlowStep, QueueStep, RouterStep, TaskStep
+    from mlrun_b200.serving.v2_serving import V2ModelServer
+
+    assert mlrun.serving.VotingEnsemble is VotingEnsemble and mlrun.serving.V2ModelServer is V2ModelServer
+    assert mlrun.serving.routers.ModelRouter is ModelRouter and mlrun.serving.server.MockEvent is MockEvent
+    assert mlrun.ServingRuntime is mlrun.serving.ServingRuntime and type(mlrun.new_function("f", kind="serving")) is mlrun.ServingRuntime
+    assert all(isinstance(c, type) for c in (ParallelRun, GraphContext, GraphServer, ErrorStep, FlowStep, QueueStep, RouterStep, TaskStep))
+    assert callable(create_graph_server)
