@@ -103,6 +103,11 @@ def _lookup(name, namespaces):
 
 def _import(path):
     path = _REF_PATHS.get(path, path)
+    if path.startswith("mlrun."):  # any other class of the reference's serving / feature-store packages, by its own path
+        try:
+            return _import("mlrun_b200." + path[len("mlrun."):])
+        except ImportError:
+            pass
     module, _, attr = path.rpartition(".")
     if not module:
         raise ImportError(f"cannot import {path!r}")
